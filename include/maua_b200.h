@@ -1,0 +1,159 @@
+/*
+ * maua_b200.h -- C ABI of libmaua_b200.so, the Blackwell (sm_100a) replacement for the
+ * audio-reactive StyleGAN render path of maua-maua-maua/maua.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes and a raw CUDA stream
+ * handle, returns 0 on success or a negative MB_E* code (message via mb_last_error()).
+ * No C++ exception crosses the boundary, nothing here allocates inside a forward call:
+ * the caller (PyTorch in the reference) owns every tensor including outputs and the
+ * workspace, the library owns only the opaque `mb_net` handle (re-packed weights).
+ *
+ * Each declaration cites the reference interface it replaces (paths relative to the
+ * reference checkout, maua @ d968fd9).  `maua/GAN/nv` is an un-vendored submodule
+ * (maua-maua-maua/nvGAN @ 7809c05, fork of NVlabs/stylegan3); for those the upstream
+ * file is named.
+ */
+#ifndef MAUA_B200_H
+#define MAUA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_OK 0
+#define MB_EINVAL (-1)   /* bad argument / shape / name */
+#define MB_ECUDA (-2)    /* CUDA runtime or driver error */
+#define MB_ESTATE (-3)   /* call order (forward before finalize, ...) */
+#define MB_ENOMEM (-4)   /* workspace too small */
+#define MB_ENODEV (-5)   /* no sm_100 device */
+
+typedef void* mb_stream; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------- */
+
+/* Select the device and check it is compute capability 10.x.  No CPU fallback exists. */
+int mb_init(int device);
+/* Thread-local message of the last failing call on this thread. */
+const char* mb_last_error(void);
+/* ABI version (bumped on any signature change). */
+int mb_abi_version(void);
+
+/* ---- StyleGAN3 synthesis network ---------------------------------------------------
+ * Replaces `stylegan3.SynthesisNetwork(w_dim=512, img_resolution=1024, img_channels=3)`
+ * as constructed at maua/GAN/wrappers/stylegan3.py:33 and called at :60
+ * (`self.G_synth.forward(latents)`); upstream training/networks_stylegan3.py
+ * SynthesisNetwork / SynthesisInput / SynthesisLayer.
+ */
+typedef struct mb_sg3_cfg {
+    int32_t w_dim;            /* 512 */
+    int32_t img_resolution;   /* 1024 */
+    int32_t img_channels;     /* 3 */
+    int32_t channel_base;     /* 32768 (T) / 65536 (R) */
+    int32_t channel_max;      /* 512 (T) / 1024 (R) */
+    int32_t num_layers;       /* 14 */
+    int32_t num_critical;     /* 2 */
+    int32_t conv_kernel;      /* 3 (T) / 1 (R) */
+    int32_t filter_size;      /* 6 */
+    int32_t lrelu_upsampling; /* 2 */
+    int32_t use_radial_filters; /* 0 (T) / 1 (R) */
+    int32_t margin_size;      /* 10 */
+    double first_cutoff;      /* 2 */
+    double first_stopband;    /* 2**2.1 */
+    double last_stopband_rel; /* 2**0.3 */
+    double output_scale;      /* 0.25 */
+    double conv_clamp;        /* 256 */
+} mb_sg3_cfg;
+
+/* Per-layer geometry as derived by upstream SynthesisNetwork.__init__ (index 0..num_layers,
+ * the last entry is the ToRGB layer).  Pure host arithmetic: usable without a GPU. */
+typedef struct mb_sg3_layer {
+    int32_t idx, is_torgb, is_critically_sampled, use_fp16;
+    int32_t in_channels, out_channels;
+    int32_t in_size, out_size;
+    int32_t in_sampling_rate, out_sampling_rate, tmp_sampling_rate;
+    int32_t conv_kernel, up, down, up_taps, down_taps, down_radial;
+    int32_t pad_lo, pad_hi;
+    double in_cutoff, out_cutoff, in_half_width, out_half_width;
+    char name[32];            /* "L{idx}_{out_size}_{out_channels}" */
+} mb_sg3_layer;
+
+typedef struct mb_net mb_net;
+
+void mb_sg3_default_cfg(mb_sg3_cfg* cfg, int config_r /*0 = StyleGAN3-T, 1 = StyleGAN3-R*/);
+/* Host-only geometry query (no device needed). layers must hold cfg->num_layers+1 entries. */
+int mb_sg3_geometry(const mb_sg3_cfg* cfg, mb_sg3_layer* layers, int32_t* input_channels,
+                    int32_t* input_size, double* input_sampling_rate, double* input_bandwidth);
+
+int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out);
+void mb_net_destroy(mb_net* net);
+
+/* Upload one tensor of the generator state dict.  `name` is the upstream state-dict key
+ * ("input.freqs", "input.phases", "input.weight", "input.affine.weight", "input.affine.bias",
+ * "input.transform", "L3_52_512.weight", ".bias", ".affine.weight", ".affine.bias",
+ * ".magnitude_ema", ".up_filter", ".down_filter").  `data` is a DEVICE pointer to contiguous
+ * float32; the library copies / re-packs it (fp16 K-major tiles for the tensor-core path) on
+ * `stream`.  Replaces `load_state_dict` / parameter access of the torch module
+ * (maua/GAN/wrappers/stylegan3.py:35,56-59). */
+int mb_net_set_param(mb_net* net, const char* name, const float* data, const int64_t* shape,
+                     int ndim, mb_stream stream);
+/* Derive packed operands (pre-normalised fp16 weights, squared-weight tables). Call after the
+ * last set_param and again after any later set_param. */
+int mb_net_finalize(mb_net* net, mb_stream stream);
+
+size_t mb_net_workspace_bytes(const mb_net* net, int batch);
+
+#define MB_OUT_F32_NCHW 0 /* float32 [B,3,H,W], the synthesizer's raw output (~[-1,1]) */
+#define MB_OUT_U8_NHWC 2  /* uint8 [B,H,W,3] = round(clamp((x+1)/2,0,1)*255): the
+                             tensor2bytes() wire format of maua/ops/io.py:47-70 */
+
+/* One synthesis forward for `batch` frames.
+ *   ws        device float32 [batch, num_ws, w_dim]   (W+ latents, stylegan3.py:51 `latents`)
+ *   transform device float32 [3,3] or NULL            (G_synth.input.transform, stylegan3.py:59)
+ *   out       device buffer of out_fmt
+ *   workspace device buffer of >= mb_net_workspace_bytes(net, batch) bytes, 1024-aligned
+ * Enqueues on `stream` and returns; no allocation, no host sync. */
+int mb_net_forward(mb_net* net, const float* ws, const float* transform, int batch, void* out,
+                   int out_fmt, void* workspace, size_t workspace_bytes, mb_stream stream);
+
+/* Debug / parity aid: copy the activation a layer produced during the LAST forward into
+ * `out` as float32 [B,C,H,W] (undoing the style pre-multiplication is the caller's business:
+ * what is stored is x * style_{next}).  idx = -1 is the SynthesisInput output. */
+int mb_net_read_activation(mb_net* net, int idx, int batch, float* out, mb_stream stream);
+/* Number of kernels the last forward launched (for bench.py's gpu_launches). */
+int mb_net_last_launch_count(const mb_net* net);
+/* 0 = tcgen05 tensor-core conv (product path), 1 = plain CUDA-core conv (bisecting aid for the
+ * parity tests; never used by the host facade). */
+int mb_net_set_conv_impl(mb_net* net, int impl);
+/* Test / tuning knobs: "conv_impl" (0|1), "conv_tile_w" (64|32), "flrelu_impl" (0 auto | 1 generic),
+ * "debug_stop" (stop the forward after layer N; -1 = after the input layer; default: run all). */
+int mb_net_set_option(mb_net* net, const char* key, int value);
+/* Shape [C,H,W] of the activation mb_net_read_activation would return. */
+int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h, int32_t* w);
+
+/* ---- op-level entry points (parity tests call the same kernels the network uses) ---- */
+
+/* modulated_conv2d, upstream networks_stylegan3.py modulated_conv2d (grouped-conv
+ * formulation; in-tree twin maua/GAN/wrappers/inference/ops.py:146-186).
+ *   x [B,Cin,H,W] f32, w [Cout,Cin,k,k] f32, s [B,Cin] f32 -> y [B,Cout,H+k-1,W+k-1] f32
+ * padding = k-1, demodulate as given, input_gain scalar.  All device pointers. */
+int mb_modulated_conv2d(const float* x, const float* w, const float* s, float* y, int B, int Cin,
+                        int Cout, int H, int W, int k, int demodulate, float input_gain,
+                        int impl, mb_stream stream);
+
+/* filtered_lrelu, upstream torch_utils/ops/filtered_lrelu.py (reference semantics
+ * _filtered_lrelu_ref): bias -> zero-insert x`up` -> FIR fu (gain up^2) with padding
+ * [px0,px1,py0,py1] -> leaky-relu(slope)*gain -> clamp -> FIR fd -> decimate x`down`.
+ *   x [B,C,H,W] f32, fu [up_taps] (separable) or NULL, fd [down_taps] separable or
+ *   [down_taps,down_taps] when fd_2d, b [C] or NULL -> y [B,C,Ho,Wo] f32 */
+int mb_filtered_lrelu(const float* x, const float* fu, const float* fd, const float* b, float* y,
+                      int B, int C, int H, int W, int up, int down, int up_taps, int down_taps,
+                      int fd_2d, int px0, int px1, int py0, int py1, float gain, float slope,
+                      float clamp, mb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAUA_B200_H */

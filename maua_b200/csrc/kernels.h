@@ -1,0 +1,106 @@
+// Internal launch interfaces between the translation units of libmaua_b200.
+//
+// Device activation format ("planar-h"): fp16 [B][C][H][Wp], Wp = W rounded up to 8 elements so
+// every row starts 16-byte aligned (TMA global-stride rule); only [0,W) of a row is meaningful.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace mb {
+
+static inline int pitch8(int w) { return (w + 7) / 8 * 8; }
+
+// ---- conv_tc.cu ------------------------------------------------------------------------
+struct ConvTcArgs {
+    const __half* x;    // [B][Cin][Hin][Wp_in], already multiplied by the style
+    const __half* wpk;  // packed weights [round_up(Cout,128)][k*k*nCC*64], see pack_weights
+    const float* d;     // [B][Cout] demodulation coefficients or nullptr
+    __half* y;          // [B][Cout][Hin+k-1][Wp_out]
+    int B, Cin, Cout, Hin, Win, Wp_in, Wp_out, ksz;
+    int tile_w;         // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int num_sms;
+};
+int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);
+int conv_tc_smem_bytes(int tw);
+
+// ---- sg3_misc.cu -----------------------------------------------------------------------
+// K index of the packed weight matrix: (((kw*nCC + cc)*k + kh)*64 + c_local)
+size_t packed_weight_elems(int Cout, int Cin, int ksz);
+// W f32 [Cout][Cin][k][k] -> optional per-cout pre-normalisation (demodulate) -> fp16 packed,
+// wsqT f32 [Cin][Cout] = sum_k Wn^2 (for the demodulation coefficients).
+int pack_weights_launch(const float* w, __half* wpk, float* wsqT, int Cout, int Cin, int ksz, int prenorm,
+                        cudaStream_t stream);
+// Plain CUDA-core direct convolution on the same operands (bisecting aid, see mb_net_set_conv_impl).
+int conv_simt_launch(const ConvTcArgs& p, cudaStream_t stream);
+
+struct StyleLayerDesc {
+    const float* affine_w;  // [Cin][w_dim]
+    const float* affine_b;  // [Cin]
+    const float* wsqT;      // [Cin][Cout] or nullptr (no demodulation)
+    const float* magnitude_ema;  // scalar on device
+    float* s_out;           // [B][Cin]  normalised style * input_gain
+    float* d_out;           // [B][Cout] or nullptr
+    int Cin, Cout, ws_index, demodulate;
+    float style_scale;      // torgb: 1/sqrt(Cin*k*k), else 1
+};
+constexpr int kMaxLayers = 24;
+struct StylesArgs {
+    StyleLayerDesc L[kMaxLayers];
+    int num_layers, B, num_ws, w_dim;
+    const float* ws;  // [B][num_ws][w_dim]
+};
+int styles_launch(const StylesArgs& a, cudaStream_t stream);
+
+struct InputArgs {
+    const float* ws;          // [B][num_ws][w_dim], uses ws[:,0]
+    const float* affine_w;    // [4][w_dim]
+    const float* affine_b;    // [4]
+    const float* transform;   // [3][3]
+    const float* freqs;       // [C][2]
+    const float* phases;      // [C]
+    const float* weightT;     // [C(j)][C(c)] = weight[c][j] transposed
+    const float* style;       // [B][C] style of layer 0 (normalised * input_gain)
+    float* scratch;           // [B][C][4]: fx, fy, phase, amplitude
+    __half* out;              // [B][C][size][Wp]
+    int B, num_ws, w_dim, C, size, Wp;
+    float sampling_rate, bandwidth;
+};
+int sg3_input_launch(const InputArgs& a, cudaStream_t stream);
+
+struct ToRgbArgs {
+    const __half* x;     // [B][Cin][H][Wp] (already * style of the torgb layer)
+    const float* w;      // [Cout<=4][Cin] raw weights (no demodulation)
+    const float* bias;   // [Cout]
+    void* out;
+    int B, Cin, Cout, H, W, Wp, out_fmt;
+    float clamp, output_scale;
+};
+int torgb_out_launch(const ToRgbArgs& a, cudaStream_t stream);
+
+// x f32 [B][C][H][W] * s[b][c] * gain -> fp16 planar-h (s may be nullptr)
+int modulate_to_half_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Wp,
+                            cudaStream_t stream);
+// fp16 planar-h -> f32 [B][C][H][W]
+int half_to_float_launch(const __half* x, float* out, int B, int C, int H, int W, int Wp, cudaStream_t stream);
+// op-level helper: s -> normalised s (if demodulate), d[b][o]
+int style_demod_launch(const float* s, const float* wsqT, float* s_out, float* d_out, int B, int Cin, int Cout,
+                       int demodulate, float input_gain, cudaStream_t stream);
+
+// ---- flrelu.cu -------------------------------------------------------------------------
+struct FlreluArgs {
+    const __half* x;     // [B][C][Hin][Wp_in]
+    const float* bias;   // [C] or nullptr
+    const float* scale;  // [B][C] multiplier applied to the result (next layer's style) or nullptr
+    __half* y;           // [B][C][Hout][Wp_out]
+    float fu[32];        // HOST copy of the up filter taps (without the up^2 gain); [1]={1} when up == 1
+    float fd[144];       // HOST copy: [down_taps] or [down_taps^2] (row-major) when fd_2d
+    int B, C, Hin, Win, Wp_in, Hout, Wout, Wp_out;
+    int up, down, up_taps, down_taps, fd_2d;
+    int px0, py0;        // leading padding of the zero-inserted signal (may be negative = crop)
+    float gain, slope, clamp;
+    int num_sms;
+};
+int flrelu_launch(const FlreluArgs& a, cudaStream_t stream);
+
+}  // namespace mb

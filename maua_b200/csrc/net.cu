@@ -1,0 +1,705 @@
+// libmaua_b200 C ABI: library init, the StyleGAN3 synthesis-network handle and its per-layer
+// pipeline (styles -> input -> [modulated conv (tcgen05) -> filtered_lrelu] x N -> ToRGB/out),
+// plus op-level entry points that run the very same kernels for the parity tests.
+// Reference: maua/GAN/wrappers/stylegan3.py:33,51-60 (ctor + forward call sites); upstream
+// training/networks_stylegan3.py SynthesisNetwork.__init__/forward for geometry and data flow.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb {
+
+static thread_local std::string g_err;
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int g_device = -1;
+static int g_num_sms = 148;
+
+int flrelu_generic_launch_public(const FlreluArgs& a, cudaStream_t stream);
+
+}  // namespace mb
+
+using namespace mb;
+
+struct Param {
+    float* dev = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;
+    bool set = false;
+};
+
+struct LayerState {
+    mb_sg3_layer g;
+    Param weight, bias, affine_w, affine_b, magnitude_ema, up_filter, down_filter;
+    __half* wpk = nullptr;
+    float* wsqT = nullptr;
+    std::vector<float> fu, fd;  // host copies
+};
+
+struct mb_net {
+    mb_sg3_cfg cfg;
+    std::vector<LayerState> layers;  // num_layers + 1
+    int in_channels = 0, in_size = 0;
+    double in_sr = 0, in_bw = 0;
+    Param in_freqs, in_phases, in_weight, in_affine_w, in_affine_b, in_transform;
+    float* in_weightT = nullptr;
+    std::map<std::string, Param*> by_name;
+    bool finalized = false;
+    int conv_impl = 0;
+    int conv_tile_w = 64;
+    int flrelu_impl = 0;  // 0 = auto (register-blocked where supported), 1 = generic everywhere
+    int debug_stop = 1 << 30;
+    int last_launches = 0;
+    // layout of the last forward (for read_activation)
+    void* last_ws = nullptr;
+    int last_batch = 0;
+    const __half* last_act = nullptr;
+    int last_act_c = 0, last_act_h = 0, last_act_w = 0;
+};
+
+// ---------------------------------------------------------------------------------------
+// geometry (host only)
+// ---------------------------------------------------------------------------------------
+extern "C" void mb_sg3_default_cfg(mb_sg3_cfg* c, int config_r) {
+    memset(c, 0, sizeof(*c));
+    c->w_dim = 512;
+    c->img_resolution = 1024;
+    c->img_channels = 3;
+    c->channel_base = config_r ? 65536 : 32768;
+    c->channel_max = config_r ? 1024 : 512;
+    c->num_layers = 14;
+    c->num_critical = 2;
+    c->conv_kernel = config_r ? 1 : 3;
+    c->filter_size = 6;
+    c->lrelu_upsampling = 2;
+    c->use_radial_filters = config_r ? 1 : 0;
+    c->margin_size = 10;
+    c->first_cutoff = 2.0;
+    c->first_stopband = pow(2.0, 2.1);
+    c->last_stopband_rel = pow(2.0, 0.3);
+    c->output_scale = 0.25;
+    c->conv_clamp = 256.0;
+}
+
+extern "C" int mb_sg3_geometry(const mb_sg3_cfg* c, mb_sg3_layer* L, int32_t* input_channels, int32_t* input_size,
+                               double* input_sampling_rate, double* input_bandwidth) {
+    MB_REQUIRE(c && L, "mb_sg3_geometry: null argument");
+    const int N = c->num_layers;
+    MB_REQUIRE(N >= 3 && N + 1 <= kMaxLayers && c->num_critical < N, "mb_sg3_geometry: num_layers %d unsupported", N);
+    MB_REQUIRE(c->conv_kernel == 1 || c->conv_kernel == 3, "mb_sg3_geometry: conv_kernel must be 1 or 3");
+    const double res = c->img_resolution;
+    const double last_cutoff = res / 2;
+    const double last_stopband = last_cutoff * c->last_stopband_rel;
+    std::vector<double> cut(N + 1), stop(N + 1), sr(N + 1), hw(N + 1), size(N + 1), ch(N + 1);
+    for (int i = 0; i <= N; ++i) {
+        double e = static_cast<double>(i) / (N - c->num_critical);
+        if (e > 1) e = 1;
+        cut[i] = c->first_cutoff * pow(last_cutoff / c->first_cutoff, e);
+        stop[i] = c->first_stopband * pow(last_stopband / c->first_stopband, e);
+        double m = stop[i] * 2 < res ? stop[i] * 2 : res;
+        sr[i] = exp2(ceil(log2(m)));
+        hw[i] = (stop[i] > sr[i] / 2 ? stop[i] : sr[i] / 2) - cut[i];
+        size[i] = sr[i] + c->margin_size * 2;
+        double chv = (c->channel_base / 2.0) / cut[i];
+        if (chv > c->channel_max) chv = c->channel_max;
+        ch[i] = nearbyint(chv);
+    }
+    size[N] = res;
+    size[N - 1] = res;
+    ch[N] = c->img_channels;
+    for (int idx = 0; idx <= N; ++idx) {
+        const int prev = idx > 0 ? idx - 1 : 0;
+        mb_sg3_layer& g = L[idx];
+        memset(&g, 0, sizeof(g));
+        g.idx = idx;
+        g.is_torgb = idx == N;
+        g.is_critically_sampled = idx >= N - c->num_critical;
+        g.use_fp16 = sr[idx] * 16 > res;
+        g.in_channels = static_cast<int>(ch[prev]);
+        g.out_channels = static_cast<int>(ch[idx]);
+        g.in_size = static_cast<int>(size[prev]);
+        g.out_size = static_cast<int>(size[idx]);
+        g.in_sampling_rate = static_cast<int>(sr[prev]);
+        g.out_sampling_rate = static_cast<int>(sr[idx]);
+        const int mx = g.in_sampling_rate > g.out_sampling_rate ? g.in_sampling_rate : g.out_sampling_rate;
+        g.tmp_sampling_rate = mx * (g.is_torgb ? 1 : c->lrelu_upsampling);
+        g.conv_kernel = g.is_torgb ? 1 : c->conv_kernel;
+        g.up = static_cast<int>(nearbyint(static_cast<double>(g.tmp_sampling_rate) / g.in_sampling_rate));
+        g.down = static_cast<int>(nearbyint(static_cast<double>(g.tmp_sampling_rate) / g.out_sampling_rate));
+        g.up_taps = (g.up > 1 && !g.is_torgb) ? c->filter_size * g.up : 1;
+        g.down_taps = (g.down > 1 && !g.is_torgb) ? c->filter_size * g.down : 1;
+        g.down_radial = c->use_radial_filters && !g.is_critically_sampled;
+        int pad_total = (g.out_size - 1) * g.down + 1;
+        pad_total -= (g.in_size + g.conv_kernel - 1) * g.up;
+        pad_total += g.up_taps + g.down_taps - 2;
+        // python floor division
+        int num = pad_total + g.up;
+        int lo = num / 2;
+        if ((num % 2 != 0) && (num < 0)) --lo;
+        g.pad_lo = lo;
+        g.pad_hi = pad_total - lo;
+        g.in_cutoff = cut[prev];
+        g.out_cutoff = cut[idx];
+        g.in_half_width = hw[prev];
+        g.out_half_width = hw[idx];
+        snprintf(g.name, sizeof(g.name), "L%d_%d_%d", idx, g.out_size, g.out_channels);
+    }
+    if (input_channels) *input_channels = static_cast<int>(ch[0]);
+    if (input_size) *input_size = static_cast<int>(size[0]);
+    if (input_sampling_rate) *input_sampling_rate = sr[0];
+    if (input_bandwidth) *input_bandwidth = cut[0];
+    return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// library
+// ---------------------------------------------------------------------------------------
+extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
+extern "C" int mb_abi_version(void) { return 1; }
+
+extern "C" int mb_init(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error("mb_init: no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return MB_ENODEV;
+    }
+    MB_REQUIRE(device >= 0 && device < n, "mb_init: device %d out of range (%d devices)", device, n);
+    cudaDeviceProp prop;
+    MB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("mb_init: device %d is sm_%d%d; libmaua_b200 is built for sm_100a only", device, prop.major, prop.minor);
+        return MB_ENODEV;
+    }
+    MB_CUDA(cudaSetDevice(device));
+    g_device = device;
+    g_num_sms = prop.multiProcessorCount;
+    return MB_OK;
+}
+
+static int alloc_param(Param& p, std::initializer_list<int64_t> shape) {
+    p.shape.assign(shape.begin(), shape.end());
+    p.numel = 1;
+    for (int64_t s : p.shape) p.numel *= static_cast<size_t>(s);
+    MB_CUDA(cudaMalloc(&p.dev, sizeof(float) * (p.numel ? p.numel : 1)));
+    return MB_OK;
+}
+
+extern "C" int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out) {
+    MB_REQUIRE(cfg && out, "mb_sg3_create: null argument");
+    if (g_device < 0) {
+        int r = mb_init(0);
+        if (r != MB_OK) return r;
+    }
+    mb_net* net = new mb_net();
+    net->cfg = *cfg;
+    std::vector<mb_sg3_layer> geo(cfg->num_layers + 1);
+    int r = mb_sg3_geometry(cfg, geo.data(), &net->in_channels, &net->in_size, &net->in_sr, &net->in_bw);
+    if (r != MB_OK) {
+        delete net;
+        return r;
+    }
+    const int wd = cfg->w_dim;
+    const int C0 = net->in_channels;
+#define TRY(x)            \
+    do {                  \
+        int _r = (x);     \
+        if (_r != MB_OK) {\
+            mb_net_destroy(net); \
+            return _r;    \
+        }                 \
+    } while (0)
+    TRY(alloc_param(net->in_freqs, {C0, 2}));
+    TRY(alloc_param(net->in_phases, {C0}));
+    TRY(alloc_param(net->in_weight, {C0, C0}));
+    TRY(alloc_param(net->in_affine_w, {4, wd}));
+    TRY(alloc_param(net->in_affine_b, {4}));
+    TRY(alloc_param(net->in_transform, {3, 3}));
+    if (cudaMalloc(&net->in_weightT, sizeof(float) * C0 * C0) != cudaSuccess) {
+        set_error("cudaMalloc failed");
+        mb_net_destroy(net);
+        return MB_ECUDA;
+    }
+    net->by_name["input.freqs"] = &net->in_freqs;
+    net->by_name["input.phases"] = &net->in_phases;
+    net->by_name["input.weight"] = &net->in_weight;
+    net->by_name["input.affine.weight"] = &net->in_affine_w;
+    net->by_name["input.affine.bias"] = &net->in_affine_b;
+    net->by_name["input.transform"] = &net->in_transform;
+    {
+        const float eye[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        cudaMemcpy(net->in_transform.dev, eye, sizeof(eye), cudaMemcpyHostToDevice);
+        net->in_transform.set = true;
+    }
+    net->layers.resize(geo.size());
+    for (size_t i = 0; i < geo.size(); ++i) {
+        LayerState& L = net->layers[i];
+        L.g = geo[i];
+        const int k = L.g.conv_kernel;
+        TRY(alloc_param(L.weight, {L.g.out_channels, L.g.in_channels, k, k}));
+        TRY(alloc_param(L.bias, {L.g.out_channels}));
+        TRY(alloc_param(L.affine_w, {L.g.in_channels, wd}));
+        TRY(alloc_param(L.affine_b, {L.g.in_channels}));
+        TRY(alloc_param(L.magnitude_ema, {}));
+        {
+            const float one = 1.0f;
+            cudaMemcpy(L.magnitude_ema.dev, &one, sizeof(one), cudaMemcpyHostToDevice);
+            L.magnitude_ema.set = true;
+        }
+        if (L.g.up_taps > 1) TRY(alloc_param(L.up_filter, {L.g.up_taps}));
+        if (L.g.down_taps > 1) {
+            if (L.g.down_radial)
+                TRY(alloc_param(L.down_filter, {L.g.down_taps, L.g.down_taps}));
+            else
+                TRY(alloc_param(L.down_filter, {L.g.down_taps}));
+        }
+        const std::string n = L.g.name;
+        net->by_name[n + ".weight"] = &L.weight;
+        net->by_name[n + ".bias"] = &L.bias;
+        net->by_name[n + ".affine.weight"] = &L.affine_w;
+        net->by_name[n + ".affine.bias"] = &L.affine_b;
+        net->by_name[n + ".magnitude_ema"] = &L.magnitude_ema;
+        if (L.up_filter.dev) net->by_name[n + ".up_filter"] = &L.up_filter;
+        if (L.down_filter.dev) net->by_name[n + ".down_filter"] = &L.down_filter;
+        if (!L.g.is_torgb) {
+            const size_t ne = packed_weight_elems(L.g.out_channels, L.g.in_channels, k);
+            if (cudaMalloc(&L.wpk, ne * sizeof(__half)) != cudaSuccess ||
+                cudaMalloc(&L.wsqT, sizeof(float) * L.g.in_channels * L.g.out_channels) != cudaSuccess) {
+                set_error("cudaMalloc failed for packed weights of %s", L.g.name);
+                mb_net_destroy(net);
+                return MB_ECUDA;
+            }
+        }
+    }
+#undef TRY
+    if (const char* e = getenv("MB_CONV_TILE_W")) net->conv_tile_w = atoi(e) == 32 ? 32 : 64;
+    if (const char* e = getenv("MB_FLRELU_IMPL")) net->flrelu_impl = atoi(e);
+    *out = net;
+    return MB_OK;
+}
+
+extern "C" void mb_net_destroy(mb_net* net) {
+    if (!net) return;
+    for (auto& kv : net->by_name)
+        if (kv.second->dev) cudaFree(kv.second->dev);
+    for (auto& L : net->layers) {
+        if (L.wpk) cudaFree(L.wpk);
+        if (L.wsqT) cudaFree(L.wsqT);
+    }
+    if (net->in_weightT) cudaFree(net->in_weightT);
+    delete net;
+}
+
+extern "C" int mb_net_set_param(mb_net* net, const char* name, const float* data, const int64_t* shape, int ndim,
+                                mb_stream stream) {
+    MB_REQUIRE(net && name && data, "mb_net_set_param: null argument");
+    auto it = net->by_name.find(name);
+    MB_REQUIRE(it != net->by_name.end(), "mb_net_set_param: unknown parameter '%s'", name);
+    Param& p = *it->second;
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= static_cast<size_t>(shape[i]);
+    bool same = static_cast<size_t>(ndim) == p.shape.size();
+    for (int i = 0; same && i < ndim; ++i) same = shape[i] == p.shape[i];
+    if (!same && numel == p.numel && numel == 1) same = true;  // scalars: [] vs [1]
+    MB_REQUIRE(same, "mb_net_set_param: shape mismatch for '%s' (got %d dims, %zu elements; expected %zu elements)",
+               name, ndim, numel, p.numel);
+    MB_CUDA(cudaMemcpyAsync(p.dev, data, sizeof(float) * p.numel, cudaMemcpyDeviceToDevice,
+                            static_cast<cudaStream_t>(stream)));
+    p.set = true;
+    net->finalized = false;
+    return MB_OK;
+}
+
+namespace {
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n * n) {
+        const int r = idx / n, c = idx % n;
+        out[c * n + r] = in[idx];
+    }
+}
+}  // namespace
+
+extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
+    MB_REQUIRE(net, "mb_net_finalize: null net");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    for (auto& kv : net->by_name) {
+        if (!kv.second->set) {
+            set_error("mb_net_finalize: parameter '%s' was never set", kv.first.c_str());
+            return MB_ESTATE;
+        }
+    }
+    const int C0 = net->in_channels;
+    transpose_kernel<<<ceil_div(C0 * C0, 256), 256, 0, stream>>>(net->in_weight.dev, net->in_weightT, C0);
+    MB_CUDA(cudaGetLastError());
+    for (auto& L : net->layers) {
+        if (!L.g.is_torgb) {
+            int r = pack_weights_launch(L.weight.dev, L.wpk, L.wsqT, L.g.out_channels, L.g.in_channels, L.g.conv_kernel,
+                                        /*prenorm=*/1, stream);
+            if (r != MB_OK) return r;
+        }
+        L.fu.assign(32, 0.0f);
+        L.fd.assign(144, 0.0f);
+        L.fu[0] = 1.0f;
+        L.fd[0] = 1.0f;
+        if (L.up_filter.dev)
+            MB_CUDA(cudaMemcpyAsync(L.fu.data(), L.up_filter.dev, sizeof(float) * L.up_filter.numel, cudaMemcpyDeviceToHost, stream));
+        if (L.down_filter.dev)
+            MB_CUDA(cudaMemcpyAsync(L.fd.data(), L.down_filter.dev, sizeof(float) * L.down_filter.numel, cudaMemcpyDeviceToHost, stream));
+    }
+    MB_CUDA(cudaStreamSynchronize(stream));
+    net->finalized = true;
+    return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// workspace
+// ---------------------------------------------------------------------------------------
+namespace {
+struct WsLayout {
+    size_t styles_off, d_off, scratch_off, x_off, y_off, total;
+    std::vector<size_t> style_l, d_l;  // per-layer float offsets inside styles / d blocks
+};
+WsLayout ws_layout(const mb_net* net, int B) {
+    WsLayout w;
+    size_t ns = 0, nd = 0;
+    size_t max_x = static_cast<size_t>(B) * net->in_channels * net->in_size * pitch8(net->in_size);
+    size_t max_y = 0;
+    for (const auto& L : net->layers) {
+        w.style_l.push_back(ns);
+        w.d_l.push_back(nd);
+        ns += static_cast<size_t>(B) * L.g.in_channels;
+        nd += static_cast<size_t>(B) * L.g.out_channels;
+        const size_t xin = static_cast<size_t>(B) * L.g.in_channels * L.g.in_size * pitch8(L.g.in_size);
+        if (xin > max_x) max_x = xin;
+        if (!L.g.is_torgb) {
+            const int ho = L.g.in_size + L.g.conv_kernel - 1;
+            const size_t y = static_cast<size_t>(B) * L.g.out_channels * ho * pitch8(ho);
+            if (y > max_y) max_y = y;
+            const size_t xo = static_cast<size_t>(B) * L.g.out_channels * L.g.out_size * pitch8(L.g.out_size);
+            if (xo > max_x) max_x = xo;
+        }
+    }
+    size_t off = 0;
+    w.styles_off = off; off = round_up_sz(off + ns * sizeof(float), 1024);
+    w.d_off = off; off = round_up_sz(off + nd * sizeof(float), 1024);
+    w.scratch_off = off; off = round_up_sz(off + static_cast<size_t>(B) * net->in_channels * 4 * sizeof(float), 1024);
+    w.x_off = off; off = round_up_sz(off + max_x * sizeof(__half), 1024);
+    w.y_off = off; off = round_up_sz(off + max_y * sizeof(__half), 1024);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t mb_net_workspace_bytes(const mb_net* net, int batch) {
+    if (!net || batch <= 0) return 0;
+    return ws_layout(net, batch).total;
+}
+
+extern "C" int mb_net_set_conv_impl(mb_net* net, int impl) {
+    MB_REQUIRE(net && (impl == 0 || impl == 1), "mb_net_set_conv_impl: bad argument");
+    net->conv_impl = impl;
+    return MB_OK;
+}
+
+extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
+    MB_REQUIRE(net && key, "mb_net_set_option: null argument");
+    const std::string k = key;
+    if (k == "conv_impl") net->conv_impl = value;
+    else if (k == "conv_tile_w") net->conv_tile_w = value == 32 ? 32 : 64;
+    else if (k == "flrelu_impl") net->flrelu_impl = value;
+    else if (k == "debug_stop") net->debug_stop = value;
+    else {
+        set_error("mb_net_set_option: unknown option '%s'", key);
+        return MB_EINVAL;
+    }
+    return MB_OK;
+}
+
+extern "C" int mb_net_last_launch_count(const mb_net* net) { return net ? net->last_launches : 0; }
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transform, int B, void* out, int out_fmt,
+                              void* workspace, size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(net && ws && out && workspace, "mb_net_forward: null argument");
+    MB_REQUIRE(B > 0, "mb_net_forward: batch must be positive");
+    MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
+    if (!net->finalized) {
+        set_error("mb_net_forward: call mb_net_finalize after setting parameters");
+        return MB_ESTATE;
+    }
+    MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
+    const WsLayout wl = ws_layout(net, B);
+    if (workspace_bytes < wl.total) {
+        set_error("mb_net_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, wl.total);
+        return MB_ENOMEM;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float* styles = reinterpret_cast<float*>(base + wl.styles_off);
+    float* dco = reinterpret_cast<float*>(base + wl.d_off);
+    float* scratch = reinterpret_cast<float*>(base + wl.scratch_off);
+    __half* X = reinterpret_cast<__half*>(base + wl.x_off);
+    __half* Y = reinterpret_cast<__half*>(base + wl.y_off);
+    const int nl = static_cast<int>(net->layers.size());
+    int launches = 0;
+    int r;
+
+    // 1. styles + demodulation coefficients of every layer
+    {
+        StylesArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.num_layers = nl;
+        sa.B = B;
+        sa.num_ws = net->cfg.num_layers + 2;
+        sa.w_dim = net->cfg.w_dim;
+        sa.ws = ws;
+        for (int i = 0; i < nl; ++i) {
+            const LayerState& L = net->layers[i];
+            StyleLayerDesc& d = sa.L[i];
+            d.affine_w = L.affine_w.dev;
+            d.affine_b = L.affine_b.dev;
+            d.wsqT = L.wsqT;
+            d.magnitude_ema = L.magnitude_ema.dev;
+            d.s_out = styles + wl.style_l[i];
+            d.d_out = L.g.is_torgb ? nullptr : dco + wl.d_l[i];
+            d.Cin = L.g.in_channels;
+            d.Cout = L.g.out_channels;
+            d.ws_index = i + 1;
+            d.demodulate = !L.g.is_torgb;
+            d.style_scale = L.g.is_torgb ? 1.0f / sqrtf(static_cast<float>(L.g.in_channels * L.g.conv_kernel * L.g.conv_kernel)) : 1.0f;
+        }
+        if ((r = styles_launch(sa, stream)) != MB_OK) return r;
+        launches += 1;
+    }
+    // 2. Fourier-feature input, pre-multiplied by layer 0's style
+    {
+        InputArgs ia;
+        ia.ws = ws;
+        ia.affine_w = net->in_affine_w.dev;
+        ia.affine_b = net->in_affine_b.dev;
+        ia.transform = transform ? transform : net->in_transform.dev;
+        ia.freqs = net->in_freqs.dev;
+        ia.phases = net->in_phases.dev;
+        ia.weightT = net->in_weightT;
+        ia.style = styles + wl.style_l[0];
+        ia.scratch = scratch;
+        ia.out = X;
+        ia.B = B;
+        ia.num_ws = net->cfg.num_layers + 2;
+        ia.w_dim = net->cfg.w_dim;
+        ia.C = net->in_channels;
+        ia.size = net->in_size;
+        ia.Wp = pitch8(net->in_size);
+        ia.sampling_rate = static_cast<float>(net->in_sr);
+        ia.bandwidth = static_cast<float>(net->in_bw);
+        if ((r = sg3_input_launch(ia, stream)) != MB_OK) return r;
+        launches += 2;
+    }
+    net->last_ws = workspace;
+    net->last_batch = B;
+    net->last_act = X;
+    net->last_act_c = net->in_channels;
+    net->last_act_h = net->last_act_w = net->in_size;
+    if (net->debug_stop < 0) {
+        net->last_launches = launches;
+        return MB_OK;
+    }
+    // 3. layers
+    for (int i = 0; i < nl; ++i) {
+        const LayerState& L = net->layers[i];
+        const mb_sg3_layer& g = L.g;
+        if (g.is_torgb) {
+            ToRgbArgs ta;
+            ta.x = X;
+            ta.w = L.weight.dev;
+            ta.bias = L.bias.dev;
+            ta.out = out;
+            ta.B = B; ta.Cin = g.in_channels; ta.Cout = g.out_channels;
+            ta.H = g.in_size; ta.W = g.in_size; ta.Wp = pitch8(g.in_size);
+            ta.out_fmt = out_fmt;
+            ta.clamp = static_cast<float>(net->cfg.conv_clamp);
+            ta.output_scale = static_cast<float>(net->cfg.output_scale);
+            MB_REQUIRE(g.up == 1 && g.down == 1 && g.conv_kernel == 1 && g.in_size == g.out_size,
+                       "forward: unexpected ToRGB geometry");
+            if ((r = torgb_out_launch(ta, stream)) != MB_OK) return r;
+            launches += 1;
+            break;
+        }
+        ConvTcArgs ca;
+        ca.x = X;
+        ca.wpk = L.wpk;
+        ca.d = dco + wl.d_l[i];
+        ca.y = Y;
+        ca.B = B; ca.Cin = g.in_channels; ca.Cout = g.out_channels;
+        ca.Hin = g.in_size; ca.Win = g.in_size; ca.Wp_in = pitch8(g.in_size);
+        const int hc = g.in_size + g.conv_kernel - 1;
+        ca.Wp_out = pitch8(hc);
+        ca.ksz = g.conv_kernel;
+        ca.tile_w = net->conv_tile_w;
+        ca.num_sms = g_num_sms;
+        r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
+        if (r != MB_OK) return r;
+        launches += 1;
+
+        FlreluArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.x = Y;
+        fa.bias = L.bias.dev;
+        fa.scale = styles + wl.style_l[i + 1];
+        fa.y = X;
+        memcpy(fa.fu, L.fu.data(), sizeof(fa.fu));
+        memcpy(fa.fd, L.fd.data(), sizeof(fa.fd));
+        fa.B = B; fa.C = g.out_channels;
+        fa.Hin = hc; fa.Win = hc; fa.Wp_in = pitch8(hc);
+        fa.Hout = g.out_size; fa.Wout = g.out_size; fa.Wp_out = pitch8(g.out_size);
+        fa.up = g.up; fa.down = g.down; fa.up_taps = g.up_taps; fa.down_taps = g.down_taps;
+        fa.fd_2d = g.down_radial;
+        fa.px0 = g.pad_lo; fa.py0 = g.pad_lo;
+        fa.gain = sqrtf(2.0f); fa.slope = 0.2f;
+        fa.clamp = static_cast<float>(net->cfg.conv_clamp);
+        fa.num_sms = g_num_sms;
+        r = net->flrelu_impl == 1 ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
+        if (r != MB_OK) return r;
+        launches += 1;
+        net->last_act_c = g.out_channels;
+        net->last_act_h = net->last_act_w = g.out_size;
+        if (net->debug_stop <= i) break;
+    }
+    net->last_launches = launches;
+    return MB_OK;
+}
+
+extern "C" int mb_net_read_activation(mb_net* net, int idx, int batch, float* out, mb_stream stream) {
+    (void)idx;
+    MB_REQUIRE(net && out && net->last_act, "mb_net_read_activation: no forward has run");
+    MB_REQUIRE(batch == net->last_batch, "mb_net_read_activation: batch mismatch");
+    return half_to_float_launch(net->last_act, out, batch, net->last_act_c, net->last_act_h, net->last_act_w,
+                                pitch8(net->last_act_w), static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h, int32_t* w) {
+    MB_REQUIRE(net && c && h && w, "mb_net_activation_shape: null argument");
+    *c = net->last_act_c; *h = net->last_act_h; *w = net->last_act_w;
+    return MB_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// op-level entry points
+// ---------------------------------------------------------------------------------------
+extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* s, float* y, int B, int Cin, int Cout,
+                                   int H, int W, int k, int demodulate, float input_gain, int impl, mb_stream stream_) {
+    MB_REQUIRE(x && w && s && y, "mb_modulated_conv2d: null argument");
+    MB_REQUIRE(k == 1 || k == 3, "mb_modulated_conv2d: kernel size %d unsupported (1 or 3)", k);
+    if (g_device < 0) {
+        int r = mb_init(0);
+        if (r != MB_OK) return r;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int Ho = H + k - 1, Wo = W + k - 1;
+    const int Wp = pitch8(W), Wpo = pitch8(Wo);
+    __half *xh = nullptr, *wpk = nullptr, *yh = nullptr;
+    float *wsqT = nullptr, *sn = nullptr, *d = nullptr;
+    const size_t nx = static_cast<size_t>(B) * Cin * H * Wp, ny = static_cast<size_t>(B) * Cout * Ho * Wpo;
+    MB_CUDA(cudaMalloc(&xh, nx * 2));
+    MB_CUDA(cudaMalloc(&yh, ny * 2));
+    MB_CUDA(cudaMalloc(&wpk, packed_weight_elems(Cout, Cin, k) * 2));
+    MB_CUDA(cudaMalloc(&wsqT, sizeof(float) * Cin * Cout));
+    MB_CUDA(cudaMalloc(&sn, sizeof(float) * B * Cin));
+    MB_CUDA(cudaMalloc(&d, sizeof(float) * B * Cout));
+    int r = pack_weights_launch(w, wpk, wsqT, Cout, Cin, k, demodulate, stream);
+    if (r == MB_OK) r = style_demod_launch(s, wsqT, sn, d, B, Cin, Cout, demodulate, input_gain, stream);
+    if (r == MB_OK) r = modulate_to_half_launch(x, sn, 1.0f, xh, B, Cin, H, W, Wp, stream);
+    if (r == MB_OK) {
+        ConvTcArgs ca;
+        ca.x = xh; ca.wpk = wpk; ca.d = d; ca.y = yh;
+        ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Wp_in = Wp; ca.Wp_out = Wpo; ca.ksz = k;
+        ca.tile_w = (impl == 2) ? 32 : 64;
+        ca.num_sms = g_num_sms;
+        r = (impl == 1) ? conv_simt_launch(ca, stream) : conv_tc_launch(ca, stream);
+    }
+    if (r == MB_OK) r = half_to_float_launch(yh, y, B, Cout, Ho, Wo, Wpo, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(xh); cudaFree(yh); cudaFree(wpk); cudaFree(wsqT); cudaFree(sn); cudaFree(d);
+    if (r == MB_OK && e != cudaSuccess) {
+        set_error("mb_modulated_conv2d: %s", cudaGetErrorString(e));
+        return MB_ECUDA;
+    }
+    return r;
+}
+
+extern "C" int mb_filtered_lrelu(const float* x, const float* fu, const float* fd, const float* b, float* y, int B,
+                                 int C, int H, int W, int up, int down, int up_taps, int down_taps, int fd_2d, int px0,
+                                 int px1, int py0, int py1, float gain, float slope, float clamp, mb_stream stream_) {
+    MB_REQUIRE(x && y, "mb_filtered_lrelu: null argument");
+    MB_REQUIRE(up >= 1 && down >= 1 && up_taps >= 1 && up_taps <= 32 && down_taps >= 1 && down_taps <= 12,
+               "mb_filtered_lrelu: unsupported filter sizes");
+    MB_REQUIRE((fu != nullptr) == (up_taps > 1) && (fd != nullptr) == (down_taps > 1),
+               "mb_filtered_lrelu: filter pointer / tap count mismatch");
+    if (g_device < 0) {
+        int r = mb_init(0);
+        if (r != MB_OK) return r;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int Ho = (H * up + py0 + py1 - (up_taps - 1) - (down_taps - 1) + (down - 1)) / down;
+    const int Wo = (W * up + px0 + px1 - (up_taps - 1) - (down_taps - 1) + (down - 1)) / down;
+    MB_REQUIRE(Ho > 0 && Wo > 0, "mb_filtered_lrelu: empty output");
+    FlreluArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.fu[0] = 1.0f;
+    fa.fd[0] = 1.0f;
+    if (fu) MB_CUDA(cudaMemcpy(fa.fu, fu, sizeof(float) * up_taps, cudaMemcpyDeviceToHost));
+    if (fd) MB_CUDA(cudaMemcpy(fa.fd, fd, sizeof(float) * (fd_2d ? down_taps * down_taps : down_taps), cudaMemcpyDeviceToHost));
+    const int Wp = pitch8(W), Wpo = pitch8(Wo);
+    __half *xh = nullptr, *yh = nullptr;
+    MB_CUDA(cudaMalloc(&xh, static_cast<size_t>(B) * C * H * Wp * 2));
+    MB_CUDA(cudaMalloc(&yh, static_cast<size_t>(B) * C * Ho * Wpo * 2));
+    int r = modulate_to_half_launch(x, nullptr, 1.0f, xh, B, C, H, W, Wp, stream);
+    fa.x = xh; fa.bias = b; fa.scale = nullptr; fa.y = yh;
+    fa.B = B; fa.C = C; fa.Hin = H; fa.Win = W; fa.Wp_in = Wp; fa.Hout = Ho; fa.Wout = Wo; fa.Wp_out = Wpo;
+    fa.up = up; fa.down = down; fa.up_taps = up_taps; fa.down_taps = down_taps; fa.fd_2d = fd_2d;
+    fa.px0 = px0; fa.py0 = py0;
+    fa.gain = gain; fa.slope = slope; fa.clamp = clamp;
+    fa.num_sms = g_num_sms;
+    const char* impl = getenv("MB_FLRELU_IMPL");
+    if (r == MB_OK) r = (impl && atoi(impl) == 1) ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
+    if (r == MB_OK) r = half_to_float_launch(yh, y, B, C, Ho, Wo, Wpo, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaFree(xh); cudaFree(yh);
+    if (r == MB_OK && e != cudaSuccess) {
+        set_error("mb_filtered_lrelu: %s", cudaGetErrorString(e));
+        return MB_ECUDA;
+    }
+    return r;
+}

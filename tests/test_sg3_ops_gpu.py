@@ -1,0 +1,75 @@
+"""Parity of the two hot ops (through the C ABI) against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg3 as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(got, ref):
+    ref = ref.double()
+    return float((got.double().cpu() - ref).abs().max() / ref.square().mean().sqrt())
+
+
+CONV_CASES = [
+    # B, Cin, Cout, H, W, k, demod
+    (2, 64, 128, 20, 20, 3, True),
+    (2, 81, 51, 70, 66, 3, True),
+    (1, 512, 512, 38, 38, 3, True),
+    (2, 128, 96, 40, 24, 1, True),
+    (1, 203, 130, 150, 150, 3, True),
+    (1, 32, 3, 64, 64, 1, False),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", [1, 0, 2])
+def test_modulated_conv2d(cuda, case, impl):
+    from maua_b200 import ops
+
+    B, Cin, Cout, H, W, k, demod = case
+    g = torch.Generator().manual_seed(1234 + Cin + H)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g)
+    s = torch.randn(B, Cin, generator=g) + 1.0
+    gain = 0.7
+    ref = O.modulated_conv2d_ref(x, w, s, demodulate=demod, padding=k - 1, input_gain=torch.tensor(gain))
+    got = ops.modulated_conv2d(x.to(cuda), w.to(cuda), s.to(cuda), demodulate=demod, input_gain=gain, impl=impl)
+    assert got.shape == ref.shape
+    # fp16 operands (x*s, W) and fp16 output, fp32 accumulation: a few 1e-3 of the output RMS
+    assert _rel_err(got, ref) < 8e-3
+
+
+FL_CASES = [
+    # C, H, W, up, down, ut, dt, pad(lo,hi), radial
+    (3, 38, 38, 2, 2, 12, 12, (9, 8), False),
+    (2, 54, 54, 4, 2, 24, 12, (-6, -9), False),
+    (2, 150, 130, 2, 2, 12, 12, (-11, -12), False),
+    (2, 86, 86, 4, 2, 24, 12, (-6, -9), True),
+    (4, 33, 47, 1, 1, 1, 1, (0, 0), False),
+    (2, 40, 40, 2, 1, 12, 1, (5, 6), False),
+    (2, 40, 40, 1, 2, 1, 12, (5, 6), False),
+]
+
+
+@pytest.mark.parametrize("case", FL_CASES)
+@pytest.mark.parametrize("impl", ["auto", "generic"])
+def test_filtered_lrelu(cuda, case, impl, monkeypatch):
+    from maua_b200 import ops
+
+    C, H, W, up, down, ut, dt, (lo, hi), radial = case
+    monkeypatch.setenv("MB_FLRELU_IMPL", "1" if impl == "generic" else "0")
+    g = torch.Generator().manual_seed(99 + H)
+    x = (torch.randn(2, C, H, W, generator=g) * 2).half().float()
+    b = torch.randn(C, generator=g)
+    fu = O.design_lowpass_filter(ut, 8.0, 9.0, 64.0) if ut > 1 else None
+    fd = O.design_lowpass_filter(dt, 8.0, 9.0, 64.0, radial=radial) if dt > 1 else None
+    pad = [lo, hi, lo, hi]
+    ref = O.filtered_lrelu_ref(x, fu=fu, fd=fd, b=b, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256)
+    got = ops.filtered_lrelu(x.to(cuda), None if fu is None else fu.to(cuda), None if fd is None else fd.to(cuda),
+                             b.to(cuda), up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256)
+    assert got.shape == ref.shape
+    # fp32 arithmetic, fp16 output rounding only
+    assert _rel_err(got, ref) < 2e-3

@@ -127,7 +127,7 @@ int mb_net_last_launch_count(const mb_net* net);
 /* 0 = tcgen05 tensor-core conv (product path), 1 = plain CUDA-core conv (bisecting aid for the
  * parity tests; never used by the host facade). */
 int mb_net_set_conv_impl(mb_net* net, int impl);
-/* Test / tuning knobs: "conv_impl" (0|1), "conv_tile_w" (64|32), "flrelu_impl" (0 auto | 1 generic),
+/* Test / tuning knobs: "conv_impl" (0|1), "conv_tile_w" (32|16), "flrelu_impl" (0 auto | 1 generic),
  * "debug_stop" (stop the forward after layer N; -1 = after the input layer; default: run all). */
 int mb_net_set_option(mb_net* net, const char* key, int value);
 /* Shape [C,H,W] of the activation mb_net_read_activation would return. */

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "mb_net_set_conv_impl": (C.c_int, [_P, C.c_int]),
     "mb_net_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "mb_net_activation_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_debug_read": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "mb_modulated_conv2d": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_int, _P]),
     "mb_filtered_lrelu": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -101,6 +102,13 @@ def check(code: int):
     if code != 0:
         msg = load().mb_last_error()
         raise RuntimeError(f"libmaua_b200 error {code}: {msg.decode() if msg else ''}")
+
+
+def debug_words(n=24):
+    """Debug words kernels wrote to mapped host memory (MB_DEBUG=1); readable after a failed launch."""
+    buf = (C.c_int * n)()
+    load().mb_debug_read(buf, n)
+    return list(buf)
 
 
 def ptr(t):

@@ -82,12 +82,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Debug words in mapped host memory (survive a trapped kernel): see mb_debug_read().
+__device__ __forceinline__ void dbg_inc(volatile int* dbg, int idx) {
+    if (dbg && blockIdx.x == 0) dbg[idx] = dbg[idx] + 1;
+}
 // Bounded spin: a broken pipeline traps instead of hanging the GPU box (a hang is a strike).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dbg = nullptr, int tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("mbar_wait timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+        if (++spins > (1u << 22)) {
+            if (dbg) {
+                dbg[16] = tag;
+                dbg[17] = blockIdx.x;
+                dbg[18] = threadIdx.x;
+                dbg[19] = static_cast<int>(parity);
+                __threadfence_system();
+            }
             __trap();
         }
     }
@@ -183,5 +193,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled get_encode_tiled();
+int* debug_words_device();  // mapped host memory or nullptr (MB_DEBUG=1)
 
 }  // namespace mb

@@ -8,14 +8,18 @@
 //
 // GEMM view per CTA tile:  D[128 couts, 256 pixels] += A[128, K] * B[K, 256]
 //   A = packed weights, K-major, SWIZZLE_128B tiles [128 x 64] (TMA 2D)
-//   B = activations, planar NCHW fp16, *MN-major* (pixels contiguous): one TMA 4D box
-//       (TW pixels, 64 channels, TH+k-1 rows) per (kw, 64-channel chunk).  The kh taps reuse the
-//       same shared-memory patch through row-offset descriptors (aligned to the swizzle atom),
-//       so each activation byte crosses L2->smem k times, not k*k times.  Zero padding of the
-//       convolution = TMA out-of-bounds fill (negative / past-the-end coordinates).
+//   B = activations, channels-last fp16 [B][H][W][Cp], K-major: one TMA 4D box
+//       (64 channels, TW pixels, TH+k-1 rows) per (kw, 64-channel chunk) lands as
+//       [(TH+k-1)*TW pixel rows][128 B] in the canonical SWIZZLE_128B layout.  The kh taps reuse
+//       the same shared-memory patch through row-offset descriptors (kh*TW rows = whole swizzle
+//       atoms), so each activation byte crosses L2->smem k times, not k*k times.  The kw taps need
+//       their own loads (measured: the TMA unit rejects box starts that are not 16-byte aligned,
+//       so a 1-pixel shift is only expressible on an outer dimension -> channels-last).  Zero
+//       padding of the convolution = TMA out-of-bounds fill (negative / past-the-end coordinates).
 //   D = fp32 in TMEM (2 x 256 columns, double buffered against the epilogue).
 // Warp roles (256 threads): warp0 TMA producer, warp1 MMA issuer, warp2 TMEM alloc,
-// warps4-7 epilogue (tcgen05.ld -> *d -> fp16 -> 128 B row segments of the NCHW output).
+// warps4-7 epilogue (tcgen05.ld -> *d -> fp16 -> row segments of the planar NCHW output that
+// filtered_lrelu consumes).
 #include "common.cuh"
 #include "kernels.h"
 
@@ -32,12 +36,9 @@ constexpr int kATileBytes = kTileM * kKC * 2;  // 16 KB
 template <int TW>
 struct Geo {
     static constexpr int TH = kTileN / TW;
-    static constexpr int ROWB = TW * 2;              // bytes per pixel row segment (swizzle span)
-    static constexpr int ATOM = ROWB * 8;            // 8 channels x ROWB
-    static constexpr int SLAB = kKC * ROWB;          // one h-row of the patch: 64 channels
+    static constexpr int SLAB = TW * 128;            // one h-row of the patch: TW pixels x 64 channels
     static constexpr int PATCH_MAX = (TH + 2) * SLAB;
     static constexpr int STAGE = 3 * kATileBytes + PATCH_MAX;
-    static constexpr uint32_t LAYOUT = (TW == 64) ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
     static constexpr int SMEM = kStages * STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -47,6 +48,7 @@ struct KArgs {
     const float* d;  // [B][Cout] or nullptr
     __half* y;
     long long plane_out;  // Hout * Wp_out
+    int* dbg;             // debug words (mapped host memory) or nullptr
 };
 
 template <int TW>
@@ -105,13 +107,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const int h0 = ht * G::TH, w0 = wt * TW, m0 = mt * kTileM;
                 for (int kw = 0; kw < a.ksz; ++kw) {
                     for (int cc = 0; cc < a.nCC; ++cc) {
-                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                         uint8_t* st = smem + s * G::STAGE;
                         mbar_arrive_expect_tx(&full[s], stage_bytes);
                         const int kblk = (kw * a.nCC + cc) * a.ksz;
                         for (int kh = 0; kh < a.ksz; ++kh)
                             tma_load_2d(st + kh * kATileBytes, &tmap_w, &full[s], (kblk + kh) * kKC, m0);
-                        tma_load_4d(st + 3 * kATileBytes, &tmap_x, &full[s], w0 + kw - pad, cc * kKC, h0 - pad, b);
+                        tma_load_4d(st + 3 * kATileBytes, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
+                        dbg_inc(a.dbg, 0);
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -120,13 +123,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, /*A K-major*/ 0, /*B MN-major*/ 1);
+            constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, /*A K-major*/ 0, /*B K-major*/ 0);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-                mbar_wait(&tempty[acc], acc_ph ^ 1);
+                mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTileN;
                 uint32_t accumulate = 0;
@@ -134,20 +137,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     const int cc = it % a.nCC;
                     int nk16 = (a.Cin - cc * kKC + 15) / 16;
                     if (nk16 > 4) nk16 = 4;
-                    mbar_wait(&full[s], ph);
+                    mbar_wait(&full[s], ph, a.dbg, 3);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * G::STAGE);
                     const uint32_t sb = sa + 3 * kATileBytes;
                     for (int kh = 0; kh < a.ksz; ++kh) {
                         for (int j = 0; j < nk16; ++j) {
                             const uint64_t da = make_smem_desc(sa + kh * kATileBytes + j * 32, 16, 1024, 2);
-                            const uint64_t db =
-                                make_smem_desc(sb + kh * G::SLAB + j * 2 * G::ATOM, G::SLAB, G::ATOM, G::LAYOUT);
+                            const uint64_t db = make_smem_desc(sb + kh * G::SLAB + j * 32, 16, 1024, 2);
                             umma_f16(d_tmem, da, db, idesc, accumulate);
                             accumulate = 1;
                         }
                     }
                     umma_commit(&empty[s]);
+                    dbg_inc(a.dbg, 1);
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull[acc]);
@@ -171,7 +174,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const float scale = (co_ok && a.d) ? a.d[b * a.Cout + co] : 1.0f;
             __half* yplane = a.y + (static_cast<long long>(b) * a.Cout + (co_ok ? co : 0)) * a.plane_out;
 
-            mbar_wait(&tfull[acc], acc_ph);
+            mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < kTileN / 32; ++ch) {
@@ -179,13 +182,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + ch * 32, v);
                 tmem_ld_wait();
                 const int n0 = ch * 32;
-                const int h = h0 + n0 / TW;
-                const int w = w0 + n0 % TW;
-                if (co_ok && h < a.Hout) {
-                    __half* dst = yplane + static_cast<long long>(h) * a.Wp_out + w;
+                if (co_ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        if (w + g * 8 < a.Wp_out) {
+                        const int n = n0 + g * 8;
+                        const int h = h0 + n / TW;
+                        const int w = w0 + n % TW;
+                        if (h < a.Hout && w < a.Wp_out) {
                             uint4 pk;
                             __half2 h0v = __floats2half2_rn(__uint_as_float(v[g * 8 + 0]) * scale,
                                                             __uint_as_float(v[g * 8 + 1]) * scale);
@@ -199,14 +202,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                             pk.y = *reinterpret_cast<uint32_t*>(&h1v);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2v);
                             pk.w = *reinterpret_cast<uint32_t*>(&h3v);
-                            *reinterpret_cast<uint4*>(dst + g * 8) = pk;
+                            *reinterpret_cast<uint4*>(yplane + static_cast<long long>(h) * a.Wp_out + w) = pk;
                         }
                     }
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (lane == 0) { mbar_arrive(&tempty[acc]); if (q == 0) dbg_inc(a.dbg, 2); }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     }
@@ -218,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
 }  // namespace
 
-int conv_tc_smem_bytes(int tw) { return tw == 64 ? Geo<64>::SMEM : Geo<32>::SMEM; }
+int conv_tc_smem_bytes(int tw) { return tw == 32 ? Geo<32>::SMEM : Geo<16>::SMEM; }
 
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     PFN_encodeTiled enc = get_encode_tiled();
@@ -226,11 +229,11 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return MB_ECUDA;
     }
-    const int tw = p.tile_w == 32 ? 32 : 64;
+    const int tw = p.tile_w == 16 ? 16 : 32;
     const int th = kTileN / tw;
     const int pad = p.ksz - 1;
     MB_REQUIRE(p.ksz == 1 || p.ksz == 3, "conv_tc: kernel size %d unsupported", p.ksz);
-    MB_REQUIRE(p.Wp_in % 8 == 0 && p.Wp_out % 8 == 0, "conv_tc: row pitch must be a multiple of 8 elements");
+    MB_REQUIRE(p.Cp_in % 8 == 0 && p.Wp_out % 8 == 0, "conv_tc: channel / row pitch must be a multiple of 8 elements");
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(p.wpk) & 15) == 0,
                "conv_tc: pointers must be 16-byte aligned");
@@ -253,20 +256,18 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         }
     }
     {
-        const long long plane = static_cast<long long>(p.Hin) * p.Wp_in;
-        cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Win), static_cast<cuuint64_t>(p.Cin),
+        const cuuint64_t cp = static_cast<cuuint64_t>(p.Cp_in);
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.Win),
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
-        cuuint64_t strides[3] = {static_cast<cuuint64_t>(plane) * 2, static_cast<cuuint64_t>(p.Wp_in) * 2,
-                                 static_cast<cuuint64_t>(plane) * p.Cin * 2};
-        cuuint32_t box[4] = {static_cast<cuuint32_t>(tw), kKC, static_cast<cuuint32_t>(th + pad), 1};
+        cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
+        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th + pad), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         tw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled(activations) failed: %d (W=%d C=%d H=%d B=%d pitch=%d)",
-                      static_cast<int>(r), p.Win, p.Cin, p.Hin, p.B, p.Wp_in);
+            set_error("cuTensorMapEncodeTiled(activations) failed: %d (W=%d C=%d H=%d B=%d Cp=%d)",
+                      static_cast<int>(r), p.Win, p.Cin, p.Hin, p.B, p.Cp_in);
             return MB_ECUDA;
         }
     }
@@ -281,23 +282,24 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
     a.d = p.d; a.y = p.y;
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
+    a.dbg = debug_words_device();
 
     int grid = a.total_tiles < p.num_sms ? a.total_tiles : p.num_sms;
     if (grid < 1) grid = 1;
-    if (tw == 64) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<64>::SMEM));
-            attr_done = true;
-        }
-        conv_tc_kernel<64><<<grid, 256, Geo<64>::SMEM, stream>>>(tm_w, tm_x, a);
-    } else {
+    if (tw == 32) {
         static bool attr_done = false;
         if (!attr_done) {
             MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<32>::SMEM));
             attr_done = true;
         }
         conv_tc_kernel<32><<<grid, 256, Geo<32>::SMEM, stream>>>(tm_w, tm_x, a);
+    } else {
+        static bool attr_done = false;
+        if (!attr_done) {
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<16>::SMEM));
+            attr_done = true;
+        }
+        conv_tc_kernel<16><<<grid, 256, Geo<16>::SMEM, stream>>>(tm_w, tm_x, a);
     }
     MB_CUDA(cudaGetLastError());
     return MB_OK;

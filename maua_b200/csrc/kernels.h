@@ -1,7 +1,12 @@
 // Internal launch interfaces between the translation units of libmaua_b200.
 //
-// Device activation format ("planar-h"): fp16 [B][C][H][Wp], Wp = W rounded up to 8 elements so
-// every row starts 16-byte aligned (TMA global-stride rule); only [0,W) of a row is meaningful.
+// Device activation formats (fp16):
+//   "planar":        [B][C][H][Wp], Wp = W rounded up to 8 elements (16-byte aligned rows); only
+//                    [0,W) of a row is meaningful.  Produced by the conv epilogue and by
+//                    filtered_lrelu, consumed by filtered_lrelu and the ToRGB/output kernel.
+//   "channels-last": [B][H][W][Cp], Cp = C rounded up to 8 (TMA global strides are multiples of
+//                    16 bytes).  The conv's activation operand: the TMA box start must be 16-byte
+//                    aligned, so the 1-pixel kw shifts have to live on an outer dimension.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -13,12 +18,12 @@ static inline int pitch8(int w) { return (w + 7) / 8 * 8; }
 
 // ---- conv_tc.cu ------------------------------------------------------------------------
 struct ConvTcArgs {
-    const __half* x;    // [B][Cin][Hin][Wp_in], already multiplied by the style
+    const __half* x;    // channels-last [B][Hin][Win][Cp_in], already multiplied by the style
     const __half* wpk;  // packed weights [round_up(Cout,128)][k*k*nCC*64], see pack_weights
     const float* d;     // [B][Cout] demodulation coefficients or nullptr
-    __half* y;          // [B][Cout][Hin+k-1][Wp_out]
-    int B, Cin, Cout, Hin, Win, Wp_in, Wp_out, ksz;
-    int tile_w;         // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    __half* y;          // planar [B][Cout][Hin+k-1][Wp_out]
+    int B, Cin, Cout, Hin, Win, Cp_in, Wp_out, ksz;
+    int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
     int num_sms;
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);
@@ -62,8 +67,8 @@ struct InputArgs {
     const float* weightT;     // [C(j)][C(c)] = weight[c][j] transposed
     const float* style;       // [B][C] style of layer 0 (normalised * input_gain)
     float* scratch;           // [B][C][4]: fx, fy, phase, amplitude
-    __half* out;              // [B][C][size][Wp]
-    int B, num_ws, w_dim, C, size, Wp;
+    __half* out;              // channels-last [B][size][size][Cp]
+    int B, num_ws, w_dim, C, size, Cp;
     float sampling_rate, bandwidth;
 };
 int sg3_input_launch(const InputArgs& a, cudaStream_t stream);
@@ -78,11 +83,18 @@ struct ToRgbArgs {
 };
 int torgb_out_launch(const ToRgbArgs& a, cudaStream_t stream);
 
-// x f32 [B][C][H][W] * s[b][c] * gain -> fp16 planar-h (s may be nullptr)
+// x f32 [B][C][H][W] * s[b][c] * gain -> fp16 planar (s may be nullptr)
 int modulate_to_half_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Wp,
                             cudaStream_t stream);
-// fp16 planar-h -> f32 [B][C][H][W]
+// x f32 [B][C][H][W] * s[b][c] * gain -> fp16 channels-last [B][H][W][Cp]
+int modulate_to_nhwc_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Cp,
+                            cudaStream_t stream);
+// fp16 planar -> f32 [B][C][H][W]
 int half_to_float_launch(const __half* x, float* out, int B, int C, int H, int W, int Wp, cudaStream_t stream);
+// fp16 channels-last -> f32 [B][C][H][W]
+int nhwc_to_float_launch(const __half* x, float* out, int B, int C, int H, int W, int Cp, cudaStream_t stream);
+// fp16 planar [B][C][H][Wp] -> fp16 channels-last [B][H][W][Cp] (pad channels written as zero)
+int planar_to_nhwc_launch(const __half* x, __half* out, int B, int C, int H, int W, int Wp, int Cp, cudaStream_t stream);
 // op-level helper: s -> normalised s (if demodulate), d[b][o]
 int style_demod_launch(const float* s, const float* wsqT, float* s_out, float* d_out, int B, int Cin, int Cout,
                        int demodulate, float input_gain, cudaStream_t stream);

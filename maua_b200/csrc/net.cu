@@ -43,6 +43,9 @@ PFN_encodeTiled get_encode_tiled() {
 
 static int g_device = -1;
 static int g_num_sms = 148;
+static int* g_dbg_host = nullptr;
+static int* g_dbg_dev = nullptr;
+int* debug_words_device() { return g_dbg_dev; }
 
 int flrelu_generic_launch_public(const FlreluArgs& a, cudaStream_t stream);
 
@@ -75,7 +78,7 @@ struct mb_net {
     std::map<std::string, Param*> by_name;
     bool finalized = false;
     int conv_impl = 0;
-    int conv_tile_w = 64;
+    int conv_tile_w = 32;
     int flrelu_impl = 0;  // 0 = auto (register-blocked where supported), 1 = generic everywhere
     int debug_stop = 1 << 30;
     int last_launches = 0;
@@ -83,6 +86,7 @@ struct mb_net {
     void* last_ws = nullptr;
     int last_batch = 0;
     const __half* last_act = nullptr;
+    bool last_act_nhwc = false;
     int last_act_c = 0, last_act_h = 0, last_act_w = 0;
 };
 
@@ -186,6 +190,12 @@ extern "C" int mb_sg3_geometry(const mb_sg3_cfg* c, mb_sg3_layer* L, int32_t* in
 extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
 extern "C" int mb_abi_version(void) { return 1; }
 
+/* Debug words written by kernels into mapped host memory (enabled by MB_DEBUG=1 before mb_init). */
+extern "C" int mb_debug_read(int* out, int n) {
+    for (int i = 0; i < n && i < 64; ++i) out[i] = g_dbg_host ? g_dbg_host[i] : -1;
+    return g_dbg_host ? MB_OK : MB_ESTATE;
+}
+
 extern "C" int mb_init(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -203,6 +213,11 @@ extern "C" int mb_init(int device) {
     MB_CUDA(cudaSetDevice(device));
     g_device = device;
     g_num_sms = prop.multiProcessorCount;
+    if (!g_dbg_host && getenv("MB_DEBUG")) {
+        MB_CUDA(cudaHostAlloc(&g_dbg_host, 64 * sizeof(int), cudaHostAllocMapped));
+        memset(g_dbg_host, 0, 64 * sizeof(int));
+        MB_CUDA(cudaHostGetDevicePointer(&g_dbg_dev, g_dbg_host, 0));
+    }
     return MB_OK;
 }
 
@@ -301,7 +316,7 @@ extern "C" int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out) {
         }
     }
 #undef TRY
-    if (const char* e = getenv("MB_CONV_TILE_W")) net->conv_tile_w = atoi(e) == 32 ? 32 : 64;
+    if (const char* e = getenv("MB_CONV_TILE_W")) net->conv_tile_w = atoi(e) == 16 ? 16 : 32;
     if (const char* e = getenv("MB_FLRELU_IMPL")) net->flrelu_impl = atoi(e);
     *out = net;
     return MB_OK;
@@ -385,28 +400,30 @@ extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
 // workspace
 // ---------------------------------------------------------------------------------------
 namespace {
+inline int cpad8(int c) { return (c + 7) / 8 * 8; }
 struct WsLayout {
-    size_t styles_off, d_off, scratch_off, x_off, y_off, total;
+    size_t styles_off, d_off, scratch_off, x_off, y_off, p_off, total;
     std::vector<size_t> style_l, d_l;  // per-layer float offsets inside styles / d blocks
 };
+// X: channels-last conv input; Y: planar conv output; P: planar filtered_lrelu output.
 WsLayout ws_layout(const mb_net* net, int B) {
     WsLayout w;
     size_t ns = 0, nd = 0;
-    size_t max_x = static_cast<size_t>(B) * net->in_channels * net->in_size * pitch8(net->in_size);
-    size_t max_y = 0;
+    size_t max_x = static_cast<size_t>(B) * net->in_size * net->in_size * cpad8(net->in_channels);
+    size_t max_y = 0, max_p = 0;
     for (const auto& L : net->layers) {
         w.style_l.push_back(ns);
         w.d_l.push_back(nd);
         ns += static_cast<size_t>(B) * L.g.in_channels;
         nd += static_cast<size_t>(B) * L.g.out_channels;
-        const size_t xin = static_cast<size_t>(B) * L.g.in_channels * L.g.in_size * pitch8(L.g.in_size);
-        if (xin > max_x) max_x = xin;
         if (!L.g.is_torgb) {
+            const size_t xin = static_cast<size_t>(B) * L.g.in_size * L.g.in_size * cpad8(L.g.in_channels);
+            if (xin > max_x) max_x = xin;
             const int ho = L.g.in_size + L.g.conv_kernel - 1;
             const size_t y = static_cast<size_t>(B) * L.g.out_channels * ho * pitch8(ho);
             if (y > max_y) max_y = y;
-            const size_t xo = static_cast<size_t>(B) * L.g.out_channels * L.g.out_size * pitch8(L.g.out_size);
-            if (xo > max_x) max_x = xo;
+            const size_t po = static_cast<size_t>(B) * L.g.out_channels * L.g.out_size * pitch8(L.g.out_size);
+            if (po > max_p) max_p = po;
         }
     }
     size_t off = 0;
@@ -415,6 +432,7 @@ WsLayout ws_layout(const mb_net* net, int B) {
     w.scratch_off = off; off = round_up_sz(off + static_cast<size_t>(B) * net->in_channels * 4 * sizeof(float), 1024);
     w.x_off = off; off = round_up_sz(off + max_x * sizeof(__half), 1024);
     w.y_off = off; off = round_up_sz(off + max_y * sizeof(__half), 1024);
+    w.p_off = off; off = round_up_sz(off + max_p * sizeof(__half), 1024);
     w.total = off;
     return w;
 }
@@ -435,7 +453,7 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     MB_REQUIRE(net && key, "mb_net_set_option: null argument");
     const std::string k = key;
     if (k == "conv_impl") net->conv_impl = value;
-    else if (k == "conv_tile_w") net->conv_tile_w = value == 32 ? 32 : 64;
+    else if (k == "conv_tile_w") net->conv_tile_w = value == 16 ? 16 : 32;
     else if (k == "flrelu_impl") net->flrelu_impl = value;
     else if (k == "debug_stop") net->debug_stop = value;
     else {
@@ -472,6 +490,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     float* scratch = reinterpret_cast<float*>(base + wl.scratch_off);
     __half* X = reinterpret_cast<__half*>(base + wl.x_off);
     __half* Y = reinterpret_cast<__half*>(base + wl.y_off);
+    __half* P = reinterpret_cast<__half*>(base + wl.p_off);
     const int nl = static_cast<int>(net->layers.size());
     int launches = 0;
     int r;
@@ -521,7 +540,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ia.w_dim = net->cfg.w_dim;
         ia.C = net->in_channels;
         ia.size = net->in_size;
-        ia.Wp = pitch8(net->in_size);
+        ia.Cp = cpad8(net->in_channels);
         ia.sampling_rate = static_cast<float>(net->in_sr);
         ia.bandwidth = static_cast<float>(net->in_bw);
         if ((r = sg3_input_launch(ia, stream)) != MB_OK) return r;
@@ -530,6 +549,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     net->last_ws = workspace;
     net->last_batch = B;
     net->last_act = X;
+    net->last_act_nhwc = true;
     net->last_act_c = net->in_channels;
     net->last_act_h = net->last_act_w = net->in_size;
     if (net->debug_stop < 0) {
@@ -542,7 +562,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         const mb_sg3_layer& g = L.g;
         if (g.is_torgb) {
             ToRgbArgs ta;
-            ta.x = X;
+            ta.x = P;
             ta.w = L.weight.dev;
             ta.bias = L.bias.dev;
             ta.out = out;
@@ -563,7 +583,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ca.d = dco + wl.d_l[i];
         ca.y = Y;
         ca.B = B; ca.Cin = g.in_channels; ca.Cout = g.out_channels;
-        ca.Hin = g.in_size; ca.Win = g.in_size; ca.Wp_in = pitch8(g.in_size);
+        ca.Hin = g.in_size; ca.Win = g.in_size; ca.Cp_in = cpad8(g.in_channels);
         const int hc = g.in_size + g.conv_kernel - 1;
         ca.Wp_out = pitch8(hc);
         ca.ksz = g.conv_kernel;
@@ -578,7 +598,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         fa.x = Y;
         fa.bias = L.bias.dev;
         fa.scale = styles + wl.style_l[i + 1];
-        fa.y = X;
+        fa.y = P;
         memcpy(fa.fu, L.fu.data(), sizeof(fa.fu));
         memcpy(fa.fd, L.fd.data(), sizeof(fa.fd));
         fa.B = B; fa.C = g.out_channels;
@@ -593,9 +613,18 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         r = net->flrelu_impl == 1 ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
         if (r != MB_OK) return r;
         launches += 1;
+        net->last_act = P;
+        net->last_act_nhwc = false;
         net->last_act_c = g.out_channels;
         net->last_act_h = net->last_act_w = g.out_size;
         if (net->debug_stop <= i) break;
+        if (!net->layers[i + 1].g.is_torgb) {
+            // the next conv reads channels-last (TMA box starts must be 16-byte aligned)
+            r = planar_to_nhwc_launch(P, X, B, g.out_channels, g.out_size, g.out_size, pitch8(g.out_size),
+                                      cpad8(g.out_channels), stream);
+            if (r != MB_OK) return r;
+            launches += 1;
+        }
     }
     net->last_launches = launches;
     return MB_OK;
@@ -605,6 +634,9 @@ extern "C" int mb_net_read_activation(mb_net* net, int idx, int batch, float* ou
     (void)idx;
     MB_REQUIRE(net && out && net->last_act, "mb_net_read_activation: no forward has run");
     MB_REQUIRE(batch == net->last_batch, "mb_net_read_activation: batch mismatch");
+    if (net->last_act_nhwc)
+        return nhwc_to_float_launch(net->last_act, out, batch, net->last_act_c, net->last_act_h, net->last_act_w,
+                                    cpad8(net->last_act_c), static_cast<cudaStream_t>(stream));
     return half_to_float_launch(net->last_act, out, batch, net->last_act_c, net->last_act_h, net->last_act_w,
                                 pitch8(net->last_act_w), static_cast<cudaStream_t>(stream));
 }
@@ -628,10 +660,10 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int Ho = H + k - 1, Wo = W + k - 1;
-    const int Wp = pitch8(W), Wpo = pitch8(Wo);
+    const int Cp = (Cin + 7) / 8 * 8, Wpo = pitch8(Wo);
     __half *xh = nullptr, *wpk = nullptr, *yh = nullptr;
     float *wsqT = nullptr, *sn = nullptr, *d = nullptr;
-    const size_t nx = static_cast<size_t>(B) * Cin * H * Wp, ny = static_cast<size_t>(B) * Cout * Ho * Wpo;
+    const size_t nx = static_cast<size_t>(B) * H * W * Cp, ny = static_cast<size_t>(B) * Cout * Ho * Wpo;
     MB_CUDA(cudaMalloc(&xh, nx * 2));
     MB_CUDA(cudaMalloc(&yh, ny * 2));
     MB_CUDA(cudaMalloc(&wpk, packed_weight_elems(Cout, Cin, k) * 2));
@@ -640,12 +672,12 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
     MB_CUDA(cudaMalloc(&d, sizeof(float) * B * Cout));
     int r = pack_weights_launch(w, wpk, wsqT, Cout, Cin, k, demodulate, stream);
     if (r == MB_OK) r = style_demod_launch(s, wsqT, sn, d, B, Cin, Cout, demodulate, input_gain, stream);
-    if (r == MB_OK) r = modulate_to_half_launch(x, sn, 1.0f, xh, B, Cin, H, W, Wp, stream);
+    if (r == MB_OK) r = modulate_to_nhwc_launch(x, sn, 1.0f, xh, B, Cin, H, W, Cp, stream);
     if (r == MB_OK) {
         ConvTcArgs ca;
         ca.x = xh; ca.wpk = wpk; ca.d = d; ca.y = yh;
-        ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Wp_in = Wp; ca.Wp_out = Wpo; ca.ksz = k;
-        ca.tile_w = (impl == 2) ? 32 : 64;
+        ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
+        ca.tile_w = (impl == 2) ? 16 : 32;
         ca.num_sms = g_num_sms;
         r = (impl == 1) ? conv_simt_launch(ca, stream) : conv_tc_launch(ca, stream);
     }

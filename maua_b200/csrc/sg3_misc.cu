@@ -102,7 +102,7 @@ __global__ void conv_simt_kernel(ConvTcArgs p, int Hout, int Wout) {
                     const int cc = ci >> 6, cl = ci & 63;
                     const float wv = __half2float(p.wpk[co * Ktot + (((kw * nCC + cc) * p.ksz + kh) << 6) + cl]);
                     const float xv =
-                        __half2float(p.x[((static_cast<long long>(b) * p.Cin + ci) * p.Hin + hi) * p.Wp_in + wi]);
+                        __half2float(p.x[((static_cast<long long>(b) * p.Hin + hi) * p.Win + wi) * p.Cp_in + ci]);
                     acc = fmaf(wv, xv, acc);
                 }
             }
@@ -239,15 +239,18 @@ __global__ void __launch_bounds__(256) input_feat_kernel(InputArgs a) {
             for (int i = 0; i < kInPix; ++i) acc[i] = fmaf(sm[i * a.C + j], wv, acc[i]);
         }
         const float st = a.style ? a.style[static_cast<long long>(b) * a.C + cidx] : 1.0f;
-        __half* o = a.out + (static_cast<long long>(b) * a.C + cidx) * a.size * a.Wp;
+        __half* o = a.out + static_cast<long long>(b) * npix * a.Cp + cidx;
 #pragma unroll
         for (int i = 0; i < kInPix; ++i) {
             const int pix = p0 + i;
-            if (pix < npix) {
-                const int h = pix / a.size, w = pix - h * a.size;
-                o[h * a.Wp + w] = __float2half_rn(acc[i] * st);
-            }
+            if (pix < npix) o[static_cast<long long>(pix) * a.Cp] = __float2half_rn(acc[i] * st);
         }
+    }
+    // zero the channel padding [C, Cp)
+    for (int idx = threadIdx.x; idx < kInPix * (a.Cp - a.C); idx += blockDim.x) {
+        const int i = idx / (a.Cp - a.C), cpad = a.C + idx % (a.Cp - a.C);
+        const int pix = p0 + i;
+        if (pix < npix) a.out[(static_cast<long long>(b) * npix + pix) * a.Cp + cpad] = __float2half_rn(0.0f);
     }
 }
 
@@ -359,6 +362,68 @@ __global__ void half_to_float_kernel(const __half* __restrict__ x, float* __rest
     }
 }
 
+__global__ void modulate_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ s, float gain,
+                                        __half* __restrict__ out, int B, int C, int H, int W, int Cp) {
+    const long long total = static_cast<long long>(B) * H * W * Cp;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % Cp);
+        long long r = idx / Cp;
+        const int w = static_cast<int>(r % W); r /= W;
+        const int h = static_cast<int>(r % H);
+        const int b = static_cast<int>(r / H);
+        float v = 0.0f;
+        if (c < C) {
+            v = x[((static_cast<long long>(b) * C + c) * H + h) * W + w] * gain;
+            if (s) v *= s[b * C + c];
+        }
+        out[idx] = __float2half_rn(v);
+    }
+}
+
+__global__ void nhwc_to_float_kernel(const __half* __restrict__ x, float* __restrict__ out, int B, int C, int H, int W,
+                                     int Cp) {
+    const long long total = static_cast<long long>(B) * C * H * W;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int w = static_cast<int>(idx % W);
+        long long r = idx / W;
+        const int h = static_cast<int>(r % H); r /= H;
+        const int c = static_cast<int>(r % C);
+        const int b = static_cast<int>(r / C);
+        out[idx] = __half2float(x[((static_cast<long long>(b) * H + h) * W + w) * Cp + c]);
+    }
+}
+
+// planar -> channels-last through a shared-memory tile: one CTA = (b, h, 32 pixels) x all channels.
+// Reads are 64-byte row segments per channel, writes are one contiguous run of 32*Cp halves.
+constexpr int kTrP = 32;
+__global__ void __launch_bounds__(256) planar_to_nhwc_kernel(const __half* __restrict__ x, __half* __restrict__ out,
+                                                             int C, int H, int W, int Wp, int Cp) {
+    extern __shared__ __half tile[];  // [Cp][kTrP + 2]
+    const int w0 = blockIdx.x * kTrP, h = blockIdx.y, b = blockIdx.z;
+    const __half2 zero2 = __float2half2_rn(0.0f);
+    // load: thread -> (channel, pixel pair)
+    for (int idx = threadIdx.x; idx < Cp * (kTrP / 2); idx += blockDim.x) {
+        const int c = idx / (kTrP / 2), pp = idx % (kTrP / 2);
+        const int w = w0 + pp * 2;
+        __half2 v = zero2;
+        if (c < C && w < Wp) v = *reinterpret_cast<const __half2*>(x + ((static_cast<long long>(b) * C + c) * H + h) * Wp + w);
+        *reinterpret_cast<__half2*>(tile + c * (kTrP + 2) + pp * 2) = v;
+    }
+    __syncthreads();
+    // store: thread -> (pixel, channel pair)
+    const int npx = (W - w0) < kTrP ? (W - w0) : kTrP;
+    __half* o = out + ((static_cast<long long>(b) * H + h) * W + w0) * Cp;
+    for (int idx = threadIdx.x; idx < npx * (Cp / 2); idx += blockDim.x) {
+        const int px = idx / (Cp / 2), cp2 = idx % (Cp / 2);
+        __half2 v;
+        v.x = tile[(cp2 * 2) * (kTrP + 2) + px];
+        v.y = tile[(cp2 * 2 + 1) * (kTrP + 2) + px];
+        *reinterpret_cast<__half2*>(o + static_cast<long long>(px) * Cp + cp2 * 2) = v;
+    }
+}
+
 // op-level helper, grid B.
 __global__ void style_demod_kernel(const float* __restrict__ s, const float* __restrict__ wsqT, float* s_out,
                                    float* d_out, int Cin, int Cout, int demodulate, float input_gain) {
@@ -448,6 +513,34 @@ int modulate_to_half_launch(const float* x, const float* s, float gain, __half* 
                             cudaStream_t stream) {
     const long long total = static_cast<long long>(B) * C * H * Wp;
     modulate_to_half_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, s, gain, out, B, C, H, W, Wp);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int modulate_to_nhwc_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Cp,
+                            cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * H * W * Cp;
+    modulate_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, s, gain, out, B, C, H, W, Cp);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int nhwc_to_float_launch(const __half* x, float* out, int B, int C, int H, int W, int Cp, cudaStream_t stream) {
+    const long long total = static_cast<long long>(B) * C * H * W;
+    nhwc_to_float_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, out, B, C, H, W, Cp);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+int planar_to_nhwc_launch(const __half* x, __half* out, int B, int C, int H, int W, int Wp, int Cp, cudaStream_t stream) {
+    const size_t smem = static_cast<size_t>(Cp) * (kTrP + 2) * sizeof(__half);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        MB_CUDA(cudaFuncSetAttribute(planar_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        smem_set = smem;
+    }
+    dim3 grid(ceil_div(W, kTrP), H, B);
+    planar_to_nhwc_kernel<<<grid, 256, smem, stream>>>(x, out, C, H, W, Wp, Cp);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -7,6 +7,7 @@ from oracle import sg3 as O
 from maua_b200 import ops
 
 dev = torch.device("cuda:0")
+IMPLS = (1, 0, 2)
 print(torch.cuda.get_device_name(0), flush=True)
 
 
@@ -19,7 +20,7 @@ def conv_case(B, Cin, Cout, H, W, k, demod=True):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(B, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, k, k, generator=g); s = torch.randn(B, Cin, generator=g) + 1
     ref = O.modulated_conv2d_ref(x, w, s, demodulate=demod, padding=k - 1)
-    for impl in (1, 0, 2):
+    for impl in IMPLS:
         try:
             got = ops.modulated_conv2d(x.to(dev), w.to(dev), s.to(dev), demodulate=demod, impl=impl)
             torch.cuda.synchronize()
@@ -32,8 +33,9 @@ def conv_case(B, Cin, Cout, H, W, k, demod=True):
                 print("   err cols:", d.amax(dim=(0, 1, 2))[:12].tolist())
                 print("   got[0,0,:3,:6]", got[0, 0, :3, :6].cpu().tolist()); print("   ref[0,0,:3,:6]", ref[0, 0, :3, :6].tolist())
         except Exception as ex:
-            print(f"conv impl{impl} FAILED: {ex}", flush=True)
-            traceback.print_exc()
+            print(f"conv impl{impl} FAILED: {str(ex)[:200]}", flush=True)
+            from maua_b200 import _lib
+            print("   debug words:", _lib.debug_words(), flush=True)
 
 
 def fl_case(C, H, W, up, down, ut, dt, lo, hi, radial=False):
@@ -55,6 +57,9 @@ def fl_case(C, H, W, up, down, ut, dt, lo, hi, radial=False):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which.startswith("conv") and len(which) > 4:
+        IMPLS = (int(which[4:]),)
+        which = "conv"
     if which in ("all", "fl"):
         fl_case(3, 38, 38, 2, 2, 12, 12, 9, 8)
         fl_case(2, 54, 54, 4, 2, 24, 12, -6, -9)
@@ -67,3 +72,56 @@ if __name__ == "__main__":
         conv_case(2, 128, 96, 40, 24, 1)
         conv_case(1, 512, 512, 38, 38, 3)
     print("probe done", flush=True)
+
+
+def net_case(res=256, cb=8192, cm=128, B=2, config="T"):
+    from maua_b200.GAN.networks import stylegan3 as N
+    kw = dict(channel_base=cb, channel_max=cm)
+    if config == "R":
+        kw.update(conv_kernel=1, use_radial_filters=True)
+    onet = O.make_synthesis("T", img_resolution=res, seed=0, **kw)
+    torch.manual_seed(0)
+    net = N.SynthesisNetwork(w_dim=512, img_resolution=res, img_channels=3, **kw)
+    net.load_state_dict(onet.state_dict())
+    torch.manual_seed(5)
+    ws = torch.randn(B, net.num_ws, 512)
+    ref, acts = onet(ws, return_activations=True)
+    layers = [getattr(onet, n) for n in onet.layer_names]
+    wsu = ws.unbind(1)
+
+    def style(i):
+        l = layers[i]
+        s = l.affine(wsu[i + 1])
+        if l.is_torgb:
+            return s * (1 / np.sqrt(l.in_channels * l.conv_kernel ** 2))
+        return s * s.square().mean(1, keepdim=True).rsqrt()
+
+    for impl in (1, 0):
+        net.set_option("conv_impl", impl)
+        for stop in range(-1, len(layers) - 1):
+            net.set_option("debug_stop", stop)
+            try:
+                net(ws.to(dev))
+                a = net.read_activation(B)
+                torch.cuda.synchronize()
+                want = acts[stop + 1] * style(stop + 1)[:, :, None, None]
+                print(f"net{res} impl{impl} after layer {stop}: shape {tuple(a.shape)} rel err {rel(a, want):.3e}", flush=True)
+            except Exception as ex:
+                print(f"net impl{impl} stop{stop} FAILED: {ex}", flush=True)
+                break
+        net.set_option("debug_stop", 1 << 30)
+        try:
+            out = net(ws.to(dev))
+            torch.cuda.synchronize()
+            pe = ((out.cpu() + 1) / 2).clamp(0, 1) - ((ref + 1) / 2).clamp(0, 1)
+            print(f"net{res} impl{impl} FINAL: rel {rel(out, ref):.3e} max-abs pixel err {pe.abs().max():.3e}  launches {net.last_launch_count()}", flush=True)
+            u8 = net(ws.to(dev), out_fmt="u8")
+            want8 = (((ref + 1) / 2).clamp(0, 1) * 255).round().permute(0, 2, 3, 1)
+            print("   u8 max diff", (u8.cpu().float() - want8).abs().max().item(), flush=True)
+        except Exception as ex:
+            print(f"net impl{impl} final FAILED: {ex}", flush=True)
+
+
+if __name__ == "__main__" and (len(sys.argv) > 1 and sys.argv[1] in ("net", "allnet")):
+    net_case()
+    print("net probe done", flush=True)

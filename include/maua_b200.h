@@ -128,8 +128,14 @@ int mb_net_last_launch_count(const mb_net* net);
  * parity tests; never used by the host facade). */
 int mb_net_set_conv_impl(mb_net* net, int impl);
 /* Test / tuning knobs: "conv_impl" (0|1), "conv_tile_w" (32|16), "flrelu_impl" (0 auto | 1 generic),
- * "debug_stop" (stop the forward after layer N; -1 = after the input layer; default: run all). */
+ * "debug_stop" (stop the forward after layer N; -1 = after the input layer; default: run all),
+ * "profile" (0 off | 1 record per-launch CUDA events of the last forward | 2 accumulate over forwards),
+ * "profile_reset" (drop accumulated records). */
 int mb_net_set_option(mb_net* net, const char* key, int value);
+/* Per-launch device times (CUDA events on the forward's stream) of the last forward run with option
+ * "profile"=1; call after synchronising the stream.  kind: 0 styles, 1 input, 2 modulated conv,
+ * 3 filtered_lrelu, 4 layout transpose, 5 torgb/output.  Returns the number of records (<= cap). */
+int mb_net_profile_read(mb_net* net, float* ms, int32_t* kind, int32_t* layer, int cap);
 /* Shape [C,H,W] of the activation mb_net_read_activation would return. */
 int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h, int32_t* w);
 

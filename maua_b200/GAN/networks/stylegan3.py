@@ -252,6 +252,9 @@ class SynthesisNetwork(torch.nn.Module):
             self._sync_params(device)
             ws32 = ws.detach().to(torch.float32).contiguous()
             B = ws32.shape[0]
+            if ws32.ndim == 3 and ws32.shape[1] > self.num_ws and ws32.shape[2] == self.w_dim:
+                # the reference's StyleGANMapper always emits num_ws=18 (wrappers/stylegan.py:18)
+                ws32 = ws32[:, :self.num_ws].contiguous()
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
             res = self.img_resolution
@@ -278,6 +281,13 @@ class SynthesisNetwork(torch.nn.Module):
         out = torch.empty(batch, c.value, h.value, w.value, device="cuda", dtype=torch.float32)
         _lib.check(lib.mb_net_read_activation(self._handle(), 0, batch, _lib.ptr(out), _lib.stream_ptr()))
         return out
+
+    def profile_read(self):
+        """[(kind, layer, ms)] of the last forward (needs set_option('profile', 1) and a stream sync)."""
+        cap = 8192
+        ms, kind, layer = (C.c_float * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)()
+        n = _lib.load().mb_net_profile_read(self._handle(), ms, kind, layer, cap)
+        return [(kind[i], layer[i], ms[i]) for i in range(n)]
 
     def last_launch_count(self):
         return _lib.load().mb_net_last_launch_count(self._handle())

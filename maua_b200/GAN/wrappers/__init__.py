@@ -1,0 +1,105 @@
+"""Generator-wrapper API: mirrors maua/GAN/wrappers/__init__.py:20-112 (MauaMapper / MauaSynthesizer /
+MauaGenerator.render / get_generator_class) without the reference's import-time global torch flags.
+
+``render`` keeps the reference contract -- ``inputs`` is a dict of ``[T, ...]`` tensors, frames come back
+as ``[B,3,H,W]`` in [0,1] -- but feeds batches from pinned host memory straight into the sm_100a
+synthesis pipeline instead of a DataLoader + fp16 module cast.
+"""
+from typing import Generator
+
+import torch
+
+
+class MauaMapper(torch.nn.Module):
+    def forward(self):
+        raise NotImplementedError()
+
+
+class MauaSynthesizer(torch.nn.Module):
+    _hook_handles = []
+
+    def forward(self):
+        raise NotImplementedError()
+
+    def change_output_resolution(self):
+        raise NotImplementedError()
+
+    def refresh_model_hooks(self):
+        for handle in self._hook_handles:
+            handle.remove()
+        self._hook_handles = []
+
+
+def _batches(inputs, batch_size, device):
+    """Pinned host staging + async H2D per batch (reference: TensorDataset/DataLoader, __init__.py:63-75)."""
+    keys = list(inputs.keys())
+    T = len(next(iter(inputs.values())))
+    staged = {}
+    for k in keys:
+        v = inputs[k]
+        if len(v) != T:
+            raise ValueError("all render inputs must share the leading (frame) dimension")
+        v = v.detach()
+        if not v.is_cuda:
+            v = v.cpu().contiguous()
+            if torch.cuda.is_available():
+                v = v.pin_memory()
+        staged[k] = v
+    for i in range(0, T, batch_size):
+        yield {k: staged[k][i:i + batch_size].to(device, non_blocking=True) for k in keys}
+
+
+class MauaGenerator(torch.nn.Module):
+    MapperCls = None
+    SynthesizerCls = None
+
+    def __init__(self, mapper_kwargs={}, synthesizer_kwargs={}) -> None:
+        super().__init__()
+        self.mapper = self.__class__.MapperCls(**mapper_kwargs)
+        self.synthesizer = self.__class__.SynthesizerCls(**synthesizer_kwargs)
+
+    def forward(self):
+        raise NotImplementedError()
+
+    def render(
+        self,
+        inputs,
+        batch_size=32,
+        postprocess_fn=lambda x: x,
+        device=torch.device("cuda" if torch.cuda.is_available() else "cpu"),
+        fp16=True,
+        batched=True,
+        verbose=False,
+    ) -> Generator[torch.Tensor, None, None]:
+        # fp16 is accepted for signature compatibility: every layer already runs fp16 operands with
+        # fp32 accumulation on the tensor cores (what the reference's force_half does, :78-86).
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("maua_b200 renders on CUDA only (no CPU fallback)")
+        self.to(device)
+        it = _batches(inputs, batch_size, device)
+        if verbose:
+            from tqdm import tqdm
+
+            it = tqdm(it, smoothing=0.8, unit_scale=batch_size, unit="img")
+        for batch in it:
+            frame_batch = self.synthesizer.forward(**batch).add(1).div(2).clamp(0, 1)
+            frame_batch = postprocess_fn(frame_batch)
+            if batched:
+                yield frame_batch
+            else:
+                for frame in frame_batch:
+                    yield frame[None]
+
+
+def get_generator_class(architecture: str) -> MauaGenerator:
+    if architecture == "stylegan3":
+        from .stylegan3 import StyleGAN3
+
+        return StyleGAN3
+    if architecture == "stylegan2":
+        from .stylegan2 import StyleGAN2
+
+        return StyleGAN2
+    else:
+        raise Exception(f"Architecture not found: {architecture}")

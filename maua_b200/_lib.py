@@ -56,6 +56,7 @@ _SIGNATURES = {
     "mb_net_last_launch_count": (C.c_int, [_P]),
     "mb_net_set_conv_impl": (C.c_int, [_P, C.c_int]),
     "mb_net_set_option": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "mb_net_profile_read": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]),
     "mb_net_activation_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_debug_read": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "mb_modulated_conv2d": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

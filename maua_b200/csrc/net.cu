@@ -82,6 +82,12 @@ struct mb_net {
     int flrelu_impl = 0;  // 0 = auto (register-blocked where supported), 1 = generic everywhere
     int debug_stop = 1 << 30;
     int last_launches = 0;
+    // optional per-launch timing (CUDA events on the forward's stream), see mb_net_profile_read
+    int profile = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    struct ProfRec { int kind, layer, ev0, ev1; };
+    std::vector<ProfRec> prof;
+    int ev_used = 0;
     // layout of the last forward (for read_activation)
     void* last_ws = nullptr;
     int last_batch = 0;
@@ -221,6 +227,14 @@ extern "C" int mb_init(int device) {
     return MB_OK;
 }
 
+// First use without mb_init(): adopt the thread's CURRENT device (the one the caller's PyTorch selected),
+// never force device 0 -- one process per GPU, ranks > 0 must stay on their own device.
+static int ensure_init() {
+    int dev = 0;
+    MB_CUDA(cudaGetDevice(&dev));
+    return mb_init(dev);
+}
+
 static int alloc_param(Param& p, std::initializer_list<int64_t> shape) {
     p.shape.assign(shape.begin(), shape.end());
     p.numel = 1;
@@ -232,7 +246,7 @@ static int alloc_param(Param& p, std::initializer_list<int64_t> shape) {
 extern "C" int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out) {
     MB_REQUIRE(cfg && out, "mb_sg3_create: null argument");
     if (g_device < 0) {
-        int r = mb_init(0);
+        int r = ensure_init();
         if (r != MB_OK) return r;
     }
     mb_net* net = new mb_net();
@@ -331,6 +345,7 @@ extern "C" void mb_net_destroy(mb_net* net) {
         if (L.wsqT) cudaFree(L.wsqT);
     }
     if (net->in_weightT) cudaFree(net->in_weightT);
+    for (cudaEvent_t e : net->ev_pool) cudaEventDestroy(e);
     delete net;
 }
 
@@ -456,6 +471,8 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     else if (k == "conv_tile_w") net->conv_tile_w = value == 16 ? 16 : 32;
     else if (k == "flrelu_impl") net->flrelu_impl = value;
     else if (k == "debug_stop") net->debug_stop = value;
+    else if (k == "profile") net->profile = value;
+    else if (k == "profile_reset") { net->prof.clear(); net->ev_used = 0; }
     else {
         set_error("mb_net_set_option: unknown option '%s'", key);
         return MB_EINVAL;
@@ -464,6 +481,22 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
 }
 
 extern "C" int mb_net_last_launch_count(const mb_net* net) { return net ? net->last_launches : 0; }
+
+/* Per-launch device times of the last forward run with option "profile"=1 (call after the stream has
+ * been synchronised).  kind: 0 styles, 1 input, 2 modulated conv, 3 filtered_lrelu, 4 layout
+ * transpose, 5 torgb/output.  Returns the number of records written (<= cap). */
+extern "C" int mb_net_profile_read(mb_net* net, float* ms, int32_t* kind, int32_t* layer, int cap) {
+    if (!net) return 0;
+    int n = 0;
+    for (const auto& rec : net->prof) {
+        if (n >= cap) break;
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, net->ev_pool[rec.ev0], net->ev_pool[rec.ev1]) != cudaSuccess) t = -1.0f;
+        ms[n] = t; kind[n] = rec.kind; layer[n] = rec.layer;
+        ++n;
+    }
+    return n;
+}
 
 // ---------------------------------------------------------------------------------------
 // forward
@@ -494,6 +527,26 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     const int nl = static_cast<int>(net->layers.size());
     int launches = 0;
     int r;
+    if (net->profile != 2) {  // 2 = accumulate records over several forwards until "profile_reset"
+        net->prof.clear();
+        net->ev_used = 0;
+    }
+    auto ev_next = [&]() -> int {
+        if (net->ev_used == static_cast<int>(net->ev_pool.size())) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            net->ev_pool.push_back(e);
+        }
+        cudaEventRecord(net->ev_pool[net->ev_used], stream);
+        return net->ev_used++;
+    };
+    int ev_prev = net->profile ? ev_next() : -1;
+    auto prof_mark = [&](int kind, int layer) {
+        if (!net->profile) return;
+        const int e = ev_next();
+        net->prof.push_back({kind, layer, ev_prev, e});
+        ev_prev = e;
+    };
 
     // 1. styles + demodulation coefficients of every layer
     {
@@ -521,6 +574,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         }
         if ((r = styles_launch(sa, stream)) != MB_OK) return r;
         launches += 1;
+        prof_mark(0, -1);
     }
     // 2. Fourier-feature input, pre-multiplied by layer 0's style
     {
@@ -545,6 +599,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ia.bandwidth = static_cast<float>(net->in_bw);
         if ((r = sg3_input_launch(ia, stream)) != MB_OK) return r;
         launches += 2;
+        prof_mark(1, -1);
     }
     net->last_ws = workspace;
     net->last_batch = B;
@@ -575,6 +630,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
                        "forward: unexpected ToRGB geometry");
             if ((r = torgb_out_launch(ta, stream)) != MB_OK) return r;
             launches += 1;
+            prof_mark(5, i);
             break;
         }
         ConvTcArgs ca;
@@ -592,6 +648,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         if (r != MB_OK) return r;
         launches += 1;
+        prof_mark(2, i);
 
         FlreluArgs fa;
         memset(&fa, 0, sizeof(fa));
@@ -613,6 +670,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         r = net->flrelu_impl == 1 ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
         if (r != MB_OK) return r;
         launches += 1;
+        prof_mark(3, i);
         net->last_act = P;
         net->last_act_nhwc = false;
         net->last_act_c = g.out_channels;
@@ -624,6 +682,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
                                       cpad8(g.out_channels), stream);
             if (r != MB_OK) return r;
             launches += 1;
+            prof_mark(4, i);
         }
     }
     net->last_launches = launches;
@@ -655,7 +714,7 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
     MB_REQUIRE(x && w && s && y, "mb_modulated_conv2d: null argument");
     MB_REQUIRE(k == 1 || k == 3, "mb_modulated_conv2d: kernel size %d unsupported (1 or 3)", k);
     if (g_device < 0) {
-        int r = mb_init(0);
+        int r = ensure_init();
         if (r != MB_OK) return r;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -700,7 +759,7 @@ extern "C" int mb_filtered_lrelu(const float* x, const float* fu, const float* f
     MB_REQUIRE((fu != nullptr) == (up_taps > 1) && (fd != nullptr) == (down_taps > 1),
                "mb_filtered_lrelu: filter pointer / tap count mismatch");
     if (g_device < 0) {
-        int r = mb_init(0);
+        int r = ensure_init();
         if (r != MB_OK) return r;
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -1,0 +1,132 @@
+"""Parity of the whole synthesis path (through mb_net_forward) against the CPU oracle.
+Tolerance (BASELINE.json north_star): <= 1e-3 max-abs on fp32 pixels, pixels = clamp((x+1)/2, 0, 1)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sg3 as O
+
+pytestmark = pytest.mark.gpu
+PIX_TOL = 1e-3
+
+
+def pix(x):
+    return ((x.float().cpu() + 1) / 2).clamp(0, 1)
+
+
+def make_pair(config, res, seed=0, **kw):
+    from maua_b200.GAN.networks import stylegan3 as N
+
+    extra = dict(O.SG3_R_KWARGS) if config == "R" else {}
+    extra.update(kw)
+    onet = O.make_synthesis("T", img_resolution=res, seed=seed, **extra)
+    torch.manual_seed(seed)
+    net = N.SynthesisNetwork(w_dim=512, img_resolution=res, img_channels=3, **extra)
+    net.load_state_dict(onet.state_dict())
+    return onet, net
+
+
+@pytest.mark.parametrize("config,kw", [("T", dict(channel_base=8192, channel_max=128)),
+                                       ("R", dict(channel_base=8192, channel_max=160))])
+def test_small_network_layers_and_pixels(cuda, config, kw):
+    onet, net = make_pair(config, 256, **kw)
+    torch.manual_seed(5)
+    ws = torch.randn(2, net.num_ws, 512)
+    ref, acts = onet(ws, return_activations=True)
+    layers = [getattr(onet, n) for n in onet.layer_names]
+    wsu = ws.unbind(1)
+
+    def style(i):
+        s = layers[i].affine(wsu[i + 1])
+        if layers[i].is_torgb:
+            return s * (1 / np.sqrt(layers[i].in_channels * layers[i].conv_kernel ** 2))
+        return s * s.square().mean(1, keepdim=True).rsqrt()
+
+    for stop in range(-1, len(layers) - 1):
+        net.set_option("debug_stop", stop)
+        net(ws.to(cuda))
+        got = net.read_activation(2).cpu()
+        want = acts[stop + 1] * style(stop + 1)[:, :, None, None]
+        rel = float((got - want).abs().max() / want.square().mean().sqrt())
+        assert rel < 4e-2, (stop, rel)
+    net.set_option("debug_stop", 1 << 30)
+    out = net(ws.to(cuda))
+    assert float((pix(out) - pix(ref)).abs().max()) <= PIX_TOL
+    u8 = net(ws.to(cuda), out_fmt="u8").cpu()
+    want8 = (pix(ref) * 255).round().permute(0, 2, 3, 1)
+    assert float((u8.float() - want8).abs().max()) <= 1.0
+
+
+def test_golden_fixtures(cuda):
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "sg3_tiny.pt"))
+    cases = {"T64": ("T", dict(img_resolution=64, channel_base=1024, channel_max=32)),
+             "R64": ("R", dict(img_resolution=64, channel_base=2048, channel_max=48))}
+    for name, (config, kw) in cases.items():
+        kw = dict(kw)
+        res = kw.pop("img_resolution")
+        _, net = make_pair(config, res, seed=3, **kw)
+        out = net(gold[name]["ws"].to(cuda))
+        assert float((pix(out) - pix(gold[name]["img"])).abs().max()) <= PIX_TOL + 5e-4  # golden stored as fp16
+
+
+def test_full_size_frame_matches_oracle(cuda):
+    """BASELINE.json configs[1] network (StyleGAN3-T 1024^2, random init, seed 0), one frame."""
+    from maua_b200.workload import c2_latents
+
+    onet, net = make_pair("T", 1024)
+    lat, _ = c2_latents(net.num_ws)
+    ws = lat[100:101]
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = onet(ws)
+    out = net(ws.to(cuda))
+    err = float((pix(out) - pix(ref)).abs().max())
+    assert err <= PIX_TOL, err
+    assert out.shape == (1, 3, 1024, 1024)
+
+
+def test_batch_invariance_and_determinism(cuda):
+    _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    torch.manual_seed(9)
+    ws = torch.randn(3, net.num_ws, 512, device=cuda)
+    a = net(ws).clone()
+    b = net(ws).clone()
+    assert torch.equal(a, b)
+    single = torch.cat([net(ws[i:i + 1]).clone() for i in range(3)])
+    assert torch.equal(a, single)
+
+
+def test_user_transform_matches_oracle(cuda):
+    onet, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    m = torch.tensor([[0.9, 0.3, 0.05], [-0.3, 0.9, -0.02], [0.0, 0.0, 1.0]])
+    onet.input.transform.copy_(m)
+    net.input.transform.copy_(m)
+    torch.manual_seed(4)
+    ws = torch.randn(1, net.num_ws, 512)
+    assert float((pix(net(ws.to(cuda))) - pix(onet(ws))).abs().max()) <= PIX_TOL
+
+
+def test_render_api(cuda):
+    from maua_b200.GAN.wrappers import get_generator_class
+
+    torch.manual_seed(0)
+    G = get_generator_class("stylegan3")(model_file=None)
+    torch.manual_seed(1)
+    lat = torch.randn(3, 16, 512)
+    frames = list(G.render({"latents": lat}, batch_size=2, device=cuda))
+    assert [tuple(f.shape) for f in frames] == [(2, 3, 1024, 1024), (1, 3, 1024, 1024)]
+    allf = torch.cat(frames)
+    assert float(allf.min()) >= 0 and float(allf.max()) <= 1
+    direct = G.synthesizer(latents=lat.to(cuda)).add(1).div(2).clamp(0, 1)
+    assert torch.equal(allf, direct)
+    assert G.synthesizer.G_synth.last_launch_count() > 30
+
+
+def test_errors_are_python_exceptions(cuda):
+    _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    with pytest.raises(ValueError):
+        net(torch.randn(1, 3, 512, device=cuda))
+    from maua_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.modulated_conv2d(torch.randn(1, 4, 8, 8, device=cuda), torch.randn(4, 4, 5, 5, device=cuda), torch.randn(1, 4, device=cuda))

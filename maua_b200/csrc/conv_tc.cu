@@ -46,6 +46,7 @@ struct KArgs {
     int B, Cin, Cout, Hout, Wout, Wp_out, ksz, nCC;
     int tiles_m, tiles_w, tiles_h, total_tiles;
     const float* d;  // [B][Cout] or nullptr
+    const float* bias;  // [Cout] or nullptr
     __half* y;
     long long plane_out;  // Hout * Wp_out
     int* dbg;             // debug words (mapped host memory) or nullptr
@@ -172,6 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const int co = mt * kTileM + q * 32 + lane;
             const bool co_ok = co < a.Cout;
             const float scale = (co_ok && a.d) ? a.d[b * a.Cout + co] : 1.0f;
+            const float bias = (co_ok && a.bias) ? a.bias[co] : 0.0f;
             __half* yplane = a.y + (static_cast<long long>(b) * a.Cout + (co_ok ? co : 0)) * a.plane_out;
 
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
@@ -190,14 +192,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         const int w = w0 + n % TW;
                         if (h < a.Hout && w < a.Wp_out) {
                             uint4 pk;
-                            __half2 h0v = __floats2half2_rn(__uint_as_float(v[g * 8 + 0]) * scale,
-                                                            __uint_as_float(v[g * 8 + 1]) * scale);
-                            __half2 h1v = __floats2half2_rn(__uint_as_float(v[g * 8 + 2]) * scale,
-                                                            __uint_as_float(v[g * 8 + 3]) * scale);
-                            __half2 h2v = __floats2half2_rn(__uint_as_float(v[g * 8 + 4]) * scale,
-                                                            __uint_as_float(v[g * 8 + 5]) * scale);
-                            __half2 h3v = __floats2half2_rn(__uint_as_float(v[g * 8 + 6]) * scale,
-                                                            __uint_as_float(v[g * 8 + 7]) * scale);
+                            __half2 h0v = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 0]), scale, bias),
+                                                            fmaf(__uint_as_float(v[g * 8 + 1]), scale, bias));
+                            __half2 h1v = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 2]), scale, bias),
+                                                            fmaf(__uint_as_float(v[g * 8 + 3]), scale, bias));
+                            __half2 h2v = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 4]), scale, bias),
+                                                            fmaf(__uint_as_float(v[g * 8 + 5]), scale, bias));
+                            __half2 h3v = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 6]), scale, bias),
+                                                            fmaf(__uint_as_float(v[g * 8 + 7]), scale, bias));
                             pk.x = *reinterpret_cast<uint32_t*>(&h0v);
                             pk.y = *reinterpret_cast<uint32_t*>(&h1v);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2v);
@@ -280,7 +282,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.tiles_w = ceil_div(a.Wout, tw);
     a.tiles_h = ceil_div(a.Hout, th);
     a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
-    a.d = p.d; a.y = p.y;
+    a.d = p.d; a.bias = p.bias; a.y = p.y;
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
     a.dbg = debug_words_device();
 

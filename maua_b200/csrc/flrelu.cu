@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(256) flrelu_generic_kernel(FlreluArgs a, int t
 
 }  // namespace
 
-int flrelu_sep_launch(const FlreluArgs& a, cudaStream_t stream);  // flrelu_sep.cu
+int flrelu_sep_launch(const FlreluArgs& a, cudaStream_t stream);  // flrelu_sep.cu (CUDA cores)
 bool flrelu_sep_supported(const FlreluArgs& a);
+int flrelu_mma_launch(const FlreluArgs& a, cudaStream_t stream);  // flrelu_mma.cu (tensor cores)
+bool flrelu_mma_supported(const FlreluArgs& a);
 
 static int flrelu_generic_launch(const FlreluArgs& a, cudaStream_t stream) {
     MB_REQUIRE(a.up >= 1 && a.down >= 1 && a.up_taps >= 1 && a.up_taps <= 32 && a.down_taps >= 1 &&
@@ -169,12 +171,14 @@ static int flrelu_generic_launch(const FlreluArgs& a, cudaStream_t stream) {
     return MB_OK;
 }
 
-int flrelu_launch(const FlreluArgs& a, cudaStream_t stream) {
+// impl: 0 = best available (tensor-core chain, else generic), 1 = generic loops, 2 = CUDA-core polyphase kernel
+int flrelu_launch_impl(const FlreluArgs& a, int impl, cudaStream_t stream) {
     if (a.B == 0 || a.C == 0) return MB_OK;
-    if (flrelu_sep_supported(a)) return flrelu_sep_launch(a, stream);
+    if (impl == 0 && flrelu_mma_supported(a)) return flrelu_mma_launch(a, stream);
+    if (impl == 2 && flrelu_sep_supported(a)) return flrelu_sep_launch(a, stream);
     return flrelu_generic_launch(a, stream);
 }
 
-int flrelu_generic_launch_public(const FlreluArgs& a, cudaStream_t stream) { return flrelu_generic_launch(a, stream); }
+int flrelu_launch(const FlreluArgs& a, cudaStream_t stream) { return flrelu_launch_impl(a, 0, stream); }
 
 }  // namespace mb

@@ -1,0 +1,428 @@
+// filtered_lrelu on the tensor cores: the four separable FIR passes of a StyleGAN3 layer
+// (up-H, up-V, [lrelu], down-H, down-V) as a register-resident chain of banded Toeplitz GEMMs.
+//
+// Why: on CUDA cores this op needs ~72 useful FMAs (154 issued instructions) per output pixel and
+// is issue-bound at ~5 % of HBM bandwidth (profiles/r1_ncu_v1_first_path.md).  A 1-D FIR is a
+// multiplication by a banded constant matrix, so each pass is D = A_const * B with the filter as the
+// A operand of mma.sync.m16n8k16 (fp16 in, fp32 accumulate).  The accumulator fragment of one pass is
+// bit-for-bit the B fragment layout of the next pass *transposed*, which is exactly what a separable
+// 2-D filter needs (pass k contracts the axis pass k-1 left untouched):
+//     S1  A1^T[Jx][iy] = sum_ix Uh[Jx][ix] X[iy][ix]        (B from shared memory, X = conv output tile)
+//     S2  T   [Jy][Jx] = sum_iy Uv[Jy][iy] A1^T[Jx][iy]     -> lrelu * gain, clamp
+//     S3  O3^T[ox][Jy] = sum_Jx Dh[ox][Jx] T[Jy][Jx]
+//     S4  Out [oy][ox] = sum_Jy Dv[oy][Jy] O3^T[ox][Jy]
+// so one warp carries a 32x32 output tile of one channel from the fp16 input tile to the fp16 output
+// without any intermediate leaving the register file (no shared-memory round trips, no block barriers).
+// The (2*32+10)^2 upsampled intermediate is produced and consumed in five 16-row strips.
+// Filter taps are split hi+lo in fp16 (two MMAs per block): rounding the taps to a single fp16 is a
+// systematic error that costs up to 1e-3 in the final pixels (scratch/emul_mma_fir.py), the split
+// brings the constant operand to ~2^-22.  Intermediates are rounded to fp16 between passes (measured
+// harmless: 2.8e-4 vs 2.7e-4 max pixel error end to end).
+//
+// Index conventions as in flrelu.cu.  Supported: down=2/12 taps with up=2/12 taps or up=4/24 taps,
+// separable filters (every non-ToRGB layer of StyleGAN3-T and the critically sampled layers of -R).
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb {
+namespace {
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ int fdiv(int a, int b) {
+    int q = a / b;
+    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
+    return q;
+}
+
+constexpr int kOT = 32;      // output tile edge per warp
+constexpr int kStrips = 5;   // 16-row strips of the intermediate (2*32+10 = 74 -> 80 rows)
+constexpr int kJB = 10;      // n8 blocks across the intermediate (80 columns)
+constexpr int kMB = 5;       // m16 blocks across the intermediate
+constexpr int kXP = 56;      // shared-memory row pitch of the input tile, in halfs (conflict-free B loads)
+constexpr int kWarps = 8;
+
+template <int UP>
+struct MC {
+    static constexpr int NIB = (UP == 2) ? 6 : 4;   // n8 blocks of input rows/cols a tile needs
+    static constexpr int IYT = NIB * 8;
+    static constexpr int NVAR = (UP == 2) ? 1 : 2;   // distinct up-filter fragments (window offset 0 / 4)
+    static constexpr int NFRAG = (NVAR + 3) * 2;     // hi/lo of NVAR up fragments and 3 down fragments
+    static constexpr int XBYTES = IYT * kXP * 2;
+    static constexpr int SMEM = kWarps * 2 * XBYTES;  // double-buffered input tile per warp
+    __host__ __device__ static constexpr int wblk(int j) { return UP == 2 ? j : (j >> 1); }
+    __host__ __device__ static constexpr int var(int j) { return UP == 2 ? 0 : (j & 1); }
+};
+
+struct MmaParams {
+    const __half* x;
+    const float* bias;
+    const float* scale;
+    __half* y;
+    const uint4* frags;  // [NFRAG][32]
+    int C, Hin, Win, Wp_in, Hout, Wout, Wp_out, px0, py0, tiles_x, tiles_y, e, tpw;
+    float gain, slope, clamp;
+};
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One warp = a run of `tpw` consecutive 32x32 output tiles of one (b, c) plane; the input tile of
+// tile t+1 is fetched with cp.async (zero-filled outside the image) while tile t is in the MMA chain.
+template <int UP>
+__global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaParams p) {
+    using K = MC<UP>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    __half* Xbuf = reinterpret_cast<__half*>(smem_raw + warp * 2 * K::XBYTES);
+
+    const int ntiles = p.tiles_x * p.tiles_y;
+    const int tile0 = (blockIdx.x * kWarps + warp) * p.tpw;
+    if (tile0 >= ntiles) return;  // warps are independent: no block-level barrier below
+    const int tile_end = min(tile0 + p.tpw, ntiles);
+    const int c = blockIdx.y, b = blockIdx.z;
+    const __half* xp = p.x + (static_cast<long long>(b) * p.C + c) * p.Hin * p.Wp_in;
+
+    // constant Toeplitz fragments (hi, lo)
+    uint4 AU[K::NVAR][2], AD[3][2];
+#pragma unroll
+    for (int v = 0; v < K::NVAR; ++v) {
+        AU[v][0] = p.frags[(v * 2 + 0) * 32 + lane];
+        AU[v][1] = p.frags[(v * 2 + 1) * 32 + lane];
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        AD[s][0] = p.frags[((K::NVAR + s) * 2 + 0) * 32 + lane];
+        AD[s][1] = p.frags[((K::NVAR + s) * 2 + 1) * 32 + lane];
+    }
+    const float g1 = p.gain, g2 = p.gain * p.slope, cl = p.clamp;
+    const float oscale = p.scale ? p.scale[b * p.C + c] : 1.0f;
+    __half* yp = p.y + (static_cast<long long>(b) * p.C + c) * p.Hout * p.Wp_out;
+
+    // first input sample each axis needs: n = ceil((2*o0 - pad)/UP), shifted down by e so it is even;
+    // rows are loaded from the 16-byte aligned column ixa <= ix0.
+    auto origin = [&](int tile, int& ox0, int& oy0, int& ix0, int& iy0) {
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        ox0 = tx * kOT;
+        oy0 = ty * kOT;
+        ix0 = -fdiv(-(2 * ox0 - p.px0), UP) - p.e;
+        iy0 = -fdiv(-(2 * oy0 - p.py0), UP) - p.e;
+    };
+    auto load_tile = [&](int tile, __half* X) {
+        int ox0, oy0, ix0, iy0;
+        origin(tile, ox0, oy0, ix0, iy0);
+        const int ixa = fdiv(ix0, 8) * 8;
+        if (p.bias == nullptr) {
+            for (int idx = lane; idx < K::IYT * 7; idx += 32) {
+                const int row = idx / 7, ch = idx - row * 7;
+                const int iy = iy0 + row, ixc = ixa + ch * 8;
+                int bytes = 0;
+                const __half* src = xp;
+                if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
+                    bytes = min(8, p.Win - ixc) * 2;
+                    src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
+                }
+                cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
+            }
+        } else {  // op-level API with a bias: synchronous path, bias added in fp32 and re-rounded
+            const float bias = p.bias[c];
+            for (int idx = lane; idx < K::IYT * 7; idx += 32) {
+                const int row = idx / 7, ch = idx - row * 7;
+                const int iy = iy0 + row, ixc = ixa + ch * 8;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
+                    v = *reinterpret_cast<const uint4*>(xp + static_cast<long long>(iy) * p.Wp_in + ixc);
+                    __half* hv = reinterpret_cast<__half*>(&v);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        hv[i] = (ixc + i >= p.Win) ? __float2half_rn(0.0f) : __float2half_rn(__half2float(hv[i]) + bias);
+                }
+                *reinterpret_cast<uint4*>(X + row * kXP + ch * 8) = v;
+            }
+        }
+        cp_async_commit();
+    };
+
+    load_tile(tile0, Xbuf);
+    int buf = 0;
+    for (int tile = tile0; tile < tile_end; ++tile, buf ^= 1) {
+        const __half* X = Xbuf + buf * (K::XBYTES / 2);
+        if (tile + 1 < tile_end) {
+            load_tile(tile + 1, Xbuf + (buf ^ 1) * (K::XBYTES / 2));
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        int ox0, oy0, ix0, iy0;
+        origin(tile, ox0, oy0, ix0, iy0);
+        const int dx = ix0 - fdiv(ix0, 8) * 8;  // even by construction
+
+        uint32_t P1a[kMB][2], P1b[kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers
+        int have_a = -1, have_b = -1;       // compile-time constants after unrolling
+
+        auto stage1 = [&](int blk, uint32_t (&P)[kMB][2]) {
+#pragma unroll
+            for (int m = 0; m < kMB; ++m) {
+                const int w0 = K::wblk(m) * 8;
+                const __half* src = X + (blk * 8 + g) * kXP + dx + w0 + 2 * tig;
+                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + 8);
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(acc, AU[K::var(m)][0], b0, b1);
+                mma16816(acc, AU[K::var(m)][1], b0, b1);
+                P[m][0] = pack2(acc[0], acc[1]);
+                P[m][1] = pack2(acc[2], acc[3]);
+            }
+        };
+
+        float OUT[2][4][4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) OUT[i][n][k] = 0.0f;
+
+#pragma unroll
+        for (int j = 0; j < kStrips; ++j) {
+            // ---- S1 for the two input-row blocks this strip's window covers
+            const int wb = K::wblk(j);
+            if (have_a != wb) {
+                if (have_b == wb) {
+#pragma unroll
+                    for (int m = 0; m < kMB; ++m) { P1a[m][0] = P1b[m][0]; P1a[m][1] = P1b[m][1]; }
+                } else {
+                    stage1(wb, P1a);
+                }
+                have_a = wb;
+                have_b = -1;
+            }
+            if (have_b != wb + 1) {
+                stage1(wb + 1, P1b);
+                have_b = wb + 1;
+            }
+            // ---- S2 (+activation): T[16 rows of strip j][80 cols], packed as B operands of S3
+            uint32_t P2[kJB][2];
+#pragma unroll
+            for (int nb = 0; nb < kJB; ++nb) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                mma16816(acc, AU[K::var(j)][0], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
+                mma16816(acc, AU[K::var(j)][1], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float t1 = acc[k] * g1, t2 = acc[k] * g2;
+                    acc[k] = fminf(fmaxf(fmaxf(t1, t2), -cl), cl);
+                }
+                P2[nb][0] = pack2(acc[0], acc[1]);
+                P2[nb][1] = pack2(acc[2], acc[3]);
+            }
+            // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
+            uint32_t P3[4][2];
+#pragma unroll
+            for (int mo = 0; mo < 2; ++mo) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        const int nb = 4 * mo + 2 * s;
+                        mma16816(acc, AD[s][0], P2[nb][h], P2[nb + 1][h]);
+                        mma16816(acc, AD[s][1], P2[nb][h], P2[nb + 1][h]);
+                    }
+                    P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
+                    P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+                }
+            }
+            // ---- S4: strip j is k-step s = j - 2i of output row block i
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int s = j - 2 * i;
+                if (s >= 0 && s < 3) {
+#pragma unroll
+                    for (int no = 0; no < 4; ++no) {
+                        mma16816(OUT[i][no], AD[s][0], P3[no][0], P3[no][1]);
+                        mma16816(OUT[i][no], AD[s][1], P3[no][0], P3[no][1]);
+                    }
+                }
+            }
+        }
+
+        // ---- store: * next-layer style, fp16, two adjacent columns per thread
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int no = 0; no < 4; ++no) {
+                const int ox = ox0 + no * 8 + 2 * tig;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int oy = oy0 + i * 16 + hh * 8 + g;
+                    if (oy < p.Hout && ox < p.Wout) {
+                        const uint32_t v = pack2(OUT[i][no][hh * 2 + 0] * oscale, OUT[i][no][hh * 2 + 1] * oscale);
+                        // Wp_out is even and ox is even: the pair never straddles the padded row
+                        *reinterpret_cast<uint32_t*>(yp + static_cast<long long>(oy) * p.Wp_out + ox) = v;
+                    }
+                }
+            }
+        }
+        __syncwarp();  // every lane is done reading X[buf] before the next iteration's prefetch overwrites it
+    }
+}
+
+// ---- host: constant fragments -------------------------------------------------------------------
+struct FragCache {
+    int up = 0, rho = -1, e = -1;
+    float fu[32], fd[12];
+    uint4* dev = nullptr;
+};
+FragCache g_cache[8];
+int g_cache_n = 0;
+
+inline uint16_t f2h_bits(float f) {
+    __half h = __float2half_rn(f);
+    uint16_t b;
+    memcpy(&b, &h, 2);
+    return b;
+}
+inline float h2f_bits(uint16_t b) {
+    __half h;
+    memcpy(&h, &b, 2);
+    return __half2float(h);
+}
+
+// A[a][c] (16x16) -> per-lane registers in mma.m16n8k16 A-fragment order, hi and lo parts
+void emit_fragment(const float (&A)[16][16], uint4* hi, uint4* lo) {
+    for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, tig = lane & 3;
+        const int rows[4] = {g, g + 8, g, g + 8};
+        const int cols[4] = {2 * tig, 2 * tig, 2 * tig + 8, 2 * tig + 8};
+        uint32_t rh[4], rl[4];
+        for (int r = 0; r < 4; ++r) {
+            uint16_t h0 = f2h_bits(A[rows[r]][cols[r]]), h1 = f2h_bits(A[rows[r]][cols[r] + 1]);
+            uint16_t l0 = f2h_bits(A[rows[r]][cols[r]] - h2f_bits(h0)), l1 = f2h_bits(A[rows[r]][cols[r] + 1] - h2f_bits(h1));
+            rh[r] = static_cast<uint32_t>(h0) | (static_cast<uint32_t>(h1) << 16);
+            rl[r] = static_cast<uint32_t>(l0) | (static_cast<uint32_t>(l1) << 16);
+        }
+        hi[lane] = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+        lo[lane] = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+    }
+}
+
+template <int UP>
+int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
+    using K = MC<UP>;
+    for (int i = 0; i < g_cache_n; ++i) {
+        FragCache& fc = g_cache[i];
+        if (fc.up == UP && fc.rho == rho && fc.e == e && memcmp(fc.fu, a.fu, sizeof(float) * 6 * UP) == 0 &&
+            memcmp(fc.fd, a.fd, sizeof(float) * 12) == 0) {
+            *out = fc.dev;
+            return MB_OK;
+        }
+    }
+    std::vector<uint4> host(K::NFRAG * 32);
+    constexpr int UT = 6 * UP;
+    for (int v = 0; v < K::NVAR; ++v) {
+        float A[16][16] = {};
+        const int off = (UP == 2) ? 0 : 4 * v;
+        for (int r = 0; r < 16; ++r) {
+            // ceil((r - rho) / UP) and the phase of row r
+            const int num = r - rho;
+            int n = num / UP;
+            if (num % UP != 0 && num > 0) ++n;  // ceil for positive, trunc == ceil for negative
+            const int ph = UP * n - num;
+            for (int m = 0; m < 6; ++m) {
+                const int col = off + e + n + m;
+                if (col >= 0 && col < 16) A[r][col] = static_cast<float>(UP) * a.fu[UT - 1 - ph - UP * m];
+            }
+        }
+        emit_fragment(A, &host[(v * 2 + 0) * 32], &host[(v * 2 + 1) * 32]);
+    }
+    for (int s = 0; s < 3; ++s) {
+        float A[16][16] = {};
+        for (int r = 0; r < 16; ++r)
+            for (int col = 0; col < 16; ++col) {
+                const int k = 16 * s + col - 2 * r;
+                if (k >= 0 && k < 12) A[r][col] = a.fd[11 - k];
+            }
+        emit_fragment(A, &host[((K::NVAR + s) * 2 + 0) * 32], &host[((K::NVAR + s) * 2 + 1) * 32]);
+    }
+    FragCache& fc = g_cache[g_cache_n % 8];
+    if (fc.dev) cudaFree(fc.dev);
+    MB_CUDA(cudaMalloc(&fc.dev, host.size() * sizeof(uint4)));
+    MB_CUDA(cudaMemcpy(fc.dev, host.data(), host.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+    fc.up = UP; fc.rho = rho; fc.e = e;
+    memcpy(fc.fu, a.fu, sizeof(float) * 6 * UP);
+    memcpy(fc.fd, a.fd, sizeof(float) * 12);
+    ++g_cache_n;
+    *out = fc.dev;
+    return MB_OK;
+}
+
+template <int UP>
+int launch(const FlreluArgs& a, cudaStream_t stream) {
+    using K = MC<UP>;
+    // layer constants: rho = pad mod UP (phase of the first intermediate sample of a tile),
+    // e = parity of ceil(-pad/UP) (makes the first input column of every tile even)
+    const int rho = ((a.px0 % UP) + UP) % UP;
+    int q = (-a.px0) / UP;
+    if ((-a.px0) % UP != 0 && (-a.px0) > 0) ++q;  // ceil(-pad/UP)
+    const int e = ((q % 2) + 2) % 2;
+    uint4* frags = nullptr;
+    int r = build_frags<UP>(a, rho, e, &frags);
+    if (r != MB_OK) return r;
+    MmaParams p;
+    p.x = a.x; p.bias = a.bias; p.scale = a.scale; p.y = a.y; p.frags = frags;
+    p.C = a.C; p.Hin = a.Hin; p.Win = a.Win; p.Wp_in = a.Wp_in; p.Hout = a.Hout; p.Wout = a.Wout; p.Wp_out = a.Wp_out;
+    p.px0 = a.px0; p.py0 = a.py0;
+    p.tiles_x = ceil_div(a.Wout, kOT); p.tiles_y = ceil_div(a.Hout, kOT);
+    p.e = e;
+    const int ntiles = p.tiles_x * p.tiles_y;
+    p.tpw = ntiles < 64 ? 1 : (ntiles < 256 ? 2 : 4);
+    p.gain = a.gain; p.slope = a.slope; p.clamp = a.clamp >= 0.0f ? a.clamp : 3.0e38f;
+    static bool attr_done = false;
+    if (!attr_done) {
+        MB_CUDA(cudaFuncSetAttribute(flrelu_mma_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        attr_done = true;
+    }
+    dim3 grid(ceil_div(ntiles, kWarps * p.tpw), a.C, a.B);
+    flrelu_mma_kernel<UP><<<grid, kWarps * 32, K::SMEM, stream>>>(p);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+}  // namespace
+
+bool flrelu_mma_supported(const FlreluArgs& a) {
+    if (a.fd_2d || a.down != 2 || a.down_taps != 12) return false;
+    if (!((a.up == 2 && a.up_taps == 12) || (a.up == 4 && a.up_taps == 24))) return false;
+    if (a.px0 != a.py0) return false;
+    if (a.C > 65535 || a.B > 65535) return false;
+    if (a.slope < 0.0f || a.slope > 1.0f || a.gain <= 0.0f) return false;  // lrelu written as max(t*g, t*g*slope)
+    return true;
+}
+
+int flrelu_mma_launch(const FlreluArgs& a, cudaStream_t stream) {
+    return a.up == 2 ? launch<2>(a, stream) : launch<4>(a, stream);
+}
+
+}  // namespace mb

@@ -21,6 +21,7 @@ struct ConvTcArgs {
     const __half* x;    // channels-last [B][Hin][Win][Cp_in], already multiplied by the style
     const __half* wpk;  // packed weights [round_up(Cout,128)][k*k*nCC*64], see pack_weights
     const float* d;     // [B][Cout] demodulation coefficients or nullptr
+    const float* bias;  // [Cout] added after demodulation (the layer bias filtered_lrelu would add) or nullptr
     __half* y;          // planar [B][Cout][Hin+k-1][Wp_out]
     int B, Cin, Cout, Hin, Win, Cp_in, Wp_out, ksz;
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
@@ -114,5 +115,7 @@ struct FlreluArgs {
     int num_sms;
 };
 int flrelu_launch(const FlreluArgs& a, cudaStream_t stream);
+// impl: 0 = best available (tensor-core chain), 1 = generic loops, 2 = CUDA-core polyphase kernel
+int flrelu_launch_impl(const FlreluArgs& a, int impl, cudaStream_t stream);
 
 }  // namespace mb

@@ -47,7 +47,6 @@ static int* g_dbg_host = nullptr;
 static int* g_dbg_dev = nullptr;
 int* debug_words_device() { return g_dbg_dev; }
 
-int flrelu_generic_launch_public(const FlreluArgs& a, cudaStream_t stream);
 
 }  // namespace mb
 
@@ -79,7 +78,7 @@ struct mb_net {
     bool finalized = false;
     int conv_impl = 0;
     int conv_tile_w = 32;
-    int flrelu_impl = 0;  // 0 = auto (register-blocked where supported), 1 = generic everywhere
+    int flrelu_impl = 0;  // 0 = tensor-core chain where supported, 1 = generic loops, 2 = CUDA-core polyphase kernel
     int debug_stop = 1 << 30;
     int last_launches = 0;
     // optional per-launch timing (CUDA events on the forward's stream), see mb_net_profile_read
@@ -637,6 +636,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ca.x = X;
         ca.wpk = L.wpk;
         ca.d = dco + wl.d_l[i];
+        ca.bias = L.bias.dev;  // the layer bias is added in the conv epilogue (single fp16 rounding)
         ca.y = Y;
         ca.B = B; ca.Cin = g.in_channels; ca.Cout = g.out_channels;
         ca.Hin = g.in_size; ca.Win = g.in_size; ca.Cp_in = cpad8(g.in_channels);
@@ -653,7 +653,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         FlreluArgs fa;
         memset(&fa, 0, sizeof(fa));
         fa.x = Y;
-        fa.bias = L.bias.dev;
+        fa.bias = nullptr;
         fa.scale = styles + wl.style_l[i + 1];
         fa.y = P;
         memcpy(fa.fu, L.fu.data(), sizeof(fa.fu));
@@ -667,7 +667,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         fa.gain = sqrtf(2.0f); fa.slope = 0.2f;
         fa.clamp = static_cast<float>(net->cfg.conv_clamp);
         fa.num_sms = g_num_sms;
-        r = net->flrelu_impl == 1 ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
+        r = flrelu_launch_impl(fa, net->flrelu_impl, stream);
         if (r != MB_OK) return r;
         launches += 1;
         prof_mark(3, i);
@@ -734,7 +734,7 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
     if (r == MB_OK) r = modulate_to_nhwc_launch(x, sn, 1.0f, xh, B, Cin, H, W, Cp, stream);
     if (r == MB_OK) {
         ConvTcArgs ca;
-        ca.x = xh; ca.wpk = wpk; ca.d = d; ca.y = yh;
+        ca.x = xh; ca.wpk = wpk; ca.d = d; ca.bias = nullptr; ca.y = yh;
         ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
         ca.tile_w = (impl == 2) ? 16 : 32;
         ca.num_sms = g_num_sms;
@@ -784,7 +784,7 @@ extern "C" int mb_filtered_lrelu(const float* x, const float* fu, const float* f
     fa.gain = gain; fa.slope = slope; fa.clamp = clamp;
     fa.num_sms = g_num_sms;
     const char* impl = getenv("MB_FLRELU_IMPL");
-    if (r == MB_OK) r = (impl && atoi(impl) == 1) ? flrelu_generic_launch_public(fa, stream) : flrelu_launch(fa, stream);
+    if (r == MB_OK) r = flrelu_launch_impl(fa, impl ? atoi(impl) : 0, stream);
     if (r == MB_OK) r = half_to_float_launch(yh, y, B, C, Ho, Wo, Wpo, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
     cudaFree(xh); cudaFree(yh);

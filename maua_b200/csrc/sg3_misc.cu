@@ -108,6 +108,7 @@ __global__ void conv_simt_kernel(ConvTcArgs p, int Hout, int Wout) {
             }
         }
         if (p.d) acc *= p.d[b * p.Cout + co];
+        if (p.bias) acc += p.bias[co];
         p.y[((static_cast<long long>(b) * p.Cout + co) * Hout + ho) * p.Wp_out + wo] = __float2half_rn(acc);
     }
 }

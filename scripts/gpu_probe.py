@@ -45,7 +45,7 @@ def fl_case(C, H, W, up, down, ut, dt, lo, hi, radial=False):
     fd = O.design_lowpass_filter(dt, 8.0, 9.0, 64.0, radial=radial) if dt > 1 else None
     pad = [lo, hi, lo, hi]
     ref = O.filtered_lrelu_ref(x, fu=fu, fd=fd, b=b, up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256)
-    for impl in ("1", "0"):
+    for impl in ("1", "2", "0"):
         os.environ["MB_FLRELU_IMPL"] = impl
         try:
             got = ops.filtered_lrelu(x.to(dev), None if fu is None else fu.to(dev), None if fd is None else fd.to(dev), b.to(dev),
@@ -66,6 +66,8 @@ if __name__ == "__main__":
         fl_case(2, 150, 130, 2, 2, 12, 12, -11, -12)
         fl_case(2, 86, 86, 4, 2, 24, 12, -6, -9, True)
         fl_case(4, 33, 47, 1, 1, 1, 1, 0, 0)
+        fl_case(1, 200, 180, 4, 2, 24, 12, -7, -8)
+        fl_case(1, 90, 70, 2, 2, 12, 12, -10, -13)
     if which in ("all", "conv"):
         conv_case(1, 64, 128, 20, 20, 3)
         conv_case(2, 81, 51, 70, 66, 3)

@@ -51,16 +51,19 @@ FL_CASES = [
     (4, 33, 47, 1, 1, 1, 1, (0, 0), False),
     (2, 40, 40, 2, 1, 12, 1, (5, 6), False),
     (2, 40, 40, 1, 2, 1, 12, (5, 6), False),
+    (1, 300, 280, 2, 2, 12, 12, (9, 8), False),
+    (1, 200, 180, 4, 2, 24, 12, (-7, -8), False),
+    (1, 90, 70, 2, 2, 12, 12, (-10, -13), False),
 ]
 
 
 @pytest.mark.parametrize("case", FL_CASES)
-@pytest.mark.parametrize("impl", ["auto", "generic"])
+@pytest.mark.parametrize("impl", ["tensorcore", "generic", "cudacore"])
 def test_filtered_lrelu(cuda, case, impl, monkeypatch):
     from maua_b200 import ops
 
     C, H, W, up, down, ut, dt, (lo, hi), radial = case
-    monkeypatch.setenv("MB_FLRELU_IMPL", "1" if impl == "generic" else "0")
+    monkeypatch.setenv("MB_FLRELU_IMPL", {"tensorcore": "0", "generic": "1", "cudacore": "2"}[impl])
     g = torch.Generator().manual_seed(99 + H)
     x = (torch.randn(2, C, H, W, generator=g) * 2).half().float()
     b = torch.randn(C, generator=g)

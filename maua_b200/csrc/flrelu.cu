@@ -175,6 +175,7 @@ static int flrelu_generic_launch(const FlreluArgs& a, cudaStream_t stream) {
 int flrelu_launch_impl(const FlreluArgs& a, int impl, cudaStream_t stream) {
     if (a.B == 0 || a.C == 0) return MB_OK;
     if (impl == 0 && flrelu_mma_supported(a)) return flrelu_mma_launch(a, stream);
+    MB_REQUIRE(a.y_nhwc == nullptr, "filtered_lrelu: channels-last output needs the tensor-core kernel");
     if (impl == 2 && flrelu_sep_supported(a)) return flrelu_sep_launch(a, stream);
     return flrelu_generic_launch(a, stream);
 }

@@ -72,7 +72,7 @@ struct MmaParams {
     const float* scale;
     __half* y;
     const uint4* frags;  // [NFRAG][32]
-    int C, Hin, Win, Wp_in, Hout, Wout, Wp_out, px0, py0, tiles_x, tiles_y, e, tpw;
+    int C, Hin, Win, Wp_in, Hout, Wout, Wp_out, Cp_out, px0, py0, tiles_x, tiles_y, e, tpw;
     float gain, slope, clamp;
 };
 
@@ -84,6 +84,103 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// The four-pass chain for one 32x32 output tile; X = fp16 input tile in shared memory (row pitch kXP),
+// dx = even column offset of the first needed input sample inside the tile rows.
+template <int UP>
+__device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR][2], const uint4 (&AD)[3][2],
+                                      float g1, float g2, float cl, int g, int tig, float (&OUT)[2][4][4]) {
+    using K = MC<UP>;
+    uint32_t P1a[kMB][2], P1b[kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers
+    int have_a = -1, have_b = -1;       // compile-time constants after unrolling
+
+    auto stage1 = [&](int blk, uint32_t (&P)[kMB][2]) {
+#pragma unroll
+        for (int m = 0; m < kMB; ++m) {
+            const int w0 = K::wblk(m) * 8;
+            const __half* src = X + (blk * 8 + g) * kXP + dx + w0 + 2 * tig;
+            const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src);
+            const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + 8);
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(acc, AU[K::var(m)][0], b0, b1);
+            mma16816(acc, AU[K::var(m)][1], b0, b1);
+            P[m][0] = pack2(acc[0], acc[1]);
+            P[m][1] = pack2(acc[2], acc[3]);
+        }
+    };
+
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) OUT[i][n][k] = 0.0f;
+
+#pragma unroll
+    for (int j = 0; j < kStrips; ++j) {
+        // ---- S1 for the two input-row blocks this strip's window covers
+        const int wb = K::wblk(j);
+        if (have_a != wb) {
+            if (have_b == wb) {
+#pragma unroll
+                for (int m = 0; m < kMB; ++m) { P1a[m][0] = P1b[m][0]; P1a[m][1] = P1b[m][1]; }
+            } else {
+                stage1(wb, P1a);
+            }
+            have_a = wb;
+            have_b = -1;
+        }
+        if (have_b != wb + 1) {
+            stage1(wb + 1, P1b);
+            have_b = wb + 1;
+        }
+        // ---- S2 (+activation): T[16 rows of strip j][80 cols], packed as B operands of S3
+        uint32_t P2[kJB][2];
+#pragma unroll
+        for (int nb = 0; nb < kJB; ++nb) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            mma16816(acc, AU[K::var(j)][0], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
+            mma16816(acc, AU[K::var(j)][1], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float t1 = acc[k] * g1, t2 = acc[k] * g2;
+                acc[k] = fminf(fmaxf(fmaxf(t1, t2), -cl), cl);
+            }
+            P2[nb][0] = pack2(acc[0], acc[1]);
+            P2[nb][1] = pack2(acc[2], acc[3]);
+        }
+        // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
+        uint32_t P3[4][2];
+#pragma unroll
+        for (int mo = 0; mo < 2; ++mo) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const int nb = 4 * mo + 2 * s;
+                    mma16816(acc, AD[s][0], P2[nb][h], P2[nb + 1][h]);
+                    mma16816(acc, AD[s][1], P2[nb][h], P2[nb + 1][h]);
+                }
+                P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
+                P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+            }
+        }
+        // ---- S4: strip j is k-step s = j - 2i of output row block i
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int s = j - 2 * i;
+            if (s >= 0 && s < 3) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no) {
+                    mma16816(OUT[i][no], AD[s][0], P3[no][0], P3[no][1]);
+                    mma16816(OUT[i][no], AD[s][1], P3[no][0], P3[no][1]);
+                }
+            }
+        }
+    }
+
 }
 
 // One warp = a run of `tpw` consecutive 32x32 output tiles of one (b, c) plane; the input tile of
@@ -178,95 +275,8 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         origin(tile, ox0, oy0, ix0, iy0);
         const int dx = ix0 - fdiv(ix0, 8) * 8;  // even by construction
 
-        uint32_t P1a[kMB][2], P1b[kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers
-        int have_a = -1, have_b = -1;       // compile-time constants after unrolling
-
-        auto stage1 = [&](int blk, uint32_t (&P)[kMB][2]) {
-#pragma unroll
-            for (int m = 0; m < kMB; ++m) {
-                const int w0 = K::wblk(m) * 8;
-                const __half* src = X + (blk * 8 + g) * kXP + dx + w0 + 2 * tig;
-                const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src);
-                const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + 8);
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(acc, AU[K::var(m)][0], b0, b1);
-                mma16816(acc, AU[K::var(m)][1], b0, b1);
-                P[m][0] = pack2(acc[0], acc[1]);
-                P[m][1] = pack2(acc[2], acc[3]);
-            }
-        };
-
         float OUT[2][4][4];
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-#pragma unroll
-            for (int n = 0; n < 4; ++n)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) OUT[i][n][k] = 0.0f;
-
-#pragma unroll
-        for (int j = 0; j < kStrips; ++j) {
-            // ---- S1 for the two input-row blocks this strip's window covers
-            const int wb = K::wblk(j);
-            if (have_a != wb) {
-                if (have_b == wb) {
-#pragma unroll
-                    for (int m = 0; m < kMB; ++m) { P1a[m][0] = P1b[m][0]; P1a[m][1] = P1b[m][1]; }
-                } else {
-                    stage1(wb, P1a);
-                }
-                have_a = wb;
-                have_b = -1;
-            }
-            if (have_b != wb + 1) {
-                stage1(wb + 1, P1b);
-                have_b = wb + 1;
-            }
-            // ---- S2 (+activation): T[16 rows of strip j][80 cols], packed as B operands of S3
-            uint32_t P2[kJB][2];
-#pragma unroll
-            for (int nb = 0; nb < kJB; ++nb) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                mma16816(acc, AU[K::var(j)][0], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
-                mma16816(acc, AU[K::var(j)][1], P1a[nb >> 1][nb & 1], P1b[nb >> 1][nb & 1]);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float t1 = acc[k] * g1, t2 = acc[k] * g2;
-                    acc[k] = fminf(fmaxf(fmaxf(t1, t2), -cl), cl);
-                }
-                P2[nb][0] = pack2(acc[0], acc[1]);
-                P2[nb][1] = pack2(acc[2], acc[3]);
-            }
-            // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
-            uint32_t P3[4][2];
-#pragma unroll
-            for (int mo = 0; mo < 2; ++mo) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const int nb = 4 * mo + 2 * s;
-                        mma16816(acc, AD[s][0], P2[nb][h], P2[nb + 1][h]);
-                        mma16816(acc, AD[s][1], P2[nb][h], P2[nb + 1][h]);
-                    }
-                    P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
-                    P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
-                }
-            }
-            // ---- S4: strip j is k-step s = j - 2i of output row block i
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int s = j - 2 * i;
-                if (s >= 0 && s < 3) {
-#pragma unroll
-                    for (int no = 0; no < 4; ++no) {
-                        mma16816(OUT[i][no], AD[s][0], P3[no][0], P3[no][1]);
-                        mma16816(OUT[i][no], AD[s][1], P3[no][0], P3[no][1]);
-                    }
-                }
-            }
-        }
+        fir_chain<UP>(X, dx, AU, AD, g1, g2, cl, g, tig, OUT);
 
         // ---- store: * next-layer style, fp16, two adjacent columns per thread
 #pragma unroll
@@ -286,6 +296,125 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
             }
         }
         __syncwarp();  // every lane is done reading X[buf] before the next iteration's prefetch overwrites it
+    }
+}
+
+
+// ---- channels-last output variant -----------------------------------------------------------------
+// The next conv reads channels-last (its TMA box start must be 16-byte aligned, conv_tc.cu), so for every
+// layer that feeds a conv the transpose is fused here: one CTA = 16 warps = 16 consecutive channels of
+// the same run of tiles.  Each warp stages its finished 32x32 tile in shared memory, then the CTA writes
+// 32-byte (16 channel) pixel chunks -- full DRAM sectors -- into [B][H][W][Cp].
+constexpr int kCG = 16;          // channels per CTA
+constexpr int kSP = 40;          // staging row pitch in halfs (conflict-free fragment stores)
+constexpr int kStageBytes = kOT * kSP * 2;
+
+template <int UP>
+__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaParams p) {
+    using K = MC<UP>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    __half* Xbuf = reinterpret_cast<__half*>(smem_raw + warp * 2 * K::XBYTES);
+    __half* stage_all = reinterpret_cast<__half*>(smem_raw + kCG * 2 * K::XBYTES);
+    __half* stage = stage_all + warp * (kStageBytes / 2);
+
+    const int ntiles = p.tiles_x * p.tiles_y;
+    const int tile0 = blockIdx.x * p.tpw;
+    const int tile_end = min(tile0 + p.tpw, ntiles);
+    const int c0 = blockIdx.y * kCG, b = blockIdx.z;
+    const int c = c0 + warp;
+    const bool valid = c < p.C;
+    const __half* xp = p.x + (static_cast<long long>(b) * p.C + (valid ? c : 0)) * p.Hin * p.Wp_in;
+
+    uint4 AU[K::NVAR][2], AD[3][2];
+#pragma unroll
+    for (int v = 0; v < K::NVAR; ++v) {
+        AU[v][0] = p.frags[(v * 2 + 0) * 32 + lane];
+        AU[v][1] = p.frags[(v * 2 + 1) * 32 + lane];
+    }
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        AD[s][0] = p.frags[((K::NVAR + s) * 2 + 0) * 32 + lane];
+        AD[s][1] = p.frags[((K::NVAR + s) * 2 + 1) * 32 + lane];
+    }
+    const float g1 = p.gain, g2 = p.gain * p.slope, cl = p.clamp;
+    const float oscale = (valid && p.scale) ? p.scale[b * p.C + c] : 1.0f;
+
+    if (!valid)  // channel padding of the last group: its staging plane stays zero
+        for (int i = lane; i < kStageBytes / 16; i += 32) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+
+    auto origin = [&](int tile, int& ox0, int& oy0, int& ix0, int& iy0) {
+        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+        ox0 = tx * kOT;
+        oy0 = ty * kOT;
+        ix0 = -fdiv(-(2 * ox0 - p.px0), UP) - p.e;
+        iy0 = -fdiv(-(2 * oy0 - p.py0), UP) - p.e;
+    };
+    auto load_tile = [&](int tile, __half* X) {
+        int ox0, oy0, ix0, iy0;
+        origin(tile, ox0, oy0, ix0, iy0);
+        const int ixa = fdiv(ix0, 8) * 8;
+        for (int idx = lane; idx < K::IYT * 7; idx += 32) {
+            const int row = idx / 7, ch = idx - row * 7;
+            const int iy = iy0 + row, ixc = ixa + ch * 8;
+            int bytes = 0;
+            const __half* src = xp;
+            if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
+                bytes = min(8, p.Win - ixc) * 2;
+                src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
+            }
+            cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
+        }
+        cp_async_commit();
+    };
+
+    if (valid) load_tile(tile0, Xbuf);
+    int buf = 0;
+    for (int tile = tile0; tile < tile_end; ++tile, buf ^= 1) {
+        int ox0, oy0, ix0, iy0;
+        origin(tile, ox0, oy0, ix0, iy0);
+        if (valid) {
+            const __half* X = Xbuf + buf * (K::XBYTES / 2);
+            if (tile + 1 < tile_end) {
+                load_tile(tile + 1, Xbuf + (buf ^ 1) * (K::XBYTES / 2));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const int dx = ix0 - fdiv(ix0, 8) * 8;
+            float OUT[2][4][4];
+            fir_chain<UP>(X, dx, AU, AD, g1, g2, cl, g, tig, OUT);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        *reinterpret_cast<uint32_t*>(stage + (i * 16 + hh * 8 + g) * kSP + no * 8 + 2 * tig) =
+                            pack2(OUT[i][no][hh * 2 + 0] * oscale, OUT[i][no][hh * 2 + 1] * oscale);
+        }
+        __syncthreads();
+        // cooperative write-out: thread -> pixel, 16 channels (32 bytes) per pixel
+        for (int px = threadIdx.x; px < kOT * kOT; px += kCG * 32) {
+            const int ly = px >> 5, lx = px & 31;
+            const int oy = oy0 + ly, ox = ox0 + lx;
+            if (oy < p.Hout && ox < p.Wout) {
+                const __half* sp = stage_all + ly * kSP + lx;
+                uint32_t w[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * k) * (kStageBytes / 2));
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * k + 1) * (kStageBytes / 2));
+                    w[k] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + c0);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -393,12 +522,31 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     MmaParams p;
     p.x = a.x; p.bias = a.bias; p.scale = a.scale; p.y = a.y; p.frags = frags;
     p.C = a.C; p.Hin = a.Hin; p.Win = a.Win; p.Wp_in = a.Wp_in; p.Hout = a.Hout; p.Wout = a.Wout; p.Wp_out = a.Wp_out;
+    p.Cp_out = 0;
     p.px0 = a.px0; p.py0 = a.py0;
     p.tiles_x = ceil_div(a.Wout, kOT); p.tiles_y = ceil_div(a.Hout, kOT);
     p.e = e;
     const int ntiles = p.tiles_x * p.tiles_y;
     p.tpw = ntiles < 64 ? 1 : (ntiles < 256 ? 2 : 4);
     p.gain = a.gain; p.slope = a.slope; p.clamp = a.clamp >= 0.0f ? a.clamp : 3.0e38f;
+    if (a.y_nhwc) {
+        // fused transpose: 16 channels per CTA, 32-byte pixel chunks into [B][H][W][Cp_out]
+        MB_REQUIRE(a.bias == nullptr, "filtered_lrelu: the channels-last variant takes the bias from the conv epilogue");
+        MB_REQUIRE(a.Cp_out % 16 == 0 && a.Cp_out >= round_up(a.C, kCG), "filtered_lrelu: Cp_out must cover whole 16-channel groups");
+        p.y = a.y_nhwc;
+        p.Cp_out = a.Cp_out;
+        p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : 4);
+        constexpr int smem = kCG * 2 * K::XBYTES + kCG * kStageBytes;
+        static bool attr_nhwc = false;
+        if (!attr_nhwc) {
+            MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            attr_nhwc = true;
+        }
+        dim3 grid(ceil_div(ntiles, p.tpw), ceil_div(a.C, kCG), a.B);
+        flrelu_mma_nhwc_kernel<UP><<<grid, kCG * 32, smem, stream>>>(p);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         MB_CUDA(cudaFuncSetAttribute(flrelu_mma_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));

@@ -105,7 +105,9 @@ struct FlreluArgs {
     const __half* x;     // [B][C][Hin][Wp_in]
     const float* bias;   // [C] or nullptr
     const float* scale;  // [B][C] multiplier applied to the result (next layer's style) or nullptr
-    __half* y;           // [B][C][Hout][Wp_out]
+    __half* y;           // planar [B][C][Hout][Wp_out]
+    __half* y_nhwc;      // if set: write channels-last [B][Hout][Wout][Cp_out] instead (tensor-core kernel only)
+    int Cp_out;
     float fu[32];        // HOST copy of the up filter taps (without the up^2 gain); [1]={1} when up == 1
     float fd[144];       // HOST copy: [down_taps] or [down_taps^2] (row-major) when fd_2d
     int B, C, Hin, Win, Wp_in, Hout, Wout, Wp_out;
@@ -117,5 +119,6 @@ struct FlreluArgs {
 int flrelu_launch(const FlreluArgs& a, cudaStream_t stream);
 // impl: 0 = best available (tensor-core chain), 1 = generic loops, 2 = CUDA-core polyphase kernel
 int flrelu_launch_impl(const FlreluArgs& a, int impl, cudaStream_t stream);
+bool flrelu_mma_supported(const FlreluArgs& a);
 
 }  // namespace mb

@@ -414,7 +414,7 @@ extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
 // workspace
 // ---------------------------------------------------------------------------------------
 namespace {
-inline int cpad8(int c) { return (c + 7) / 8 * 8; }
+inline int cpad8(int c) { return (c + 15) / 16 * 16; }  // channel pitch: whole 16-channel (32-byte) groups
 struct WsLayout {
     size_t styles_off, d_off, scratch_off, x_off, y_off, p_off, total;
     std::vector<size_t> style_l, d_l;  // per-layer float offsets inside styles / d blocks
@@ -667,17 +667,25 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         fa.gain = sqrtf(2.0f); fa.slope = 0.2f;
         fa.clamp = static_cast<float>(net->cfg.conv_clamp);
         fa.num_sms = g_num_sms;
+        // Layers that feed another conv write channels-last straight from the tensor-core kernel; the
+        // fallback kernels (and the last layer, whose consumer is the planar ToRGB kernel) write planar.
+        const bool next_is_conv = !net->layers[i + 1].g.is_torgb;
+        FlreluArgs probe = fa;
+        const bool fused = next_is_conv && net->flrelu_impl == 0 && net->debug_stop > i && flrelu_mma_supported(probe);
+        if (fused) {
+            fa.y_nhwc = X;
+            fa.Cp_out = cpad8(g.out_channels);
+        }
         r = flrelu_launch_impl(fa, net->flrelu_impl, stream);
         if (r != MB_OK) return r;
         launches += 1;
         prof_mark(3, i);
-        net->last_act = P;
-        net->last_act_nhwc = false;
+        net->last_act = fused ? X : P;
+        net->last_act_nhwc = fused;
         net->last_act_c = g.out_channels;
         net->last_act_h = net->last_act_w = g.out_size;
         if (net->debug_stop <= i) break;
-        if (!net->layers[i + 1].g.is_torgb) {
-            // the next conv reads channels-last (TMA box starts must be 16-byte aligned)
+        if (next_is_conv && !fused) {
             r = planar_to_nhwc_launch(P, X, B, g.out_channels, g.out_size, g.out_size, pitch8(g.out_size),
                                       cpad8(g.out_channels), stream);
             if (r != MB_OK) return r;

@@ -5,6 +5,17 @@ from oracle import sg3
 torch.set_num_threads(os.cpu_count())
 def h(x): return x.half().float()
 
+def qfilt(f, phases):
+    # fp16 taps, then rescale each polyphase branch so its DC gain matches the exact filter (applied in fp32 outside the MMA)
+    fq = h(f)
+    corr = torch.ones_like(f)
+    n = f.numel()
+    for p in range(phases):
+        idx = torch.arange(p, n, phases)
+        corr[idx] = f[idx].sum() / fq[idx].sum()
+    return fq, corr
+
+DC = False
 def fir_chain(y, l, filt_half, inter_half, split=False):
     # y: conv output fp32 [B,C,H,W]; returns filtered_lrelu result following reference semantics
     B, C, H, W = y.shape
@@ -18,7 +29,9 @@ def fir_chain(y, l, filt_half, inter_half, split=False):
         t = x
     else:
         fuq = fu * up
-        if filt_half and not split: fuq = h(fuq)
+        if filt_half and not split:
+            fq, corr = qfilt(fuq, up)
+            fuq = fq * corr if DC else fq
         # zero insert
         xz = x.reshape(B, C, H, 1, W, 1); xz = F.pad(xz, [0, up - 1, 0, 0, 0, up - 1]).reshape(B, C, H * up, W * up)
         xz = F.pad(xz, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
@@ -32,7 +45,11 @@ def fir_chain(y, l, filt_half, inter_half, split=False):
     if inter_half: t = h(t)
     if fd is None:
         return t
-    fdq = h(fd) if (filt_half and not split) else fd
+    if filt_half and not split:
+        fq, corr = qfilt(fd, 1)
+        fdq = fq * corr if DC else fq
+    else:
+        fdq = fd
     f = fdq.flip(0)[None, None].repeat(C, 1, 1)
     o = F.conv2d(t, f.unsqueeze(2), groups=C)
     if inter_half: o = h(o)
@@ -72,7 +89,9 @@ torch.manual_seed(1)
 ws = torch.randn(1, 16, 512)
 ref = net(ws)
 pix = lambda y: (y + 1) / 2
-for cfg in [dict(filt_half=False, inter_half=False), dict(filt_half=False, inter_half=True), dict(filt_half=True, inter_half=True)]:
+for cfg in [dict(filt_half=False, inter_half=True), dict(filt_half=True, inter_half=True), dict(filt_half=True, inter_half=True, dc=True)]:
+    DC = cfg.pop('dc', False)
     out = emulate(net, ws, **cfg)
+    cfg['dc'] = DC
     e = (pix(out).clamp(0, 1) - pix(ref).clamp(0, 1)).abs()
     print(cfg, "max-abs pix err %.3e  rms %.3e" % (e.max(), e.square().mean().sqrt()), flush=True)

@@ -53,7 +53,9 @@ def test_small_network_layers_and_pixels(cuda, config, kw):
         assert rel < 4e-2, (stop, rel)
     net.set_option("debug_stop", 1 << 30)
     out = net(ws.to(cuda))
-    assert float((pix(out) - pix(ref)).abs().max()) <= PIX_TOL
+    err = float((pix(out) - pix(ref)).abs().max())
+    print(f"{config} 256^2: max-abs pixel error vs oracle {err:.3e}")
+    assert err <= PIX_TOL, err
     u8 = net(ws.to(cuda), out_fmt="u8").cpu()
     want8 = (pix(ref) * 255).round().permute(0, 2, 3, 1)
     assert float((u8.float() - want8).abs().max()) <= 1.0
@@ -82,6 +84,7 @@ def test_full_size_frame_matches_oracle(cuda):
     ref = onet(ws)
     out = net(ws.to(cuda))
     err = float((pix(out) - pix(ref)).abs().max())
+    print(f"full-size 1024^2 frame: max-abs pixel error vs oracle {err:.3e}")
     assert err <= PIX_TOL, err
     assert out.shape == (1, 3, 1024, 1024)
 

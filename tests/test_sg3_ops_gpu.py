@@ -74,5 +74,6 @@ def test_filtered_lrelu(cuda, case, impl, monkeypatch):
     got = ops.filtered_lrelu(x.to(cuda), None if fu is None else fu.to(cuda), None if fd is None else fd.to(cuda),
                              b.to(cuda), up=up, down=down, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256)
     assert got.shape == ref.shape
-    # fp32 arithmetic, fp16 output rounding only: max error relative to the RMS, values reach ~4-5 RMS
-    assert _rel_err(got, ref) < 5e-3
+    # max error relative to the RMS (values reach ~4-5 RMS).  CUDA-core kernels: fp32 arithmetic, fp16 output
+    # rounding only.  Tensor-core chain: fp16 taps (DC-corrected) and fp16 rounding between the four passes.
+    assert _rel_err(got, ref) < (1e-2 if impl == "tensorcore" else 5e-3)

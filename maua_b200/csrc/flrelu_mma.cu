@@ -48,6 +48,11 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t clamp2(uint32_t v, uint32_t c) {
+    __half2 h = *reinterpret_cast<__half2*>(&v), ch = *reinterpret_cast<__half2*>(&c);
+    h = __hmin2(__hmax2(h, __hneg2(ch)), ch);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ int fdiv(int a, int b) {
     int q = a / b;
     if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
@@ -102,7 +107,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // carrying gain, slope and the DC corrections of the fp16-rounded up-filter branches (see build_frags).
 template <int UP>
 __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR], const uint4 (&AD)[3],
-                                          const float (&ga)[2], const float (&gb)[2], float cl, int g, int tig,
+                                          const float (&ga)[2], const float (&gb)[2], uint32_t cl2, int g, int tig,
                                           float (&OUT)[2][4][4]) {
     using K = MC<UP>;
     uint32_t P1[2][kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers (slot = block & 1)
@@ -140,13 +145,14 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
         for (int nb = 0; nb < kJB; ++nb) {
             float acc[4];
             mma16816_z(acc, AU[K::var(j)], P1[wb & 1][nb >> 1][nb & 1], P1[(wb + 1) & 1][nb >> 1][nb & 1]);
-            // lrelu(t) * gain = max(t*g, t*g*slope) for 0 <= slope <= 1, then clamp
-            const float v0 = fminf(fmaxf(fmaxf(acc[0] * ga[0], acc[0] * ga[1]), -cl), cl);
-            const float v1 = fminf(fmaxf(fmaxf(acc[1] * gb[0], acc[1] * gb[1]), -cl), cl);
-            const float v2 = fminf(fmaxf(fmaxf(acc[2] * ga[0], acc[2] * ga[1]), -cl), cl);
-            const float v3 = fminf(fmaxf(fmaxf(acc[3] * gb[0], acc[3] * gb[1]), -cl), cl);
-            P2[nb][0] = pack2(v0, v1);
-            P2[nb][1] = pack2(v2, v3);
+            // lrelu(t) * gain = a*t + b*|t| with a = g(1+slope)/2, b = g(1-slope)/2 (fp32), then clamp on the
+            // packed halves (|clamp| <= 65504; an fp32 overflow packs to inf and is clamped all the same)
+            const float v0 = fmaf(fabsf(acc[0]), ga[1], acc[0] * ga[0]);
+            const float v1 = fmaf(fabsf(acc[1]), gb[1], acc[1] * gb[0]);
+            const float v2 = fmaf(fabsf(acc[2]), ga[1], acc[2] * ga[0]);
+            const float v3 = fmaf(fabsf(acc[3]), gb[1], acc[3] * gb[0]);
+            P2[nb][0] = clamp2(pack2(v0, v1), cl2);
+            P2[nb][1] = clamp2(pack2(v2, v3), cl2);
         }
         // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
         uint32_t P3[4][2];
@@ -197,10 +203,11 @@ __device__ __forceinline__ void lane_setup(const MmaParams& p, int lane, LaneCon
     const float cy = p.cu[((p.rho - g) % UP + UP) % UP];
     const float cx0 = p.cu[((p.rho - 2 * tig) % UP + UP) % UP];
     const float cx1 = p.cu[((p.rho - 2 * tig - 1) % UP + UP) % UP];
-    L.ga[0] = p.gain * cy * cx0;
-    L.ga[1] = L.ga[0] * p.slope;
-    L.gb[0] = p.gain * cy * cx1;
-    L.gb[1] = L.gb[0] * p.slope;
+    const float a0 = p.gain * cy * cx0, a1 = p.gain * cy * cx1;
+    L.ga[0] = a0 * 0.5f * (1.0f + p.slope);  // a*t + b*|t| == lrelu(t)*gain
+    L.ga[1] = a0 * 0.5f * (1.0f - p.slope);
+    L.gb[0] = a1 * 0.5f * (1.0f + p.slope);
+    L.gb[1] = a1 * 0.5f * (1.0f - p.slope);
 }
 
 // One warp = a run of `tpw` consecutive 32x32 output tiles of one (b, c) plane; the input tile of
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
 
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
-    const float cl = p.clamp;
+    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
     const float oscale = (p.scale ? p.scale[b * p.C + c] : 1.0f) * p.cd2;
     __half* yp = p.y + (static_cast<long long>(b) * p.C + c) * p.Hout * p.Wp_out;
 
@@ -286,7 +293,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         const int dx = ix0 - fdiv(ix0, 8) * 8;  // even by construction
 
         float OUT[2][4][4];
-        fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl, g, tig, OUT);
+        fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT);
 
         // ---- store: * next-layer style, fp16, two adjacent columns per thread
 #pragma unroll
@@ -339,7 +346,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
 
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
-    const float cl = p.clamp;
+    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
     const float oscale = ((valid && p.scale) ? p.scale[b * p.C + c] : 1.0f) * p.cd2;
 
     if (!valid)  // channel padding of the last group: its staging plane stays zero
@@ -386,7 +393,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
             __syncwarp();
             const int dx = ix0 - fdiv(ix0, 8) * 8;
             float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl, g, tig, OUT);
+            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT);
 #pragma unroll
             for (int i = 0; i < 2; ++i)
 #pragma unroll

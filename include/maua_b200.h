@@ -159,6 +159,24 @@ int mb_filtered_lrelu(const float* x, const float* fu, const float* fd, const fl
                       int fd_2d, int px0, int px1, int py0, int py1, float gain, float slope,
                       float clamp, mb_stream stream);
 
+/* ---- audio features ----------------------------------------------------------------------------
+ * Onset envelope + RMS of the torch-native feature path, one fused pass on the device:
+ *   onsets(audio, sr) = normalize(onset_strength(percussive(audio), sr))     features/audio.py:20-28
+ *   rms(audio, sr)                                                            features/audio.py:31-37
+ * (maua/audiovisual/audioreactive/selfsupervised/features/; n_fft 2048, hop 1024, HPSS 31-tap medians,
+ * margin 8, 128 Slaney mel bands up to 11025 Hz, top_db 80) and the strict-local-maximum peak rule of
+ * audioreactive/signal.py:69-76.
+ *   audio          device float32 [n], n a multiple of 1024 (the path resamples to sr = 1024*fps,
+ *                  selfsupervised/sample.py:29-30, so one hop = one video frame), n >= 16384
+ *   mel_filterbank device float32 [128,1025] (host-designed: depends on sr)
+ *   onsets, rms    device float32 [T], T = n / 1024;  peak_idx device int32 [T]; n_peaks device int32 [1]
+ *   percussive_out device float32 [n] or NULL (the HPSS percussive signal, for parity tests)
+ */
+size_t mb_audio_workspace_bytes(int64_t n_samples);
+int mb_audio_onsets_rms(const float* audio, int64_t n, const float* mel_filterbank, float margin,
+                        float* onsets, float* rms, int32_t* peak_idx, int32_t* n_peaks,
+                        float* percussive_out, void* workspace, size_t workspace_bytes, mb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

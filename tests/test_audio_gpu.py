@@ -1,0 +1,59 @@
+"""Device audio features (through mb_audio_onsets_rms) against the reference-generated golden vectors and the
+oracle; onset-peak frame indices must be BIT-EXACT (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import audio as OA
+
+pytestmark = pytest.mark.gpu
+G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "audio.pt"))
+
+
+def test_against_reference_golden_vectors(cuda):
+    from maua_b200.audiovisual import audioreactive as ar
+
+    y, sr = G["audio_exact"].to(cuda), G["sr"]
+    on, rms = ar.onsets_rms(y, sr)
+    assert on.shape == (len(G["onsets"]), 1) and rms.shape == on.shape
+    assert float((on[:, 0].cpu() - G["onsets"]).abs().max()) < 2e-4      # fp32, different FFT / log10 rounding
+    assert float((rms[:, 0].cpu() - G["rms"]).abs().max()) < 1e-6
+    assert torch.equal(ar.onset_peaks(y, sr).cpu(), G["peaks"])          # bit-exact indices
+    perc = ar.percussive(y).cpu()
+    ref = OA.percussive(G["audio_exact"])
+    assert float((perc - ref).abs().max()) < 1e-4 * float(ref.abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("fps,dur", [(24, 30.0), (60, 12.0)])
+def test_config_sized_sweep_matches_oracle(cuda, fps, dur):
+    """BASELINE.json configs[1] audio (30 s @ 24 fps -> 720 frames) and a 60 fps variant, tremolo sweep."""
+    from maua_b200.audiovisual import audioreactive as ar
+    from maua_b200.workload import sine_sweep
+
+    sr = 1024 * fps
+    y48, _ = sine_sweep(dur, tremolo_hz=4.0)
+    t = np.arange(int(dur * sr)) / sr
+    y = torch.from_numpy(np.interp(t, np.arange(len(y48)) / 48000.0, y48).astype(np.float32))
+    ref_on = OA.onsets(y, sr)[:, 0]
+    ref_pk = OA.peak_indices(ref_on)
+    on, rms = ar.onsets_rms(y.to(cuda), sr)
+    assert on.shape[0] == int(dur * fps)
+    assert float((on[:, 0].cpu() - ref_on).abs().max()) < 5e-4
+    assert float((rms[:, 0].cpu() - OA.rms(y)[:, 0]).abs().max()) < 1e-6
+    got_pk = ar.onset_peaks(y.to(cuda), sr).cpu()
+    margins = torch.minimum(ref_on[ref_pk] - ref_on[(ref_pk - 1).clamp(0)], ref_on[ref_pk] - ref_on[(ref_pk + 1).clamp(max=len(ref_on) - 1)])
+    solid = ref_pk[margins > 1e-4]  # peaks whose margin is far above fp32 noise must be found exactly
+    assert set(solid.tolist()) <= set(got_pk.tolist())
+    if float(margins.min()) > 1e-4:
+        assert torch.equal(got_pk, ref_pk)
+
+
+def test_errors(cuda):
+    from maua_b200.audiovisual import audioreactive as ar
+
+    with pytest.raises(ValueError):
+        ar.onsets(torch.zeros(30000, device=cuda), 24576)
+    with pytest.raises(RuntimeError):
+        ar.onsets(torch.zeros(32768), 24576)

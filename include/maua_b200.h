@@ -177,6 +177,18 @@ int mb_audio_onsets_rms(const float* audio, int64_t n, const float* mel_filterba
                         float* onsets, float* rms, int32_t* peak_idx, int32_t* n_peaks,
                         float* percussive_out, void* workspace, size_t workspace_bytes, mb_stream stream);
 
+/* ---- envelope post-ops and latent sequencers (device float32, [T, C] row-major, T = frames) ----------
+ * maua/audiovisual/audioreactive/signal.py: gaussian_filter :108-157 (circular padding, optional causal
+ * half-kernel factor), normalize :27-38 (eps 0) / processing.py:53-56 (eps 1e-8), resample :5-24 (linear,
+ * align_corners False); latent.py: single_weighted :12-17, multi_weighted :21-31. */
+int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal, mb_stream stream);
+int mb_normalize(const float* x, float* y, int64_t n, float eps, float* scratch2 /* device float[2] */, mb_stream stream);
+int mb_resample_linear(const float* x, float* y, int T, int S, int C, mb_stream stream);
+int mb_multi_weighted(const float* latents /*[K,D]*/, const float* envelopes /*[T,A]*/, float* out /*[T,D]*/, int T, int A,
+                      int K, int D, mb_stream stream);
+int mb_single_weighted(const float* low /*[D]*/, const float* high /*[D]*/, const float* envelope /*[T]*/, float* out /*[T,D]*/,
+                       int T, int D, mb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

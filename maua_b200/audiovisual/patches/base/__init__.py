@@ -1,0 +1,57 @@
+"""Patch plugin API: mirror of maua/audiovisual/patches/base/__init__.py:7-45 (MauaPatch, get_patch_from_file)."""
+import torch
+
+
+def load_audio(audio_file, offset=0, duration=-1):
+    """(audio float32 [N] mono, sr, duration_s) -- audioreactive/audio.py:15-48 without the joblib cache.
+    WAV files through the standard library (this image has no ffmpeg / torchaudio backend for mp3)."""
+    import wave
+
+    import numpy as np
+
+    with wave.open(audio_file, "rb") as w:
+        sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+        raw = w.readframes(n)
+    if width != 2:
+        raise NotImplementedError("load_audio: 16-bit PCM WAV only")
+    a = np.frombuffer(raw, dtype="<i2").astype(np.float32).reshape(-1, ch).mean(axis=1) / 32768.0
+    start = int(offset * sr)
+    end = len(a) if duration is None or duration < 0 else min(len(a), start + int(duration * sr))
+    a = a[start:end]
+    return torch.from_numpy(a.copy()), sr, len(a) / sr
+
+
+class MauaPatch:
+    def __init__(self, audio_file, fps=24, offset=0, duration=-1) -> None:
+        self.fps = fps
+        self.audio_file = audio_file
+        self.audio, self.sr, self.duration = load_audio(audio_file, offset, duration)
+        self.audio = self.audio.numpy()
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.n_frames = round(self.duration * self.fps)
+
+    def process_audio(self):
+        pass
+
+    def force_output_size(self, video):
+        t, c, h, w = video.shape
+        if (w, h) != tuple(self.synthesizer.output_size):
+            raise NotImplementedError("output resampling (maua/ops/image.py:214-240) is not built yet (SURVEY §8a a22)")
+        return video
+
+
+def get_patch_from_file(filepath, class_name=None):
+    import importlib
+    import inspect
+
+    module_name = filepath.replace(".py", "").replace("/", ".")
+    for _, cls in inspect.getmembers(importlib.import_module(module_name), inspect.isclass):
+        if (
+            cls.__module__ == module_name
+            and issubclass(cls, MauaPatch)
+            and ((class_name is not None and cls.__name__ == class_name) or class_name is None)
+        ):
+            return cls
+    raise Exception(
+        "Patch not found! Are you sure there is a class that extends MauaPatch in the file you specified and that the name you (might have) specified is correct?"
+    )

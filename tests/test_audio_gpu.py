@@ -61,3 +61,23 @@ def test_errors(cuda):
         ar.onsets(torch.zeros(30000, device=cuda), 24576)
     with pytest.raises(RuntimeError):
         ar.onsets(torch.zeros(32768), 24576)
+
+
+def test_signal_and_latent_ops_against_reference_vectors(cuda):
+    """Envelope post-ops / latent sequencers vs vectors produced by the reference's own signal.py / latent.py."""
+    from maua_b200.audiovisual import audioreactive as ar
+    from oracle import signal as OS
+
+    env = G["onsets"].to(cuda)
+    assert float((ar.gaussian_filter(env, 2.0).cpu() - G["gauss2"]).abs().max()) < 1e-6
+    assert float((ar.resample(env, 57).cpu() - G["resample57"]).abs().max()) < 1e-6
+    assert float((ar.percentile_clip(env.clone(), 90)[:, 0].cpu() - G["pclip90"]).abs().max()) < 1e-6
+    assert float((ar.multi_weighted(G["keys"].to(cuda), G["chroma"].to(cuda)).cpu() - G["multi_weighted"]).abs().max()) < 1e-5
+    torch.manual_seed(3)
+    lat = torch.randn(720, 16, 512)
+    ref = OS.gaussian_filter(lat, 2.0, causal=0.3)
+    assert float((ar.gaussian_filter(lat.to(cuda), 2.0, causal=0.3).cpu() - ref).abs().max()) < 1e-5
+    e = torch.rand(720)
+    assert float((ar.single_weighted(lat[0].to(cuda), lat[1].to(cuda), e.to(cuda)).cpu() - OS.single_weighted(lat[0], lat[1], e)).abs().max()) < 1e-6
+    assert float((ar.normalize(lat.to(cuda)).cpu() - OS.normalize(lat)).abs().max()) < 1e-6
+    assert float((ar.compress(e.to(cuda), 0.5, 0.5).cpu() - OS.compress(e, 0.5, 0.5)).abs().max()) < 1e-6

@@ -210,6 +210,21 @@ class SynthesisNetwork(torch.nn.Module):
         except Exception:
             pass
 
+    # tensors the reference wrapper edits in place between forwards (wrappers/stylegan3.py:54-59)
+    _POKED = ("input.affine.bias", "input.affine.weight", "input.transform")
+
+    def _param_key(self, name, t):
+        """Identity of a parameter's current value: storage pointer + autograd version counter.  Inference-mode
+        tensors carry no version counter; for those the three tensors the wrapper pokes are fingerprinted."""
+        try:
+            version = t._version
+        except RuntimeError:
+            version = None
+            if name in self._POKED:
+                d = t.detach().double()
+                version = (float(d.sum()), float((d * d).sum()))
+        return (t.data_ptr(), version, str(t.device), tuple(t.shape))
+
     def _sync_params(self, device):
         """Upload every parameter / buffer whose storage or version changed since the last forward."""
         lib = _lib.load()
@@ -219,7 +234,7 @@ class SynthesisNetwork(torch.nn.Module):
         for name, t in list(self.named_parameters()) + list(self.named_buffers()):
             if t is None:
                 continue
-            key = (t.data_ptr(), t._version, str(t.device), tuple(t.shape))
+            key = self._param_key(name, t)
             if self._uploaded.get(name) == key:
                 continue
             d = t.detach().to(device=device, dtype=torch.float32).contiguous()

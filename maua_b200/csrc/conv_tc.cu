@@ -259,7 +259,9 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     }
     {
         const cuuint64_t cp = static_cast<cuuint64_t>(p.Cp_in);
-        cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cin), static_cast<cuuint64_t>(p.Win),
+        // channel extent = the padded pitch: the pad channels hold real zeros (written by the producers), which keeps
+        // the inner box dimension in bounds wherever Cp is a multiple of 64
+        cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cp_in), static_cast<cuuint64_t>(p.Win),
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
         cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
         cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th + pad), 1};

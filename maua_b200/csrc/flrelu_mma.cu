@@ -105,10 +105,15 @@ __device__ __forceinline__ void cp_async_wait() {
 // dx = even column offset of the first needed input sample inside the tile rows.
 // ga/gb: activation multipliers for the even / odd column of this lane's accumulator pairs, already
 // carrying gain, slope and the DC corrections of the fp16-rounded up-filter branches (see build_frags).
-template <int UP>
+struct NoHook {
+    __device__ __forceinline__ void operator()() const {}
+};
+// `x_dead` is invoked right after the last read of X (the last stage-1 block): a single-buffered caller
+// issues the prefetch of its next input tile there.
+template <int UP, class Hook = NoHook>
 __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR], const uint4 (&AD)[3],
                                           const float (&ga)[2], const float (&gb)[2], uint32_t cl2, int g, int tig,
-                                          float (&OUT)[2][4][4]) {
+                                          float (&OUT)[2][4][4], Hook x_dead = Hook()) {
     using K = MC<UP>;
     uint32_t P1[2][kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers (slot = block & 1)
     int have0 = -1, have1 = -1;  // compile-time constants after unrolling
@@ -139,6 +144,7 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
             stage1(wb + 1);
             if ((wb + 1) & 1) have1 = wb + 1; else have0 = wb + 1;
         }
+        if (j == kStrips - 1) x_dead();
         // ---- S2 (+activation): T[16 rows of strip j][80 cols], packed as B operands of S3
         uint32_t P2[kJB][2];
 #pragma unroll
@@ -332,25 +338,37 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
-    __half* Xbuf = reinterpret_cast<__half*>(smem_raw + warp * 2 * K::XBYTES);
-    __half* stage_all = reinterpret_cast<__half*>(smem_raw + kCG * 2 * K::XBYTES);
-    __half* stage = stage_all + warp * (kStageBytes / 2);
+    // layout: [16 warps] input tile (single buffer) | [2 buffers][16 planes] staging | 4 mbarriers
+    __half* X = reinterpret_cast<__half*>(smem_raw + warp * K::XBYTES);
+    __half* stage_base = reinterpret_cast<__half*>(smem_raw + kCG * K::XBYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes);
+    uint64_t* full = bars;       // [2] all 16 planes of a staging buffer written
+    uint64_t* empty = bars + 2;  // [2] all 16 write-out shares of a staging buffer done
 
     const int ntiles = p.tiles_x * p.tiles_y;
     const int tile0 = blockIdx.x * p.tpw;
-    const int tile_end = min(tile0 + p.tpw, ntiles);
+    const int n = min(p.tpw, ntiles - tile0);
     const int c0 = blockIdx.y * kCG, b = blockIdx.z;
     const int c = c0 + warp;
     const bool valid = c < p.C;
     const __half* xp = p.x + (static_cast<long long>(b) * p.C + (valid ? c : 0)) * p.Hin * p.Wp_in;
 
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[i], kCG);
+        fence_barrier_init();
+    }
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
     const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
     const float oscale = ((valid && p.scale) ? p.scale[b * p.C + c] : 1.0f) * p.cd2;
 
-    if (!valid)  // channel padding of the last group: its staging plane stays zero
-        for (int i = lane; i < kStageBytes / 16; i += 32) reinterpret_cast<uint4*>(stage)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (!valid) {  // channel padding of the last group: both staging planes of this warp stay zero
+        for (int sb = 0; sb < 2; ++sb) {
+            uint4* z = reinterpret_cast<uint4*>(stage_base + (sb * kCG + warp) * (kStageBytes / 2));
+            for (int i = lane; i < kStageBytes / 16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    __syncthreads();  // barriers initialised (the only block-wide barrier: warps run decoupled from here on)
 
     auto origin = [&](int tile, int& ox0, int& oy0, int& ix0, int& iy0) {
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
         ix0 = -fdiv(-(2 * ox0 - p.px0), UP) - p.e;
         iy0 = -fdiv(-(2 * oy0 - p.py0), UP) - p.e;
     };
-    auto load_tile = [&](int tile, __half* X) {
+    auto load_tile = [&](int tile) {
         int ox0, oy0, ix0, iy0;
         origin(tile, ox0, oy0, ix0, iy0);
         const int ixa = fdiv(ix0, 8) * 8;
@@ -376,54 +394,70 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
         }
         cp_async_commit();
     };
-
-    if (valid) load_tile(tile0, Xbuf);
-    int buf = 0;
-    for (int tile = tile0; tile < tile_end; ++tile, buf ^= 1) {
+    // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
+    auto write_out = [&](int tile, int sb) {
         int ox0, oy0, ix0, iy0;
         origin(tile, ox0, oy0, ix0, iy0);
-        if (valid) {
-            const __half* X = Xbuf + buf * (K::XBYTES / 2);
-            if (tile + 1 < tile_end) {
-                load_tile(tile + 1, Xbuf + (buf ^ 1) * (K::XBYTES / 2));
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-            const int dx = ix0 - fdiv(ix0, 8) * 8;
-            float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT);
+        const __half* st = stage_base + sb * kCG * (kStageBytes / 2);
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int no = 0; no < 4; ++no)
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh)
-                        *reinterpret_cast<uint32_t*>(stage + (i * 16 + hh * 8 + g) * kSP + no * 8 + 2 * tig) =
-                            pack2(OUT[i][no][hh * 2 + 0] * oscale, OUT[i][no][hh * 2 + 1] * oscale);
-        }
-        __syncthreads();
-        // cooperative write-out: thread -> pixel, 16 channels (32 bytes) per pixel
-        for (int px = threadIdx.x; px < kOT * kOT; px += kCG * 32) {
-            const int ly = px >> 5, lx = px & 31;
+        for (int k = 0; k < 2; ++k) {
+            const int ly = 2 * warp + k, lx = lane;
             const int oy = oy0 + ly, ox = ox0 + lx;
             if (oy < p.Hout && ox < p.Wout) {
-                const __half* sp = stage_all + ly * kSP + lx;
+                const __half* sp = st + ly * kSP + lx;
                 uint32_t w[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * k) * (kStageBytes / 2));
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * k + 1) * (kStageBytes / 2));
-                    w[k] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+                for (int q = 0; q < 8; ++q) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * q) * (kStageBytes / 2));
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * q + 1) * (kStageBytes / 2));
+                    w[q] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
                 }
                 uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + c0);
                 dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
         }
-        __syncthreads();
+    };
+
+    if (valid) load_tile(tile0);
+    for (int i = 0; i < n; ++i) {
+        const int tile = tile0 + i, sb = i & 1;
+        // the staging buffer is free once every warp has written out its share of tile i-2
+        if (i >= 2) mbar_wait(&empty[sb], ((i >> 1) - 1) & 1);
+        if (valid) {
+            cp_async_wait<0>();
+            __syncwarp();
+            int ox0, oy0, ix0, iy0;
+            origin(tile, ox0, oy0, ix0, iy0);
+            const int dx = ix0 - fdiv(ix0, 8) * 8;
+            float OUT[2][4][4];
+            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT, [&]() {
+                __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
+                if (i + 1 < n) load_tile(tile + 1);
+            });
+            __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        *reinterpret_cast<uint32_t*>(stage + (ii * 16 + hh * 8 + g) * kSP + no * 8 + 2 * tig) =
+                            pack2(OUT[ii][no][hh * 2 + 0] * oscale, OUT[ii][no][hh * 2 + 1] * oscale);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[sb]);
+        // write out this warp's share of the PREVIOUS tile while the other warps are still computing tile i
+        if (i >= 1) {
+            mbar_wait(&full[sb ^ 1], ((i - 1) >> 1) & 1);
+            write_out(tile - 1, sb ^ 1);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[sb ^ 1]);
+        }
     }
+    const int last = n - 1;
+    mbar_wait(&full[last & 1], (last >> 1) & 1);
+    write_out(tile0 + last, last & 1);
 }
 
 // ---- host: constant fragments -------------------------------------------------------------------
@@ -567,8 +601,8 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         MB_REQUIRE(a.Cp_out % 16 == 0 && a.Cp_out >= round_up(a.C, kCG), "filtered_lrelu: Cp_out must cover whole 16-channel groups");
         p.y = a.y_nhwc;
         p.Cp_out = a.Cp_out;
-        p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : 4);
-        constexpr int smem = kCG * 2 * K::XBYTES + kCG * kStageBytes;
+        p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
+        constexpr int smem = kCG * K::XBYTES + 2 * kCG * kStageBytes + 64;
         static bool attr_nhwc = false;
         if (!attr_nhwc) {
             MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

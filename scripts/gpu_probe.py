@@ -73,6 +73,9 @@ if __name__ == "__main__":
         conv_case(2, 81, 51, 70, 66, 3)
         conv_case(2, 128, 96, 40, 24, 1)
         conv_case(1, 512, 512, 38, 38, 3)
+        conv_case(2, 51, 32, 100, 90, 3)
+        conv_case(1, 32, 32, 70, 70, 3)
+        conv_case(1, 32, 3, 64, 64, 1, False)
     print("probe done", flush=True)
 
 

@@ -21,11 +21,14 @@ CONV_CASES = [
     (2, 128, 96, 40, 24, 1, True),
     (1, 203, 130, 150, 150, 3, True),
     (1, 32, 3, 64, 64, 1, False),
+    (2, 51, 32, 100, 90, 3, True),
+    (1, 32, 32, 70, 70, 3, True),
+    (1, 96, 64, 33, 41, 3, True),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [1, 0, 2])
+@pytest.mark.parametrize("impl", [1, 0, 2])  # 1 CUDA cores, 0 tcgen05 (32-wide pixel tiles), 2 tcgen05 16-wide tiles
 def test_modulated_conv2d(cuda, case, impl):
     from maua_b200 import ops
 

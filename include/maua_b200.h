@@ -90,6 +90,16 @@ int mb_sg3_geometry(const mb_sg3_cfg* cfg, mb_sg3_layer* layers, int32_t* input_
 int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out);
 void mb_net_destroy(mb_net* net);
 
+/* ---- StyleGAN2 synthesis network --------------------------------------------------------------------
+ * Replaces the reference's in-tree inference network `SynthesisNetwork(w_dim=512, img_resolution=R, img_channels=3)`
+ * (maua/GAN/wrappers/inference/stylegan2.py:385-436; constructed at maua/GAN/wrappers/stylegan2.py:34-36) including
+ * its ops modulated_conv2d / conv2d_resample / upfirdn2d / upsample2d / bias_act (inference/ops.py:65-233).
+ * The returned handle is driven through the same mb_net_* entry points; state-dict keys are the reference's
+ * ("bs.0.const", "bs.3.conv0.affine.weight", "bs.2.conv1.noise_const", "bs.1.torgb.bias", ...); noise_mode "const". */
+int mb_sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base, int channel_max, mb_net** out);
+/* num_ws of the network behind the handle (StyleGAN3: num_layers + 2; StyleGAN2: convs + final ToRGB). */
+int mb_net_num_ws(const mb_net* net);
+
 /* Upload one tensor of the generator state dict.  `name` is the upstream state-dict key
  * ("input.freqs", "input.phases", "input.weight", "input.affine.weight", "input.affine.bias",
  * "input.transform", "L3_52_512.weight", ".bias", ".affine.weight", ".affine.bias",

@@ -17,6 +17,7 @@ import scipy.special
 import torch
 
 from ... import _lib
+from ._native import NativeNet
 
 
 def sg3_cfg(w_dim=512, img_resolution=1024, img_channels=3, channel_base=32768, channel_max=512, num_layers=14,
@@ -162,7 +163,7 @@ class SynthesisLayer(torch.nn.Module):
             radial=bool(g["down_radial"])))
 
 
-class SynthesisNetwork(torch.nn.Module):
+class SynthesisNetwork(NativeNet):
     """``SynthesisNetwork(w_dim=512, img_resolution=1024, img_channels=3)`` as built at
     maua/GAN/wrappers/stylegan3.py:33; forward(ws [B,num_ws,w_dim]) -> float32 [B,3,H,W]."""
 
@@ -180,82 +181,10 @@ class SynthesisNetwork(torch.nn.Module):
         for g in geo["layers"]:
             setattr(self, g["name"], SynthesisLayer(w_dim, g, conv_clamp=self._cfg.conv_clamp))
             self.layer_names.append(g["name"])
-        self._net = None          # mb_net* handle
-        self._uploaded = {}       # state-dict key -> (data_ptr, version, device)
-        self._workspace = {}      # batch -> uint8 tensor
-        self._options = {}
+        self._init_native()
 
-    # ---- library handle management ----------------------------------------------------
-    def _handle(self):
-        if self._net is None:
-            lib = _lib.load()
-            h = C.c_void_p()
-            _lib.check(lib.mb_sg3_create(C.byref(self._cfg), C.byref(h)))
-            self._net = h
-            for k, v in self._options.items():
-                _lib.check(lib.mb_net_set_option(self._net, k.encode(), int(v)))
-        return self._net
-
-    def set_option(self, key, value):
-        """Test / tuning knobs of the library (see include/maua_b200.h mb_net_set_option)."""
-        self._options[key] = int(value)
-        if self._net is not None:
-            _lib.check(_lib.load().mb_net_set_option(self._net, key.encode(), int(value)))
-
-    def __del__(self):
-        try:
-            if self._net is not None:
-                _lib.load().mb_net_destroy(self._net)
-                self._net = None
-        except Exception:
-            pass
-
-    # tensors the reference wrapper edits in place between forwards (wrappers/stylegan3.py:54-59)
-    _POKED = ("input.affine.bias", "input.affine.weight", "input.transform")
-
-    def _param_key(self, name, t):
-        """Identity of a parameter's current value: storage pointer + autograd version counter.  Inference-mode
-        tensors carry no version counter; for those the three tensors the wrapper pokes are fingerprinted."""
-        try:
-            version = t._version
-        except RuntimeError:
-            version = None
-            if name in self._POKED:
-                d = t.detach().double()
-                version = (float(d.sum()), float((d * d).sum()))
-        return (t.data_ptr(), version, str(t.device), tuple(t.shape))
-
-    def _sync_params(self, device):
-        """Upload every parameter / buffer whose storage or version changed since the last forward."""
-        lib = _lib.load()
-        net = self._handle()
-        changed = False
-        keep = []
-        for name, t in list(self.named_parameters()) + list(self.named_buffers()):
-            if t is None:
-                continue
-            key = self._param_key(name, t)
-            if self._uploaded.get(name) == key:
-                continue
-            d = t.detach().to(device=device, dtype=torch.float32).contiguous()
-            keep.append(d)
-            shape = (C.c_int64 * max(d.ndim, 1))(*d.shape)
-            _lib.check(lib.mb_net_set_param(net, name.encode(), _lib.ptr(d), shape, d.ndim, _lib.stream_ptr()))
-            self._uploaded[name] = key
-            changed = True
-        if changed:
-            _lib.check(lib.mb_net_finalize(net, _lib.stream_ptr()))  # synchronises the stream
-        del keep
-
-    def _get_workspace(self, batch, device):
-        key = (batch, str(device))
-        ws = self._workspace.get(key)
-        if ws is None:
-            nbytes = _lib.load().mb_net_workspace_bytes(self._handle(), batch)
-            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-            self._workspace = {key: ws}  # keep only the latest batch size resident
-        off = (-ws.data_ptr()) % 1024
-        return ws, off, ws.numel() - 1024
+    def _create(self, lib, handle_ref):
+        _lib.check(lib.mb_sg3_create(C.byref(self._cfg), handle_ref))
 
     # ---- forward ------------------------------------------------------------------------
     def forward(self, ws, out_fmt="f32", out=None, **unused):
@@ -287,25 +216,6 @@ class SynthesisNetwork(torch.nn.Module):
             _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
                                           C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
         return out
-
-    def read_activation(self, batch):
-        """float32 [B,C,H,W] of the last activation the previous forward produced (x * next style)."""
-        lib = _lib.load()
-        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
-        _lib.check(lib.mb_net_activation_shape(self._handle(), C.byref(c), C.byref(h), C.byref(w)))
-        out = torch.empty(batch, c.value, h.value, w.value, device="cuda", dtype=torch.float32)
-        _lib.check(lib.mb_net_read_activation(self._handle(), 0, batch, _lib.ptr(out), _lib.stream_ptr()))
-        return out
-
-    def profile_read(self):
-        """[(kind, layer, ms)] of the last forward (needs set_option('profile', 1) and a stream sync)."""
-        cap = 8192
-        ms, kind, layer = (C.c_float * cap)(), (C.c_int32 * cap)(), (C.c_int32 * cap)()
-        n = _lib.load().mb_net_profile_read(self._handle(), ms, kind, layer, cap)
-        return [(kind[i], layer[i], ms[i]) for i in range(n)]
-
-    def last_launch_count(self):
-        return _lib.load().mb_net_last_launch_count(self._handle())
 
 
 SG3_R_KWARGS = dict(conv_kernel=1, channel_base=65536, channel_max=1024, use_radial_filters=True)

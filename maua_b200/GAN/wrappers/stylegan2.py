@@ -1,0 +1,111 @@
+"""StyleGAN2 wrapper: mirrors maua/GAN/wrappers/stylegan2.py:21-213 on top of the sm_100a network (csrc/sg2.cu).
+
+Kept in behaviour: ctor arguments, ``layer_names`` (:48-51), ``modulation_targets``, ``forward(latents, ..., **noise)``
+swapping each SynthesisLayer's ``noise_const`` for the per-frame map of the batch (:81-96, bicubic resize + warning on
+a shape mismatch) and ``make_noise_pyramid`` (:196-213).  The network-bending feature warps (translation / zoom /
+rotation hooks, :153-194) and non-native output sizes (:100-151) are row N2 of SURVEY §8f.
+"""
+import warnings
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from ..networks import stylegan2
+from .stylegan import StyleGAN, StyleGANMapper, StyleGANSynthesizer, load_network
+
+
+class StyleGAN2Mapper(StyleGANMapper):
+    MapperClsFn = lambda inference: stylegan2.MappingNetwork
+
+
+class StyleGAN2Synthesizer(StyleGANSynthesizer):
+    __constants__ = ["w_dim", "num_ws", "layer_names"]
+
+    def __init__(
+        self, model_file: str, inference: bool, output_size: Optional[Tuple[int, int]], strategy: str, layer: int
+    ) -> None:
+        super().__init__()
+        if model_file is None or model_file == "None":
+            self.G_synth = stylegan2.SynthesisNetwork(w_dim=512, img_resolution=1024, img_channels=3)
+        else:
+            self.G_synth = load_network(model_file, inference).synthesis
+        if output_size is None:
+            output_size = (self.G_synth.img_resolution, self.G_synth.img_resolution)
+        self.w_dim, self.num_ws = self.G_synth.w_dim, self.G_synth.num_ws
+        self.layer_names = [
+            f"bs.{c//2}.conv{1 if block_size == 4 else c % 2}"
+            for c, block_size in enumerate(sorted(self.G_synth.block_resolutions * 2))
+        ]
+        self.modulation_targets = {
+            "latent_w": (self.w_dim,),
+            "latent_w_plus": (self.num_ws, self.w_dim),
+            "translation": (2,),
+            "rotation": (1,),
+        }
+        self.translate_hook, self.rotate_hook, self.zoom_hook = None, None, None
+        self.change_output_resolution(output_size, strategy, layer)
+
+    def forward(
+        self,
+        latents: Tensor,
+        translation: Optional[Tensor] = None,
+        translation_layer: int = 7,
+        zoom: Optional[Tensor] = None,
+        zoom_layer: int = 7,
+        zoom_center: Optional[int] = None,
+        rotation: Optional[Tensor] = None,
+        rotation_layer: int = 7,
+        rotation_center: Optional[int] = None,
+        **noise,
+    ) -> Tensor:
+        if translation is not None or zoom is not None or rotation is not None:
+            raise NotImplementedError(
+                "feature-map translation / zoom / rotation (kornia hooks, maua/GAN/wrappers/stylegan2.py:153-194) "
+                "are not built yet (SURVEY §8f N2)"
+            )
+        if noise:
+            noises, l = list(noise.values()), 0
+            for block in self.G_synth.bs:
+                if l >= len(noises):
+                    continue
+                for c in ([block.conv0] if getattr(block, "conv0", None) is not None else []) + [block.conv1]:
+                    if l >= len(noises):
+                        break
+                    noise_l = noises[l].to(c.noise_const, non_blocking=True)
+                    if (noise_l.shape[-2], noise_l.shape[-1]) != (c.noise_const.shape[-2], c.noise_const.shape[-1]):
+                        warnings.warn(
+                            f"Supplied noise for SynthesisLayer {l} has shape {noise_l.shape} while the expected "
+                            f"shape is {c.noise_const.shape}. Resizing the supplied noise to match..."
+                        )
+                        h, w = c.noise_const.shape[-2], c.noise_const.shape[-1]
+                        noise_l = torch.nn.functional.interpolate(noise_l, (h, w), mode="bicubic", align_corners=False)
+                    setattr(c, "noise_const", noise_l)
+                    l += 1
+        return self.G_synth.forward(latents, noise_mode="const")
+
+    def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
+        self.refresh_model_hooks()
+        if tuple(output_size) != (self.G_synth.img_resolution, self.G_synth.img_resolution):
+            raise NotImplementedError(
+                "non-native output sizes (feature-map resize hooks, maua/GAN/wrappers/stylegan2.py:100-151) "
+                "are not built yet (SURVEY §8f N2)"
+            )
+        self.output_size = output_size
+
+    def make_noise_pyramid(self, noise, layer_limit=8):
+        noises = {}
+        for l, layer in enumerate(self.layer_names[1:]):
+            if l > layer_limit:
+                continue
+            _, block, conv = layer.split(".")
+            synth_layer = getattr(self.G_synth.bs[int(block)], conv)
+            h, w = synth_layer.noise_const.shape[-2], synth_layer.noise_const.shape[-1]
+            noises[f"noise{l}"] = torch.nn.functional.interpolate(noise, (h, w), mode="bicubic", align_corners=False).cpu()
+            noises[f"noise{l}"] /= noises[f"noise{l}"].std((1, 2, 3), keepdim=True)
+        return noises
+
+
+class StyleGAN2(StyleGAN):
+    SynthesizerCls = StyleGAN2Synthesizer
+    MapperCls = StyleGAN2Mapper

@@ -48,6 +48,8 @@ _SIGNATURES = {
                                   C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mb_sg3_create": (C.c_int, [C.POINTER(SG3Cfg), C.POINTER(_P)]),
     "mb_net_destroy": (None, [_P]),
+    "mb_sg2_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mb_net_num_ws": (C.c_int, [_P]),
     "mb_net_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
     "mb_net_finalize": (C.c_int, [_P, _P]),
     "mb_net_workspace_bytes": (C.c_size_t, [_P, C.c_int]),

@@ -43,7 +43,7 @@ struct Geo {
 };
 
 struct KArgs {
-    int B, Cin, Cout, Hout, Wout, Wp_out, ksz, nCC;
+    int B, Cin, Cout, Hout, Wout, Wp_out, ksz, nCC, pad;
     int tiles_m, tiles_w, tiles_h, total_tiles;
     const float* d;  // [B][Cout] or nullptr
     const float* bias;  // [Cout] or nullptr
@@ -67,8 +67,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int pad = a.ksz - 1;
-    const int patch_rows = G::TH + pad;
+    const int pad = a.pad;
+    const int patch_rows = G::TH + a.ksz - 1;
     const uint32_t stage_bytes = a.ksz * kATileBytes + patch_rows * G::SLAB;
     const int iters = a.ksz * a.nCC;
 
@@ -233,7 +233,9 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     }
     const int tw = p.tile_w == 16 ? 16 : 32;
     const int th = kTileN / tw;
-    const int pad = p.ksz - 1;
+    const int pad = p.pad;
+    const int halo = p.ksz - 1;
+    MB_REQUIRE(pad >= 0 && pad <= halo, "conv_tc: padding %d unsupported for kernel size %d", pad, p.ksz);
     MB_REQUIRE(p.ksz == 1 || p.ksz == 3, "conv_tc: kernel size %d unsupported", p.ksz);
     MB_REQUIRE(p.Cp_in % 8 == 0 && p.Wp_out % 8 == 0, "conv_tc: channel / row pitch must be a multiple of 8 elements");
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
@@ -264,7 +266,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cp_in), static_cast<cuuint64_t>(p.Win),
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
         cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
-        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th + pad), 1};
+        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th + halo), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -278,8 +280,8 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
 
     KArgs a;
     a.B = p.B; a.Cin = p.Cin; a.Cout = p.Cout;
-    a.Hout = p.Hin + pad; a.Wout = p.Win + pad; a.Wp_out = p.Wp_out;
-    a.ksz = p.ksz; a.nCC = nCC;
+    a.Hout = p.Hin + 2 * pad - halo; a.Wout = p.Win + 2 * pad - halo; a.Wp_out = p.Wp_out;
+    a.ksz = p.ksz; a.nCC = nCC; a.pad = pad;
     a.tiles_m = Mp / kTileM;
     a.tiles_w = ceil_div(a.Wout, tw);
     a.tiles_h = ceil_div(a.Hout, th);

@@ -24,6 +24,7 @@ struct ConvTcArgs {
     const float* bias;  // [Cout] added after demodulation (the layer bias filtered_lrelu would add) or nullptr
     __half* y;          // planar [B][Cout][Hin+k-1][Wp_out]
     int B, Cin, Cout, Hin, Win, Cp_in, Wp_out, ksz;
+    int pad;            // zero padding per side (StyleGAN3: ksz-1 'full', StyleGAN2: ksz/2 'same'); output = in + 2*pad - (ksz-1)
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
     int num_sms;
 };
@@ -36,7 +37,7 @@ size_t packed_weight_elems(int Cout, int Cin, int ksz);
 // W f32 [Cout][Cin][k][k] -> optional per-cout pre-normalisation (demodulate) -> fp16 packed,
 // wsqT f32 [Cin][Cout] = sum_k Wn^2 (for the demodulation coefficients).
 int pack_weights_launch(const float* w, __half* wpk, float* wsqT, int Cout, int Cin, int ksz, int prenorm,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int flip = 0);  // flip: spatially mirrored taps (transposed conv as conv)
 // Plain CUDA-core direct convolution on the same operands (bisecting aid, see mb_net_set_conv_impl).
 int conv_simt_launch(const ConvTcArgs& p, cudaStream_t stream);
 
@@ -48,6 +49,7 @@ struct StyleLayerDesc {
     float* s_out;           // [B][Cin]  normalised style * input_gain
     float* d_out;           // [B][Cout] or nullptr
     int Cin, Cout, ws_index, demodulate;
+    int normalize_style;    // StyleGAN3 rescales the style to unit RMS before demodulation, StyleGAN2 does not
     float style_scale;      // torgb: 1/sqrt(Cin*k*k), else 1
 };
 constexpr int kMaxLayers = 24;

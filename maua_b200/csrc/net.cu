@@ -14,6 +14,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "sg2.h"
 
 namespace mb {
 
@@ -68,6 +69,7 @@ struct LayerState {
 };
 
 struct mb_net {
+    mb::Sg2Net* sg2 = nullptr;  // set: this handle is a StyleGAN2 network (sg2.cu); the fields below are unused
     mb_sg3_cfg cfg;
     std::vector<LayerState> layers;  // num_layers + 1
     int in_channels = 0, in_size = 0;
@@ -335,8 +337,36 @@ extern "C" int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out) {
     return MB_OK;
 }
 
+/* StyleGAN2 synthesis network of the reference's in-tree inference module (maua/GAN/wrappers/inference/stylegan2.py:385,
+ * ctor call maua/GAN/wrappers/stylegan2.py:34-36).  The handle is used with the same mb_net_* entry points; parameter names
+ * are the reference's state-dict keys ("bs.3.conv0.affine.weight", "bs.0.const", "bs.2.conv1.noise_const", ...). */
+extern "C" int mb_sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base, int channel_max, mb_net** out) {
+    MB_REQUIRE(out, "mb_sg2_create: null argument");
+    if (g_device < 0) {
+        int r = ensure_init();
+        if (r != MB_OK) return r;
+    }
+    Sg2Net* n = nullptr;
+    int r = sg2_create(w_dim, img_resolution, img_channels, channel_base, channel_max, &n);
+    if (r != MB_OK) return r;
+    mb_net* net = new mb_net();
+    net->sg2 = n;
+    *out = net;
+    return MB_OK;
+}
+
+extern "C" int mb_net_num_ws(const mb_net* net) {
+    if (!net) return 0;
+    return net->sg2 ? sg2_num_ws(net->sg2) : net->cfg.num_layers + 2;
+}
+
 extern "C" void mb_net_destroy(mb_net* net) {
     if (!net) return;
+    if (net->sg2) {
+        sg2_destroy(net->sg2);
+        delete net;
+        return;
+    }
     for (auto& kv : net->by_name)
         if (kv.second->dev) cudaFree(kv.second->dev);
     for (auto& L : net->layers) {
@@ -351,6 +381,7 @@ extern "C" void mb_net_destroy(mb_net* net) {
 extern "C" int mb_net_set_param(mb_net* net, const char* name, const float* data, const int64_t* shape, int ndim,
                                 mb_stream stream) {
     MB_REQUIRE(net && name && data, "mb_net_set_param: null argument");
+    if (net->sg2) return sg2_set_param(net->sg2, name, data, shape, ndim, static_cast<cudaStream_t>(stream));
     auto it = net->by_name.find(name);
     MB_REQUIRE(it != net->by_name.end(), "mb_net_set_param: unknown parameter '%s'", name);
     Param& p = *it->second;
@@ -381,6 +412,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
     MB_REQUIRE(net, "mb_net_finalize: null net");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (net->sg2) return sg2_finalize(net->sg2, stream);
     for (auto& kv : net->by_name) {
         if (!kv.second->set) {
             set_error("mb_net_finalize: parameter '%s' was never set", kv.first.c_str());
@@ -454,11 +486,13 @@ WsLayout ws_layout(const mb_net* net, int B) {
 
 extern "C" size_t mb_net_workspace_bytes(const mb_net* net, int batch) {
     if (!net || batch <= 0) return 0;
+    if (net->sg2) return sg2_workspace_bytes(net->sg2, batch);
     return ws_layout(net, batch).total;
 }
 
 extern "C" int mb_net_set_conv_impl(mb_net* net, int impl) {
     MB_REQUIRE(net && (impl == 0 || impl == 1), "mb_net_set_conv_impl: bad argument");
+    if (net->sg2) sg2_set_conv_impl(net->sg2, impl);
     net->conv_impl = impl;
     return MB_OK;
 }
@@ -466,7 +500,10 @@ extern "C" int mb_net_set_conv_impl(mb_net* net, int impl) {
 extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     MB_REQUIRE(net && key, "mb_net_set_option: null argument");
     const std::string k = key;
-    if (k == "conv_impl") net->conv_impl = value;
+    if (k == "conv_impl") {
+        net->conv_impl = value;
+        if (net->sg2) sg2_set_conv_impl(net->sg2, value);
+    }
     else if (k == "conv_tile_w") net->conv_tile_w = value == 16 ? 16 : 32;
     else if (k == "flrelu_impl") net->flrelu_impl = value;
     else if (k == "debug_stop") net->debug_stop = value;
@@ -479,7 +516,10 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     return MB_OK;
 }
 
-extern "C" int mb_net_last_launch_count(const mb_net* net) { return net ? net->last_launches : 0; }
+extern "C" int mb_net_last_launch_count(const mb_net* net) {
+    if (net && net->sg2) return sg2_last_launches(net->sg2);
+    return net ? net->last_launches : 0;
+}
 
 /* Per-launch device times of the last forward run with option "profile"=1 (call after the stream has
  * been synchronised).  kind: 0 styles, 1 input, 2 modulated conv, 3 filtered_lrelu, 4 layout
@@ -505,6 +545,10 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     MB_REQUIRE(net && ws && out && workspace, "mb_net_forward: null argument");
     MB_REQUIRE(B > 0, "mb_net_forward: batch must be positive");
     MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
+    if (net->sg2) {
+        MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
+        return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, static_cast<cudaStream_t>(stream_));
+    }
     if (!net->finalized) {
         set_error("mb_net_forward: call mb_net_finalize after setting parameters");
         return MB_ESTATE;
@@ -569,6 +613,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
             d.Cout = L.g.out_channels;
             d.ws_index = i + 1;
             d.demodulate = !L.g.is_torgb;
+            d.normalize_style = 1;
             d.style_scale = L.g.is_torgb ? 1.0f / sqrtf(static_cast<float>(L.g.in_channels * L.g.conv_kernel * L.g.conv_kernel)) : 1.0f;
         }
         if ((r = styles_launch(sa, stream)) != MB_OK) return r;
@@ -643,6 +688,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         const int hc = g.in_size + g.conv_kernel - 1;
         ca.Wp_out = pitch8(hc);
         ca.ksz = g.conv_kernel;
+        ca.pad = g.conv_kernel - 1;
         ca.tile_w = net->conv_tile_w;
         ca.num_sms = g_num_sms;
         r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
@@ -744,6 +790,7 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
         ConvTcArgs ca;
         ca.x = xh; ca.wpk = wpk; ca.d = d; ca.bias = nullptr; ca.y = yh;
         ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
+        ca.pad = k - 1;
         ca.tile_w = (impl == 2) ? 16 : 32;
         ca.num_sms = g_num_sms;
         r = (impl == 1) ? conv_simt_launch(ca, stream) : conv_tc_launch(ca, stream);

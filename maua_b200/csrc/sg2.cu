@@ -1,0 +1,544 @@
+// StyleGAN2 synthesis network on the sm_100a kernels: replaces the reference's in-tree inference network
+// maua/GAN/wrappers/inference/stylegan2.py:195-436 (SynthesisLayer / ToRGBLayer / SynthesisBlock /
+// SynthesisNetwork, architecture 'skip') and its ops (inference/ops.py: modulated_conv2d :146, conv2d_resample
+// :189, upfirdn2d :87, upsample2d :117, bias_act :65).
+//
+// Per block (resolution r):  conv0 = stride-2 transposed 3x3 modulated conv + 4x4 FIR  ->  conv1 = 3x3 'same'
+// modulated conv  ->  ToRGB 1x1 (no demodulation) added to the FIR-upsampled image of the previous block.
+//   * both 3x3 convs run on the tcgen05 implicit-GEMM kernel (conv_tc.cu): conv1 with padding 1; conv0 as a
+//     stride-1 'full' convolution with spatially flipped taps over the zero-inserted input (identical arithmetic
+//     to conv_transpose2d(stride 2), ops.py:224);
+//   * everything between two convs is ONE fused kernel (sg2_act_kernel): [4x4 FIR, gain 4] + noise + bias +
+//     leaky-ReLU*sqrt2 + clamp (bias_act), the next conv's style and the planar -> channels-last store, plus the
+//     ToRGB reduction over channels and the skip-image accumulation.
+// Styles are folded into the activations and the demodulation coefficient into the conv epilogue, exactly as for
+// StyleGAN3 (net.cu); the feature map after conv1 has two consumers (ToRGB and the next conv0) with different
+// styles, so the fused kernel applies each while the activation tile is in shared memory.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sg2.h"
+
+namespace mb {
+namespace {
+
+inline int cpad16(int c) { return (c + 15) / 16 * 16; }
+
+// x channels-last [B][h][w][Cp] -> zero-inserted [B][2h-1][2w-1][Cp] (uint4 = 8 channels per thread)
+__global__ void zero_insert_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int h, int w, int cp8) {
+    const int H2 = 2 * h - 1, W2 = 2 * w - 1;
+    const long long total = static_cast<long long>(B) * H2 * W2 * cp8;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % cp8);
+        long long r = idx / cp8;
+        const int X = static_cast<int>(r % W2); r /= W2;
+        const int Y = static_cast<int>(r % H2);
+        const int b = static_cast<int>(r / H2);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!(X & 1) && !(Y & 1)) v = x[((static_cast<long long>(b) * h + (Y >> 1)) * w + (X >> 1)) * cp8 + c];
+        y[idx] = v;
+    }
+}
+
+// const [C][r][r] f32 * style[b][c] -> channels-last fp16 [B][r][r][Cp]
+__global__ void const_input_kernel(const float* __restrict__ cst, const float* __restrict__ style, __half* __restrict__ out,
+                                   int B, int C, int r, int Cp) {
+    const long long total = static_cast<long long>(B) * r * r * Cp;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % Cp);
+        long long q = idx / Cp;
+        const int px = static_cast<int>(q % (r * r));
+        const int b = static_cast<int>(q / (r * r));
+        out[idx] = __float2half_rn(c < C ? cst[c * r * r + px] * style[b * C + c] : 0.0f);
+    }
+}
+
+struct ActArgs {
+    const __half* y;        // planar conv output [B][C][Hy][Wpy]; Hy = R (+1 with FIR)
+    const float* noise;     // [R][R] (noise_bstride 0) or per-frame [B][R][R] (noise_bstride R*R) or nullptr
+    const float* bias;      // [C]
+    const float* style_next;  // [B][C] or nullptr (last block)
+    __half* x_next;         // channels-last [B][R][R][Cp] or nullptr
+    const float* rgb_w;     // [3][C] ToRGB weight or nullptr (no ToRGB after conv0)
+    const float* rgb_style; // [B][C] (already * 1/sqrt(C))
+    const float* rgb_bias;  // [3]
+    const float* img_prev;  // [B][3][R][R] upsampled skip image or nullptr
+    float* img;             // [B][3][R][R]
+    int B, C, R, Hy, Wpy, Cp, fir, nimg;
+    long long noise_bstride;
+    float clamp;
+};
+constexpr int kActP = 32;  // pixels per CTA
+
+// one CTA = (b, row h, 32 pixels) x all channels
+__global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
+    extern __shared__ float xs[];  // [C][kActP + 1]
+    const int w0 = blockIdx.x * kActP, h = blockIdx.y, b = blockIdx.z;
+    // separable [1,3,3,1]/8 * 2 per axis = the 4x4 FIR of setup_filter([1,3,3,1]) with gain up^2 = 4 (ops.py:225,236)
+    const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    for (int idx = threadIdx.x; idx < a.C * kActP; idx += blockDim.x) {
+        const int c = idx / kActP, px = idx - c * kActP;
+        const int w = w0 + px;
+        float v = 0.0f;
+        if (w < a.R) {
+            const __half* yp = a.y + (static_cast<long long>(b) * a.C + c) * a.Hy * a.Wpy;
+            if (a.fir) {
+                // upfirdn2d(pad 1): out[h][w] = sum_{ky,kx} f[ky] f[kx] y[h - 1 + ky][w - 1 + kx], zero outside
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) {
+                    const int yy = h - 1 + ky;
+                    if (yy < 0 || yy >= a.Hy) continue;
+                    float row = 0.0f;
+#pragma unroll
+                    for (int kx = 0; kx < 4; ++kx) {
+                        const int xx = w - 1 + kx;
+                        if (xx >= 0 && xx < a.Hy) row = fmaf(f4[kx], __half2float(yp[static_cast<long long>(yy) * a.Wpy + xx]), row);
+                    }
+                    v = fmaf(f4[ky], row, v);
+                }
+            } else {
+                v = __half2float(yp[static_cast<long long>(h) * a.Wpy + w]);
+            }
+            if (a.noise) v += a.noise[b * a.noise_bstride + h * a.R + w];
+            v += a.bias[c];
+            v = (v < 0.0f ? v * 0.2f : v) * 1.41421356237309515f;
+            v = fminf(fmaxf(v, -a.clamp), a.clamp);
+        }
+        xs[c * (kActP + 1) + px] = v;
+    }
+    __syncthreads();
+    const int npx = min(kActP, a.R - w0);
+    if (a.x_next) {
+        __half* o = a.x_next + ((static_cast<long long>(b) * a.R + h) * a.R + w0) * a.Cp;
+        for (int idx = threadIdx.x; idx < npx * (a.Cp / 2); idx += blockDim.x) {
+            const int px = idx / (a.Cp / 2), c = (idx - px * (a.Cp / 2)) * 2;
+            const float s0 = c < a.C ? a.style_next[b * a.C + c] : 0.0f;
+            const float s1 = c + 1 < a.C ? a.style_next[b * a.C + c + 1] : 0.0f;
+            const float v0 = c < a.C ? xs[c * (kActP + 1) + px] * s0 : 0.0f;
+            const float v1 = c + 1 < a.C ? xs[(c + 1) * (kActP + 1) + px] * s1 : 0.0f;
+            *reinterpret_cast<__half2*>(o + static_cast<long long>(px) * a.Cp + c) = __floats2half2_rn(v0, v1);
+        }
+    }
+    if (a.rgb_w) {
+        // ToRGB: 1x1 modulated conv without demodulation + bias + clamp, added to the upsampled skip image
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int item = warp; item < npx * a.nimg; item += nw) {
+            const int px = item / a.nimg, o = item - px * a.nimg;
+            float acc = 0.0f;
+            for (int c = lane; c < a.C; c += 32)
+                acc = fmaf(xs[c * (kActP + 1) + px], a.rgb_w[o * a.C + c] * a.rgb_style[b * a.C + c], acc);
+            for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+            if (lane == 0) {
+                float v = fminf(fmaxf(acc + a.rgb_bias[o], -a.clamp), a.clamp);
+                const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.R + h) * a.R + w0 + px;
+                if (a.img_prev) v += a.img_prev[oi];
+                a.img[oi] = v;
+            }
+        }
+    }
+}
+
+// upsample2d(img, [1,3,3,1]): zero-insert x2, pad (2,1), 4x4 FIR with gain 4 (ops.py:117-133) on [N][r][r] planes
+__global__ void upsample_rgb_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int r) {
+    const int R = 2 * r;
+    const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    const long long total = static_cast<long long>(N) * R * R;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(idx % R);
+        long long q = idx / R;
+        const int Y = static_cast<int>(q % R);
+        const int n = static_cast<int>(q / R);
+        const float* xp = x + static_cast<long long>(n) * r * r;
+        float acc = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const int my = Y + ky - 2;  // index into the zero-inserted signal
+            if (my < 0 || (my & 1) || (my >> 1) >= r) continue;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const int mx = X + kx - 2;
+                if (mx < 0 || (mx & 1) || (mx >> 1) >= r) continue;
+                acc = fmaf(f4[ky] * f4[kx], xp[(my >> 1) * r + (mx >> 1)], acc);
+            }
+        }
+        y[idx] = acc;
+    }
+}
+
+__global__ void img_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int B, int C, int R) {
+    const long long total = static_cast<long long>(B) * R * R * C;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(idx % C);
+        long long q = idx / C;
+        const int px = static_cast<int>(q % (static_cast<long long>(R) * R));
+        const int b = static_cast<int>(q / (static_cast<long long>(R) * R));
+        float v = (img[(static_cast<long long>(b) * C + c) * R * R + px] + 1.0f) * 0.5f;
+        v = fminf(fmaxf(v, 0.0f), 1.0f);
+        out[idx] = static_cast<uint8_t>(rintf(v * 255.0f));
+    }
+}
+
+int grid1d(long long total) {
+    long long g = (total + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    return g < 1 ? 1 : static_cast<int>(g);
+}
+
+}  // namespace
+
+struct Sg2Param {
+    float* dev = nullptr;
+    std::vector<int64_t> shape;
+    size_t numel = 0;      // elements currently held
+    size_t capacity = 0;   // elements allocated
+    size_t plane = 0;      // noise maps only: r*r; numel may then be any multiple of it (per-frame noise [B,1,r,r])
+    bool set = false;
+};
+struct Sg2Layer {   // one modulated conv (conv0 / conv1) or ToRGB
+    int cin = 0, cout = 0, res = 0, up = 1, ksz = 3;
+    Sg2Param affine_w, affine_b, weight, bias, noise;
+    __half* wpk = nullptr;
+    float* wsqT = nullptr;
+};
+struct Sg2Block {
+    int res = 0, cin = 0, cout = 0;
+    Sg2Param cst;
+    Sg2Layer conv0, conv1, torgb;
+    bool has_conv0 = false;
+};
+struct Sg2Net {
+    int w_dim = 512, res = 0, img_channels = 3, num_ws = 0;
+    std::vector<Sg2Block> blocks;
+    std::map<std::string, Sg2Param*> by_name;
+    bool finalized = false;
+    int conv_impl = 0;
+    int last_launches = 0;
+};
+
+static int sg2_alloc(Sg2Param& p, std::initializer_list<int64_t> shape) {
+    p.shape.assign(shape.begin(), shape.end());
+    p.numel = 1;
+    for (int64_t s : p.shape) p.numel *= static_cast<size_t>(s);
+    MB_CUDA(cudaMalloc(&p.dev, sizeof(float) * p.numel));
+    p.capacity = p.numel;
+    return MB_OK;
+}
+
+void sg2_destroy(Sg2Net* n) {
+    if (!n) return;
+    for (auto& kv : n->by_name)
+        if (kv.second->dev) cudaFree(kv.second->dev);
+    for (auto& b : n->blocks)
+        for (Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
+            if (L->wpk) cudaFree(L->wpk);
+            if (L->wsqT) cudaFree(L->wsqT);
+        }
+    delete n;
+}
+
+int sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base, int channel_max, Sg2Net** out) {
+    MB_REQUIRE(img_resolution >= 8 && (img_resolution & (img_resolution - 1)) == 0 && img_resolution <= 2048,
+               "mb_sg2_create: img_resolution must be a power of two in [8, 2048]");
+    MB_REQUIRE(img_channels >= 1 && img_channels <= 4, "mb_sg2_create: img_channels must be 1..4");
+    Sg2Net* n = new Sg2Net();
+    n->w_dim = w_dim; n->res = img_resolution; n->img_channels = img_channels;
+    auto ch = [&](int r) { int c = channel_base / r; return c < channel_max ? c : channel_max; };
+    int bi = 0;
+    for (int r = 4; r <= img_resolution; r *= 2, ++bi) {
+        n->blocks.emplace_back();
+    }
+    bi = 0;
+    for (int r = 4; r <= img_resolution; r *= 2, ++bi) {
+        Sg2Block& b = n->blocks[bi];
+        b.res = r; b.cout = ch(r); b.cin = r > 4 ? ch(r / 2) : 0; b.has_conv0 = r > 4;
+        const std::string pre = "bs." + std::to_string(bi) + ".";
+        auto add_layer = [&](Sg2Layer& L, const std::string& name, int cin, int cout, int ksz, int up, bool noise) -> int {
+            L.cin = cin; L.cout = cout; L.res = r; L.up = up; L.ksz = ksz;
+            int rc;
+            if ((rc = sg2_alloc(L.affine_w, {cin, w_dim})) != MB_OK) return rc;
+            if ((rc = sg2_alloc(L.affine_b, {cin})) != MB_OK) return rc;
+            if ((rc = sg2_alloc(L.weight, {cout, cin, ksz, ksz})) != MB_OK) return rc;
+            if ((rc = sg2_alloc(L.bias, {cout})) != MB_OK) return rc;
+            n->by_name[pre + name + ".affine.weight"] = &L.affine_w;
+            n->by_name[pre + name + ".affine.bias"] = &L.affine_b;
+            n->by_name[pre + name + ".weight"] = &L.weight;
+            n->by_name[pre + name + ".bias"] = &L.bias;
+            if (noise) {
+                if ((rc = sg2_alloc(L.noise, {r, r})) != MB_OK) return rc;
+                L.noise.plane = static_cast<size_t>(r) * r;
+                n->by_name[pre + name + ".noise_const"] = &L.noise;
+            }
+            if (ksz == 3) {
+                if (cudaMalloc(&L.wpk, packed_weight_elems(cout, cin, 3) * sizeof(__half)) != cudaSuccess ||
+                    cudaMalloc(&L.wsqT, sizeof(float) * cin * cout) != cudaSuccess) {
+                    set_error("mb_sg2_create: cudaMalloc failed");
+                    return MB_ECUDA;
+                }
+            }
+            return MB_OK;
+        };
+        int rc = MB_OK;
+        if (!b.has_conv0) {
+            rc = sg2_alloc(b.cst, {b.cout, r, r});
+            n->by_name[pre + "const"] = &b.cst;
+        } else {
+            rc = add_layer(b.conv0, "conv0", b.cin, b.cout, 3, 2, true);
+        }
+        if (rc == MB_OK) rc = add_layer(b.conv1, "conv1", b.cout, b.cout, 3, 1, true);
+        if (rc == MB_OK) rc = add_layer(b.torgb, "torgb", b.cout, img_channels, 1, 1, false);
+        if (rc != MB_OK) {
+            sg2_destroy(n);
+            return rc;
+        }
+        n->num_ws += b.has_conv0 ? 2 : 1;
+    }
+    n->num_ws += 1;  // the last block's ToRGB
+    *out = n;
+    return MB_OK;
+}
+
+int sg2_set_param(Sg2Net* n, const char* name, const float* data, const int64_t* shape, int ndim, cudaStream_t stream) {
+    auto it = n->by_name.find(name);
+    if (it == n->by_name.end()) {
+        // buffers of the reference state dict that carry no information for this implementation
+        const std::string s = name;
+        if (s.size() > 15 && s.compare(s.size() - 15, 15, "resample_filter") == 0) return MB_OK;
+        set_error("mb_net_set_param: unknown StyleGAN2 parameter '%s'", name);
+        return MB_EINVAL;
+    }
+    Sg2Param& p = *it->second;
+    size_t numel = 1;
+    for (int i = 0; i < ndim; ++i) numel *= static_cast<size_t>(shape[i]);
+    if (p.plane) {
+        // the reference swaps noise_const for a per-frame [B,1,r,r] tensor on every call (wrappers/stylegan2.py:81-96)
+        MB_REQUIRE(numel >= p.plane && numel % p.plane == 0, "mb_net_set_param: '%s' has %zu elements, expected a multiple of %zu",
+                   name, numel, p.plane);
+        if (numel > p.capacity) {
+            MB_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(p.dev);
+            p.dev = nullptr; p.capacity = 0;
+            MB_CUDA(cudaMalloc(&p.dev, sizeof(float) * numel));
+            p.capacity = numel;
+        }
+        p.numel = numel;
+        MB_CUDA(cudaMemcpyAsync(p.dev, data, sizeof(float) * numel, cudaMemcpyDeviceToDevice, stream));
+        p.set = true;
+        return MB_OK;  // noise maps feed no derived operand: the network stays finalized
+    }
+    MB_REQUIRE(numel == p.numel, "mb_net_set_param: '%s' has %zu elements, expected %zu", name, numel, p.numel);
+    MB_CUDA(cudaMemcpyAsync(p.dev, data, sizeof(float) * p.numel, cudaMemcpyDeviceToDevice, stream));
+    p.set = true;
+    n->finalized = false;
+    return MB_OK;
+}
+
+int sg2_finalize(Sg2Net* n, cudaStream_t stream) {
+    for (auto& kv : n->by_name)
+        if (!kv.second->set) {
+            set_error("mb_net_finalize: StyleGAN2 parameter '%s' was never set", kv.first.c_str());
+            return MB_ESTATE;
+        }
+    for (auto& b : n->blocks) {
+        int rc;
+        if (b.has_conv0 && (rc = pack_weights_launch(b.conv0.weight.dev, b.conv0.wpk, b.conv0.wsqT, b.conv0.cout, b.conv0.cin, 3, 0,
+                                                     stream, /*flip=*/1)) != MB_OK)
+            return rc;
+        if ((rc = pack_weights_launch(b.conv1.weight.dev, b.conv1.wpk, b.conv1.wsqT, b.conv1.cout, b.conv1.cin, 3, 0, stream, 0)) != MB_OK)
+            return rc;
+    }
+    MB_CUDA(cudaStreamSynchronize(stream));
+    n->finalized = true;
+    return MB_OK;
+}
+
+namespace {
+struct Sg2Ws {
+    size_t styles, d, x, xu, y, img0, img1, total;
+    std::vector<size_t> style_l, d_l;  // per layer (conv0, conv1, torgb per block) float offsets
+};
+Sg2Ws sg2_ws(const Sg2Net* n, int B) {
+    Sg2Ws w;
+    size_t ns = 0, nd = 0, mx = 0, mxu = 0, my = 0;
+    for (const auto& b : n->blocks) {
+        for (const Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
+            w.style_l.push_back(ns);
+            w.d_l.push_back(nd);
+            ns += static_cast<size_t>(B) * L->cin;
+            nd += static_cast<size_t>(B) * L->cout;
+        }
+        const size_t r = b.res;
+        mx = std::max(mx, static_cast<size_t>(B) * r * r * cpad16(b.cout));
+        if (b.has_conv0) {
+            mx = std::max(mx, static_cast<size_t>(B) * (r / 2) * (r / 2) * cpad16(b.cin));
+            mxu = std::max(mxu, static_cast<size_t>(B) * (r - 1) * (r - 1) * cpad16(b.cin));
+            my = std::max(my, static_cast<size_t>(B) * b.cout * (r + 1) * pitch8(static_cast<int>(r + 1)));
+        }
+        my = std::max(my, static_cast<size_t>(B) * b.cout * r * pitch8(static_cast<int>(r)));
+    }
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 1024); return o; };
+    w.styles = take(ns * 4); w.d = take(nd * 4);
+    w.x = take(mx * 2); w.xu = take(mxu * 2); w.y = take(my * 2);
+    const size_t img = static_cast<size_t>(B) * n->img_channels * n->res * n->res * 4;
+    w.img0 = take(img); w.img1 = take(img);
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+size_t sg2_workspace_bytes(const Sg2Net* n, int B) { return sg2_ws(n, B).total; }
+int sg2_num_ws(const Sg2Net* n) { return n->num_ws; }
+int sg2_last_launches(const Sg2Net* n) { return n->last_launches; }
+void sg2_set_conv_impl(Sg2Net* n, int impl) { n->conv_impl = impl; }
+
+int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
+                int num_sms, cudaStream_t stream) {
+    if (!n->finalized) {
+        set_error("mb_net_forward: call mb_net_finalize after setting parameters");
+        return MB_ESTATE;
+    }
+    const Sg2Ws wl = sg2_ws(n, B);
+    if (workspace_bytes < wl.total) {
+        set_error("mb_net_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, wl.total);
+        return MB_ENOMEM;
+    }
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float* styles = reinterpret_cast<float*>(base + wl.styles);
+    float* dco = reinterpret_cast<float*>(base + wl.d);
+    __half* X = reinterpret_cast<__half*>(base + wl.x);
+    __half* XU = reinterpret_cast<__half*>(base + wl.xu);
+    __half* Y = reinterpret_cast<__half*>(base + wl.y);
+    float* img[2] = {reinterpret_cast<float*>(base + wl.img0), reinterpret_cast<float*>(base + wl.img1)};
+    int launches = 0, rc;
+
+    // styles (+ demodulation coefficients) of every layer; ws index: block i uses ws[w_idx + {0,1,2}]
+    {
+        int w_idx = 0, li = 0;
+        StylesArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.B = B; sa.num_ws = n->num_ws; sa.w_dim = n->w_dim; sa.ws = ws;
+        auto flush = [&]() -> int {
+            if (sa.num_layers == 0) return MB_OK;
+            int r = styles_launch(sa, stream);
+            launches += 1;
+            sa.num_layers = 0;
+            return r;
+        };
+        for (const auto& b : n->blocks) {
+            int j = 0;
+            for (const Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
+                const bool present = !(L == &b.conv0 && !b.has_conv0);
+                if (present) {
+                    StyleLayerDesc& d = sa.L[sa.num_layers++];
+                    d.affine_w = L->affine_w.dev; d.affine_b = L->affine_b.dev;
+                    d.wsqT = L->wsqT; d.magnitude_ema = nullptr;
+                    d.s_out = styles + wl.style_l[li];
+                    d.d_out = L->ksz == 3 ? dco + wl.d_l[li] : nullptr;
+                    d.Cin = L->cin; d.Cout = L->cout; d.ws_index = w_idx + j;
+                    d.demodulate = L->ksz == 3; d.normalize_style = 0;
+                    d.style_scale = L->ksz == 1 ? 1.0f / sqrtf(static_cast<float>(L->cin)) : 1.0f;
+                    ++j;
+                    if (sa.num_layers == kMaxLayers && (rc = flush()) != MB_OK) return rc;
+                }
+                ++li;
+            }
+            w_idx += b.has_conv0 ? 2 : 1;
+        }
+        if ((rc = flush()) != MB_OK) return rc;
+    }
+
+    int cur = 0;  // which img buffer holds the previous block's image
+    bool have_img = false;
+    for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
+        const Sg2Block& b = n->blocks[bi];
+        const int r = b.res;
+        const bool last = bi + 1 == n->blocks.size();
+        const float* s_conv0 = styles + wl.style_l[bi * 3 + 0];
+        const float* s_conv1 = styles + wl.style_l[bi * 3 + 1];
+        const float* s_rgb = styles + wl.style_l[bi * 3 + 2];
+        auto conv = [&](const Sg2Layer& L, const __half* xin, int hin, int pad, const float* d) -> int {
+            ConvTcArgs ca;
+            ca.x = xin; ca.wpk = L.wpk; ca.d = d; ca.bias = nullptr; ca.y = Y;
+            ca.B = B; ca.Cin = L.cin; ca.Cout = L.cout; ca.Hin = hin; ca.Win = hin; ca.Cp_in = cpad16(L.cin);
+            ca.Wp_out = pitch8(hin + 2 * pad - 2); ca.ksz = 3; ca.pad = pad; ca.tile_w = 32; ca.num_sms = num_sms;
+            launches += 1;
+            return n->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
+        };
+        auto act = [&](const Sg2Layer& L, int fir, const float* style_next, bool rgb, const float* prev) -> int {
+            ActArgs a;
+            a.y = Y; a.noise = L.noise.dev; a.bias = L.bias.dev;
+            const size_t nb = L.noise.numel / L.noise.plane;
+            MB_REQUIRE(nb == 1 || nb == static_cast<size_t>(B), "mb_net_forward: noise of a %dx%d layer holds %zu maps, batch is %d",
+                       r, r, nb, B);
+            a.noise_bstride = nb == 1 ? 0 : static_cast<long long>(L.noise.plane);
+            a.style_next = style_next; a.x_next = style_next ? X : nullptr;
+            a.rgb_w = rgb ? b.torgb.weight.dev : nullptr; a.rgb_style = s_rgb; a.rgb_bias = b.torgb.bias.dev;
+            a.img_prev = prev; a.img = img[cur ^ 1];
+            a.B = B; a.C = L.cout; a.R = r; a.Hy = fir ? r + 1 : r; a.Wpy = pitch8(a.Hy); a.Cp = cpad16(L.cout);
+            a.fir = fir; a.nimg = n->img_channels; a.clamp = 256.0f;
+            const size_t smem = sizeof(float) * L.cout * (kActP + 1);
+            static size_t smem_set = 0;
+            if (smem > 48 * 1024 && smem > smem_set) {
+                MB_CUDA(cudaFuncSetAttribute(sg2_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                smem_set = smem;
+            }
+            dim3 grid(ceil_div(r, kActP), r, B);
+            sg2_act_kernel<<<grid, 256, smem, stream>>>(a);
+            MB_CUDA(cudaGetLastError());
+            launches += 1;
+            return MB_OK;
+        };
+        if (!b.has_conv0) {
+            const long long tot = static_cast<long long>(B) * r * r * cpad16(b.cout);
+            const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout));
+            MB_CUDA(cudaGetLastError());
+            launches += 1;
+        } else {
+            // conv0: X holds x * style(conv0) at r/2 -> zero insert -> 'full' conv with flipped taps -> FIR + act
+            const int h = r / 2, cp8 = cpad16(b.cin) / 8;
+            const long long tot = static_cast<long long>(B) * (2 * h - 1) * (2 * h - 1) * cp8;
+            zero_insert_kernel<<<grid1d(tot), 256, 0, stream>>>(reinterpret_cast<const uint4*>(X), reinterpret_cast<uint4*>(XU), B, h, h, cp8);
+            MB_CUDA(cudaGetLastError());
+            launches += 1;
+            if ((rc = conv(b.conv0, XU, 2 * h - 1, 2, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
+            if ((rc = act(b.conv0, 1, s_conv1, false, nullptr)) != MB_OK) return rc;
+        }
+        (void)s_conv0;
+        if ((rc = conv(b.conv1, X, r, 1, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
+        const float* prev = nullptr;
+        if (have_img) {
+            // img[cur] (r/2) -> upsampled into img[cur^1]?  keep three-step: upsample into the other buffer, accumulate in place
+            const long long tot = static_cast<long long>(B) * n->img_channels * r * r;
+            upsample_rgb_kernel<<<grid1d(tot), 256, 0, stream>>>(img[cur], img[cur ^ 1], B * n->img_channels, r / 2);
+            MB_CUDA(cudaGetLastError());
+            launches += 1;
+            prev = img[cur ^ 1];
+        }
+        const float* s_next = last ? nullptr : styles + wl.style_l[(bi + 1) * 3 + 0];
+        if ((rc = act(b.conv1, 0, s_next, true, prev)) != MB_OK) return rc;
+        cur ^= 1;
+        have_img = true;
+    }
+    const long long nout = static_cast<long long>(B) * n->img_channels * n->res * n->res;
+    if (out_fmt == MB_OUT_F32_NCHW) {
+        MB_CUDA(cudaMemcpyAsync(out, img[cur], nout * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    } else {
+        img_to_u8_kernel<<<grid1d(nout), 256, 0, stream>>>(img[cur], static_cast<uint8_t*>(out), B, n->img_channels, n->res);
+        MB_CUDA(cudaGetLastError());
+        launches += 1;
+    }
+    n->last_launches = launches;
+    return MB_OK;
+}
+
+}  // namespace mb

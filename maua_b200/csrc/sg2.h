@@ -1,0 +1,19 @@
+// StyleGAN2 network object behind the mb_net handle (sg2.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace mb {
+struct Sg2Net;
+int sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base, int channel_max, Sg2Net** out);
+void sg2_destroy(Sg2Net* n);
+int sg2_set_param(Sg2Net* n, const char* name, const float* data, const int64_t* shape, int ndim, cudaStream_t stream);
+int sg2_finalize(Sg2Net* n, cudaStream_t stream);
+size_t sg2_workspace_bytes(const Sg2Net* n, int B);
+int sg2_num_ws(const Sg2Net* n);
+int sg2_last_launches(const Sg2Net* n);
+void sg2_set_conv_impl(Sg2Net* n, int impl);
+int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
+                int num_sms, cudaStream_t stream);
+}  // namespace mb

@@ -37,7 +37,7 @@ __device__ __forceinline__ float block_reduce_sum(float v, float* s_red) {
 
 // grid = round_up(Cout,128) rows; row >= Cout is zero padding.
 __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restrict__ wpk, float* __restrict__ wsqT,
-                                    int Cout, int Cin, int ksz, int prenorm) {
+                                    int Cout, int Cin, int ksz, int prenorm, int flip) {
     __shared__ float s_red[32];
     const int o = blockIdx.x;
     const int nCC = (Cin + 63) / 64;
@@ -64,7 +64,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
         const int kw = static_cast<int>(r);
         const int ci = cc * 64 + cl;
         float v = 0.0f;
-        if (ci < Cin) v = wo[(ci * ksz + kh) * ksz + kw] * scale;
+        if (ci < Cin) v = wo[(ci * ksz + (flip ? ksz - 1 - kh : kh)) * ksz + (flip ? ksz - 1 - kw : kw)] * scale;
         row[i] = __float2half_rn(v);
     }
     if (wsqT) {
@@ -82,7 +82,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __half* __restr
 __global__ void conv_simt_kernel(ConvTcArgs p, int Hout, int Wout) {
     const long long total = static_cast<long long>(p.B) * p.Cout * Hout * Wout;
     const int nCC = (p.Cin + 63) / 64;
-    const int pad = p.ksz - 1;
+    const int pad = p.pad;
     const long long Ktot = static_cast<long long>(p.ksz) * p.ksz * nCC * 64;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) styles_kernel(const __grid_constant__ Sty
         if (lane == 0) s_s[i] = (acc + L.affine_b[i]) * L.style_scale;
     }
     __syncthreads();
-    if (L.demodulate) {
+    if (L.demodulate && L.normalize_style) {
         float ss = 0.0f;
         for (int i = threadIdx.x; i < L.Cin; i += blockDim.x) ss += s_s[i] * s_s[i];
         ss = block_reduce_sum(ss, s_red);
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) styles_kernel(const __grid_constant__ Sty
         for (int i = threadIdx.x; i < L.Cin; i += blockDim.x) s_s[i] *= nrm;
         __syncthreads();
     }
-    const float input_gain = rsqrtf(*L.magnitude_ema);
+    const float input_gain = L.magnitude_ema ? rsqrtf(*L.magnitude_ema) : 1.0f;
     for (int i = threadIdx.x; i < L.Cin; i += blockDim.x) L.s_out[static_cast<long long>(b) * L.Cin + i] = s_s[i] * input_gain;
     if (L.d_out) {
         for (int o = threadIdx.x; o < L.Cout; o += blockDim.x) {
@@ -463,14 +463,14 @@ static int grid_for(long long total, int block) {
 }  // namespace
 
 int pack_weights_launch(const float* w, __half* wpk, float* wsqT, int Cout, int Cin, int ksz, int prenorm,
-                        cudaStream_t stream) {
-    pack_weights_kernel<<<round_up(Cout, 128), 256, 0, stream>>>(w, wpk, wsqT, Cout, Cin, ksz, prenorm);
+                        cudaStream_t stream, int flip) {
+    pack_weights_kernel<<<round_up(Cout, 128), 256, 0, stream>>>(w, wpk, wsqT, Cout, Cin, ksz, prenorm, flip);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }
 
 int conv_simt_launch(const ConvTcArgs& p, cudaStream_t stream) {
-    const int Hout = p.Hin + p.ksz - 1, Wout = p.Win + p.ksz - 1;
+    const int Hout = p.Hin + 2 * p.pad - (p.ksz - 1), Wout = p.Win + 2 * p.pad - (p.ksz - 1);
     const long long total = static_cast<long long>(p.B) * p.Cout * Hout * Wout;
     conv_simt_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p, Hout, Wout);
     MB_CUDA(cudaGetLastError());

@@ -96,7 +96,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // The whole warp runs the loop and one ELECTED lane issues: a TMA / tcgen05 instruction inside a divergent
+        // `if (lane == 0)` region is wrapped by the compiler in a per-thread vote loop (BRA.U.ANY) that costs ~90
+        // cycles per instruction (measured, scratch/umma_bench.cu); under an elect.sync predicate it is issued directly.
+        {
+            const bool leader = elect_one();
             int s = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
@@ -109,21 +113,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 for (int kw = 0; kw < a.ksz; ++kw) {
                     for (int cc = 0; cc < a.nCC; ++cc) {
                         mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
-                        uint8_t* st = smem + s * G::STAGE;
-                        mbar_arrive_expect_tx(&full[s], stage_bytes);
-                        const int kblk = (kw * a.nCC + cc) * a.ksz;
-                        for (int kh = 0; kh < a.ksz; ++kh)
-                            tma_load_2d(st + kh * kATileBytes, &tmap_w, &full[s], (kblk + kh) * kKC, m0);
-                        tma_load_4d(st + 3 * kATileBytes, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
-                        dbg_inc(a.dbg, 0);
+                        if (leader) {
+                            uint8_t* st = smem + s * G::STAGE;
+                            mbar_arrive_expect_tx(&full[s], stage_bytes);
+                            const int kblk = (kw * a.nCC + cc) * a.ksz;
+                            for (int kh = 0; kh < a.ksz; ++kh)
+                                tma_load_2d(st + kh * kATileBytes, &tmap_w, &full[s], (kblk + kh) * kKC, m0);
+                            tma_load_4d(st + 3 * kATileBytes, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
+                        }
+                        __syncwarp();
                         if (++s == kStages) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+        {
+            const bool leader = elect_one();
             constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, /*A K-major*/ 0, /*B K-major*/ 0);
             int s = 0;
             uint32_t ph = 0;
@@ -142,19 +149,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * G::STAGE);
                     const uint32_t sb = sa + 3 * kATileBytes;
-                    for (int kh = 0; kh < a.ksz; ++kh) {
-                        for (int j = 0; j < nk16; ++j) {
-                            const uint64_t da = make_smem_desc(sa + kh * kATileBytes + j * 32, 16, 1024, 2);
-                            const uint64_t db = make_smem_desc(sb + kh * G::SLAB + j * 32, 16, 1024, 2);
-                            umma_f16(d_tmem, da, db, idesc, accumulate);
-                            accumulate = 1;
+                    const uint64_t da0 = make_smem_desc(sa, 16, 1024, 2);
+                    const uint64_t db0 = make_smem_desc(sb, 16, 1024, 2);
+                    if (leader) {
+                        for (int kh = 0; kh < a.ksz; ++kh) {
+#pragma unroll 4
+                            for (int j = 0; j < nk16; ++j) {
+                                umma_f16(d_tmem, da0 + static_cast<uint64_t>((kh * kATileBytes + j * 32) >> 4),
+                                         db0 + static_cast<uint64_t>((kh * G::SLAB + j * 32) >> 4), idesc, accumulate);
+                                accumulate = 1;
+                            }
                         }
+                        umma_commit(&empty[s]);
                     }
-                    umma_commit(&empty[s]);
-                    dbg_inc(a.dbg, 1);
+                    __syncwarp();
                     if (++s == kStages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[acc]);
+                if (leader) umma_commit(&tfull[acc]);
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
@@ -221,6 +233,187 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Pixel-major variant for the narrow top layers (Cout <= 96: L10..L13 of StyleGAN3-T hold 81/51/32/32 couts).
+// The tile above pads couts to UMMA M = 128, so those layers spend 1.6x..4x of their tensor time on zero rows.
+// Here the roles are swapped:   D[128 pixels, Np couts] += A[128 pixels, K] * B[K, Np couts],  Np = ceil16(Cout),
+// the SAME shared-memory patch serves as the A operand (4 image rows x 32 pixels = 128 K-major rows; the 8-row
+// tile is two such halves with their own accumulators) and the SAME packed weight tiles as B (box of Np rows).
+// MMA time per 256 pixels and K=16 drops from 128 cycles to Np cycles; smaller stages allow a deeper pipeline.
+// Epilogue: one TMEM lane = one pixel, so a warp stores 32 consecutive pixels (64 B) of one cout per instruction.
+constexpr int kPmTW = 32, kPmTH = 8;
+constexpr int kPmSlab = kPmTW * 128;
+constexpr int kPmPatch = (kPmTH + 2) * kPmSlab;  // 40 KB
+constexpr int kPmMaxStages = 4;
+constexpr int kPmSmemBudget = 200 * 1024;
+
+struct PmArgs {
+    KArgs k;
+    int Np, stages, stage_bytes_alloc;
+};
+
+__global__ void __launch_bounds__(256, 1)
+conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, PmArgs pa) {
+    const KArgs& a = pa.k;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nst = pa.stages;
+    const int STAGE = pa.stage_bytes_alloc;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * STAGE);
+    uint64_t* full = bars;                         // [kPmMaxStages]
+    uint64_t* empty = bars + kPmMaxStages;         // [kPmMaxStages]
+    uint64_t* tfull = bars + 2 * kPmMaxStages;     // [2]
+    uint64_t* tempty = bars + 2 * kPmMaxStages + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPmMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int pad = a.pad;
+    const int Np = pa.Np;
+    const int w_tile = Np * 128;                   // bytes of one [Np x 64] weight tile
+    const int patch_rows = kPmTH + a.ksz - 1;
+    const uint32_t stage_bytes = a.ksz * w_tile + patch_rows * kPmSlab;
+    const int iters = a.ksz * a.nCC;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            const int h0 = ht * kPmTH, w0 = wt * kPmTW;
+            for (int kw = 0; kw < a.ksz; ++kw) {
+                for (int cc = 0; cc < a.nCC; ++cc) {
+                    mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
+                    if (leader) {
+                        uint8_t* st = smem + s * STAGE;
+                        mbar_arrive_expect_tx(&full[s], stage_bytes);
+                        const int kblk = (kw * a.nCC + cc) * a.ksz;
+                        for (int kh = 0; kh < a.ksz; ++kh)
+                            tma_load_2d(st + kPmPatch + kh * w_tile, &tmap_w, &full[s], (kblk + kh) * kKC, 0);
+                        tma_load_4d(st, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
+                    }
+                    __syncwarp();
+                    if (++s == nst) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(128, Np, 0, 0);
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 2 * Np;
+            uint32_t accumulate = 0;
+            for (int it = 0; it < iters; ++it) {
+                const int cc = it % a.nCC;
+                int nk16 = (a.Cin - cc * kKC + 15) / 16;
+                if (nk16 > 4) nk16 = 4;
+                mbar_wait(&full[s], ph, a.dbg, 3);
+                tc_fence_after();
+                const uint32_t sx = smem_u32(smem + s * STAGE);
+                const uint64_t dx = make_smem_desc(sx, 16, 1024, 2);
+                const uint64_t dw = make_smem_desc(sx + kPmPatch, 16, 1024, 2);
+                if (leader) {
+                    for (int kh = 0; kh < a.ksz; ++kh) {
+#pragma unroll 4
+                        for (int j = 0; j < nk16; ++j) {
+                            const uint64_t dwk = dw + static_cast<uint64_t>((kh * w_tile + j * 32) >> 4);
+                            const uint64_t dxk = dx + static_cast<uint64_t>((kh * kPmSlab + j * 32) >> 4);
+                            umma_f16(d_tmem, dxk, dwk, idesc, accumulate);
+                            umma_f16(d_tmem + Np, dxk + static_cast<uint64_t>((4 * kPmSlab) >> 4), dwk, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+            if (leader) umma_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;  // TMEM lane quadrant == image row of the half tile
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            const int w = wt * kPmTW + lane;
+            const bool w_ok = w < a.Wp_out;
+            const float* dptr = a.d ? a.d + b * a.Cout : nullptr;
+            mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int h = ht * kPmTH + half * 4 + q;
+                const bool ok = w_ok && h < a.Hout;
+                __half* yp = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + static_cast<long long>(h) * a.Wp_out + w;
+#pragma unroll 1
+                for (int c0 = 0; c0 < Np; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * Np + half * Np + c0, v);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int co = c0 + i;
+                            if (co < a.Cout) {
+                                const float scale = dptr ? __ldg(dptr + co) : 1.0f;
+                                const float bias = a.bias ? __ldg(a.bias + co) : 0.0f;
+                                yp[co * a.plane_out] = __float2half_rn(fmaf(__uint_as_float(v[i]), scale, bias));
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 int conv_tc_smem_bytes(int tw) { return tw == 32 ? Geo<32>::SMEM : Geo<16>::SMEM; }
@@ -231,7 +424,9 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return MB_ECUDA;
     }
-    const int tw = p.tile_w == 16 ? 16 : 32;
+    const int Np = round_up(p.Cout, 16);
+    const bool pixel_major = p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128;
+    const int tw = pixel_major ? kPmTW : (p.tile_w == 16 ? 16 : 32);
     const int th = kTileN / tw;
     const int pad = p.pad;
     const int halo = p.ksz - 1;
@@ -249,7 +444,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Mp)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
-        cuuint32_t box[2] = {kKC, kTileM};
+        cuuint32_t box[2] = {kKC, static_cast<cuuint32_t>(pixel_major ? Np : kTileM)};
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.wpk), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -290,6 +485,27 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
     a.dbg = debug_words_device();
 
+    if (pixel_major) {
+        PmArgs pa;
+        pa.k = a;
+        pa.k.tiles_m = 1;
+        pa.k.total_tiles = p.B * a.tiles_h * a.tiles_w;
+        pa.Np = Np;
+        pa.stage_bytes_alloc = kPmPatch + 3 * Np * 128;
+        pa.stages = kPmSmemBudget / pa.stage_bytes_alloc;
+        if (pa.stages > kPmMaxStages) pa.stages = kPmMaxStages;
+        const int smem_bytes = pa.stages * pa.stage_bytes_alloc + 1024 + 256;
+        static int attr_bytes = 0;
+        if (smem_bytes > attr_bytes) {
+            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+            attr_bytes = smem_bytes;
+        }
+        int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
+        if (grid < 1) grid = 1;
+        conv_pm_kernel<<<grid, 256, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
     int grid = a.total_tiles < p.num_sms ? a.total_tiles : p.num_sms;
     if (grid < 1) grid = 1;
     if (tw == 32) {

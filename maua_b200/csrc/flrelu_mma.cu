@@ -21,6 +21,7 @@
 //
 // Index conventions as in flrelu.cu.  Supported: down=2/12 taps with up=2/12 taps or up=4/24 taps,
 // separable filters (every non-ToRGB layer of StyleGAN3-T and the critically sampled layers of -R).
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -460,6 +461,148 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     write_out(tile0 + last, last & 1);
 }
 
+
+// ---- persistent channels-last variant --------------------------------------------------------------
+// Same arithmetic and staging scheme as flrelu_mma_nhwc_kernel, restructured after the ncu source view of that
+// kernel showed ~18 % of all warp samples parked on its two mbarrier waits (every warp had to wait for the slowest
+// warp's previous tile before starting its next one) and one exposed first-tile load + last write-out per 8-tile CTA:
+//   * one CTA per SM walks a contiguous range of the (batch, channel group, tile) index space, so the input
+//     prefetch chain and the write-out pipeline never drain until the layer is done;
+//   * three staging buffers and a write-out that lags TWO tiles behind: a warp may run two tiles ahead of the
+//     slowest warp of its CTA before it blocks.
+constexpr int kNSB = 3;
+
+template <int UP>
+__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const MmaParams p, int ngroups, int total) {
+    using K = MC<UP>;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    __half* X = reinterpret_cast<__half*>(smem_raw + warp * K::XBYTES);
+    __half* stage_base = reinterpret_cast<__half*>(smem_raw + kCG * K::XBYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kCG * K::XBYTES + kNSB * kCG * kStageBytes);
+    uint64_t* full = bars;           // [kNSB] all 16 planes of a staging buffer written
+    uint64_t* empty = bars + kNSB;   // [kNSB] all 16 write-out shares of a staging buffer done
+
+    const int ntiles = p.tiles_x * p.tiles_y;
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    const int start = blockIdx.x * per;
+    const int n = min(per, total - start);
+    if (n <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * kNSB; ++i) mbar_init(&bars[i], kCG);
+        fence_barrier_init();
+    }
+    LaneConsts<UP> LC;
+    lane_setup<UP>(p, lane, LC);
+    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
+    __syncthreads();  // barriers initialised (the only block-wide barrier: warps run decoupled from here on)
+
+    struct Item { int b, c0, tile, ox0, oy0, ix0, iy0; };
+    auto item = [&](int idx) {
+        Item it;
+        it.tile = idx % ntiles;
+        const int r = idx / ntiles;
+        it.c0 = (r % ngroups) * kCG;
+        it.b = r / ngroups;
+        const int ty = it.tile / p.tiles_x, tx = it.tile - ty * p.tiles_x;
+        it.ox0 = tx * kOT;
+        it.oy0 = ty * kOT;
+        it.ix0 = -fdiv(-(2 * it.ox0 - p.px0), UP) - p.e;
+        it.iy0 = -fdiv(-(2 * it.oy0 - p.py0), UP) - p.e;
+        return it;
+    };
+    auto load_tile = [&](const Item& it) {
+        if (it.c0 + warp >= p.C) return;
+        const __half* xp = p.x + (static_cast<long long>(it.b) * p.C + it.c0 + warp) * p.Hin * p.Wp_in;
+        const int ixa = fdiv(it.ix0, 8) * 8;
+        for (int idx = lane; idx < K::IYT * 7; idx += 32) {
+            const int row = idx / 7, ch = idx - row * 7;
+            const int iy = it.iy0 + row, ixc = ixa + ch * 8;
+            int bytes = 0;
+            const __half* src = xp;
+            if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
+                bytes = min(8, p.Win - ixc) * 2;
+                src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
+            }
+            cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
+        }
+        cp_async_commit();
+    };
+    // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
+    auto write_out = [&](const Item& it, int sb) {
+        const __half* st = stage_base + sb * kCG * (kStageBytes / 2);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int ly = 2 * warp + k, lx = lane;
+            const int oy = it.oy0 + ly, ox = it.ox0 + lx;
+            if (oy < p.Hout && ox < p.Wout) {
+                const __half* sp = st + ly * kSP + lx;
+                uint32_t w[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * q) * (kStageBytes / 2));
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * q + 1) * (kStageBytes / 2));
+                    w[q] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(it.b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + it.c0);
+                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+        }
+    };
+    auto drain = [&](int j) {  // write out tile j of this CTA's range (all 16 warps take part)
+        const int sb = j % kNSB;
+        mbar_wait(&full[sb], (j / kNSB) & 1);
+        write_out(item(start + j), sb);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[sb]);
+    };
+
+    Item cur = item(start);
+    load_tile(cur);
+    for (int i = 0; i < n; ++i) {
+        const int sb = i % kNSB;
+        if (i >= 2) drain(i - 2);
+        // the staging buffer is free once every warp has written out its share of tile i-3
+        if (i >= kNSB) mbar_wait(&empty[sb], ((i / kNSB) - 1) & 1);
+        Item nxt = cur;
+        if (i + 1 < n) nxt = item(start + i + 1);
+        __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
+        const int c = cur.c0 + warp;
+        if (c < p.C) {
+            cp_async_wait<0>();
+            __syncwarp();
+            const int dx = cur.ix0 - fdiv(cur.ix0, 8) * 8;
+            const float oscale = (p.scale ? p.scale[cur.b * p.C + c] : 1.0f) * p.cd2;
+            float OUT[2][4][4];
+            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT, [&]() {
+                __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
+                if (i + 1 < n) load_tile(nxt);
+            });
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        *reinterpret_cast<uint32_t*>(stage + (ii * 16 + hh * 8 + g) * kSP + no * 8 + 2 * tig) =
+                            pack2(OUT[ii][no][hh * 2 + 0] * oscale, OUT[ii][no][hh * 2 + 1] * oscale);
+        } else {
+            // channel padding of the last group: this warp's plane is zero
+            uint4* z = reinterpret_cast<uint4*>(stage);
+            for (int k = lane; k < kStageBytes / 16; k += 32) z[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (i + 1 < n) load_tile(nxt);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[sb]);
+        cur = nxt;
+    }
+    if (n >= 2) drain(n - 2);
+    drain(n - 1);
+}
+
 // ---- host: constant fragments -------------------------------------------------------------------
 struct FragCache {
     int up = 0, rho = -1, e = -1;
@@ -602,6 +745,26 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.y = a.y_nhwc;
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
+        static int variant = -1;
+        if (variant < 0) {
+            const char* e = getenv("MB_FLRELU_NHWC");
+            variant = e ? atoi(e) : 1;
+        }
+        if (variant == 1) {
+            constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;
+            static bool attr_p = false;
+            if (!attr_p) {
+                MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_p_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
+                attr_p = true;
+            }
+            const int ngroups = ceil_div(a.C, kCG);
+            const int total = a.B * ngroups * ntiles;
+            const int sms = a.num_sms > 0 ? a.num_sms : 148;
+            const int grid = total < sms ? total : sms;
+            flrelu_mma_nhwc_p_kernel<UP><<<grid, kCG * 32, smem_p, stream>>>(p, ngroups, total);
+            MB_CUDA(cudaGetLastError());
+            return MB_OK;
+        }
         constexpr int smem = kCG * K::XBYTES + 2 * kCG * kStageBytes + 64;
         static bool attr_nhwc = false;
         if (!attr_nhwc) {

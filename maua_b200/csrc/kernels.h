@@ -26,6 +26,7 @@ struct ConvTcArgs {
     int B, Cin, Cout, Hin, Win, Cp_in, Wp_out, ksz;
     int pad;            // zero padding per side (StyleGAN3: ksz-1 'full', StyleGAN2: ksz/2 'same'); output = in + 2*pad - (ksz-1)
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
+    int pm_max_cout = 96;  // layers with ceil16(Cout) <= this run the pixel-major tile (0 = never)
     int num_sms;
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);

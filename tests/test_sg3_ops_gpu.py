@@ -24,11 +24,15 @@ CONV_CASES = [
     (2, 51, 32, 100, 90, 3, True),
     (1, 32, 32, 70, 70, 3, True),
     (1, 96, 64, 33, 41, 3, True),
+    (2, 128, 81, 60, 50, 3, True),
+    (1, 40, 17, 45, 37, 3, True),
 ]
 
 
 @pytest.mark.parametrize("case", CONV_CASES)
-@pytest.mark.parametrize("impl", [1, 0, 2])  # 1 CUDA cores, 0 tcgen05 (32-wide pixel tiles), 2 tcgen05 16-wide tiles
+# 1 CUDA cores, 0 tcgen05 (product dispatch: pixel-major tile for <= 96 couts, cout-major above), 2 tcgen05 16-wide
+# cout-major tiles, 3 cout-major forced, 4 pixel-major up to 128 couts
+@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4])
 def test_modulated_conv2d(cuda, case, impl):
     from maua_b200 import ops
 

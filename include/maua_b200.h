@@ -155,8 +155,10 @@ int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h, int32_t* 
  * formulation; in-tree twin maua/GAN/wrappers/inference/ops.py:146-186).
  *   x [B,Cin,H,W] f32, w [Cout,Cin,k,k] f32, s [B,Cin] f32 -> y [B,Cout,H+k-1,W+k-1] f32
  * padding = k-1, demodulate as given, input_gain scalar.  All device pointers.
- * impl: 0 product dispatch (tcgen05; pixel-major tile for <= 96 couts, cout-major tile above), 1 CUDA-core direct
- * convolution (bisecting aid), 2 cout-major with 16-wide pixel tiles, 3 cout-major forced, 4 pixel-major up to 128 couts. */
+ * impl: 0 product dispatch (tcgen05; cout-major tile, pixel-major tile for <= 64 couts with > 32 cins; narrow layers
+ * keep their weight tiles resident in shared memory), 1 CUDA-core direct convolution (bisecting aid), 2 cout-major
+ * with 16-wide pixel tiles, 3 cout-major with full 128-row weight tiles streamed per stage (first path),
+ * 4 pixel-major tile for everything up to 128 couts. */
 int mb_modulated_conv2d(const float* x, const float* w, const float* s, float* y, int B, int Cin,
                         int Cout, int H, int W, int k, int demodulate, float input_gain,
                         int impl, mb_stream stream);

@@ -27,19 +27,16 @@ namespace mb {
 
 namespace {
 
-constexpr int kStages = 2;
+constexpr int kMaxStages = 6;
 constexpr int kTileM = 128;         // couts per tile (UMMA M)
 constexpr int kTileN = 256;         // pixels per tile (UMMA N)
 constexpr int kKC = 64;             // channels per pipeline stage
-constexpr int kATileBytes = kTileM * kKC * 2;  // 16 KB
+constexpr int kSmemMax = 232448;    // 227 KB dynamic shared memory per CTA on sm_100
 
 template <int TW>
 struct Geo {
     static constexpr int TH = kTileN / TW;
     static constexpr int SLAB = TW * 128;            // one h-row of the patch: TW pixels x 64 channels
-    static constexpr int PATCH_MAX = (TH + 2) * SLAB;
-    static constexpr int STAGE = 3 * kATileBytes + PATCH_MAX;
-    static constexpr int SMEM = kStages * STAGE + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct KArgs {
@@ -50,6 +47,10 @@ struct KArgs {
     __half* y;
     long long plane_out;  // Hout * Wp_out
     int* dbg;             // debug words (mapped host memory) or nullptr
+    // shared-memory plan (conv_tc_launch): see the layout comment in conv_tc_kernel
+    int a_tile_bytes;     // one [a_rows x 64] weight tile (a_rows = 128, or ceil8(Cout) when Cout fits one M tile)
+    int resident;         // 1: every weight tile stays in shared memory for the whole kernel
+    int nstages, stage_bytes;
 };
 
 template <int TW>
@@ -58,27 +59,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     using G = Geo<TW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * G::STAGE);
-    uint64_t* full = bars;                    // [kStages]
-    uint64_t* empty = bars + kStages;         // [kStages]
-    uint64_t* tfull = bars + 2 * kStages;     // [2]
-    uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    // Layout: [resident weight tiles (ksz*ksz*nCC x a_tile_bytes) | nstages x stage | barriers], a stage being
+    // [ksz weight tiles (streaming mode only) | activation patch].  The narrow top layers (Cout <= 64: L11..L13 of
+    // StyleGAN3-T) were L2->SM bandwidth bound at ~12 TB/s re-fetching 48 KB of zero-padded weight rows per stage
+    // (r1 layer timings); their whole weight matrix now stays in shared memory and the stages only carry patches.
+    // UMMA M stays 128: the rows past a_rows read whatever follows in shared memory and land in accumulator lanes
+    // the epilogue never stores.
+    const int nst = a.nstages;
+    const int n_wtiles = a.ksz * a.ksz * a.nCC;
+    uint8_t* stages = smem + (a.resident ? n_wtiles * a.a_tile_bytes : 0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + nst * a.stage_bytes);
+    uint64_t* full = bars;                       // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;         // [kMaxStages]
+    uint64_t* tfull = bars + 2 * kMaxStages;     // [2]
+    uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
+    uint64_t* wfull = bars + 2 * kMaxStages + 4;   // [1] resident weights landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int pad = a.pad;
     const int patch_rows = G::TH + a.ksz - 1;
-    const uint32_t stage_bytes = a.ksz * kATileBytes + patch_rows * G::SLAB;
+    const int a_bytes_stage = a.resident ? 0 : a.ksz * a.a_tile_bytes;
+    const uint32_t stage_tx = a_bytes_stage + patch_rows * G::SLAB;
     const int iters = a.ksz * a.nCC;
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_x);
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < nst; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
+        mbar_init(wfull, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 4);
@@ -103,6 +116,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const bool leader = elect_one();
             int s = 0;
             uint32_t ph = 0;
+            if (a.resident && leader && blockIdx.x < a.total_tiles) {
+                mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(n_wtiles * a.a_tile_bytes));
+                for (int i = 0; i < n_wtiles; ++i) tma_load_2d(smem + i * a.a_tile_bytes, &tmap_w, wfull, i * kKC, 0);
+            }
+            __syncwarp();
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
                 int r = t;
                 const int mt = r % a.tiles_m; r /= a.tiles_m;
@@ -114,15 +132,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     for (int cc = 0; cc < a.nCC; ++cc) {
                         mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                         if (leader) {
-                            uint8_t* st = smem + s * G::STAGE;
-                            mbar_arrive_expect_tx(&full[s], stage_bytes);
-                            const int kblk = (kw * a.nCC + cc) * a.ksz;
-                            for (int kh = 0; kh < a.ksz; ++kh)
-                                tma_load_2d(st + kh * kATileBytes, &tmap_w, &full[s], (kblk + kh) * kKC, m0);
-                            tma_load_4d(st + 3 * kATileBytes, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
+                            uint8_t* st = stages + s * a.stage_bytes;
+                            mbar_arrive_expect_tx(&full[s], stage_tx);
+                            if (!a.resident) {
+                                const int kblk = (kw * a.nCC + cc) * a.ksz;
+                                for (int kh = 0; kh < a.ksz; ++kh)
+                                    tma_load_2d(st + kh * a.a_tile_bytes, &tmap_w, &full[s], (kblk + kh) * kKC, m0);
+                            }
+                            tma_load_4d(st + a_bytes_stage, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
                         }
                         __syncwarp();
-                        if (++s == kStages) { s = 0; ph ^= 1; }
+                        if (++s == nst) { s = 0; ph ^= 1; }
                     }
                 }
             }
@@ -136,6 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             uint32_t ph = 0;
             int acc = 0;
             uint32_t acc_ph = 0;
+            if (a.resident && blockIdx.x < a.total_tiles) mbar_wait(wfull, 0, a.dbg, 5);
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
                 mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
                 tc_fence_after();
@@ -147,15 +168,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     if (nk16 > 4) nk16 = 4;
                     mbar_wait(&full[s], ph, a.dbg, 3);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * G::STAGE);
-                    const uint32_t sb = sa + 3 * kATileBytes;
+                    const uint32_t st = smem_u32(stages + s * a.stage_bytes);
+                    const uint32_t sa = a.resident ? smem_u32(smem) + it * a.ksz * a.a_tile_bytes : st;
+                    const uint32_t sb = st + a_bytes_stage;
                     const uint64_t da0 = make_smem_desc(sa, 16, 1024, 2);
                     const uint64_t db0 = make_smem_desc(sb, 16, 1024, 2);
                     if (leader) {
                         for (int kh = 0; kh < a.ksz; ++kh) {
 #pragma unroll 4
                             for (int j = 0; j < nk16; ++j) {
-                                umma_f16(d_tmem, da0 + static_cast<uint64_t>((kh * kATileBytes + j * 32) >> 4),
+                                umma_f16(d_tmem, da0 + static_cast<uint64_t>((kh * a.a_tile_bytes + j * 32) >> 4),
                                          db0 + static_cast<uint64_t>((kh * G::SLAB + j * 32) >> 4), idesc, accumulate);
                                 accumulate = 1;
                             }
@@ -163,7 +185,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         umma_commit(&empty[s]);
                     }
                     __syncwarp();
-                    if (++s == kStages) { s = 0; ph ^= 1; }
+                    if (++s == nst) { s = 0; ph ^= 1; }
                 }
                 if (leader) umma_commit(&tfull[acc]);
                 __syncwarp();
@@ -235,22 +257,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
 
 // ---------------------------------------------------------------------------------------------------------
-// Pixel-major variant for the narrow top layers (Cout <= 96: L10..L13 of StyleGAN3-T hold 81/51/32/32 couts).
-// The tile above pads couts to UMMA M = 128, so those layers spend 1.6x..4x of their tensor time on zero rows.
-// Here the roles are swapped:   D[128 pixels, Np couts] += A[128 pixels, K] * B[K, Np couts],  Np = ceil16(Cout),
+// Pixel-major variant for the narrow top layers (Cout <= 64: L11..L13 of StyleGAN3-T hold 51/32/32 couts).
+// The tile above pads couts to UMMA M = 128, so those layers spend 2.5x..4x of their tensor time on zero rows
+// (ncu r1: tensor pipe 64..82 % busy at 250..470 useful TFLOP/s).  Here the roles are swapped:
+//     D[128 pixels, Np couts] += A[128 pixels, K] * B[K, Np couts],  Np = ceil16(Cout),
 // the SAME shared-memory patch serves as the A operand (4 image rows x 32 pixels = 128 K-major rows; the 8-row
 // tile is two such halves with their own accumulators) and the SAME packed weight tiles as B (box of Np rows).
-// MMA time per 256 pixels and K=16 drops from 128 cycles to Np cycles; smaller stages allow a deeper pipeline.
-// Epilogue: one TMEM lane = one pixel, so a warp stores 32 consecutive pixels (64 B) of one cout per instruction.
+// MMA time per 256 pixels and K=16 drops from 128 cycles to max(Np, shared-memory read of A) cycles.  The weight
+// tiles stay resident in shared memory whenever they fit (they do for every layer this variant is used for).
+// Epilogue: one TMEM lane = one pixel.  Neighbouring lanes swap one cout of every cout pair (one SHFL + PRMT), so a
+// lane stores two adjacent pixels of one cout (4 bytes) and a warp store covers 2 x 64-byte row segments; the
+// per-cout (demodulation, bias) pairs come from a per-warp shared-memory table refreshed when the frame changes.
 constexpr int kPmTW = 32, kPmTH = 8;
 constexpr int kPmSlab = kPmTW * 128;
-constexpr int kPmPatch = (kPmTH + 2) * kPmSlab;  // 40 KB
 constexpr int kPmMaxStages = 4;
-constexpr int kPmSmemBudget = 200 * 1024;
 
 struct PmArgs {
     KArgs k;
-    int Np, stages, stage_bytes_alloc;
+    int Np, stages, stage_bytes_alloc, resident;
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -260,20 +284,26 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nst = pa.stages;
     const int STAGE = pa.stage_bytes_alloc;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * STAGE);
+    const int Np = pa.Np;
+    const int w_tile = Np * 128;                   // bytes of one [Np x 64] weight tile
+    const int n_wtiles = a.ksz * a.ksz * a.nCC;
+    const int patch_rows = kPmTH + a.ksz - 1;
+    const int patch_bytes = patch_rows * kPmSlab;
+    // layout: [resident weight tiles | stages: patch (+ ksz weight tiles when streaming) | (scale,bias) tables | barriers]
+    uint8_t* stages = smem + (pa.resident ? n_wtiles * w_tile : 0);
+    float2* sc_tab = reinterpret_cast<float2*>(stages + nst * STAGE);   // [4 warps][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sc_tab + 4 * 128);
     uint64_t* full = bars;                         // [kPmMaxStages]
     uint64_t* empty = bars + kPmMaxStages;         // [kPmMaxStages]
     uint64_t* tfull = bars + 2 * kPmMaxStages;     // [2]
     uint64_t* tempty = bars + 2 * kPmMaxStages + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPmMaxStages + 4);
+    uint64_t* wfull = bars + 2 * kPmMaxStages + 4;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPmMaxStages + 5);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int pad = a.pad;
-    const int Np = pa.Np;
-    const int w_tile = Np * 128;                   // bytes of one [Np x 64] weight tile
-    const int patch_rows = kPmTH + a.ksz - 1;
-    const uint32_t stage_bytes = a.ksz * w_tile + patch_rows * kPmSlab;
+    const uint32_t stage_tx = patch_bytes + (pa.resident ? 0 : a.ksz * w_tile);
     const int iters = a.ksz * a.nCC;
 
     if (threadIdx.x == 0) {
@@ -287,6 +317,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 4);
         }
+        mbar_init(wfull, 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -302,6 +333,11 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const bool leader = elect_one();
         int s = 0;
         uint32_t ph = 0;
+        if (pa.resident && leader && blockIdx.x < a.total_tiles) {
+            mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(n_wtiles * w_tile));
+            for (int i = 0; i < n_wtiles; ++i) tma_load_2d(smem + i * w_tile, &tmap_w, wfull, i * kKC, 0);
+        }
+        __syncwarp();
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             int r = t;
             const int wt = r % a.tiles_w; r /= a.tiles_w;
@@ -312,11 +348,13 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 for (int cc = 0; cc < a.nCC; ++cc) {
                     mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                     if (leader) {
-                        uint8_t* st = smem + s * STAGE;
-                        mbar_arrive_expect_tx(&full[s], stage_bytes);
-                        const int kblk = (kw * a.nCC + cc) * a.ksz;
-                        for (int kh = 0; kh < a.ksz; ++kh)
-                            tma_load_2d(st + kPmPatch + kh * w_tile, &tmap_w, &full[s], (kblk + kh) * kKC, 0);
+                        uint8_t* st = stages + s * STAGE;
+                        mbar_arrive_expect_tx(&full[s], stage_tx);
+                        if (!pa.resident) {
+                            const int kblk = (kw * a.nCC + cc) * a.ksz;
+                            for (int kh = 0; kh < a.ksz; ++kh)
+                                tma_load_2d(st + patch_bytes + kh * w_tile, &tmap_w, &full[s], (kblk + kh) * kKC, 0);
+                        }
                         tma_load_4d(st, &tmap_x, &full[s], cc * kKC, w0 + kw - pad, h0 - pad, b);
                     }
                     __syncwarp();
@@ -331,6 +369,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         uint32_t ph = 0;
         int acc = 0;
         uint32_t acc_ph = 0;
+        if (pa.resident && blockIdx.x < a.total_tiles) mbar_wait(wfull, 0, a.dbg, 5);
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
             tc_fence_after();
@@ -342,9 +381,10 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 if (nk16 > 4) nk16 = 4;
                 mbar_wait(&full[s], ph, a.dbg, 3);
                 tc_fence_after();
-                const uint32_t sx = smem_u32(smem + s * STAGE);
+                const uint32_t sx = smem_u32(stages + s * STAGE);
+                const uint32_t sw = pa.resident ? smem_u32(smem) + it * a.ksz * w_tile : sx + patch_bytes;
                 const uint64_t dx = make_smem_desc(sx, 16, 1024, 2);
-                const uint64_t dw = make_smem_desc(sx + kPmPatch, 16, 1024, 2);
+                const uint64_t dw = make_smem_desc(sw, 16, 1024, 2);
                 if (leader) {
                     for (int kh = 0; kh < a.ksz; ++kh) {
 #pragma unroll 4
@@ -367,38 +407,53 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
     } else if (warp >= 4) {
         const int q = warp - 4;  // TMEM lane quadrant == image row of the half tile
+        float2* tab = sc_tab + q * 128;
+        const int par = lane & 1;
+        const uint32_t sel = par ? 0x3276u : 0x5410u;   // even lane keeps cout c of a pair, odd lane cout c+1
         int acc = 0;
         uint32_t acc_ph = 0;
+        int tab_b = -1;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             int r = t;
             const int wt = r % a.tiles_w; r /= a.tiles_w;
             const int ht = r % a.tiles_h; r /= a.tiles_h;
             const int b = r;
+            if (b != tab_b) {  // warp-uniform
+                __syncwarp();
+                for (int i = lane; i < Np; i += 32) {
+                    const bool ok = i < a.Cout;
+                    tab[i] = make_float2((ok && a.d) ? a.d[b * a.Cout + i] : (ok ? 1.0f : 0.0f), (ok && a.bias) ? a.bias[i] : 0.0f);
+                }
+                __syncwarp();
+                tab_b = b;
+            }
             const int w = wt * kPmTW + lane;
-            const bool w_ok = w < a.Wp_out;
-            const float* dptr = a.d ? a.d + b * a.Cout : nullptr;
+            const bool w_ok = w < a.Wp_out;   // Wp_out is even: both pixels of a lane pair are in or out together
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const int h = ht * kPmTH + half * 4 + q;
                 const bool ok = w_ok && h < a.Hout;
-                __half* yp = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + static_cast<long long>(h) * a.Wp_out + w;
+                // this lane's cout plane of pair k is (2k + par); it stores pixels (w & ~1, w | 1)
+                __half* yp = a.y + (static_cast<long long>(b) * a.Cout + par) * a.plane_out + static_cast<long long>(h) * a.Wp_out + (w & ~1);
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * Np + half * Np;
 #pragma unroll 1
                 for (int c0 = 0; c0 < Np; c0 += 16) {
                     uint32_t v[16];
-                    tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * Np + half * Np + c0, v);
+                    tmem_ld_32x32b_x16(taddr + c0, v);
                     tmem_ld_wait();
-                    if (ok) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int co = c0 + i;
-                            if (co < a.Cout) {
-                                const float scale = dptr ? __ldg(dptr + co) : 1.0f;
-                                const float bias = a.bias ? __ldg(a.bias + co) : 0.0f;
-                                yp[co * a.plane_out] = __float2half_rn(fmaf(__uint_as_float(v[i]), scale, bias));
-                            }
-                        }
+                    for (int k = 0; k < 8; ++k) {
+                        const float4 sb = *reinterpret_cast<const float4*>(tab + c0 + 2 * k);  // (d, bias) of couts c, c+1
+                        const __half2 mine = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k]), sb.x, sb.y),
+                                                               fmaf(__uint_as_float(v[2 * k + 1]), sb.z, sb.w));
+                        const uint32_t m = *reinterpret_cast<const uint32_t*>(&mine);
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, m, 1);
+                        const uint32_t pr = __byte_perm(m, o, sel);
+                        const int co = c0 + 2 * k + par;
+                        if (ok && co < a.Cout)
+                            *reinterpret_cast<uint32_t*>(yp + static_cast<long long>(c0 + 2 * k) * a.plane_out) = pr;
                     }
                 }
             }
@@ -416,7 +471,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 
 }  // namespace
 
-int conv_tc_smem_bytes(int tw) { return tw == 32 ? Geo<32>::SMEM : Geo<16>::SMEM; }
+int conv_tc_smem_bytes(int /*tw*/) { return kSmemMax; }
 
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     PFN_encodeTiled enc = get_encode_tiled();
@@ -425,7 +480,9 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         return MB_ECUDA;
     }
     const int Np = round_up(p.Cout, 16);
-    const bool pixel_major = p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128;
+    // pixel-major pays off where the cout-major tile wastes >= half of its M rows and K is deep enough to amortise
+    // the per-tile epilogue (B200 A/B, r1: L11 1.38 -> 1.23 ms, L12 0.77 -> 0.66 ms, but L13 with Cin = 32 0.50 -> 0.60 ms)
+    const bool pixel_major = p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && (p.Cin > 32 || p.pm_max_cout > 64);
     const int tw = pixel_major ? kPmTW : (p.tile_w == 16 ? 16 : 32);
     const int th = kTileN / tw;
     const int pad = p.pad;
@@ -440,11 +497,25 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     const int Mp = round_up(p.Cout, kTileM);
     const long long Ktot = static_cast<long long>(p.ksz) * p.ksz * nCC * kKC;
 
+    // shared-memory plan of the cout-major kernel (layout comment in conv_tc_kernel)
+    const int a_rows = (Mp == kTileM && p.narrow_a) ? round_up(p.Cout, 8) : kTileM;
+    const int a_tile_bytes = a_rows * kKC * 2;
+    const int patch_bytes = (th + halo) * tw * 128;
+    const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/;
+    const int w_all = p.ksz * p.ksz * nCC * a_tile_bytes;
+    const bool resident = p.narrow_a && Mp == kTileM && w_all + 2 * patch_bytes + fixed_bytes <= kSmemMax;
+    const int stage_alloc = patch_bytes + (resident ? 0 : p.ksz * a_tile_bytes);
+    int nstages = (kSmemMax - fixed_bytes - (resident ? w_all : 0)) / stage_alloc;
+    if (nstages > kMaxStages) nstages = kMaxStages;
+    MB_REQUIRE(pixel_major || nstages >= 2, "conv_tc: shared-memory plan does not fit (%d-byte stages)", stage_alloc);
+    // the UMMA reads 128 A rows from every tile start: the last tile must still end inside the allocation
+    const int smem_cm = fixed_bytes + (resident ? w_all : 0) + nstages * stage_alloc;
+
     CUtensorMap tm_w, tm_x;
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Mp)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
-        cuuint32_t box[2] = {kKC, static_cast<cuuint32_t>(pixel_major ? Np : kTileM)};
+        cuuint32_t box[2] = {kKC, static_cast<cuuint32_t>(pixel_major ? Np : a_rows)};
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.wpk), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -484,6 +555,10 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.d = p.d; a.bias = p.bias; a.y = p.y;
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
     a.dbg = debug_words_device();
+    a.a_tile_bytes = a_tile_bytes;
+    a.resident = resident ? 1 : 0;
+    a.nstages = nstages;
+    a.stage_bytes = stage_alloc;
 
     if (pixel_major) {
         PmArgs pa;
@@ -491,14 +566,20 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         pa.k.tiles_m = 1;
         pa.k.total_tiles = p.B * a.tiles_h * a.tiles_w;
         pa.Np = Np;
-        pa.stage_bytes_alloc = kPmPatch + 3 * Np * 128;
-        pa.stages = kPmSmemBudget / pa.stage_bytes_alloc;
+        const int w_tile = Np * 128;
+        const int pm_patch = (kPmTH + halo) * kPmSlab;
+        const int pm_fixed = 1024 /*align*/ + 4 * 128 * 8 /*(scale,bias) tables*/ + 256 /*barriers*/;
+        const int pm_w_all = p.ksz * p.ksz * nCC * w_tile;
+        pa.resident = (pm_w_all + 2 * pm_patch + pm_fixed <= kSmemMax) ? 1 : 0;
+        pa.stage_bytes_alloc = pm_patch + (pa.resident ? 0 : p.ksz * w_tile);
+        pa.stages = (kSmemMax - pm_fixed - (pa.resident ? pm_w_all : 0)) / pa.stage_bytes_alloc;
         if (pa.stages > kPmMaxStages) pa.stages = kPmMaxStages;
-        const int smem_bytes = pa.stages * pa.stage_bytes_alloc + 1024 + 256;
-        static int attr_bytes = 0;
-        if (smem_bytes > attr_bytes) {
-            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-            attr_bytes = smem_bytes;
+        MB_REQUIRE(pa.stages >= 2, "conv_tc: pixel-major shared-memory plan does not fit");
+        const int smem_bytes = pm_fixed + (pa.resident ? pm_w_all : 0) + pa.stages * pa.stage_bytes_alloc;
+        static bool attr_pm = false;
+        if (!attr_pm) {
+            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            attr_pm = true;
         }
         int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
         if (grid < 1) grid = 1;
@@ -511,17 +592,17 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     if (tw == 32) {
         static bool attr_done = false;
         if (!attr_done) {
-            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<32>::SMEM));
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_done = true;
         }
-        conv_tc_kernel<32><<<grid, 256, Geo<32>::SMEM, stream>>>(tm_w, tm_x, a);
+        conv_tc_kernel<32><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
     } else {
         static bool attr_done = false;
         if (!attr_done) {
-            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Geo<16>::SMEM));
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_done = true;
         }
-        conv_tc_kernel<16><<<grid, 256, Geo<16>::SMEM, stream>>>(tm_w, tm_x, a);
+        conv_tc_kernel<16><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
     }
     MB_CUDA(cudaGetLastError());
     return MB_OK;

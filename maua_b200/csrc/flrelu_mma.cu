@@ -745,11 +745,15 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.y = a.y_nhwc;
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
-        static int variant = -1;
-        if (variant < 0) {
+        // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200:
+        // the persistent kernel wins on small maps and on up=2 layers without a partial channel group, the grid
+        // version on the large up=4 layers and wherever the last channel group is mostly padding)
+        static int forced = -2;
+        if (forced == -2) {
             const char* e = getenv("MB_FLRELU_NHWC");
-            variant = e ? atoi(e) : 1;
+            forced = e ? atoi(e) : -1;
         }
+        const int variant = forced >= 0 ? forced : ((a.Hout <= 160 || (UP == 2 && a.C % kCG == 0)) ? 1 : 0);
         if (variant == 1) {
             constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;
             static bool attr_p = false;

@@ -26,7 +26,8 @@ struct ConvTcArgs {
     int B, Cin, Cout, Hin, Win, Cp_in, Wp_out, ksz;
     int pad;            // zero padding per side (StyleGAN3: ksz-1 'full', StyleGAN2: ksz/2 'same'); output = in + 2*pad - (ksz-1)
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
-    int pm_max_cout = 96;  // layers with ceil16(Cout) <= this run the pixel-major tile (0 = never)
+    int pm_max_cout = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major tile (0 = never)
+    int narrow_a = 1;      // Cout <= 128: load only ceil8(Cout) weight rows per tile and keep them resident when they fit
     int num_sms;
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);

@@ -14,13 +14,17 @@
 // so one warp carries a 32x32 output tile of one channel from the fp16 input tile to the fp16 output
 // without any intermediate leaving the register file (no shared-memory round trips, no block barriers).
 // The (2*32+10)^2 upsampled intermediate is produced and consumed in five 16-row strips.
-// Filter taps are split hi+lo in fp16 (two MMAs per block): rounding the taps to a single fp16 is a
-// systematic error that costs up to 1e-3 in the final pixels (scratch/emul_mma_fir.py), the split
-// brings the constant operand to ~2^-22.  Intermediates are rounded to fp16 between passes (measured
-// harmless: 2.8e-4 vs 2.7e-4 max pixel error end to end).
+// Filter taps are single fp16 values.  Rounding every tap to nearest is a *systematic* DC-gain error per polyphase
+// branch that costs up to 1e-3 in the final pixels (scratch/emul_mma_fir.py), so the host picks, per branch, the
+// round-up/round-down combination of its six taps whose sum is closest to the exact branch gain (tune_branch,
+// residual ~1e-6), and the down filter's DC error is one fp32 factor in the output scale.  That leaves the
+// activation free of per-lane fp32 multipliers: it runs on packed halves as max(t, slope*t) and a clamp (4 half2
+// instructions per 4 values), with the lrelu gain moved behind the (linear) down filter into the output scale.
+// Intermediates are rounded to fp16 between passes (measured harmless: 2.8e-4 vs 2.7e-4 max pixel error end to end).
 //
 // Index conventions as in flrelu.cu.  Supported: down=2/12 taps with up=2/12 taps or up=4/24 taps,
 // separable filters (every non-ToRGB layer of StyleGAN3-T and the critically sampled layers of -R).
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,10 +53,18 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ uint32_t clamp2(uint32_t v, uint32_t c) {
-    __half2 h = *reinterpret_cast<__half2*>(&v), ch = *reinterpret_cast<__half2*>(&c);
+// leaky relu (0 <= slope <= 1, gain applied later) and clamp on two packed halves
+__device__ __forceinline__ uint32_t lrelu_clamp2(uint32_t v, uint32_t s, uint32_t c) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    const __half2 sh = *reinterpret_cast<__half2*>(&s), ch = *reinterpret_cast<__half2*>(&c);
+    h = __hmax2(h, __hmul2(h, sh));
     h = __hmin2(__hmax2(h, __hneg2(ch)), ch);
     return *reinterpret_cast<uint32_t*>(&h);
+}
+// first input sample an axis needs for output o0: ceil((2*o0 - pad) / UP) - e   (UP is 2 or 4: shifts)
+template <int UP>
+__device__ __forceinline__ int first_in(int o0, int pad, int e) {
+    return ((2 * o0 - pad + UP - 1) >> (UP == 2 ? 1 : 2)) - e;
 }
 __device__ __forceinline__ int fdiv(int a, int b) {
     int q = a / b;
@@ -86,10 +98,10 @@ struct MmaParams {
     __half* y;
     const uint4* frags;  // [NFRAG][32]
     int C, Hin, Win, Wp_in, Hout, Wout, Wp_out, Cp_out, px0, py0, tiles_x, tiles_y, e, tpw;
-    float gain, slope, clamp;
-    int rho;      // phase of the first intermediate sample of a tile: pad mod UP
-    float cd2;    // (DC correction of the fp16-rounded down filter)^2, folded into the output scale
-    float cu[4];  // DC correction per up-filter polyphase branch (exact / fp16-rounded branch sum)
+    float slope;
+    float clamp_pre;  // clamp / gain: the clamp acts before the gain, which is folded into out_gain
+    float out_gain;   // gain * (DC correction of the fp16-rounded down filter)^2
+    int rho;          // phase of the first intermediate sample of a tile: pad mod UP
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -104,8 +116,7 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // The four-pass chain for one 32x32 output tile; X = fp16 input tile in shared memory (row pitch kXP),
 // dx = even column offset of the first needed input sample inside the tile rows.
-// ga/gb: activation multipliers for the even / odd column of this lane's accumulator pairs, already
-// carrying gain, slope and the DC corrections of the fp16-rounded up-filter branches (see build_frags).
+// sl2 / cl2: slope and clamp (pre-gain) replicated in both halves.
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
@@ -113,7 +124,7 @@ struct NoHook {
 // issues the prefetch of its next input tile there.
 template <int UP, class Hook = NoHook>
 __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR], const uint4 (&AD)[3],
-                                          const float (&ga)[2], const float (&gb)[2], uint32_t cl2, int g, int tig,
+                                          uint32_t sl2, uint32_t cl2, int g, int tig,
                                           float (&OUT)[2][4][4], Hook x_dead = Hook()) {
     using K = MC<UP>;
     uint32_t P1[2][kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers (slot = block & 1)
@@ -152,14 +163,9 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
         for (int nb = 0; nb < kJB; ++nb) {
             float acc[4];
             mma16816_z(acc, AU[K::var(j)], P1[wb & 1][nb >> 1][nb & 1], P1[(wb + 1) & 1][nb >> 1][nb & 1]);
-            // lrelu(t) * gain = a*t + b*|t| with a = g(1+slope)/2, b = g(1-slope)/2 (fp32), then clamp on the
-            // packed halves (|clamp| <= 65504; an fp32 overflow packs to inf and is clamped all the same)
-            const float v0 = fmaf(fabsf(acc[0]), ga[1], acc[0] * ga[0]);
-            const float v1 = fmaf(fabsf(acc[1]), gb[1], acc[1] * gb[0]);
-            const float v2 = fmaf(fabsf(acc[2]), ga[1], acc[2] * ga[0]);
-            const float v3 = fmaf(fabsf(acc[3]), gb[1], acc[3] * gb[0]);
-            P2[nb][0] = clamp2(pack2(v0, v1), cl2);
-            P2[nb][1] = clamp2(pack2(v2, v3), cl2);
+            // activation on the packed halves (an fp32 overflow packs to inf and is clamped all the same)
+            P2[nb][0] = lrelu_clamp2(pack2(acc[0], acc[1]), sl2, cl2);
+            P2[nb][1] = lrelu_clamp2(pack2(acc[2], acc[3]), sl2, cl2);
         }
         // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
         uint32_t P3[4][2];
@@ -190,31 +196,46 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
     }
 }
 
-// Per-lane setup shared by both kernels: constant fragments and activation multipliers.
+// Per-lane setup shared by the kernels: constant fragments and activation constants.
 template <int UP>
 struct LaneConsts {
     uint4 AU[MC<UP>::NVAR];
     uint4 AD[3];
-    float ga[2], gb[2];
+    uint32_t sl2, cl2;
 };
 template <int UP>
 __device__ __forceinline__ void lane_setup(const MmaParams& p, int lane, LaneConsts<UP>& L) {
     using K = MC<UP>;
-    const int g = lane >> 2, tig = lane & 3;
 #pragma unroll
     for (int v = 0; v < K::NVAR; ++v) L.AU[v] = p.frags[v * 32 + lane];
 #pragma unroll
     for (int s = 0; s < 3; ++s) L.AD[s] = p.frags[(K::NVAR + s) * 32 + lane];
-    // phase of intermediate row/column a inside a 16-block: (rho - a) mod UP; the fp16-rounded taps of each
-    // polyphase branch are renormalised to the exact branch DC gain here, in fp32, for free.
-    const float cy = p.cu[((p.rho - g) % UP + UP) % UP];
-    const float cx0 = p.cu[((p.rho - 2 * tig) % UP + UP) % UP];
-    const float cx1 = p.cu[((p.rho - 2 * tig - 1) % UP + UP) % UP];
-    const float a0 = p.gain * cy * cx0, a1 = p.gain * cy * cx1;
-    L.ga[0] = a0 * 0.5f * (1.0f + p.slope);  // a*t + b*|t| == lrelu(t)*gain
-    L.ga[1] = a0 * 0.5f * (1.0f - p.slope);
-    L.gb[0] = a1 * 0.5f * (1.0f + p.slope);
-    L.gb[1] = a1 * 0.5f * (1.0f - p.slope);
+    L.sl2 = pack2(p.slope, p.slope);
+    const float c = fminf(p.clamp_pre, 65504.0f);
+    L.cl2 = pack2(c, c);
+}
+
+// Fetch the [IYT rows x 56 halfs] input tile of one warp with cp.async (zero fill outside the image = padding).
+// Lane -> (row mod 4, 16-byte chunk): the chunk column and its byte count are per-tile constants of the lane and
+// the row loop is fully unrolled with immediate offsets (this loader was 15 % of the kernel's instructions when
+// it derived row and chunk from a running index, ncu r1).
+template <int UP>
+__device__ __forceinline__ void load_tile_async(const MmaParams& p, const __half* xp, __half* X, int ix0, int iy0, int lane) {
+    using K = MC<UP>;
+    const int rsub = lane >> 3, ch = lane & 7;
+    const int ixc = (ix0 & ~7) + ch * 8;
+    const bool col_ok = ch < 7 && ixc >= 0 && ixc < p.Win;
+    const int col_bytes = col_ok ? min(8, p.Win - ixc) * 2 : 0;
+    const __half* src = xp + static_cast<long long>(iy0 + rsub) * p.Wp_in + ixc;
+    __half* dst = X + rsub * kXP + ch * 8;
+    if (ch < 7) {
+#pragma unroll
+        for (int it = 0; it < K::IYT / 4; ++it) {
+            const bool ok = static_cast<unsigned>(iy0 + rsub + 4 * it) < static_cast<unsigned>(p.Hin);
+            cp_async16_zfill(dst + it * 4 * kXP, (ok && col_ok) ? src + static_cast<long long>(it) * 4 * p.Wp_in : xp, ok ? col_bytes : 0);
+        }
+    }
+    cp_async_commit();
 }
 
 // One warp = a run of `tpw` consecutive 32x32 output tiles of one (b, c) plane; the input tile of
@@ -236,8 +257,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
 
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
-    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
-    const float oscale = (p.scale ? p.scale[b * p.C + c] : 1.0f) * p.cd2;
+    const float oscale = (p.scale ? p.scale[b * p.C + c] : 1.0f) * p.out_gain;
     __half* yp = p.y + (static_cast<long long>(b) * p.C + c) * p.Hout * p.Wp_out;
 
     // first input sample each axis needs: n = ceil((2*o0 - pad)/UP), shifted down by e so it is even;
@@ -246,25 +266,16 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         ox0 = tx * kOT;
         oy0 = ty * kOT;
-        ix0 = -fdiv(-(2 * ox0 - p.px0), UP) - p.e;
-        iy0 = -fdiv(-(2 * oy0 - p.py0), UP) - p.e;
+        ix0 = first_in<UP>(ox0, p.px0, p.e);
+        iy0 = first_in<UP>(oy0, p.py0, p.e);
     };
     auto load_tile = [&](int tile, __half* X) {
         int ox0, oy0, ix0, iy0;
         origin(tile, ox0, oy0, ix0, iy0);
-        const int ixa = fdiv(ix0, 8) * 8;
+        const int ixa = ix0 & ~7;
         if (p.bias == nullptr) {
-            for (int idx = lane; idx < K::IYT * 7; idx += 32) {
-                const int row = idx / 7, ch = idx - row * 7;
-                const int iy = iy0 + row, ixc = ixa + ch * 8;
-                int bytes = 0;
-                const __half* src = xp;
-                if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
-                    bytes = min(8, p.Win - ixc) * 2;
-                    src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
-                }
-                cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
-            }
+            load_tile_async<UP>(p, xp, X, ix0, iy0, lane);
+            return;
         } else {  // op-level API with a bias: synchronous path, bias added in fp32 and re-rounded
             const float bias = p.bias[c];
             for (int idx = lane; idx < K::IYT * 7; idx += 32) {
@@ -297,10 +308,10 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         __syncwarp();
         int ox0, oy0, ix0, iy0;
         origin(tile, ox0, oy0, ix0, iy0);
-        const int dx = ix0 - fdiv(ix0, 8) * 8;  // even by construction
+        const int dx = ix0 & 7;  // even by construction
 
         float OUT[2][4][4];
-        fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT);
+        fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT);
 
         // ---- store: * next-layer style, fp16, two adjacent columns per thread
 #pragma unroll
@@ -360,8 +371,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     }
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
-    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
-    const float oscale = ((valid && p.scale) ? p.scale[b * p.C + c] : 1.0f) * p.cd2;
+    const float oscale = ((valid && p.scale) ? p.scale[b * p.C + c] : 1.0f) * p.out_gain;
 
     if (!valid) {  // channel padding of the last group: both staging planes of this warp stay zero
         for (int sb = 0; sb < 2; ++sb) {
@@ -375,25 +385,13 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
         const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
         ox0 = tx * kOT;
         oy0 = ty * kOT;
-        ix0 = -fdiv(-(2 * ox0 - p.px0), UP) - p.e;
-        iy0 = -fdiv(-(2 * oy0 - p.py0), UP) - p.e;
+        ix0 = first_in<UP>(ox0, p.px0, p.e);
+        iy0 = first_in<UP>(oy0, p.py0, p.e);
     };
     auto load_tile = [&](int tile) {
         int ox0, oy0, ix0, iy0;
         origin(tile, ox0, oy0, ix0, iy0);
-        const int ixa = fdiv(ix0, 8) * 8;
-        for (int idx = lane; idx < K::IYT * 7; idx += 32) {
-            const int row = idx / 7, ch = idx - row * 7;
-            const int iy = iy0 + row, ixc = ixa + ch * 8;
-            int bytes = 0;
-            const __half* src = xp;
-            if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
-                bytes = min(8, p.Win - ixc) * 2;
-                src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
-            }
-            cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
-        }
-        cp_async_commit();
+        load_tile_async<UP>(p, xp, X, ix0, iy0, lane);
     };
     // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
     auto write_out = [&](int tile, int sb) {
@@ -430,9 +428,9 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
             __syncwarp();
             int ox0, oy0, ix0, iy0;
             origin(tile, ox0, oy0, ix0, iy0);
-            const int dx = ix0 - fdiv(ix0, 8) * 8;
+            const int dx = ix0 & 7;
             float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT, [&]() {
+            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, [&]() {
                 __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
                 if (i + 1 < n) load_tile(tile + 1);
             });
@@ -466,11 +464,17 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
 // Same arithmetic and staging scheme as flrelu_mma_nhwc_kernel, restructured after the ncu source view of that
 // kernel showed ~18 % of all warp samples parked on its two mbarrier waits (every warp had to wait for the slowest
 // warp's previous tile before starting its next one) and one exposed first-tile load + last write-out per 8-tile CTA:
-//   * one CTA per SM walks a contiguous range of the (batch, channel group, tile) index space, so the input
+//   * one CTA per SM walks a contiguous range of the (frame, tile, channel group) index space -- channel group
+//     fastest, so the cheap items of a partial last group are spread evenly over the CTAs -- and the input
 //     prefetch chain and the write-out pipeline never drain until the layer is done;
 //   * three staging buffers and a write-out that lags TWO tiles behind: a warp may run two tiles ahead of the
-//     slowest warp of its CTA before it blocks.
+//     slowest warp of its CTA before it blocks;
+//   * item coordinates advance incrementally (no per-tile integer divisions).
 constexpr int kNSB = 3;
+
+struct ItemPos {
+    int grp, tx, ty, b;
+};
 
 template <int UP>
 __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const MmaParams p, int ngroups, int total) {
@@ -484,7 +488,6 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
     uint64_t* full = bars;           // [kNSB] all 16 planes of a staging buffer written
     uint64_t* empty = bars + kNSB;   // [kNSB] all 16 write-out shares of a staging buffer done
 
-    const int ntiles = p.tiles_x * p.tiles_y;
     const int per = (total + gridDim.x - 1) / gridDim.x;
     const int start = blockIdx.x * per;
     const int n = min(per, total - start);
@@ -496,88 +499,87 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
     }
     LaneConsts<UP> LC;
     lane_setup<UP>(p, lane, LC);
-    const uint32_t cl2 = pack2(fminf(p.clamp, 65504.0f), fminf(p.clamp, 65504.0f));
     __syncthreads();  // barriers initialised (the only block-wide barrier: warps run decoupled from here on)
 
-    struct Item { int b, c0, tile, ox0, oy0, ix0, iy0; };
-    auto item = [&](int idx) {
-        Item it;
-        it.tile = idx % ntiles;
-        const int r = idx / ntiles;
-        it.c0 = (r % ngroups) * kCG;
-        it.b = r / ngroups;
-        const int ty = it.tile / p.tiles_x, tx = it.tile - ty * p.tiles_x;
-        it.ox0 = tx * kOT;
-        it.oy0 = ty * kOT;
-        it.ix0 = -fdiv(-(2 * it.ox0 - p.px0), UP) - p.e;
-        it.iy0 = -fdiv(-(2 * it.oy0 - p.py0), UP) - p.e;
-        return it;
-    };
-    auto load_tile = [&](const Item& it) {
-        if (it.c0 + warp >= p.C) return;
-        const __half* xp = p.x + (static_cast<long long>(it.b) * p.C + it.c0 + warp) * p.Hin * p.Wp_in;
-        const int ixa = fdiv(it.ix0, 8) * 8;
-        for (int idx = lane; idx < K::IYT * 7; idx += 32) {
-            const int row = idx / 7, ch = idx - row * 7;
-            const int iy = it.iy0 + row, ixc = ixa + ch * 8;
-            int bytes = 0;
-            const __half* src = xp;
-            if (iy >= 0 && iy < p.Hin && ixc >= 0 && ixc < p.Win) {
-                bytes = min(8, p.Win - ixc) * 2;
-                src = xp + static_cast<long long>(iy) * p.Wp_in + ixc;
+    auto advance = [&](ItemPos& q) {
+        if (++q.grp == ngroups) {
+            q.grp = 0;
+            if (++q.tx == p.tiles_x) {
+                q.tx = 0;
+                if (++q.ty == p.tiles_y) { q.ty = 0; ++q.b; }
             }
-            cp_async16_zfill(X + row * kXP + ch * 8, src, bytes);
         }
-        cp_async_commit();
+    };
+    auto load_tile = [&](const ItemPos& q) {
+        const int c = q.grp * kCG + warp;
+        if (c >= p.C) return;
+        const __half* xp = p.x + (static_cast<long long>(q.b) * p.C + c) * p.Hin * p.Wp_in;
+        load_tile_async<UP>(p, xp, X, first_in<UP>(q.tx * kOT, p.px0, p.e), first_in<UP>(q.ty * kOT, p.py0, p.e), lane);
     };
     // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
-    auto write_out = [&](const Item& it, int sb) {
+    auto write_out = [&](const ItemPos& q, int sb) {
         const __half* st = stage_base + sb * kCG * (kStageBytes / 2);
+        const int ox = q.tx * kOT + lane;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const int ly = 2 * warp + k, lx = lane;
-            const int oy = it.oy0 + ly, ox = it.ox0 + lx;
+            const int ly = 2 * warp + k;
+            const int oy = q.ty * kOT + ly;
             if (oy < p.Hout && ox < p.Wout) {
-                const __half* sp = st + ly * kSP + lx;
+                const __half* sp = st + ly * kSP + lane;
                 uint32_t w[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * q) * (kStageBytes / 2));
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * q + 1) * (kStageBytes / 2));
-                    w[q] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+                for (int qq = 0; qq < 8; ++qq) {
+                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * qq) * (kStageBytes / 2));
+                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * qq + 1) * (kStageBytes / 2));
+                    w[qq] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
                 }
-                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(it.b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + it.c0);
+                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(q.b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + q.grp * kCG);
                 dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
                 dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
             }
         }
     };
-    auto drain = [&](int j) {  // write out tile j of this CTA's range (all 16 warps take part)
+    auto drain = [&](const ItemPos& q, int j) {  // write out tile j of this CTA's range (all 16 warps take part)
         const int sb = j % kNSB;
         mbar_wait(&full[sb], (j / kNSB) & 1);
-        write_out(item(start + j), sb);
+        write_out(q, sb);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[sb]);
     };
 
-    Item cur = item(start);
+    ItemPos cur;
+    {
+        int r = start;
+        cur.grp = r % ngroups; r /= ngroups;
+        cur.tx = r % p.tiles_x; r /= p.tiles_x;
+        cur.ty = r % p.tiles_y; r /= p.tiles_y;
+        cur.b = r;
+    }
+    // items i-1 and i-2, packed into one register each (grp | tx << 8 | ty << 16 | b << 24: launch() checks the ranges)
+    auto pack_pos = [](const ItemPos& q) { return static_cast<uint32_t>(q.grp | (q.tx << 8) | (q.ty << 16) | (q.b << 24)); };
+    auto unpack_pos = [](uint32_t v) {
+        ItemPos q;
+        q.grp = v & 255; q.tx = (v >> 8) & 255; q.ty = (v >> 16) & 255; q.b = v >> 24;
+        return q;
+    };
+    uint32_t old1 = pack_pos(cur), old2 = old1;
     load_tile(cur);
     for (int i = 0; i < n; ++i) {
         const int sb = i % kNSB;
-        if (i >= 2) drain(i - 2);
+        if (i >= 2) drain(unpack_pos(old2), i - 2);
         // the staging buffer is free once every warp has written out its share of tile i-3
         if (i >= kNSB) mbar_wait(&empty[sb], ((i / kNSB) - 1) & 1);
-        Item nxt = cur;
-        if (i + 1 < n) nxt = item(start + i + 1);
+        ItemPos nxt = cur;
+        advance(nxt);
         __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
-        const int c = cur.c0 + warp;
+        const int c = cur.grp * kCG + warp;
         if (c < p.C) {
+            const float oscale = (p.scale ? p.scale[cur.b * p.C + c] : 1.0f) * p.out_gain;
             cp_async_wait<0>();
             __syncwarp();
-            const int dx = cur.ix0 - fdiv(cur.ix0, 8) * 8;
-            const float oscale = (p.scale ? p.scale[cur.b * p.C + c] : 1.0f) * p.cd2;
+            const int dx = first_in<UP>(cur.tx * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.ga, LC.gb, cl2, g, tig, OUT, [&]() {
+            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, [&]() {
                 __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
                 if (i + 1 < n) load_tile(nxt);
             });
@@ -597,10 +599,13 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[sb]);
+        old2 = old1;
+        old1 = pack_pos(cur);
         cur = nxt;
     }
-    if (n >= 2) drain(n - 2);
-    drain(n - 1);
+    // after the loop: old1 = item n-1, old2 = item n-2
+    if (n >= 2) drain(unpack_pos(old2), n - 2);
+    drain(unpack_pos(old1), n - 1);
 }
 
 // ---- host: constant fragments -------------------------------------------------------------------
@@ -638,29 +643,69 @@ void emit_fragment(const float (&A)[16][16], uint4* out) {
     }
 }
 
-// DC corrections: the taps enter the MMAs rounded to fp16, which is a *systematic* gain error per polyphase
-// branch (measured: up to 1e-3 in the final pixels when left alone, scratch/emul_mma_fir.py).  Each branch is
-// renormalised to its exact DC gain with an fp32 factor that rides on multiplies the kernel does anyway.
-template <int UP>
-void dc_corrections(const FlreluArgs& a, float (&cu)[4], float& cd2) {
-    constexpr int UT = 6 * UP;
-    for (int r = 0; r < 4; ++r) cu[r] = 1.0f;
-    for (int r = 0; r < UP; ++r) {
-        double exact = 0.0, rounded = 0.0;
-        for (int m = 0; m < 6; ++m) {
-            const float t = static_cast<float>(UP) * a.fu[UT - 1 - r - UP * m];
-            exact += t;
-            rounded += h2f_bits(f2h_bits(t));
+// fp16 taps of one polyphase branch with an (almost) exact DC gain: every tap may round down or up; of the 2^n
+// combinations the one whose sum is closest to the exact sum wins (ties: least squared tap error).  Rounding all
+// taps to nearest instead leaves a systematic gain error of up to ~3e-4 per branch and pass, which showed up as
+// 1e-3 in the final pixels (scratch/emul_mma_fir.py).
+inline void tune_branch(const float* taps, int n, float* out) {
+    float lo[8], hi[8];
+    double exact = 0.0;
+    for (int i = 0; i < n; ++i) {
+        exact += taps[i];
+        const uint16_t nb = f2h_bits(taps[i]);
+        const float nf = h2f_bits(nb);
+        if (nf == taps[i]) {
+            lo[i] = hi[i] = nf;
+        } else {
+            // neighbouring fp16 value on the other side of the exact tap (sign-magnitude bit pattern +-1)
+            const bool mag_up = fabsf(nf) < fabsf(taps[i]);
+            uint16_t ob = static_cast<uint16_t>(mag_up ? nb + 1 : nb - 1);
+            if ((nb & 0x7fff) == 0) ob = static_cast<uint16_t>((taps[i] < 0 ? 0x8000 : 0) | 1);
+            const float of = h2f_bits(ob);
+            lo[i] = nf < of ? nf : of;
+            hi[i] = nf < of ? of : nf;
         }
-        cu[r] = static_cast<float>(exact / rounded);
+    }
+    double best_err = 1e30, best_sq = 1e30;
+    int best = 0;
+    for (int m = 0; m < (1 << n); ++m) {
+        double sum = 0.0, sq = 0.0;
+        for (int i = 0; i < n; ++i) {
+            const float v = (m >> i & 1) ? hi[i] : lo[i];
+            sum += v;
+            sq += (static_cast<double>(v) - taps[i]) * (static_cast<double>(v) - taps[i]);
+        }
+        const double err = fabs(sum - exact);
+        if (err < best_err - 1e-12 || (err < best_err + 1e-12 && sq < best_sq)) {
+            best_err = err; best_sq = sq; best = m;
+        }
+    }
+    for (int i = 0; i < n; ++i) out[i] = (best >> i & 1) ? hi[i] : lo[i];
+}
+
+// up filter (with the up gain) as fp16-exact floats, branch by branch: fu16[UT - 1 - ph - UP*m] for phase ph
+template <int UP>
+void tuned_up_taps(const FlreluArgs& a, float (&fu16)[32]) {
+    constexpr int UT = 6 * UP;
+    for (int ph = 0; ph < UP; ++ph) {
+        float t[6], o[6];
+        for (int m = 0; m < 6; ++m) t[m] = static_cast<float>(UP) * a.fu[UT - 1 - ph - UP * m];
+        tune_branch(t, 6, o);
+        for (int m = 0; m < 6; ++m) fu16[UT - 1 - ph - UP * m] = o[m];
+    }
+}
+// down filter: its two polyphase branches are tuned separately; what remains of the total DC error is folded into
+// the fp32 output scale (returned as exact / rounded).
+inline double tuned_down_taps(const FlreluArgs& a, float (&fd16)[12]) {
+    for (int ph = 0; ph < 2; ++ph) {
+        float t[6], o[6];
+        for (int m = 0; m < 6; ++m) t[m] = a.fd[ph + 2 * m];
+        tune_branch(t, 6, o);
+        for (int m = 0; m < 6; ++m) fd16[ph + 2 * m] = o[m];
     }
     double exact = 0.0, rounded = 0.0;
-    for (int k = 0; k < 12; ++k) {
-        exact += a.fd[k];
-        rounded += h2f_bits(f2h_bits(a.fd[k]));
-    }
-    const double cd = exact / rounded;
-    cd2 = static_cast<float>(cd * cd);
+    for (int k = 0; k < 12; ++k) { exact += a.fd[k]; rounded += fd16[k]; }
+    return exact / rounded;
 }
 
 template <int UP>
@@ -676,6 +721,9 @@ int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
     }
     std::vector<uint4> host(K::NFRAG * 32);
     constexpr int UT = 6 * UP;
+    float fu16[32], fd16[12];
+    tuned_up_taps<UP>(a, fu16);
+    tuned_down_taps(a, fd16);
     for (int v = 0; v < K::NVAR; ++v) {
         float A[16][16] = {};
         const int off = (UP == 2) ? 0 : 4 * v;
@@ -687,7 +735,7 @@ int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
             const int ph = UP * n - num;
             for (int m = 0; m < 6; ++m) {
                 const int col = off + e + n + m;
-                if (col >= 0 && col < 16) A[r][col] = static_cast<float>(UP) * a.fu[UT - 1 - ph - UP * m];
+                if (col >= 0 && col < 16) A[r][col] = fu16[UT - 1 - ph - UP * m];
             }
         }
         emit_fragment(A, &host[v * 32]);
@@ -697,7 +745,7 @@ int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
         for (int r = 0; r < 16; ++r)
             for (int col = 0; col < 16; ++col) {
                 const int k = 16 * s + col - 2 * r;
-                if (k >= 0 && k < 12) A[r][col] = a.fd[11 - k];
+                if (k >= 0 && k < 12) A[r][col] = fd16[11 - k];
             }
         emit_fragment(A, &host[(K::NVAR + s) * 32]);
     }
@@ -734,10 +782,15 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     p.tiles_x = ceil_div(a.Wout, kOT); p.tiles_y = ceil_div(a.Hout, kOT);
     p.e = e;
     p.rho = rho;
-    dc_corrections<UP>(a, p.cu, p.cd2);
+    {
+        float fd16[12];
+        const double cd = tuned_down_taps(a, fd16);
+        p.out_gain = static_cast<float>(static_cast<double>(a.gain) * cd * cd);
+    }
     const int ntiles = p.tiles_x * p.tiles_y;
     p.tpw = ntiles < 64 ? 1 : (ntiles < 256 ? 2 : 4);
-    p.gain = a.gain; p.slope = a.slope; p.clamp = a.clamp >= 0.0f ? a.clamp : 3.0e38f;
+    p.slope = a.slope;
+    p.clamp_pre = a.clamp >= 0.0f ? a.clamp / a.gain : 3.0e38f;
     if (a.y_nhwc) {
         // fused transpose: 16 channels per CTA, 32-byte pixel chunks into [B][H][W][Cp_out]
         MB_REQUIRE(a.bias == nullptr, "filtered_lrelu: the channels-last variant takes the bias from the conv epilogue");
@@ -745,15 +798,17 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.y = a.y_nhwc;
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
-        // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200:
-        // the persistent kernel wins on small maps and on up=2 layers without a partial channel group, the grid
-        // version on the large up=4 layers and wherever the last channel group is mostly padding)
+        // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200,
+        // scripts/layer_times.py: the persistent kernel wins on small maps and on up=2 layers, the grid version on
+        // the large up=4 layers and on large maps whose last channel group is mostly padding)
         static int forced = -2;
         if (forced == -2) {
             const char* e = getenv("MB_FLRELU_NHWC");
             forced = e ? atoi(e) : -1;
         }
-        const int variant = forced >= 0 ? forced : ((a.Hout <= 160 || (UP == 2 && a.C % kCG == 0)) ? 1 : 0);
+        const bool packable = ceil_div(a.C, kCG) <= 255 && p.tiles_x <= 255 && p.tiles_y <= 255 && a.B <= 255;
+        const bool prefer_p = UP == 2 ? (a.C % kCG == 0 || a.Hout <= 300) : a.Hout <= 100;
+        const int variant = !packable ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
         if (variant == 1) {
             constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;
             static bool attr_p = false;

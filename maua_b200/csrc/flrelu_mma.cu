@@ -66,11 +66,6 @@ template <int UP>
 __device__ __forceinline__ int first_in(int o0, int pad, int e) {
     return ((2 * o0 - pad + UP - 1) >> (UP == 2 ? 1 : 2)) - e;
 }
-__device__ __forceinline__ int fdiv(int a, int b) {
-    int q = a / b;
-    if ((a % b != 0) && ((a < 0) != (b < 0))) --q;
-    return q;
-}
 
 constexpr int kOT = 32;      // output tile edge per warp
 constexpr int kStrips = 5;   // 16-row strips of the intermediate (2*32+10 = 74 -> 80 rows)
@@ -344,6 +339,31 @@ constexpr int kCG = 16;          // channels per CTA
 constexpr int kSP = 40;          // staging row pitch in halfs (conflict-free fragment stores)
 constexpr int kStageBytes = kOT * kSP * 2;
 
+// Write-out share of one warp for a finished 32x32 tile held as 16 staged channel planes: image rows 2*warp and
+// 2*warp+1, one pixel per lane and row (16 LDS.U16 -> one 32-byte chunk).  A variant reading pixel pairs with
+// LDS.32 + PRMT issued fewer instructions but pushed the up=4 kernel into 70+ bytes of spills and measured slower.
+__device__ __forceinline__ void write_out_tile(const MmaParams& p, const __half* st, int warp, int lane, int b, int c0,
+                                               int ox0, int oy0) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int ly = 2 * warp + k, lx = lane;
+        const int oy = oy0 + ly, ox = ox0 + lx;
+        if (oy < p.Hout && ox < p.Wout) {
+            const __half* sp = st + ly * kSP + lx;
+            uint32_t w[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * q) * (kStageBytes / 2));
+                const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * q + 1) * (kStageBytes / 2));
+                w[q] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + c0);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    }
+}
+
 template <int UP>
 __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaParams p) {
     using K = MC<UP>;
@@ -381,58 +401,31 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     }
     __syncthreads();  // barriers initialised (the only block-wide barrier: warps run decoupled from here on)
 
-    auto origin = [&](int tile, int& ox0, int& oy0, int& ix0, int& iy0) {
-        const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-        ox0 = tx * kOT;
-        oy0 = ty * kOT;
-        ix0 = first_in<UP>(ox0, p.px0, p.e);
-        iy0 = first_in<UP>(oy0, p.py0, p.e);
+    // tile coordinates advance incrementally along the run (one division per CTA, none per tile); tx | ty << 16 in
+    // one register each for tile i and tile i-1 (this kernel sits at the 128-register limit)
+    uint32_t pos = static_cast<uint32_t>(tile0 % p.tiles_x) | (static_cast<uint32_t>(tile0 / p.tiles_x) << 16);
+    uint32_t ppos = pos;
+    auto load_tile = [&](uint32_t q) {
+        load_tile_async<UP>(p, xp, X, first_in<UP>((q & 0xffff) * kOT, p.px0, p.e), first_in<UP>((q >> 16) * kOT, p.py0, p.e), lane);
     };
-    auto load_tile = [&](int tile) {
-        int ox0, oy0, ix0, iy0;
-        origin(tile, ox0, oy0, ix0, iy0);
-        load_tile_async<UP>(p, xp, X, ix0, iy0, lane);
-    };
-    // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
-    auto write_out = [&](int tile, int sb) {
-        int ox0, oy0, ix0, iy0;
-        origin(tile, ox0, oy0, ix0, iy0);
-        const __half* st = stage_base + sb * kCG * (kStageBytes / 2);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int ly = 2 * warp + k, lx = lane;
-            const int oy = oy0 + ly, ox = ox0 + lx;
-            if (oy < p.Hout && ox < p.Wout) {
-                const __half* sp = st + ly * kSP + lx;
-                uint32_t w[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * q) * (kStageBytes / 2));
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * q + 1) * (kStageBytes / 2));
-                    w[q] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + c0);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-        }
+    auto write_out = [&](uint32_t q, int sb) {
+        write_out_tile(p, stage_base + sb * kCG * (kStageBytes / 2), warp, lane, b, c0, (q & 0xffff) * kOT, (q >> 16) * kOT);
     };
 
-    if (valid) load_tile(tile0);
+    if (valid) load_tile(pos);
     for (int i = 0; i < n; ++i) {
-        const int tile = tile0 + i, sb = i & 1;
+        const int sb = i & 1;
+        const uint32_t npos = ((pos & 0xffff) + 1 == static_cast<uint32_t>(p.tiles_x)) ? (pos & 0xffff0000u) + 0x10000u : pos + 1;
         // the staging buffer is free once every warp has written out its share of tile i-2
         if (i >= 2) mbar_wait(&empty[sb], ((i >> 1) - 1) & 1);
         if (valid) {
             cp_async_wait<0>();
             __syncwarp();
-            int ox0, oy0, ix0, iy0;
-            origin(tile, ox0, oy0, ix0, iy0);
-            const int dx = ix0 & 7;
+            const int dx = first_in<UP>((pos & 0xffff) * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
             fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, [&]() {
                 __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
-                if (i + 1 < n) load_tile(tile + 1);
+                if (i + 1 < n) load_tile(npos);
             });
             __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
 #pragma unroll
@@ -449,14 +442,16 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
         // write out this warp's share of the PREVIOUS tile while the other warps are still computing tile i
         if (i >= 1) {
             mbar_wait(&full[sb ^ 1], ((i - 1) >> 1) & 1);
-            write_out(tile - 1, sb ^ 1);
+            write_out(ppos, sb ^ 1);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[sb ^ 1]);
         }
+        ppos = pos;
+        pos = npos;
     }
     const int last = n - 1;
     mbar_wait(&full[last & 1], (last >> 1) & 1);
-    write_out(tile0 + last, last & 1);
+    write_out(ppos, last & 1);
 }
 
 
@@ -516,28 +511,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
         const __half* xp = p.x + (static_cast<long long>(q.b) * p.C + c) * p.Hin * p.Wp_in;
         load_tile_async<UP>(p, xp, X, first_in<UP>(q.tx * kOT, p.px0, p.e), first_in<UP>(q.ty * kOT, p.py0, p.e), lane);
     };
-    // this warp's share of a finished tile: rows 2*warp, 2*warp+1 (64 pixels x 16 channels = 32-byte chunks)
     auto write_out = [&](const ItemPos& q, int sb) {
-        const __half* st = stage_base + sb * kCG * (kStageBytes / 2);
-        const int ox = q.tx * kOT + lane;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int ly = 2 * warp + k;
-            const int oy = q.ty * kOT + ly;
-            if (oy < p.Hout && ox < p.Wout) {
-                const __half* sp = st + ly * kSP + lane;
-                uint32_t w[8];
-#pragma unroll
-                for (int qq = 0; qq < 8; ++qq) {
-                    const uint16_t lo = *reinterpret_cast<const uint16_t*>(sp + (2 * qq) * (kStageBytes / 2));
-                    const uint16_t hi = *reinterpret_cast<const uint16_t*>(sp + (2 * qq + 1) * (kStageBytes / 2));
-                    w[qq] = static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(p.y + ((static_cast<long long>(q.b) * p.Hout + oy) * p.Wout + ox) * p.Cp_out + q.grp * kCG);
-                dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-        }
+        write_out_tile(p, stage_base + sb * kCG * (kStageBytes / 2), warp, lane, q.b, q.grp * kCG, q.tx * kOT, q.ty * kOT);
     };
     auto drain = [&](const ItemPos& q, int j) {  // write out tile j of this CTA's range (all 16 warps take part)
         const int sb = j % kNSB;
@@ -799,15 +774,15 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
         // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200,
-        // scripts/layer_times.py: the persistent kernel wins on small maps and on up=2 layers, the grid version on
-        // the large up=4 layers and on large maps whose last channel group is mostly padding)
+        // scripts/layer_times.py: the persistent kernel wins on the small maps, the grid version on the large ones,
+        // earlier for up=4 whose persistent build spills at the 128-register limit)
         static int forced = -2;
         if (forced == -2) {
             const char* e = getenv("MB_FLRELU_NHWC");
             forced = e ? atoi(e) : -1;
         }
         const bool packable = ceil_div(a.C, kCG) <= 255 && p.tiles_x <= 255 && p.tiles_y <= 255 && a.B <= 255;
-        const bool prefer_p = UP == 2 ? (a.C % kCG == 0 || a.Hout <= 300) : a.Hout <= 100;
+        const bool prefer_p = a.Hout <= (UP == 2 ? 300 : 100);
         const int variant = !packable ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
         if (variant == 1) {
             constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;

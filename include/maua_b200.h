@@ -191,6 +191,29 @@ int mb_audio_onsets_rms(const float* audio, int64_t n, const float* mel_filterba
                         float* onsets, float* rms, int32_t* peak_idx, int32_t* n_peaks,
                         float* percussive_out, void* workspace, size_t workspace_bytes, mb_stream stream);
 
+/* harmonic(audio, margin) (which = 0) / percussive(audio, margin) (which = 1), features/audio.py:13-24:
+ * STFT -> HPSS soft mask -> iSTFT, device float32 [n] -> [n].  Workspace: mb_audio_workspace_bytes(n). */
+int mb_audio_hpss_component(const float* audio, int64_t n, float margin, int which, float* out,
+                            void* workspace, size_t workspace_bytes, mb_stream stream);
+
+/* Constant-Q chroma, rosa/spectral.py:286-325 chroma_cqt over rosa/constantq.py:13-116 cqt (recursive octaves:
+ * kaiser-sinc decimation by 2, rectangular STFT, sparse FFT-domain filter bank) and rosa/convert.py:69-117.
+ *   audio        device float32 [n], n a multiple of hop; hop a multiple of 2^(n_octaves-1)
+ *   decim_kernel device float32 [decim_taps]: torchaudio sinc_interp_kaiser 2:1 kernel (host-designed), left pad
+ *                decim_width
+ *   basis_*      CSR of the per-octave one-sided FFT basis [bins_per_octave, n_fft/2+1] (complex64 values as float
+ *                pairs), the octave-0 matrix; octave i uses it scaled by sqrt(2^i) (constantq.py:98)
+ *   inv_sqrt_len device float32 [n_bins] = 1/sqrt(filter length) (constantq.py:105-113)
+ *   fold         device float32 [n_chroma, n_bins] (cq_to_chroma)
+ *   cqt_mag      device float32 [n_bins, T] or NULL (|CQT|, for parity tests); chroma device float32 [n_chroma, T]
+ */
+size_t mb_chroma_workspace_bytes(int64_t n_samples, int n_bins, int hop);
+int mb_chroma_cqt(const float* audio, int64_t n, int hop, int n_fft, int n_octaves, int bins_per_octave,
+                  const float* decim_kernel, int decim_taps, int decim_width, const int32_t* basis_rowptr,
+                  const int32_t* basis_col, const float* basis_val, const float* inv_sqrt_len, const float* fold,
+                  int n_chroma, float threshold, int normalize, float* cqt_mag, float* chroma, void* workspace,
+                  size_t workspace_bytes, mb_stream stream);
+
 /* ---- envelope post-ops and latent sequencers (device float32, [T, C] row-major, T = frames) ----------
  * maua/audiovisual/audioreactive/signal.py: gaussian_filter :108-157 (circular padding, optional causal
  * half-kernel factor), normalize :27-38 (eps 0) / processing.py:53-56 (eps 1e-8), resample :5-24 (linear,

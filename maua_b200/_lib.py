@@ -62,6 +62,10 @@ _SIGNATURES = {
     "mb_net_activation_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_audio_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "mb_audio_onsets_rms": (C.c_int, [_P, C.c_int64, _P, C.c_float, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "mb_audio_hpss_component": (C.c_int, [_P, C.c_int64, C.c_float, C.c_int, _P, _P, C.c_size_t, _P]),
+    "mb_chroma_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
+    "mb_chroma_cqt": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P,
+                                C.c_int, C.c_float, C.c_int, _P, _P, _P, C.c_size_t, _P]),
     "mb_gaussian_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _P]),
     "mb_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P]),
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),

@@ -1,5 +1,6 @@
 """Audio-reactive feature / envelope / latent functions on the device (mirror of
 maua.audiovisual.audioreactive and its torch-native twin selfsupervised.features.audio)."""
-from .features import mel_filterbank, onset_peaks, onsets, onsets_rms, percussive, rms  # noqa: F401
+from .chroma import chroma_cqt, cqt_magnitude  # noqa: F401
+from .features import harmonic, mel_filterbank, onset_peaks, onsets, onsets_rms, percussive, rms  # noqa: F401
 from .latent import multi_weighted, single_weighted  # noqa: F401,E402
 from .signal import compress, expand, gaussian_filter, normalize, percentile, percentile_clip, resample  # noqa: F401,E402

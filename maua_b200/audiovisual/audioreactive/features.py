@@ -92,9 +92,32 @@ def rms(y, sr, frame_length=N_FFT, hop_length=HOP, center=True, pad_mode="reflec
     return _features(y, sr)[1].unsqueeze(-1)
 
 
+def _hpss_component(audio, margin, which):
+    if not audio.is_cuda:
+        raise RuntimeError("maua_b200 audio features need a CUDA tensor (no CPU fallback)")
+    lib = _lib.load()
+    y = audio.detach().to(torch.float32).contiguous().reshape(-1)
+    n = y.numel()
+    if n % HOP:
+        raise ValueError(f"audio length must be a multiple of {HOP} (resample to sr = 1024 * fps first)")
+    with torch.cuda.device(y.device):
+        out = torch.empty_like(y)
+        nbytes = lib.mb_audio_workspace_bytes(n)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=y.device)
+        off = (-ws.data_ptr()) % 256
+        _lib.check(lib.mb_audio_hpss_component(_lib.ptr(y), n, float(margin), int(which), _lib.ptr(out),
+                                               C.c_void_p(ws.data_ptr() + off), nbytes, _lib.stream_ptr()))
+    return out
+
+
+def harmonic(audio, margin=8.0):
+    """HPSS harmonic component (features/audio.py:13-17)."""
+    return _hpss_component(audio, margin, 0)
+
+
 def percussive(audio, margin=8.0):
     """HPSS percussive component (features/audio.py:20-24)."""
-    return _features(audio, 2 * 11025.0, margin=margin, want_percussive=True)[4]
+    return _hpss_component(audio, margin, 1)
 
 
 def onset_peaks(audio, sr):

@@ -346,3 +346,36 @@ extern "C" int mb_audio_onsets_rms(const float* audio, int64_t n, const float* m
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }
+
+/* harmonic(audio, margin) / percussive(audio, margin) of features/audio.py:13-24: STFT -> HPSS soft mask -> iSTFT. */
+extern "C" int mb_audio_hpss_component(const float* audio, int64_t n, float margin, int which, float* out, void* workspace,
+                                       size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(audio && out && workspace, "mb_audio_hpss_component: null argument");
+    MB_REQUIRE(which == 0 || which == 1, "mb_audio_hpss_component: which must be 0 (harmonic) or 1 (percussive)");
+    MB_REQUIRE(n >= 16 * kHop && n % kHop == 0, "mb_audio_hpss_component: need a multiple of %d samples (>= %d), got %lld", kHop,
+               16 * kHop, static_cast<long long>(n));
+    MB_REQUIRE(margin != 1.0f, "mb_audio_hpss_component: margin == 1 (split_zeros branch) is not implemented");
+    const AudioWs w = audio_ws(n);
+    if (workspace_bytes < w.total) {
+        set_error("mb_audio_hpss_component: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+        return MB_ENOMEM;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int T = static_cast<int>(n / kHop);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float2* tw = reinterpret_cast<float2*>(base + w.tw);
+    float* window = reinterpret_cast<float*>(base + w.window);
+    float2* spec = reinterpret_cast<float2*>(base + w.spec);
+    float* mag = reinterpret_cast<float*>(base + w.mag);
+    float2* comp = reinterpret_cast<float2*>(base + w.perc);
+    float* frames = reinterpret_cast<float*>(base + w.frames);
+    float* rms_tmp = reinterpret_cast<float*>(base + w.env);
+    audio_tables_kernel<<<kNfft / 256, 256, 0, stream>>>(tw, window);
+    stft_kernel<<<T + 1, 256, 0, stream>>>(audio, n, T, 0, tw, window, spec, mag, rms_tmp, nullptr, nullptr);
+    dim3 hg((kBins + 127) / 128, T + 1);
+    hpss_kernel<<<hg, 128, 0, stream>>>(spec, mag, T + 1, margin, which, comp);
+    istft_frame_kernel<<<T + 1, 256, 0, stream>>>(comp, tw, window, frames);
+    istft_ola_kernel<<<148 * 4, 256, 0, stream>>>(frames, window, n, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}

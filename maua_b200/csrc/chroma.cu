@@ -1,0 +1,214 @@
+// Constant-Q chroma on the GPU: the torch-native chroma_cqt of the reference,
+// maua/audiovisual/audioreactive/selfsupervised/features/rosa/constantq.py:13-116 (recursive octave-by-octave
+// CQT: kaiser-windowed sinc decimation by 2, rectangular-window STFT, sparse FFT-domain filter bank),
+// rosa/spectral.py:286-325 (chroma_cqt: |CQT| -> fold 36 bins/octave onto 12 chroma -> / max) and
+// rosa/convert.py:69-117 (cq_to_chroma).
+//
+// Data flow (one launch each):
+//   decimate_kernel x (n_octaves-1)  y_{i+1}[j] = sqrt(2) * sum_k h[k] y_i[2j + k - width]   (28-tap polyphase FIR,
+//                                    host-designed exactly as torchaudio's sinc_interp_kaiser kernel)
+//   cqt_kernel<NFFT>   grid (T, n_octaves): one CTA stages the NFFT-sample frame of its octave in shared memory
+//                      (reflect padding), runs a radix-2 Stockham FFT there and applies the sparse filter bank
+//                      (CSR, ~15 non-zeros per bin: the SAME matrix in every octave up to sqrt(2^i), constantq.py:98):
+//                      |sum_f B[k,f] X[f]| / sqrt(length_k) -> C[n_bins][T]
+//   chroma_fold_kernel chroma[c,t] = sum_b fold[c,b] C[b,t], global max via atomicMax on the (non-negative) bits
+//   chroma_norm_kernel chroma /= max
+// The audio is a few MB and every stage a handful of microseconds: latency bound, as SURVEY §8d expects.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb {
+namespace {
+
+__device__ __forceinline__ int reflect_idx(long long i, long long n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return static_cast<int>(i);
+}
+
+__global__ void decimate_kernel(const float* __restrict__ x, long long n_in, float* __restrict__ y, long long n_out,
+                                const float* __restrict__ h, int taps, int width, float post_scale) {
+    __shared__ float hs[64];
+    if (threadIdx.x < taps) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < n_out;
+         j += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float acc = 0.0f;
+        const long long base = 2 * j - width;
+        for (int k = 0; k < taps; ++k) {
+            const long long i = base + k;
+            const float v = (i >= 0 && i < n_in) ? x[i] : 0.0f;
+            acc = fmaf(hs[k], v, acc);
+        }
+        y[j] = acc * post_scale;
+    }
+}
+
+template <int N>
+__device__ float2* fft_pow2(float2* x, float2* y, const float2* tw) {
+    for (int ns = 1; ns < N; ns <<= 1) {
+        for (int j = threadIdx.x; j < N / 2; j += blockDim.x) {
+            const int k = j & (ns - 1);
+            const float2 w = tw[k * (N / 2 / ns)];
+            const float2 a = x[j], b0 = x[j + N / 2];
+            const float2 b = make_float2(w.x * b0.x - w.y * b0.y, w.x * b0.y + w.y * b0.x);
+            const int j0 = ((j - k) << 1) + k;
+            y[j0] = make_float2(a.x + b.x, a.y + b.y);
+            y[j0 + ns] = make_float2(a.x - b.x, a.y - b.y);
+        }
+        __syncthreads();
+        float2* t = x; x = y; y = t;
+    }
+    return x;
+}
+
+struct OctaveSrc {
+    const float* y[8];
+    long long n[8];
+};
+
+template <int N>
+__global__ void __launch_bounds__(256) cqt_kernel(OctaveSrc src, int hop0, int T, int bins_per_octave, int n_bins,
+                                                  const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                  const float2* __restrict__ val, const float* __restrict__ inv_sqrt_len,
+                                                  float* __restrict__ C) {
+    __shared__ float2 bufA[N];
+    __shared__ float2 bufB[N];
+    __shared__ float2 tw[N / 2];
+    const int t = blockIdx.x, oct = blockIdx.y;
+    const float* y = src.y[oct];
+    const long long n = src.n[oct];
+    const int hop = hop0 >> oct;
+    for (int i = threadIdx.x; i < N / 2; i += blockDim.x) {
+        float s, c;
+        sincospif(static_cast<float>(i) / static_cast<float>(N / 2), &s, &c);
+        tw[i] = make_float2(c, -s);
+    }
+    const long long start = static_cast<long long>(t) * hop - N / 2;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) bufA[i] = make_float2(y[reflect_idx(start + i, n)], 0.0f);
+    __syncthreads();
+    const float2* X = fft_pow2<N>(bufA, bufB, tw);
+    const float oct_scale = sqrtf(static_cast<float>(1 << oct));  // constantq.py:98
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int b = warp; b < bins_per_octave; b += (blockDim.x >> 5)) {
+        float re = 0.0f, im = 0.0f;
+        for (int e = rowptr[b] + lane; e < rowptr[b + 1]; e += 32) {
+            const float2 w = val[e];
+            const float2 x = X[col[e]];
+            re += w.x * x.x - w.y * x.y;
+            im += w.x * x.y + w.y * x.x;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            re += __shfl_xor_sync(0xffffffffu, re, o);
+            im += __shfl_xor_sync(0xffffffffu, im, o);
+        }
+        if (lane == 0) {
+            const int gb = n_bins - bins_per_octave * (oct + 1) + b;  // octave 0 = top octave (constantq.py:166-186)
+            if (gb >= 0) C[static_cast<long long>(gb) * T + t] = hypotf(re * oct_scale, im * oct_scale) * inv_sqrt_len[gb];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) chroma_fold_kernel(const float* __restrict__ C, const float* __restrict__ fold, int n_bins,
+                                                          int n_chroma, int T, float threshold, float* __restrict__ chroma,
+                                                          int* __restrict__ max_bits) {
+    __shared__ float red[8];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    float v = 0.0f;
+    if (idx < n_chroma * T) {
+        const int c = idx / T, t = idx - c * T;
+        for (int b = 0; b < n_bins; ++b) {
+            const float f = fold[c * n_bins + b];
+            if (f != 0.0f) v = fmaf(f, C[static_cast<long long>(b) * T + t], v);
+        }
+        if (v < threshold) v = 0.0f;
+        chroma[idx] = v;
+    }
+    float m = v;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        atomicMax(max_bits, __float_as_int(fmaxf(m, 0.0f)));  // non-negative floats order like their bit patterns
+    }
+}
+
+__global__ void chroma_norm_kernel(float* __restrict__ chroma, int n, const int* __restrict__ max_bits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) chroma[i] = chroma[i] / __int_as_float(*max_bits);
+}
+
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" size_t mb_chroma_workspace_bytes(int64_t n_samples, int n_bins, int hop) {
+    if (n_samples <= 0 || hop <= 0) return 0;
+    const size_t T = static_cast<size_t>(n_samples / hop);
+    // decimated signals sum to < n samples; CQT magnitudes; max word
+    return up256(sizeof(float) * static_cast<size_t>(n_samples + 64)) + up256(sizeof(float) * n_bins * T) + 256;
+}
+
+extern "C" int mb_chroma_cqt(const float* audio, int64_t n, int hop, int n_fft, int n_octaves, int bins_per_octave,
+                             const float* decim_kernel, int decim_taps, int decim_width, const int32_t* basis_rowptr,
+                             const int32_t* basis_col, const float* basis_val, const float* inv_sqrt_len, const float* fold,
+                             int n_chroma, float threshold, int normalize, float* cqt_mag, float* chroma, void* workspace,
+                             size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(audio && decim_kernel && basis_rowptr && basis_col && basis_val && inv_sqrt_len && fold && chroma && workspace,
+               "mb_chroma_cqt: null argument");
+    MB_REQUIRE(n_octaves >= 1 && n_octaves <= 8, "mb_chroma_cqt: 1..8 octaves, got %d", n_octaves);
+    MB_REQUIRE(n_fft == 512 || n_fft == 1024 || n_fft == 2048, "mb_chroma_cqt: n_fft %d unsupported (512, 1024, 2048)", n_fft);
+    MB_REQUIRE(hop > 0 && (hop % (1 << (n_octaves - 1))) == 0,
+               "mb_chroma_cqt: hop_length must be a multiple of 2^%d for a %d-octave CQT (constantq.py:66-72)", n_octaves - 1, n_octaves);
+    MB_REQUIRE(n > 0 && n % hop == 0, "mb_chroma_cqt: need a whole number of hops, got %lld samples", static_cast<long long>(n));
+    MB_REQUIRE(decim_taps > 0 && decim_taps <= 64, "mb_chroma_cqt: decimation kernel of %d taps unsupported", decim_taps);
+    MB_REQUIRE((n >> (n_octaves - 1)) > n_fft / 2, "mb_chroma_cqt: audio too short for reflect padding in the lowest octave");
+    const int n_bins = n_octaves * bins_per_octave;
+    const int T = static_cast<int>(n / hop);
+    const size_t need = mb_chroma_workspace_bytes(n, n_bins, hop);
+    if (workspace_bytes < need) {
+        set_error("mb_chroma_cqt: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return MB_ENOMEM;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float* ybuf = reinterpret_cast<float*>(base);
+    float* Cws = reinterpret_cast<float*>(base + up256(sizeof(float) * static_cast<size_t>(n + 64)));
+    int* max_bits = reinterpret_cast<int*>(base + need - 256);
+    float* C = cqt_mag ? cqt_mag : Cws;
+
+    OctaveSrc src;
+    src.y[0] = audio;
+    src.n[0] = n;
+    float* next = ybuf;
+    for (int i = 1; i < n_octaves; ++i) {
+        const long long n_in = src.n[i - 1], n_out = (n_in + 1) / 2;  // ceil(new_freq * length / orig_freq)
+        const int blocks = static_cast<int>((n_out + 255) / 256 < 148 * 8 ? (n_out + 255) / 256 : 148 * 8);
+        decimate_kernel<<<blocks, 256, 0, stream>>>(src.y[i - 1], n_in, next, n_out, decim_kernel, decim_taps, decim_width,
+                                                    1.41421356237309515f);  // my_y *= np.sqrt(2), constantq.py:84
+        src.y[i] = next;
+        src.n[i] = n_out;
+        next += (n_out + 3) / 4 * 4;
+    }
+    for (int i = n_octaves; i < 8; ++i) { src.y[i] = nullptr; src.n[i] = 0; }
+    dim3 grid(T, n_octaves);
+    const float2* val = reinterpret_cast<const float2*>(basis_val);
+    if (n_fft == 512)
+        cqt_kernel<512><<<grid, 256, 0, stream>>>(src, hop, T, bins_per_octave, n_bins, basis_rowptr, basis_col, val, inv_sqrt_len, C);
+    else if (n_fft == 1024)
+        cqt_kernel<1024><<<grid, 256, 0, stream>>>(src, hop, T, bins_per_octave, n_bins, basis_rowptr, basis_col, val, inv_sqrt_len, C);
+    else
+        cqt_kernel<2048><<<grid, 256, 0, stream>>>(src, hop, T, bins_per_octave, n_bins, basis_rowptr, basis_col, val, inv_sqrt_len, C);
+    MB_CUDA(cudaMemsetAsync(max_bits, 0, sizeof(int), stream));
+    const int total = n_chroma * T;
+    chroma_fold_kernel<<<(total + 255) / 256, 256, 0, stream>>>(C, fold, n_bins, n_chroma, T, threshold, chroma, max_bits);
+    if (normalize) chroma_norm_kernel<<<(total + 255) / 256, 256, 0, stream>>>(chroma, total, max_bits);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}

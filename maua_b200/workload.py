@@ -65,9 +65,10 @@ def c2_latents(num_ws: int = 16, duration_s: float = 30.0, fps: int = 24):
 
 def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 24):
     """Config 2 latents with the audio-reactive part computed ON THE DEVICE by the library's feature kernels:
-    sweep -> resample to sr = 1024*fps (one hop per frame) -> onsets / rms (mb_audio_onsets_rms) -> Gaussian
-    smoothing -> chroma-weighted key-latent mix blended by the onset envelope.  Returns (latents [T,num_ws,512]
-    on `device`, info dict with the device time of the feature pass)."""
+    sweep -> resample to sr = 1024*fps (one hop per frame) -> onsets / rms (mb_audio_onsets_rms) and constant-Q
+    chroma of the harmonic component (mb_audio_hpss_component + mb_chroma_cqt) -> Gaussian smoothing ->
+    chroma-weighted key-latent mix blended by the onset envelope.  Returns (latents [T,num_ws,512] on `device`,
+    info dict with the device time of the feature pass)."""
     from .audiovisual import audioreactive as ar
 
     audio, sr_file = sine_sweep(duration_s, tremolo_hz=4.0)
@@ -75,17 +76,18 @@ def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 
     sr = 1024 * fps
     t = np.arange(T * 1024) / sr
     y = torch.from_numpy(np.interp(t, np.arange(len(audio)) / sr_file, audio).astype(np.float32)).to(device)
-    _, chroma = host_envelopes(audio, sr_file, T)        # CQT chroma (row a9) is not built yet: pseudo-chroma drive
-    ar.onsets_rms(y, sr)                                   # warm-up (allocations, module load)
+    ar.onsets_rms(y, sr)                                   # warm-up (allocations, module load, filter design)
+    ar.chroma_cqt(ar.harmonic(y), sr, tuning=0.0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     onsets, rms = ar.onsets_rms(y, sr)
+    chroma = ar.chroma_cqt(ar.harmonic(y), sr, tuning=0.0).T.contiguous()   # [T, 12]
     e1.record()
     torch.cuda.synchronize()
     keys = key_latents(num_ws).to(device)
     drive = ar.gaussian_filter(onsets[:, 0], 2.0)
     drive = ar.normalize(drive, eps=1e-8)
-    tonal = ar.multi_weighted(keys, chroma.to(device))
+    tonal = ar.multi_weighted(keys, chroma + 1e-6)
     K = keys.shape[0]
     pos = torch.linspace(0, 4 * K, T + 1, device=device)[:-1]
     i0 = pos.floor().long() % K

@@ -148,3 +148,143 @@ def peak_indices(env):
     idx = torch.arange(n)
     m = (e > e[(idx + 1).clamp(0, n - 1)]) & (e > e[(idx - 1).clamp(0, n - 1)])
     return idx[m]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# constant-Q chroma.  Restates rosa/constantq.py:13-269, rosa/spectral.py:286-325
+# (chroma_cqt) and rosa/convert.py:69-125 (cq_to_chroma, hz_to_midi).  PINNED bit-for-bit against the reference's own
+# functions by tests/golden/make_audio_golden.py (tuning passed explicitly: the reference's tuning=None default runs
+# rosa/pitch.py:estimate_tuning first, which is not on the restated path).
+# ---------------------------------------------------------------------------------------------------------
+C1_HZ = 32.70319566257483  # librosa.note_to_hz("C1"), the reference's fmin default (convert.py:129-130)
+
+
+def cqt_frequencies(n_bins, fmin, bins_per_octave=12):
+    """constantq.py:205-208."""
+    return fmin * 2.0 ** (torch.arange(0, n_bins, dtype=torch.float) / bins_per_octave)
+
+
+def constant_q_lengths(sr, fmin, n_bins=84, bins_per_octave=12, filter_scale=1, gamma=0):
+    """constantq.py:211-216."""
+    alpha = 2.0 ** (1.0 / bins_per_octave) - 1.0
+    q = float(filter_scale) / alpha
+    freq = fmin * (2.0 ** (torch.arange(n_bins, dtype=torch.float) / bins_per_octave))
+    return q * sr / (freq + gamma / alpha)
+
+
+def constant_q(sr, fmin, n_bins, bins_per_octave, filter_scale=1, gamma=0):
+    """constantq.py:219-262 with pad_fft=True: hann-windowed complex exponentials, L1-normalised, centre-padded to
+    the next power of two of the longest filter."""
+    lengths = constant_q_lengths(sr, fmin, n_bins=n_bins, bins_per_octave=bins_per_octave, filter_scale=filter_scale, gamma=gamma)
+    freqs = fmin * (2.0 ** (torch.arange(n_bins, dtype=torch.float) / bins_per_octave))
+    filters = []
+    for ilen, freq in zip(lengths, freqs):
+        ilen2 = torch.div(ilen, 2, rounding_mode="floor")
+        sig = torch.exp(torch.arange(-ilen2, ilen2, dtype=torch.float) * 1j * 2 * torch.pi * freq / sr)
+        sig = sig * torch.hann_window(len(sig))
+        sig = sig / sig.norm(p=1, dim=0)
+        filters.append(sig)
+    max_len = int(2.0 ** (torch.ceil(torch.log2(max(lengths)))))
+    out = []
+    for f in filters:
+        lpad = int((max_len - f.shape[-1]) // 2)
+        out.append(F.pad(f, (lpad, int(max_len - f.shape[-1] - lpad)), mode="constant"))
+    return torch.stack(out), lengths
+
+
+def sparsify_rows_dense(x, quantile=0.01):
+    """constantq.py:146-163, returned as a DENSE matrix with the dropped entries zeroed (the reference builds a
+    sparse COO tensor of the kept entries; `sparse.mm(D)` sums exactly those products)."""
+    mags = torch.abs(x)
+    norms = torch.sum(mags, axis=1, keepdims=True)
+    mag_sort = torch.sort(mags, axis=1).values
+    cumulative_mag = torch.cumsum(mag_sort / norms, axis=1)
+    threshold_idx = torch.argmin((cumulative_mag < quantile).to(torch.uint8), axis=1)
+    keep = mags >= mag_sort[torch.arange(x.shape[0]), threshold_idx][:, None]
+    return torch.where(keep, x, torch.zeros_like(x)), keep
+
+
+def cqt_filter_fft(sr, fmin, n_bins, bins_per_octave, filter_scale=1, sparsity=0.01, gamma=0.0):
+    """constantq.py:119-143 -> (dense-with-zeros one-sided FFT basis [n_bins, n_fft/2+1], keep mask, n_fft)."""
+    basis, lengths = constant_q(sr, fmin, n_bins, bins_per_octave, filter_scale, gamma)
+    n_fft = basis.shape[1]
+    basis = basis * (lengths[:, None] / float(n_fft))
+    fft_basis = torch.fft.fft(basis, n=n_fft, axis=1)[:, : (n_fft // 2) + 1]
+    dense, keep = sparsify_rows_dense(fft_basis, quantile=sparsity)
+    return dense, keep, n_fft
+
+
+def cqt(y, sr, hop_length=1024, fmin=None, n_bins=84, bins_per_octave=12, tuning=0.0, filter_scale=1, sparsity=0.01):
+    """constantq.py:13-116 with gamma=0 (cqt = vqt special case): recursive octave-by-octave transform."""
+    import numpy as np
+    from torchaudio.functional import resample
+
+    n_octaves = int(np.ceil(float(n_bins) / bins_per_octave))
+    n_filters = min(bins_per_octave, n_bins)
+    fmin = torch.tensor(C1_HZ).float() if fmin is None else torch.as_tensor(fmin).float()
+    fmin = fmin * 2.0 ** (tuning / bins_per_octave)
+    freqs = cqt_frequencies(n_bins, fmin, bins_per_octave=bins_per_octave)[-bins_per_octave:]
+    fmin_t = torch.min(freqs)
+    my_y, my_sr, my_hop = y, sr, hop_length
+    resp = []
+    for i in range(n_octaves):
+        if i > 0:
+            my_y = resample(my_y, my_sr, my_sr / 2, resampling_method="sinc_interp_kaiser")
+            my_y = my_y * np.sqrt(2)
+            my_sr /= 2.0
+            my_hop //= 2
+        dense, keep, n_fft = cqt_filter_fft(my_sr, fmin_t * 2.0**-i, n_filters, bins_per_octave, filter_scale, sparsity, gamma=0)
+        dense = dense * np.sqrt(2**i)
+        d = torch.stft(my_y, n_fft=n_fft, hop_length=my_hop, center=True, window=None, pad_mode="reflect", return_complex=True)[:, :-1]
+        # the reference multiplies a sparse COO matrix: the same sparse op keeps the restatement bit-comparable
+        resp.append(_sparse_mm_like_reference(dense, keep, d))
+    max_col = min(c.shape[-1] for c in resp)
+    out = torch.empty((n_bins, max_col), dtype=resp[0].dtype)
+    end = n_bins
+    for c in resp:
+        n_oct = c.shape[0]
+        if end < n_oct:
+            out[:end] = c[-end:, :max_col]
+        else:
+            out[end - n_oct: end] = c[:, :max_col]
+        end -= n_oct
+    lengths = constant_q_lengths(sr, fmin, n_bins=n_bins, bins_per_octave=bins_per_octave, filter_scale=filter_scale, gamma=0)
+    return out / torch.sqrt(lengths[:, None])
+
+
+def _sparse_mm_like_reference(dense, keep, d):
+    """fft_basis.mm(D) for the reference's sparse COO basis (constantq.py:160-163, 188)."""
+    idx = keep.nonzero().permute(1, 0)
+    sp = torch.sparse_coo_tensor(idx, dense[keep], size=dense.shape, dtype=dense.dtype)
+    return sp.mm(d)
+
+
+def hz_to_midi(f):
+    import numpy as np
+    return 12 * (np.log2(f) - np.log2(440.0)) + 69
+
+
+def cq_to_chroma(n_input, bins_per_octave=12, n_chroma=12, fmin=None):
+    """convert.py:69-117 (base_c=True, window=None)."""
+    import numpy as np
+    n_merge = float(bins_per_octave) / n_chroma
+    fmin = torch.tensor(C1_HZ).float() if fmin is None else fmin
+    m = torch.repeat_interleave(torch.eye(n_chroma), round(n_merge), dim=1)
+    m = torch.roll(m, -int(n_merge // 2), dims=1)
+    n_octaves = np.ceil(float(n_input) / bins_per_octave)
+    m = torch.tile(m, (1, int(n_octaves)))[:, :n_input]
+    midi_0 = hz_to_midi(fmin) % 12
+    roll = int(torch.round(midi_0 * (n_chroma / 12.0)))
+    return torch.roll(m, roll, dims=0).to(torch.float)
+
+
+def chroma_cqt(y, sr, hop_length=1024, fmin=None, threshold=0.0, tuning=0.0, n_chroma=12, n_octaves=7, bins_per_octave=36, norm=True):
+    """spectral.py:286-325 -> [12, T]."""
+    c = torch.abs(cqt(y, sr=sr, hop_length=hop_length, fmin=fmin, n_bins=n_octaves * bins_per_octave,
+                      bins_per_octave=bins_per_octave, tuning=tuning))
+    chroma = cq_to_chroma(c.shape[0], bins_per_octave=bins_per_octave, n_chroma=n_chroma, fmin=fmin) @ c
+    if threshold is not None:
+        chroma[chroma < threshold] = 0.0
+    if norm:
+        chroma = chroma / chroma.max()
+    return chroma

@@ -56,6 +56,7 @@ sys.modules[eq.__name__] = eq
 ref_audio = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.audio")
 ref_spec = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.spectral")
 ref_beat = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.beat")
+ref_cq = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.constantq")
 ref_signal = importlib.import_module("maua.audiovisual.audioreactive.signal")
 ref_latent = importlib.import_module("maua.audiovisual.audioreactive.latent")
 
@@ -92,6 +93,17 @@ with torch.inference_mode():
     rms_ref = ref_audio.rms(y, sr)
     same(OA.rms(y), rms_ref, "rms")
 
+    import warnings
+    warnings.filterwarnings("ignore")  # torchaudio's deprecation notice for the "kaiser_window" method name
+    harm_ref = ref_audio.harmonic(y)
+    same(OA.harmonic(y), harm_ref, "harmonic")
+    cq_ref = ref_cq.cqt(y.clone(), sr, n_bins=252, bins_per_octave=36, tuning=0.0)
+    same(OA.cqt(y.clone(), sr, n_bins=252, bins_per_octave=36, tuning=0.0), cq_ref, "cqt")
+    chroma_ref = ref_spec.chroma_cqt(y.clone(), sr, tuning=0.0)
+    same(OA.chroma_cqt(y.clone(), sr, tuning=0.0), chroma_ref, "chroma_cqt")
+    chroma_h_ref = ref_spec.chroma_cqt(harm_ref.clone(), sr, tuning=0.0)
+    same(OA.chroma_cqt(OA.harmonic(y), sr, tuning=0.0), chroma_h_ref, "chroma_cqt(harmonic)")
+
     env = on_ref[:, 0].clone()
     same(OS.normalize(env), ref_signal.normalize(env), "signal.normalize")
     same(OS.resample(env, 57), ref_signal.resample(env, 57), "signal.resample")
@@ -113,6 +125,7 @@ with torch.inference_mode():
                onsets=on_ref[:, 0], rms=rms_ref[:, 0], peaks=peaks, peak_margins=margins,
                gauss2=ref_signal.gaussian_filter(env, 2.0), pclip90=ref_signal.percentile_clip(env.clone(), 90)[:, 0],
                resample57=ref_signal.resample(env, 57), lat=lat[:, :2, :4].clone(), lat_gauss=ref_signal.gaussian_filter(lat, 3.0, causal=0.3)[:, :2, :4].clone(),
+               harmonic=harm_ref.half(), cqt_abs=cq_ref.abs(), chroma_cqt=chroma_ref, chroma_cqt_harmonic=chroma_h_ref,
                keys=keys, chroma=chroma, multi_weighted=mw_ref, slerp_loops=ref_latent.slerp_loops(keys, 60, 2))
 torch.save(out, os.path.join(ROOT, "tests", "golden", "audio.pt"))
 print("oracle == reference on every pinned function; wrote tests/golden/audio.pt",

@@ -81,3 +81,54 @@ def test_signal_and_latent_ops_against_reference_vectors(cuda):
     assert float((ar.single_weighted(lat[0].to(cuda), lat[1].to(cuda), e.to(cuda)).cpu() - OS.single_weighted(lat[0], lat[1], e)).abs().max()) < 1e-6
     assert float((ar.normalize(lat.to(cuda)).cpu() - OS.normalize(lat)).abs().max()) < 1e-6
     assert float((ar.compress(e.to(cuda), 0.5, 0.5).cpu() - OS.compress(e, 0.5, 0.5)).abs().max()) < 1e-6
+
+
+def test_constant_q_chroma_against_reference_golden_vectors(cuda):
+    """chroma_cqt / |cqt| / harmonic on the device vs vectors produced by the reference's own functions."""
+    from maua_b200.audiovisual import audioreactive as ar
+
+    y, sr = G["audio_exact"].to(cuda), G["sr"]
+    cq = ar.cqt_magnitude(y, sr, n_bins=252, bins_per_octave=36, tuning=0.0).cpu()
+    assert cq.shape == G["cqt_abs"].shape
+    assert float((cq - G["cqt_abs"]).abs().max()) < 2e-5 * float(G["cqt_abs"].max())     # fp32 FFT / summation order
+    ch = ar.chroma_cqt(y, sr, tuning=0.0).cpu()
+    assert ch.shape == (12, len(G["onsets"]))
+    assert float((ch - G["chroma_cqt"]).abs().max()) < 5e-5 and abs(float(ch.max()) - 1.0) < 1e-6
+    harm = ar.harmonic(y)
+    ref_h = OA.harmonic(G["audio_exact"])
+    assert float((harm.cpu() - ref_h).abs().max()) < 1e-4 * float(ref_h.abs().max()) + 1e-6
+    chh = ar.chroma_cqt(harm, sr, tuning=0.0).cpu()     # the chromagram() front half: chroma of the harmonic signal
+    assert float((chh - G["chroma_cqt_harmonic"]).abs().max()) < 2e-4
+
+
+@pytest.mark.parametrize("fps,dur", [(24, 30.0), (60, 6.0)])
+def test_config_sized_chroma_matches_oracle(cuda, fps, dur):
+    """BASELINE.json configs[1] audio length (n_fft 1024 per octave) and a 60 fps rate (n_fft 2048 per octave)."""
+    import warnings
+
+    from maua_b200.audiovisual import audioreactive as ar
+    from maua_b200.workload import sine_sweep
+
+    warnings.filterwarnings("ignore")
+    sr = 1024 * fps
+    y48, _ = sine_sweep(dur, tremolo_hz=4.0)
+    t = np.arange(int(dur * sr)) / sr
+    y = torch.from_numpy(np.interp(t, np.arange(len(y48)) / 48000.0, y48).astype(np.float32))
+    y = y + 0.01 * torch.randn(len(y), generator=torch.Generator().manual_seed(3))
+    ref = OA.chroma_cqt(y.clone(), sr, tuning=0.0)
+    got = ar.chroma_cqt(y.to(cuda), sr, tuning=0.0).cpu()
+    assert got.shape == ref.shape == (12, int(dur * fps))
+    assert float((got - ref).abs().max()) < 1e-4
+
+
+def test_chroma_errors(cuda):
+    from maua_b200.audiovisual import audioreactive as ar
+
+    with pytest.raises(RuntimeError):
+        ar.chroma_cqt(torch.zeros(1024 * 64), 24576)            # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        ar.chroma_cqt(torch.zeros(1000, device=cuda), 24576)
+    with pytest.raises(NotImplementedError):
+        ar.chroma_cqt(torch.zeros(1024 * 64, device=cuda), 24576, tuning=None)
+    with pytest.raises(RuntimeError):
+        ar.chroma_cqt(torch.zeros(1024 * 64, device=cuda), 24576, hop_length=32)   # hop not a multiple of 2^6

@@ -41,3 +41,33 @@ def test_mel_filterbank_of_the_host_facade_matches_oracle():
 
     for sr in (24576, 61440):
         assert torch.allclose(mel_filterbank(sr, fmax=11025.0), OA.mel_filterbank(sr, fmax=11025.0), atol=1e-6)
+
+
+def test_constant_q_chroma_matches_reference_vectors():
+    """oracle chroma_cqt / cqt / harmonic vs the vectors the REFERENCE's own functions produced (make_audio_golden.py)."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    y, sr = G["audio_exact"], G["sr"]
+    assert torch.equal(OA.chroma_cqt(y.clone(), sr, tuning=0.0), G["chroma_cqt"])
+    assert torch.equal(OA.cqt(y.clone(), sr, n_bins=252, bins_per_octave=36, tuning=0.0).abs(), G["cqt_abs"])
+    assert torch.equal(OA.chroma_cqt(OA.harmonic(y), sr, tuning=0.0), G["chroma_cqt_harmonic"])
+
+
+def test_chroma_design_of_the_host_facade_matches_oracle_and_torchaudio():
+    """The product's host-side constant design (decimation taps, sparse filter bank, fold matrix) is the reference's."""
+    from torchaudio.functional import functional as TF
+
+    from maua_b200.audiovisual.audioreactive import chroma as CH
+
+    k, w = CH.kaiser_decimation_kernel()
+    rk, rw = TF._get_sinc_resample_kernel(2, 1, 1, 6, 0.99, "sinc_interp_kaiser", None)
+    assert w == rw and torch.equal(k, rk.reshape(-1))
+    for sr in (24 * 1024, 60 * 1024):
+        f0 = torch.tensor(CH.C1_HZ).float()
+        top = (f0 * 2.0 ** (torch.arange(0, 252, dtype=torch.float) / 36))[-36:]
+        rowptr, col, val, n_fft = CH.octave_filter_bank(sr, torch.min(top), 36)
+        dense, keep, nf = OA.cqt_filter_fft(sr, torch.min(top), 36, 36)
+        assert n_fft == nf and int(rowptr[-1]) == int(keep.sum()) and torch.equal(val, dense[keep])
+        assert torch.equal(col.long(), keep.nonzero()[:, 1])
+    assert torch.equal(CH.cq_to_chroma(252, 36, 12), OA.cq_to_chroma(252, 36, 12))

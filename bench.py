@@ -27,6 +27,27 @@ METRIC = "frames/sec StyleGAN3 1024^2 audio-reactive render"
 WORKLOAD = "StyleGAN3-T 1024^2 random-init, 30 s @ 24 fps (720 frames) audio-reactive latents, 48 kHz sine sweep"
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The driver reads ONE JSON line from stdout: route everything libraries print there (the NCCL version banner
+    of a multi-rank run, warnings) to stderr and keep the real stdout for emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -147,7 +168,7 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -312,7 +333,7 @@ def run_ours(args):
         "kernel_ms_per_step": {names[k]: round(v, 4) for k, v in sorted(per_kind.items())},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -330,6 +351,7 @@ def main():
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
+        guard_stdout()
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world == 1:
@@ -337,6 +359,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+    guard_stdout()
     return run_ours(args)
 
 

@@ -226,6 +226,24 @@ int mb_multi_weighted(const float* latents /*[K,D]*/, const float* envelopes /*[
 int mb_single_weighted(const float* low /*[D]*/, const float* high /*[D]*/, const float* envelope /*[T]*/, float* out /*[T,D]*/,
                        int T, int D, mb_stream stream);
 
+/* latent.py: slerp_loops :68-80 = mb_slerp_rows (the [steps * K*n_loops, L, D] table of spherical interpolants between
+ * consecutive looped keys, row = step * nseg + segment as the reference's reshape orders them) followed by
+ * mb_resample_linear to `size`; spline_loops :83-92 = natural cubic spline through cat([keys] * n_loops + [keys[0]]) at
+ * uniform knots, evaluated at linspace(0, 1, size) (workspace: device float32 [(K*n_loops+1) * C]); select_modulo :34-45
+ * up to its final gaussian_filter (sorted_envelope = ascending sort of envelope). keys [K, C] row-major. */
+int mb_slerp_rows(const float* keys, int K, int L, int D, int n_loops, int steps, float* rows, mb_stream stream);
+int mb_spline_loops(const float* keys, int K, int C, int n_loops, int size, float* out, float* workspace, mb_stream stream);
+int mb_select_modulo(const float* envelope, const float* sorted_envelope, int T, const float* keys, int K, int C,
+                     float* out, mb_stream stream);
+
+/* selfsupervised/noise.py: Blend :11-25 (two_sided = 1, noise [2, M, P]) / Multiply :28-40 (two_sided = 0, noise [M, P]) with
+ * modulator rows [B, M] -> out [B, P], P = H * W; Loop :43-54 (idx [B] = phases of the batch, noise [3, P]); the
+ * Average / Modulate / ScaleBias combinators :57-86 as out = a x mx[b] + c y (my[b] | 1 - my[b]) + bias (y, mx, my may be NULL). */
+int mb_noise_mix(const float* noise, const float* modulator, int B, int M, int P, int two_sided, float* out, mb_stream stream);
+int mb_noise_loop(const float* idx, const float* noise, int B, int P, float sigma, float* out, mb_stream stream);
+int mb_noise_combine(const float* x, const float* y, const float* mx, const float* my, int one_minus, float a, float c,
+                     float bias, int B, int P, float* out, mb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

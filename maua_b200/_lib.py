@@ -71,6 +71,12 @@ _SIGNATURES = {
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mb_multi_weighted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mb_single_weighted": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
+    "mb_slerp_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "mb_spline_loops": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "mb_select_modulo": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "mb_noise_mix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "mb_noise_loop": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
+    "mb_noise_combine": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P]),
     "mb_debug_read": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "mb_modulated_conv2d": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_int, _P]),

@@ -2,5 +2,6 @@
 maua.audiovisual.audioreactive and its torch-native twin selfsupervised.features.audio)."""
 from .chroma import chroma_cqt, cqt_magnitude  # noqa: F401
 from .features import harmonic, mel_filterbank, onset_peaks, onsets, onsets_rms, percussive, rms  # noqa: F401
-from .latent import multi_weighted, single_weighted  # noqa: F401,E402
+from .latent import multi_weighted, select_modulo, single_weighted, slerp_loops, spline_loops, tempo_loops  # noqa: F401,E402
+from . import noise  # noqa: F401,E402
 from .signal import compress, expand, gaussian_filter, normalize, percentile, percentile_clip, resample  # noqa: F401,E402

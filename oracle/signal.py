@@ -113,3 +113,46 @@ def slerp_loops(y, size, n_loops):
     out = slerp(y[:-1], y[1:], t)
     out = out.reshape(-1, *out.shape[2:])
     return F.interpolate(out.permute(1, 2, 0), size=size, mode="linear", align_corners=False).permute(2, 0, 1)
+
+
+def select_modulo(latents, envelope, smooth=2):
+    """latent.py:34-45: quartile clamp -> normalise -> round to a key index -> gather -> causal=0 Gaussian."""
+    low, high = torch.quantile(envelope, 0.25), torch.quantile(envelope, 0.75)
+    indices = normalize(envelope.clamp(low, high))
+    indices = (indices * (len(latents) - 1)).round().long()
+    return gaussian_filter(latents[indices], smooth, causal=0)
+
+
+def spline_loops(y, size, n_loops):
+    """latent.py:83-92.  The reference evaluates torchcubicspline.NaturalCubicSpline (third-party, un-pinned in
+    setup.py:104, absent from the checkout): the published algorithm -- the C2 piecewise cubic through the knots with
+    zero second derivative at both ends -- is restated here in float64 and checked against scipy's
+    CubicSpline(bc_type="natural") in tests/test_oracle_audio.py.  PARITY UNPINNED against the reference's own call."""
+    import numpy as np
+
+    y = torch.cat([y] * n_loops + [y[[0]]])
+    m = len(y)
+    yy = y.reshape(m, -1).double().numpy()
+    h = 1.0 / (m - 1)
+    z = np.zeros_like(yy)
+    if m > 2:
+        a = np.zeros((m - 2, m - 2))
+        np.fill_diagonal(a, 4.0)
+        idx = np.arange(m - 3)
+        a[idx, idx + 1] = 1.0
+        a[idx + 1, idx] = 1.0
+        rhs = 6.0 / h ** 2 * (yy[:-2] - 2 * yy[1:-1] + yy[2:])
+        z[1:-1] = np.linalg.solve(a, rhs)
+    t = np.linspace(0.0, 1.0, size)
+    u = t * (m - 1)
+    i = np.minimum(np.floor(u).astype(np.int64), m - 2)
+    f = (u - i)[:, None]
+    g = 1.0 - f
+    out = g * yy[i] + f * yy[i + 1] + h * h / 6.0 * ((g ** 3 - g) * z[i] + (f ** 3 - f) * z[i + 1])
+    return torch.from_numpy(out).to(y.dtype).reshape(size, *y.shape[1:])
+
+
+def tempo_loops(latents, n_frames, fps, tempo, type="spline"):
+    """latent.py:95-102."""
+    n_loops = round(n_frames / fps * (tempo / 4 / 60))
+    return spline_loops(latents, n_frames, n_loops) if type == "spline" else slerp_loops(latents, n_frames, n_loops)

@@ -59,9 +59,10 @@ ref_beat = importlib.import_module("maua.audiovisual.audioreactive.selfsupervise
 ref_cq = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.constantq")
 ref_signal = importlib.import_module("maua.audiovisual.audioreactive.signal")
 ref_latent = importlib.import_module("maua.audiovisual.audioreactive.latent")
+ref_noise = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.noise")
 
 from maua_b200.workload import sine_sweep  # noqa: E402
-from oracle import audio as OA, signal as OS  # noqa: E402
+from oracle import audio as OA, noise as ON, signal as OS  # noqa: E402
 
 torch.manual_seed(0)
 fps, dur = 24, 4.0
@@ -119,6 +120,23 @@ with torch.inference_mode():
     assert torch.allclose(OS.multi_weighted(keys, chroma.clone()), mw_ref, atol=1e-6), "multi_weighted"
     same(OS.slerp_loops(keys, 60, 2), ref_latent.slerp_loops(keys, 60, 2), "slerp_loops")
 
+    sel_ref = ref_latent.select_modulo(keys, env.clone(), smooth=2)
+    same(OS.select_modulo(keys, env.clone(), smooth=2), sel_ref, "select_modulo")
+
+    # noise sequencers: the reference's own classes on a seeded CPU generator
+    rng = torch.Generator().manual_seed(7)
+    mod = torch.rand(len(env), 3, generator=rng)
+    nb = ref_noise.Blend(rng, len(env), (16, 24), mod)
+    nm = ref_noise.Multiply(rng, len(env), (16, 24), mod)
+    nl = ref_noise.Loop(rng, len(env), (16, 24), n_loops=2, sigma=5)
+    i0, bsz = 5, 7
+    same(ON.blend(nb.noise, mod, i0, bsz), nb(i0, bsz), "noise Blend")
+    same(ON.multiply(nm.noise, mod, i0, bsz), nm(i0, bsz), "noise Multiply")
+    same(ON.loop(nl.noise, nl.idx, nl.sigma, i0, bsz), nl(i0, bsz), "noise Loop")
+    comb = ref_noise.ScaleBias(ref_noise.Modulate(ref_noise.Average(nb, nl), nm, mod), 0.7, 0.1)
+    comb_ref = comb(i0, bsz)
+    same(ON.scale_bias(ON.modulate(ON.average(nb(i0, bsz), nl(i0, bsz)), nm(i0, bsz), mod.mean(1), i0, bsz), 0.7, 0.1), comb_ref, "noise combinators")
+
     peaks = OA.peak_indices(on_ref)
     margins = torch.minimum(on_ref[peaks, 0] - on_ref[(peaks - 1).clamp(0), 0], on_ref[peaks, 0] - on_ref[(peaks + 1).clamp(max=len(on_ref) - 1), 0])
     out = dict(sr=sr, fps=fps, audio=y.half(), audio_exact=y, stft_abs=d.abs()[:, ::16].half(), perc_abs=pr.abs()[:, ::16].half(),
@@ -126,6 +144,9 @@ with torch.inference_mode():
                gauss2=ref_signal.gaussian_filter(env, 2.0), pclip90=ref_signal.percentile_clip(env.clone(), 90)[:, 0],
                resample57=ref_signal.resample(env, 57), lat=lat[:, :2, :4].clone(), lat_gauss=ref_signal.gaussian_filter(lat, 3.0, causal=0.3)[:, :2, :4].clone(),
                harmonic=harm_ref.half(), cqt_abs=cq_ref.abs(), chroma_cqt=chroma_ref, chroma_cqt_harmonic=chroma_h_ref,
+               select_modulo=sel_ref, env=env.clone(),
+               noise=dict(mod=mod, blend_noise=nb.noise.clone(), mult_noise=nm.noise.clone(), loop_noise=nl.noise.clone(), loop_idx=nl.idx.clone(),
+                          i=i0, b=bsz, blend=nb(i0, bsz), multiply=nm(i0, bsz), loop=nl(i0, bsz), combined=comb_ref),
                keys=keys, chroma=chroma, multi_weighted=mw_ref, slerp_loops=ref_latent.slerp_loops(keys, 60, 2))
 torch.save(out, os.path.join(ROOT, "tests", "golden", "audio.pt"))
 print("oracle == reference on every pinned function; wrote tests/golden/audio.pt",

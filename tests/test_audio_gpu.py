@@ -132,3 +132,40 @@ def test_chroma_errors(cuda):
         ar.chroma_cqt(torch.zeros(1024 * 64, device=cuda), 24576, tuning=None)
     with pytest.raises(RuntimeError):
         ar.chroma_cqt(torch.zeros(1024 * 64, device=cuda), 24576, hop_length=32)   # hop not a multiple of 2^6
+
+
+def test_latent_sequencers_on_device(cuda):
+    """slerp_loops / select_modulo vs vectors of the reference's own functions, spline_loops / tempo_loops vs the oracle."""
+    from maua_b200.audiovisual import audioreactive as ar
+    from oracle import signal as OS
+
+    keys = G["keys"].to(cuda)
+    sl = ar.slerp_loops(keys, 60, 2).cpu()
+    assert sl.shape == G["slerp_loops"].shape and float((sl - G["slerp_loops"]).abs().max()) < 2e-5
+    sm = ar.select_modulo(keys, G["env"].to(cuda), smooth=2).cpu()
+    assert sm.shape == G["select_modulo"].shape and float((sm - G["select_modulo"]).abs().max()) < 1e-5
+    torch.manual_seed(5)
+    big = torch.randn(12, 16, 512)
+    sp = ar.spline_loops(big.to(cuda), 720, 4).cpu()
+    ref = OS.spline_loops(big, 720, 4)
+    assert sp.shape == (720, 16, 512) and float((sp - ref).abs().max()) < 2e-4 * float(ref.abs().max())
+    tl = ar.tempo_loops(big.to(cuda), 720, 24, 120.0, type="slerp").cpu()
+    assert float((tl - OS.tempo_loops(big, 720, 24, 120.0, type="slerp")).abs().max()) < 5e-5
+
+
+def test_noise_sequencers_on_device(cuda):
+    """Blend / Multiply / Loop and the combinators vs vectors produced by the reference's own classes."""
+    from maua_b200.audiovisual.audioreactive import noise as NS
+
+    n = G["noise"]
+    mod, i, b = n["mod"].to(cuda), n["i"], n["b"]
+    rng = torch.Generator().manual_seed(0)
+    nb = NS.Blend(rng, len(mod), (16, 24), mod, noise=n["blend_noise"])
+    nm = NS.Multiply(rng, len(mod), (16, 24), mod, noise=n["mult_noise"])
+    nl = NS.Loop(rng, len(mod), (16, 24), n_loops=2, sigma=5, noise=n["loop_noise"], device=cuda)
+    assert float((nb(i, b).cpu() - n["blend"]).abs().max()) < 1e-5
+    assert float((nm(i, b).cpu() - n["multiply"]).abs().max()) < 1e-5
+    assert float((nl(i, b).cpu() - n["loop"]).abs().max()) < 2e-4      # sin(cos(.) * 10): fast-math free, fp32 argument rounding
+    comb = NS.ScaleBias(NS.Modulate(NS.Average(nb, nl), nm, mod), 0.7, 0.1)
+    out = comb(i, b)
+    assert out.shape == (b, 16, 24) and float((out.cpu() - n["combined"]).abs().max()) < 2e-4

@@ -71,3 +71,24 @@ def test_chroma_design_of_the_host_facade_matches_oracle_and_torchaudio():
         assert n_fft == nf and int(rowptr[-1]) == int(keep.sum()) and torch.equal(val, dense[keep])
         assert torch.equal(col.long(), keep.nonzero()[:, 1])
     assert torch.equal(CH.cq_to_chroma(252, 36, 12), OA.cq_to_chroma(252, 36, 12))
+
+
+def test_sequencers_match_reference_vectors_and_scipy():
+    """select_modulo / noise sequencers vs vectors of the reference's own code; the natural spline (third-party in the
+    reference, absent here) vs scipy's CubicSpline(bc_type="natural")."""
+    import numpy as np
+    from scipy.interpolate import CubicSpline
+
+    from oracle import noise as ON
+
+    assert torch.equal(OS.select_modulo(G["keys"], G["env"].clone(), smooth=2), G["select_modulo"])
+    n = G["noise"]
+    assert torch.equal(ON.blend(n["blend_noise"], n["mod"], n["i"], n["b"]), n["blend"])
+    assert torch.equal(ON.multiply(n["mult_noise"], n["mod"], n["i"], n["b"]), n["multiply"])
+    assert torch.equal(ON.loop(n["loop_noise"], n["loop_idx"], 5, n["i"], n["b"]), n["loop"])
+    keys, size, n_loops = G["keys"], 97, 3
+    got = OS.spline_loops(keys, size, n_loops)
+    y = torch.cat([keys] * n_loops + [keys[[0]]]).reshape(len(keys) * n_loops + 1, -1).double().numpy()
+    ref = CubicSpline(np.linspace(0, 1, len(y)), y, bc_type="natural")(np.linspace(0, 1, size))
+    assert got.shape == (size, 4, 8)
+    assert float(np.abs(got.reshape(size, -1).numpy() - ref).max()) < 1e-5

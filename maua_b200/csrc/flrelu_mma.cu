@@ -97,6 +97,8 @@ struct MmaParams {
     float clamp_pre;  // clamp / gain: the clamp acts before the gain, which is folded into out_gain
     float out_gain;   // gain * (DC correction of the fp16-rounded down filter)^2
     int rho;          // phase of the first intermediate sample of a tile: pad mod UP
+    int nt;           // radial down filter: number of separable terms (0 = separable filter, fragments in registers)
+    const uint4* rfrags;  // [nt][6][32] fragments of the terms (down-H k-steps 0..2, down-V k-steps 0..2)
 };
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -117,13 +119,25 @@ struct NoHook {
 };
 // `x_dead` is invoked right after the last read of X (the last stage-1 block): a single-buffered caller
 // issues the prefetch of its next input tile there.
-template <int UP, class Hook = NoHook>
+// Radial (non-separable) down filters of StyleGAN3-R: the 12x12 jinc*kaiser filter is symmetric and numerically of rank
+// 2..4 (eigenvalues fall off by 1e-2 per term), so it runs as `nt` separable terms F = sum_k g_k h_k^T whose fragments
+// (per term: three down-H and three down-V k-steps) sit in shared memory (`sAD`, [nt][6][32] uint4) and accumulate
+// into the same output registers.  nt == 0 selects the separable filter held in registers (AD).
+template <int UP, bool RAD = false, class Hook = NoHook>
 __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR], const uint4 (&AD)[3],
                                           uint32_t sl2, uint32_t cl2, int g, int tig,
-                                          float (&OUT)[2][4][4], Hook x_dead = Hook()) {
+                                          float (&OUT)[2][4][4], Hook x_dead = Hook(), const uint4* sAD = nullptr, int nt = 0) {
     using K = MC<UP>;
     uint32_t P1[2][kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers (slot = block & 1)
     int have0 = -1, have1 = -1;  // compile-time constants after unrolling
+    if constexpr (RAD) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int no = 0; no < 4; ++no)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) OUT[i][no][q] = 0.0f;
+    }
 
     auto stage1 = [&](int blk) {
 #pragma unroll
@@ -162,29 +176,60 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
             P2[nb][0] = lrelu_clamp2(pack2(acc[0], acc[1]), sl2, cl2);
             P2[nb][1] = lrelu_clamp2(pack2(acc[2], acc[3]), sl2, cl2);
         }
-        // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
-        uint32_t P3[4][2];
+        if constexpr (!RAD) {
+            // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
+            uint32_t P3[4][2];
 #pragma unroll
-        for (int mo = 0; mo < 2; ++mo) {
+            for (int mo = 0; mo < 2; ++mo) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float acc[4];
-                mma16816_z(acc, AD[0], P2[4 * mo][h], P2[4 * mo + 1][h]);
-                mma16816(acc, AD[1], P2[4 * mo + 2][h], P2[4 * mo + 3][h]);
-                mma16816(acc, AD[2], P2[4 * mo + 4][h], P2[4 * mo + 5][h]);
-                P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
-                P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+                for (int h = 0; h < 2; ++h) {
+                    float acc[4];
+                    mma16816_z(acc, AD[0], P2[4 * mo][h], P2[4 * mo + 1][h]);
+                    mma16816(acc, AD[1], P2[4 * mo + 2][h], P2[4 * mo + 3][h]);
+                    mma16816(acc, AD[2], P2[4 * mo + 4][h], P2[4 * mo + 5][h]);
+                    P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
+                    P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+                }
             }
-        }
-        // ---- S4: strip j is k-step s = j - 2i of output row block i
+            // ---- S4: strip j is k-step s = j - 2i of output row block i
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int s = j - 2 * i;
-            if (s >= 0 && s < 3) {
+            for (int i = 0; i < 2; ++i) {
+                const int s = j - 2 * i;
+                if (s >= 0 && s < 3) {
 #pragma unroll
-                for (int no = 0; no < 4; ++no) {
-                    if (s == 0) mma16816_z(OUT[i][no], AD[0], P3[no][0], P3[no][1]);
-                    else mma16816(OUT[i][no], AD[s], P3[no][0], P3[no][1]);
+                    for (int no = 0; no < 4; ++no) {
+                        if (s == 0) mma16816_z(OUT[i][no], AD[0], P3[no][0], P3[no][1]);
+                        else mma16816(OUT[i][no], AD[s], P3[no][0], P3[no][1]);
+                    }
+                }
+            }
+        } else {
+            const int lane = g * 4 + tig;
+#pragma unroll 1
+            for (int k = 0; k < nt; ++k) {
+                const uint4* fr = sAD + (k * 6) * 32 + lane;
+                const uint4 H0 = fr[0], H1 = fr[32], H2 = fr[64];
+                uint32_t P3[4][2];
+#pragma unroll
+                for (int mo = 0; mo < 2; ++mo) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        float acc[4];
+                        mma16816_z(acc, H0, P2[4 * mo][h], P2[4 * mo + 1][h]);
+                        mma16816(acc, H1, P2[4 * mo + 2][h], P2[4 * mo + 3][h]);
+                        mma16816(acc, H2, P2[4 * mo + 4][h], P2[4 * mo + 5][h]);
+                        P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
+                        P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int s = j - 2 * i;
+                    if (s >= 0 && s < 3) {
+                        const uint4 V = fr[(3 + s) * 32];
+#pragma unroll
+                        for (int no = 0; no < 4; ++no) mma16816(OUT[i][no], V, P3[no][0], P3[no][1]);
+                    }
                 }
             }
         }
@@ -235,13 +280,19 @@ __device__ __forceinline__ void load_tile_async(const MmaParams& p, const __half
 
 // One warp = a run of `tpw` consecutive 32x32 output tiles of one (b, c) plane; the input tile of
 // tile t+1 is fetched with cp.async (zero-filled outside the image) while tile t is in the MMA chain.
-template <int UP>
+template <int UP, bool RAD>
 __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaParams p) {
     using K = MC<UP>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
     __half* Xbuf = reinterpret_cast<__half*>(smem_raw + warp * 2 * K::XBYTES);
+    const uint4* sAD = reinterpret_cast<const uint4*>(smem_raw + K::SMEM);
+    if (RAD) {  // radial down filter: term fragments -> shared memory (before any warp leaves)
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + K::SMEM);
+        for (int i = threadIdx.x; i < p.nt * 6 * 32; i += blockDim.x) dst[i] = p.rfrags[i];
+        __syncthreads();
+    }
 
     const int ntiles = p.tiles_x * p.tiles_y;
     const int tile0 = (blockIdx.x * kWarps + warp) * p.tpw;
@@ -306,7 +357,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         const int dx = ix0 & 7;  // even by construction
 
         float OUT[2][4][4];
-        fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT);
+        fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, NoHook(), sAD, p.nt);
 
         // ---- store: * next-layer style, fp16, two adjacent columns per thread
 #pragma unroll
@@ -364,7 +415,7 @@ __device__ __forceinline__ void write_out_tile(const MmaParams& p, const __half*
     }
 }
 
-template <int UP>
+template <int UP, bool RAD>
 __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaParams p) {
     using K = MC<UP>;
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -376,6 +427,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes);
     uint64_t* full = bars;       // [2] all 16 planes of a staging buffer written
     uint64_t* empty = bars + 2;  // [2] all 16 write-out shares of a staging buffer done
+    const uint4* sAD = reinterpret_cast<const uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + 64);
+    if (RAD) {  // radial down filter: term fragments -> shared memory (visible after the __syncthreads below)
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + 64);
+        for (int i = threadIdx.x; i < p.nt * 6 * 32; i += blockDim.x) dst[i] = p.rfrags[i];
+    }
 
     const int ntiles = p.tiles_x * p.tiles_y;
     const int tile0 = blockIdx.x * p.tpw;
@@ -423,10 +479,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
             __syncwarp();
             const int dx = first_in<UP>((pos & 0xffff) * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, [&]() {
+            auto x_dead = [&]() {
                 __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
                 if (i + 1 < n) load_tile(npos);
-            });
+            };
+            fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, x_dead, sAD, p.nt);
             __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii)
@@ -554,10 +611,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
             __syncwarp();
             const int dx = first_in<UP>(cur.tx * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
-            fir_chain<UP>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, [&]() {
+            auto x_dead = [&]() {
                 __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
                 if (i + 1 < n) load_tile(nxt);
-            });
+            };
+            fir_chain<UP, false>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, x_dead);
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
@@ -585,9 +643,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
 
 // ---- host: constant fragments -------------------------------------------------------------------
 struct FragCache {
-    int up = 0, rho = -1, e = -1;
-    float fu[32], fd[12];
+    int up = 0, rho = -1, e = -1, fd_2d = 0;
+    float fu[32], fd[144];
     uint4* dev = nullptr;
+    int nt = 0;             // radial: number of separable terms, fragments at dev + NFRAG * 32
+    double rad_gain = 1.0;  // radial: exact DC gain / DC gain of the fp16 terms
 };
 FragCache g_cache[8];
 int g_cache_n = 0;
@@ -683,22 +743,104 @@ inline double tuned_down_taps(const FlreluArgs& a, float (&fd16)[12]) {
     return exact / rounded;
 }
 
+// ---- radial 12x12 down filters (StyleGAN3-R): symmetric eigen-decomposition into separable terms ----------------
+constexpr int kMaxTerms = 4;
+constexpr double kTermTol = 5e-5;   // terms below this fraction of the leading eigenvalue are dropped
+
+// cyclic Jacobi for a symmetric 12x12 matrix: A = V diag(w) V^T
+inline void jacobi12(double (&A)[12][12], double (&V)[12][12], double (&w)[12]) {
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int i = 0; i < 12; ++i)
+            for (int j = i + 1; j < 12; ++j) off += A[i][j] * A[i][j];
+        if (off < 1e-30) break;
+        for (int p = 0; p < 12; ++p)
+            for (int q = p + 1; q < 12; ++q) {
+                if (fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 12; ++k) {
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 12; ++k) {
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 12; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = c * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    for (int i = 0; i < 12; ++i) w[i] = A[i][i];
+}
+
+struct RadialTerms {
+    int nt = 0;
+    float h[kMaxTerms][12], g[kMaxTerms][12];  // F[ky][kx] ~= sum_k g_k[ky] h_k[kx]
+    bool ok = false;
+};
+
+// F row-major [ky][kx]; ok = symmetric and reproduced by <= kMaxTerms terms to kTermTol
+inline RadialTerms radial_terms(const float* F) {
+    RadialTerms rt;
+    double A[12][12], V[12][12], w[12];
+    double amax = 0.0;
+    for (int i = 0; i < 12; ++i)
+        for (int j = 0; j < 12; ++j) {
+            A[i][j] = 0.5 * (static_cast<double>(F[i * 12 + j]) + F[j * 12 + i]);
+            amax = fmax(amax, fabs(A[i][j]));
+            if (fabs(static_cast<double>(F[i * 12 + j]) - F[j * 12 + i]) > 1e-6 * (fabs(static_cast<double>(F[i * 12 + j])) + 1e-12) + 1e-12) return rt;
+        }
+    jacobi12(A, V, w);
+    int order[12];
+    for (int i = 0; i < 12; ++i) order[i] = i;
+    for (int i = 0; i < 12; ++i)
+        for (int j = i + 1; j < 12; ++j)
+            if (fabs(w[order[j]]) > fabs(w[order[i]])) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
+    const double w0 = fabs(w[order[0]]);
+    if (w0 <= 0.0) return rt;
+    int nt = 0;
+    while (nt < 12 && fabs(w[order[nt]]) > kTermTol * w0) ++nt;
+    if (nt > kMaxTerms) return rt;
+    rt.nt = nt;
+    for (int k = 0; k < nt; ++k) {
+        const double lam = w[order[k]], r = sqrt(fabs(lam));
+        for (int i = 0; i < 12; ++i) {
+            rt.g[k][i] = static_cast<float>(r * V[i][order[k]]);
+            rt.h[k][i] = static_cast<float>((lam < 0 ? -r : r) * V[i][order[k]]);
+        }
+    }
+    rt.ok = true;
+    return rt;
+}
+
 template <int UP>
-int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
+int build_frags(const FlreluArgs& a, int rho, int e, uint4** out, FragCache** cache_out = nullptr) {
     using K = MC<UP>;
     for (int i = 0; i < g_cache_n && i < 8; ++i) {
         FragCache& fc = g_cache[i];
-        if (fc.up == UP && fc.rho == rho && fc.e == e && memcmp(fc.fu, a.fu, sizeof(float) * 6 * UP) == 0 &&
-            memcmp(fc.fd, a.fd, sizeof(float) * 12) == 0) {
+        if (fc.up == UP && fc.rho == rho && fc.e == e && fc.fd_2d == a.fd_2d && memcmp(fc.fu, a.fu, sizeof(float) * 6 * UP) == 0 &&
+            memcmp(fc.fd, a.fd, sizeof(float) * (a.fd_2d ? 144 : 12)) == 0) {
             *out = fc.dev;
+            if (cache_out) *cache_out = &fc;
             return MB_OK;
         }
     }
     std::vector<uint4> host(K::NFRAG * 32);
+    int nt = 0;
+    double rad_gain = 1.0;
     constexpr int UT = 6 * UP;
-    float fu16[32], fd16[12];
+    float fu16[32], fd16[12] = {};
     tuned_up_taps<UP>(a, fu16);
-    tuned_down_taps(a, fd16);
+    if (!a.fd_2d) tuned_down_taps(a, fd16);
     for (int v = 0; v < K::NVAR; ++v) {
         float A[16][16] = {};
         const int off = (UP == 2) ? 0 : 4 * v;
@@ -724,16 +866,54 @@ int build_frags(const FlreluArgs& a, int rho, int e, uint4** out) {
             }
         emit_fragment(A, &host[(K::NVAR + s) * 32]);
     }
+    if (a.fd_2d) {
+        // separable terms of the radial filter: per term three down-H fragments (taps h_k) and three down-V fragments
+        // (taps g_k); the leading term's polyphase branches are DC-tuned like a separable filter, the small terms are
+        // rounded to nearest, and what is left of the total DC error goes into the fp32 output scale.
+        const RadialTerms rt = radial_terms(a.fd);
+        MB_REQUIRE(rt.ok, "filtered_lrelu: 2-D down filter is not a low-rank symmetric (radial) filter");
+        nt = rt.nt;
+        host.resize((K::NFRAG + nt * 6) * 32);
+        double exact = 0.0, rounded = 0.0;
+        for (int i = 0; i < 144; ++i) exact += a.fd[i];
+        for (int k = 0; k < nt; ++k) {
+            float t16[2][12];
+            for (int hv = 0; hv < 2; ++hv) {
+                const float* taps = hv == 0 ? rt.h[k] : rt.g[k];
+                for (int ph = 0; ph < 2; ++ph) {
+                    float t[6], o[6];
+                    for (int m = 0; m < 6; ++m) t[m] = taps[ph + 2 * m];
+                    if (k == 0) tune_branch(t, 6, o);
+                    else for (int m = 0; m < 6; ++m) o[m] = h2f_bits(f2h_bits(t[m]));
+                    for (int m = 0; m < 6; ++m) t16[hv][ph + 2 * m] = o[m];
+                }
+                for (int s = 0; s < 3; ++s) {
+                    float A[16][16] = {};
+                    for (int r = 0; r < 16; ++r)
+                        for (int col = 0; col < 16; ++col) {
+                            const int kk = 16 * s + col - 2 * r;
+                            if (kk >= 0 && kk < 12) A[r][col] = t16[hv][11 - kk];
+                        }
+                    emit_fragment(A, &host[(K::NFRAG + k * 6 + hv * 3 + s) * 32]);
+                }
+            }
+            double sh = 0.0, sg = 0.0;
+            for (int i = 0; i < 12; ++i) { sh += t16[0][i]; sg += t16[1][i]; }
+            rounded += sh * sg;
+        }
+        rad_gain = exact / rounded;
+    }
     FragCache& fc = g_cache[g_cache_n % 8];
     if (fc.dev) cudaFree(fc.dev);
     fc.dev = nullptr;
     MB_CUDA(cudaMalloc(&fc.dev, host.size() * sizeof(uint4)));
     MB_CUDA(cudaMemcpy(fc.dev, host.data(), host.size() * sizeof(uint4), cudaMemcpyHostToDevice));
-    fc.up = UP; fc.rho = rho; fc.e = e;
+    fc.up = UP; fc.rho = rho; fc.e = e; fc.fd_2d = a.fd_2d; fc.nt = nt; fc.rad_gain = rad_gain;
     memcpy(fc.fu, a.fu, sizeof(float) * 6 * UP);
-    memcpy(fc.fd, a.fd, sizeof(float) * 12);
+    memcpy(fc.fd, a.fd, sizeof(float) * (a.fd_2d ? 144 : 12));
     ++g_cache_n;
     *out = fc.dev;
+    if (cache_out) *cache_out = &fc;
     return MB_OK;
 }
 
@@ -747,9 +927,14 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     if ((-a.px0) % UP != 0 && (-a.px0) > 0) ++q;  // ceil(-pad/UP)
     const int e = ((q % 2) + 2) % 2;
     uint4* frags = nullptr;
-    int r = build_frags<UP>(a, rho, e, &frags);
+    FragCache* fc = nullptr;
+    int r = build_frags<UP>(a, rho, e, &frags, &fc);
     if (r != MB_OK) return r;
+    const bool radial = a.fd_2d != 0;
     MmaParams p;
+    p.nt = radial ? fc->nt : 0;
+    p.rfrags = radial ? frags + K::NFRAG * 32 : nullptr;
+    const int rad_smem = p.nt * 6 * 32 * static_cast<int>(sizeof(uint4));
     p.x = a.x; p.bias = a.bias; p.scale = a.scale; p.y = a.y; p.frags = frags;
     p.C = a.C; p.Hin = a.Hin; p.Win = a.Win; p.Wp_in = a.Wp_in; p.Hout = a.Hout; p.Wout = a.Wout; p.Wp_out = a.Wp_out;
     p.Cp_out = 0;
@@ -757,7 +942,9 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     p.tiles_x = ceil_div(a.Wout, kOT); p.tiles_y = ceil_div(a.Hout, kOT);
     p.e = e;
     p.rho = rho;
-    {
+    if (radial) {
+        p.out_gain = static_cast<float>(static_cast<double>(a.gain) * fc->rad_gain);
+    } else {
         float fd16[12];
         const double cd = tuned_down_taps(a, fd16);
         p.out_gain = static_cast<float>(static_cast<double>(a.gain) * cd * cd);
@@ -783,7 +970,7 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         }
         const bool packable = ceil_div(a.C, kCG) <= 255 && p.tiles_x <= 255 && p.tiles_y <= 255 && a.B <= 255;
         const bool prefer_p = a.Hout <= (UP == 2 ? 300 : 100);
-        const int variant = !packable ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
+        const int variant = (!packable || radial) ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
         if (variant == 1) {
             constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;
             static bool attr_p = false;
@@ -800,23 +987,29 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
             return MB_OK;
         }
         constexpr int smem = kCG * K::XBYTES + 2 * kCG * kStageBytes + 64;
+        constexpr int smem_max = smem + kMaxTerms * 6 * 32 * static_cast<int>(sizeof(uint4));
         static bool attr_nhwc = false;
         if (!attr_nhwc) {
-            MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_kernel<UP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_kernel<UP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
             attr_nhwc = true;
         }
         dim3 grid(ceil_div(ntiles, p.tpw), ceil_div(a.C, kCG), a.B);
-        flrelu_mma_nhwc_kernel<UP><<<grid, kCG * 32, smem, stream>>>(p);
+        if (radial) flrelu_mma_nhwc_kernel<UP, true><<<grid, kCG * 32, smem + rad_smem, stream>>>(p);
+        else flrelu_mma_nhwc_kernel<UP, false><<<grid, kCG * 32, smem, stream>>>(p);
         MB_CUDA(cudaGetLastError());
         return MB_OK;
     }
     static bool attr_done = false;
     if (!attr_done) {
-        MB_CUDA(cudaFuncSetAttribute(flrelu_mma_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        MB_CUDA(cudaFuncSetAttribute(flrelu_mma_kernel<UP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        MB_CUDA(cudaFuncSetAttribute(flrelu_mma_kernel<UP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     K::SMEM + kMaxTerms * 6 * 32 * static_cast<int>(sizeof(uint4))));
         attr_done = true;
     }
     dim3 grid(ceil_div(ntiles, kWarps * p.tpw), a.C, a.B);
-    flrelu_mma_kernel<UP><<<grid, kWarps * 32, K::SMEM, stream>>>(p);
+    if (radial) flrelu_mma_kernel<UP, true><<<grid, kWarps * 32, K::SMEM + rad_smem, stream>>>(p);
+    else flrelu_mma_kernel<UP, false><<<grid, kWarps * 32, K::SMEM, stream>>>(p);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }
@@ -824,7 +1017,8 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
 }  // namespace
 
 bool flrelu_mma_supported(const FlreluArgs& a) {
-    if (a.fd_2d || a.down != 2 || a.down_taps != 12) return false;
+    if (a.down != 2 || a.down_taps != 12) return false;
+    if (a.fd_2d && !radial_terms(a.fd).ok) return false;   // radial filters run as a few separable terms
     if (!((a.up == 2 && a.up_taps == 12) || (a.up == 4 && a.up_taps == 24))) return false;
     if (a.px0 != a.py0) return false;
     if (a.C > 65535 || a.B > 65535) return false;

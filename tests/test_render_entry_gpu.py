@@ -47,3 +47,22 @@ def test_generate_from_patch_memmap_and_raw_sink(cuda, tmp_path):
         first = np.fromfile(raw, dtype=np.uint8, count=1024 * 1024 * 3).reshape(1024, 1024, 3)
         # same generator seed -> same frames as the memmap render (round vs truncate: off by at most 1)
         assert int(np.abs(first.astype(np.int16) - video[0].transpose(1, 2, 0).astype(np.int16)).max()) <= 1
+
+
+def test_async_frame_downloader_round_trip(cuda):
+    """Frames written by consecutive batches arrive intact and in order through the side-stream pinned ring."""
+    import torch
+
+    from maua_b200.audiovisual.render._loop import AsyncFrameDownloader
+
+    dl = AsyncFrameDownloader((2, 8, 8, 3), cuda, depth=2)
+    got = []
+    for i in range(5):
+        buf = dl.device_buffer(i)
+        buf.fill_(i + 1)
+        dl.download(i)
+        if i >= 1:
+            got.append(int(dl.host(i - 1)[0, 0, 0, 0]))
+    got.append(int(dl.host(4)[-1, -1, -1, -1]))
+    dl.synchronize()
+    assert got == [1, 2, 3, 4, 5]

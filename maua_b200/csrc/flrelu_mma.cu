@@ -930,7 +930,8 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     FragCache* fc = nullptr;
     int r = build_frags<UP>(a, rho, e, &frags, &fc);
     if (r != MB_OK) return r;
-    const bool radial = a.fd_2d != 0;
+    const bool radial = a.fd_2d != 0;   // (routing the separable filter through the shared-memory fragment path to free
+                                        //  12 registers measured 6 % slower: 8.19 vs 7.71 ms/step)
     MmaParams p;
     p.nt = radial ? fc->nt : 0;
     p.rfrags = radial ? frags + K::NFRAG * 32 : nullptr;

@@ -179,8 +179,9 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // Shared-memory matrix descriptor (sm_100 "version 1").  layout: 2 = SWIZZLE_128B, 4 = 64B, 6 = 32B.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout) {
+                                                   uint32_t layout, uint32_t base_offset = 0) {
     uint64_t d = 0;
+    d |= static_cast<uint64_t>(base_offset & 7) << 49;  // start not aligned to the 1024-byte swizzle repeat: (addr >> 7) & 7
     d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;

@@ -268,6 +268,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 // Epilogue: one TMEM lane = one pixel.  Neighbouring lanes swap one cout of every cout pair (one SHFL + PRMT), so a
 // lane stores two adjacent pixels of one cout (4 bytes) and a warp store covers 2 x 64-byte row segments; the
 // per-cout (demodulation, bias) pairs come from a per-warp shared-memory table refreshed when the frame changes.
+// With resident weights ONE patch load per 64-channel chunk serves all nine taps (`shift`): tap (kh, kw) reads the
+// 128-row A window that starts kh image rows (whole swizzle atoms) and kw pixels (kw * 128 bytes, INSIDE an atom)
+// further on -- the tensor core applies the 128-byte swizzle to absolute shared-memory address bits, so a descriptor
+// start that is not 1024-byte aligned needs no base offset (probed on B200, scripts/conv_shift_probe.py).  The tile
+// is then 30 pixels wide so every shifted window stays inside the 32-pixel patch; TMA traffic drops 2.8x.
 constexpr int kPmTW = 32, kPmTH = 8;
 constexpr int kPmSlab = kPmTW * 128;
 constexpr int kPmMaxStages = 4;
@@ -275,6 +280,9 @@ constexpr int kPmMaxStages = 4;
 struct PmArgs {
     KArgs k;
     int Np, stages, stage_bytes_alloc, resident;
+    int shift;   // 0: one patch load per (kw, chunk); 1 / 2: ONE patch load per chunk, the kw shift is a +128-byte start
+                 // offset of the A descriptor (2: with the descriptor's base-offset field set to the row phase)
+    int tile_w;  // valid output pixels per tile row: 32, or 30 when the shifted window must stay inside the 32-px patch
 };
 
 __global__ void __launch_bounds__(256, 1)
@@ -291,7 +299,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int patch_bytes = patch_rows * kPmSlab;
     // layout: [resident weight tiles | stages: patch (+ ksz weight tiles when streaming) | (scale,bias) tables | barriers]
     uint8_t* stages = smem + (pa.resident ? n_wtiles * w_tile : 0);
-    float2* sc_tab = reinterpret_cast<float2*>(stages + nst * STAGE);   // [4 warps][128]
+    float2* sc_tab = reinterpret_cast<float2*>(stages + nst * STAGE);   // [4 warps][128] (demodulation, bias) of the current frame
     uint64_t* bars = reinterpret_cast<uint64_t*>(sc_tab + 4 * 128);
     uint64_t* full = bars;                         // [kPmMaxStages]
     uint64_t* empty = bars + kPmMaxStages;         // [kPmMaxStages]
@@ -343,8 +351,8 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const int wt = r % a.tiles_w; r /= a.tiles_w;
             const int ht = r % a.tiles_h; r /= a.tiles_h;
             const int b = r;
-            const int h0 = ht * kPmTH, w0 = wt * kPmTW;
-            for (int kw = 0; kw < a.ksz; ++kw) {
+            const int h0 = ht * kPmTH, w0 = wt * pa.tile_w;
+            for (int kw = 0; kw < (pa.shift ? 1 : a.ksz); ++kw) {
                 for (int cc = 0; cc < a.nCC; ++cc) {
                     mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                     if (leader) {
@@ -375,13 +383,38 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 2 * Np;
             uint32_t accumulate = 0;
-            for (int it = 0; it < iters; ++it) {
+            for (int it = 0; it < (pa.shift ? a.nCC : iters); ++it) {
                 const int cc = it % a.nCC;
                 int nk16 = (a.Cin - cc * kKC + 15) / 16;
                 if (nk16 > 4) nk16 = 4;
                 mbar_wait(&full[s], ph, a.dbg, 3);
                 tc_fence_after();
                 const uint32_t sx = smem_u32(stages + s * STAGE);
+                if (pa.shift) {
+                    // one resident patch serves all nine taps: tap (kh, kw) reads the 128-row window that starts
+                    // kh image rows (whole swizzle atoms) and kw pixels (kw * 128 bytes, inside an atom) further on
+                    if (leader) {
+                        for (int kw = 0; kw < a.ksz; ++kw) {
+                            const uint32_t sw = smem_u32(smem) + ((kw * a.nCC + cc) * a.ksz) * w_tile;
+                            const uint64_t dx = make_smem_desc(sx + kw * 128, 16, 1024, 2, pa.shift == 2 ? kw : 0);
+                            const uint64_t dw = make_smem_desc(sw, 16, 1024, 2);
+                            for (int kh = 0; kh < a.ksz; ++kh) {
+#pragma unroll 4
+                                for (int j = 0; j < nk16; ++j) {
+                                    const uint64_t dwk = dw + static_cast<uint64_t>((kh * w_tile + j * 32) >> 4);
+                                    const uint64_t dxk = dx + static_cast<uint64_t>((kh * kPmSlab + j * 32) >> 4);
+                                    umma_f16(d_tmem, dxk, dwk, idesc, accumulate);
+                                    umma_f16(d_tmem + Np, dxk + static_cast<uint64_t>((4 * kPmSlab) >> 4), dwk, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                        }
+                        umma_commit(&empty[s]);
+                    }
+                    __syncwarp();
+                    if (++s == nst) { s = 0; ph ^= 1; }
+                    continue;
+                }
                 const uint32_t sw = pa.resident ? smem_u32(smem) + it * a.ksz * w_tile : sx + patch_bytes;
                 const uint64_t dx = make_smem_desc(sx, 16, 1024, 2);
                 const uint64_t dw = make_smem_desc(sw, 16, 1024, 2);
@@ -407,7 +440,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         }
     } else if (warp >= 4) {
         const int q = warp - 4;  // TMEM lane quadrant == image row of the half tile
-        float2* tab = sc_tab + q * 128;
+        float2* tab = sc_tab + q * 128;   // per-warp copy (one table shared under a named barrier measured 20 % slower)
         const int par = lane & 1;
         const uint32_t sel = par ? 0x3276u : 0x5410u;   // even lane keeps cout c of a pair, odd lane cout c+1
         int acc = 0;
@@ -427,8 +460,8 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 __syncwarp();
                 tab_b = b;
             }
-            const int w = wt * kPmTW + lane;
-            const bool w_ok = w < a.Wp_out;   // Wp_out is even: both pixels of a lane pair are in or out together
+            const int w = wt * pa.tile_w + lane;
+            const bool w_ok = w < a.Wp_out && lane < pa.tile_w;   // Wp_out and tile_w are even: lane pairs are in or out together
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
 #pragma unroll 1
@@ -566,11 +599,19 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         pa.k.tiles_m = 1;
         pa.k.total_tiles = p.B * a.tiles_h * a.tiles_w;
         pa.Np = Np;
+        pa.shift = 0;
+        pa.tile_w = kPmTW;
         const int w_tile = Np * 128;
         const int pm_patch = (kPmTH + halo) * kPmSlab;
         const int pm_fixed = 1024 /*align*/ + 4 * 128 * 8 /*(scale,bias) tables*/ + 256 /*barriers*/;
         const int pm_w_all = p.ksz * p.ksz * nCC * w_tile;
         pa.resident = (pm_w_all + 2 * pm_patch + pm_fixed <= kSmemMax) ? 1 : 0;
+        pa.shift = (p.ksz == 3 && pa.resident) ? p.pm_shift : 0;
+        pa.tile_w = pa.shift ? 30 : kPmTW;
+        if (pa.shift) {
+            pa.k.tiles_w = ceil_div(a.Wout, pa.tile_w);
+            pa.k.total_tiles = p.B * a.tiles_h * pa.k.tiles_w;
+        }
         pa.stage_bytes_alloc = pm_patch + (pa.resident ? 0 : p.ksz * w_tile);
         pa.stages = (kSmemMax - pm_fixed - (pa.resident ? pm_w_all : 0)) / pa.stage_bytes_alloc;
         if (pa.stages > kPmMaxStages) pa.stages = kPmMaxStages;

@@ -117,16 +117,19 @@ __device__ __forceinline__ void cp_async_wait() {
 struct NoHook {
     __device__ __forceinline__ void operator()() const {}
 };
-// `x_dead` is invoked right after the last read of X (the last stage-1 block): a single-buffered caller
-// issues the prefetch of its next input tile there.
+// The input tile is consumed in two halves of NIB/2 row blocks.  `dead0` / `dead1` are invoked right after the last
+// read of the first / second half, `wait1` right before the first read of the second half: a single-buffered caller
+// refills each half with the next tile's rows as soon as it is dead (and only blocks on the second half when it
+// gets there), so the fetch latency hides behind two to four strips of MMAs.
 // Radial (non-separable) down filters of StyleGAN3-R: the 12x12 jinc*kaiser filter is symmetric and numerically of rank
 // 2..4 (eigenvalues fall off by 1e-2 per term), so it runs as `nt` separable terms F = sum_k g_k h_k^T whose fragments
 // (per term: three down-H and three down-V k-steps) sit in shared memory (`sAD`, [nt][6][32] uint4) and accumulate
 // into the same output registers.  nt == 0 selects the separable filter held in registers (AD).
-template <int UP, bool RAD = false, class Hook = NoHook>
+template <int UP, bool RAD = false, class W1 = NoHook, class D0 = NoHook, class D1 = NoHook>
 __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (&AU)[MC<UP>::NVAR], const uint4 (&AD)[3],
                                           uint32_t sl2, uint32_t cl2, int g, int tig,
-                                          float (&OUT)[2][4][4], Hook x_dead = Hook(), const uint4* sAD = nullptr, int nt = 0) {
+                                          float (&OUT)[2][4][4], W1 wait1 = W1(), D0 dead0 = D0(), D1 dead1 = D1(),
+                                          const uint4* sAD = nullptr, int nt = 0) {
     using K = MC<UP>;
     uint32_t P1[2][kMB][2];  // packed A1^T of the two input-row n8 blocks the strip window covers (slot = block & 1)
     int have0 = -1, have1 = -1;  // compile-time constants after unrolling
@@ -140,6 +143,7 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
     }
 
     auto stage1 = [&](int blk) {
+        if (blk == K::NIB / 2) wait1();
 #pragma unroll
         for (int m = 0; m < kMB; ++m) {
             const int w0 = K::wblk(m) * 8;
@@ -151,6 +155,8 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
             P1[blk & 1][m][0] = pack2(acc[0], acc[1]);
             P1[blk & 1][m][1] = pack2(acc[2], acc[3]);
         }
+        if (blk == K::NIB / 2 - 1) dead0();
+        if (blk == K::NIB - 1) dead1();
     };
 
 #pragma unroll
@@ -165,7 +171,6 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
             stage1(wb + 1);
             if ((wb + 1) & 1) have1 = wb + 1; else have0 = wb + 1;
         }
-        if (j == kStrips - 1) x_dead();
         // ---- S2 (+activation): T[16 rows of strip j][80 cols], packed as B operands of S3
         uint32_t P2[kJB][2];
 #pragma unroll
@@ -256,6 +261,7 @@ __device__ __forceinline__ void lane_setup(const MmaParams& p, int lane, LaneCon
 }
 
 // Fetch the [IYT rows x 56 halfs] input tile of one warp with cp.async (zero fill outside the image = padding).
+// Used by the planar-output kernel (double-buffered); the channels-last kernels fetch by TMA (tma_half_tile).
 // Lane -> (row mod 4, 16-byte chunk): the chunk column and its byte count are per-tile constants of the lane and
 // the row loop is fully unrolled with immediate offsets (this loader was 15 % of the kernel's instructions when
 // it derived row and chunk from a running index, ncu r1).
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
         const int dx = ix0 & 7;  // even by construction
 
         float OUT[2][4][4];
-        fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, NoHook(), sAD, p.nt);
+        fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, NoHook(), NoHook(), NoHook(), sAD, p.nt);
 
         // ---- store: * next-layer style, fp16, two adjacent columns per thread
 #pragma unroll
@@ -387,8 +393,21 @@ __global__ void __launch_bounds__(kWarps * 32, 2) flrelu_mma_kernel(const MmaPar
 // the same run of tiles.  Each warp stages its finished 32x32 tile in shared memory, then the CTA writes
 // 32-byte (16 channel) pixel chunks -- full DRAM sectors -- into [B][H][W][Cp].
 constexpr int kCG = 16;          // channels per CTA
+constexpr int kTailBytes = 512;  // staging mbarriers (<= 6) at +0, per-warp input-tile mbarriers [16][2] at +64
 constexpr int kSP = 40;          // staging row pitch in halfs (conflict-free fragment stores)
 constexpr int kStageBytes = kOT * kSP * 2;
+
+// One half (NIB/2 row blocks) of a warp's input tile by TMA: box (56 halfs, IYT/2 rows, 1 plane) of the planar conv
+// output viewed as [B*C][Hin][Win] with row pitch Wp_in -- out-of-image rows / columns (the zero padding of the
+// upsampler, and the pad columns [Win, Wp_in)) arrive as zeros.  One elected lane, one instruction, no address math.
+template <int UP>
+__device__ __forceinline__ void tma_half_tile(const CUtensorMap* tmap, __half* X, uint64_t* xbar, int half, int ix0, int iy0,
+                                              int plane) {
+    using K = MC<UP>;
+    constexpr uint32_t kHalfBytes = (K::IYT / 2) * kXP * 2;
+    mbar_arrive_expect_tx(&xbar[half], kHalfBytes);
+    tma_load_3d(X + half * (K::IYT / 2) * kXP, tmap, &xbar[half], ix0 & ~7, iy0 + half * (K::IYT / 2), plane);
+}
 
 // Write-out share of one warp for a finished 32x32 tile held as 16 staged channel planes: image rows 2*warp and
 // 2*warp+1, one pixel per lane and row (16 LDS.U16 -> one 32-byte chunk).  A variant reading pixel pairs with
@@ -416,20 +435,22 @@ __device__ __forceinline__ void write_out_tile(const MmaParams& p, const __half*
 }
 
 template <int UP, bool RAD>
-__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaParams p) {
+__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const __grid_constant__ CUtensorMap tmap_x, const MmaParams p) {
     using K = MC<UP>;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~uintptr_t(127));  // TMA destinations
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
-    // layout: [16 warps] input tile (single buffer) | [2 buffers][16 planes] staging | 4 mbarriers
+    // layout: [16 warps] input tile (single buffer) | [2 buffers][16 planes] staging | mbarriers | radial fragments
     __half* X = reinterpret_cast<__half*>(smem_raw + warp * K::XBYTES);
     __half* stage_base = reinterpret_cast<__half*>(smem_raw + kCG * K::XBYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes);
     uint64_t* full = bars;       // [2] all 16 planes of a staging buffer written
     uint64_t* empty = bars + 2;  // [2] all 16 write-out shares of a staging buffer done
-    const uint4* sAD = reinterpret_cast<const uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + 64);
+    uint64_t* xbar = bars + 8 + 2 * warp;   // [2] halves of this warp's input tile landed
+    const uint4* sAD = reinterpret_cast<const uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + kTailBytes);
     if (RAD) {  // radial down filter: term fragments -> shared memory (visible after the __syncthreads below)
-        uint4* dst = reinterpret_cast<uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + 64);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + kCG * K::XBYTES + 2 * kCG * kStageBytes + kTailBytes);
         for (int i = threadIdx.x; i < p.nt * 6 * 32; i += blockDim.x) dst[i] = p.rfrags[i];
     }
 
@@ -439,10 +460,12 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     const int c0 = blockIdx.y * kCG, b = blockIdx.z;
     const int c = c0 + warp;
     const bool valid = c < p.C;
-    const __half* xp = p.x + (static_cast<long long>(b) * p.C + (valid ? c : 0)) * p.Hin * p.Wp_in;
+    const int plane = b * p.C + (valid ? c : 0);
 
     if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_x);
         for (int i = 0; i < 4; ++i) mbar_init(&bars[i], kCG);
+        for (int i = 0; i < 2 * kCG; ++i) mbar_init(&bars[8 + i], 1);
         fence_barrier_init();
     }
     LaneConsts<UP> LC;
@@ -461,29 +484,37 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_kernel(const MmaP
     // one register each for tile i and tile i-1 (this kernel sits at the 128-register limit)
     uint32_t pos = static_cast<uint32_t>(tile0 % p.tiles_x) | (static_cast<uint32_t>(tile0 / p.tiles_x) << 16);
     uint32_t ppos = pos;
-    auto load_tile = [&](uint32_t q) {
-        load_tile_async<UP>(p, xp, X, first_in<UP>((q & 0xffff) * kOT, p.px0, p.e), first_in<UP>((q >> 16) * kOT, p.py0, p.e), lane);
+    auto load_half = [&](uint32_t q, int half) {   // one lane issues
+        tma_half_tile<UP>(&tmap_x, X, xbar, half, first_in<UP>((q & 0xffff) * kOT, p.px0, p.e),
+                          first_in<UP>((q >> 16) * kOT, p.py0, p.e), plane);
     };
     auto write_out = [&](uint32_t q, int sb) {
         write_out_tile(p, stage_base + sb * kCG * (kStageBytes / 2), warp, lane, b, c0, (q & 0xffff) * kOT, (q >> 16) * kOT);
     };
 
-    if (valid) load_tile(pos);
+    uint32_t xph = 0;  // parity of this warp's input-tile barriers: both complete once per tile
+    if (valid && lane == 0) { load_half(pos, 0); load_half(pos, 1); }
     for (int i = 0; i < n; ++i) {
         const int sb = i & 1;
         const uint32_t npos = ((pos & 0xffff) + 1 == static_cast<uint32_t>(p.tiles_x)) ? (pos & 0xffff0000u) + 0x10000u : pos + 1;
         // the staging buffer is free once every warp has written out its share of tile i-2
         if (i >= 2) mbar_wait(&empty[sb], ((i >> 1) - 1) & 1);
         if (valid) {
-            cp_async_wait<0>();
-            __syncwarp();
+            mbar_wait(&xbar[0], xph);
             const int dx = first_in<UP>((pos & 0xffff) * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
-            auto x_dead = [&]() {
-                __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
-                if (i + 1 < n) load_tile(npos);
+            const bool more = i + 1 < n;
+            auto wait1 = [&]() { mbar_wait(&xbar[1], xph); };
+            auto dead0 = [&]() {
+                __syncwarp();  // every lane is done reading the first half: refill it with the next tile's rows
+                if (more && lane == 0) load_half(npos, 0);
             };
-            fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, x_dead, sAD, p.nt);
+            auto dead1 = [&]() {
+                __syncwarp();
+                if (more && lane == 0) load_half(npos, 1);
+            };
+            fir_chain<UP, RAD>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, wait1, dead0, dead1, sAD, p.nt);
+            xph ^= 1;
             __half* stage = stage_base + (sb * kCG + warp) * (kStageBytes / 2);
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii)
@@ -529,9 +560,11 @@ struct ItemPos {
 };
 
 template <int UP>
-__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const MmaParams p, int ngroups, int total) {
+__global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const __grid_constant__ CUtensorMap tmap_x, const MmaParams p,
+                                                                        int ngroups, int total) {
     using K = MC<UP>;
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    extern __shared__ uint8_t smem_dyn[];
+    uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 127) & ~uintptr_t(127));  // TMA destinations
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
     __half* X = reinterpret_cast<__half*>(smem_raw + warp * K::XBYTES);
@@ -539,6 +572,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kCG * K::XBYTES + kNSB * kCG * kStageBytes);
     uint64_t* full = bars;           // [kNSB] all 16 planes of a staging buffer written
     uint64_t* empty = bars + kNSB;   // [kNSB] all 16 write-out shares of a staging buffer done
+    uint64_t* xbar = bars + 8 + 2 * warp;   // [2] halves of this warp's input tile landed
 
     const int per = (total + gridDim.x - 1) / gridDim.x;
     const int start = blockIdx.x * per;
@@ -546,7 +580,9 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
     if (n <= 0) return;
 
     if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_x);
         for (int i = 0; i < 2 * kNSB; ++i) mbar_init(&bars[i], kCG);
+        for (int i = 0; i < 2 * kCG; ++i) mbar_init(&bars[8 + i], 1);
         fence_barrier_init();
     }
     LaneConsts<UP> LC;
@@ -562,11 +598,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
             }
         }
     };
-    auto load_tile = [&](const ItemPos& q) {
+    auto load_half = [&](const ItemPos& q, int half) {   // one lane issues; no-op for the padding channels of a last group
         const int c = q.grp * kCG + warp;
         if (c >= p.C) return;
-        const __half* xp = p.x + (static_cast<long long>(q.b) * p.C + c) * p.Hin * p.Wp_in;
-        load_tile_async<UP>(p, xp, X, first_in<UP>(q.tx * kOT, p.px0, p.e), first_in<UP>(q.ty * kOT, p.py0, p.e), lane);
+        tma_half_tile<UP>(&tmap_x, X, xbar, half, first_in<UP>(q.tx * kOT, p.px0, p.e), first_in<UP>(q.ty * kOT, p.py0, p.e),
+                          q.b * p.C + c);
     };
     auto write_out = [&](const ItemPos& q, int sb) {
         write_out_tile(p, stage_base + sb * kCG * (kStageBytes / 2), warp, lane, q.b, q.grp * kCG, q.tx * kOT, q.ty * kOT);
@@ -595,7 +631,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
         return q;
     };
     uint32_t old1 = pack_pos(cur), old2 = old1;
-    load_tile(cur);
+    uint32_t xph = 0;  // parity of this warp's input-tile barriers: both complete once per tile this warp computes
+    if (lane == 0) { load_half(cur, 0); load_half(cur, 1); }
     for (int i = 0; i < n; ++i) {
         const int sb = i % kNSB;
         if (i >= 2) drain(unpack_pos(old2), i - 2);
@@ -607,15 +644,21 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
         const int c = cur.grp * kCG + warp;
         if (c < p.C) {
             const float oscale = (p.scale ? p.scale[cur.b * p.C + c] : 1.0f) * p.out_gain;
-            cp_async_wait<0>();
-            __syncwarp();
+            mbar_wait(&xbar[0], xph);
             const int dx = first_in<UP>(cur.tx * kOT, p.px0, p.e) & 7;
             float OUT[2][4][4];
-            auto x_dead = [&]() {
-                __syncwarp();  // every lane is done reading X: prefetch the next tile into the same buffer
-                if (i + 1 < n) load_tile(nxt);
+            const bool more = i + 1 < n;
+            auto wait1 = [&]() { mbar_wait(&xbar[1], xph); };
+            auto dead0 = [&]() {
+                __syncwarp();  // every lane is done reading the first half: refill it with the next tile's rows
+                if (more && lane == 0) load_half(nxt, 0);
             };
-            fir_chain<UP, false>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, x_dead);
+            auto dead1 = [&]() {
+                __syncwarp();
+                if (more && lane == 0) load_half(nxt, 1);
+            };
+            fir_chain<UP, false>(X, dx, LC.AU, LC.AD, LC.sl2, LC.cl2, g, tig, OUT, wait1, dead0, dead1);
+            xph ^= 1;
 #pragma unroll
             for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
@@ -628,7 +671,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const Mm
             // channel padding of the last group: this warp's plane is zero
             uint4* z = reinterpret_cast<uint4*>(stage);
             for (int k = lane; k < kStageBytes / 16; k += 32) z[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (i + 1 < n) load_tile(nxt);
+            if (i + 1 < n && lane == 0) { load_half(nxt, 0); load_half(nxt, 1); }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full[sb]);
@@ -962,18 +1005,39 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
         // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200,
-        // scripts/layer_times.py: the persistent kernel wins on the small maps, the grid version on the large ones,
-        // earlier for up=4 whose persistent build spills at the 128-register limit)
+        // scripts/layer_times.py: with TMA-fed input tiles the persistent kernel only wins on the small maps (<= 100^2))
         static int forced = -2;
         if (forced == -2) {
             const char* e = getenv("MB_FLRELU_NHWC");
             forced = e ? atoi(e) : -1;
         }
         const bool packable = ceil_div(a.C, kCG) <= 255 && p.tiles_x <= 255 && p.tiles_y <= 255 && a.B <= 255;
-        const bool prefer_p = a.Hout <= (UP == 2 ? 300 : 100);
+        const bool prefer_p = a.Hout <= 100;
         const int variant = (!packable || radial) ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
+        // the planar input as a 3-D tensor [B*C][Hin][Win] (row pitch Wp_in): half-tile boxes of (56 halfs, IYT/2 rows)
+        CUtensorMap tm_x;
+        {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) {
+                set_error("cuTensorMapEncodeTiled not available from the driver");
+                return MB_ECUDA;
+            }
+            MB_REQUIRE(a.Wp_in % 8 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "filtered_lrelu: input rows must be 16-byte aligned");
+            cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.Win), static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B) * a.C};
+            cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.Wp_in) * 2, static_cast<cuuint64_t>(a.Wp_in) * 2 * a.Hin};
+            cuuint32_t box[3] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(K::IYT / 2), 1};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult cr = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(a.x), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled(filtered_lrelu input) failed: %d (W=%d H=%d planes=%d pitch=%d)", static_cast<int>(cr),
+                          a.Win, a.Hin, a.B * a.C, a.Wp_in);
+                return MB_ECUDA;
+            }
+        }
         if (variant == 1) {
-            constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + 64;
+            constexpr int smem_p = kCG * K::XBYTES + kNSB * kCG * kStageBytes + kTailBytes + 128;
             static bool attr_p = false;
             if (!attr_p) {
                 MB_CUDA(cudaFuncSetAttribute(flrelu_mma_nhwc_p_kernel<UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p));
@@ -983,11 +1047,11 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
             const int total = a.B * ngroups * ntiles;
             const int sms = a.num_sms > 0 ? a.num_sms : 148;
             const int grid = total < sms ? total : sms;
-            flrelu_mma_nhwc_p_kernel<UP><<<grid, kCG * 32, smem_p, stream>>>(p, ngroups, total);
+            flrelu_mma_nhwc_p_kernel<UP><<<grid, kCG * 32, smem_p, stream>>>(tm_x, p, ngroups, total);
             MB_CUDA(cudaGetLastError());
             return MB_OK;
         }
-        constexpr int smem = kCG * K::XBYTES + 2 * kCG * kStageBytes + 64;
+        constexpr int smem = kCG * K::XBYTES + 2 * kCG * kStageBytes + kTailBytes + 128;
         constexpr int smem_max = smem + kMaxTerms * 6 * 32 * static_cast<int>(sizeof(uint4));
         static bool attr_nhwc = false;
         if (!attr_nhwc) {
@@ -996,8 +1060,8 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
             attr_nhwc = true;
         }
         dim3 grid(ceil_div(ntiles, p.tpw), ceil_div(a.C, kCG), a.B);
-        if (radial) flrelu_mma_nhwc_kernel<UP, true><<<grid, kCG * 32, smem + rad_smem, stream>>>(p);
-        else flrelu_mma_nhwc_kernel<UP, false><<<grid, kCG * 32, smem, stream>>>(p);
+        if (radial) flrelu_mma_nhwc_kernel<UP, true><<<grid, kCG * 32, smem + rad_smem, stream>>>(tm_x, p);
+        else flrelu_mma_nhwc_kernel<UP, false><<<grid, kCG * 32, smem, stream>>>(tm_x, p);
         MB_CUDA(cudaGetLastError());
         return MB_OK;
     }

@@ -1,0 +1,27 @@
+"""profiles/traffic.json from an ncu CSV of one B=8 forward:
+  ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
+      -k regex:'flrelu|conv_' --launch-skip 28 --launch-count 28 --csv --log-file gpurun_out/traffic.csv \
+      python scripts/one_forward.py 8 T
+bench.py reports these measured DRAM bytes per step as roofline.traffic next to the algorithmic bytes."""
+import csv, json, sys
+src, dst, B = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 8
+rows = [r for r in csv.reader(open(src)) if len(r) >= 15 and r[0].isdigit()]
+acc = {"filtered_lrelu": {"bytes": 0.0, "ns": 0.0, "launches": set()}, "modulated_conv2d": {"bytes": 0.0, "ns": 0.0, "launches": set()}}
+for r in rows:
+    name, metric, unit, val = r[4], r[12], r[13], float(r[14].replace(",", ""))
+    fam = "filtered_lrelu" if "flrelu" in name else ("modulated_conv2d" if "conv_" in name else None)
+    if fam is None:
+        continue
+    acc[fam]["launches"].add(r[0])
+    if metric.startswith("dram__bytes"):
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+        acc[fam]["bytes"] += val * scale
+    elif metric.startswith("gpu__time_duration"):
+        acc[fam]["ns"] += val * {"ns": 1.0, "us": 1e3, "ms": 1e6}[unit]
+out = {"source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE forward (B=%d), scripts/make_traffic.py" % B}
+for fam, d in acc.items():
+    out["%s_bytes_per_step_b%d" % (fam, B)] = d["bytes"]
+    out["%s_launches" % fam] = len(d["launches"])
+    out["%s_ncu_ms" % fam] = d["ns"] / 1e6
+json.dump(out, open(dst, "w"), indent=1)
+print(json.dumps(out))

@@ -285,6 +285,7 @@ struct PmArgs {
     int tile_w;  // valid output pixels per tile row: 32, or 30 when the shifted window must stay inside the 32-px patch
 };
 
+template <bool SHIFT>
 __global__ void __launch_bounds__(256, 1)
 conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, PmArgs pa) {
     const KArgs& a = pa.k;
@@ -352,7 +353,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const int ht = r % a.tiles_h; r /= a.tiles_h;
             const int b = r;
             const int h0 = ht * kPmTH, w0 = wt * pa.tile_w;
-            for (int kw = 0; kw < (pa.shift ? 1 : a.ksz); ++kw) {
+            for (int kw = 0; kw < (SHIFT ? 1 : a.ksz); ++kw) {
                 for (int cc = 0; cc < a.nCC; ++cc) {
                     mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                     if (leader) {
@@ -383,14 +384,14 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * 2 * Np;
             uint32_t accumulate = 0;
-            for (int it = 0; it < (pa.shift ? a.nCC : iters); ++it) {
+            for (int it = 0; it < (SHIFT ? a.nCC : iters); ++it) {
                 const int cc = it % a.nCC;
                 int nk16 = (a.Cin - cc * kKC + 15) / 16;
                 if (nk16 > 4) nk16 = 4;
                 mbar_wait(&full[s], ph, a.dbg, 3);
                 tc_fence_after();
                 const uint32_t sx = smem_u32(stages + s * STAGE);
-                if (pa.shift) {
+                if constexpr (SHIFT) {
                     // one resident patch serves all nine taps: tap (kh, kw) reads the 128-row window that starts
                     // kh image rows (whole swizzle atoms) and kw pixels (kw * 128 bytes, inside an atom) further on
                     if (leader) {
@@ -619,12 +620,14 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         const int smem_bytes = pm_fixed + (pa.resident ? pm_w_all : 0) + pa.stages * pa.stage_bytes_alloc;
         static bool attr_pm = false;
         if (!attr_pm) {
-            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_pm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_pm = true;
         }
         int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
         if (grid < 1) grid = 1;
-        conv_pm_kernel<<<grid, 256, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        if (pa.shift) conv_pm_kernel<true><<<grid, 256, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        else conv_pm_kernel<false><<<grid, 256, smem_bytes, stream>>>(tm_w, tm_x, pa);
         MB_CUDA(cudaGetLastError());
         return MB_OK;
     }

@@ -327,7 +327,7 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frames_per_gpu": per,
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush",
                    "output": "uint8 NHWC frames resident in HBM",
-                   "audio_features": {**audio_info, "note": "device STFT/HPSS/onset/rms + harmonic constant-Q chroma pass run once before the timed region"}, "sharding": f"contiguous frame ranges over {world} rank(s), no data-path collective"},
+                   "audio_features": {**audio_info, "note": "device STFT/HPSS/onset/rms + chromagram (harmonic, tuning estimate, constant-Q, CENS) pass run once before the timed region"}, "sharding": f"contiguous frame ranges over {world} rank(s), no data-path collective"},
         "clocks": clk,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * net.num_ws * 512 * 4,
                 "d2h_bytes_per_step": B * 1024 * 1024 * 3},

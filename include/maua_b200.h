@@ -214,6 +214,20 @@ int mb_chroma_cqt(const float* audio, int64_t n, int hop, int n_fft, int n_octav
                   int n_chroma, float threshold, int normalize, float* cqt_mag, float* chroma, void* workspace,
                   size_t workspace_bytes, mb_stream stream);
 
+/* estimate_tuning(y, sr, bins_per_octave=...) of rosa/pitch.py:9-120 (piptrack with the reference defaults: n_fft 2048,
+ * hop 512, 150..4000 Hz, threshold 0.1; median magnitude gate; histogram peak of the pitch residuals) -> tuning in
+ * fractions of a bin, device float32 [1].  audio: device float32 [n], n a multiple of 512. */
+size_t mb_tuning_workspace_bytes(int64_t n_samples);
+int mb_estimate_tuning(const float* audio, int64_t n, float sr, int bins_per_octave, int bins /* ceil(1 / resolution) */, float* tuning,
+                       void* workspace, size_t workspace_bytes, mb_stream stream);
+
+/* chroma_cens of rosa/spectral.py:239-280 after chroma_cqt(norm=False): L1 normalisation per frame, the smooth 4-step
+ * quantiser (natural cubic spline through host-designed knots, coef = [a | b | c | d] per interval, then the smooth
+ * step function), win_len-tap temporal smoothing (zero-padded 'same'), L2 normalisation per frame.
+ * chroma_raw / scratch / out: device float32 [n_chroma, T]. */
+int mb_chroma_cens_post(const float* chroma_raw, int n_chroma, int T, const float* knots_x, const float* coef, int n_knots,
+                        const float* smooth_win, int win_len, float* scratch, float* out, mb_stream stream);
+
 /* ---- envelope post-ops and latent sequencers (device float32, [T, C] row-major, T = frames) ----------
  * maua/audiovisual/audioreactive/signal.py: gaussian_filter :108-157 (circular padding, optional causal
  * half-kernel factor), normalize :27-38 (eps 0) / processing.py:53-56 (eps 1e-8), resample :5-24 (linear,

@@ -66,6 +66,9 @@ _SIGNATURES = {
     "mb_chroma_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int, C.c_int]),
     "mb_chroma_cqt": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P,
                                 C.c_int, C.c_float, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "mb_tuning_workspace_bytes": (C.c_size_t, [C.c_int64]),
+    "mb_estimate_tuning": (C.c_int, [_P, C.c_int64, C.c_float, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
+    "mb_chroma_cens_post": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P, _P]),
     "mb_gaussian_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _P]),
     "mb_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P]),
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),

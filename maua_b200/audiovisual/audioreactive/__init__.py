@@ -1,6 +1,6 @@
 """Audio-reactive feature / envelope / latent functions on the device (mirror of
 maua.audiovisual.audioreactive and its torch-native twin selfsupervised.features.audio)."""
-from .chroma import chroma_cqt, cqt_magnitude  # noqa: F401
+from .chroma import chroma_cens, chroma_cqt, chromagram, cqt_magnitude, estimate_tuning  # noqa: F401
 from .features import harmonic, mel_filterbank, onset_peaks, onsets, onsets_rms, percussive, rms  # noqa: F401
 from .latent import multi_weighted, select_modulo, single_weighted, slerp_loops, spline_loops, tempo_loops  # noqa: F401,E402
 from . import noise  # noqa: F401,E402

@@ -154,3 +154,102 @@ def cqt_magnitude(y, sr, hop_length=1024, fmin=None, n_bins=84, bins_per_octave=
     if n_bins % bins_per_octave:
         raise NotImplementedError("cqt_magnitude: n_bins must be a whole number of octaves")
     return _run(y, sr, hop_length, fmin, n_bins, bins_per_octave, tuning, 12, None, False, True)[1]
+
+
+# ---- tuning estimate and CENS chroma: the rest of chromagram() ------------------------------------------------------
+def estimate_tuning(y, sr, n_fft=2048, resolution=0.01, bins_per_octave=12):
+    """rosa/pitch.py:9-24 (piptrack defaults of :27-37) -> 0-dim CUDA tensor, tuning in fractions of a bin."""
+    if not y.is_cuda:
+        raise RuntimeError("maua_b200 chroma features need a CUDA tensor (no CPU fallback)")
+    if n_fft != 2048:
+        raise NotImplementedError("estimate_tuning: only n_fft=2048 (the reference default)")
+    lib = _lib.load()
+    y = y.detach().to(torch.float32).contiguous().reshape(-1)
+    n = y.numel()
+    if n % 512:
+        raise ValueError("audio length must be a multiple of 512 (n_fft // 4, the reference's piptrack hop)")
+    with torch.cuda.device(y.device):
+        out = torch.empty(1, device=y.device)
+        nbytes = lib.mb_tuning_workspace_bytes(n)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=y.device)
+        off = (-ws.data_ptr()) % 256
+        _lib.check(lib.mb_estimate_tuning(_lib.ptr(y), n, float(sr), int(bins_per_octave), int(np.ceil(1.0 / resolution)), _lib.ptr(out),
+                                          C.c_void_p(ws.data_ptr() + off), nbytes, _lib.stream_ptr()))
+    return out[0]
+
+
+def _natural_cubic_coeffs(x, y):
+    """Natural cubic spline through (x_i, y_i) in float64: per interval S(t) = a + b f + c f^2 + d f^3, f = t - x_i --
+    the quantities torchcubicspline.natural_cubic_spline_coeffs hands to the reference's spline_eval (spectral.py:189-203)."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(x)
+    h = np.diff(x)
+    m = np.zeros(n)
+    if n > 2:
+        a_ = np.zeros((n - 2, n - 2))
+        rhs = 6.0 * ((y[2:] - y[1:-1]) / h[1:] - (y[1:-1] - y[:-2]) / h[:-1])
+        i = np.arange(n - 2)
+        a_[i, i] = 2.0 * (h[:-1] + h[1:])
+        a_[i[1:], i[1:] - 1] = h[1:-1]
+        a_[i[:-1], i[:-1] + 1] = h[1:-1]
+        m[1:-1] = np.linalg.solve(a_, rhs)
+    a = y[:-1]
+    b = (y[1:] - y[:-1]) / h - h * (2.0 * m[:-1] + m[1:]) / 6.0
+    c = m[:-1] / 2.0
+    d = (m[1:] - m[:-1]) / (6.0 * h)
+    return a, b, c, d
+
+
+def cens_quantiser_design():
+    """Knots of the smooth 4-step CENS quantisation curve (spectral.py:164-188) and its natural-spline coefficients
+    -> (x float32 [240], coef float32 [4, 239])."""
+    steps = [0.4, 0.2, 0.1, 0.05]
+    p1, p2, p3, p4 = np.diff(list(reversed(steps + [0])))
+    xs = [torch.linspace(-0.1, 0.025, 101)[:-1], torch.linspace(0.025, p1, 11)[:-1], torch.linspace(p1, p1 + p2, 11)[:-1],
+          torch.linspace(p1 + p2, p1 + p2 + p3, 11)[:-1], torch.linspace(p1 + p2 + p3, 0.5, 11)[:-1], torch.linspace(0.5, 1.1, 100)]
+    ys = torch.cat((0.5 * torch.ones(len(xs[0])), xs[1] / p1, (xs[2] - p1) / p2 + 1, (xs[3] - p1 - p2) / p3 + 2,
+                    (xs[4] - p1 - p2 - p3) / p4 + 3, 4.5 * torch.ones(len(xs[5]))))
+    x = torch.cat(xs)
+    coef = np.stack(_natural_cubic_coeffs(x.numpy(), ys.numpy()))
+    return x.float().contiguous(), torch.from_numpy(coef).float().contiguous()
+
+
+_cens_cache = {}
+
+
+def chroma_cens(y, sr, hop_length=1024, fmin=None, tuning=None, n_chroma=12, n_octaves=7, bins_per_octave=36, window=None,
+                win_len_smooth=41, smoothing_window=torch.hann_window):
+    """rosa/spectral.py:239-280 -> [n_chroma, T]: chroma_cqt(norm=False) -> L1 -> smooth quantiser -> temporal
+    smoothing -> L2.  tuning=None estimates it on the device first, as the reference does (one scalar read-back: the
+    filter bank is designed for that tuning)."""
+    if tuning is None:
+        tuning = float(estimate_tuning(y, sr, bins_per_octave=bins_per_octave).item())
+    raw = chroma_cqt(y, sr, hop_length=hop_length, fmin=fmin, threshold=0.0, tuning=tuning, n_chroma=n_chroma, n_octaves=n_octaves,
+                     window=window, bins_per_octave=bins_per_octave, norm=False)
+    dev = raw.device
+    key = (str(dev), int(win_len_smooth), smoothing_window)
+    d = _cens_cache.get(key)
+    if d is None:
+        kx, coef = cens_quantiser_design()
+        if win_len_smooth:
+            win = smoothing_window(win_len_smooth + 2)
+            win = win / torch.sum(win)
+        else:
+            win = torch.ones(1)
+        d = (kx.to(dev), coef.to(dev), win.float().contiguous().to(dev))
+        _cens_cache[key] = d
+    kx, coef, win = d
+    T = raw.shape[1]
+    with torch.cuda.device(dev):
+        scratch, out = torch.empty_like(raw), torch.empty_like(raw)
+        _lib.check(_lib.load().mb_chroma_cens_post(_lib.ptr(raw), n_chroma, T, _lib.ptr(kx), _lib.ptr(coef), kx.numel(), _lib.ptr(win),
+                                                   win.numel(), _lib.ptr(scratch), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def chromagram(audio, sr):
+    """features/audio.py:44: chroma_cens(harmonic(audio), sr).T -> [T, 12]."""
+    from .features import harmonic
+
+    return chroma_cens(harmonic(audio), sr).T

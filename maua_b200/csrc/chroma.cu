@@ -141,6 +141,180 @@ __global__ void chroma_norm_kernel(float* __restrict__ chroma, int n, const int*
     if (i < n) chroma[i] = chroma[i] / __int_as_float(*max_bits);
 }
 
+// ---- tuning estimate: rosa/pitch.py:9-120 -----------------------------------------------------------------------
+// piptrack: hann STFT (n_fft 2048, hop 512), parabolic peak interpolation, per-frame relative threshold, band limit;
+// one CTA per frame, the spectrum never leaves shared memory; writes dense pitch / magnitude planes (zeros elsewhere).
+constexpr int kPipFft = 2048, kPipHop = 512, kPipBins = kPipFft / 2 + 1;
+
+__global__ void __launch_bounds__(256) piptrack_kernel(const float* __restrict__ y, long long n, float sr, float fmin, float fmax,
+                                                       float threshold, float* __restrict__ pitch, float* __restrict__ mag) {
+    __shared__ float2 bufA[kPipFft];
+    __shared__ float2 bufB[kPipFft];
+    __shared__ float2 tw[kPipFft / 2];
+    __shared__ float red[8];
+    const int t = blockIdx.x;
+    for (int i = threadIdx.x; i < kPipFft / 2; i += blockDim.x) {
+        float s, c;
+        sincospif(static_cast<float>(i) / static_cast<float>(kPipFft / 2), &s, &c);
+        tw[i] = make_float2(c, -s);
+    }
+    const long long start = static_cast<long long>(t) * kPipHop - kPipFft / 2;
+    for (int i = threadIdx.x; i < kPipFft; i += blockDim.x) {
+        const float w = 0.5f - 0.5f * cospif(2.0f * static_cast<float>(i) / static_cast<float>(kPipFft));  // periodic hann
+        bufA[i] = make_float2(y[reflect_idx(start + i, n)] * w, 0.0f);
+    }
+    __syncthreads();
+    const float2* X = fft_pow2<kPipFft>(bufA, bufB, tw);
+    float* S = reinterpret_cast<float*>(X == bufA ? bufB : bufA);   // the other buffer is free now
+    float mx = 0.0f;
+    for (int k = threadIdx.x; k < kPipBins; k += blockDim.x) {
+        const float m = hypotf(X[k].x, X[k].y);
+        S[k] = m;
+        mx = fmaxf(mx, m);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    const float ref = threshold * mx;
+    const float fhi = fminf(fmax, sr * 0.5f), flo = fmaxf(fmin, 0.0f);
+    for (int k = threadIdx.x; k < kPipBins; k += blockDim.x) {
+        const float s0 = S[k];
+        float p = 0.0f, m = 0.0f;
+        // torch.linspace(0, sr/2, 1025)[k]
+        const float step = (sr * 0.5f) / static_cast<float>(kPipBins - 1);
+        const float fk = k < kPipBins / 2 ? step * static_cast<float>(k) : sr * 0.5f - step * static_cast<float>(kPipBins - 1 - k);
+        if (fk >= flo && fk < fhi) {
+            // localmax(S * (S > ref)): x > left neighbour (0 outside) and x >= right neighbour (0 outside)
+            const float x = s0 > ref ? s0 : 0.0f;
+            const float xl = k > 0 ? (S[k - 1] > ref ? S[k - 1] : 0.0f) : 0.0f;
+            const float xr = k < kPipBins - 1 ? (S[k + 1] > ref ? S[k + 1] : 0.0f) : 0.0f;
+            if (x > xl && x >= xr) {
+                float avg = 0.0f, shift = 0.0f;
+                if (k > 0 && k < kPipBins - 1) {
+                    avg = 0.5f * (S[k + 1] - S[k - 1]);
+                    float sh = 2.0f * s0 - S[k + 1] - S[k - 1];
+                    sh = sh + (fabsf(sh) < 1.17549435e-38f ? 1.0f : 0.0f);
+                    shift = avg / sh;
+                }
+                p = (static_cast<float>(k) + shift) * sr / static_cast<float>(kPipFft);
+                m = s0 + 0.5f * avg * shift;
+            }
+        }
+        pitch[static_cast<long long>(t) * kPipBins + k] = p;
+        mag[static_cast<long long>(t) * kPipBins + k] = m;
+    }
+}
+
+// Single CTA: lower median of mag over pitch > 0 (bitwise bisection on the non-negative float patterns), then the
+// 1/resolution-bin histogram of the pitch residuals relative to the bin grid over mag >= median, first arg-max ->
+// tuning = linspace(-0.5, 0.5, bins + 1)[argmax]   (pitch.py:12-24, 100-120)
+__global__ void __launch_bounds__(1024) tuning_kernel(const float* __restrict__ pitch, const float* __restrict__ mag, long long total,
+                                                      int bins_per_octave, int bins, float* __restrict__ tuning) {
+    __shared__ unsigned long long s_cnt;
+    __shared__ int hist[512];
+    const int tid = threadIdx.x;
+    auto block_count = [&](unsigned int trial, bool count_all) {
+        unsigned long long c = 0;
+        for (long long i = tid; i < total; i += blockDim.x)
+            if (pitch[i] > 0.0f && (count_all || __float_as_uint(mag[i]) < trial)) ++c;
+        __syncthreads();
+        if (tid == 0) s_cnt = 0;
+        __syncthreads();
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((tid & 31) == 0) atomicAdd(&s_cnt, c);
+        __syncthreads();
+        return s_cnt;
+    };
+    const unsigned long long K = block_count(0u, true);
+    if (K == 0) {
+        if (tid == 0) *tuning = 0.0f;
+        return;
+    }
+    const unsigned long long k = (K - 1) / 2;   // torch.median: the lower of the two middle values
+    unsigned int prefix = 0;
+    for (int bit = 30; bit >= 0; --bit) {
+        const unsigned int trial = prefix | (1u << bit);
+        if (block_count(trial, false) <= k) prefix = trial;
+    }
+    const float thr = __uint_as_float(prefix);
+    for (int i = tid; i < bins; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    const float a440 = 440.0f / 16.0f;
+    for (long long i = tid; i < total; i += blockDim.x) {
+        const float f = pitch[i];
+        if (f > 0.0f && mag[i] >= thr) {
+            float r = static_cast<float>(bins_per_octave) * log2f(f / a440);
+            r = r - floorf(r);                 // python-style % 1.0
+            if (r >= 0.5f) r -= 1.0f;
+            // torch.histc(bins, min=-0.5, max=0.5): bin = (x - min) / (max - min) * bins, x == max in the last bin
+            int b = static_cast<int>((r + 0.5f) * static_cast<float>(bins));
+            if (b >= bins) b = bins - 1;
+            if (b >= 0) atomicAdd(&hist[b], 1);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < bins; ++i)
+            if (hist[i] > hist[best]) best = i;
+        // torch.linspace(-0.5, 0.5, bins + 1)[best]
+        const float step = 1.0f / static_cast<float>(bins);
+        const int steps = bins + 1;
+        *tuning = best < steps / 2 ? -0.5f + step * static_cast<float>(best) : 0.5f - step * static_cast<float>(steps - 1 - best);
+    }
+}
+
+// ---- CENS post-processing: rosa/spectral.py:239-280 after chroma_cqt(norm=False) -----------------------------------
+// L1 normalise each frame -> natural-spline quantiser curve (host-designed knots / coefficients) -> smooth step
+__global__ void cens_quantise_kernel(const float* __restrict__ chroma, int nc, int T, const float* __restrict__ kx,
+                                     const float* __restrict__ coef, int nk, float* __restrict__ q) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nc * T) return;
+    const int t = idx % T;
+    float l1 = 0.0f;
+    for (int c = 0; c < nc; ++c) l1 += fabsf(chroma[c * T + t]);
+    const float v = chroma[idx] / l1;
+    // torch.bucketize(v, kx) - 1 (right=False: first index with kx[i] >= v), clamped to [0, nk - 2]
+    int lo = 0, hi = nk;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (kx[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    int i = lo - 1;
+    i = i < 0 ? 0 : (i > nk - 2 ? nk - 2 : i);
+    const int ni = nk - 1;
+    const float f = v - kx[i];
+    const float w = coef[i] + (coef[ni + i] + (coef[2 * ni + i] + coef[3 * ni + i] * f) * f) * f;
+    // step_function(w, h = 0.25, alpha = 20)
+    const float fl = floorf(w - 0.5f);
+    const float r = (w - 0.5f) - fl - 0.5f;
+    const float m = 1.0f / (1.0f + expf(-20.0f)) - 0.5f;
+    q[idx] = 0.25f * (fl + 1.0f / (2.0f * m) * 1.0f / (1.0f + expf(-40.0f * r)));
+}
+
+// temporal smoothing (zero-padded 'same' correlation with `win`, L taps) and L2 normalisation per frame
+__global__ void cens_smooth_kernel(const float* __restrict__ q, int nc, int T, const float* __restrict__ win, int L,
+                                   float* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    const int left = (L - 1) / 2;   // torch 'same' padding: total L - 1, the extra one on the right for even L
+    float v[16];
+    float ss = 0.0f;
+    for (int c = 0; c < nc; ++c) {
+        float acc = 0.0f;
+        for (int k = 0; k < L; ++k) {
+            const int tt = t + k - left;
+            if (tt >= 0 && tt < T) acc = fmaf(win[k], q[c * T + tt], acc);
+        }
+        v[c] = acc;
+        ss += acc * acc;
+    }
+    const float nrm = sqrtf(ss);
+    for (int c = 0; c < nc; ++c) out[c * T + t] = v[c] / nrm;
+}
+
 size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace
@@ -209,6 +383,44 @@ extern "C" int mb_chroma_cqt(const float* audio, int64_t n, int hop, int n_fft, 
     const int total = n_chroma * T;
     chroma_fold_kernel<<<(total + 255) / 256, 256, 0, stream>>>(C, fold, n_bins, n_chroma, T, threshold, chroma, max_bits);
     if (normalize) chroma_norm_kernel<<<(total + 255) / 256, 256, 0, stream>>>(chroma, total, max_bits);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" size_t mb_tuning_workspace_bytes(int64_t n_samples) {
+    if (n_samples <= 0) return 0;
+    const size_t frames = static_cast<size_t>(n_samples / kPipHop);
+    return 2 * up256(sizeof(float) * frames * kPipBins);
+}
+
+extern "C" int mb_estimate_tuning(const float* audio, int64_t n, float sr, int bins_per_octave, int bins, float* tuning,
+                                  void* workspace, size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(audio && tuning && workspace, "mb_estimate_tuning: null argument");
+    MB_REQUIRE(n >= 4 * kPipFft && n % kPipHop == 0, "mb_estimate_tuning: need a multiple of %d samples (>= %d)", kPipHop, 4 * kPipFft);
+    MB_REQUIRE(bins >= 1 && bins <= 512, "mb_estimate_tuning: %d histogram bins unsupported (1..512)", bins);
+    const size_t need = mb_tuning_workspace_bytes(n);
+    if (workspace_bytes < need) {
+        set_error("mb_estimate_tuning: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+        return MB_ENOMEM;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int frames = static_cast<int>(n / kPipHop);   // stft(center=True) has n / hop + 1 columns, spectrogram() drops the last
+    float* pitch = static_cast<float*>(workspace);
+    float* mag = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + need / 2);
+    piptrack_kernel<<<frames, 256, 0, stream>>>(audio, n, sr, 150.0f, 4000.0f, 0.1f, pitch, mag);
+    tuning_kernel<<<1, 1024, 0, stream>>>(pitch, mag, static_cast<long long>(frames) * kPipBins, bins_per_octave, bins, tuning);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_chroma_cens_post(const float* chroma_raw, int n_chroma, int T, const float* knots_x, const float* coef, int n_knots,
+                                   const float* smooth_win, int win_len, float* scratch, float* out, mb_stream stream_) {
+    MB_REQUIRE(chroma_raw && knots_x && coef && smooth_win && scratch && out, "mb_chroma_cens_post: null argument");
+    MB_REQUIRE(n_chroma >= 1 && n_chroma <= 16 && T > 0 && n_knots >= 2 && win_len >= 1, "mb_chroma_cens_post: bad argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int total = n_chroma * T;
+    cens_quantise_kernel<<<(total + 255) / 256, 256, 0, stream>>>(chroma_raw, n_chroma, T, knots_x, coef, n_knots, scratch);
+    cens_smooth_kernel<<<(T + 127) / 128, 128, 0, stream>>>(scratch, n_chroma, T, smooth_win, win_len, out);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -65,8 +65,8 @@ def c2_latents(num_ws: int = 16, duration_s: float = 30.0, fps: int = 24):
 
 def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 24):
     """Config 2 latents with the audio-reactive part computed ON THE DEVICE by the library's feature kernels:
-    sweep -> resample to sr = 1024*fps (one hop per frame) -> onsets / rms (mb_audio_onsets_rms) and constant-Q
-    chroma of the harmonic component (mb_audio_hpss_component + mb_chroma_cqt) -> Gaussian smoothing ->
+    sweep -> resample to sr = 1024*fps (one hop per frame) -> onsets / rms (mb_audio_onsets_rms) and the chromagram
+    (mb_audio_hpss_component -> mb_estimate_tuning -> mb_chroma_cqt -> mb_chroma_cens_post) -> Gaussian smoothing ->
     chroma-weighted key-latent mix blended by the onset envelope.  Returns (latents [T,num_ws,512] on `device`,
     info dict with the device time of the feature pass)."""
     from .audiovisual import audioreactive as ar
@@ -77,11 +77,11 @@ def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 
     t = np.arange(T * 1024) / sr
     y = torch.from_numpy(np.interp(t, np.arange(len(audio)) / sr_file, audio).astype(np.float32)).to(device)
     ar.onsets_rms(y, sr)                                   # warm-up (allocations, module load, filter design)
-    ar.chroma_cqt(ar.harmonic(y), sr, tuning=0.0)
+    ar.chromagram(y, sr)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     onsets, rms = ar.onsets_rms(y, sr)
-    chroma = ar.chroma_cqt(ar.harmonic(y), sr, tuning=0.0).T.contiguous()   # [T, 12]
+    chroma = ar.chromagram(y, sr).contiguous()   # [T, 12]: harmonic -> tuning estimate -> constant-Q -> CENS
     e1.record()
     torch.cuda.synchronize()
     keys = key_latents(num_ws).to(device)

@@ -288,3 +288,137 @@ def chroma_cqt(y, sr, hop_length=1024, fmin=None, threshold=0.0, tuning=0.0, n_c
     if norm:
         chroma = chroma / chroma.max()
     return chroma
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tuning estimate (rosa/pitch.py:9-120) and CENS chroma (rosa/spectral.py:164-280): the rest of chromagram()
+# (features/audio.py:44).  estimate_tuning is PINNED bit-for-bit against the reference's own function by
+# tests/golden/make_audio_golden.py.  chroma_cens evaluates a natural cubic spline whose coefficients the reference
+# takes from the third-party torchcubicspline (un-pinned in setup.py:104, absent from the checkout): the published
+# algorithm is restated (natural_cubic_coeffs) and checked against scipy's CubicSpline(bc_type="natural") --
+# PARITY UNPINNED against the reference's own call for that stage.
+# ---------------------------------------------------------------------------------------------------------
+def localmax(x):
+    """pitch.py:88-97 (axis 0)."""
+    xp = F.pad(x, (0, 0, 1, 1))
+    return (x > xp[:-2]) & (x >= xp[2:])
+
+
+def piptrack(y, sr, n_fft=2048, fmin=150.0, fmax=4000.0, threshold=0.1):
+    """pitch.py:27-85 with the reference defaults (hop_length=None -> torch.stft's n_fft // 4)."""
+    s = torch.stft(y, n_fft=n_fft, hop_length=None, center=True, window=_win(n_fft, y.device), pad_mode="reflect",
+                   return_complex=True)[:, :-1].abs()
+    fmin = max(fmin, 0)
+    fmax = min(fmax, float(sr) / 2)
+    fft_freqs = torch.linspace(0, float(sr) / 2, int(1 + n_fft // 2))
+    avg = 0.5 * (s[2:] - s[:-2])
+    shift = 2 * s[1:-1] - s[2:] - s[:-2]
+    shift = avg / (shift + (torch.abs(shift) < torch.finfo(shift.dtype).tiny))
+    avg = F.pad(avg, [0, 0, 1, 1], mode="constant")
+    shift = F.pad(shift, [0, 0, 1, 1], mode="constant")
+    dskew = 0.5 * avg * shift
+    pitches = torch.zeros_like(s)
+    mags = torch.zeros_like(s)
+    freq_mask = ((fmin <= fft_freqs) & (fft_freqs < fmax)).reshape((-1, 1))
+    ref_value = threshold * torch.max(s, axis=0).values
+    idx = torch.argwhere(freq_mask & localmax(s * (s > ref_value)))
+    pitches[idx[:, 0], idx[:, 1]] = (idx[:, 0] + shift[idx[:, 0], idx[:, 1]]) * float(sr) / n_fft
+    mags[idx[:, 0], idx[:, 1]] = s[idx[:, 0], idx[:, 1]] + dskew[idx[:, 0], idx[:, 1]]
+    return pitches, mags
+
+
+def pitch_tuning(frequencies, resolution=0.01, bins_per_octave=12):
+    """pitch.py:100-120: histogram peak of the pitch residuals relative to the bin grid."""
+    import numpy as np
+
+    frequencies = torch.atleast_1d(frequencies)
+    frequencies = frequencies[frequencies > 0]
+    if not torch.any(frequencies):
+        return 0.0
+    residual = (bins_per_octave * torch.log2(frequencies / (440.0 / 16))) % 1.0
+    residual[residual >= 0.5] -= 1.0
+    bins = int(np.ceil(1.0 / resolution))
+    counts = torch.histc(residual, bins=bins, min=-0.5, max=0.5)
+    tuning = torch.linspace(-0.5, 0.5, bins + 1)
+    return tuning[torch.argmax(counts)]
+
+
+def estimate_tuning(y, sr, n_fft=2048, resolution=0.01, bins_per_octave=12):
+    """pitch.py:9-24."""
+    pitch, mag = piptrack(y, sr, n_fft=n_fft)
+    pitch_mask = pitch > 0
+    threshold = torch.median(mag[pitch_mask]) if pitch_mask.any() else 0.0
+    return pitch_tuning(pitch[(mag >= threshold) & pitch_mask], resolution=resolution, bins_per_octave=bins_per_octave)
+
+
+def natural_cubic_coeffs(x, y):
+    """Natural cubic spline through (x_i, y_i), float64: per interval S(t) = a + b f + c f^2 + d f^3, f = t - x_i
+    (the form torchcubicspline's NaturalCubicSpline evaluates; spectral.py:189,192-203 consume (x, a, b, c, d))."""
+    import numpy as np
+
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    n = len(x)
+    h = np.diff(x)
+    m = np.zeros(n)  # second derivatives, m_0 = m_{n-1} = 0
+    if n > 2:
+        a_ = np.zeros((n - 2, n - 2))
+        rhs = 6.0 * ((y[2:] - y[1:-1]) / h[1:] - (y[1:-1] - y[:-2]) / h[:-1])
+        for i in range(n - 2):
+            a_[i, i] = 2.0 * (h[i] + h[i + 1])
+            if i > 0:
+                a_[i, i - 1] = h[i]
+            if i < n - 3:
+                a_[i, i + 1] = h[i + 1]
+        m[1:-1] = np.linalg.solve(a_, rhs)
+    a = y[:-1]
+    b = (y[1:] - y[:-1]) / h - h * (2.0 * m[:-1] + m[1:]) / 6.0
+    c = m[:-1] / 2.0
+    d = (m[1:] - m[:-1]) / (6.0 * h)
+    return x, a, b, c, d
+
+
+def cens_quantiser_knots():
+    """spectral.py:164-188: the knots of the smooth 4-step quantisation curve."""
+    import numpy as np
+
+    steps = [0.4, 0.2, 0.1, 0.05]
+    p1, p2, p3, p4 = np.diff(list(reversed(steps + [0])))
+    xs = [torch.linspace(-0.1, 0.025, 101)[:-1], torch.linspace(0.025, p1, 11)[:-1], torch.linspace(p1, p1 + p2, 11)[:-1],
+          torch.linspace(p1 + p2, p1 + p2 + p3, 11)[:-1], torch.linspace(p1 + p2 + p3, 0.5, 11)[:-1], torch.linspace(0.5, 1.1, 100)]
+    ys = torch.cat((0.5 * torch.ones(len(xs[0])), xs[1] / p1, (xs[2] - p1) / p2 + 1, (xs[3] - p1 - p2) / p3 + 2,
+                    (xs[4] - p1 - p2 - p3) / p4 + 3, 4.5 * torch.ones(len(xs[5]))))
+    return torch.cat(xs), ys
+
+
+def spline_quantize(chroma):
+    """spectral.py:192-219: spline_eval on the quantiser knots, then the smooth step function (h = 0.25, alpha = 20)."""
+    import numpy as np
+
+    xs, ys = cens_quantiser_knots()
+    x, a, b, c, d = (torch.from_numpy(np.asarray(v)).float() for v in natural_cubic_coeffs(xs.numpy(), ys.numpy()))
+    index = (torch.bucketize(chroma, x) - 1).clamp(0, len(b) - 1)
+    f = chroma - x[index]
+    w = a[index] + (b[index] + (c[index] + d[index] * f) * f) * f
+    alpha, hq = 20, 0.25
+    r = (w - 0.5) - torch.floor(w - 0.5) - 0.5
+    m = 1 / (1 + np.exp(-alpha)) - 0.5
+    return hq * (torch.floor(w - 0.5) + 1 / (2 * m) * 1 / (1 + torch.exp(-2 * alpha * r)))
+
+
+def chroma_cens(y, sr, hop_length=1024, tuning=None, win_len_smooth=41):
+    """spectral.py:239-280 -> [12, T]."""
+    if tuning is None:
+        tuning = float(estimate_tuning(y, sr, bins_per_octave=36))
+    chroma = chroma_cqt(y, sr, hop_length=hop_length, tuning=tuning, norm=False)
+    chroma = chroma / torch.norm(chroma, p=1, dim=0)
+    q = spline_quantize(chroma)
+    win = torch.hann_window(win_len_smooth + 2)
+    win = win / torch.sum(win)
+    cens = F.conv1d(q.unsqueeze(0), win.tile(12, 1, 1), groups=12, padding="same").squeeze(0)
+    return cens / torch.norm(cens, p=2, dim=0)
+
+
+def chromagram(audio, sr):
+    """features/audio.py:44."""
+    return chroma_cens(harmonic(audio), sr).T

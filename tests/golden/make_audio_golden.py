@@ -56,6 +56,7 @@ sys.modules[eq.__name__] = eq
 ref_audio = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.audio")
 ref_spec = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.spectral")
 ref_beat = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.beat")
+ref_pitch = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.pitch")
 ref_cq = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.rosa.constantq")
 ref_signal = importlib.import_module("maua.audiovisual.audioreactive.signal")
 ref_latent = importlib.import_module("maua.audiovisual.audioreactive.latent")
@@ -105,6 +106,16 @@ with torch.inference_mode():
     chroma_h_ref = ref_spec.chroma_cqt(harm_ref.clone(), sr, tuning=0.0)
     same(OA.chroma_cqt(OA.harmonic(y), sr, tuning=0.0), chroma_h_ref, "chroma_cqt(harmonic)")
 
+    pit_ref, mag_ref = ref_pitch.piptrack(y, sr)
+    pit_o, mag_o = OA.piptrack(y, sr)
+    same(pit_o, pit_ref, "piptrack pitches"); same(mag_o, mag_ref, "piptrack mags")
+    tun_ref = ref_pitch.estimate_tuning(y, sr, bins_per_octave=36)
+    same(torch.as_tensor(OA.estimate_tuning(y, sr, bins_per_octave=36)), torch.as_tensor(tun_ref), "estimate_tuning")
+    tun_h_ref = ref_pitch.estimate_tuning(harm_ref, sr, bins_per_octave=36)
+    same(torch.as_tensor(OA.estimate_tuning(harm_ref, sr, bins_per_octave=36)), torch.as_tensor(tun_h_ref), "estimate_tuning(harmonic)")
+    chroma_tuned_ref = ref_spec.chroma_cqt(harm_ref.clone(), sr, tuning=None, norm=False)   # the reference's own tuning default
+    same(OA.chroma_cqt(harm_ref.clone(), sr, tuning=float(tun_h_ref), norm=False), chroma_tuned_ref, "chroma_cqt(tuning=None)")
+
     env = on_ref[:, 0].clone()
     same(OS.normalize(env), ref_signal.normalize(env), "signal.normalize")
     same(OS.resample(env, 57), ref_signal.resample(env, 57), "signal.resample")
@@ -147,6 +158,7 @@ with torch.inference_mode():
                select_modulo=sel_ref, env=env.clone(),
                noise=dict(mod=mod, blend_noise=nb.noise.clone(), mult_noise=nm.noise.clone(), loop_noise=nl.noise.clone(), loop_idx=nl.idx.clone(),
                           i=i0, b=bsz, blend=nb(i0, bsz), multiply=nm(i0, bsz), loop=nl(i0, bsz), combined=comb_ref),
+               tuning=float(tun_ref), tuning_harmonic=float(tun_h_ref), chroma_cqt_tuned_raw=chroma_tuned_ref,
                keys=keys, chroma=chroma, multi_weighted=mw_ref, slerp_loops=ref_latent.slerp_loops(keys, 60, 2))
 torch.save(out, os.path.join(ROOT, "tests", "golden", "audio.pt"))
 print("oracle == reference on every pinned function; wrote tests/golden/audio.pt",

@@ -169,3 +169,28 @@ def test_noise_sequencers_on_device(cuda):
     comb = NS.ScaleBias(NS.Modulate(NS.Average(nb, nl), nm, mod), 0.7, 0.1)
     out = comb(i, b)
     assert out.shape == (b, 16, 24) and float((out.cpu() - n["combined"]).abs().max()) < 2e-4
+
+
+def test_tuning_and_chromagram_on_device(cuda):
+    """estimate_tuning vs the reference's own values (golden), chroma_cqt with that tuning vs the reference's
+    tuning=None result, chroma_cens / chromagram vs the oracle."""
+    import warnings
+
+    from maua_b200.audiovisual import audioreactive as ar
+
+    warnings.filterwarnings("ignore")
+    y, sr = G["audio_exact"], G["sr"]
+    tun = float(ar.estimate_tuning(y.to(cuda), sr, bins_per_octave=36))
+    assert abs(tun - G["tuning"]) < 1e-6
+    harm = OA.harmonic(y)
+    tun_h = float(ar.estimate_tuning(harm.to(cuda), sr, bins_per_octave=36))
+    assert abs(tun_h - G["tuning_harmonic"]) < 1e-6
+    raw = ar.chroma_cqt(harm.to(cuda), sr, tuning=tun_h, norm=False).cpu()
+    assert float((raw - G["chroma_cqt_tuned_raw"]).abs().max()) < 2e-5 * float(G["chroma_cqt_tuned_raw"].max())
+    ref = OA.chroma_cens(harm, sr)
+    got = ar.chroma_cens(harm.to(cuda), sr).cpu()
+    assert got.shape == ref.shape == (12, len(G["onsets"]))
+    assert float((got - ref).abs().max()) < 2e-3        # the smooth step has slope ~10 per unit: 1e-4 in, 1e-3 out
+    cg = ar.chromagram(y.to(cuda), sr).cpu()
+    assert cg.shape == (len(G["onsets"]), 12) and float((cg - OA.chromagram(y, sr)).abs().max()) < 3e-3
+    assert float((cg.norm(dim=1) - 1).abs().max()) < 1e-5

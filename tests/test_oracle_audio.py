@@ -92,3 +92,27 @@ def test_sequencers_match_reference_vectors_and_scipy():
     ref = CubicSpline(np.linspace(0, 1, len(y)), y, bc_type="natural")(np.linspace(0, 1, size))
     assert got.shape == (size, 4, 8)
     assert float(np.abs(got.reshape(size, -1).numpy() - ref).max()) < 1e-5
+
+
+def test_tuning_estimate_and_cens_quantiser():
+    """estimate_tuning vs the reference's own value; the CENS quantiser spline (third-party in the reference) vs scipy's
+    natural CubicSpline; the product's host design equals the oracle's."""
+    import numpy as np
+    from scipy.interpolate import CubicSpline
+
+    from maua_b200.audiovisual.audioreactive import chroma as CH
+
+    y, sr = G["audio_exact"], G["sr"]
+    assert float(OA.estimate_tuning(y, sr, bins_per_octave=36)) == G["tuning"]
+    xs, ys = OA.cens_quantiser_knots()
+    x, a, b, c, d = OA.natural_cubic_coeffs(xs.numpy(), ys.numpy())
+    ref = CubicSpline(xs.double().numpy(), ys.double().numpy(), bc_type="natural")
+    t = np.linspace(-0.09, 1.09, 4001)
+    i = np.clip(np.searchsorted(x, t, side="left") - 1, 0, len(a) - 1)
+    f = t - x[i]
+    assert np.abs(a[i] + (b[i] + (c[i] + d[i] * f) * f) * f - ref(t)).max() < 1e-9
+    kx, coef = CH.cens_quantiser_design()
+    assert torch.equal(kx, xs.float())
+    assert np.abs(coef.numpy() - np.stack([a, b, c, d]).astype(np.float32)).max() == 0.0
+    q = OA.spline_quantize(torch.tensor([[0.0, 0.03, 0.07, 0.15, 0.3, 0.6, 1.0]]))
+    assert torch.allclose(q, torch.tensor([[0.0, 0.0, 0.25, 0.5, 0.75, 1.0, 1.0]]), atol=2e-3)   # the 4-step CENS staircase

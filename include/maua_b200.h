@@ -258,6 +258,18 @@ int mb_noise_loop(const float* idx, const float* noise, int B, int P, float sigm
 int mb_noise_combine(const float* x, const float* y, const float* mx, const float* my, int one_minus, float a, float c,
                      float bias, int B, int P, float* out, mb_stream stream);
 
+/* ---- image-space helpers (planar float32 [planes, h, w]) -----------------------------------------------------
+ * mb_resize_bicubic: F.interpolate(mode="bicubic", align_corners=...) as maua/ops/image.py:240 (resample, True) and
+ *   maua/GAN/wrappers/stylegan2.py:205 (make_noise_pyramid, False) call it;
+ * mb_fir_reflect: the separable Lanczos prefilter of resample (image.py:228-238): 1-D FIR along H (axis 0) or W (axis 1),
+ *   reflect padding (n_taps - 1) / 2;
+ * mb_std_normalize: x[s] /= std(x[s]) (unbiased), stylegan2.py:212;
+ * mb_perlin_noise: maua/ops/noise.py:27-88 for host-drawn unit gradients [r0+1, r1+1, r2+1, 3] -> [s0, s1, s2] in [-1, 1]. */
+int mb_resize_bicubic(const float* x, float* y, int planes, int h, int w, int out_h, int out_w, int align_corners, mb_stream stream);
+int mb_fir_reflect(const float* x, float* y, int planes, int h, int w, const float* taps, int n_taps, int axis, mb_stream stream);
+int mb_std_normalize(float* x, int samples, int64_t per_sample, mb_stream stream);
+int mb_perlin_noise(const float* gradients, int s0, int s1, int s2, int r0, int r1, int r2, float* out, mb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,6 +9,8 @@ import warnings
 from typing import Optional, Tuple
 
 import torch
+
+from ... import ops
 from torch import Tensor
 
 from ..networks import stylegan2
@@ -79,7 +81,7 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
                             f"shape is {c.noise_const.shape}. Resizing the supplied noise to match..."
                         )
                         h, w = c.noise_const.shape[-2], c.noise_const.shape[-1]
-                        noise_l = torch.nn.functional.interpolate(noise_l, (h, w), mode="bicubic", align_corners=False)
+                        noise_l = ops.resize_bicubic(noise_l, (h, w), align_corners=False)
                     setattr(c, "noise_const", noise_l)
                     l += 1
         return self.G_synth.forward(latents, noise_mode="const")
@@ -101,8 +103,8 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
             _, block, conv = layer.split(".")
             synth_layer = getattr(self.G_synth.bs[int(block)], conv)
             h, w = synth_layer.noise_const.shape[-2], synth_layer.noise_const.shape[-1]
-            noises[f"noise{l}"] = torch.nn.functional.interpolate(noise, (h, w), mode="bicubic", align_corners=False).cpu()
-            noises[f"noise{l}"] /= noises[f"noise{l}"].std((1, 2, 3), keepdim=True)
+            # bicubic resize and unit-std normalisation on the device (stylegan2.py:203-212), returned on the host like the reference
+            noises[f"noise{l}"] = ops.std_normalize_(ops.resize_bicubic(noise.cuda(), (h, w), align_corners=False)).cpu()
         return noises
 
 

@@ -80,6 +80,10 @@ _SIGNATURES = {
     "mb_noise_mix": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "mb_noise_loop": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "mb_noise_combine": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, _P, _P]),
+    "mb_resize_bicubic": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "mb_fir_reflect": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "mb_std_normalize": (C.c_int, [_P, C.c_int, C.c_int64, _P]),
+    "mb_perlin_noise": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "mb_debug_read": (C.c_int, [C.POINTER(C.c_int), C.c_int]),
     "mb_modulated_conv2d": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_float, C.c_int, _P]),

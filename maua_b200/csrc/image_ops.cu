@@ -1,0 +1,188 @@
+// Image-space helpers of the render path (rows a12 / a22 of SURVEY §8a):
+//   maua/ops/image.py:214-240 resample: separable Lanczos-2 prefilter (reflect padding) when shrinking, then bicubic
+//     interpolation with align_corners=True (MauaPatch.force_output_size);
+//   maua/GAN/wrappers/stylegan2.py:196-213 make_noise_pyramid: bicubic resize (align_corners=False) of a noise map to
+//     each layer's noise size, divided by its per-sample standard deviation;
+//   maua/ops/noise.py:27-88 perlin_noise: 3-D gradient noise from host-drawn gradient angles.
+// The bicubic kernel follows torch's upsample_bicubic2d (A = -0.75, source index NOT clamped, taps clamped to the
+// image), so F.interpolate(mode="bicubic") -- what the reference calls -- is the parity target.  Planar float32.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace mb {
+namespace {
+
+__device__ __forceinline__ void cubic_w(float t, float (&w)[4]) {
+    const float A = -0.75f;
+    const float x0 = t + 1.0f, x3 = 2.0f - t, x2 = 1.0f - t;
+    w[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+    w[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+    w[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+    w[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+
+__global__ void bicubic_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int h, int w, int oh, int ow,
+                               int align_corners) {
+    const long long total = static_cast<long long>(planes) * oh * ow;
+    const float sh = align_corners ? (oh > 1 ? static_cast<float>(h - 1) / static_cast<float>(oh - 1) : 0.0f)
+                                   : static_cast<float>(h) / static_cast<float>(oh);
+    const float sw = align_corners ? (ow > 1 ? static_cast<float>(w - 1) / static_cast<float>(ow - 1) : 0.0f)
+                                   : static_cast<float>(w) / static_cast<float>(ow);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % ow);
+        const int oy = static_cast<int>((idx / ow) % oh);
+        const long long pl = idx / (static_cast<long long>(ow) * oh);
+        const float ry = align_corners ? sh * static_cast<float>(oy) : sh * (static_cast<float>(oy) + 0.5f) - 0.5f;
+        const float rx = align_corners ? sw * static_cast<float>(ox) : sw * (static_cast<float>(ox) + 0.5f) - 0.5f;
+        const float fy = floorf(ry), fx = floorf(rx);
+        const int iy = static_cast<int>(fy), ix = static_cast<int>(fx);
+        float wy[4], wx[4];
+        cubic_w(ry - fy, wy);
+        cubic_w(rx - fx, wx);
+        const float* src = x + pl * h * w;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int yy = min(max(iy - 1 + j, 0), h - 1);
+            float row = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int xx = min(max(ix - 1 + i, 0), w - 1);
+                row += wx[i] * src[yy * w + xx];
+            }
+            acc += wy[j] * row;
+        }
+        y[idx] = acc;
+    }
+}
+
+// 1-D FIR along H (axis = 0) or W (axis = 1) with torch 'reflect' padding of (taps - 1) / 2 on both sides
+__global__ void fir_reflect_kernel(const float* __restrict__ x, float* __restrict__ y, int planes, int h, int w, const float* __restrict__ k,
+                                   int taps, int axis) {
+    const long long total = static_cast<long long>(planes) * h * w;
+    const int pad = (taps - 1) / 2;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int xx = static_cast<int>(idx % w);
+        const int yy = static_cast<int>((idx / w) % h);
+        const float* src = x + (idx / (static_cast<long long>(w) * h)) * h * w;
+        const int n = axis == 0 ? h : w;
+        float acc = 0.0f;
+        for (int t = 0; t < taps; ++t) {
+            int p = (axis == 0 ? yy : xx) + t - pad;
+            if (p < 0) p = -p;
+            if (p >= n) p = 2 * (n - 1) - p;
+            acc = fmaf(k[t], axis == 0 ? src[p * w + xx] : src[yy * w + p], acc);
+        }
+        y[idx] = acc;
+    }
+}
+
+// x[s, :] /= std(x[s, :]) (unbiased, as torch.std); one CTA per sample, two-pass mean / variance
+__global__ void __launch_bounds__(256) std_normalize_kernel(float* __restrict__ x, long long per) {
+    __shared__ float red[8];
+    __shared__ float s_val;
+    float* p = x + blockIdx.x * per;
+    auto bsum = [&](float v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.0f;
+            for (int i = 0; i < 8; ++i) s += red[i];
+            s_val = s;
+        }
+        __syncthreads();
+        return s_val;
+    };
+    float s = 0.0f;
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) s += p[i];
+    const float mean = bsum(s) / static_cast<float>(per);
+    float v = 0.0f;
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+        const float d = p[i] - mean;
+        v += d * d;
+    }
+    const float sd = sqrtf(bsum(v) / static_cast<float>(per - 1));
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) p[i] = p[i] / sd;
+}
+
+// perlin_noise (ops/noise.py:27-88): grad [r0+1][r1+1][r2+1][3] unit gradients (tileable wrap already applied by the host)
+__global__ void perlin_kernel(const float* __restrict__ grad, int s0, int s1, int s2, int r0, int r1, int r2, float* __restrict__ out) {
+    const long long total = static_cast<long long>(s0) * s1 * s2;
+    const int d0 = s0 / r0, d1 = s1 / r1, d2 = s2 / r2;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int k = static_cast<int>(idx % s2), j = static_cast<int>((idx / s2) % s1), i = static_cast<int>(idx / (static_cast<long long>(s2) * s1));
+        // np.mgrid[0:res:delta] % 1 in float32: position inside the lattice cell
+        float g[3];
+        const int ii[3] = {i, j, k};
+        const int ss[3] = {s0, s1, s2}, rr[3] = {r0, r1, r2};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float pos = static_cast<float>(static_cast<double>(ii[a]) * (static_cast<double>(rr[a]) / ss[a]));
+            g[a] = pos - floorf(pos);
+        }
+        const int c0 = i / d0, c1 = j / d1, c2 = k / d2;
+        auto dotg = [&](int a, int b, int c) {
+            const float* gv = grad + ((static_cast<long long>(c0 + a) * (r1 + 1) + (c1 + b)) * (r2 + 1) + (c2 + c)) * 3;
+            return (g[0] - a) * gv[0] + (g[1] - b) * gv[1] + (g[2] - c) * gv[2];
+        };
+        float t[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) t[a] = g[a] * g[a] * g[a] * (g[a] * (g[a] * 6.0f - 15.0f) + 10.0f);
+        const float n00 = dotg(0, 0, 0) * (1.0f - t[0]) + t[0] * dotg(1, 0, 0);
+        const float n10 = dotg(0, 1, 0) * (1.0f - t[0]) + t[0] * dotg(1, 1, 0);
+        const float n01 = dotg(0, 0, 1) * (1.0f - t[0]) + t[0] * dotg(1, 0, 1);
+        const float n11 = dotg(0, 1, 1) * (1.0f - t[0]) + t[0] * dotg(1, 1, 1);
+        const float n0 = (1.0f - t[1]) * n00 + t[1] * n10;
+        const float n1 = (1.0f - t[1]) * n01 + t[1] * n11;
+        out[idx] = ((1.0f - t[2]) * n0 + t[2] * n1) * 2.0f - 1.0f;
+    }
+}
+
+int grid_of(long long total) {
+    long long g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    return g < 1 ? 1 : static_cast<int>(g);
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" int mb_resize_bicubic(const float* x, float* y, int planes, int h, int w, int out_h, int out_w, int align_corners, mb_stream stream) {
+    MB_REQUIRE(x && y && planes > 0 && h > 0 && w > 0 && out_h > 0 && out_w > 0, "mb_resize_bicubic: bad argument");
+    bicubic_kernel<<<grid_of(static_cast<long long>(planes) * out_h * out_w), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, h, w, out_h, out_w,
+                                                                                                                       align_corners);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_fir_reflect(const float* x, float* y, int planes, int h, int w, const float* taps, int n_taps, int axis, mb_stream stream) {
+    MB_REQUIRE(x && y && taps && x != y && planes > 0 && h > 0 && w > 0 && n_taps > 0 && (axis == 0 || axis == 1), "mb_fir_reflect: bad argument");
+    MB_REQUIRE((n_taps - 1) / 2 < (axis == 0 ? h : w), "mb_fir_reflect: reflect padding %d does not fit the axis", (n_taps - 1) / 2);
+    fir_reflect_kernel<<<grid_of(static_cast<long long>(planes) * h * w), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, planes, h, w, taps, n_taps, axis);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_std_normalize(float* x, int samples, int64_t per_sample, mb_stream stream) {
+    MB_REQUIRE(x && samples > 0 && per_sample > 1, "mb_std_normalize: bad argument");
+    std_normalize_kernel<<<samples, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, per_sample);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_perlin_noise(const float* gradients, int s0, int s1, int s2, int r0, int r1, int r2, float* out, mb_stream stream) {
+    MB_REQUIRE(gradients && out && r0 > 0 && r1 > 0 && r2 > 0 && s0 % r0 == 0 && s1 % r1 == 0 && s2 % r2 == 0,
+               "mb_perlin_noise: shape must be a multiple of res");
+    perlin_kernel<<<grid_of(static_cast<long long>(s0) * s1 * s2), 256, 0, static_cast<cudaStream_t>(stream)>>>(gradients, s0, s1, s2, r0, r1, r2, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}

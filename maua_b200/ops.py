@@ -61,3 +61,88 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=2 
                                          int(up), int(down), up_taps, down_taps, fd_2d, px0, px1, py0, py1, float(gain),
                                          float(slope), float(-1 if clamp is None else clamp), _lib.stream_ptr()))
     return y
+
+
+# ---- image-space helpers (csrc/image_ops.cu) ---------------------------------------------------------------------
+def resize_bicubic(x, size, align_corners=False):
+    """F.interpolate(x, size, mode="bicubic", align_corners=...) on the device kernels: x [N,C,h,w] -> [N,C,H,W]."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "x")
+    n, c, h, w = x.shape
+    oh, ow = int(size[0]), int(size[1])
+    y = torch.empty(n, c, oh, ow, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mb_resize_bicubic(_lib.ptr(x), _lib.ptr(y), n * c, h, w, oh, ow, int(bool(align_corners)), _lib.stream_ptr()))
+    return y
+
+
+def std_normalize_(x):
+    """x /= x.std((1, 2, 3), keepdim=True) in place (maua/GAN/wrappers/stylegan2.py:212)."""
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise RuntimeError("std_normalize_: contiguous float32 CUDA tensor required")
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mb_std_normalize(_lib.ptr(x), x.shape[0], x[0].numel(), _lib.stream_ptr()))
+    return x
+
+
+def _lanczos_taps(ratio, a=2):
+    """lanczos(ramp(ratio, 2), 2) of maua/ops/image.py:196-211 (host design of the prefilter taps)."""
+    import math
+
+    n = math.ceil(2 / ratio + 1)
+    out = torch.empty([n])
+    cur = 0
+    for i in range(n):
+        out[i] = cur
+        cur += ratio
+    x = torch.cat([-out[1:].flip([0]), out])[1:-1]
+    sinc = lambda v: torch.where(v != 0, torch.sin(math.pi * v) / (math.pi * v), v.new_ones([]))  # noqa: E731
+    cond = torch.logical_and(-a < x, x < a)
+    k = torch.where(cond, sinc(x) * sinc(x / a), x.new_zeros([]))
+    return (k / k.sum()).contiguous()
+
+
+def resample(input, size, align_corners=True):
+    """maua/ops/image.py:214-240: Lanczos-2 prefilter along each shrinking axis (reflect padding), then bicubic."""
+    lib = _lib.load()
+    x = _cuda_f32(input, "input")
+    n, c, h, w = x.shape
+    if isinstance(size, (int, float)):
+        short, long = (w, h) if w <= h else (h, w)
+        new_short, new_long = round(size), round(size * long / short)
+        dw, dh = (new_short, new_long) if w <= h else (new_long, new_short)
+    else:
+        dh, dw = size
+    with torch.cuda.device(x.device):
+        for axis, (dst, src) in enumerate(((dh, h), (dw, w))):
+            if dst < src:
+                k = _lanczos_taps(dst / src).to(x.device)
+                y = torch.empty_like(x)
+                _lib.check(lib.mb_fir_reflect(_lib.ptr(x), _lib.ptr(y), n * c, h, w, _lib.ptr(k), k.numel(), axis, _lib.stream_ptr()))
+                x = y
+    return resize_bicubic(x, (dh, dw), align_corners=align_corners)
+
+
+def perlin_noise(shape, res, tileable=(True, False, False), rng=None):
+    """maua/ops/noise.py:27-88: 3-D gradient noise [shape] in [-1, 1] on the device.  Gradient angles are drawn on the host
+    from `rng` (np.random by default, exactly as the reference draws them); `res` must divide `shape` (the reference snaps
+    it to the closest divisor with a random tie-break, ops/noise.py:14-20: pass an exact divisor)."""
+    import numpy as np
+
+    if any(s % r for s, r in zip(shape, res)):
+        raise ValueError("perlin_noise: res must divide shape")
+    rnd = np.random if rng is None else rng
+    theta = 2 * np.pi * rnd.rand(res[0] + 1, res[1] + 1, res[2] + 1).astype(np.float32)
+    phi = 2 * np.pi * rnd.rand(res[0] + 1, res[1] + 1, res[2] + 1).astype(np.float32)
+    g = np.stack((np.sin(phi) * np.cos(theta), np.sin(phi) * np.sin(theta), np.cos(phi)), axis=3)
+    if tileable[0]:
+        g[-1, :, :] = g[0, :, :]
+    if tileable[1]:
+        g[:, -1, :] = g[:, 0, :]
+    if tileable[2]:
+        g[:, :, -1] = g[:, :, 0]
+    grad = torch.from_numpy(np.ascontiguousarray(g.astype(np.float32))).cuda()
+    out = torch.empty(tuple(shape), device=grad.device)
+    with torch.cuda.device(grad.device):
+        _lib.check(_lib.load().mb_perlin_noise(_lib.ptr(grad), shape[0], shape[1], shape[2], res[0], res[1], res[2], _lib.ptr(out), _lib.stream_ptr()))
+    return out

@@ -36,7 +36,18 @@ class MauaPatch:
     def force_output_size(self, video):
         t, c, h, w = video.shape
         if (w, h) != tuple(self.synthesizer.output_size):
-            raise NotImplementedError("output resampling (maua/ops/image.py:214-240) is not built yet (SURVEY §8a a22)")
+            # Lanczos-prefiltered bicubic resampling on the device (patches/base/__init__.py:21-25, ops/image.py:214-240)
+            from .... import ops
+
+            ow, oh = self.synthesizer.output_size
+            if not torch.is_tensor(video):
+                import numpy as np
+
+                video = torch.from_numpy(np.ascontiguousarray(video))
+            frames = video.to(self.device)
+            scale = 255.0 if frames.dtype == torch.uint8 else 1.0
+            out = ops.resample(frames.float() / scale, (oh, ow))
+            video = (out.clamp(0, 1) * 255).round().to(torch.uint8) if scale == 255.0 else out
         return video
 
 

@@ -116,6 +116,7 @@ int mb_net_finalize(mb_net* net, mb_stream stream);
 size_t mb_net_workspace_bytes(const mb_net* net, int batch);
 
 #define MB_OUT_F32_NCHW 0 /* float32 [B,3,H,W], the synthesizer's raw output (~[-1,1]) */
+#define MB_OUT_F32_NCHW_01 1 /* float32 [B,3,H,W] = clamp((x+1)/2, 0, 1): what MauaGenerator.render yields (wrappers/__init__.py:93) */
 #define MB_OUT_U8_NHWC 2  /* uint8 [B,H,W,3] = round(clamp((x+1)/2,0,1)*255): the
                              tensor2bytes() wire format of maua/ops/io.py:47-70 */
 

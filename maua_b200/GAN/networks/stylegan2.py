@@ -193,8 +193,8 @@ class SynthesisNetwork(NativeNet):
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
             res = self.img_resolution
-            if out_fmt == "f32":
-                fmt = _lib.MB_OUT_F32_NCHW
+            if out_fmt in ("f32", "f32_01"):
+                fmt = _lib.MB_OUT_F32_NCHW if out_fmt == "f32" else _lib.MB_OUT_F32_NCHW_01
                 if out is None:
                     out = torch.empty(B, self.img_channels, res, res, device=device, dtype=torch.float32)
             elif out_fmt == "u8":
@@ -202,7 +202,7 @@ class SynthesisNetwork(NativeNet):
                 if out is None:
                     out = torch.empty(B, res, res, self.img_channels, device=device, dtype=torch.uint8)
             else:
-                raise ValueError("out_fmt must be 'f32' or 'u8'")
+                raise ValueError("out_fmt must be 'f32', 'f32_01' or 'u8'")
             wsb, off, nbytes = self._get_workspace(B, device)
             _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
                                           C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))

@@ -83,7 +83,8 @@ class MauaGenerator(torch.nn.Module):
 
             it = tqdm(it, smoothing=0.8, unit_scale=batch_size, unit="img")
         for batch in it:
-            frame_batch = self.synthesizer.forward(**batch).add(1).div(2).clamp(0, 1)
+            # (x + 1) / 2 .clamp(0, 1) of the reference (:93) is fused into the network's last kernel (MB_OUT_F32_NCHW_01)
+            frame_batch = self.synthesizer.forward(**batch, out_fmt="f32_01")
             frame_batch = postprocess_fn(frame_batch)
             if batched:
                 yield frame_batch

@@ -59,6 +59,7 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
         rotation: Optional[Tensor] = None,
         rotation_layer: int = 7,
         rotation_center: Optional[int] = None,
+        out_fmt: str = "f32",
         **noise,
     ) -> Tensor:
         if translation is not None or zoom is not None or rotation is not None:
@@ -84,7 +85,7 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
                         noise_l = ops.resize_bicubic(noise_l, (h, w), align_corners=False)
                     setattr(c, "noise_const", noise_l)
                     l += 1
-        return self.G_synth.forward(latents, noise_mode="const")
+        return self.G_synth.forward(latents, noise_mode="const", out_fmt=out_fmt)
 
     def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
         self.refresh_model_hooks()

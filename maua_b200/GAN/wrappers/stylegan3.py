@@ -46,15 +46,17 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
         self.change_output_resolution(output_size, strategy, layer)
 
     def forward(
-        self, latents: torch.Tensor = None, translation: torch.Tensor = None, rotation: torch.Tensor = None
+        self, latents: torch.Tensor = None, translation: torch.Tensor = None, rotation: torch.Tensor = None, out_fmt: str = "f32"
     ) -> torch.Tensor:
+        # out_fmt is an extension of the reference signature: "f32_01" fuses render()'s (x+1)/2 .clamp(0,1) into the
+        # last kernel, "u8" also the uint8 conversion of tensor2bytes; the default is the reference's raw ~[-1,1] output
         if translation == 0 and rotation == 0:
             # stabilization trick by @RiversHaveWings and @nshepperd1
             self.G_synth.input.affine.bias.data.add_(self.avg_shift)
             self.G_synth.input.affine.weight.data.zero_()
         elif not (translation is None or rotation is None):
             self.G_synth.input.transform.copy_(make_transform_mat(translation, rotation))
-        return self.G_synth.forward(latents)
+        return self.G_synth.forward(latents, out_fmt=out_fmt)
 
     def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
         self.refresh_model_hooks()

@@ -11,6 +11,7 @@ import os
 from ._build import LIB_PATH
 
 MB_OUT_F32_NCHW = 0
+MB_OUT_F32_NCHW_01 = 1
 MB_OUT_U8_NHWC = 2
 
 

@@ -143,11 +143,15 @@ __global__ void chroma_norm_kernel(float* __restrict__ chroma, int n, const int*
 
 // ---- tuning estimate: rosa/pitch.py:9-120 -----------------------------------------------------------------------
 // piptrack: hann STFT (n_fft 2048, hop 512), parabolic peak interpolation, per-frame relative threshold, band limit;
-// one CTA per frame, the spectrum never leaves shared memory; writes dense pitch / magnitude planes (zeros elsewhere).
+// one CTA per frame, the spectrum never leaves shared memory.  Only the selected (pitch > 0) bins matter downstream and
+// the median / histogram that consume them are order independent, so they are appended to a compact list through one
+// atomic counter instead of being written as dense [frames][1025] planes (the dense form made the single-CTA
+// selection kernel scan 1.5 M zeros 33 times: 6 ms at configs[1]).
 constexpr int kPipFft = 2048, kPipHop = 512, kPipBins = kPipFft / 2 + 1;
 
 __global__ void __launch_bounds__(256) piptrack_kernel(const float* __restrict__ y, long long n, float sr, float fmin, float fmax,
-                                                       float threshold, float* __restrict__ pitch, float* __restrict__ mag) {
+                                                       float threshold, float* __restrict__ pitch, float* __restrict__ mag,
+                                                       unsigned int* __restrict__ count, unsigned int cap) {
     __shared__ float2 bufA[kPipFft];
     __shared__ float2 bufB[kPipFft];
     __shared__ float2 tw[kPipFft / 2];
@@ -202,19 +206,26 @@ __global__ void __launch_bounds__(256) piptrack_kernel(const float* __restrict__
                 m = s0 + 0.5f * avg * shift;
             }
         }
-        pitch[static_cast<long long>(t) * kPipBins + k] = p;
-        mag[static_cast<long long>(t) * kPipBins + k] = m;
+        if (p > 0.0f) {
+            const unsigned int slot = atomicAdd(count, 1u);
+            if (slot < cap) {
+                pitch[slot] = p;
+                mag[slot] = m;
+            }
+        }
     }
 }
 
 // Single CTA: lower median of mag over pitch > 0 (bitwise bisection on the non-negative float patterns), then the
 // 1/resolution-bin histogram of the pitch residuals relative to the bin grid over mag >= median, first arg-max ->
 // tuning = linspace(-0.5, 0.5, bins + 1)[argmax]   (pitch.py:12-24, 100-120)
-__global__ void __launch_bounds__(1024) tuning_kernel(const float* __restrict__ pitch, const float* __restrict__ mag, long long total,
+__global__ void __launch_bounds__(1024) tuning_kernel(const float* __restrict__ pitch, const float* __restrict__ mag,
+                                                      const unsigned int* __restrict__ count, unsigned int cap,
                                                       int bins_per_octave, int bins, float* __restrict__ tuning) {
     __shared__ unsigned long long s_cnt;
     __shared__ int hist[512];
     const int tid = threadIdx.x;
+    const long long total = *count < cap ? *count : cap;
     auto block_count = [&](unsigned int trial, bool count_all) {
         unsigned long long c = 0;
         for (long long i = tid; i < total; i += blockDim.x)
@@ -390,7 +401,7 @@ extern "C" int mb_chroma_cqt(const float* audio, int64_t n, int hop, int n_fft, 
 extern "C" size_t mb_tuning_workspace_bytes(int64_t n_samples) {
     if (n_samples <= 0) return 0;
     const size_t frames = static_cast<size_t>(n_samples / kPipHop);
-    return 2 * up256(sizeof(float) * frames * kPipBins);
+    return 2 * up256(sizeof(float) * frames * kPipBins) + 256;   // worst case every bin selected; + the counter
 }
 
 extern "C" int mb_estimate_tuning(const float* audio, int64_t n, float sr, int bins_per_octave, int bins, float* tuning,
@@ -405,10 +416,14 @@ extern "C" int mb_estimate_tuning(const float* audio, int64_t n, float sr, int b
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int frames = static_cast<int>(n / kPipHop);   // stft(center=True) has n / hop + 1 columns, spectrogram() drops the last
+    const size_t plane = (need - 256) / 2;
     float* pitch = static_cast<float*>(workspace);
-    float* mag = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + need / 2);
-    piptrack_kernel<<<frames, 256, 0, stream>>>(audio, n, sr, 150.0f, 4000.0f, 0.1f, pitch, mag);
-    tuning_kernel<<<1, 1024, 0, stream>>>(pitch, mag, static_cast<long long>(frames) * kPipBins, bins_per_octave, bins, tuning);
+    float* mag = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + plane);
+    unsigned int* count = reinterpret_cast<unsigned int*>(static_cast<uint8_t*>(workspace) + 2 * plane);
+    const unsigned int cap = static_cast<unsigned int>(static_cast<size_t>(frames) * kPipBins);
+    MB_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned int), stream));
+    piptrack_kernel<<<frames, 256, 0, stream>>>(audio, n, sr, 150.0f, 4000.0f, 0.1f, pitch, mag, count, cap);
+    tuning_kernel<<<1, 1024, 0, stream>>>(pitch, mag, count, cap, bins_per_octave, bins, tuning);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

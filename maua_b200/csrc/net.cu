@@ -550,7 +550,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
                               void* workspace, size_t workspace_bytes, mb_stream stream_) {
     MB_REQUIRE(net && ws && out && workspace, "mb_net_forward: null argument");
     MB_REQUIRE(B > 0, "mb_net_forward: batch must be positive");
-    MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
+    MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
     if (net->sg2) {
         MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
         return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, static_cast<cudaStream_t>(stream_));
@@ -695,7 +695,9 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ca.Wp_out = pitch8(hc);
         ca.ksz = g.conv_kernel;
         ca.pad = g.conv_kernel - 1;
-        ca.tile_w = net->conv_tile_w;
+        // 16x16 pixel tiles on the small maps (<= 64^2: a third fewer tiles per wave, measured 0.084 -> 0.061 ms on L0..L2),
+        // 32x8 elsewhere (fewer halo rows per TMA box)
+        ca.tile_w = (net->conv_tile_w == 32 && hc <= 64 && g.conv_kernel == 3) ? 16 : net->conv_tile_w;
         ca.pm_max_cout = net->conv_pm_max;
         ca.narrow_a = net->conv_narrow_a;
         ca.pm_shift = net->conv_pm_shift;

@@ -305,6 +305,9 @@ def run_ours(args):
         tr = json.load(open(traffic_file))
         roof_fl["traffic"] = tr.get("filtered_lrelu_bytes_per_step_b%d" % B)
         roof_conv["traffic"] = tr.get("modulated_conv2d_bytes_per_step_b%d" % B)
+        roof_fl["traffic_note"] = roof_conv["traffic_note"] = (
+            "bytes per step: ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the kernel family's 14 launches of one "
+            "forward (profiles/traffic.json); algorithmic bytes per step = achieved * ms_per_step")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -89,6 +89,32 @@ def test_full_size_frame_matches_oracle(cuda):
     assert out.shape == (1, 3, 1024, 1024)
 
 
+def test_full_size_R_frame_matches_oracle(cuda):
+    """BASELINE.json configs[2] network (StyleGAN3-R 1024^2: 1x1 convs, radial down filters run as separable
+    eigen-terms on the tensor-core chain), one frame."""
+    onet, net = make_pair("R", 1024)
+    torch.manual_seed(3)
+    ws = torch.randn(1, net.num_ws, 512)
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = onet(ws)
+    out = net(ws.to(cuda))
+    err = float((pix(out) - pix(ref)).abs().max())
+    print(f"full-size StyleGAN3-R 1024^2 frame: max-abs pixel error vs oracle {err:.3e}")
+    assert err <= PIX_TOL, err
+
+
+def test_output_formats_are_consistent(cuda):
+    """f32_01 = clamp((f32 + 1) / 2, 0, 1) and u8 = round(255 * f32_01) in NHWC: the conversions fused into the last kernel."""
+    _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    torch.manual_seed(4)
+    ws = torch.randn(2, net.num_ws, 512, device=cuda)
+    raw = net(ws).clone()
+    unit = net(ws, out_fmt="f32_01").clone()
+    u8 = net(ws, out_fmt="u8").clone()
+    assert torch.equal(unit, ((raw + 1) * 0.5).clamp(0, 1))
+    assert torch.equal(u8, (unit * 255).round().to(torch.uint8).permute(0, 2, 3, 1))
+
+
 def test_batch_invariance_and_determinism(cuda):
     _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
     torch.manual_seed(9)

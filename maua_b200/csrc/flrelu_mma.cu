@@ -49,6 +49,15 @@ __device__ __forceinline__ void mma16816_z(float (&c)[4], const uint4& a, uint32
         : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
         : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(0.0f));
 }
+// fp16-accumulator form, C = 0: the two result registers are (row g: cols 2tig, 2tig+1) and (row g+8: same cols) as packed
+// halves -- bit for bit the B fragment the next pass wants, so the up-sampling passes (single k-step, result rounded to
+// fp16 anyway) need neither fp32 accumulators nor F2FP packs (160 of ~1150 issued instructions per tile).
+__device__ __forceinline__ void mma16816_h(uint32_t (&d)[2], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f16.f16.f16.f16 {%0,%1}, {%2,%3,%4,%5}, {%6,%7}, {%8,%8};"
+        : "=r"(d[0]), "=r"(d[1])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "r"(0u));
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __half2 h = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -150,10 +159,7 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
             const __half* src = X + (blk * 8 + g) * kXP + dx + w0 + 2 * tig;
             const uint32_t b0 = *reinterpret_cast<const uint32_t*>(src);
             const uint32_t b1 = *reinterpret_cast<const uint32_t*>(src + 8);
-            float acc[4];
-            mma16816_z(acc, AU[K::var(m)], b0, b1);
-            P1[blk & 1][m][0] = pack2(acc[0], acc[1]);
-            P1[blk & 1][m][1] = pack2(acc[2], acc[3]);
+            mma16816_h(P1[blk & 1][m], AU[K::var(m)], b0, b1);
         }
         if (blk == K::NIB / 2 - 1) dead0();
         if (blk == K::NIB - 1) dead1();
@@ -175,11 +181,11 @@ __device__ __forceinline__ void fir_chain(const __half* X, int dx, const uint4 (
         uint32_t P2[kJB][2];
 #pragma unroll
         for (int nb = 0; nb < kJB; ++nb) {
-            float acc[4];
-            mma16816_z(acc, AU[K::var(j)], P1[wb & 1][nb >> 1][nb & 1], P1[(wb + 1) & 1][nb >> 1][nb & 1]);
-            // activation on the packed halves (an fp32 overflow packs to inf and is clamped all the same)
-            P2[nb][0] = lrelu_clamp2(pack2(acc[0], acc[1]), sl2, cl2);
-            P2[nb][1] = lrelu_clamp2(pack2(acc[2], acc[3]), sl2, cl2);
+            uint32_t t2[2];
+            mma16816_h(t2, AU[K::var(j)], P1[wb & 1][nb >> 1][nb & 1], P1[(wb + 1) & 1][nb >> 1][nb & 1]);
+            // activation on the packed halves (an overflow arrives as inf and is clamped all the same)
+            P2[nb][0] = lrelu_clamp2(t2[0], sl2, cl2);
+            P2[nb][1] = lrelu_clamp2(t2[1], sl2, cl2);
         }
         if constexpr (!RAD) {
             // ---- S3: O3^T[ox m16 block mo][16 rows of strip j], packed as B operands of S4
@@ -1005,14 +1011,15 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
         p.Cp_out = a.Cp_out;
         p.tpw = ntiles < 16 ? 1 : (ntiles < 128 ? 2 : (ntiles < 600 ? 4 : 8));
         // 0: one CTA per (tile run, channel group, frame); 1: persistent CTAs; default: by layer shape (r1 A/B on B200,
-        // scripts/layer_times.py: with TMA-fed input tiles the persistent kernel only wins on the small maps (<= 100^2))
+        // scripts/layer_times.py: the persistent kernel wins up to ~300^2 and on up=2 layers without a partial channel
+        // group, the grid version on the large up=4 layers and on large maps whose last channel group is mostly padding)
         static int forced = -2;
         if (forced == -2) {
             const char* e = getenv("MB_FLRELU_NHWC");
             forced = e ? atoi(e) : -1;
         }
         const bool packable = ceil_div(a.C, kCG) <= 255 && p.tiles_x <= 255 && p.tiles_y <= 255 && a.B <= 255;
-        const bool prefer_p = a.Hout <= 100;
+        const bool prefer_p = a.Hout <= 300 || (UP == 2 && a.C % kCG == 0);
         const int variant = (!packable || radial) ? 0 : (forced >= 0 ? forced : (prefer_p ? 1 : 0));
         // the planar input as a 3-D tensor [B*C][Hin][Win] (row pitch Wp_in): half-tile boxes of (56 halfs, IYT/2 rows)
         CUtensorMap tm_x;

@@ -204,16 +204,19 @@ __global__ void __launch_bounds__(128) input_prep_kernel(InputArgs a) {
 }
 
 constexpr int kInPix = 16;
-// grid (ceil(size*size/16), B), 256 threads: Fourier features for 16 pixels, then the channel mix.
+// grid (ceil(size*size/16), B), 256 threads: Fourier features for 16 pixels, then the channel mix (fp32 FFMA: exact
+// parity with the oracle matters more here than tensor-core speed; the whole layer is 0.7 GFLOP/frame).
+// Features are staged [channel j][16 pixels] so one LDS.128 feeds four FMAs, and a thread owns output channels
+// tid and tid + 256 so every staged value is used twice: 4 LDS + 2 LDG per 32 FMA (was 16 LDS + 1 LDG per 16 FMA).
 __global__ void __launch_bounds__(256) input_feat_kernel(InputArgs a) {
-    extern __shared__ float sm[];  // [kInPix][C]
+    extern __shared__ __align__(16) float sm[];  // [C][kInPix]
     const int b = blockIdx.y;
     const int p0 = blockIdx.x * kInPix;
     const int npix = a.size * a.size;
     const float theta = 0.5f * static_cast<float>(a.size) / a.sampling_rate;
     const float* sc = a.scratch + static_cast<long long>(b) * a.C * 4;
     for (int idx = threadIdx.x; idx < kInPix * a.C; idx += blockDim.x) {
-        const int pl = idx / a.C, j = idx - pl * a.C;
+        const int j = idx / kInPix, pl = idx - j * kInPix;
         const int pix = p0 + pl;
         float v = 0.0f;
         if (pix < npix) {
@@ -226,25 +229,39 @@ __global__ void __launch_bounds__(256) input_feat_kernel(InputArgs a) {
             arg = arg + f.z;
             v = sinf(arg * 6.283185307179586f) * f.w;
         }
-        sm[pl * a.C + j] = v;
+        sm[j * kInPix + pl] = v;
     }
     __syncthreads();
     const float wscale = rsqrtf(static_cast<float>(a.C));
-    for (int cidx = threadIdx.x; cidx < a.C; cidx += blockDim.x) {
-        float acc[kInPix];
+    for (int c0 = threadIdx.x; c0 < a.C; c0 += 2 * blockDim.x) {
+        const int c1 = c0 + blockDim.x;
+        const bool two = c1 < a.C;
+        float acc0[kInPix], acc1[kInPix];
 #pragma unroll
-        for (int i = 0; i < kInPix; ++i) acc[i] = 0.0f;
+        for (int i = 0; i < kInPix; ++i) acc0[i] = acc1[i] = 0.0f;
         for (int j = 0; j < a.C; ++j) {
-            const float wv = a.weightT[static_cast<long long>(j) * a.C + cidx] * wscale;
+            const float* wrow = a.weightT + static_cast<long long>(j) * a.C;
+            const float w0 = wrow[c0] * wscale;
+            const float w1 = two ? wrow[c1] * wscale : 0.0f;
 #pragma unroll
-            for (int i = 0; i < kInPix; ++i) acc[i] = fmaf(sm[i * a.C + j], wv, acc[i]);
+            for (int q = 0; q < kInPix / 4; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(sm + j * kInPix + 4 * q);
+                acc0[4 * q + 0] = fmaf(x.x, w0, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(x.x, w1, acc1[4 * q + 0]);
+                acc0[4 * q + 1] = fmaf(x.y, w0, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(x.y, w1, acc1[4 * q + 1]);
+                acc0[4 * q + 2] = fmaf(x.z, w0, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(x.z, w1, acc1[4 * q + 2]);
+                acc0[4 * q + 3] = fmaf(x.w, w0, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(x.w, w1, acc1[4 * q + 3]);
+            }
         }
-        const float st = a.style ? a.style[static_cast<long long>(b) * a.C + cidx] : 1.0f;
-        __half* o = a.out + static_cast<long long>(b) * npix * a.Cp + cidx;
+        const float st0 = a.style ? a.style[static_cast<long long>(b) * a.C + c0] : 1.0f;
+        const float st1 = (a.style && two) ? a.style[static_cast<long long>(b) * a.C + c1] : 1.0f;
+        __half* o = a.out + static_cast<long long>(b) * npix * a.Cp;
 #pragma unroll
         for (int i = 0; i < kInPix; ++i) {
             const int pix = p0 + i;
-            if (pix < npix) o[static_cast<long long>(pix) * a.Cp] = __float2half_rn(acc[i] * st);
+            if (pix < npix) {
+                o[static_cast<long long>(pix) * a.Cp + c0] = __float2half_rn(acc0[i] * st0);
+                if (two) o[static_cast<long long>(pix) * a.Cp + c1] = __float2half_rn(acc1[i] * st1);
+            }
         }
     }
     // zero the channel padding [C, Cp)

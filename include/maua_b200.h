@@ -122,12 +122,37 @@ size_t mb_net_workspace_bytes(const mb_net* net, int batch);
 
 /* One synthesis forward for `batch` frames.
  *   ws        device float32 [batch, num_ws, w_dim]   (W+ latents, stylegan3.py:51 `latents`)
- *   transform device float32 [3,3] or NULL            (G_synth.input.transform, stylegan3.py:59)
+ *   transform device float32 [3,3] or NULL            (G_synth.input.transform, stylegan3.py:59); see also
+ *             mb_net_forward_xf for one matrix per frame
  *   out       device buffer of out_fmt
  *   workspace device buffer of >= mb_net_workspace_bytes(net, batch) bytes, 1024-aligned
  * Enqueues on `stream` and returns; no allocation, no host sync. */
 int mb_net_forward(mb_net* net, const float* ws, const float* transform, int batch, void* out,
                    int out_fmt, void* workspace, size_t workspace_bytes, mb_stream stream);
+
+/* mb_net_forward with ONE input transform per frame: transforms = device float32 [batch,3,3].  The reference's
+ * make_transform_mat (stylegan3.py:82-93) squeezes its arguments and so only supports one translation / rotation per
+ * call; this entry point lifts that limit for batched audio-reactive translation / rotation
+ * tracks.  StyleGAN3 handles only. */
+int mb_net_forward_xf(mb_net* net, const float* ws, const float* transforms, int batch, void* out,
+                      int out_fmt, void* workspace, size_t workspace_bytes, mb_stream stream);
+
+/* Output-size hook of the StyleGAN3 wrapper (maua/GAN/wrappers/stylegan3.py:62-117 change_output_resolution / get_hook):
+ * the output of one synthesis module is resized and every later layer runs on the resized, possibly non-square map.
+ *   module    0 = SynthesisInput, i = the layer layer_names[i-1] (the reference's `layer` argument); must feed another
+ *             layer of the network (0 <= module <= num_layers; resizing the finished image is the caller's business)
+ *   strategy  MB_RESIZE_NONE removes the hook;
+ *             MB_RESIZE_STRETCH: a, b = target height, width; bicubic, align_corners=False (stylegan3.py:101-104);
+ *             MB_RESIZE_PAD_ZERO: a, b = rows / columns of zeros added on EACH side, negative crops (stylegan3.py:108-115)
+ * Changes mb_net_workspace_bytes and the output shape (mb_net_output_shape).  StyleGAN3 handles only. */
+#define MB_RESIZE_NONE 0
+#define MB_RESIZE_STRETCH 1
+#define MB_RESIZE_PAD_ZERO 2
+int mb_net_set_resize(mb_net* net, int module, int strategy, int a, int b);
+/* Host-only (no device needed): the image size a network of this configuration produces under such a hook. */
+int mb_sg3_resized_output(const mb_sg3_cfg* cfg, int module, int strategy, int a, int b, int32_t* height, int32_t* width);
+/* Height and width of the image mb_net_forward writes (img_resolution unless a resize hook is set). */
+int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width);
 
 /* Debug / parity aid: copy the activation a layer produced during the LAST forward into
  * `out` as float32 [B,C,H,W] (undoing the style pre-multiplication is the caller's business:

@@ -186,8 +186,38 @@ class SynthesisNetwork(NativeNet):
     def _create(self, lib, handle_ref):
         _lib.check(lib.mb_sg3_create(C.byref(self._cfg), handle_ref))
 
+    # ---- output-size hook ---------------------------------------------------------------
+    def set_resize(self, module, strategy=None, a=0, b=0):
+        """Resize the output of one synthesis module (0 = ``input``, i = ``layer_names[i-1]``) inside the forward:
+        what the reference does with ``register_forward_hook(get_hook(...))`` (maua/GAN/wrappers/stylegan3.py:77-78,
+        :96-117).  strategy "stretch": (a, b) = target (height, width), bicubic; "pad-zero": (a, b) = zero rows / columns
+        added on each side (negative crops); None removes the hook."""
+        code = {None: _lib.MB_RESIZE_NONE, "stretch": _lib.MB_RESIZE_STRETCH, "pad-zero": _lib.MB_RESIZE_PAD_ZERO}
+        if strategy not in code:
+            raise Exception(f"Resize strategy not found: {strategy}")
+        self._resize = (int(module), code[strategy], int(a), int(b))
+        self._workspace = {}
+        if self._net is not None:  # otherwise applied when the library handle is created (first forward)
+            _lib.check(_lib.load().mb_net_set_resize(self._net, *self._resize))
+
+    def _handle(self):
+        fresh = self._net is None
+        net = super()._handle()
+        if fresh and getattr(self, "_resize", None) is not None:
+            _lib.check(_lib.load().mb_net_set_resize(net, *self._resize))
+        return net
+
+    def output_hw(self):
+        """(height, width) of the image the next forward writes."""
+        h, w = C.c_int32(), C.c_int32()
+        module, code, a, b = getattr(self, "_resize", None) or (0, _lib.MB_RESIZE_NONE, 0, 0)
+        _lib.check(_lib.load().mb_sg3_resized_output(C.byref(self._cfg), module, code, a, b, C.byref(h), C.byref(w)))  # host only
+        return h.value, w.value
+
     # ---- forward ------------------------------------------------------------------------
-    def forward(self, ws, out_fmt="f32", out=None, **unused):
+    def forward(self, ws, out_fmt="f32", out=None, transforms=None, **unused):
+        """transforms: optional float [B,3,3], one ``input.transform`` per frame (extension of the reference, whose
+        buffer is shared by the batch: maua/GAN/wrappers/stylegan3.py:59)."""
         if not ws.is_cuda:
             raise RuntimeError("maua_b200 SynthesisNetwork.forward needs CUDA latents: there is no CPU path")
         lib = _lib.load()
@@ -201,20 +231,29 @@ class SynthesisNetwork(NativeNet):
                 ws32 = ws32[:, :self.num_ws].contiguous()
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
-            res = self.img_resolution
+            oh, ow = self.output_hw()
             if out_fmt in ("f32", "f32_01"):
                 fmt = _lib.MB_OUT_F32_NCHW if out_fmt == "f32" else _lib.MB_OUT_F32_NCHW_01
-                if out is None:
-                    out = torch.empty(B, self.img_channels, res, res, device=device, dtype=torch.float32)
+                shape, dtype = (B, self.img_channels, oh, ow), torch.float32
             elif out_fmt == "u8":
                 fmt = _lib.MB_OUT_U8_NHWC
-                if out is None:
-                    out = torch.empty(B, res, res, self.img_channels, device=device, dtype=torch.uint8)
+                shape, dtype = (B, oh, ow, self.img_channels), torch.uint8
             else:
                 raise ValueError("out_fmt must be 'f32', 'f32_01' or 'u8'")
+            if out is None:
+                out = torch.empty(shape, device=device, dtype=dtype)
+            elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or out.device != device:
+                raise ValueError(f"out must be a contiguous {dtype} tensor of shape {shape} on {device}")
             wsb, off, nbytes = self._get_workspace(B, device)
-            _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
-                                          C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
+            if transforms is None:
+                _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
+                                              C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
+            else:
+                xf = transforms.detach().to(device=device, dtype=torch.float32).contiguous()
+                if tuple(xf.shape) != (B, 3, 3):
+                    raise ValueError(f"transforms must be [B,3,3] = {(B, 3, 3)}, got {tuple(xf.shape)}")
+                _lib.check(lib.mb_net_forward_xf(self._handle(), _lib.ptr(ws32), _lib.ptr(xf), B, _lib.ptr(out), fmt,
+                                                 C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
         return out
 
 

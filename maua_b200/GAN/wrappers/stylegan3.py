@@ -3,7 +3,11 @@
 Kept verbatim in behaviour: ``layer_multipliers``, ctor arguments, ``forward(latents, translation,
 rotation)`` including the stabilisation trick (:54-57) and ``make_transform_mat`` (:82-93, note the
 reference's matrix has a zero bottom-right entry, so it always takes the pseudo-inverse path).
-Arbitrary output sizes (forward hooks resizing feature maps, :62-117) are row N2 of SURVEY §8f.
+Arbitrary output sizes (:62-117): the reference registers a torch forward hook that resizes one module's output; here
+the same arithmetic decides module and size and the resize runs as a kernel inside ``mb_net_forward``
+(``SynthesisNetwork.set_resize``); ``_hook_handles`` keeps a removable handle so ``refresh_model_hooks`` works unchanged.
+``forward`` additionally accepts a whole batch of translations / rotations (one transform per frame), which the
+reference's ``make_transform_mat`` cannot express (it squeezes its arguments).
 """
 import warnings
 from typing import Optional, Tuple
@@ -50,6 +54,12 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
     ) -> torch.Tensor:
         # out_fmt is an extension of the reference signature: "f32_01" fuses render()'s (x+1)/2 .clamp(0,1) into the
         # last kernel, "u8" also the uint8 conversion of tensor2bytes; the default is the reference's raw ~[-1,1] output
+        batched = (
+            torch.is_tensor(translation) and torch.is_tensor(rotation) and translation.ndim == 2 and translation.shape[0] > 1
+        )
+        if batched:
+            # one transform per frame (not expressible in the reference: make_transform_mat squeezes to one matrix)
+            return self.G_synth.forward(latents, out_fmt=out_fmt, transforms=make_transform_mats(translation, rotation))
         if translation == 0 and rotation == 0:
             # stabilization trick by @RiversHaveWings and @nshepperd1
             self.G_synth.input.affine.bias.data.add_(self.avg_shift)
@@ -60,12 +70,58 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
 
     def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
         self.refresh_model_hooks()
+
         if tuple(output_size) != (self.G_synth.img_resolution, self.G_synth.img_resolution):
-            raise NotImplementedError(
-                "non-native output sizes (feature-map resize hooks, maua/GAN/wrappers/stylegan3.py:62-117) "
-                "are not built yet (SURVEY §8f N2)"
-            )
+            lay_mult = layer_multipliers[self.G_synth.img_resolution][layer]
+
+            unrounded_size = np.array(output_size) / lay_mult + 20
+            size = np.round(unrounded_size).astype(int)
+            if sum(abs(unrounded_size - size)) > 1e-10:
+                warnings.warn(
+                    f"Layer {layer} resizes to multiples of {lay_mult}. --output-size rounded to {lay_mult * (size - 20)}"
+                )
+
+            self._hook_handles.append(install_hook(self.G_synth, layer, size, strategy))
+
         self.output_size = output_size
+
+
+class _ResizeHandle:
+    """Stands in for the torch RemovableHandle the reference keeps in ``_hook_handles`` (wrappers/__init__.py:34-37)."""
+
+    def __init__(self, G_synth):
+        self.G_synth = G_synth
+
+    def remove(self):
+        self.G_synth.set_resize(0, None)
+
+
+def install_hook(G_synth, layer, size, strategy):
+    """get_hook of the reference (stylegan3.py:96-117) as a device-side resize of module `layer`'s output
+    (0 = input, i = layer_names[i-1], exactly the module the reference hooks at :77)."""
+    size = np.flip(size)  # W,H --> H,W
+    if layer > G_synth.num_layers:
+        raise NotImplementedError(
+            "resizing the finished image (layer > num_layers) is not a network hook here: resample the frames instead "
+            "(maua_b200.ops.resample / MauaPatch.force_output_size)"
+        )
+    if strategy == "stretch":
+        G_synth.set_resize(layer, "stretch", int(size[0]), int(size[1]))
+    elif strategy == "pad-zero":
+        original_size = getattr(G_synth, G_synth.layer_names[max(layer - 1, 0)]).out_size
+        pad_h, pad_w = (size - original_size).astype(int) // 2
+        G_synth.set_resize(layer, "pad-zero", int(pad_h), int(pad_w))
+    else:
+        raise Exception(f"Resize strategy not found: {strategy}")
+    return _ResizeHandle(G_synth)
+
+
+def make_transform_mats(translate: torch.Tensor, angle: torch.Tensor) -> torch.Tensor:
+    """make_transform_mat for every row of translate [B,2] / angle [B] or [B,1]: float32 [B,3,3]."""
+    t = translate.detach().cpu().double().reshape(-1, 2)
+    a = angle.detach().cpu().double().reshape(-1)
+    mats = [make_transform_mat(t[i], a[i]) for i in range(t.shape[0])]
+    return torch.stack(mats).to(torch.float32)
 
 
 def make_transform_mat(translate: Tuple[float, float], angle: float) -> torch.Tensor:

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libmaua_b200.so")
-SOURCES = ["net.cu", "conv_tc.cu", "flrelu.cu", "flrelu_sep.cu", "flrelu_mma.cu", "sg3_misc.cu", "sg2.cu", "audio.cu", "chroma.cu", "signal_ops.cu", "sequencers.cu", "image_ops.cu"]
+SOURCES = ["net.cu", "conv_tc.cu", "flrelu.cu", "flrelu_sep.cu", "flrelu_mma.cu", "sg3_misc.cu", "feature_resize.cu", "sg2.cu", "audio.cu", "chroma.cu", "signal_ops.cu", "sequencers.cu", "image_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

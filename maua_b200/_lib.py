@@ -13,6 +13,7 @@ from ._build import LIB_PATH
 MB_OUT_F32_NCHW = 0
 MB_OUT_F32_NCHW_01 = 1
 MB_OUT_U8_NHWC = 2
+MB_RESIZE_NONE, MB_RESIZE_STRETCH, MB_RESIZE_PAD_ZERO = 0, 1, 2
 
 
 class SG3Cfg(C.Structure):
@@ -55,6 +56,10 @@ _SIGNATURES = {
     "mb_net_finalize": (C.c_int, [_P, _P]),
     "mb_net_workspace_bytes": (C.c_size_t, [_P, C.c_int]),
     "mb_net_forward": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, C.c_size_t, _P]),
+    "mb_net_forward_xf": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int, _P, C.c_size_t, _P]),
+    "mb_net_set_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "mb_sg3_resized_output": (C.c_int, [C.POINTER(SG3Cfg), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mb_net_output_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_net_read_activation": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "mb_net_last_launch_count": (C.c_int, [_P]),
     "mb_net_set_conv_impl": (C.c_int, [_P, C.c_int]),

@@ -67,7 +67,8 @@ struct InputArgs {
     const float* ws;          // [B][num_ws][w_dim], uses ws[:,0]
     const float* affine_w;    // [4][w_dim]
     const float* affine_b;    // [4]
-    const float* transform;   // [3][3]
+    const float* transform;   // [3][3] (transform_stride 0) or one matrix per sample [B][3][3] (transform_stride 9)
+    int transform_stride;
     const float* freqs;       // [C][2]
     const float* phases;      // [C]
     const float* weightT;     // [C(j)][C(c)] = weight[c][j] transposed
@@ -104,6 +105,12 @@ int planar_to_nhwc_launch(const __half* x, __half* out, int B, int C, int H, int
 // op-level helper: s -> normalised s (if demodulate), d[b][o]
 int style_demod_launch(const float* s, const float* wsqT, float* s_out, float* d_out, int B, int Cin, int Cout,
                        int demodulate, float input_gain, cudaStream_t stream);
+
+// ---- feature_resize.cu (output-size hooks; mode = MB_RESIZE_STRETCH | MB_RESIZE_PAD_ZERO) -------
+int resize_nhwc_launch(const __half* x, __half* y, int B, int h, int w, int Cp, int oh, int ow, int mode, int pad_t, int pad_l,
+                       int num_sms, cudaStream_t stream);
+int resize_planar_launch(const __half* x, __half* y, int planes, int h, int w, int Wp, int oh, int ow, int Wpo, int mode,
+                         int pad_t, int pad_l, int num_sms, cudaStream_t stream);
 
 // ---- flrelu.cu -------------------------------------------------------------------------
 struct FlreluArgs {

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <map>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -86,6 +87,8 @@ struct mb_net {
     int flrelu_impl = 0;  // 0 = tensor-core chain where supported, 1 = generic loops, 2 = CUDA-core polyphase kernel
     int debug_stop = 1 << 30;
     int last_launches = 0;
+    // output-size hook (mb_net_set_resize): module 0 = input, i = layers[i-1]
+    int resize_module = -1, resize_mode = MB_RESIZE_NONE, resize_a = 0, resize_b = 0;
     // optional per-launch timing (CUDA events on the forward's stream), see mb_net_profile_read
     int profile = 0;
     std::vector<cudaEvent_t> ev_pool;
@@ -198,7 +201,7 @@ extern "C" int mb_sg3_geometry(const mb_sg3_cfg* c, mb_sg3_layer* L, int32_t* in
 // library
 // ---------------------------------------------------------------------------------------
 extern "C" const char* mb_last_error(void) { return g_err.c_str(); }
-extern "C" int mb_abi_version(void) { return 1; }
+extern "C" int mb_abi_version(void) { return 2; }
 
 /* Debug words written by kernels into mapped host memory (enabled by MB_DEBUG=1 before mb_init). */
 extern "C" int mb_debug_read(int* out, int n) {
@@ -451,28 +454,87 @@ extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
 namespace {
 inline int cpad8(int c) { return (c + 15) / 16 * 16; }  // channel pitch: whole 16-channel (32-byte) groups
 struct WsLayout {
-    size_t styles_off, d_off, scratch_off, x_off, y_off, p_off, total;
+    size_t styles_off, d_off, scratch_off, x_off, x2_off, y_off, p_off, total;
     std::vector<size_t> style_l, d_l;  // per-layer float offsets inside styles / d blocks
 };
-// X: channels-last conv input; Y: planar conv output; P: planar filtered_lrelu output.
-WsLayout ws_layout(const mb_net* net, int B) {
+// Feature-map sizes of one forward: the nominal geometry unless an output-size hook is set, in which case every
+// module after the hooked one sees the resized map: conv out = in + k - 1, filtered_lrelu out =
+// (in*up + pad_lo + pad_hi - (up_taps-1) - (down_taps-1) + down-1) / down per axis (upstream filtered_lrelu.py).
+struct LayerSize { int hin, win, hc, wc, hout, wout; };
+struct SizePlan {
+    int in_h, in_w;              // SynthesisInput output after its hook
+    std::vector<LayerSize> l;    // one per layer (ToRGB: hc = hin, hout = hin)
+    int out_h, out_w;
+    bool ok;
+};
+struct ResizeSpec { int module, mode, a, b; };
+void hook_size(const ResizeSpec& rs, int module, int& h, int& w) {
+    if (rs.mode == MB_RESIZE_NONE || rs.module != module) return;
+    if (rs.mode == MB_RESIZE_STRETCH) { h = rs.a; w = rs.b; }
+    else { h += 2 * rs.a; w += 2 * rs.b; }
+}
+SizePlan size_plan_geo(const mb_sg3_layer* geo, int n_layers, int in_size, const ResizeSpec& rs) {
+    SizePlan sp;
+    int h = in_size, w = in_size;
+    sp.ok = true;
+    hook_size(rs, 0, h, w);
+    if (h <= 0 || w <= 0) sp.ok = false;
+    sp.in_h = h; sp.in_w = w;
+    for (int i = 0; i < n_layers; ++i) {
+        const mb_sg3_layer& g = geo[i];
+        LayerSize ls;
+        ls.hin = h; ls.win = w;
+        ls.hc = h + g.conv_kernel - 1; ls.wc = w + g.conv_kernel - 1;
+        const int extra = g.pad_lo + g.pad_hi - (g.up_taps - 1) - (g.down_taps - 1) + (g.down - 1);
+        ls.hout = (ls.hc * g.up + extra) / g.down;
+        ls.wout = (ls.wc * g.up + extra) / g.down;
+        if (ls.hin <= 0 || ls.win <= 0 || ls.hc * g.up + extra <= 0 || ls.wc * g.up + extra <= 0 || ls.hout <= 0 || ls.wout <= 0)
+            sp.ok = false;
+        sp.l.push_back(ls);
+        h = ls.hout; w = ls.wout;
+        if (!g.is_torgb) hook_size(rs, i + 1, h, w);
+        if (h <= 0 || w <= 0) sp.ok = false;
+    }
+    sp.out_h = h; sp.out_w = w;
+    return sp;
+}
+SizePlan size_plan(const mb_net* net) {
+    std::vector<mb_sg3_layer> geo;
+    for (const auto& L : net->layers) geo.push_back(L.g);
+    return size_plan_geo(geo.data(), static_cast<int>(geo.size()), net->in_size,
+                         ResizeSpec{net->resize_module, net->resize_mode, net->resize_a, net->resize_b});
+}
+// X: channels-last conv input (X2: its resized copy when a hook is set); Y: planar conv output; P: planar filtered_lrelu output.
+WsLayout ws_layout(const mb_net* net, int B, const SizePlan& sp) {
     WsLayout w;
     size_t ns = 0, nd = 0;
     size_t max_x = static_cast<size_t>(B) * net->in_size * net->in_size * cpad8(net->in_channels);
+    {
+        const size_t x0 = static_cast<size_t>(B) * sp.in_h * sp.in_w * cpad8(net->in_channels);
+        if (x0 > max_x) max_x = x0;
+    }
     size_t max_y = 0, max_p = 0;
-    for (const auto& L : net->layers) {
+    for (size_t i = 0; i < net->layers.size(); ++i) {
+        const auto& L = net->layers[i];
+        const LayerSize& ls = sp.l[i];
         w.style_l.push_back(ns);
         w.d_l.push_back(nd);
         ns += static_cast<size_t>(B) * L.g.in_channels;
         nd += static_cast<size_t>(B) * L.g.out_channels;
         if (!L.g.is_torgb) {
-            const size_t xin = static_cast<size_t>(B) * L.g.in_size * L.g.in_size * cpad8(L.g.in_channels);
+            const size_t xin = static_cast<size_t>(B) * ls.hin * ls.win * cpad8(L.g.in_channels);
             if (xin > max_x) max_x = xin;
-            const int ho = L.g.in_size + L.g.conv_kernel - 1;
-            const size_t y = static_cast<size_t>(B) * L.g.out_channels * ho * pitch8(ho);
+            // pre-hook output of this layer in channels-last form (what the fused filtered_lrelu writes)
+            const size_t xout = static_cast<size_t>(B) * ls.hout * ls.wout * cpad8(L.g.out_channels);
+            if (xout > max_x) max_x = xout;
+            const size_t y = static_cast<size_t>(B) * L.g.out_channels * ls.hc * pitch8(ls.wc);
             if (y > max_y) max_y = y;
-            const size_t po = static_cast<size_t>(B) * L.g.out_channels * L.g.out_size * pitch8(L.g.out_size);
+            const size_t po = static_cast<size_t>(B) * L.g.out_channels * ls.hout * pitch8(ls.wout);
             if (po > max_p) max_p = po;
+        } else {
+            // a hook on the last conv layer resizes the planar map P into Y
+            const size_t y = static_cast<size_t>(B) * L.g.in_channels * ls.hin * pitch8(ls.win);
+            if (net->resize_mode != MB_RESIZE_NONE && y > max_y) max_y = y;
         }
     }
     size_t off = 0;
@@ -480,6 +542,8 @@ WsLayout ws_layout(const mb_net* net, int B) {
     w.d_off = off; off = round_up_sz(off + nd * sizeof(float), 1024);
     w.scratch_off = off; off = round_up_sz(off + static_cast<size_t>(B) * net->in_channels * 4 * sizeof(float), 1024);
     w.x_off = off; off = round_up_sz(off + max_x * sizeof(__half), 1024);
+    w.x2_off = off;
+    if (net->resize_mode != MB_RESIZE_NONE) off = round_up_sz(off + max_x * sizeof(__half), 1024);
     w.y_off = off; off = round_up_sz(off + max_y * sizeof(__half), 1024);
     w.p_off = off; off = round_up_sz(off + max_p * sizeof(__half), 1024);
     w.total = off;
@@ -490,7 +554,54 @@ WsLayout ws_layout(const mb_net* net, int B) {
 extern "C" size_t mb_net_workspace_bytes(const mb_net* net, int batch) {
     if (!net || batch <= 0) return 0;
     if (net->sg2) return sg2_workspace_bytes(net->sg2, batch);
-    return ws_layout(net, batch).total;
+    const SizePlan sp = size_plan(net);
+    if (!sp.ok) return 0;
+    return ws_layout(net, batch, sp).total;
+}
+
+extern "C" int mb_net_set_resize(mb_net* net, int module, int strategy, int a, int b) {
+    MB_REQUIRE(net && !net->sg2, "mb_net_set_resize: needs a StyleGAN3 handle");
+    if (strategy == MB_RESIZE_NONE) {
+        net->resize_module = -1; net->resize_mode = MB_RESIZE_NONE; net->resize_a = net->resize_b = 0;
+        return MB_OK;
+    }
+    MB_REQUIRE(strategy == MB_RESIZE_STRETCH || strategy == MB_RESIZE_PAD_ZERO, "mb_net_set_resize: unknown strategy %d", strategy);
+    MB_REQUIRE(module >= 0 && module <= net->cfg.num_layers,
+               "mb_net_set_resize: module %d out of range (0 = input .. %d = last layer before ToRGB)", module, net->cfg.num_layers);
+    MB_REQUIRE(strategy != MB_RESIZE_STRETCH || (a > 0 && b > 0), "mb_net_set_resize: stretch needs a positive target size, got %dx%d", a, b);
+    const int om = net->resize_module, os = net->resize_mode, oa = net->resize_a, ob = net->resize_b;
+    net->resize_module = module; net->resize_mode = strategy; net->resize_a = a; net->resize_b = b;
+    if (!size_plan(net).ok) {
+        net->resize_module = om; net->resize_mode = os; net->resize_a = oa; net->resize_b = ob;
+        set_error("mb_net_set_resize: the requested size leaves an empty feature map somewhere in the network");
+        return MB_EINVAL;
+    }
+    return MB_OK;
+}
+
+extern "C" int mb_sg3_resized_output(const mb_sg3_cfg* cfg, int module, int strategy, int a, int b, int32_t* height, int32_t* width) {
+    MB_REQUIRE(cfg && height && width, "mb_sg3_resized_output: null argument");
+    MB_REQUIRE(cfg->num_layers > 0 && cfg->num_layers < kMaxLayers, "mb_sg3_resized_output: bad num_layers");
+    std::vector<mb_sg3_layer> geo(cfg->num_layers + 1);
+    int32_t ch = 0, in_size = 0;
+    const int r = mb_sg3_geometry(cfg, geo.data(), &ch, &in_size, nullptr, nullptr);
+    if (r != MB_OK) return r;
+    MB_REQUIRE(strategy == MB_RESIZE_NONE || (module >= 0 && module <= cfg->num_layers), "mb_sg3_resized_output: module %d out of range", module);
+    const SizePlan sp = size_plan_geo(geo.data(), static_cast<int>(geo.size()), in_size, ResizeSpec{module, strategy, a, b});
+    MB_REQUIRE(sp.ok, "mb_sg3_resized_output: the requested size leaves an empty feature map somewhere in the network");
+    *height = sp.out_h; *width = sp.out_w;
+    return MB_OK;
+}
+
+extern "C" int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width) {
+    MB_REQUIRE(net && height && width, "mb_net_output_shape: null argument");
+    if (net->sg2) {
+        *height = *width = sg2_resolution(net->sg2);
+        return MB_OK;
+    }
+    const SizePlan sp = size_plan(net);
+    *height = sp.out_h; *width = sp.out_w;
+    return MB_OK;
 }
 
 extern "C" int mb_net_set_conv_impl(mb_net* net, int impl) {
@@ -546,8 +657,23 @@ extern "C" int mb_net_profile_read(mb_net* net, float* ms, int32_t* kind, int32_
 // ---------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------
+static int net_forward(mb_net* net, const float* ws, const float* transform, int transform_stride, int B, void* out, int out_fmt,
+                       void* workspace, size_t workspace_bytes, mb_stream stream_);
+
 extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transform, int B, void* out, int out_fmt,
                               void* workspace, size_t workspace_bytes, mb_stream stream_) {
+    return net_forward(net, ws, transform, 0, B, out, out_fmt, workspace, workspace_bytes, stream_);
+}
+
+extern "C" int mb_net_forward_xf(mb_net* net, const float* ws, const float* transforms, int B, void* out, int out_fmt,
+                                 void* workspace, size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(net && !net->sg2, "mb_net_forward_xf: needs a StyleGAN3 handle");
+    MB_REQUIRE(transforms, "mb_net_forward_xf: null transforms");
+    return net_forward(net, ws, transforms, 9, B, out, out_fmt, workspace, workspace_bytes, stream_);
+}
+
+static int net_forward(mb_net* net, const float* ws, const float* transform, int transform_stride, int B, void* out, int out_fmt,
+                       void* workspace, size_t workspace_bytes, mb_stream stream_) {
     MB_REQUIRE(net && ws && out && workspace, "mb_net_forward: null argument");
     MB_REQUIRE(B > 0, "mb_net_forward: batch must be positive");
     MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
@@ -560,7 +686,9 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         return MB_ESTATE;
     }
     MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
-    const WsLayout wl = ws_layout(net, B);
+    const SizePlan sp = size_plan(net);
+    MB_REQUIRE(sp.ok, "mb_net_forward: the output-size hook leaves an empty feature map");
+    const WsLayout wl = ws_layout(net, B, sp);
     if (workspace_bytes < wl.total) {
         set_error("mb_net_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, wl.total);
         return MB_ENOMEM;
@@ -571,6 +699,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     float* dco = reinterpret_cast<float*>(base + wl.d_off);
     float* scratch = reinterpret_cast<float*>(base + wl.scratch_off);
     __half* X = reinterpret_cast<__half*>(base + wl.x_off);
+    __half* X2 = reinterpret_cast<__half*>(base + wl.x2_off);
     __half* Y = reinterpret_cast<__half*>(base + wl.y_off);
     __half* P = reinterpret_cast<__half*>(base + wl.p_off);
     const int nl = static_cast<int>(net->layers.size());
@@ -633,6 +762,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ia.affine_w = net->in_affine_w.dev;
         ia.affine_b = net->in_affine_b.dev;
         ia.transform = transform ? transform : net->in_transform.dev;
+        ia.transform_stride = transform ? transform_stride : 0;
         ia.freqs = net->in_freqs.dev;
         ia.phases = net->in_phases.dev;
         ia.weightT = net->in_weightT;
@@ -657,6 +787,20 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     net->last_act_nhwc = true;
     net->last_act_c = net->in_channels;
     net->last_act_h = net->last_act_w = net->in_size;
+    // output-size hook on the module whose channels-last output sits in X (h x w): resize into X2 and swap
+    auto hook_nhwc = [&](int module, int channels, int h, int w, int oh, int ow) -> int {
+        if (net->resize_mode == MB_RESIZE_NONE || net->resize_module != module) return MB_OK;
+        const int rr = resize_nhwc_launch(X, X2, B, h, w, cpad8(channels), oh, ow, net->resize_mode, net->resize_a, net->resize_b,
+                                          g_num_sms, stream);
+        if (rr != MB_OK) return rr;
+        std::swap(X, X2);
+        launches += 1;
+        prof_mark(4, module - 1);
+        net->last_act = X;
+        net->last_act_h = oh; net->last_act_w = ow;
+        return MB_OK;
+    };
+    if ((r = hook_nhwc(0, net->in_channels, net->in_size, net->in_size, sp.in_h, sp.in_w)) != MB_OK) return r;
     if (net->debug_stop < 0) {
         net->last_launches = launches;
         return MB_OK;
@@ -665,6 +809,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
     for (int i = 0; i < nl; ++i) {
         const LayerState& L = net->layers[i];
         const mb_sg3_layer& g = L.g;
+        const LayerSize& ls = sp.l[i];
         if (g.is_torgb) {
             ToRgbArgs ta;
             ta.x = P;
@@ -672,7 +817,7 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
             ta.bias = L.bias.dev;
             ta.out = out;
             ta.B = B; ta.Cin = g.in_channels; ta.Cout = g.out_channels;
-            ta.H = g.in_size; ta.W = g.in_size; ta.Wp = pitch8(g.in_size);
+            ta.H = ls.hin; ta.W = ls.win; ta.Wp = pitch8(ls.win);
             ta.out_fmt = out_fmt;
             ta.clamp = static_cast<float>(net->cfg.conv_clamp);
             ta.output_scale = static_cast<float>(net->cfg.output_scale);
@@ -690,14 +835,14 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         ca.bias = L.bias.dev;  // the layer bias is added in the conv epilogue (single fp16 rounding)
         ca.y = Y;
         ca.B = B; ca.Cin = g.in_channels; ca.Cout = g.out_channels;
-        ca.Hin = g.in_size; ca.Win = g.in_size; ca.Cp_in = cpad8(g.in_channels);
-        const int hc = g.in_size + g.conv_kernel - 1;
-        ca.Wp_out = pitch8(hc);
+        ca.Hin = ls.hin; ca.Win = ls.win; ca.Cp_in = cpad8(g.in_channels);
+        const int hc = ls.hc, wc = ls.wc;
+        ca.Wp_out = pitch8(wc);
         ca.ksz = g.conv_kernel;
         ca.pad = g.conv_kernel - 1;
         // 16x16 pixel tiles on the small maps (<= 64^2: a third fewer tiles per wave, measured 0.084 -> 0.061 ms on L0..L2),
         // 32x8 elsewhere (fewer halo rows per TMA box)
-        ca.tile_w = (net->conv_tile_w == 32 && hc <= 64 && g.conv_kernel == 3) ? 16 : net->conv_tile_w;
+        ca.tile_w = (net->conv_tile_w == 32 && hc <= 64 && wc <= 64 && g.conv_kernel == 3) ? 16 : net->conv_tile_w;
         ca.pm_max_cout = net->conv_pm_max;
         ca.narrow_a = net->conv_narrow_a;
         ca.pm_shift = net->conv_pm_shift;
@@ -716,8 +861,8 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         memcpy(fa.fu, L.fu.data(), sizeof(fa.fu));
         memcpy(fa.fd, L.fd.data(), sizeof(fa.fd));
         fa.B = B; fa.C = g.out_channels;
-        fa.Hin = hc; fa.Win = hc; fa.Wp_in = pitch8(hc);
-        fa.Hout = g.out_size; fa.Wout = g.out_size; fa.Wp_out = pitch8(g.out_size);
+        fa.Hin = hc; fa.Win = wc; fa.Wp_in = pitch8(wc);
+        fa.Hout = ls.hout; fa.Wout = ls.wout; fa.Wp_out = pitch8(ls.wout);
         fa.up = g.up; fa.down = g.down; fa.up_taps = g.up_taps; fa.down_taps = g.down_taps;
         fa.fd_2d = g.down_radial;
         fa.px0 = g.pad_lo; fa.py0 = g.pad_lo;
@@ -740,15 +885,34 @@ extern "C" int mb_net_forward(mb_net* net, const float* ws, const float* transfo
         net->last_act = fused ? X : P;
         net->last_act_nhwc = fused;
         net->last_act_c = g.out_channels;
-        net->last_act_h = net->last_act_w = g.out_size;
-        if (net->debug_stop <= i) break;
+        net->last_act_h = ls.hout; net->last_act_w = ls.wout;
+        if (net->debug_stop <= i && !(net->resize_mode != MB_RESIZE_NONE && net->resize_module == i + 1)) break;
         if (next_is_conv && !fused) {
-            r = planar_to_nhwc_launch(P, X, B, g.out_channels, g.out_size, g.out_size, pitch8(g.out_size),
+            r = planar_to_nhwc_launch(P, X, B, g.out_channels, ls.hout, ls.wout, pitch8(ls.wout),
                                       cpad8(g.out_channels), stream);
             if (r != MB_OK) return r;
             launches += 1;
             prof_mark(4, i);
+            net->last_act = X;
+            net->last_act_nhwc = true;
         }
+        // output-size hook on this layer (module i + 1)
+        if (next_is_conv) {
+            if ((r = hook_nhwc(i + 1, g.out_channels, ls.hout, ls.wout, sp.l[i + 1].hin, sp.l[i + 1].win)) != MB_OK) return r;
+        } else if (net->resize_mode != MB_RESIZE_NONE && net->resize_module == i + 1) {
+            // the last conv layer feeds the planar ToRGB kernel: resize P into Y and hand Y over
+            const int oh = sp.l[i + 1].hin, ow = sp.l[i + 1].win;
+            r = resize_planar_launch(P, Y, B * g.out_channels, ls.hout, ls.wout, pitch8(ls.wout), oh, ow, pitch8(ow),
+                                     net->resize_mode, net->resize_a, net->resize_b, g_num_sms, stream);
+            if (r != MB_OK) return r;
+            std::swap(P, Y);
+            launches += 1;
+            prof_mark(4, i);
+            net->last_act = P;
+            net->last_act_nhwc = false;
+            net->last_act_h = oh; net->last_act_w = ow;
+        }
+        if (net->debug_stop <= i) break;
     }
     net->last_launches = launches;
     return MB_OK;

@@ -404,6 +404,7 @@ Sg2Ws sg2_ws(const Sg2Net* n, int B) {
 
 size_t sg2_workspace_bytes(const Sg2Net* n, int B) { return sg2_ws(n, B).total; }
 int sg2_num_ws(const Sg2Net* n) { return n->num_ws; }
+int sg2_resolution(const Sg2Net* n) { return n->res; }
 int sg2_last_launches(const Sg2Net* n) { return n->last_launches; }
 void sg2_set_conv_impl(Sg2Net* n, int impl) { n->conv_impl = impl; }
 

@@ -182,7 +182,8 @@ __global__ void __launch_bounds__(128) input_prep_kernel(InputArgs a) {
         // m_rt = m_r @ m_t
         float mrt[9] = {t0, -t1, t0 * (-t2) + (-t1) * (-t3), t1, t0, t1 * (-t2) + t0 * (-t3), 0.f, 0.f, 1.f};
         float u[9];
-        for (int i = 0; i < 9; ++i) u[i] = a.transform ? a.transform[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
+        const float* tf = a.transform ? a.transform + static_cast<long long>(b) * a.transform_stride : nullptr;
+        for (int i = 0; i < 9; ++i) u[i] = tf ? tf[i] : ((i % 4 == 0) ? 1.0f : 0.0f);
         // M = mrt @ u ; keep rows 0,1
         for (int r = 0; r < 2; ++r)
             for (int cidx = 0; cidx < 3; ++cidx)

@@ -60,8 +60,13 @@ def test_no_cpu_fallback(gen):
         gen.synthesizer.G_synth(torch.randn(1, 16, 512))
     with pytest.raises(RuntimeError):
         next(gen.render({"latents": torch.randn(2, 16, 512)}, device="cpu"))
-    with pytest.raises(NotImplementedError):
-        StyleGAN3Synthesizer(None, False, (512, 512), "stretch", 0)
+    # a non-native output size is a host-side decision (hook module + size); rendering it still needs the GPU
+    S = StyleGAN3Synthesizer(None, False, (512, 768), "stretch", 0)
+    assert S.G_synth.output_hw() == (768, 512) and len(S._hook_handles) == 1
+    with pytest.raises(RuntimeError):
+        S(latents=torch.randn(1, 16, 512))
+    S.refresh_model_hooks()
+    assert S.G_synth.output_hw() == (1024, 1024) and S._hook_handles == []
 
 
 def test_mapping_network_matches_oracle():

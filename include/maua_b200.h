@@ -154,6 +154,17 @@ int mb_sg3_resized_output(const mb_sg3_cfg* cfg, int module, int strategy, int a
 /* Height and width of the image mb_net_forward writes (img_resolution unless a resize hook is set). */
 int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width);
 
+/* Network-bending feature-map warps of StyleGAN2Synthesizer (maua/GAN/wrappers/stylegan2.py:65-80,153-194: forward hooks
+ * running kornia translate / scale / rotate with padding_mode="reflection" on the output of layer_names[layer]).
+ * Every forward that follows applies warp i to the activation of `layers[i]` (hook order = array order) until
+ * n_warps = 0 clears them.  kornia is an absent, un-pinned dependency (setup.py:59): its published warp_affine
+ * (affine_grid + bilinear grid_sample, align_corners=True) is what the kernel restates.
+ *   layers    host int32 [n_warps], index into the wrapper's layer_names (0..2*blocks-1; 0 and 1 both name bs.0.conv1)
+ *   inv_mats  device float32 [n_warps, batch, 2, 3]: destination pixel (x, y, 1) -> source pixel, i.e. the inverse of
+ *             the 2x3 matrix kornia builds; caller-owned, must stay valid while the warps are set
+ * Changes mb_net_workspace_bytes.  StyleGAN2 handles only. */
+int mb_sg2_set_warps(mb_net* net, int n_warps, const int32_t* layers, const float* inv_mats, int batch);
+
 /* Debug / parity aid: copy the activation a layer produced during the LAST forward into
  * `out` as float32 [B,C,H,W] (undoing the style pre-multiplication is the caller's business:
  * what is stored is x * style_{next}).  idx = -1 is the SynthesisInput output. */

@@ -177,7 +177,14 @@ class SynthesisNetwork(NativeNet):
         # per-frame noise maps are swapped in on every call by the wrapper (wrappers/stylegan2.py:83-96): always upload
         return name.endswith("noise_const") and t.ndim != 2
 
-    def forward(self, ws, noise_mode="const", out_fmt="f32", out=None, **unused):
+    def layer_resolution(self, layer):
+        """Resolution of the wrapper's layer_names[layer] (maua/GAN/wrappers/stylegan2.py:48-51: entries 0 and 1 are
+        bs.0.conv1, entry 2i / 2i+1 are block i's conv0 / conv1)."""
+        return self.block_resolutions[layer // 2]
+
+    def forward(self, ws, noise_mode="const", out_fmt="f32", out=None, warps=None, **unused):
+        """warps: optional list of (layer, inv_mats float [B,2,3]) feature-map warps applied in list order to the output
+        of layer_names[layer] (the reference's kornia forward hooks, wrappers/stylegan2.py:153-194)."""
         if noise_mode != "const":
             raise ValueError("only noise_mode='const' is built (what the reference wrapper passes, wrappers/stylegan2.py:98)")
         if not ws.is_cuda:
@@ -203,7 +210,22 @@ class SynthesisNetwork(NativeNet):
                     out = torch.empty(B, res, res, self.img_channels, device=device, dtype=torch.uint8)
             else:
                 raise ValueError("out_fmt must be 'f32', 'f32_01' or 'u8'")
-            wsb, off, nbytes = self._get_workspace(B, device)
-            _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
-                                          C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
+            warps = list(warps or [])
+            if bool(warps) != getattr(self, "_warps_on", False):
+                self._workspace = {}  # the warp ping-pong buffers change the workspace size
+                self._warps_on = bool(warps)
+            mats = None
+            if warps:
+                layers = (C.c_int32 * len(warps))(*[int(l) for l, _ in warps])
+                mats = torch.stack([m.detach().to(device=device, dtype=torch.float32).reshape(-1, 2, 3).expand(B, 2, 3)
+                                    for _, m in warps]).contiguous()
+                _lib.check(lib.mb_sg2_set_warps(self._handle(), len(warps), layers, _lib.ptr(mats), B))
+            try:
+                wsb, off, nbytes = self._get_workspace(B, device)
+                _lib.check(lib.mb_net_forward(self._handle(), _lib.ptr(ws32), None, B, _lib.ptr(out), fmt,
+                                              C.c_void_p(wsb.data_ptr() + off), nbytes, _lib.stream_ptr()))
+            finally:
+                if warps:
+                    _lib.check(lib.mb_sg2_set_warps(self._handle(), 0, None, None, 0))
+                    mats.record_stream(torch.cuda.current_stream(device))
         return out

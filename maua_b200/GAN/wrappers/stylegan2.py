@@ -2,9 +2,14 @@
 
 Kept in behaviour: ctor arguments, ``layer_names`` (:48-51), ``modulation_targets``, ``forward(latents, ..., **noise)``
 swapping each SynthesisLayer's ``noise_const`` for the per-frame map of the batch (:81-96, bicubic resize + warning on
-a shape mismatch) and ``make_noise_pyramid`` (:196-213).  The network-bending feature warps (translation / zoom /
-rotation hooks, :153-194) and non-native output sizes (:100-151) are row N2 of SURVEY §8f.
+a shape mismatch) and ``make_noise_pyramid`` (:196-213), and the network-bending feature warps (translation / zoom /
+rotation, :65-80 and :153-194): the reference registers kornia forward hooks on ``layer_names[layer]`` that stay installed
+until the same kind of warp is applied again; here each installed hook is a (layer, matrices) record and the warps run
+as kernels between that layer's activation and its consumers (``mb_sg2_set_warps``), in the order torch would call the
+hooks (re-applying a warp moves it to the end, as remove + register does).  Non-native output sizes (:100-151, which
+inject ``torch.normal`` noise into the resized map) are not built.
 """
+from collections import OrderedDict
 import warnings
 from typing import Optional, Tuple
 
@@ -14,6 +19,7 @@ from ... import ops
 from torch import Tensor
 
 from ..networks import stylegan2
+from . import _warp
 from .stylegan import StyleGAN, StyleGANMapper, StyleGANSynthesizer, load_network
 
 
@@ -23,6 +29,7 @@ class StyleGAN2Mapper(StyleGANMapper):
 
 class StyleGAN2Synthesizer(StyleGANSynthesizer):
     __constants__ = ["w_dim", "num_ws", "layer_names"]
+    _warp_hooks = None  # kind -> (layer, inverse matrices [B,2,3]); insertion order = hook order
 
     def __init__(
         self, model_file: str, inference: bool, output_size: Optional[Tuple[int, int]], strategy: str, layer: int
@@ -46,6 +53,7 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
             "rotation": (1,),
         }
         self.translate_hook, self.rotate_hook, self.zoom_hook = None, None, None
+        self._warp_hooks = OrderedDict()
         self.change_output_resolution(output_size, strategy, layer)
 
     def forward(
@@ -62,11 +70,12 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
         out_fmt: str = "f32",
         **noise,
     ) -> Tensor:
-        if translation is not None or zoom is not None or rotation is not None:
-            raise NotImplementedError(
-                "feature-map translation / zoom / rotation (kornia hooks, maua/GAN/wrappers/stylegan2.py:153-194) "
-                "are not built yet (SURVEY §8f N2)"
-            )
+        if translation is not None:
+            self.apply_translation(translation_layer, translation)
+        if zoom is not None:
+            self.apply_zoom(zoom_layer, zoom, zoom_center)
+        if rotation is not None:
+            self.apply_rotation(rotation_layer, rotation, rotation_center)
         if noise:
             noises, l = list(noise.values()), 0
             for block in self.G_synth.bs:
@@ -85,7 +94,37 @@ class StyleGAN2Synthesizer(StyleGANSynthesizer):
                         noise_l = ops.resize_bicubic(noise_l, (h, w), align_corners=False)
                     setattr(c, "noise_const", noise_l)
                     l += 1
-        return self.G_synth.forward(latents, noise_mode="const", out_fmt=out_fmt)
+        return self.G_synth.forward(latents, noise_mode="const", out_fmt=out_fmt, warps=list((self._warp_hooks or {}).values()))
+
+    def _install_warp(self, kind, layer, inv_mats):
+        if self._warp_hooks is None:
+            self._warp_hooks = OrderedDict()
+        self._warp_hooks.pop(kind, None)  # hook.remove() + register_forward_hook: the new hook runs last
+        self._warp_hooks[kind] = (int(layer), inv_mats)
+        return kind
+
+    def remove_warps(self):
+        """Drop every installed translation / zoom / rotation warp (the reference keeps them until overwritten)."""
+        self._warp_hooks = OrderedDict()
+        self.translate_hook, self.rotate_hook, self.zoom_hook = None, None, None
+
+    def apply_translation(self, layer, translation):
+        r = self.G_synth.layer_resolution(layer)
+        # kT.translate(output, translation * [[h, w]], padding_mode="reflection")  (stylegan2.py:161-163)
+        pixels = translation.detach().cpu().double().reshape(-1, 2) * torch.tensor([[r, r]], dtype=torch.float64)
+        self.translate_hook = self._install_warp("translate", layer, _warp.inverse_2x3(_warp.translation_matrix(pixels)))
+
+    def apply_rotation(self, layer, angle, center):
+        r = self.G_synth.layer_resolution(layer)
+        # kT.rotate(output, angle.squeeze(), center, padding_mode="reflection")  (stylegan2.py:175-177)
+        m = _warp.rotation_scale_matrix(angle, torch.ones(1), center, r, r)
+        self.rotate_hook = self._install_warp("rotate", layer, _warp.inverse_2x3(m))
+
+    def apply_zoom(self, layer, zoom, center):
+        r = self.G_synth.layer_resolution(layer)
+        # kT.scale(output, zoom.squeeze(), center, padding_mode="reflection")  (stylegan2.py:188-190)
+        m = _warp.rotation_scale_matrix(torch.zeros(1), zoom, center, r, r)
+        self.zoom_hook = self._install_warp("zoom", layer, _warp.inverse_2x3(m))
 
     def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
         self.refresh_model_hooks()

@@ -593,6 +593,11 @@ extern "C" int mb_sg3_resized_output(const mb_sg3_cfg* cfg, int module, int stra
     return MB_OK;
 }
 
+extern "C" int mb_sg2_set_warps(mb_net* net, int n_warps, const int32_t* layers, const float* inv_mats, int batch) {
+    MB_REQUIRE(net && net->sg2, "mb_sg2_set_warps: needs a StyleGAN2 handle");
+    return sg2_set_warps(net->sg2, n_warps, layers, inv_mats, batch);
+}
+
 extern "C" int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width) {
     MB_REQUIRE(net && height && width, "mb_net_output_shape: null argument");
     if (net->sg2) {

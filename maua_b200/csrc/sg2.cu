@@ -63,6 +63,7 @@ __global__ void const_input_kernel(const float* __restrict__ cst, const float* _
 
 struct ActArgs {
     const __half* y;        // planar conv output [B][C][Hy][Wpy]; Hy = R (+1 with FIR)
+    const __half* pre;      // if set: the finished activation, channels-last [B][R][R][Cp] (a warped feature map); y, noise, bias unused
     const float* noise;     // [R][R] (noise_bstride 0) or per-frame [B][R][R] (noise_bstride R*R) or nullptr
     const float* bias;      // [C]
     const float* style_next;  // [B][C] or nullptr (last block)
@@ -88,7 +89,9 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
         const int c = idx / kActP, px = idx - c * kActP;
         const int w = w0 + px;
         float v = 0.0f;
-        if (w < a.R) {
+        if (a.pre) {
+            if (w < a.R) v = __half2float(a.pre[((static_cast<long long>(b) * a.R + h) * a.R + w) * a.Cp + c]);
+        } else if (w < a.R) {
             const __half* yp = a.y + (static_cast<long long>(b) * a.C + c) * a.Hy * a.Wpy;
             if (a.fir) {
                 // upfirdn2d(pad 1): out[h][w] = sum_{ky,kx} f[ky] f[kx] y[h - 1 + ky][w - 1 + kx], zero outside
@@ -120,8 +123,8 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
         __half* o = a.x_next + ((static_cast<long long>(b) * a.R + h) * a.R + w0) * a.Cp;
         for (int idx = threadIdx.x; idx < npx * (a.Cp / 2); idx += blockDim.x) {
             const int px = idx / (a.Cp / 2), c = (idx - px * (a.Cp / 2)) * 2;
-            const float s0 = c < a.C ? a.style_next[b * a.C + c] : 0.0f;
-            const float s1 = c + 1 < a.C ? a.style_next[b * a.C + c + 1] : 0.0f;
+            const float s0 = c < a.C ? (a.style_next ? a.style_next[b * a.C + c] : 1.0f) : 0.0f;
+            const float s1 = c + 1 < a.C ? (a.style_next ? a.style_next[b * a.C + c + 1] : 1.0f) : 0.0f;
             const float v0 = c < a.C ? xs[c * (kActP + 1) + px] * s0 : 0.0f;
             const float v1 = c + 1 < a.C ? xs[(c + 1) * (kActP + 1) + px] * s1 : 0.0f;
             *reinterpret_cast<__half2*>(o + static_cast<long long>(px) * a.Cp + c) = __floats2half2_rn(v0, v1);
@@ -143,6 +146,64 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
                 a.img[oi] = v;
             }
         }
+    }
+}
+
+// Feature-map warp of the network-bending hooks (maua/GAN/wrappers/stylegan2.py:153-194: kornia translate / rotate / scale
+// with padding_mode="reflection"; kornia is an un-pinned, absent dependency: its published warp_affine = affine_grid +
+// grid_sample(bilinear, align_corners=True) is restated).  out[b, y, x, :] = bilinear sample of src[b] at
+// (sx, sy) = M_b (x, y, 1) in pixel coordinates, coordinates reflected about the centres of the border pixels.
+// One thread = 8 channels of one output pixel; channels-last fp16 [B][R][R][Cp].
+__device__ __forceinline__ float reflect_coord(float x, int size) {
+    // grid_sample reflect_coordinates(x, 0, 2 * (size - 1)) followed by clip_coordinates (align_corners=True)
+    if (size <= 1) return 0.0f;
+    const float span = static_cast<float>(size - 1);
+    x = fabsf(x);
+    const float extra = fmodf(x, span);
+    const int flips = static_cast<int>(floorf(x / span));
+    x = (flips & 1) ? span - extra : extra;
+    return fminf(fmaxf(x, 0.0f), span);
+}
+
+__global__ void __launch_bounds__(256) sg2_warp_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
+                                                       const float* __restrict__ mats /*[B][2][3]*/, int B, int R, int Cp) {
+    const int groups = Cp / 8;
+    const long long total = static_cast<long long>(B) * R * R * groups;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(idx % groups);
+        long long q = idx / groups;
+        const int x = static_cast<int>(q % R); q /= R;
+        const int y = static_cast<int>(q % R);
+        const int b = static_cast<int>(q / R);
+        const float* m = mats + b * 6;
+        const float sx = reflect_coord(m[0] * x + m[1] * y + m[2], R);
+        const float sy = reflect_coord(m[3] * x + m[4] * y + m[5], R);
+        const float fx = floorf(sx), fy = floorf(sy);
+        const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+        const float tx = sx - fx, ty = sy - fy;
+        const float wgt[4] = {(1.0f - tx) * (1.0f - ty), tx * (1.0f - ty), (1.0f - tx) * ty, tx * ty};
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+            if (xx < 0 || xx >= R || yy < 0 || yy >= R) continue;  // grid_sample: out-of-range taps count as zero
+            const uint4 v = *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(b) * R + yy) * R + xx) * Cp + g * 8);
+            const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float2 f = __half22float2(hv[c]);
+                acc[2 * c] = fmaf(wgt[t], f.x, acc[2 * c]);
+                acc[2 * c + 1] = fmaf(wgt[t], f.y, acc[2 * c + 1]);
+            }
+        }
+        uint4 o;
+        __half2* ov = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ov[c] = __floats2half2_rn(acc[2 * c], acc[2 * c + 1]);
+        *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * R + y) * R + x) * Cp + g * 8) = o;
     }
 }
 
@@ -229,6 +290,10 @@ struct Sg2Net {
     bool finalized = false;
     int conv_impl = 0;
     int last_launches = 0;
+    // feature-map warps applied by the next forwards (sg2_set_warps): layer = index into the wrapper's layer_names
+    std::vector<int> warp_layer;
+    const float* warp_mats = nullptr;  // device [n_warps][warp_batch][2][3], caller-owned
+    int warp_batch = 0;
 };
 
 static int sg2_alloc(Sg2Param& p, std::initializer_list<int64_t> shape) {
@@ -369,7 +434,7 @@ int sg2_finalize(Sg2Net* n, cudaStream_t stream) {
 
 namespace {
 struct Sg2Ws {
-    size_t styles, d, x, xu, y, img0, img1, total;
+    size_t styles, d, x, xu, y, img0, img1, t0, t1, total;
     std::vector<size_t> style_l, d_l;  // per layer (conv0, conv1, torgb per block) float offsets
 };
 Sg2Ws sg2_ws(const Sg2Net* n, int B) {
@@ -397,6 +462,8 @@ Sg2Ws sg2_ws(const Sg2Net* n, int B) {
     w.x = take(mx * 2); w.xu = take(mxu * 2); w.y = take(my * 2);
     const size_t img = static_cast<size_t>(B) * n->img_channels * n->res * n->res * 4;
     w.img0 = take(img); w.img1 = take(img);
+    w.t0 = w.t1 = off;
+    if (!n->warp_layer.empty()) { w.t0 = take(mx * 2); w.t1 = take(mx * 2); }  // ping-pong buffers of the warped feature map
     w.total = off;
     return w;
 }
@@ -407,6 +474,22 @@ int sg2_num_ws(const Sg2Net* n) { return n->num_ws; }
 int sg2_resolution(const Sg2Net* n) { return n->res; }
 int sg2_last_launches(const Sg2Net* n) { return n->last_launches; }
 void sg2_set_conv_impl(Sg2Net* n, int impl) { n->conv_impl = impl; }
+
+int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* inv_mats, int batch) {
+    MB_REQUIRE(n_warps >= 0 && n_warps <= 16, "mb_sg2_set_warps: between 0 and 16 warps, got %d", n_warps);
+    if (n_warps == 0) {
+        n->warp_layer.clear(); n->warp_mats = nullptr; n->warp_batch = 0;
+        return MB_OK;
+    }
+    MB_REQUIRE(layers && inv_mats && batch > 0, "mb_sg2_set_warps: null argument");
+    const int n_names = 2 * static_cast<int>(n->blocks.size());
+    for (int i = 0; i < n_warps; ++i)
+        MB_REQUIRE(layers[i] >= 0 && layers[i] < n_names, "mb_sg2_set_warps: layer %d out of range [0, %d)", layers[i], n_names);
+    n->warp_layer.assign(layers, layers + n_warps);
+    n->warp_mats = inv_mats;
+    n->warp_batch = batch;
+    return MB_OK;
+}
 
 int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
                 int num_sms, cudaStream_t stream) {
@@ -426,7 +509,10 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
     __half* XU = reinterpret_cast<__half*>(base + wl.xu);
     __half* Y = reinterpret_cast<__half*>(base + wl.y);
     float* img[2] = {reinterpret_cast<float*>(base + wl.img0), reinterpret_cast<float*>(base + wl.img1)};
+    __half* T[2] = {reinterpret_cast<__half*>(base + wl.t0), reinterpret_cast<__half*>(base + wl.t1)};
     int launches = 0, rc;
+    MB_REQUIRE(n->warp_layer.empty() || n->warp_batch == B, "mb_net_forward: feature-map warps were set for a batch of %d, forward got %d",
+               n->warp_batch, B);
 
     // styles (+ demodulation coefficients) of every layer; ws index: block i uses ws[w_idx + {0,1,2}]
     {
@@ -481,14 +567,15 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             launches += 1;
             return n->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         };
-        auto act = [&](const Sg2Layer& L, int fir, const float* style_next, bool rgb, const float* prev) -> int {
+        auto act_raw = [&](const Sg2Layer& L, int fir, const float* style_next, __half* x_next, bool rgb, const float* prev,
+                           const __half* pre) -> int {
             ActArgs a;
-            a.y = Y; a.noise = L.noise.dev; a.bias = L.bias.dev;
+            a.y = Y; a.pre = pre; a.noise = L.noise.dev; a.bias = L.bias.dev;
             const size_t nb = L.noise.numel / L.noise.plane;
             MB_REQUIRE(nb == 1 || nb == static_cast<size_t>(B), "mb_net_forward: noise of a %dx%d layer holds %zu maps, batch is %d",
                        r, r, nb, B);
             a.noise_bstride = nb == 1 ? 0 : static_cast<long long>(L.noise.plane);
-            a.style_next = style_next; a.x_next = style_next ? X : nullptr;
+            a.style_next = style_next; a.x_next = x_next;
             a.rgb_w = rgb ? b.torgb.weight.dev : nullptr; a.rgb_style = s_rgb; a.rgb_bias = b.torgb.bias.dev;
             a.img_prev = prev; a.img = img[cur ^ 1];
             a.B = B; a.C = L.cout; a.R = r; a.Hy = fir ? r + 1 : r; a.Wpy = pitch8(a.Hy); a.Cp = cpad16(L.cout);
@@ -505,6 +592,29 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             launches += 1;
             return MB_OK;
         };
+        // name_idx = position of this layer in the wrapper's layer_names (stylegan2.py:48-51): block 0 owns entries 0 and 1
+        // (both "bs.0.conv1"), block i entries 2i (conv0) and 2i + 1 (conv1).  With warps on the layer, the activation
+        // is first written unstyled, warped in hook order (ping-pong), and only then styled / sent through ToRGB.
+        auto act = [&](const Sg2Layer& L, int fir, const float* style_next, bool rgb, const float* prev, int name_idx) -> int {
+            bool warped = false;
+            for (int wl_ : n->warp_layer)
+                if (wl_ == name_idx || (bi == 0 && wl_ <= 1)) warped = true;
+            if (!warped) return act_raw(L, fir, style_next, style_next ? X : nullptr, rgb, prev, nullptr);
+            int rr;
+            if ((rr = act_raw(L, fir, nullptr, T[0], false, nullptr, nullptr)) != MB_OK) return rr;
+            int cur_t = 0;
+            const int cp = cpad16(L.cout);
+            for (size_t wi = 0; wi < n->warp_layer.size(); ++wi) {
+                const int wl_ = n->warp_layer[wi];
+                if (!(wl_ == name_idx || (bi == 0 && wl_ <= 1))) continue;
+                const long long tot = static_cast<long long>(B) * r * r * (cp / 8);
+                sg2_warp_kernel<<<grid1d(tot), 256, 0, stream>>>(T[cur_t], T[cur_t ^ 1], n->warp_mats + wi * static_cast<size_t>(B) * 6, B, r, cp);
+                MB_CUDA(cudaGetLastError());
+                launches += 1;
+                cur_t ^= 1;
+            }
+            return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, T[cur_t]);
+        };
         if (!b.has_conv0) {
             const long long tot = static_cast<long long>(B) * r * r * cpad16(b.cout);
             const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout));
@@ -518,7 +628,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             MB_CUDA(cudaGetLastError());
             launches += 1;
             if ((rc = conv(b.conv0, XU, 2 * h - 1, 2, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
-            if ((rc = act(b.conv0, 1, s_conv1, false, nullptr)) != MB_OK) return rc;
+            if ((rc = act(b.conv0, 1, s_conv1, false, nullptr, static_cast<int>(2 * bi))) != MB_OK) return rc;
         }
         (void)s_conv0;
         if ((rc = conv(b.conv1, X, r, 1, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
@@ -532,7 +642,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             prev = img[cur ^ 1];
         }
         const float* s_next = last ? nullptr : styles + wl.style_l[(bi + 1) * 3 + 0];
-        if ((rc = act(b.conv1, 0, s_next, true, prev)) != MB_OK) return rc;
+        if ((rc = act(b.conv1, 0, s_next, true, prev, static_cast<int>(2 * bi + 1))) != MB_OK) return rc;
         cur ^= 1;
         have_img = true;
     }

@@ -13,6 +13,7 @@ int sg2_finalize(Sg2Net* n, cudaStream_t stream);
 size_t sg2_workspace_bytes(const Sg2Net* n, int B);
 int sg2_num_ws(const Sg2Net* n);
 int sg2_resolution(const Sg2Net* n);
+int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* inv_mats, int batch);
 int sg2_last_launches(const Sg2Net* n);
 void sg2_set_conv_impl(Sg2Net* n, int impl);
 int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,

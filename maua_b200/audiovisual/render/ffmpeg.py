@@ -2,7 +2,9 @@
 
 Same constructor / call signature.  Frames are converted to the rgb24 wire format on the device and streamed
 to ``ffmpeg`` on stdin when the binary exists; without it (this image has none) the raw rgb24 stream is written
-to ``output_file + ".rgb24"`` so the sink stays testable.  Video encode is row N1 of SURVEY §8f.
+to ``output_file + ".rgb24"`` so the sink stays testable.  The device->host copies go into a ring of pinned buffers and
+a writer thread feeds the pipe (render/_sink.py), so copy and pipe write overlap the synthesis of the next batches
+(the x264 encode itself stays with ffmpeg).
 """
 import shutil
 import subprocess
@@ -11,6 +13,7 @@ import torch
 
 from . import Renderer
 from ._loop import frame_batches, to_uint8
+from ._sink import RingWriter
 
 
 class FFMPEG(Renderer):
@@ -32,21 +35,30 @@ class FFMPEG(Renderer):
         proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stderr=subprocess.DEVNULL)
         return proc.stdin, proc
 
+    ring_depth = 3
+
     def __call__(self, synthesizer, inputs, postprocess, fp16=True):
-        sink, proc = None, None
-        pinned = None
+        sink, proc, writer = None, None, None
         try:
             for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device):
                 frame_batch = postprocess(frames.add(1).div(2))
                 u8 = to_uint8(frame_batch).permute(0, 2, 3, 1).contiguous()  # rgb24: H, W, 3 per frame
-                if sink is None:
+                if writer is None:
                     sink, proc = self._open_sink(u8.shape[2], u8.shape[1])
-                    pinned = torch.empty((self.batch_size,) + tuple(u8.shape[1:]), dtype=torch.uint8).pin_memory()
-                pinned[: u8.shape[0]].copy_(u8, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                sink.write(pinned[: u8.shape[0]].numpy().tobytes())
+                    ring = [torch.empty((self.batch_size,) + tuple(u8.shape[1:]), dtype=torch.uint8).pin_memory()
+                            for _ in range(self.ring_depth)]
+                    writer = RingWriter(sink, ring)
+                k = writer.acquire()
+                writer.ring[k][: u8.shape[0]].copy_(u8, non_blocking=True)
+                event = torch.cuda.Event()
+                event.record(torch.cuda.current_stream())
+                writer.submit(k, u8.shape[0], event)
         finally:
-            if sink is not None:
-                sink.close()
-            if proc is not None:
-                proc.wait()
+            try:
+                if writer is not None:
+                    writer.close()
+            finally:
+                if sink is not None:
+                    sink.close()
+                if proc is not None:
+                    proc.wait()

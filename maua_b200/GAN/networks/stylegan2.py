@@ -229,3 +229,20 @@ class SynthesisNetwork(NativeNet):
                     _lib.check(lib.mb_sg2_set_warps(self._handle(), 0, None, None, 0))
                     mats.record_stream(torch.cuda.current_stream(device))
         return out
+
+
+class Generator(torch.nn.Module):
+    """Mapping + synthesis pair the checkpoint loaders construct (maua/GAN/wrappers/inference/stylegan2.py:439-472)."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim = z_dim, c_dim, w_dim
+        self.img_resolution, self.img_channels = img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels,
+                                          **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+
+    def forward(self, z, c=None, truncation_psi=1.0, truncation_cutoff=None, noise_mode="const", **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        return self.synthesis(ws, noise_mode, **synthesis_kwargs)

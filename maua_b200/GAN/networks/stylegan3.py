@@ -257,4 +257,21 @@ class SynthesisNetwork(NativeNet):
         return out
 
 
+class Generator(torch.nn.Module):
+    """Mapping + synthesis pair the checkpoint loaders construct (upstream networks_stylegan3.py Generator (built by maua/GAN/load.py:131-139))."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim = z_dim, c_dim, w_dim
+        self.img_resolution, self.img_channels = img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels,
+                                          **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+
+    def forward(self, z, c=None, truncation_psi=1.0, truncation_cutoff=None, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff)
+        return self.synthesis(ws, **synthesis_kwargs)
+
+
 SG3_R_KWARGS = dict(conv_kernel=1, channel_base=65536, channel_max=1024, use_radial_filters=True)

@@ -9,11 +9,10 @@ from . import MauaGenerator, MauaMapper, MauaSynthesizer
 
 
 def load_network(model_file, inference=False):
-    # Checkpoint loaders (maua/GAN/load.py:192-207) are row N4 of SURVEY §8f, not built yet.
-    raise NotImplementedError(
-        f"loading '{model_file}': checkpoint loaders are not part of this build yet; construct with "
-        "model_file=None (random init) and use load_state_dict on G_synth / G_map"
-    )
+    """Checkpoint loaders of maua/GAN/load.py:192-207 (imported lazily: the networks import this package)."""
+    from ..load import load_network as _load
+
+    return _load(model_file, inference)
 
 
 class StyleGANMapper(MauaMapper):

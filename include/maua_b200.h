@@ -195,7 +195,8 @@ int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h, int32_t* 
  * impl: 0 product dispatch (tcgen05; cout-major tile, pixel-major tile for <= 64 couts with > 32 cins; narrow layers
  * keep their weight tiles resident in shared memory), 1 CUDA-core direct convolution (bisecting aid), 2 cout-major
  * with 16-wide pixel tiles, 3 cout-major with full 128-row weight tiles streamed per stage (first path),
- * 4 pixel-major tile for everything up to 128 couts. */
+ * 4 pixel-major tile for everything up to 128 couts, 7 cout-major tile everywhere with ONE activation patch load per
+ * 64-channel chunk wherever the weights are resident (kw shifts through the B-descriptor start). */
 int mb_modulated_conv2d(const float* x, const float* w, const float* s, float* y, int B, int Cin,
                         int Cout, int H, int W, int k, int demodulate, float input_gain,
                         int impl, mb_stream stream);

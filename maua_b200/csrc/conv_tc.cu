@@ -32,6 +32,8 @@ constexpr int kTileM = 128;         // couts per tile (UMMA M)
 constexpr int kTileN = 256;         // pixels per tile (UMMA N)
 constexpr int kKC = 64;             // channels per pipeline stage
 constexpr int kSmemMax = 232448;    // 227 KB dynamic shared memory per CTA on sm_100
+constexpr int kEpiPitch = 20;       // words per cout row of the shift-mode epilogue staging tile (16 data + 4 pad)
+constexpr int kEpiStageBytes = 4 * 32 * kEpiPitch * 4;  // one [32 couts][kEpiPitch] tile per epilogue warp
 
 template <int TW>
 struct Geo {
@@ -51,6 +53,17 @@ struct KArgs {
     int a_tile_bytes;     // one [a_rows x 64] weight tile (a_rows = 128, or ceil8(Cout) when Cout fits one M tile)
     int resident;         // 1: every weight tile stays in shared memory for the whole kernel
     int nstages, stage_bytes;
+    // shift = 1 (needs resident weights, TW = 32): ONE patch load per 64-channel chunk serves all k*k taps; tap (kh, kw)
+    // reads the 256-row B window that starts kh image rows (whole swizzle atoms) and kw pixels (kw * 128 bytes, inside an
+    // atom) into the patch -- the same descriptor-start trick the pixel-major tile uses for its A operand.  A tile then
+    // yields tile_wv = TW - (k - 1) valid output columns per row (the window of the last columns wraps into the next
+    // patch row; those accumulator columns are never stored) and the activation bytes cross L2 -> smem once, not k times.
+    // Bit-correct (parity test impl 7) but OFF by default: measured on B200 it loses to the per-kw loads because the tile
+    // origin 30 * wt is only 4-byte aligned and the planar output then needs 4x the store instructions; store instructions
+    // into the [B][C][H][Wp] planes (2 MB apart at 1024^2) cost ~40-60 cycles each regardless of the bytes they carry
+    // (L13: 0.51 ms product path; shift mode 0.46 ms without its stores, 0.70 ms with every store aimed at two planes,
+    // 1.03-1.08 ms with the real 32-plane scatter, aligned or not; 0.90 ms with direct per-lane 4-byte stores).
+    int shift, tile_wv;
 };
 
 template <int TW>
@@ -75,6 +88,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     uint64_t* tempty = bars + 2 * kMaxStages + 2;  // [2]
     uint64_t* wfull = bars + 2 * kMaxStages + 4;   // [1] resident weights landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+    uint32_t* epi_stage = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 256);  // shift mode only
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -127,8 +141,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const int wt = r % a.tiles_w; r /= a.tiles_w;
                 const int ht = r % a.tiles_h; r /= a.tiles_h;
                 const int b = r;
-                const int h0 = ht * G::TH, w0 = wt * TW, m0 = mt * kTileM;
-                for (int kw = 0; kw < a.ksz; ++kw) {
+                const int h0 = ht * G::TH, w0 = wt * a.tile_wv, m0 = mt * kTileM;
+                const int nkw = a.shift ? 1 : a.ksz;
+                for (int kw = 0; kw < nkw; ++kw) {
                     for (int cc = 0; cc < a.nCC; ++cc) {
                         mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                         if (leader) {
@@ -162,7 +177,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * kTileN;
                 uint32_t accumulate = 0;
-                for (int it = 0; it < iters; ++it) {
+                const int nit = a.shift ? a.nCC : iters;
+                for (int it = 0; it < nit; ++it) {
                     const int cc = it % a.nCC;
                     int nk16 = (a.Cin - cc * kKC + 15) / 16;
                     if (nk16 > 4) nk16 = 4;
@@ -173,6 +189,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     const uint32_t sb = st + a_bytes_stage;
                     const uint64_t da0 = make_smem_desc(sa, 16, 1024, 2);
                     const uint64_t db0 = make_smem_desc(sb, 16, 1024, 2);
+                    if (a.shift) {
+                        if (leader) {
+                            for (int kw = 0; kw < a.ksz; ++kw) {
+                                const uint64_t da = make_smem_desc(smem_u32(smem) + ((kw * a.nCC + cc) * a.ksz) * a.a_tile_bytes, 16, 1024, 2);
+                                const uint64_t db = db0 + static_cast<uint64_t>((kw * 128) >> 4);
+                                for (int kh = 0; kh < a.ksz; ++kh) {
+#pragma unroll 4
+                                    for (int j = 0; j < nk16; ++j) {
+                                        umma_f16(d_tmem, da + static_cast<uint64_t>((kh * a.a_tile_bytes + j * 32) >> 4),
+                                                 db + static_cast<uint64_t>((kh * G::SLAB + j * 32) >> 4), idesc, accumulate);
+                                        accumulate = 1;
+                                    }
+                                }
+                            }
+                            umma_commit(&empty[s]);
+                        }
+                        __syncwarp();
+                        if (++s == nst) { s = 0; ph ^= 1; }
+                        continue;
+                    }
                     if (leader) {
                         for (int kh = 0; kh < a.ksz; ++kh) {
 #pragma unroll 4
@@ -203,7 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const int wt = r % a.tiles_w; r /= a.tiles_w;
             const int ht = r % a.tiles_h; r /= a.tiles_h;
             const int b = r;
-            const int h0 = ht * G::TH, w0 = wt * TW;
+            const int h0 = ht * G::TH, w0 = wt * a.tile_wv;
             const int co = mt * kTileM + q * 32 + lane;
             const bool co_ok = co < a.Cout;
             const float scale = (co_ok && a.d) ? a.d[b * a.Cout + co] : 1.0f;
@@ -218,7 +254,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN + ch * 32, v);
                 tmem_ld_wait();
                 const int n0 = ch * 32;
-                if (co_ok) {
+                if (a.shift) {
+                    // Tile origin w0 = tile_wv * wt is only 4-byte aligned and a lane (= cout) would scatter 4-byte stores
+                    // over 32 planes (measured: L13 0.51 -> 0.90 ms, store-bound).  Transpose through a per-warp staging
+                    // tile instead: lane = cout writes its 32 pixels as 4 x STS.128 (row pitch 80 B: conflict-free per
+                    // quarter warp), then half a warp reads one cout row back, so one STG.32 covers 2 x 60 contiguous bytes.
+                    // chunk ch = accumulator columns [32 ch, 32 ch + 32) = image row h0 + ch (TW = 32).
+                    const uint32_t stg = smem_u32(epi_stage) + q * (32 * kEpiPitch * 4);  // shared-space address: STS / LDS
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int k2 = 0; k2 < 16; ++k2) {
+                        const __half2 hv = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k2]), scale, bias),
+                                                             fmaf(__uint_as_float(v[2 * k2 + 1]), scale, bias));
+                        pk[k2] = *reinterpret_cast<const uint32_t*>(&hv);
+                    }
+                    __syncwarp();  // the previous chunk's read-out is done
+#pragma unroll
+                    for (int g = 0; g < 4; ++g)
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (lane * kEpiPitch + g * 4) * 4), "r"(pk[4 * g]),
+                                     "r"(pk[4 * g + 1]), "r"(pk[4 * g + 2]), "r"(pk[4 * g + 3])
+                                     : "memory");
+                    __syncwarp();
+                    const int h = h0 + ch;
+                    const int kk = lane & 15;
+                    const int w = w0 + 2 * kk;
+                    const bool px_ok = h < a.Hout && 2 * kk < a.tile_wv && w < a.Wp_out;
+                    const int co0 = mt * kTileM + q * 32 + (lane >> 4);
+                    __half* yrow = a.y + (static_cast<long long>(b) * a.Cout + co0) * a.plane_out + static_cast<long long>(h) * a.Wp_out + w;
+                    // all 16 loads first (independent, pipelined), then the stores: alternating them serialises on the
+                    // shared-memory latency, which is long while the tensor core streams its operands (measured 1300 cycles / chunk)
+                    uint32_t val[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(val[i]) : "r"(stg + ((2 * i + (lane >> 4)) * kEpiPitch + kk) * 4));
+                    if (px_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (co0 + 2 * i < a.Cout)
+                                *reinterpret_cast<uint32_t*>(yrow + static_cast<long long>(2 * i) * a.plane_out) = val[i];
+                    }
+                } else if (co_ok) {
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const int n = n0 + g * 8;
@@ -535,8 +610,11 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     const int a_rows = (Mp == kTileM && p.narrow_a) ? round_up(p.Cout, 8) : kTileM;
     const int a_tile_bytes = a_rows * kKC * 2;
     const int patch_bytes = (th + halo) * tw * 128;
-    const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/;
     const int w_all = p.ksz * p.ksz * nCC * a_tile_bytes;
+    // shift mode (one patch load per chunk, see KArgs) needs resident weights and room for its epilogue staging tiles
+    const bool want_shift = !pixel_major && p.cm_shift && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
+                            w_all + 2 * patch_bytes + 1024 + 256 + kEpiStageBytes <= kSmemMax;
+    const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (want_shift ? kEpiStageBytes : 0);
     const bool resident = p.narrow_a && Mp == kTileM && w_all + 2 * patch_bytes + fixed_bytes <= kSmemMax;
     const int stage_alloc = patch_bytes + (resident ? 0 : p.ksz * a_tile_bytes);
     int nstages = (kSmemMax - fixed_bytes - (resident ? w_all : 0)) / stage_alloc;
@@ -593,6 +671,12 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.resident = resident ? 1 : 0;
     a.nstages = nstages;
     a.stage_bytes = stage_alloc;
+    a.shift = (want_shift && resident) ? 1 : 0;
+    a.tile_wv = a.shift ? tw - halo : tw;
+    if (a.shift) {
+        a.tiles_w = ceil_div(a.Wout, a.tile_wv);
+        a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
+    }
 
     if (pixel_major) {
         PmArgs pa;

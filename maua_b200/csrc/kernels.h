@@ -28,6 +28,8 @@ struct ConvTcArgs {
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
     int pm_max_cout = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major tile (0 = never)
     int pm_shift = 1;      // pixel-major tile: 1 / 2 = one patch load per chunk, kw shifts through the A descriptor start
+    int cm_shift = 0;      // cout-major tile with resident weights: one patch load per chunk, kw shifts through the B descriptor start
+                           // (correct, measured slower than per-kw loads: see KArgs::shift in conv_tc.cu)
     int narrow_a = 1;      // Cout <= 128: load only ceil8(Cout) weight rows per tile and keep them resident when they fit
     int num_sms;
 };

@@ -83,6 +83,7 @@ struct mb_net {
     int conv_tile_w = 32;
     int conv_pm_max = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major conv tile
     int conv_narrow_a = 1; // narrow/resident weight tiles for Cout <= 128 (conv_tc.cu)
+    int conv_cm_shift = 0; // cout-major tile with resident weights: one patch load per chunk (conv_tc.cu)
     int conv_pm_shift = 1; // pixel-major tile: one patch load per chunk, kw shift via the descriptor start (conv_tc.cu)
     int flrelu_impl = 0;  // 0 = tensor-core chain where supported, 1 = generic loops, 2 = CUDA-core polyphase kernel
     int debug_stop = 1 << 30;
@@ -627,6 +628,7 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     else if (k == "conv_pm_max") net->conv_pm_max = value;
     else if (k == "conv_narrow_a") net->conv_narrow_a = value;
     else if (k == "conv_pm_shift") net->conv_pm_shift = value;
+    else if (k == "conv_cm_shift") net->conv_cm_shift = value;
     else if (k == "flrelu_impl") net->flrelu_impl = value;
     else if (k == "debug_stop") net->debug_stop = value;
     else if (k == "profile") net->profile = value;
@@ -851,6 +853,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         ca.pm_max_cout = net->conv_pm_max;
         ca.narrow_a = net->conv_narrow_a;
         ca.pm_shift = net->conv_pm_shift;
+        ca.cm_shift = net->conv_cm_shift;
         ca.num_sms = g_num_sms;
         r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         if (r != MB_OK) return r;
@@ -972,10 +975,11 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
         ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
         ca.pad = k - 1;
         ca.tile_w = (impl == 2) ? 16 : 32;
-        ca.pm_max_cout = (impl >= 4) ? 128 : ((impl == 0) ? 64 : 0);  // 4..6: pixel-major tile for every layer up to 128 couts
+        ca.pm_max_cout = (impl >= 4 && impl <= 6) ? 128 : ((impl == 0) ? 64 : 0);  // 4..6: pixel-major tile for every layer up to 128 couts
         ca.pm_shift = (impl == 0 || impl == 5) ? 1 : (impl == 6 ? 2 : 0);  // 4: one patch load per kw; 5: single load, shifted
                                                                            // A descriptors; 6: + base-offset field (WRONG results:
                                                                            // kept as the probe of scripts/conv_shift_probe.py)
+        ca.cm_shift = (impl == 7) ? 1 : 0;  // 7: cout-major tile everywhere, single patch load + shifted B descriptors
         ca.narrow_a = (impl == 3) ? 0 : 1;       // 3: always stream full 128-row weight tiles (the r1 first path)
         ca.num_sms = g_num_sms;
         r = (impl == 1) ? conv_simt_launch(ca, stream) : conv_tc_launch(ca, stream);

@@ -31,8 +31,8 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES)
 # 1 CUDA cores, 0 tcgen05 product dispatch (narrow layers: resident weight tiles), 2 the same with 16-wide tiles,
-# 3 full weight tiles streamed per stage, 4 pixel-major tile up to 128 couts
-@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4])
+# 3 full weight tiles streamed per stage, 4 pixel-major tile up to 128 couts, 7 cout-major tile with one patch load per chunk
+@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4, 7])
 def test_modulated_conv2d(cuda, case, impl):
     from maua_b200 import ops
 

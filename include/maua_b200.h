@@ -278,6 +278,18 @@ int mb_multi_weighted(const float* latents /*[K,D]*/, const float* envelopes /*[
 int mb_single_weighted(const float* low /*[D]*/, const float* high /*[D]*/, const float* envelope /*[T]*/, float* out /*[T,D]*/,
                        int T, int D, mb_stream stream);
 
+/* Twins of the torch-native feature path (maua/audiovisual/audioreactive/selfsupervised/):
+ * features/processing.py:11-50 gaussian_filter with mode="reflect" (pad_mode 1; 0 = circular = mb_gaussian_filter);
+ * mir.py:13-21 salience_weighted's final (short / long)^2 * envelope; latent.py:69-78 the merge step of latent_patch on
+ * layers [lay0, lay1) of latents [T, L, D] in place (mode 0 average, 1 modulate by modulation[T], 2 overwrite);
+ * latent.py:7-13 spline_loop_latents: natural cubic spline through cat(keys, keys[0]) evaluated at
+ * linspace(0, n_loops, size) % 1 (fractional n_loops allowed; workspace: device float32 [(K+1) * C]). */
+int mb_gaussian_filter_ex(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal, int pad_mode, mb_stream stream);
+int mb_salience(const float* short_env, const float* long_env, const float* envelope, float* out, int64_t n, mb_stream stream);
+int mb_latent_merge(float* latents, const float* sequence, const float* modulation, int mode, int lay0, int lay1, int T, int L,
+                    int D, mb_stream stream);
+int mb_spline_loop_latents(const float* keys, int K, int C, float n_loops, int size, float* out, float* workspace, mb_stream stream);
+
 /* latent.py: slerp_loops :68-80 = mb_slerp_rows (the [steps * K*n_loops, L, D] table of spherical interpolants between
  * consecutive looped keys, row = step * nseg + segment as the reference's reshape orders them) followed by
  * mb_resample_linear to `size`; spline_loops :83-92 = natural cubic spline through cat([keys] * n_loops + [keys[0]]) at

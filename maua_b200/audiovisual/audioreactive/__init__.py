@@ -5,3 +5,4 @@ from .features import harmonic, mel_filterbank, onset_peaks, onsets, onsets_rms,
 from .latent import multi_weighted, select_modulo, single_weighted, slerp_loops, spline_loops, tempo_loops  # noqa: F401,E402
 from . import noise  # noqa: F401,E402
 from .signal import compress, expand, gaussian_filter, normalize, percentile, percentile_clip, resample  # noqa: F401,E402
+from . import selfsupervised  # noqa: F401,E402  (torch-native twins: latent_patch, noise_patch, salience_weighted, ...)

@@ -1,0 +1,179 @@
+"""Torch-native ("selfsupervised") envelope / latent / noise patch functions on the device: mirror of
+maua/audiovisual/audioreactive/selfsupervised/{features/processing.py, mir.py, latent.py, noise.py} (rows a7, a10, a11,
+a12 of SURVEY §8a), same names and arguments.  CUDA tensors only; the per-element arithmetic runs in the library's
+kernels (csrc/signal_ops.cu, csrc/sequencers.cu), order statistics (quantile / sort / randperm) are torch device ops."""
+from __future__ import annotations
+
+import torch
+
+from ... import _lib
+from . import noise as _noise
+from .latent import single_weighted
+from .signal import _cuda32
+
+_PAD = {"circular": 0, "reflect": 1}
+
+
+def gaussian_filter(x, sigma, mode: str = "circular", causal: float = 1):
+    """features/processing.py:11-50: temporal Gaussian, `mode` padding; the causal factor is commented out upstream (:24),
+    so `causal` is accepted and ignored exactly like there.  Any trailing shape ([T], [T,C], [T,C,L], [T,C,H,W])."""
+    if mode not in _PAD:
+        raise NotImplementedError(f"gaussian_filter: padding mode '{mode}' (built: circular, reflect)")
+    x = _cuda32(x, "x")
+    T = x.shape[0]
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mb_gaussian_filter_ex(_lib.ptr(x), _lib.ptr(y), T, x.numel() // T, float(sigma), 0, 0.0, _PAD[mode],
+                                                     _lib.stream_ptr()))
+    return y
+
+
+def normalize(array):
+    """features/processing.py:53-56: (x - min) / (max(x - min) + 1e-8)."""
+    from .signal import normalize as _normalize
+
+    return _normalize(array, eps=1e-8)
+
+
+def salience_weighted(envelope, short_sigma=5, long_sigma=80):
+    """mir.py:13-21: (gaussian(short) / gaussian(long))^2 * envelope, reflect padding -> [T, 1]."""
+    env = _cuda32(envelope, "envelope")
+    if env.dim() > 1:
+        env = env.squeeze(1)
+    env = env.contiguous()
+    short = gaussian_filter(env, short_sigma, mode="reflect", causal=0)
+    long = gaussian_filter(env, long_sigma, mode="reflect", causal=0)
+    out = torch.empty_like(env)
+    with torch.cuda.device(env.device):
+        _lib.check(_lib.load().mb_salience(_lib.ptr(short), _lib.ptr(long), _lib.ptr(env), _lib.ptr(out), env.numel(), _lib.stream_ptr()))
+    return out.unsqueeze(1) if out.dim() < 2 else out
+
+
+def _peaks(sig):
+    n = sig.shape[0]
+    i = torch.arange(n, device=sig.device)
+    return (sig > sig[(i + 1).clamp(0, n - 1)]) & (sig > sig[(i - 1).clamp(0, n - 1)])
+
+
+def clamp_peaks_percentile(signal, percent):
+    """features/processing.py:102-122: clamp each column to the `percent` quantile of its strict local maxima."""
+    signal = _cuda32(signal, "signal")
+    if signal.dim() < 2:
+        signal = signal.unsqueeze(1)
+    cols = [torch.clamp(sig, None, torch.quantile(sig[_peaks(sig)], percent / 100)) for sig in signal.unbind(1)]
+    return torch.stack(cols, dim=1)
+
+
+def clamp_upper_percentile(signal, percentile):
+    signal = _cuda32(signal, "signal")
+    return torch.clamp(signal, None, torch.quantile(signal, percentile / 100, dim=0))
+
+
+def clamp_lower_percentile(signal, percentile):
+    signal = _cuda32(signal, "signal")
+    return torch.clamp(signal, torch.quantile(signal, percentile / 100, dim=0), None)
+
+
+def emphasize(envs, strength, percentile):
+    """features/processing.py:133-139."""
+    envs = _cuda32(envs, "envs")
+    lo = envs.min(dim=0).values
+    x = envs - lo
+    hi = x.max(dim=0).values
+    x = x / hi
+    x = x * (1 + torch.tanh(strength * (x - torch.quantile(x, q=percentile / 100, dim=0))))
+    return (x * hi) + lo
+
+
+def spline_loop_latents(y, size, n_loops=1):
+    """latent.py:7-13: natural cubic spline through cat(y, y[0]) walked n_loops (may be fractional) times."""
+    lat = _cuda32(y, "y")
+    K, Cc = lat.shape[0], lat[0].numel()
+    out = torch.empty((size,) + tuple(lat.shape[1:]), device=lat.device)
+    ws = torch.empty((K + 1) * Cc, device=lat.device)
+    with torch.cuda.device(lat.device):
+        _lib.check(_lib.load().mb_spline_loop_latents(_lib.ptr(lat), K, Cc, float(n_loops), int(size), _lib.ptr(out), _lib.ptr(ws),
+                                                      _lib.stream_ptr()))
+    return out
+
+
+_LATENT_LAYERS = {"low": (0, 6), "mid": (6, 12), "high": (12, 18), "lowmid": (0, 12), "midhigh": (6, 18), "all": (0, 18)}
+
+
+def latent_patch(rng, latents, palette, segmentations, features, tempo, fps, patch_type, segments, loop_bars, seq_feat,
+                 seq_feat_weight, mod_feat, mod_feat_weight, merge_type, merge_depth):
+    """latent.py:16-80: one random-patch step on the W+ sequence `latents` [T, num_ws, 512] (modified in place and
+    returned, as in the reference)."""
+    if not latents.is_cuda or latents.dtype != torch.float32 or not latents.is_contiguous():
+        raise RuntimeError("latent_patch: latents must be a contiguous float32 CUDA tensor (it is updated in place)")
+    palette = _cuda32(palette, "palette")
+    feature = seq_feat_weight * _cuda32(features[seq_feat], seq_feat)
+    segmentation = segmentations[(seq_feat, segments)]
+    permutation = torch.randperm(len(palette), generator=rng, device=rng.device).to(palette.device)
+    lib = _lib.load()
+    T, L, D = latents.shape
+
+    if patch_type == "segmentation":
+        selection = permutation[:segments]
+        selectseq = selection[segmentation.to(selection.device)]
+        sequence = gaussian_filter(palette[selectseq], 5)
+    elif patch_type == "feature":
+        n_select = feature.shape[1]
+        if n_select == 1:
+            selection = permutation[:2]
+            sequence = single_weighted(palette[selection[1]], palette[selection[0]], feature.reshape(-1))
+        else:
+            selection = permutation[:n_select]
+            pal = palette[selection].reshape(n_select, -1).contiguous()
+            sequence = torch.empty((T,) + tuple(palette.shape[1:]), device=palette.device)
+            with torch.cuda.device(palette.device):  # einsum("TN,NWL->TWL") = the mixing kernel of the noise sequencers
+                _lib.check(lib.mb_noise_mix(_lib.ptr(pal), _lib.ptr(feature.contiguous()), T, n_select, pal.shape[1], 0,
+                                            _lib.ptr(sequence), _lib.stream_ptr()))
+    elif patch_type == "loop":
+        selection = permutation[:segments]
+        n_loops = len(latents) / fps / 60 / tempo / 4 / loop_bars
+        sequence = spline_loop_latents(palette[selection], len(latents), n_loops=n_loops)
+    else:
+        raise ValueError(f"latent_patch: unknown patch_type '{patch_type}'")
+    sequence = gaussian_filter(sequence, 1)
+
+    lay0, lay1 = _LATENT_LAYERS[merge_depth]
+    mode = {"average": 0, "modulate": 1}.get(merge_type, 2)
+    modulation = None
+    if mode == 1:
+        modulation = (mod_feat_weight * _cuda32(features[mod_feat], mod_feat)).reshape(-1).contiguous()
+        if modulation.numel() != T:
+            raise ValueError("latent_patch: a modulation feature must have one value per frame")
+    with torch.cuda.device(latents.device):
+        _lib.check(lib.mb_latent_merge(_lib.ptr(latents), _lib.ptr(sequence.contiguous()), _lib.ptr(modulation), mode, lay0, lay1, T, L, D,
+                                       _lib.stream_ptr()))
+    return latents
+
+
+_NOISE_LAYERS = {"low": range(0, 6), "mid": range(6, 12), "high": range(12, 17), "lowmid": range(0, 12), "midhigh": range(6, 17),
+                 "all": range(0, 17)}
+
+
+def noise_patch(rng, noise, features, tempo, fps, patch_type, loop_bars, seq_feat, seq_feat_weight, mod_feat, mod_feat_weight,
+                merge_type, merge_depth, noise_mean, noise_std):
+    """noise.py:89-140: wrap the per-layer noise sequencers of `noise` (list) with one random-patch step."""
+    lays = _NOISE_LAYERS[merge_depth]
+    feature = seq_feat_weight * features[seq_feat]
+    for n in lays:
+        if patch_type == "blend":
+            new_noise = _noise.Blend(rng=rng, length=len(feature), size=noise[n].size, modulator=feature)
+        elif patch_type == "multiply":
+            new_noise = _noise.Multiply(rng=rng, length=len(feature), size=noise[n].size, modulator=feature)
+        elif patch_type == "loop":
+            n_loops = len(feature) / fps / 60 / tempo / 4 / loop_bars
+            new_noise = _noise.Loop(rng=rng, length=len(feature), size=noise[n].size, n_loops=n_loops, device=feature.device)
+        else:
+            raise ValueError(f"noise_patch: unknown patch_type '{patch_type}'")
+        if merge_type == "average":
+            noise[n] = _noise.Average(left=noise[n], right=new_noise)
+        elif merge_type == "modulate":
+            noise[n] = _noise.Modulate(left=noise[n], right=new_noise, modulator=mod_feat_weight * features[mod_feat])
+        else:  # overwrite
+            noise[n] = new_noise
+        noise[n] = _noise.ScaleBias(noise[n], scale=noise_std, bias=noise_mean)
+    return noise

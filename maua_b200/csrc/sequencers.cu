@@ -94,14 +94,22 @@ __global__ void spline_solve_kernel(const float* __restrict__ keys, int K, int C
     }
 }
 
+// t_end = 1, wrap = 0: evaluate at linspace(0, 1, size) (spline_loops).  wrap = 1: at linspace(0, t_end, size) % 1
+// (selfsupervised/latent.py:7-13 spline_loop_latents; linspace as ATen computes it: from the start up to the middle,
+// from the end beyond it).
 __global__ void spline_eval_kernel(const float* __restrict__ keys, const float* __restrict__ z, int K, int C, int M, int size,
-                                   float* __restrict__ out) {
+                                   float* __restrict__ out, float t_end, int wrap) {
     const long long total = static_cast<long long>(size) * C;
     const float h = 1.0f / static_cast<float>(M - 1);
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int j = static_cast<int>(idx / C), c = static_cast<int>(idx - static_cast<long long>(j) * C);
-        const float t = size > 1 ? static_cast<float>(j) / static_cast<float>(size - 1) : 0.0f;
+        float t = size > 1 ? static_cast<float>(j) / static_cast<float>(size - 1) : 0.0f;
+        if (wrap) {
+            const float step = size > 1 ? t_end / static_cast<float>(size - 1) : 0.0f;
+            t = j < size / 2 ? step * static_cast<float>(j) : t_end - step * static_cast<float>(size - 1 - j);
+            t = fmodf(t, 1.0f);
+        }
         const float u = t * static_cast<float>(M - 1);
         int i = static_cast<int>(u);
         if (i > M - 2) i = M - 2;
@@ -212,7 +220,19 @@ extern "C" int mb_spline_loops(const float* keys, int K, int C, int n_loops, int
     MB_REQUIRE(M >= 2 && M <= 4096, "mb_spline_loops: %d knots unsupported", M);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     spline_solve_kernel<<<(C + 127) / 128, 128, 0, s>>>(keys, K, C, M, workspace);
-    spline_eval_kernel<<<grid_for(static_cast<long long>(size) * C), 256, 0, s>>>(keys, workspace, K, C, M, size, out);
+    spline_eval_kernel<<<grid_for(static_cast<long long>(size) * C), 256, 0, s>>>(keys, workspace, K, C, M, size, out, 1.0f, 0);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_spline_loop_latents(const float* keys, int K, int C, float n_loops, int size, float* out, float* workspace,
+                                      mb_stream stream) {
+    MB_REQUIRE(keys && out && workspace && K > 0 && C > 0 && n_loops >= 0.0f && size > 0, "mb_spline_loop_latents: bad argument");
+    const int M = K + 1;  // torch.cat((y, y[[0]])): ONE loop of knots, walked n_loops times by the wrapped positions
+    MB_REQUIRE(M >= 2 && M <= 4096, "mb_spline_loop_latents: %d knots unsupported", M);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    spline_solve_kernel<<<(C + 127) / 128, 128, 0, s>>>(keys, K, C, M, workspace);
+    spline_eval_kernel<<<grid_for(static_cast<long long>(size) * C), 256, 0, s>>>(keys, workspace, K, C, M, size, out, n_loops, 1);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

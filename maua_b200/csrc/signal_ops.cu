@@ -12,8 +12,10 @@ namespace mb {
 namespace {
 
 // depthwise temporal Gaussian with circular padding; kernel taps built in shared memory (signal.py:125-131)
+// pad_mode 1 = torch 'reflect' padding (selfsupervised/features/processing.py:11-50 with mode="reflect", used by
+// salience_weighted, selfsupervised/mir.py:16-17): index -i -> i, T-1+i -> T-1-i
 __global__ void gaussian_filter_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C, float sigma,
-                                       int radius, int causal_mode, float causal) {
+                                       int radius, int causal_mode, float causal, int pad_mode) {
     extern __shared__ float k[];  // [2*radius+1]
     __shared__ float ksum;
     for (int i = threadIdx.x; i < 2 * radius + 1; i += blockDim.x) {
@@ -37,8 +39,13 @@ __global__ void gaussian_filter_kernel(const float* __restrict__ x, float* __res
         float acc = 0.0f;
         for (int i = 0; i < 2 * radius + 1; ++i) {
             int tt = t + i - radius;
-            tt %= T;
-            if (tt < 0) tt += T;
+            if (pad_mode == 1) {
+                if (tt < 0) tt = -tt;
+                if (tt > T - 1) tt = 2 * (T - 1) - tt;
+            } else {
+                tt %= T;
+                if (tt < 0) tt += T;
+            }
             acc = fmaf(k[i] * inv, x[static_cast<long long>(tt) * C + c], acc);
         }
         y[idx] = acc;
@@ -71,6 +78,41 @@ __global__ void normalize_apply_kernel(const float* __restrict__ x, float* __res
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         y[i] = (x[i] - lo) / den;
+}
+
+// salience_weighted (selfsupervised/mir.py:13-21): (short / long)^2 * envelope
+__global__ void salience_kernel(const float* __restrict__ s, const float* __restrict__ l, const float* __restrict__ e,
+                                float* __restrict__ out, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float r = s[i] / l[i];
+        out[i] = r * r * e[i];
+    }
+}
+
+// merge step of latent_patch (selfsupervised/latent.py:69-78) on layers [lay0, lay1) of latents [T, L, D], in place:
+// mode 0 average: (lat + seq) / 2; 1 modulate: lat * (1 - m[t]) + m[t] * seq; 2 overwrite: seq
+__global__ void latent_merge_kernel(float* __restrict__ lat, const float* __restrict__ seq, const float* __restrict__ mod, int mode,
+                                    int lay0, int lay1, int T, int L, int D) {
+    const int span = (lay1 - lay0) * D;
+    const long long total = static_cast<long long>(T) * span;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int t = static_cast<int>(idx / span);
+        const long long o = static_cast<long long>(t) * L * D + static_cast<long long>(lay0) * D + (idx - static_cast<long long>(t) * span);
+        const float a = lat[o], b = seq[o];
+        float r;
+        if (mode == 0) {
+            r = (a + b) / 2.0f;
+        } else if (mode == 1) {
+            const float m = mod[t];
+            r = a * (1.0f - m);     // the reference multiplies in place, then adds (two roundings)
+            r = r + m * b;
+        } else {
+            r = b;
+        }
+        lat[o] = r;
+    }
 }
 
 // F.interpolate(mode="linear", align_corners=False) along time: src = (dst + 0.5) * T / S - 0.5, clamped at 0
@@ -125,14 +167,39 @@ int grid1d(long long total) {
 
 using namespace mb;
 
-extern "C" int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal,
-                                  mb_stream stream) {
+extern "C" int mb_gaussian_filter_ex(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal,
+                                     int pad_mode, mb_stream stream) {
     MB_REQUIRE(x && y && x != y && T > 0 && C > 0 && sigma > 0.0f, "mb_gaussian_filter: bad argument");
+    MB_REQUIRE(pad_mode == 0 || pad_mode == 1, "mb_gaussian_filter: pad_mode %d unknown (0 circular, 1 reflect)", pad_mode);
     int radius = static_cast<int>(sigma * 4.0f);
     if (radius > 3 * T) radius = 3 * T;
-    MB_REQUIRE(radius <= T, "mb_gaussian_filter: radius %d > %d frames (the reference's short-sequence branch is not built)", radius, T);
+    MB_REQUIRE(radius <= T - pad_mode, "mb_gaussian_filter: radius %d too large for %d frames (the reference's short-sequence branch is not built)", radius, T);
     gaussian_filter_kernel<<<grid1d(static_cast<long long>(T) * C), 256, sizeof(float) * (2 * radius + 1),
-                             static_cast<cudaStream_t>(stream)>>>(x, y, T, C, sigma, radius, causal_mode, causal);
+                             static_cast<cudaStream_t>(stream)>>>(x, y, T, C, sigma, radius, causal_mode, causal, pad_mode);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal,
+                                  mb_stream stream) {
+    return mb_gaussian_filter_ex(x, y, T, C, sigma, causal_mode, causal, 0, stream);
+}
+
+extern "C" int mb_salience(const float* short_env, const float* long_env, const float* envelope, float* out, int64_t n, mb_stream stream) {
+    MB_REQUIRE(short_env && long_env && envelope && out && n > 0, "mb_salience: bad argument");
+    salience_kernel<<<grid1d(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(short_env, long_env, envelope, out, n);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_latent_merge(float* latents, const float* sequence, const float* modulation, int mode, int lay0, int lay1, int T,
+                               int L, int D, mb_stream stream) {
+    MB_REQUIRE(latents && sequence && T > 0 && L > 0 && D > 0, "mb_latent_merge: bad argument");
+    MB_REQUIRE(mode >= 0 && mode <= 2 && (mode != 1 || modulation), "mb_latent_merge: mode %d / modulation mismatch", mode);
+    if (lay1 > L) lay1 = L;   // python slicing clips (the reference's slices reach 18 layers whatever num_ws is)
+    if (lay0 >= lay1) return MB_OK;
+    latent_merge_kernel<<<grid1d(static_cast<long long>(T) * (lay1 - lay0) * D), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        latents, sequence, modulation, mode, lay0, lay1, T, L, D);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

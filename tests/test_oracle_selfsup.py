@@ -1,0 +1,45 @@
+"""oracle/selfsup.py against the committed fixture (tests/golden/selfsup.pt, written by make_selfsup_golden.py after
+checking every function against the reference's own modules) and its natural spline against scipy."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import selfsup as OS
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "selfsup.pt")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(GOLD, weights_only=False)
+
+
+def test_envelope_ops_match_fixture(gold):
+    assert torch.equal(OS.salience_weighted(gold["env"], 5, 40), gold["salience"])
+    assert torch.equal(OS.gaussian_filter(gold["envs"], 3.0, mode="reflect"), gold["gauss_reflect"])
+    assert torch.equal(OS.clamp_peaks_percentile(gold["envs"], 90), gold["clamp_peaks"])
+    assert torch.equal(OS.emphasize(gold["envs"], 2.0, 75), gold["emphasize"])
+
+
+def test_latent_patch_matches_fixture(gold):
+    T = len(gold["base_latents"])
+    assert torch.equal(OS.spline_loop_latents(gold["palette"][:5], T, 2.5), gold["spline_loop"])
+    for rec in gold["latent_patch"]:
+        kw = dict(palette=gold["palette"], segmentations=gold["segmentations"], features=gold["features"], tempo=120.0, fps=24,
+                  segments=4, loop_bars=4, seq_feat_weight=0.8, mod_feat="rms", mod_feat_weight=0.6, **rec["case"])
+        out = OS.latent_patch(torch.Generator().manual_seed(rec["seed"]), gold["base_latents"].clone(), **kw)
+        assert torch.equal(out, rec["out"]), rec["case"]
+
+
+def test_natural_spline_matches_scipy():
+    from scipy.interpolate import CubicSpline
+
+    torch.manual_seed(1)
+    y = torch.randn(7, 3, 4)
+    t_in = torch.linspace(0, 1, 7)
+    t_out = torch.linspace(0, 3.3, 101) % 1
+    got = OS.natural_spline_eval(t_in, y, t_out)
+    want = CubicSpline(t_in.double().numpy(), y.reshape(7, -1).double().numpy(), bc_type="natural")(t_out.double().numpy())
+    assert np.allclose(got.reshape(101, -1).numpy(), want, atol=1e-5)

@@ -16,7 +16,8 @@ _PAD = {"circular": 0, "reflect": 1}
 
 def gaussian_filter(x, sigma, mode: str = "circular", causal: float = 1):
     """features/processing.py:11-50: temporal Gaussian, `mode` padding; the causal factor is commented out upstream (:24),
-    so `causal` is accepted and ignored exactly like there.  Any trailing shape ([T], [T,C], [T,C,L], [T,C,H,W])."""
+    so `causal` is accepted and ignored exactly like there.  Any trailing shape ([T], [T,C], [T,C,L], [T,C,H,W]); like the
+    reference (:47-48) a 2-D input comes back squeezed ([T,1] -> [T])."""
     if mode not in _PAD:
         raise NotImplementedError(f"gaussian_filter: padding mode '{mode}' (built: circular, reflect)")
     x = _cuda32(x, "x")
@@ -25,7 +26,7 @@ def gaussian_filter(x, sigma, mode: str = "circular", causal: float = 1):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().mb_gaussian_filter_ex(_lib.ptr(x), _lib.ptr(y), T, x.numel() // T, float(sigma), 0, 0.0, _PAD[mode],
                                                      _lib.stream_ptr()))
-    return y
+    return y.squeeze() if y.dim() == 2 else y
 
 
 def normalize(array):
@@ -83,6 +84,35 @@ def emphasize(envs, strength, percentile):
     x = x / hi
     x = x * (1 + torch.tanh(strength * (x - torch.quantile(x, q=percentile / 100, dim=0))))
     return (x * hi) + lo
+
+
+def drop_strength(audio, sr):
+    """features/audio.py:38-39: emphasize(gaussian_filter(rms(audio, sr), 10), strength=10, percentile=50) -> [T, 1]."""
+    from .features import rms
+
+    return emphasize(gaussian_filter(rms(audio, sr), 10), strength=10, percentile=50).unsqueeze(1)
+
+
+def tonnetz(y, sr, chroma_fn=None):
+    """features/audio.py:46-56: tonal centroid features, 6 x 12 projection of the L1-normalised chromagram -> [T, 6].
+    chroma_fn(y, sr) -> [12, T] (default: the device chromagram, transposed)."""
+    if chroma_fn is None:
+        from .chroma import chromagram
+
+        chroma_fn = lambda a, sr: chromagram(a, sr).T
+    chroma = _cuda32(chroma_fn(y, sr), "chroma")
+    n = chroma.shape[0]
+    dim_map = torch.linspace(0, 12, n, device=chroma.device)
+    scale = torch.tensor([7.0 / 6, 7.0 / 6, 3.0 / 2, 3.0 / 2, 2.0 / 3, 2.0 / 3], device=chroma.device)
+    V = scale.reshape(-1, 1) * dim_map
+    V[::2] -= 0.5
+    R = torch.tensor([1, 1, 1, 1, 0.5, 0.5], device=chroma.device)
+    phi = (R[:, None] * torch.cos(torch.pi * V)).t().contiguous()          # [12, 6]: host-sized design matrix
+    frames = (chroma / chroma.norm(p=1, dim=0)).t().contiguous()            # [T, 12]
+    out = torch.empty(frames.shape[0], 6, device=chroma.device)
+    with torch.cuda.device(chroma.device):  # out[T, 6] = frames[T, 12] @ phi[12, 6]: the mixing kernel of the noise sequencers
+        _lib.check(_lib.load().mb_noise_mix(_lib.ptr(phi), _lib.ptr(frames), frames.shape[0], n, 6, 0, _lib.ptr(out), _lib.stream_ptr()))
+    return out
 
 
 def spline_loop_latents(y, size, n_loops=1):

@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(128) input_prep_kernel(InputArgs a) {
     }
 }
 
-constexpr int kInPix = 16;
-// grid (ceil(size*size/16), B), 256 threads: Fourier features for 16 pixels, then the channel mix (fp32 FFMA: exact
+constexpr int kInPix = 16;   // pixels per CTA.  32 halves the L2 re-reads of the [C][C] mixing matrix but needs 177 registers (one CTA per SM): measured 0.41 -> 0.61 ms at B=8, so 16 stays
+// grid (ceil(size*size/kInPix), B), 256 threads: Fourier features for kInPix pixels, then the channel mix (fp32 FFMA: exact
 // parity with the oracle matters more here than tensor-core speed; the whole layer is 0.7 GFLOP/frame).
-// Features are staged [channel j][16 pixels] so one LDS.128 feeds four FMAs, and a thread owns output channels
+// Features are staged [channel j][kInPix pixels] so one LDS.128 feeds four FMAs, and a thread owns output channels
 // tid and tid + 256 so every staged value is used twice: 4 LDS + 2 LDG per 32 FMA (was 16 LDS + 1 LDG per 16 FMA).
 __global__ void __launch_bounds__(256) input_feat_kernel(InputArgs a) {
     extern __shared__ __align__(16) float sm[];  // [C][kInPix]

@@ -79,6 +79,22 @@ def emphasize(envs, strength, percentile):
     return (x * hi) + lo
 
 
+def drop_strength_from_rms(rms):
+    """features/audio.py:38-39 given rms(audio, sr) [T, 1]."""
+    return emphasize(gaussian_filter(rms, 10), strength=10, percentile=50).unsqueeze(1)
+
+
+def tonnetz_from_chroma(chroma):
+    """features/audio.py:46-56 given chroma_fn(y, sr) [12, T] -> [T, 6]."""
+    dim_map = torch.linspace(0, 12, chroma.shape[0])
+    scale = torch.tensor([7.0 / 6, 7.0 / 6, 3.0 / 2, 3.0 / 2, 2.0 / 3, 2.0 / 3])
+    V = scale.reshape(-1, 1) * dim_map
+    V[::2] -= 0.5
+    R = torch.tensor([1, 1, 1, 1, 0.5, 0.5])
+    phi = R[:, None] * torch.cos(torch.pi * V)
+    return (phi @ (chroma / chroma.norm(p=1, dim=0))).T
+
+
 def natural_spline_eval(t_in, y, t_out):
     """Natural cubic spline through (t_in[m], y[m, ...]) with uniform knots, evaluated at t_out (float64 inside)."""
     m = len(y)

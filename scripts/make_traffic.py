@@ -1,7 +1,7 @@
-"""profiles/traffic.json from an ncu CSV of one B=8 forward:
+"""profiles/traffic.json from an ncu CSV of one forward (merged per batch size: keys ..._b8, ..._b16):
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
       -k regex:'flrelu|conv_' --launch-skip 28 --launch-count 28 --csv --log-file gpurun_out/traffic.csv \
-      python scripts/one_forward.py 8 T
+      python scripts/one_forward.py 8 T        # then: make_traffic.py gpurun_out/traffic.csv profiles/traffic.json 8
 bench.py reports these measured DRAM bytes per step as roofline.traffic next to the algorithmic bytes."""
 import csv, json, sys
 src, dst, B = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 8
@@ -18,10 +18,12 @@ for r in rows:
         acc[fam]["bytes"] += val * scale
     elif metric.startswith("gpu__time_duration"):
         acc[fam]["ns"] += val * {"ns": 1.0, "us": 1e3, "ms": 1e6}[unit]
-out = {"source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE forward (B=%d), scripts/make_traffic.py" % B}
+import os
+out = json.load(open(dst)) if os.path.exists(dst) else {}
+out["source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE forward per batch size, scripts/make_traffic.py"
 for fam, d in acc.items():
     out["%s_bytes_per_step_b%d" % (fam, B)] = d["bytes"]
     out["%s_launches" % fam] = len(d["launches"])
-    out["%s_ncu_ms" % fam] = d["ns"] / 1e6
+    out["%s_ncu_ms_b%d" % (fam, B)] = d["ns"] / 1e6
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out))

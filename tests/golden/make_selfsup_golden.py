@@ -56,7 +56,11 @@ eq = types.ModuleType("maua.audiovisual.audioreactive.selfsupervised.features.ef
 eq.quantile = lambda t, q: torch.quantile(t, q)
 sys.modules[eq.__name__] = eq
 
+rosa = _pkg("librosa"); core = _pkg("librosa.core"); conv = types.ModuleType("librosa.core.convert")
+conv.note_to_hz = lambda n: 32.70319566257483
+core.convert = conv; rosa.core = core; sys.modules["librosa.core.convert"] = conv
 ref_proc = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.processing")
+ref_audio = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.audio")
 ref_lat = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.latent")
 
 
@@ -93,6 +97,18 @@ gold["salience"] = OS.salience_weighted(env, 5, 40)
 gold["gauss_reflect"] = OS.gaussian_filter(envs, 3.0, mode="reflect")
 gold["clamp_peaks"] = OS.clamp_peaks_percentile(envs, 90)
 gold["emphasize"] = OS.emphasize(envs, 2.0, 75)
+
+# drop_strength / tonnetz of features/audio.py with their inputs injected (rms and the chromagram are pinned elsewhere)
+rms_env = torch.rand(T, 1)
+chroma = torch.rand(12, T) + 0.01
+_rms = ref_audio.rms
+ref_audio.rms = lambda audio, sr: rms_env
+same(OS.drop_strength_from_rms(rms_env), ref_audio.drop_strength(None, 0), "drop_strength")
+ref_audio.rms = _rms
+same(OS.tonnetz_from_chroma(chroma), ref_audio.tonnetz(torch.zeros(1), 0, chroma_fn=lambda a, sr: chroma), "tonnetz")
+same(OS.gaussian_filter(rms_env, 3.0), ref_proc.gaussian_filter(rms_env, 3.0), "gaussian_filter [T,1] -> [T]")
+gold["rms_env"], gold["chroma"] = rms_env, chroma
+gold["drop_strength"], gold["tonnetz"] = OS.drop_strength_from_rms(rms_env), OS.tonnetz_from_chroma(chroma)
 
 palette = torch.randn(12, 18, 16)
 same(OS.spline_loop_latents(palette[:5], T, 2.5), ref_lat.spline_loop_latents(palette[:5], T, 2.5), "spline_loop_latents")

@@ -21,6 +21,9 @@ def test_envelope_ops_match_fixture(gold):
     assert torch.equal(OS.gaussian_filter(gold["envs"], 3.0, mode="reflect"), gold["gauss_reflect"])
     assert torch.equal(OS.clamp_peaks_percentile(gold["envs"], 90), gold["clamp_peaks"])
     assert torch.equal(OS.emphasize(gold["envs"], 2.0, 75), gold["emphasize"])
+    assert torch.equal(OS.drop_strength_from_rms(gold["rms_env"]), gold["drop_strength"])
+    assert torch.equal(OS.tonnetz_from_chroma(gold["chroma"]), gold["tonnetz"])
+    assert OS.gaussian_filter(gold["rms_env"], 3.0).shape == (len(gold["rms_env"]),)   # the reference squeezes [T,1] to [T]
 
 
 def test_latent_patch_matches_fixture(gold):

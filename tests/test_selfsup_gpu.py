@@ -42,6 +42,16 @@ def test_envelope_ops(cuda, gold):
     close(S.clamp_lower_percentile(envs, 20), torch.clamp(gold["envs"], torch.quantile(gold["envs"], 0.2, dim=0), None))
     with pytest.raises(RuntimeError):
         S.gaussian_filter(gold["env"], 3.0)   # CPU tensor: no fallback
+    close(S.gaussian_filter(gold["rms_env"].to(cuda), 3.0), OS.gaussian_filter(gold["rms_env"], 3.0))   # [T,1] -> [T]
+
+
+def test_drop_strength_and_tonnetz(cuda, gold, monkeypatch):
+    from maua_b200.audiovisual.audioreactive import features as F
+    from maua_b200.audiovisual.audioreactive import selfsupervised as S
+
+    monkeypatch.setattr(F, "rms", lambda audio, sr: gold["rms_env"].to(cuda))   # the device rms is pinned in test_audio_gpu.py
+    close(S.drop_strength(None, 0), gold["drop_strength"], 2e-5)
+    close(S.tonnetz(None, 0, chroma_fn=lambda a, sr: gold["chroma"].to(cuda)), gold["tonnetz"], 1e-5)
 
 
 def test_spline_loop_latents(cuda, gold):

@@ -81,6 +81,10 @@ struct InputArgs {
     float sampling_rate, bandwidth;
 };
 int sg3_input_launch(const InputArgs& a, cudaStream_t stream);
+// tensor-core input layer: features split into fp16 hi/lo parts [fh | fl | fh] (K = 3C) for a 1x1 tcgen05 conv against
+// weights [wh | wh | wl] (sg3_input_split_weights_launch + pack_weights_launch)
+int sg3_input_features_launch(const InputArgs& a, __half* feat, cudaStream_t stream);
+int sg3_input_split_weights_launch(const float* weight, float* w3, int C, cudaStream_t stream);
 
 struct ToRgbArgs {
     const __half* x;     // [B][Cin][H][Wp] (already * style of the torgb layer)

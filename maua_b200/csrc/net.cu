@@ -77,6 +77,9 @@ struct mb_net {
     double in_sr = 0, in_bw = 0;
     Param in_freqs, in_phases, in_weight, in_affine_w, in_affine_b, in_transform;
     float* in_weightT = nullptr;
+    float* in_w3 = nullptr;      // [C][3C] f32 hi/lo split of weight / sqrt(C) (tensor-core input layer)
+    __half* in_wpk = nullptr;    // the same packed for the 1x1 tcgen05 conv
+    int input_impl = 1;          // 1: split-fp16 tcgen05 channel mix, 0: fp32 CUDA-core kernel
     std::map<std::string, Param*> by_name;
     bool finalized = false;
     int conv_impl = 0;
@@ -286,6 +289,14 @@ extern "C" int mb_sg3_create(const mb_sg3_cfg* cfg, mb_net** out) {
         mb_net_destroy(net);
         return MB_ECUDA;
     }
+    if (C0 % 16 == 0) {
+        if (cudaMalloc(&net->in_w3, sizeof(float) * C0 * 3 * C0) != cudaSuccess ||
+            cudaMalloc(&net->in_wpk, sizeof(__half) * packed_weight_elems(C0, 3 * C0, 1)) != cudaSuccess) {
+            set_error("cudaMalloc failed");
+            mb_net_destroy(net);
+            return MB_ECUDA;
+        }
+    }
     net->by_name["input.freqs"] = &net->in_freqs;
     net->by_name["input.phases"] = &net->in_phases;
     net->by_name["input.weight"] = &net->in_weight;
@@ -381,6 +392,8 @@ extern "C" void mb_net_destroy(mb_net* net) {
         if (L.wsqT) cudaFree(L.wsqT);
     }
     if (net->in_weightT) cudaFree(net->in_weightT);
+    if (net->in_w3) cudaFree(net->in_w3);
+    if (net->in_wpk) cudaFree(net->in_wpk);
     for (cudaEvent_t e : net->ev_pool) cudaEventDestroy(e);
     delete net;
 }
@@ -428,6 +441,11 @@ extern "C" int mb_net_finalize(mb_net* net, mb_stream stream_) {
     }
     const int C0 = net->in_channels;
     transpose_kernel<<<ceil_div(C0 * C0, 256), 256, 0, stream>>>(net->in_weight.dev, net->in_weightT, C0);
+    if (net->in_wpk) {
+        int rr = sg3_input_split_weights_launch(net->in_weight.dev, net->in_w3, C0, stream);
+        if (rr == MB_OK) rr = pack_weights_launch(net->in_w3, net->in_wpk, nullptr, C0, 3 * C0, 1, 0, stream);
+        if (rr != MB_OK) return rr;
+    }
     MB_CUDA(cudaGetLastError());
     for (auto& L : net->layers) {
         if (!L.g.is_torgb) {
@@ -514,7 +532,9 @@ WsLayout ws_layout(const mb_net* net, int B, const SizePlan& sp) {
         const size_t x0 = static_cast<size_t>(B) * sp.in_h * sp.in_w * cpad8(net->in_channels);
         if (x0 > max_x) max_x = x0;
     }
-    size_t max_y = 0, max_p = 0;
+    // the tensor-core input layer stages its split features in P and its planar 1x1-conv output in Y
+    size_t max_y = static_cast<size_t>(B) * net->in_channels * net->in_size * pitch8(net->in_size);
+    size_t max_p = static_cast<size_t>(B) * net->in_size * net->in_size * 3 * net->in_channels;
     for (size_t i = 0; i < net->layers.size(); ++i) {
         const auto& L = net->layers[i];
         const LayerSize& ls = sp.l[i];
@@ -630,6 +650,7 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     else if (k == "conv_pm_shift") net->conv_pm_shift = value;
     else if (k == "conv_cm_shift") net->conv_cm_shift = value;
     else if (k == "flrelu_impl") net->flrelu_impl = value;
+    else if (k == "input_impl") net->input_impl = value;
     else if (k == "debug_stop") net->debug_stop = value;
     else if (k == "profile") net->profile = value;
     else if (k == "profile_reset") { net->prof.clear(); net->ev_used = 0; }
@@ -784,8 +805,25 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         ia.Cp = cpad8(net->in_channels);
         ia.sampling_rate = static_cast<float>(net->in_sr);
         ia.bandwidth = static_cast<float>(net->in_bw);
-        if ((r = sg3_input_launch(ia, stream)) != MB_OK) return r;
-        launches += 2;
+        if (net->input_impl == 1 && net->in_wpk) {
+            // features [fh | fl | fh] -> P (free until the first filtered_lrelu), 1x1 tcgen05 conv with the layer-0 style as
+            // the epilogue scale -> planar Y, exact transpose -> channels-last X
+            const int C3 = 3 * net->in_channels;
+            __half* feat = P;
+            if ((r = sg3_input_features_launch(ia, feat, stream)) != MB_OK) return r;
+            ConvTcArgs ca;
+            ca.x = feat; ca.wpk = net->in_wpk; ca.d = ia.style; ca.bias = nullptr; ca.y = Y;
+            ca.B = B; ca.Cin = C3; ca.Cout = net->in_channels; ca.Hin = net->in_size; ca.Win = net->in_size; ca.Cp_in = C3;
+            ca.Wp_out = pitch8(net->in_size); ca.ksz = 1; ca.pad = 0; ca.tile_w = net->conv_tile_w;
+            ca.pm_max_cout = 0; ca.narrow_a = net->conv_narrow_a; ca.num_sms = g_num_sms;
+            if ((r = conv_tc_launch(ca, stream)) != MB_OK) return r;
+            if ((r = planar_to_nhwc_launch(Y, X, B, net->in_channels, net->in_size, net->in_size, pitch8(net->in_size),
+                                           cpad8(net->in_channels), stream)) != MB_OK) return r;
+            launches += 4;
+        } else {
+            if ((r = sg3_input_launch(ia, stream)) != MB_OK) return r;
+            launches += 2;
+        }
         prof_mark(1, -1);
     }
     net->last_ws = workspace;

@@ -506,6 +506,71 @@ int styles_launch(const StylesArgs& a, cudaStream_t stream) {
     return MB_OK;
 }
 
+// ---- tensor-core variant of the input layer's channel mix --------------------------------------------------------
+// x[b, p, c] = sum_j feat[b, p, j] * (weight[c, j] / sqrt(C)) is a dense [pixels x C] x [C x C] contraction per frame: it
+// runs on the tcgen05 1x1 conv (conv_tc.cu) with BOTH operands split into fp16 hi + lo parts,
+//     feat * w ~= fh * wh + fl * wh + fh * wl      (the dropped fl * wl term is ~2^-22 relative),
+// i.e. K = 3 C: features stored as [fh | fl | fh], weights as [wh | wh | wl].  Products of fp16 values are exact in the
+// fp32 accumulator, so the result keeps fp32-class accuracy (the CUDA-core kernel above ran at 23 % of the fp32 FMA
+// peak: 0.65 ms per 16 frames).  The layer-0 style rides in the conv epilogue's per-(frame, cout) scale, so the
+// activation is rounded to fp16 once, exactly like the fp32 kernel.
+__global__ void __launch_bounds__(256) input_feat_split_kernel(InputArgs a, __half* __restrict__ out) {
+    const int npix = a.size * a.size;
+    const long long total = static_cast<long long>(a.B) * npix * a.C;
+    const float theta = 0.5f * static_cast<float>(a.size) / a.sampling_rate;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int j = static_cast<int>(idx % a.C);
+        const long long q = idx / a.C;
+        const int pix = static_cast<int>(q % npix);
+        const int b = static_cast<int>(q / npix);
+        const int h = pix / a.size, w = pix - h * a.size;
+        const float gx = ((2.0f * w + 1.0f) / static_cast<float>(a.size) - 1.0f) * theta;
+        const float gy = ((2.0f * h + 1.0f) / static_cast<float>(a.size) - 1.0f) * theta;
+        const float4 f = *reinterpret_cast<const float4*>(a.scratch + (static_cast<long long>(b) * a.C + j) * 4);
+        float arg = gx * f.x + gy * f.y;
+        arg = arg + f.z;
+        const float v = sinf(arg * 6.283185307179586f) * f.w;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        __half* o = out + q * (3LL * a.C);
+        o[j] = hi;
+        o[a.C + j] = lo;
+        o[2 * a.C + j] = hi;
+    }
+}
+
+// weight [C][C] f32 -> w3 [C][3C] f32 = [wh | wh | wl] of weight / sqrt(C) (every entry exactly representable in fp16)
+__global__ void input_w3_kernel(const float* __restrict__ w, float* __restrict__ w3, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * C) return;
+    const int c = idx / C, j = idx - c * C;
+    const float v = w[idx] * rsqrtf(static_cast<float>(C));
+    const float hi = __half2float(__float2half_rn(v));
+    const float lo = __half2float(__float2half_rn(v - hi));
+    float* o = w3 + static_cast<long long>(c) * 3 * C;
+    o[j] = hi;
+    o[C + j] = hi;
+    o[2 * C + j] = lo;
+}
+
+int sg3_input_split_weights_launch(const float* weight, float* w3, int C, cudaStream_t stream) {
+    input_w3_kernel<<<ceil_div(C * C, 256), 256, 0, stream>>>(weight, w3, C);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+// input_prep + split features into `feat` (channels-last [B][size][size][3C] fp16); the caller runs the 1x1 conv
+int sg3_input_features_launch(const InputArgs& a, __half* feat, cudaStream_t stream) {
+    MB_REQUIRE(a.C % 16 == 0, "input layer: %d channels is not a multiple of 16 (tensor-core path)", a.C);
+    input_prep_kernel<<<a.B, 128, 0, stream>>>(a);
+    MB_CUDA(cudaGetLastError());
+    const long long total = static_cast<long long>(a.B) * a.size * a.size * a.C;
+    input_feat_split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a, feat);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
 int sg3_input_launch(const InputArgs& a, cudaStream_t stream) {
     input_prep_kernel<<<a.B, 128, 0, stream>>>(a);
     MB_CUDA(cudaGetLastError());

@@ -234,6 +234,23 @@ int mb_audio_onsets_rms(const float* audio, int64_t n, const float* mel_filterba
 int mb_audio_hpss_component(const float* audio, int64_t n, float margin, int which, float* out,
                             void* workspace, size_t workspace_bytes, mb_stream stream);
 
+/* Spectral descriptors of the torch-native feature list (selfsupervised/features/audio.py:59-133, the AFEATFNS of
+ * selfsupervised/mir.py:9): the device magnitude spectrogram [T][1025] (spectrogram(y), power 1, last STFT column dropped)
+ * and mel power spectrogram [T][128] (melspectrogram(y, sr)), frame-major, and on top of them
+ *   mb_spectral_flatness  exp(mean(log(max(amin, S^power)))) / mean(max(amin, S^power)) per frame            (:123-133)
+ *   mb_spectral_contrast  per octave band, power_to_db(mean of the top quantile) - power_to_db(mean of the bottom
+ *                         quantile); bands as bin ranges [lo, hi) with `cnt` bins per quantile, designed on the host
+ *                         exactly as the reference's loop (:88-113); scratch: device float32 [2 * n_bands * T]       (:69-120)
+ *   mb_mfcc               power_to_db (global top_db 80) of the mel power spectrogram (in place), orthonormal DCT-II over
+ *                         the mel bands, first n_mfcc coefficients -> [T][n_mfcc]                                    (:59-64)
+ * Workspace of mb_audio_spectrogram: mb_audio_workspace_bytes(n). */
+int mb_audio_spectrogram(const float* audio, int64_t n, const float* mel_filterbank, float* mag_out, float* mel_out,
+                         void* workspace, size_t workspace_bytes, mb_stream stream);
+int mb_spectral_flatness(const float* mag, int T, float amin, float power, float* out, mb_stream stream);
+int mb_spectral_contrast(const float* mag, int T, int n_bands, const int32_t* lo, const int32_t* hi, const int32_t* cnt,
+                         int linear, float* scratch, float* out, mb_stream stream);
+int mb_mfcc(float* mel, int T, int n_mfcc, float* out, mb_stream stream);
+
 /* Constant-Q chroma, rosa/spectral.py:286-325 chroma_cqt over rosa/constantq.py:13-116 cqt (recursive octaves:
  * kaiser-sinc decimation by 2, rectangular STFT, sparse FFT-domain filter bank) and rosa/convert.py:69-117.
  *   audio        device float32 [n], n a multiple of hop; hop a multiple of 2^(n_octaves-1)

@@ -64,6 +64,10 @@ _SIGNATURES = {
     "mb_salience": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "mb_latent_merge": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mb_spline_loop_latents": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, C.c_int, _P, _P, _P]),
+    "mb_audio_spectrogram": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.c_size_t, _P]),
+    "mb_spectral_flatness": (C.c_int, [_P, C.c_int, C.c_float, C.c_float, _P, _P]),
+    "mb_spectral_contrast": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _P, _P, _P]),
+    "mb_mfcc": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "mb_net_output_shape": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_net_read_activation": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "mb_net_last_launch_count": (C.c_int, [_P]),

@@ -1,7 +1,8 @@
 """Audio-reactive feature / envelope / latent functions on the device (mirror of
 maua.audiovisual.audioreactive and its torch-native twin selfsupervised.features.audio)."""
 from .chroma import chroma_cens, chroma_cqt, chromagram, cqt_magnitude, estimate_tuning  # noqa: F401
-from .features import harmonic, mel_filterbank, onset_peaks, onsets, onsets_rms, percussive, rms  # noqa: F401
+from .features import (harmonic, mel_filterbank, mfcc, onset_peaks, onsets, onsets_rms, percussive, rms,  # noqa: F401
+                       spectral_contrast, spectral_flatness)
 from .latent import multi_weighted, select_modulo, single_weighted, slerp_loops, spline_loops, tempo_loops  # noqa: F401,E402
 from . import noise  # noqa: F401,E402
 from .signal import compress, expand, gaussian_filter, normalize, percentile, percentile_clip, resample  # noqa: F401,E402

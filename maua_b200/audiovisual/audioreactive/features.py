@@ -130,3 +130,88 @@ def onsets_rms(audio, sr):
     """Both envelopes from one device pass -> ([T,1], [T,1])."""
     o, r, _, _, _ = _features(audio, sr)
     return o.unsqueeze(-1), r.unsqueeze(-1)
+
+
+# ---- spectral descriptors of the torch-native feature list (features/audio.py:59-133) ---------------------------------
+def _spectrogram(y, sr, want_mag, want_mel):
+    """Device magnitude spectrogram [T,1025] and / or mel power spectrogram [T,128] (frame-major)."""
+    if not y.is_cuda:
+        raise RuntimeError("maua_b200 audio features need a CUDA tensor (no CPU fallback)")
+    lib = _lib.load()
+    y = y.detach().to(torch.float32).contiguous().reshape(-1)
+    n = y.numel()
+    if n % HOP:
+        raise ValueError(f"audio length must be a multiple of {HOP} (resample to sr = 1024 * fps first)")
+    T = n // HOP
+    dev = y.device
+    with torch.cuda.device(dev):
+        mag = torch.empty(T, N_FFT // 2 + 1, device=dev) if want_mag else None
+        mel = torch.empty(T, N_MELS, device=dev) if want_mel else None
+        fb = mel_filterbank(sr, fmax=None).to(dev) if want_mel else None
+        nbytes = lib.mb_audio_workspace_bytes(n)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 256
+        _lib.check(lib.mb_audio_spectrogram(_lib.ptr(y), n, _lib.ptr(fb), _lib.ptr(mag), _lib.ptr(mel),
+                                            C.c_void_p(ws.data_ptr() + off), nbytes, _lib.stream_ptr()))
+    return mag, mel
+
+
+def spectral_flatness(y, sr, n_fft=N_FFT, hop_length=HOP, amin=1e-10, power=2.0):
+    """Geometric / arithmetic mean of the thresholded power spectrum per frame -> [T,1] (features/audio.py:123-133)."""
+    if (n_fft, hop_length) != (N_FFT, HOP):
+        raise NotImplementedError("spectral_flatness: only n_fft=2048, hop_length=1024")
+    mag, _ = _spectrogram(y, sr, True, False)
+    out = torch.empty(mag.shape[0], device=mag.device)
+    with torch.cuda.device(mag.device):
+        _lib.check(_lib.load().mb_spectral_flatness(_lib.ptr(mag), mag.shape[0], float(amin), float(power), _lib.ptr(out), _lib.stream_ptr()))
+    return out.unsqueeze(-1)
+
+
+def contrast_bands(sr, n_fft=N_FFT, fmin=200.0, n_bands=6, quantile=0.02):
+    """Bin ranges [lo, hi) and quantile sizes of the octave bands, exactly as the reference's loop builds them
+    (features/audio.py:81-108): host arithmetic on the FFT bin frequencies."""
+    freq = torch.linspace(0, float(sr) / 2, int(1 + n_fft // 2))
+    octa = torch.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** torch.arange(0, n_bands + 1))
+    lo, hi, cnt = [], [], []
+    for k, (f_low, f_high) in enumerate(zip(octa[:-1], octa[1:])):
+        band = torch.logical_and(freq >= f_low, freq <= f_high)
+        idx = band.flatten().nonzero()
+        if k > 0:
+            band[idx[0] - 1] = True
+        if k == n_bands:
+            band[idx[-1] + 1:] = True
+        where = band.nonzero().flatten()
+        first, last = int(where[0]), int(where[-1]) + 1
+        if k < n_bands:
+            last -= 1  # sub_band[:-1]
+        q = torch.round(quantile * torch.sum(band))
+        lo.append(first); hi.append(last); cnt.append(int(torch.maximum(q, torch.ones(()))))
+    return lo, hi, cnt
+
+
+def spectral_contrast(y, sr, n_fft=N_FFT, hop_length=HOP, fmin=200.0, n_bands=6, quantile=0.02, linear=False):
+    """Octave-band spectral contrast -> [T, n_bands + 1] (features/audio.py:69-120)."""
+    if (n_fft, hop_length) != (N_FFT, HOP):
+        raise NotImplementedError("spectral_contrast: only n_fft=2048, hop_length=1024")
+    mag, _ = _spectrogram(y, sr, True, False)
+    lo, hi, cnt = contrast_bands(sr, n_fft, fmin, n_bands, quantile)
+    nb, T = len(lo), mag.shape[0]
+    arr = lambda v: (C.c_int32 * nb)(*v)
+    out = torch.empty(T, nb, device=mag.device)
+    scratch = torch.empty(2 * nb * T, device=mag.device)
+    with torch.cuda.device(mag.device):
+        _lib.check(_lib.load().mb_spectral_contrast(_lib.ptr(mag), T, nb, arr(lo), arr(hi), arr(cnt), int(bool(linear)), _lib.ptr(scratch),
+                                                    _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
+def mfcc(y, sr, n_mfcc=20, norm=False):
+    """Mel-frequency cepstral coefficients -> [T, n_mfcc] (features/audio.py:59-64): dB mel spectrum, orthonormal DCT-II."""
+    _, mel = _spectrogram(y, sr, False, True)
+    out = torch.empty(mel.shape[0], int(n_mfcc), device=mel.device)
+    with torch.cuda.device(mel.device):
+        _lib.check(_lib.load().mb_mfcc(_lib.ptr(mel), mel.shape[0], int(n_mfcc), _lib.ptr(out), _lib.stream_ptr()))
+    if norm is True:
+        out = out / out.norm(p=2)
+    return out

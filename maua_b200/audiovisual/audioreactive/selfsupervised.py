@@ -207,3 +207,29 @@ def noise_patch(rng, noise, features, tempo, fps, patch_type, loop_bars, seq_fea
             noise[n] = new_noise
         noise[n] = _noise.ScaleBias(noise[n], scale=noise_std, bias=noise_mean)
     return noise
+
+
+# ---- the feature half of retrieve_music_information (mir.py:9-11, 24-25, 43) ------------------------------------------------
+UNITFEATS = ["rms", "drop_strength", "onsets", "spectral_flatness"]
+ALLFEATS = ["chromagram", "tonnetz", "mfcc", "spectral_contrast"] + UNITFEATS
+
+
+def audio_feature_functions():
+    """AFEATFNS of mir.py:9 as device functions, in the reference's order."""
+    from .chroma import chromagram
+    from .features import mfcc, onsets, rms, spectral_contrast, spectral_flatness
+
+    return [chromagram, tonnetz, mfcc, spectral_contrast, spectral_flatness, rms, drop_strength, onsets]
+
+
+def postprocess_feature(af):
+    """mir.py:43: normalize(salience_weighted(gaussian_filter(af, sigma=2)))."""
+    return normalize(salience_weighted(gaussian_filter(af, sigma=2)))
+
+
+def extract_features(audio, sr, postprocess=True):
+    """{name: [T, C]} for the eight audio features of mir.py:9 (raw, or post-processed as retrieve_music_information returns
+    them).  The segmentations and the tempo estimate of that function (Laplacian segmentation, librosa beat tracking) are
+    not built: pass them to Patch from elsewhere."""
+    feats = {fn.__name__: fn(audio, sr) for fn in audio_feature_functions()}
+    return {k: postprocess_feature(v) for k, v in feats.items()} if postprocess else feats

@@ -298,6 +298,115 @@ __global__ void audio_tables_kernel(float2* tw, float* window) {
     }
 }
 
+
+// ---- spectral descriptors of the torch-native feature list (features/audio.py:59-133) ----------------------------
+// spectral_flatness (:123-133): per frame exp(mean(log(max(amin, |X|^2)))) / mean(max(amin, |X|^2)) over the 1025 bins.
+__global__ void __launch_bounds__(256) flatness_kernel(const float* __restrict__ mag, int T, float amin, float power, float* __restrict__ out) {
+    __shared__ float s_log[8], s_sum[8];
+    const int t = blockIdx.x;
+    const float* m = mag + static_cast<long long>(t) * kBins;
+    float lsum = 0.0f, sum = 0.0f;
+    for (int k = threadIdx.x; k < kBins; k += blockDim.x) {
+        const float v = fmaxf(amin, powf(m[k], power));
+        lsum += logf(v);
+        sum += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_log[threadIdx.x >> 5] = lsum; s_sum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.0f, b = 0.0f;
+        for (int i = 0; i < 8; ++i) { a += s_log[i]; b += s_sum[i]; }
+        out[t] = expf(a / static_cast<float>(kBins)) / (b / static_cast<float>(kBins));
+    }
+}
+
+// spectral_contrast (:69-120): per frame and band, mean of the `cnt` smallest (valley) and `cnt` largest (peak) magnitudes
+// of the band's bins [lo, hi).  Selection by rank counting (ties broken by index): the same multiset the reference's sort
+// picks.  peak / valley: [n_bands][T].
+struct ContrastBands { int lo[8], hi[8], cnt[8], n; };
+__global__ void __launch_bounds__(256) contrast_kernel(const float* __restrict__ mag, int T, ContrastBands bands, float* __restrict__ peak,
+                                                        float* __restrict__ valley) {
+    __shared__ float row[kBins];
+    __shared__ float s_v[8], s_p[8];
+    const int t = blockIdx.x;
+    for (int k = threadIdx.x; k < kBins; k += blockDim.x) row[k] = mag[static_cast<long long>(t) * kBins + k];
+    __syncthreads();
+    for (int b = 0; b < bands.n; ++b) {
+        const int lo = bands.lo[b], n = bands.hi[b] - lo, cnt = bands.cnt[b];
+        float v = 0.0f, pk = 0.0f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const float x = row[lo + i];
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const float y = row[lo + j];
+                rank += (y < x) || (y == x && j < i);
+            }
+            if (rank < cnt) v += x;
+            if (rank >= n - cnt) pk += x;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+            pk += __shfl_xor_sync(0xffffffffu, pk, o);
+        }
+        if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = v; s_p[threadIdx.x >> 5] = pk; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.0f, c = 0.0f;
+            for (int i = 0; i < 8; ++i) { a += s_v[i]; c += s_p[i]; }
+            valley[static_cast<long long>(b) * T + t] = a / static_cast<float>(cnt);
+            peak[static_cast<long long>(b) * T + t] = c / static_cast<float>(cnt);
+        }
+        __syncthreads();
+    }
+}
+
+// out[t][b] = peak[b][t] - valley[b][t]
+__global__ void contrast_diff_kernel(const float* __restrict__ peak, const float* __restrict__ valley, int T, int nb, float* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= T * nb) return;
+    const int b = idx / T, t = idx - b * T;
+    out[static_cast<long long>(t) * nb + b] = peak[idx] - valley[idx];
+}
+
+// power_to_db (rosa/convert.py:7-12, ref 1, amin 1e-10, top_db 80 below the GLOBAL maximum): one block, n values in place
+__global__ void __launch_bounds__(1024) power_to_db_kernel(float* __restrict__ x, long long n, float top_db) {
+    __shared__ float s_max[32];
+    float mx = -3.0e38f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float db = 10.0f * log10f(fmaxf(1e-10f, x[i]));
+        x[i] = db;
+        mx = fmaxf(mx, db);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, s_max[i]);
+        s_max[0] = mx;
+    }
+    __syncthreads();
+    const float floor_db = s_max[0] - top_db;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) x[i] = fmaxf(x[i], floor_db);
+}
+
+// mfcc (:59-64): orthonormal DCT-II of the dB mel spectrum along the 128 mel bands, first n_mfcc coefficients.
+// db: [T][128] frame-major, out: [T][n_mfcc].
+__global__ void __launch_bounds__(128) mfcc_dct_kernel(const float* __restrict__ db, int T, int n_mfcc, float* __restrict__ out) {
+    __shared__ float row[kMels];
+    const int t = blockIdx.x;
+    row[threadIdx.x] = db[static_cast<long long>(t) * kMels + threadIdx.x];
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_mfcc; k += blockDim.x) {
+        float acc = 0.0f;
+        for (int m = 0; m < kMels; ++m) acc = fmaf(row[m], cospif(static_cast<float>(k * (2 * m + 1)) / static_cast<float>(2 * kMels)), acc);
+        out[static_cast<long long>(t) * n_mfcc + k] = acc * (k == 0 ? rsqrtf(static_cast<float>(kMels)) : sqrtf(2.0f / static_cast<float>(kMels)));
+    }
+}
+
 }  // namespace
 }  // namespace mb
 
@@ -376,6 +485,84 @@ extern "C" int mb_audio_hpss_component(const float* audio, int64_t n, float marg
     hpss_kernel<<<hg, 128, 0, stream>>>(spec, mag, T + 1, margin, which, comp);
     istft_frame_kernel<<<T + 1, 256, 0, stream>>>(comp, tw, window, frames);
     istft_ola_kernel<<<148 * 4, 256, 0, stream>>>(frames, window, n, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+/* Magnitude spectrogram and mel power spectrogram of the torch-native feature path (rosa/spectral.py:59-70:
+ * spectrogram(y)[:, :T] with power 1, melspectrogram(y, sr) with power 2), frame-major: mag [T][1025], mel [T][128]
+ * (either may be NULL).  audio: device float32 [n], n a multiple of 1024. */
+extern "C" int mb_audio_spectrogram(const float* audio, int64_t n, const float* mel_filterbank, float* mag_out, float* mel_out,
+                                    void* workspace, size_t workspace_bytes, mb_stream stream_) {
+    MB_REQUIRE(audio && workspace && (mag_out || mel_out), "mb_audio_spectrogram: null argument");
+    MB_REQUIRE(!mel_out || mel_filterbank, "mb_audio_spectrogram: mel_out needs a mel filter bank");
+    MB_REQUIRE(n >= 16 * kHop && n % kHop == 0, "mb_audio_spectrogram: need a multiple of %d samples (>= %d), got %lld", kHop, 16 * kHop,
+               static_cast<long long>(n));
+    const AudioWs w = audio_ws(n);
+    if (workspace_bytes < w.total) {
+        set_error("mb_audio_spectrogram: workspace too small (%zu < %zu bytes)", workspace_bytes, w.total);
+        return MB_ENOMEM;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int T = static_cast<int>(n / kHop);
+    uint8_t* base = static_cast<uint8_t*>(workspace);
+    float2* tw = reinterpret_cast<float2*>(base + w.tw);
+    float* window = reinterpret_cast<float*>(base + w.window);
+    audio_tables_kernel<<<kNfft / 256, 256, 0, stream>>>(tw, window);
+    if (mag_out) {
+        float2* spec = reinterpret_cast<float2*>(base + w.spec);
+        float* mag = reinterpret_cast<float*>(base + w.mag);
+        float* rms_tmp = reinterpret_cast<float*>(base + w.env);
+        stft_kernel<<<T + 1, 256, 0, stream>>>(audio, n, T, 0, tw, window, spec, mag, rms_tmp, nullptr, nullptr);
+        MB_CUDA(cudaMemcpyAsync(mag_out, mag, sizeof(float) * static_cast<size_t>(T) * kBins, cudaMemcpyDeviceToDevice, stream));
+    }
+    if (mel_out) stft_kernel<<<T, 256, 0, stream>>>(audio, n, T, 1, tw, window, nullptr, nullptr, nullptr, mel_filterbank, mel_out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+/* spectral_flatness (features/audio.py:123-133) from mag [T][1025] -> out [T]. */
+extern "C" int mb_spectral_flatness(const float* mag, int T, float amin, float power, float* out, mb_stream stream) {
+    MB_REQUIRE(mag && out && T > 0, "mb_spectral_flatness: bad argument");
+    flatness_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(mag, T, amin, power, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+/* spectral_contrast (features/audio.py:69-120) from mag [T][1025]: band b covers bins [lo[b], hi[b]) and averages its
+ * cnt[b] smallest / largest magnitudes (host-designed from the FFT bin frequencies, as the reference's loop does);
+ * out [T][n_bands] = power_to_db(peak) - power_to_db(valley) (linear = 0) or peak - valley (linear = 1).
+ * scratch: device float32 [2 * n_bands * T]. */
+extern "C" int mb_spectral_contrast(const float* mag, int T, int n_bands, const int32_t* lo, const int32_t* hi, const int32_t* cnt,
+                                    int linear, float* scratch, float* out, mb_stream stream_) {
+    MB_REQUIRE(mag && lo && hi && cnt && scratch && out && T > 0 && n_bands > 0 && n_bands <= 8, "mb_spectral_contrast: bad argument");
+    ContrastBands bands;
+    bands.n = n_bands;
+    for (int b = 0; b < n_bands; ++b) {
+        MB_REQUIRE(lo[b] >= 0 && hi[b] <= kBins && hi[b] > lo[b] && cnt[b] >= 1 && cnt[b] <= hi[b] - lo[b], "mb_spectral_contrast: bad band %d", b);
+        bands.lo[b] = lo[b]; bands.hi[b] = hi[b]; bands.cnt[b] = cnt[b];
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    float* peak = scratch;
+    float* valley = scratch + static_cast<size_t>(n_bands) * T;
+    contrast_kernel<<<T, 256, 0, stream>>>(mag, T, bands, peak, valley);
+    const long long nn = static_cast<long long>(n_bands) * T;
+    if (!linear) {
+        power_to_db_kernel<<<1, 1024, 0, stream>>>(peak, nn, 80.0f);
+        power_to_db_kernel<<<1, 1024, 0, stream>>>(valley, nn, 80.0f);
+    }
+    contrast_diff_kernel<<<(static_cast<int>(nn) + 255) / 256, 256, 0, stream>>>(peak, valley, T, n_bands, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+/* mfcc (features/audio.py:59-64) from the mel POWER spectrogram mel [T][128] (modified in place: converted to dB):
+ * power_to_db (top_db 80 below the global maximum) -> orthonormal DCT-II over the mel bands -> out [T][n_mfcc]. */
+extern "C" int mb_mfcc(float* mel, int T, int n_mfcc, float* out, mb_stream stream_) {
+    MB_REQUIRE(mel && out && T > 0 && n_mfcc > 0 && n_mfcc <= kMels, "mb_mfcc: bad argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    power_to_db_kernel<<<1, 1024, 0, stream>>>(mel, static_cast<long long>(T) * kMels, 80.0f);
+    mfcc_dct_kernel<<<T, 128, 0, stream>>>(mel, T, n_mfcc, out);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -422,3 +422,67 @@ def chroma_cens(y, sr, hop_length=1024, tuning=None, win_len_smooth=41):
 def chromagram(audio, sr):
     """features/audio.py:44."""
     return chroma_cens(harmonic(audio), sr).T
+
+
+# ---- spectral descriptors (features/audio.py:59-133) -------------------------------------------------------------------
+def dct(x, norm=None):
+    """rosa/spectral.py:35-56 (FFT-based DCT-II over the last axis)."""
+    import numpy as np
+
+    x_shape = x.shape
+    N = x_shape[-1]
+    x = x.contiguous().view(-1, N)
+    v = torch.cat([x[:, ::2], x[:, 1::2].flip([1])], dim=1)
+    Vc = torch.view_as_real(torch.fft.fft(v, dim=1))
+    k = -torch.arange(N, dtype=x.dtype)[None, :] * np.pi / (2 * N)
+    V = Vc[:, :, 0] * torch.cos(k) - Vc[:, :, 1] * torch.sin(k)
+    if norm == "ortho":
+        V[:, 0] /= np.sqrt(N) * 2
+        V[:, 1:] /= np.sqrt(N / 2) * 2
+    return 2 * V.view(*x_shape)
+
+
+def mfcc(y, sr, n_mfcc=20, norm=False):
+    """features/audio.py:59-64."""
+    S = power_to_db(melspectrogram(y, sr))
+    M = dct(S.permute(1, 0), norm="ortho").permute(1, 0)[:n_mfcc]
+    if norm is True:
+        M = M / M.norm(p=2)
+    return M.T
+
+
+def spectral_contrast(y, sr, fmin=200.0, n_bands=6, quantile=0.02, linear=False):
+    """features/audio.py:69-120."""
+    S = spectrogram(y)
+    freq = torch.linspace(0, float(sr) / 2, int(1 + N_FFT // 2))
+    octa = torch.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** torch.arange(0, n_bands + 1))
+    valley = torch.zeros((n_bands + 1, S.shape[1]))
+    peak = torch.zeros_like(valley)
+    for k, (f_low, f_high) in enumerate(zip(octa[:-1], octa[1:])):
+        current_band = torch.logical_and(freq >= f_low, freq <= f_high)
+        idx = current_band.flatten().nonzero()
+        if k > 0:
+            current_band[idx[0] - 1] = True
+        if k == n_bands:
+            current_band[idx[-1] + 1:] = True
+        sub_band = S[current_band]
+        if k < n_bands:
+            sub_band = sub_band[:-1]
+        idx = torch.round(quantile * torch.sum(current_band))
+        idx = int(torch.maximum(idx, torch.ones(())))
+        sortedr = torch.sort(sub_band, dim=0).values
+        valley[k] = torch.mean(sortedr[:idx], dim=0)
+        peak[k] = torch.mean(sortedr[-idx:], dim=0)
+    if linear:
+        return (peak - valley).T
+    return (power_to_db(peak) - power_to_db(valley)).T
+
+
+def spectral_flatness(y, sr, amin=1e-10, power=2.0):
+    """features/audio.py:123-133."""
+    S = spectrogram(y, power=1.0)
+    S_thresh = torch.maximum(torch.tensor(amin), S ** power)
+    gmean = torch.exp(torch.mean(torch.log(S_thresh), axis=0))
+    amean = torch.mean(S_thresh, axis=0)
+    return (gmean / amean).unsqueeze(-1)

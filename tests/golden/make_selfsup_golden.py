@@ -110,6 +110,17 @@ same(OS.gaussian_filter(rms_env, 3.0), ref_proc.gaussian_filter(rms_env, 3.0), "
 gold["rms_env"], gold["chroma"] = rms_env, chroma
 gold["drop_strength"], gold["tonnetz"] = OS.drop_strength_from_rms(rms_env), OS.tonnetz_from_chroma(chroma)
 
+# spectral descriptors of features/audio.py:59-133 on a 2 s test signal at sr = 1024 * 24
+from oracle import audio as OA  # noqa: E402
+sr = 1024 * 24
+tt = torch.arange(2 * sr) / sr
+sig = 0.5 * torch.sin(2 * torch.pi * (200 * tt + 900 * tt ** 2)) * (0.6 + 0.4 * torch.sin(2 * torch.pi * 3 * tt)) + 0.05 * torch.randn(2 * sr)
+same(OA.mfcc(sig, sr), ref_audio.mfcc(sig, sr), "mfcc")
+same(OA.spectral_contrast(sig, sr), ref_audio.spectral_contrast(sig, sr), "spectral_contrast")
+same(OA.spectral_flatness(sig, sr), ref_audio.spectral_flatness(sig, sr), "spectral_flatness")
+gold["spec_signal"], gold["spec_sr"] = sig, sr
+gold["mfcc"], gold["spectral_contrast"], gold["spectral_flatness"] = OA.mfcc(sig, sr), OA.spectral_contrast(sig, sr), OA.spectral_flatness(sig, sr)
+
 palette = torch.randn(12, 18, 16)
 same(OS.spline_loop_latents(palette[:5], T, 2.5), ref_lat.spline_loop_latents(palette[:5], T, 2.5), "spline_loop_latents")
 gold["palette"] = palette

@@ -46,3 +46,45 @@ def test_natural_spline_matches_scipy():
     got = OS.natural_spline_eval(t_in, y, t_out)
     want = CubicSpline(t_in.double().numpy(), y.reshape(7, -1).double().numpy(), bc_type="natural")(t_out.double().numpy())
     assert np.allclose(got.reshape(101, -1).numpy(), want, atol=1e-5)
+
+
+def test_spectral_descriptors_match_fixture(gold):
+    from oracle import audio as OA
+
+    sig, sr = gold["spec_signal"], gold["spec_sr"]
+    assert torch.equal(OA.mfcc(sig, sr), gold["mfcc"]) and gold["mfcc"].shape == (48, 20)
+    assert torch.equal(OA.spectral_contrast(sig, sr), gold["spectral_contrast"]) and gold["spectral_contrast"].shape == (48, 7)
+    assert torch.equal(OA.spectral_flatness(sig, sr), gold["spectral_flatness"]) and gold["spectral_flatness"].shape == (48, 1)
+
+
+def test_oracle_dct_is_the_orthonormal_dct2():
+    from scipy.fft import dct as sdct
+
+    from oracle import audio as OA
+
+    x = torch.randn(5, 128)
+    assert np.allclose(OA.dct(x, norm="ortho").numpy(), sdct(x.numpy(), type=2, norm="ortho", axis=-1), atol=1e-4)
+
+
+def test_contrast_band_design_matches_the_reference_loop():
+    """Host band design of the device kernel (features.contrast_bands) selects the bins the oracle's boolean masks select."""
+    from maua_b200.audiovisual.audioreactive.features import contrast_bands
+
+    sr, n_bands, fmin, quantile = 1024 * 24, 6, 200.0, 0.02
+    lo, hi, cnt = contrast_bands(sr)
+    freq = torch.linspace(0, float(sr) / 2, 1025)
+    octa = torch.zeros(n_bands + 2)
+    octa[1:] = fmin * (2.0 ** torch.arange(0, n_bands + 1))
+    for k, (f_low, f_high) in enumerate(zip(octa[:-1], octa[1:])):
+        band = torch.logical_and(freq >= f_low, freq <= f_high)
+        idx = band.flatten().nonzero()
+        if k > 0:
+            band[idx[0] - 1] = True
+        if k == n_bands:
+            band[idx[-1] + 1:] = True
+        bins = band.nonzero().flatten().tolist()
+        if k < n_bands:
+            bins = bins[:-1]
+        assert bins == list(range(lo[k], hi[k])), k
+        assert cnt[k] == int(torch.maximum(torch.round(quantile * torch.sum(band)), torch.ones(())))
+    assert hi[-1] == 1025

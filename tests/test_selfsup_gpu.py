@@ -102,3 +102,44 @@ def test_noise_patch(cuda, gold):
         mod_mean = (0.7 * gold["features"]["rms"]).mean(1)
         want = ON.scale_bias(ON.modulate(before[n].cpu(), new, mod_mean, 0, 4), 2.0, 0.1)
         close(sb(0, 4), want, 1e-4)
+
+
+def test_spectral_descriptors(cuda, gold):
+    """mfcc / spectral_contrast / spectral_flatness on the device against the pinned oracle values.  The device FFT and the
+    torch CPU FFT differ in rounding: dB-domain features are compared at 2e-3 dB-scale absolute, flatness relatively."""
+    from maua_b200.audiovisual.audioreactive import features as F
+
+    sig, sr = gold["spec_signal"].to(cuda), gold["spec_sr"]
+    m = F.mfcc(sig, sr)
+    assert m.shape == (48, 20)
+    close(m, gold["mfcc"], 5e-3)                      # coefficients are O(100): 5e-5 relative
+    c = F.spectral_contrast(sig, sr)
+    assert c.shape == (48, 7)
+    close(c, gold["spectral_contrast"], 5e-3)         # dB differences, O(10)
+    f = F.spectral_flatness(sig, sr)
+    assert f.shape == (48, 1)
+    rel = float(((f.cpu() - gold["spectral_flatness"]).abs() / gold["spectral_flatness"]).max())
+    assert rel < 1e-3, rel
+    lin = F.spectral_contrast(sig, sr, linear=True)
+    from oracle import audio as OA
+    close(lin, OA.spectral_contrast(gold["spec_signal"], sr, linear=True), 1e-3)
+
+
+def test_extract_features_end_to_end(cuda, gold):
+    """All eight AFEATFNS (mir.py:9) on the device for a 16 s signal, post-processed as retrieve_music_information does
+    (long_sigma 80 needs more than 320 frames); the chain against the oracle composition on the device's own raw features."""
+    from maua_b200.audiovisual.audioreactive import selfsupervised as S
+
+    sr = gold["spec_sr"]
+    sig = torch.cat([gold["spec_signal"], gold["spec_signal"].flip(0)] * 4).to(cuda)   # 16 s = 384 frames
+    raw = S.extract_features(sig, sr, postprocess=False)
+    assert list(raw) == ["chromagram", "tonnetz", "mfcc", "spectral_contrast", "spectral_flatness", "rms", "drop_strength", "onsets"]
+    assert {k: tuple(v.shape) for k, v in raw.items()} == {
+        "chromagram": (384, 12), "tonnetz": (384, 6), "mfcc": (384, 20), "spectral_contrast": (384, 7), "spectral_flatness": (384, 1),
+        "rms": (384, 1), "drop_strength": (384, 1), "onsets": (384, 1)}
+    post = S.extract_features(sig, sr)
+    for k, v in raw.items():
+        assert torch.isfinite(post[k]).all(), k
+        want = OS.normalize(OS.salience_weighted(OS.gaussian_filter(v.cpu(), sigma=2)))
+        close(post[k].reshape(want.shape), want, 2e-4)
+        assert float(post[k].min()) >= 0.0 and float(post[k].max()) <= 1.0 + 1e-6

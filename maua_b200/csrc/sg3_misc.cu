@@ -276,11 +276,13 @@ __global__ void __launch_bounds__(256) input_feat_kernel(InputArgs a) {
 // Fused ToRGB layer + network output: 1x1 modulated conv without demodulation (style already folded
 // into x), + bias, clamp, * output_scale; then either f32 NCHW or the uint8 NHWC wire format.
 // One thread = 8 consecutive pixels of a row (16-byte loads per channel plane).
+// COUT = a.Cout as a compile-time constant (3 for RGB: every accumulator index is static, no local-memory array)
+template <int COUT>
 __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
     __shared__ float s_w[4 * 64];
     __shared__ float s_b[4];
-    for (int i = threadIdx.x; i < a.Cout * a.Cin; i += blockDim.x) s_w[i] = a.w[i];
-    if (threadIdx.x < a.Cout) s_b[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
+    for (int i = threadIdx.x; i < COUT * a.Cin; i += blockDim.x) s_w[i] = a.w[i];
+    if (threadIdx.x < COUT) s_b[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
     __syncthreads();
     const int groups_per_row = a.Wp / 8;
     const long long total = static_cast<long long>(a.B) * a.H * groups_per_row;
@@ -293,12 +295,13 @@ __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
         const int b = static_cast<int>(r / a.H);
         const int w0 = g * 8;
         if (w0 >= a.W) continue;
-        float acc[4][8];
+        float acc[COUT][8];
 #pragma unroll
-        for (int o = 0; o < 4; ++o)
+        for (int o = 0; o < COUT; ++o)
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[o][i] = 0.0f;
         const __half* xp = a.x + static_cast<long long>(b) * a.Cin * plane + static_cast<long long>(h) * a.Wp + w0;
+#pragma unroll 4
         for (int ci = 0; ci < a.Cin; ++ci) {
             const uint4 raw = *reinterpret_cast<const uint4*>(xp + ci * plane);
             const __half2* hp = reinterpret_cast<const __half2*>(&raw);
@@ -309,44 +312,62 @@ __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
                 xv[2 * i] = f.x; xv[2 * i + 1] = f.y;
             }
 #pragma unroll
-            for (int o = 0; o < 4; ++o) {
-                if (o < a.Cout) {
-                    const float wv = s_w[o * a.Cin + ci];
+            for (int o = 0; o < COUT; ++o) {
+                const float wv = s_w[o * a.Cin + ci];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(wv, xv[i], acc[o][i]);
-                }
+                for (int i = 0; i < 8; ++i) acc[o][i] = fmaf(wv, xv[i], acc[o][i]);
             }
         }
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-            if (o < a.Cout) {
+        for (int o = 0; o < COUT; ++o) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float v = acc[o][i] + s_b[o];
-                    if (a.clamp >= 0.0f) v = fminf(fmaxf(v, -a.clamp), a.clamp);
-                    acc[o][i] = v * a.output_scale;
-                }
+            for (int i = 0; i < 8; ++i) {
+                float v = acc[o][i] + s_b[o];
+                if (a.clamp >= 0.0f) v = fminf(fmaxf(v, -a.clamp), a.clamp);
+                acc[o][i] = v * a.output_scale;
             }
         }
         if (a.out_fmt == MB_OUT_F32_NCHW || a.out_fmt == MB_OUT_F32_NCHW_01) {
             const bool unit = a.out_fmt == MB_OUT_F32_NCHW_01;   // (x + 1) / 2 clamped to [0, 1]
             float* out = static_cast<float*>(a.out);
-            for (int o = 0; o < a.Cout; ++o) {
-                float* op = out + ((static_cast<long long>(b) * a.Cout + o) * a.H + h) * a.W + w0;
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                float* op = out + ((static_cast<long long>(b) * COUT + o) * a.H + h) * a.W + w0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     if (w0 + i < a.W) op[i] = unit ? fminf(fmaxf((acc[o][i] + 1.0f) * 0.5f, 0.0f), 1.0f) : acc[o][i];
             }
         } else {
             uint8_t* out = static_cast<uint8_t*>(a.out);
-            uint8_t* op = out + ((static_cast<long long>(b) * a.H + h) * a.W + w0) * a.Cout;
+            uint8_t* op = out + ((static_cast<long long>(b) * a.H + h) * a.W + w0) * COUT;
+            if (COUT == 3 && w0 + 8 <= a.W && (a.W & 7) == 0) {
+                // 8 RGB pixels = 24 bytes at a 24-byte-multiple offset: three 8-byte stores instead of 24 single bytes
+                uint32_t pk[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                    for (int o = 0; o < 3; ++o) {
+                        float v = (acc[o][i] + 1.0f) * 0.5f;
+                        v = fminf(fmaxf(v, 0.0f), 1.0f);
+                        const uint32_t q = static_cast<uint32_t>(rintf(v * 255.0f));
+                        const int byte = i * 3 + o;
+                        pk[byte >> 2] |= q << (8 * (byte & 3));
+                    }
+                }
+                uint2* o8 = reinterpret_cast<uint2*>(op);
+                o8[0] = make_uint2(pk[0], pk[1]);
+                o8[1] = make_uint2(pk[2], pk[3]);
+                o8[2] = make_uint2(pk[4], pk[5]);
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (w0 + i < a.W) {
-                    for (int o = 0; o < a.Cout; ++o) {
+#pragma unroll
+                    for (int o = 0; o < COUT; ++o) {
                         float v = (acc[o][i] + 1.0f) * 0.5f;
                         v = fminf(fmaxf(v, 0.0f), 1.0f);
-                        op[i * a.Cout + o] = static_cast<uint8_t>(rintf(v * 255.0f));
+                        op[i * COUT + o] = static_cast<uint8_t>(rintf(v * 255.0f));
                     }
                 }
             }
@@ -589,7 +610,12 @@ int sg3_input_launch(const InputArgs& a, cudaStream_t stream) {
 int torgb_out_launch(const ToRgbArgs& a, cudaStream_t stream) {
     MB_REQUIRE(a.Cout <= 4 && a.Cin <= 64, "torgb: Cout<=4, Cin<=64 supported (got %d, %d)", a.Cout, a.Cin);
     const long long total = static_cast<long long>(a.B) * a.H * (a.Wp / 8);
-    torgb_out_kernel<<<grid_for(total, 256), 256, 0, stream>>>(a);
+    switch (a.Cout) {
+        case 1: torgb_out_kernel<1><<<grid_for(total, 256), 256, 0, stream>>>(a); break;
+        case 2: torgb_out_kernel<2><<<grid_for(total, 256), 256, 0, stream>>>(a); break;
+        case 3: torgb_out_kernel<3><<<grid_for(total, 256), 256, 0, stream>>>(a); break;
+        default: torgb_out_kernel<4><<<grid_for(total, 256), 256, 0, stream>>>(a); break;
+    }
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -12,6 +12,14 @@ Pinning status (see DESIGN.md "Oracle"):
   * oracle.audio     pinned against the reference's torch-native features
                      (``maua/audiovisual/audioreactive/selfsupervised/features``).
   * oracle.signal    pinned against ``maua/audiovisual/audioreactive/signal.py``.
+  * oracle.noise     pinned against ``selfsupervised/noise.py`` (the reference's own classes).
+  * oracle.image     pinned against ``maua/ops/image.py`` resample.
+  * oracle.selfsup   pinned against ``selfsupervised/features/processing.py`` and
+                     ``selfsupervised/latent.py`` (tests/golden/make_selfsup_golden.py);
+                     its natural cubic spline stands in for the absent
+                     torchcubicspline (restated, checked against scipy: unpinned).
+  * oracle.warp      PARITY UNPINNED: kornia (absent, un-pinned) translate / rotate /
+                     scale restated on top of torch's affine_grid / grid_sample.
   * oracle.sg3       PARITY UNPINNED: the StyleGAN3 network lives in the
                      un-vendored submodule maua/GAN/nv (maua-maua-maua/nvGAN @
                      7809c05, a fork of NVlabs/stylegan3); the restatement

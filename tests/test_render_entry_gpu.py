@@ -49,6 +49,22 @@ def test_generate_from_patch_memmap_and_raw_sink(cuda, tmp_path):
         assert int(np.abs(first.astype(np.int16) - video[0].transpose(1, 2, 0).astype(np.int16)).max()) <= 1
 
 
+def test_generate_with_output_size(cuda, tmp_path):
+    """out_size / resize_strategy / resize_layer of generate_audiovisal_from_patch reach the synthesizer's output-size hook
+    (maua/audiovisual/generate.py:27-32 -> wrappers/stylegan3.py:62-79): a 1536x1024 (W x H) render stretched at layer 0."""
+    from maua_b200.audiovisual.generate import generate_audiovisal_from_patch
+
+    wav = str(tmp_path / "sweep.wav")
+    _write_wav(wav, 2.0)
+    torch.manual_seed(0)
+    video, _ = generate_audiovisal_from_patch(
+        audio_file=wav, model_file=None, patch_file="tests/patches/sweep_patch.py", patch_name="SweepPatch", renderer="memmap",
+        renderer_kwargs=dict(cache_file=str(tmp_path / "wide.npy"), batch_size=4), fps=8, out_size=(1536, 1024),
+        resize_strategy="stretch", resize_layer=0)
+    assert video.shape == (16, 3, 1024, 1536) and video.dtype == np.uint8
+    assert 20 < float(video.mean()) < 235 and float(video[0].std()) > 5
+
+
 def test_async_frame_downloader_round_trip(cuda):
     """Frames written by consecutive batches arrive intact and in order through the side-stream pinned ring."""
     import torch

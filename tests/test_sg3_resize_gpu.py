@@ -83,6 +83,29 @@ def test_hooked_network_matches_hooked_oracle(cuda, layer, output_size, strategy
     assert torch.equal(base, fresh(ws.to(cuda)))
 
 
+def test_hook_on_the_radial_config(cuda):
+    """StyleGAN3-R (1x1 convs, radial down filters) with a non-square stretch: the generic filter fallbacks see H != W too."""
+    from maua_b200.GAN.networks import stylegan3 as N
+    from maua_b200.GAN.wrappers.stylegan3 import install_hook
+
+    kw = dict(O.SG3_R_KWARGS, channel_base=8192, channel_max=160)
+    onet = O.make_synthesis("T", img_resolution=256, seed=0, **kw)
+    torch.manual_seed(0)
+    net = N.SynthesisNetwork(w_dim=512, img_resolution=256, img_channels=3, **kw)
+    net.load_state_dict(onet.state_dict())
+    size = np.array([44, 30])  # (W, H) at layer 4
+    hooked_oracle(onet, 4, size, "stretch")
+    install_hook(net, 4, size, "stretch")
+    torch.manual_seed(6)
+    ws = torch.randn(2, net.num_ws, 512)
+    ref = onet(ws)
+    out = net(ws.to(cuda))
+    assert tuple(out.shape) == tuple(ref.shape)
+    err = float((pix(out) - pix(ref)).abs().max())
+    print(f"R config, layer 4 stretch -> {tuple(ref.shape[2:])}: max-abs pixel error {err:.3e}")
+    assert err <= PIX_TOL, err
+
+
 def test_wrapper_change_output_resolution(cuda):
     """StyleGAN3Synthesizer(output_size=(W, H), strategy, layer) end to end at the reference's default 1024^2 network:
     rounding warning (:70-73), output shape, hook removal through refresh_model_hooks."""

@@ -42,6 +42,8 @@ def recurrence_matrix(data, k=None, width=1, sym=False, bandwidth=None):
         rec = rec.minimum(rec.T)                                # mutual neighbours only
     if bandwidth is None:
         bandwidth = torch.median(rec.max(axis=1).values)
+        if not bandwidth > 0:   # degenerate track (the reference divides by zero here)
+            bandwidth = rec.max().clamp_min(1e-12)
     rec = rec * (1 - (rec < 0).float())
     rec = torch.exp(rec / (-1 * bandwidth))
     return rec * (1 - (rec >= 1).float())                       # exp(0) = 1 marks "no link"
@@ -90,7 +92,7 @@ def init_plus_plus(ds, k):
 
 def soft_k_means(data, k, num_iter, cluster_temp=5):
     """Soft k-means on the unit sphere (segment.py:107-130) -> (centres, memberships [n, k], similarities)."""
-    data = data / torch.norm(data, p=2, dim=1, keepdim=True)
+    data = data / torch.norm(data, p=2, dim=1, keepdim=True).clamp_min(1e-30)
     mu = torch.tensor(init_plus_plus(data.cpu().detach().numpy(), k)).to(data)
     for _ in range(num_iter):
         r = torch.softmax(cluster_temp * (data @ mu.t()), 1)
@@ -102,17 +104,24 @@ def soft_k_means(data, k, num_iter, cluster_temp=5):
 def laplacian_segmentation(envelope, beats, ks=(2, 4, 6, 8, 12, 16)):
     """envelope [T, C], beats: frame indices -> list of soft segmentations [T, k], one per k (segment.py:133-190)."""
     beats = list(beats)
+    if envelope.dim() == 1:
+        envelope = envelope[:, None]
+    # guards for degenerate input (silent frames give NaN chroma / tonnetz rows; the reference's NaNs would abort eigh)
+    envelope = torch.nan_to_num(envelope.float(), nan=0.0, posinf=0.0, neginf=0.0)
     bounds = zip([0] + beats, beats + [len(envelope)])
     csync = torch.stack([torch.median(envelope[a:b], dim=0).values for a, b in bounds], dim=0)
 
     rf = timelag_median_filter(recurrence_matrix(csync, width=3, sym=True))
     path_distance = torch.sum(torch.diff(csync, dim=0) ** 2, dim=1)
-    path_sim = torch.exp(-path_distance / torch.median(path_distance))
+    sigma = torch.median(path_distance)
+    if not sigma > 0:           # more than half of the beat-to-beat steps are exactly zero
+        sigma = path_distance.mean().clamp_min(1e-12)
+    path_sim = torch.exp(-path_distance / sigma)
     r_path = torch.diag(path_sim, diagonal=1) + torch.diag(path_sim, diagonal=-1)
 
     deg_path, deg_rec = r_path.sum(dim=1), rf.sum(dim=1)
-    mu = deg_path.dot(deg_path + deg_rec) / torch.sum((deg_path + deg_rec) ** 2)
-    lap = normalized_laplacian(mu * rf + (1 - mu) * r_path)
+    mu = deg_path.dot(deg_path + deg_rec) / torch.sum((deg_path + deg_rec) ** 2).clamp_min(1e-30)
+    lap = torch.nan_to_num(normalized_laplacian(mu * rf + (1 - mu) * r_path))
     try:
         _, evecs = torch.linalg.eigh(lap)
     except Exception:
@@ -122,7 +131,7 @@ def laplacian_segmentation(envelope, beats, ks=(2, 4, 6, 8, 12, 16)):
 
     out = []
     for k in ks:
-        _, member, _ = soft_k_means(evecs[:, :k] / cnorm[:, k - 1:k], k=k, num_iter=100)
+        _, member, _ = soft_k_means(evecs[:, :k] / cnorm[:, k - 1:k].clamp_min(1e-30), k=k, num_iter=100)
         out.append(F.interpolate(member.T[None], size=envelope.shape[0], mode="nearest").squeeze().T)
     return out
 

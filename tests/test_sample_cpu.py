@@ -1,0 +1,35 @@
+"""Host pieces of the random-patch entry point (audioreactive/sample.py; reference selfsupervised/sample.py:16-32)."""
+import wave
+
+import numpy as np
+import pytest
+import torch
+
+
+def _wav(path, seconds, sr=44100, channels=2):
+    t = np.arange(int(seconds * sr)) / sr
+    y = 0.5 * np.sin(2 * np.pi * 440 * t)
+    data = np.stack([y, 0.5 * y][:channels], axis=1)
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(channels); w.setsampwidth(2); w.setframerate(sr)
+        w.writeframes((data * 32767).astype("<i2").tobytes())
+
+
+def test_load_audio_resamples_to_1024_samples_per_frame(tmp_path):
+    from maua_b200.audiovisual.audioreactive.sample import load_audio
+
+    _wav(tmp_path / "a.wav", 3.0)
+    audio, sr = load_audio(str(tmp_path / "a.wav"), offset=1, duration=1.5, fps=24, device="cpu")
+    assert sr == 1024 * 24 and audio.dtype == torch.float32
+    assert len(audio) % 1024 == 0 and abs(len(audio) - 1.5 * sr) < 1024          # whole video frames of the cropped span
+    # mono mix of (y, y/2) keeps the 440 Hz tone: dominant FFT bin at 440 Hz
+    spec = torch.fft.rfft(audio).abs()
+    assert abs(int(spec.argmax()) * sr / len(audio) - 440.0) < 2.0
+    assert 0.3 < float(audio.abs().max()) < 0.45
+
+
+def test_generate_rejects_unbuilt_sizes_before_touching_the_gpu(tmp_path):
+    from maua_b200.audiovisual.audioreactive.sample import generate
+
+    with pytest.raises(NotImplementedError):
+        generate(str(tmp_path / "missing.wav"), seed=1, downscale_factor=4)

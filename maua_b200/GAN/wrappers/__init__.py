@@ -11,11 +11,16 @@ import torch
 
 
 class MauaMapper(torch.nn.Module):
+    """latent_z (+ conditioning, truncation) -> W+; implemented per architecture."""
+
     def forward(self):
         raise NotImplementedError()
 
 
 class MauaSynthesizer(torch.nn.Module):
+    """W+ (+ per-frame controls) -> images.  ``_hook_handles`` lists what change_output_resolution installed (objects with
+    ``remove()``: torch hook handles in the reference, resize handles of the native network here)."""
+
     _hook_handles = []
 
     def forward(self):
@@ -25,9 +30,9 @@ class MauaSynthesizer(torch.nn.Module):
         raise NotImplementedError()
 
     def refresh_model_hooks(self):
-        for handle in self._hook_handles:
+        installed, self._hook_handles = self._hook_handles, []
+        for handle in installed:
             handle.remove()
-        self._hook_handles = []
 
 
 def _batches(inputs, batch_size, device):
@@ -55,8 +60,9 @@ class MauaGenerator(torch.nn.Module):
 
     def __init__(self, mapper_kwargs={}, synthesizer_kwargs={}) -> None:
         super().__init__()
-        self.mapper = self.__class__.MapperCls(**mapper_kwargs)
-        self.synthesizer = self.__class__.SynthesizerCls(**synthesizer_kwargs)
+        cls = type(self)
+        self.mapper = cls.MapperCls(**mapper_kwargs)
+        self.synthesizer = cls.SynthesizerCls(**synthesizer_kwargs)
 
     def forward(self):
         raise NotImplementedError()
@@ -93,14 +99,14 @@ class MauaGenerator(torch.nn.Module):
                     yield frame[None]
 
 
+_ARCHITECTURES = {"stylegan3": (".stylegan3", "StyleGAN3"), "stylegan2": (".stylegan2", "StyleGAN2")}
+
+
 def get_generator_class(architecture: str) -> MauaGenerator:
-    if architecture == "stylegan3":
-        from .stylegan3 import StyleGAN3
+    """"stylegan2" | "stylegan3" -> generator class (imported on first use)."""
+    import importlib
 
-        return StyleGAN3
-    if architecture == "stylegan2":
-        from .stylegan2 import StyleGAN2
-
-        return StyleGAN2
-    else:
+    if architecture not in _ARCHITECTURES:
         raise Exception(f"Architecture not found: {architecture}")
+    module, name = _ARCHITECTURES[architecture]
+    return getattr(importlib.import_module(module, __name__), name)

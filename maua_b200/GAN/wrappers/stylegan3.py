@@ -69,21 +69,26 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
         return self.G_synth.forward(latents, out_fmt=out_fmt)
 
     def change_output_resolution(self, output_size: Tuple[int, int], strategy: str, layer: int):
+        """Re-target the output size (W, H): drops the installed hook, and unless the size is the native one installs a new
+        hook on module `layer` (stylegan3.py:62-79; size arithmetic in hooked_feature_size)."""
         self.refresh_model_hooks()
-
-        if tuple(output_size) != (self.G_synth.img_resolution, self.G_synth.img_resolution):
-            lay_mult = layer_multipliers[self.G_synth.img_resolution][layer]
-
-            unrounded_size = np.array(output_size) / lay_mult + 20
-            size = np.round(unrounded_size).astype(int)
-            if sum(abs(unrounded_size - size)) > 1e-10:
-                warnings.warn(
-                    f"Layer {layer} resizes to multiples of {lay_mult}. --output-size rounded to {lay_mult * (size - 20)}"
-                )
-
+        native = (self.G_synth.img_resolution, self.G_synth.img_resolution)
+        if tuple(output_size) != native:
+            size = hooked_feature_size(self.G_synth.img_resolution, output_size, layer)
             self._hook_handles.append(install_hook(self.G_synth, layer, size, strategy))
-
         self.output_size = output_size
+
+
+def hooked_feature_size(img_resolution, output_size, layer):
+    """(W, H) of the feature map module `layer` must be resized to so that the image comes out at `output_size`: the
+    module's up-sampling factor to the output divides the size, the 10-pixel margin on each side is added back, and sizes
+    that do not divide evenly are rounded with the reference's warning (stylegan3.py:66-73)."""
+    factor = layer_multipliers[img_resolution][layer]
+    exact = np.array(output_size) / factor + 20
+    size = np.round(exact).astype(int)
+    if sum(abs(exact - size)) > 1e-10:
+        warnings.warn(f"Layer {layer} resizes to multiples of {factor}. --output-size rounded to {factor * (size - 20)}")
+    return size
 
 
 class _ResizeHandle:
@@ -125,17 +130,22 @@ def make_transform_mats(translate: torch.Tensor, angle: torch.Tensor) -> torch.T
 
 
 def make_transform_mat(translate: Tuple[float, float], angle: float) -> torch.Tensor:
-    s = np.sin(angle.squeeze().cpu() / 360.0 * np.pi * 2)
-    c = np.cos(angle.squeeze().cpu() / 360.0 * np.pi * 2)
-    m = np.array([[c, s, translate.squeeze().cpu()[0]], [-s, c, translate.squeeze().cpu()[1]], [0, 0, 0]])
+    """User transform of the Fourier-feature input from a translation (x, y) and an angle in degrees (stylegan3.py:82-93):
+    the inverse of [[cos, sin, tx], [-sin, cos, ty], [0, 0, 0]].  That matrix has a zero last row, so the inverse never
+    exists and the reference always lands in its pseudo-inverse branch (with its warning); both branches are kept."""
+    turn = angle.squeeze().cpu() / 360.0 * np.pi * 2
+    sin, cos = np.sin(turn), np.cos(turn)
+    shift = translate.squeeze().cpu()
+    forward = np.array([[cos, sin, shift[0]], [-sin, cos, shift[1]], [0, 0, 0]])
     try:
-        m = np.linalg.inv(m)
+        inverse = np.linalg.inv(forward)
     except np.linalg.LinAlgError:
         warnings.warn(
-            f"Singular transform matrix, continuing with pseudo-inverse of transform matrix which might not give expected results! (If you want no translation or rotation, set them to None rather than 0)"
+            "Singular transform matrix, continuing with pseudo-inverse of transform matrix which might not give expected "
+            "results! (If you want no translation or rotation, set them to None rather than 0)"
         )
-        m = np.linalg.pinv(m)
-    return torch.from_numpy(m)
+        inverse = np.linalg.pinv(forward)
+    return torch.from_numpy(inverse)
 
 
 class StyleGAN3(StyleGAN):

@@ -79,43 +79,43 @@ class Patch(torch.nn.Module):
         self.noise_patches = [self.random_noise_patch() for _ in range(self._count())]
 
     def update_intensity(self, val):
-        draw = lambda: skewnorm(self.rng, a=5, loc=val, scale=0.5).item()
-        for p in self.latent_patches:
-            p["seq_feat_weight"] = draw()
-            p["mod_feat_weight"] = draw()
-        for p in self.noise_patches:
-            p["seq_feat_weight"] = draw()
-            p["mod_feat_weight"] = draw()
-            p["noise_std"] = draw()
+        """Re-draw every sub-patch weight around `val` (skew-normal, a = 5, scale 0.5), latent patches first (patch.py:87-95)."""
+        for patches, keys in ((self.latent_patches, ("seq_feat_weight", "mod_feat_weight")),
+                              (self.noise_patches, ("seq_feat_weight", "mod_feat_weight", "noise_std"))):
+            for sub in patches:
+                for key in keys:
+                    sub[key] = skewnorm(self.rng, a=5, loc=val, scale=0.5).item()
+
+    # One sub-patch = one dict; the tables list its keys in the reference's order (patch.py:97-125).  A tuple entry is drawn
+    # from the generator (options, weights), "ks" stands for this track's segment counts, anything else is a constant
+    # (the reference has its skew-normal weight draws commented out and uses these defaults).
+    _COMMON_TAIL = (
+        ("loop_bars", (_BARS, _BAR_WEIGHTS)),
+        ("seq_feat", (ALLFEATS, None)),
+        ("seq_feat_weight", 1),
+        ("mod_feat", (UNITFEATS, None)),
+        ("mod_feat_weight", 1),
+        ("merge_type", (["average", "modulate"], [1, 3])),
+        ("merge_depth", (_DEPTHS, _DEPTH_WEIGHTS)),
+    )
+    _LATENT_TABLE = (("patch_type", (["segmentation", "feature", "loop"], None)), ("segments", ("ks", None))) + _COMMON_TAIL
+    _NOISE_TABLE = (("patch_type", (["blend", "multiply", "loop"], None)),) + _COMMON_TAIL + (("noise_mean", 0), ("noise_std", 1))
+
+    def _draw_subpatch(self, table):
+        sub = {}
+        for key, spec in table:
+            if isinstance(spec, tuple):
+                options, weights = spec
+                sub[key] = random_choice(self.rng, self.ks if options == "ks" else options, weights=weights)
+            else:
+                sub[key] = spec
+        return sub
 
     def random_latent_patch(self):
-        r = self.rng
-        return dict(
-            patch_type=random_choice(r, ["segmentation", "feature", "loop"]),
-            segments=random_choice(r, self.ks),
-            loop_bars=random_choice(r, _BARS, weights=_BAR_WEIGHTS),
-            seq_feat=random_choice(r, ALLFEATS),
-            seq_feat_weight=1,
-            mod_feat=random_choice(r, UNITFEATS),
-            mod_feat_weight=1,
-            merge_type=random_choice(r, ["average", "modulate"], weights=[1, 3]),
-            merge_depth=random_choice(r, _DEPTHS, weights=_DEPTH_WEIGHTS),
-        )
+        return self._draw_subpatch(self._LATENT_TABLE)
 
     def random_noise_patch(self):
-        r = self.rng
-        return dict(
-            patch_type=random_choice(r, ["blend", "multiply", "loop"]),
-            loop_bars=random_choice(r, _BARS, weights=_BAR_WEIGHTS),
-            seq_feat=random_choice(r, ALLFEATS),
-            seq_feat_weight=1,
-            mod_feat=random_choice(r, UNITFEATS),
-            mod_feat_weight=1,
-            merge_type=random_choice(r, ["average", "modulate"], weights=[1, 3]),
-            merge_depth=random_choice(r, _DEPTHS, weights=_DEPTH_WEIGHTS),
-            noise_mean=0,
-            noise_std=1,
-        )
+        return self._draw_subpatch(self._NOISE_TABLE)
 
     def forward(self, latent_palette, downscale_factor=1, aspect_ratio=1):
         """-> (latents [T, num_ws, w_dim] on the device, list of 17 lazy per-layer noise sequencers)."""
@@ -135,16 +135,21 @@ class Patch(torch.nn.Module):
             noise = noise_patch(self.rng, noise, self.features, self.tempo, self.fps, **sub)
         return latents, noise
 
+    @staticmethod
+    def _table(patches):
+        """Fixed-width text table of a list of sub-patch dicts (floats with four decimals, "spectral_" dropped)."""
+        def cell(v):
+            return (f"{v:.4f}" if isinstance(v, float) else f"{v}").replace("spectral_", "")
+
+        grid = [[""] + list(patches[0])] + [[str(n)] + [cell(v) for v in sub.values()] for n, sub in enumerate(patches, start=1)]
+        widths = [max(len(row[c]) for row in grid) for c in range(len(grid[0]))]
+        grid.insert(1, ["-" * w for w in widths])
+        return [" | ".join(text.ljust(w) for text, w in zip(row, widths)) for row in grid]
+
     def __repr__(self):
-        blocks = []
-        for patches in (self.latent_patches, self.noise_patches):
-            header = [""] + list(patches[0])
-            rows = [[str(i + 1)] + [(f"{v:.4f}" if isinstance(v, float) else f"{v}").replace("spectral_", "") for v in p.values()]
-                    for i, p in enumerate(patches)]
-            widths = [max(len(r[n]) for r in [header] + rows) for n in range(len(header))]
-            table = [header, ["-" * w for w in widths]] + rows
-            blocks.append([" | ".join(cell.ljust(w) for cell, w in zip(r, widths)) for r in table])
-        return ("Patch(\n  Latent(\n    " + "\n    ".join(blocks[0]) + "\n  ),\n  Noise(\n    " + "\n    ".join(blocks[1]) + "\n  )\n)")
+        indent = "\n    "
+        latent, noise = indent.join(self._table(self.latent_patches)), indent.join(self._table(self.noise_patches))
+        return f"Patch(\n  Latent({indent}{latent}\n  ),\n  Noise({indent}{noise}\n  )\n)"
 
     _SAVED = ("seed", "latent_patches", "noise_patches", "n_base_latents", "sigma_base_noise", "loops_base_noise")
 

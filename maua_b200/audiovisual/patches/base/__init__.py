@@ -22,16 +22,19 @@ def load_audio(audio_file, offset=0, duration=-1):
 
 
 class MauaPatch:
+    """Base of the user patch files (API of maua/audiovisual/patches/base/__init__.py:7-25): holds the decoded track
+    (`audio` numpy float32 mono, `sr`, `duration` in seconds), the frame count of the render and the device; subclasses add
+    a generator (`mapper`, `synthesizer`) and override the processing stages."""
+
     def __init__(self, audio_file, fps=24, offset=0, duration=-1) -> None:
-        self.fps = fps
-        self.audio_file = audio_file
-        self.audio, self.sr, self.duration = load_audio(audio_file, offset, duration)
-        self.audio = self.audio.numpy()
+        track, self.sr, self.duration = load_audio(audio_file, offset, duration)
+        self.audio = track.numpy()
+        self.audio_file, self.fps = audio_file, fps
+        self.n_frames = round(self.duration * fps)
         self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
-        self.n_frames = round(self.duration * self.fps)
 
     def process_audio(self):
-        pass
+        """Stage 1 (optional): derive envelopes / features from `self.audio`."""
 
     def force_output_size(self, video):
         t, c, h, w = video.shape
@@ -52,16 +55,17 @@ class MauaPatch:
 
 
 def get_patch_from_file(filepath, class_name=None):
+    """The MauaPatch subclass DEFINED in the python file `filepath` (path relative to the working directory, as the
+    reference's CLI passes it), optionally the one called `class_name` (patches/base/__init__.py:28-45)."""
     import importlib
     import inspect
 
     module_name = filepath.replace(".py", "").replace("/", ".")
-    for _, cls in inspect.getmembers(importlib.import_module(module_name), inspect.isclass):
-        if (
-            cls.__module__ == module_name
-            and issubclass(cls, MauaPatch)
-            and ((class_name is not None and cls.__name__ == class_name) or class_name is None)
-        ):
+    module = importlib.import_module(module_name)
+    for name, cls in inspect.getmembers(module, inspect.isclass):
+        defined_here = cls.__module__ == module_name      # not merely imported into the patch file
+        wanted = class_name is None or name == class_name
+        if defined_here and wanted and issubclass(cls, MauaPatch):
             return cls
     raise Exception(
         "Patch not found! Are you sure there is a class that extends MauaPatch in the file you specified and that the name you (might have) specified is correct?"

@@ -49,12 +49,19 @@ def emit(line):
 
 
 def measured_peaks():
+    """HBM GB/s and dense bf16 TFLOP/s to divide by: the driver-written MEASURED_PEAKS.json (keys hbm_gbs, bf16_tflops,
+    bf16_tflops_sustained: B200_PROFILING.md) when present and readable, else the fallback figures of that guide."""
+    fallback = dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    if not os.path.exists(p):
+        return fallback
+    try:
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+        burst = float(d["bf16_tflops"])
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=burst, tf_sustained=float(d.get("bf16_tflops_sustained", burst)),
                     source="measured (MEASURED_PEAKS.json)")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+    except (OSError, ValueError, KeyError, TypeError):
+        return dict(fallback, source="fallback (B200_PROFILING.md; MEASURED_PEAKS.json unreadable)")
 
 
 class ClockSampler:

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -255,15 +256,19 @@ struct LaneConsts {
     uint32_t sl2, cl2;
 };
 template <int UP>
-__device__ __forceinline__ void lane_setup(const MmaParams& p, int lane, LaneConsts<UP>& L) {
+__device__ __forceinline__ void lane_setup(const uint4* frags, float slope, float clamp_pre, int lane, LaneConsts<UP>& L) {
     using K = MC<UP>;
 #pragma unroll
-    for (int v = 0; v < K::NVAR; ++v) L.AU[v] = p.frags[v * 32 + lane];
+    for (int v = 0; v < K::NVAR; ++v) L.AU[v] = frags[v * 32 + lane];
 #pragma unroll
-    for (int s = 0; s < 3; ++s) L.AD[s] = p.frags[(K::NVAR + s) * 32 + lane];
-    L.sl2 = pack2(p.slope, p.slope);
-    const float c = fminf(p.clamp_pre, 65504.0f);
+    for (int s = 0; s < 3; ++s) L.AD[s] = frags[(K::NVAR + s) * 32 + lane];
+    L.sl2 = pack2(slope, slope);
+    const float c = fminf(clamp_pre, 65504.0f);
     L.cl2 = pack2(c, c);
+}
+template <int UP>
+__device__ __forceinline__ void lane_setup(const MmaParams& p, int lane, LaneConsts<UP>& L) {
+    lane_setup<UP>(p.frags, p.slope, p.clamp_pre, lane, L);
 }
 
 // Fetch the [IYT rows x 56 halfs] input tile of one warp with cp.async (zero fill outside the image = padding).
@@ -690,6 +695,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_mma_nhwc_p_kernel(const __
     drain(unpack_pos(old1), n - 1);
 }
 
+#include "flrelu_stream.cuh"
+
 // ---- host: constant fragments -------------------------------------------------------------------
 struct FragCache {
     int up = 0, rho = -1, e = -1, fd_2d = 0;
@@ -1003,6 +1010,66 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     p.tpw = ntiles < 64 ? 1 : (ntiles < 256 ? 2 : 4);
     p.slope = a.slope;
     p.clamp_pre = a.clamp >= 0.0f ? a.clamp / a.gain : 3.0e38f;
+    // Streaming kernels (flrelu_stream.cuh): the product path.  MB_FLRELU_STREAM=0 selects the tile kernels below
+    // (kept for A/B runs and as the path of the op-level API with a separate bias).
+    const char* sev = getenv("MB_FLRELU_STREAM");   // read per call: the A/B tests flip it inside one process
+    const int use_stream = sev ? atoi(sev) : 1;
+    if (use_stream && a.bias == nullptr) {
+        using S = SC<UP>;
+        const int sms = a.num_sms > 0 ? a.num_sms : 148;
+        StreamParams sp;
+        sp.scale = a.scale; sp.frags = frags; sp.rfrags = p.rfrags; sp.nt = p.nt;
+        sp.C = a.C; sp.Hout = a.Hout; sp.Wout = a.Wout; sp.Wp_out = a.Wp_out; sp.Cp_out = 0;
+        sp.px0 = a.px0; sp.e = e; sp.tiles_x = p.tiles_x; sp.B = a.B;
+        sp.slope = p.slope; sp.clamp_pre = p.clamp_pre; sp.out_gain = p.out_gain;
+        sp.y = a.y;
+        if (a.y_nhwc) {
+            MB_REQUIRE(a.Cp_out % 16 == 0 && a.Cp_out == round_up(a.C, kCG), "filtered_lrelu: Cp_out must be C rounded up to whole 16-channel groups");
+            sp.y = a.y_nhwc;
+            sp.Cp_out = a.Cp_out;
+        }
+        const StreamPlan pl = plan_stream(a.B, a.C, a.Hout, p.tiles_x, sms);
+        sp.nseg = pl.nseg; sp.R = pl.R; sp.nsc = pl.nsc; sp.Rp = pl.Rp; sp.gfull = pl.gfull; sp.vlast = pl.vlast;
+        sp.n_full = pl.n_full; sp.n_total = pl.n_total;
+        CUtensorMap tm_x;
+        {
+            PFN_encodeTiled enc = get_encode_tiled();
+            if (!enc) {
+                set_error("cuTensorMapEncodeTiled not available from the driver");
+                return MB_ECUDA;
+            }
+            MB_REQUIRE(a.Wp_in % 8 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "filtered_lrelu: input rows must be 16-byte aligned");
+            cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.Win), static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B) * a.C};
+            cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.Wp_in) * 2, static_cast<cuuint64_t>(a.Wp_in) * 2 * a.Hin};
+            cuuint32_t box[3] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(kRowBlk), 1};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult cr = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(a.x), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) {
+                set_error("cuTensorMapEncodeTiled(filtered_lrelu input) failed: %d (W=%d H=%d planes=%d pitch=%d)", static_cast<int>(cr),
+                          a.Win, a.Hin, a.B * a.C, a.Wp_in);
+                return MB_ECUDA;
+            }
+        }
+        const int smem = S::SMEM + (radial ? kMaxTerms * 6 * 32 * static_cast<int>(sizeof(uint4)) : 0);
+        const int grid = sp.n_total < sms ? sp.n_total : sms;
+        auto go = [&](void (*kern)(CUtensorMap, StreamParams)) -> int {
+            static const void* configured[8] = {};   // the kernels whose dynamic shared memory limit is already raised
+            int slot = 0;
+            while (slot < 8 && configured[slot] && configured[slot] != reinterpret_cast<const void*>(kern)) ++slot;
+            if (slot == 8 || !configured[slot]) {
+                MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             S::SMEM + kMaxTerms * 6 * 32 * static_cast<int>(sizeof(uint4))));
+                if (slot < 8) configured[slot] = reinterpret_cast<const void*>(kern);
+            }
+            kern<<<grid, kCG * 32, smem, stream>>>(tm_x, sp);
+            MB_CUDA(cudaGetLastError());
+            return MB_OK;
+        };
+        if (a.y_nhwc) return radial ? go(flrelu_stream_kernel<UP, true, false>) : go(flrelu_stream_kernel<UP, false, false>);
+        return radial ? go(flrelu_stream_kernel<UP, true, true>) : go(flrelu_stream_kernel<UP, false, true>);
+    }
     if (a.y_nhwc) {
         // fused transpose: 16 channels per CTA, 32-byte pixel chunks into [B][H][W][Cp_out]
         MB_REQUIRE(a.bias == nullptr, "filtered_lrelu: the channels-last variant takes the bias from the conv epilogue");

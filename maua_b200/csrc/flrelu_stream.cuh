@@ -1,0 +1,473 @@
+// filtered_lrelu, streaming form of the tensor-core chain (included by flrelu_mma.cu inside its namespace).
+//
+// The tile kernels of flrelu_mma.cu carry one 32x32 output tile per warp through the four-pass chain; every tile
+// recomputes a vertical halo (the 74-row intermediate of a 32-row tile is produced as five 16-row strips, the
+// input as six 8-row blocks) and pays the tile's fixed costs (coordinates, barriers, write-out of 32 rows at once).
+// Here a warp walks DOWN a 32-pixel-wide column of one channel instead: per 16 output rows it computes exactly two
+// new intermediate strips and one (up=4) or two (up=2) new 8-row input blocks, so the vertical halo is paid once per
+// column segment instead of once per 32 rows (164 -> 132 HMMA per 32x32 outputs at up=2, 154 -> 122 at up=4), the
+// input arrives through a per-warp ring of 8-row TMA boxes that is refilled block by block (prefetch distance =
+// the ring, across item boundaries), and finished 16x32 blocks leave through a ring of staging buffers.
+//
+// Round-1 ncu findings this file answers (profiles/r1_ncu_final2.md, source page of flrelu_mma_nhwc_kernel):
+//   * every shared-memory access was a generic LD/ST (the 128-byte round-up of the dynamic shared base went through
+//     uintptr_t and lost the address space): 9 % of the stall samples were `lg_throttle`, the write-out's generic
+//     LD.U16 results sat on the long scoreboard.  All shared accesses below are explicit ld/st.shared on 32-bit
+//     shared addresses.
+//   * the channels-last write-out cost ~70 instructions per warp and tile (32 LD.U16 + PRMT + address math).  Here
+//     it is ldmatrix.x4.trans over the 16 staged channel planes: a thread receives four adjacent channels of one
+//     pixel in two registers, four lanes cover a pixel's 32-byte chunk: 2 LDSM + 4 STG.64 per warp and block.
+//   * 12 % of the samples were mbarrier spins coupling the 16 warps of a CTA through two staging buffers.  Blocks
+//     are half a tile, six staging buffers, write-out lags three blocks.
+//   * a partial last channel group (81 = 5*16 + 1, 51 = 3*16 + 3 channels) idled 15 / 13 warps for a whole tile.
+//     A partial group with v channels runs 16/v column segments concurrently, one per (segment, channel) warp.
+//   * items were walked so that vertically adjacent tiles were far apart in time: halo rows were re-read from DRAM
+//     (1.42x the algorithmic bytes at 16 frames per step).  Items are ordered column-fastest and dealt round-robin:
+//     at any time the 148 CTAs work on adjacent columns of the same planes, and a column has no vertical halo.
+//
+// Arithmetic: the MMA sequence per output element is the one of fir_chain() (same fragments, same accumulation
+// order), so results are bit-identical to the tile kernels.
+#pragma once
+
+constexpr int kRowBlk = 8;                         // input rows per ring block (one n8 block of the S1 GEMM)
+constexpr int kBlkBytes = kRowBlk * kXP * 2;       // 896
+constexpr int kOB = 16;                            // output rows per finished block
+constexpr int kPlaneBytes = kOB * kSP * 2 + 16;    // staged 16x32 block of one channel (+16: ldmatrix rows of 8 planes on distinct banks)
+constexpr int kBufBytes = kCG * kPlaneBytes;       // 20736 = 162 * 128
+constexpr int kSTail = 2048;                       // zero chunk | block descriptors | mbarriers
+
+template <int UP>
+struct SC {
+    static constexpr int NRING = (UP == 2) ? 6 : 4;  // input blocks in flight per warp (up=2 consumes two per output block)
+    static constexpr int NSB = 6;                    // staging buffers
+    static constexpr int LAG = 3;                    // the write-out runs this many blocks behind the staging
+    static constexpr int RING_BYTES = kCG * NRING * kBlkBytes;
+    static constexpr int SMEM = RING_BYTES + NSB * kBufBytes + kSTail + 128;
+};
+
+struct StreamParams {
+    const float* scale;
+    __half* y;
+    const uint4* frags;
+    const uint4* rfrags;
+    int C, Hout, Wout, Wp_out, Cp_out, px0, e, nt;
+    int tiles_x, B;
+    int gfull;   // full 16-channel groups
+    int vlast;   // channels of the partial last group (0 = none)
+    int nseg, R;  // full groups: segments per column, 16-row blocks per segment
+    int nsc, Rp;  // partial group: concurrent segments per item (16 / vlast), blocks per segment
+    int n_full, n_total;
+    float slope, clamp_pre, out_gain;
+};
+
+// ---- explicit shared-space accessors (32-bit shared addresses) ----
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t a, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(a));
+}
+__device__ __forceinline__ void stg64(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.global.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void stg128(void* p, const uint4& v) {
+    asm volatile("st.global.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin (a broken pipeline traps instead of hanging the GPU box).
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (++spins > (1u << 22)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+// One work item: a 32-pixel column (or `nsc` segments of it) of 16 channels (or of the v channels of the partial group).
+struct SItem {
+    int b, c0, tx, v, nsc, R, seg0, segrows;
+};
+__device__ __forceinline__ void decode_item(const StreamParams& p, int idx, SItem& it) {
+    if (idx < p.n_full) {
+        it.tx = idx % p.tiles_x;
+        int r = idx / p.tiles_x;
+        it.seg0 = r % p.nseg;
+        r /= p.nseg;
+        const int grp = r % p.gfull;
+        it.b = r / p.gfull;
+        it.c0 = grp * kCG;
+        it.v = kCG;
+        it.nsc = 1;
+        it.segrows = p.R * kOB;
+        const int left = (p.Hout - it.seg0 * it.segrows + kOB - 1) / kOB;  // blocks down to the last image row
+        it.R = left < p.R ? left : p.R;
+    } else {
+        idx -= p.n_full;
+        it.tx = idx % p.tiles_x;
+        it.b = idx / p.tiles_x;
+        it.seg0 = 0;
+        it.c0 = p.gfull * kCG;
+        it.v = p.vlast;
+        it.nsc = p.nsc;
+        it.R = p.Rp;
+        it.segrows = p.Rp * kOB;
+    }
+}
+// This warp's share of an item: channel and first output row, or false when it has none.
+__device__ __forceinline__ bool warp_share(const StreamParams& p, const SItem& it, int warp, int& c, int& oy0) {
+    const int q = (it.v == kCG) ? 0 : warp / it.v;
+    const int ch = warp - q * it.v;
+    c = it.c0 + ch;
+    oy0 = (it.seg0 + q) * it.segrows;
+    return q < it.nsc && oy0 < p.Hout;
+}
+
+template <int UP, bool RAD, bool PLANAR>
+__global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const StreamParams p) {
+    using K = MC<UP>;
+    using S = SC<UP>;
+    extern __shared__ uint8_t smem_dyn[];
+    const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;   // TMA destinations
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tig = lane & 3;
+    const uint32_t ring = sbase + warp * (S::NRING * kBlkBytes);
+    const uint32_t stg = sbase + S::RING_BYTES;
+    const uint32_t tail = stg + S::NSB * kBufBytes;
+    const uint32_t zero_a = tail;                 // 16 zero bytes: the pad channels of a partial group
+    const uint32_t desc_a = tail + 64;            // [NSB] x 32 bytes: where a staged block goes
+    const uint32_t full_a = tail + 64 + S::NSB * 32;
+    const uint32_t empty_a = full_a + S::NSB * 8;
+    const uint32_t xbar_a = empty_a + S::NSB * 8 + warp * (S::NRING * 8);
+    const uint32_t rad_a = tail + kSTail;         // radial down filter: [nt][6][32] uint4
+    static_assert(64 + SC<UP>::NSB * 48 + kCG * SC<UP>::NRING * 8 <= kSTail, "tail too small");
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_x);
+        for (int i = 0; i < S::NSB; ++i) {
+            sbar_init(full_a + 8 * i, kCG);
+            sbar_init(empty_a + 8 * i, kCG);
+        }
+        for (int i = 0; i < kCG * S::NRING; ++i) sbar_init(empty_a + S::NSB * 8 + 8 * i, 1);
+        sts128(zero_a, make_uint4(0u, 0u, 0u, 0u));
+        fence_barrier_init();
+    }
+    if (RAD) {
+        for (int i = threadIdx.x; i < p.nt * 6 * 32; i += blockDim.x) sts128(rad_a + 16 * i, p.rfrags[i]);
+    }
+    LaneConsts<UP> LC;
+    lane_setup<UP>(p.frags, p.slope, p.clamp_pre, lane, LC);
+    __syncthreads();  // the only block-wide barrier: warps run decoupled from here on
+
+    const int G = gridDim.x;
+    // layer constants of the column geometry: every column starts at the same offset inside its 16-byte aligned box
+    const int dx = first_in<UP>(0, p.px0, p.e) & 7;
+    const uint32_t xlane = static_cast<uint32_t>((g * kXP + dx + 2 * tig) * 2);
+
+    // ---- load cursor (meaningful in lane 0 only): next (item, block) this warp fetches ----
+    int l_item = static_cast<int>(blockIdx.x) - G, l_blk = 0, l_nblk = 0, l_plane = 0, l_ixa = 0, l_iy0 = 0;
+    auto refill = [&](int slot) {
+        while (l_blk >= l_nblk) {   // next item in which this warp has a share
+            l_item += G;
+            if (l_item >= p.n_total) { l_nblk = -1; return; }
+            SItem it;
+            decode_item(p, l_item, it);
+            int c, oy0;
+            if (!warp_share(p, it, warp, c, oy0)) continue;
+            l_blk = 0;
+            l_nblk = (UP == 2) ? 2 * it.R + 2 : it.R + 2;
+            l_plane = it.b * p.C + c;
+            l_ixa = first_in<UP>(it.tx * kOT, p.px0, p.e) & ~7;
+            l_iy0 = first_in<UP>(oy0, p.px0, p.e);
+        }
+        sbar_expect_tx(xbar_a + 8 * slot, kBlkBytes);
+        tma_box_3d(ring + slot * kBlkBytes, &tmap_x, xbar_a + 8 * slot, l_ixa, l_iy0 + kRowBlk * l_blk, l_plane);
+        ++l_blk;
+    };
+    if (lane == 0) {
+        for (int s = 0; s < S::NRING; ++s) {
+            if (l_nblk < 0) break;
+            refill(s);
+        }
+    }
+    int c_slot = 0;
+    uint32_t c_par = 0;   // consume cursor of the ring
+
+    // ---- staging cursors ----
+    int s_sb = 0, w_sb = 0, nb = 0;       // nb: blocks staged so far by this CTA (same count in every warp)
+    uint32_t s_par = 0, w_par = 0;        // parity of the use count of the buffer at the cursor
+
+    // item state of the compute side
+    SItem it = {};
+    int c = 0, oy0 = 0, blk = 0;
+    bool valid = false;
+    float oscale = 0.0f;
+
+    auto writeout = [&]() {
+        sbar_wait(full_a + 8 * w_sb, w_par);
+        const uint4 d0 = lds128(desc_a + 32 * w_sb), d1 = lds128(desc_a + 32 * w_sb + 16);
+        const int db = d0.x, dc0 = d0.y, dv = d0.z, dnsc = d0.w, dox0 = d1.x, doyb = d1.y, dsegrows = d1.z;
+        // ldmatrix row of this lane: matrix (lane >> 3) = pixel group (lane >> 4), channel set (lane >> 3) & 1; its 8 rows are
+        // the channels {0,1,4,5,8,9,12,13} + 2 * set, so that a thread ends up with four ADJACENT channels of one pixel.
+        const int chl = 4 * ((lane & 7) >> 1) + (lane & 1) + 2 * ((lane >> 3) & 1);
+        const uint32_t buf = stg + w_sb * kBufBytes;
+        for (int t = 0; t < dnsc; ++t) {
+            const int r = warp * dnsc + t;
+            const int q = r >> 4, yr = r & 15;
+            const int oy = doyb + q * dsegrows + yr;
+            if (oy < p.Hout) {   // warp-uniform
+                const uint32_t a = (chl < dv) ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a;
+                const uint32_t hstep = (chl < dv) ? 32u : 0u;
+                uint8_t* row = reinterpret_cast<uint8_t*>(p.y) +
+                               ((static_cast<long long>(db) * p.Hout + oy) * p.Wout * p.Cp_out + dc0) * 2 + 8 * (lane & 3);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t r4[4];
+                    ldsm_x4_trans(a + h * hstep, r4);
+                    const int ox = dox0 + h * 16 + (lane >> 2);
+                    if (ox < p.Wout) stg64(row + static_cast<long long>(ox) * p.Cp_out * 2, r4[0], r4[1]);
+                    if (ox + 8 < p.Wout) stg64(row + static_cast<long long>(ox + 8) * p.Cp_out * 2, r4[2], r4[3]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) sbar_arrive(empty_a + 8 * w_sb);
+        if (++w_sb == S::NSB) { w_sb = 0; w_par ^= 1; }
+    };
+
+    // A finished 16x32 block of this warp's channel (fp32 accumulators O) leaves the register file.
+    auto finalize = [&](float (&O)[4][4]) {
+        if constexpr (PLANAR) {
+            if (valid) {
+                const uint32_t pl = stg + warp * kPlaneBytes;
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        sts32(pl + ((hh * 8 + g) * kSP + no * 8 + 2 * tig) * 2, pack2(O[no][hh * 2 + 0] * oscale, O[no][hh * 2 + 1] * oscale));
+                __syncwarp();
+                const int row = lane >> 1, oy = oy0 + blk * kOB + row;
+                __half* yp = p.y + ((static_cast<long long>(it.b) * p.C + c) * p.Hout + oy) * p.Wp_out;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int ch = (lane & 1) * 2 + k, ox = it.tx * kOT + ch * 8;
+                    const uint4 v = lds128(pl + row * (kSP * 2) + ch * 16);
+                    if (oy < p.Hout && ox < p.Wout) stg128(yp + ox, v);
+                }
+                __syncwarp();
+            }
+            ++blk;
+        } else {
+            if (nb >= S::NSB) sbar_wait(empty_a + 8 * s_sb, s_par ^ 1);
+            if (valid) {
+                const uint32_t pl = stg + s_sb * kBufBytes + warp * kPlaneBytes;
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+                        sts32(pl + ((hh * 8 + g) * kSP + no * 8 + 2 * tig) * 2, pack2(O[no][hh * 2 + 0] * oscale, O[no][hh * 2 + 1] * oscale));
+            }
+            if (warp == 0 && lane == 0) {
+                sts128(desc_a + 32 * s_sb, make_uint4(it.b, it.c0, it.v, it.nsc));
+                sts128(desc_a + 32 * s_sb + 16, make_uint4(it.tx * kOT, it.seg0 * it.segrows + blk * kOB, it.segrows, 0));
+            }
+            __syncwarp();
+            if (lane == 0) sbar_arrive(full_a + 8 * s_sb);
+            if (++s_sb == S::NSB) { s_sb = 0; s_par ^= 1; }
+            ++nb;
+            ++blk;
+            if (nb > S::LAG) writeout();
+        }
+    };
+
+    // ---- the chain ----
+    uint32_t P1[2][kMB][2];   // packed A1^T of the two input-row blocks under the current strip
+    float OUT[2][4][4];       // two output blocks in flight (block i: strips 2i, 2i+1, 2i+2)
+
+    auto s1 = [&](uint32_t (&P)[kMB][2]) {   // consume the next ring block
+        sbar_wait(xbar_a + 8 * c_slot, c_par);
+        const uint32_t a = ring + c_slot * kBlkBytes + xlane;
+#pragma unroll
+        for (int m = 0; m < kMB; ++m) {
+            const uint32_t b0 = lds32(a + K::wblk(m) * 16), b1 = lds32(a + K::wblk(m) * 16 + 16);
+            mma16816_h(P[m], LC.AU[K::var(m)], b0, b1);
+        }
+        __syncwarp();   // every lane has its operands: the slot can take the next block of the sequence
+        if (lane == 0 && l_nblk >= 0) refill(c_slot);
+        if (++c_slot == S::NRING) { c_slot = 0; c_par ^= 1; }
+    };
+    // S2 (+activation) and S3 of one strip: P3 = packed O3^T, the B operands of S4.  RAD: term k's fragments from shared memory.
+    auto s2 = [&](const uint4& A, uint32_t (&Pa)[kMB][2], uint32_t (&Pb)[kMB][2], uint32_t (&P2)[kJB][2]) {
+#pragma unroll
+        for (int n8 = 0; n8 < kJB; ++n8) {
+            uint32_t t2[2];
+            mma16816_h(t2, A, Pa[n8 >> 1][n8 & 1], Pb[n8 >> 1][n8 & 1]);
+            P2[n8][0] = lrelu_clamp2(t2[0], LC.sl2, LC.cl2);
+            P2[n8][1] = lrelu_clamp2(t2[1], LC.sl2, LC.cl2);
+        }
+    };
+    auto s3 = [&](const uint4& H0, const uint4& H1, const uint4& H2, uint32_t (&P2)[kJB][2], uint32_t (&P3)[4][2]) {
+#pragma unroll
+        for (int mo = 0; mo < 2; ++mo) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float acc[4];
+                mma16816_z(acc, H0, P2[4 * mo][h], P2[4 * mo + 1][h]);
+                mma16816(acc, H1, P2[4 * mo + 2][h], P2[4 * mo + 3][h]);
+                mma16816(acc, H2, P2[4 * mo + 4][h], P2[4 * mo + 5][h]);
+                P3[2 * mo + 0][h] = pack2(acc[0], acc[1]);
+                P3[2 * mo + 1][h] = pack2(acc[2], acc[3]);
+            }
+        }
+    };
+    // S3 + S4 of one strip.  kstep_lo >= 0: this strip is k-step `kstep_lo` (0 or 1) of block Ocur; fin: it is also k-step 2 of Oprev.
+    auto s34 = [&](uint32_t (&P2)[kJB][2], float (&Ocur)[4][4], float (&Oprev)[4][4], int kstep_lo, bool fin) {
+        if constexpr (!RAD) {
+            uint32_t P3[4][2];
+            s3(LC.AD[0], LC.AD[1], LC.AD[2], P2, P3);
+            if (fin) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no) mma16816(Oprev[no], LC.AD[2], P3[no][0], P3[no][1]);
+            }
+            if (kstep_lo == 0) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no) mma16816_z(Ocur[no], LC.AD[0], P3[no][0], P3[no][1]);
+            } else if (kstep_lo == 1) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no) mma16816(Ocur[no], LC.AD[1], P3[no][0], P3[no][1]);
+            }
+        } else {
+            if (kstep_lo == 0) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) Ocur[no][q] = 0.0f;
+            }
+#pragma unroll 1
+            for (int k = 0; k < p.nt; ++k) {
+                const uint32_t fr = rad_a + ((k * 6) * 32 + lane) * 16;
+                const uint4 H0 = lds128(fr), H1 = lds128(fr + 512), H2 = lds128(fr + 1024);
+                uint32_t P3[4][2];
+                s3(H0, H1, H2, P2, P3);
+                if (fin) {
+                    const uint4 V = lds128(fr + 5 * 512);
+#pragma unroll
+                    for (int no = 0; no < 4; ++no) mma16816(Oprev[no], V, P3[no][0], P3[no][1]);
+                }
+                if (kstep_lo >= 0) {
+                    const uint4 V = lds128(fr + (3 + kstep_lo) * 512);
+#pragma unroll
+                    for (int no = 0; no < 4; ++no) mma16816(Ocur[no], V, P3[no][0], P3[no][1]);
+                }
+            }
+        }
+    };
+    // Output block i of the running segment (PAR = i & 1: which register set is "current").  Returns true after the last strip.
+    auto block_iter = [&](auto PARc, int i) -> bool {
+        constexpr int PAR = decltype(PARc)::value;
+        uint32_t P2[kJB][2];
+        // even strip 2i: blocks wb, wb+1
+        if constexpr (UP == 2) {
+            s1(P1[1]);                                   // input block 2i+1
+            s2(LC.AU[0], P1[0], P1[1], P2);
+        } else {
+            s1(P1[PAR ^ 1]);                             // input block i+1
+            s2(LC.AU[0], P1[PAR], P1[PAR ^ 1], P2);
+        }
+        const bool last = i == it.R;
+        s34(P2, OUT[PAR], OUT[PAR ^ 1], last ? -1 : 0, i > 0);
+        if (i > 0) finalize(OUT[PAR ^ 1]);
+        if (last) return true;
+        // odd strip 2i+1
+        if constexpr (UP == 2) {
+            s1(P1[0]);                                   // input block 2i+2
+            s2(LC.AU[0], P1[1], P1[0], P2);
+        } else {
+            s2(LC.AU[1], P1[PAR], P1[PAR ^ 1], P2);
+        }
+        s34(P2, OUT[PAR], OUT[PAR ^ 1], 1, false);
+        return false;
+    };
+
+    for (int item = blockIdx.x; item < p.n_total; item += G) {
+        decode_item(p, item, it);
+        valid = warp_share(p, it, warp, c, oy0);
+        blk = 0;
+        if (valid) {
+            oscale = (p.scale ? p.scale[it.b * p.C + c] : 1.0f) * p.out_gain;
+            s1(P1[0]);   // input block 0
+            for (int i = 0;; i += 2) {
+                if (block_iter(std::integral_constant<int, 0>(), i)) break;
+                if (block_iter(std::integral_constant<int, 1>(), i + 1)) break;
+            }
+        } else if (!PLANAR) {
+            // no share in this item: keep the staging protocol in step (and take part in the write-out)
+            float dummy[4][4];
+            for (int i = 0; i < it.R; ++i) finalize(dummy);
+        }
+    }
+    if constexpr (!PLANAR) {
+        const int pending = nb < S::LAG ? nb : S::LAG;
+        for (int k = 0; k < pending; ++k) writeout();
+    }
+}
+
+// Host side: split the columns into segments so that the round-robin deal over `sms` CTAs is even.
+struct StreamPlan {
+    int nseg, R, nsc, Rp, gfull, vlast, n_full, n_total;
+};
+inline StreamPlan plan_stream(int B, int C, int Hout, int tiles_x, int sms) {
+    StreamPlan pl;
+    pl.gfull = C / kCG;
+    pl.vlast = C % kCG;
+    const int TB = ceil_div(Hout, kOB);
+    pl.nsc = pl.vlast ? kCG / pl.vlast : 0;
+    pl.Rp = pl.vlast ? ceil_div(TB, pl.nsc) : 0;
+    const int n_part = pl.vlast ? B * tiles_x : 0;
+    long long best = -1;
+    pl.nseg = 1;
+    pl.R = TB;
+    for (int nseg = 1; nseg <= TB && nseg <= 16; ++nseg) {
+        const int R = ceil_div(TB, nseg);
+        if ((nseg - 1) * R >= TB) continue;   // an empty last segment
+        const long long n_full = static_cast<long long>(B) * pl.gfull * nseg * tiles_x;
+        // strips on the busiest CTA: its share of full items, then its share of partial items
+        const long long cost = ceil_div(static_cast<int>(n_full), sms) * (2LL * R + 1) + ceil_div(n_part, sms) * (2LL * pl.Rp + 1);
+        if (best < 0 || cost < best) { best = cost; pl.nseg = nseg; pl.R = R; }
+    }
+    pl.n_full = B * pl.gfull * pl.nseg * tiles_x;
+    pl.n_total = pl.n_full + n_part;
+    return pl;
+}

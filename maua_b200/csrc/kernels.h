@@ -96,9 +96,9 @@ struct ToRgbArgs {
 };
 int torgb_out_launch(const ToRgbArgs& a, cudaStream_t stream);
 
-// x f32 [B][C][H][W] * s[b][c] * gain -> fp16 planar (s may be nullptr)
+// x f32 [B][C][H][W] * s[b][c] * gain (+ bias[c]) -> fp16 planar (s, bias may be nullptr)
 int modulate_to_half_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Wp,
-                            cudaStream_t stream);
+                            cudaStream_t stream, const float* bias = nullptr);
 // x f32 [B][C][H][W] * s[b][c] * gain -> fp16 channels-last [B][H][W][Cp]
 int modulate_to_nhwc_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Cp,
                             cudaStream_t stream);

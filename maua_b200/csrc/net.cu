@@ -1058,18 +1058,45 @@ extern "C" int mb_filtered_lrelu(const float* x, const float* fu, const float* f
     __half *xh = nullptr, *yh = nullptr;
     MB_CUDA(cudaMalloc(&xh, static_cast<size_t>(B) * C * H * Wp * 2));
     MB_CUDA(cudaMalloc(&yh, static_cast<size_t>(B) * C * Ho * Wpo * 2));
-    int r = modulate_to_half_launch(x, nullptr, 1.0f, xh, B, C, H, W, Wp, stream);
-    fa.x = xh; fa.bias = b; fa.scale = nullptr; fa.y = yh;
+    // The tensor-core kernels take the bias already added (on the product path the conv epilogue adds it before its single
+    // fp16 rounding); MB_FLRELU_BIAS_SEPARATE=1 hands it to the kernel instead (tile kernels and CUDA-core kernels).
+    const char* impl = getenv("MB_FLRELU_IMPL");
+    const char* bsep = getenv("MB_FLRELU_BIAS_SEPARATE");
+    const bool fold_bias = b != nullptr && !(impl && atoi(impl) != 0) && !(bsep && atoi(bsep) != 0);
+    int r = modulate_to_half_launch(x, nullptr, 1.0f, xh, B, C, H, W, Wp, stream, fold_bias ? b : nullptr);
+    fa.x = xh; fa.bias = fold_bias ? nullptr : b; fa.scale = nullptr; fa.y = yh;
     fa.B = B; fa.C = C; fa.Hin = H; fa.Win = W; fa.Wp_in = Wp; fa.Hout = Ho; fa.Wout = Wo; fa.Wp_out = Wpo;
     fa.up = up; fa.down = down; fa.up_taps = up_taps; fa.down_taps = down_taps; fa.fd_2d = fd_2d;
     fa.px0 = px0; fa.py0 = py0;
     fa.gain = gain; fa.slope = slope; fa.clamp = clamp;
     fa.num_sms = g_num_sms;
-    const char* impl = getenv("MB_FLRELU_IMPL");
+    // MB_FLRELU_TEST_NHWC=1: run the channels-last variant of the tensor-core kernel (what a layer that feeds a conv uses)
+    __half* yn = nullptr;
+    const char* tn = getenv("MB_FLRELU_TEST_NHWC");
+    const int Cp = (C + 15) / 16 * 16;
+    if (tn && atoi(tn) != 0 && fa.bias == nullptr && !(impl && atoi(impl) != 0) && flrelu_mma_supported(fa)) {
+        MB_CUDA(cudaMalloc(&yn, static_cast<size_t>(B) * Ho * Wo * Cp * 2));
+        MB_CUDA(cudaMemsetAsync(yn, 0xff, static_cast<size_t>(B) * Ho * Wo * Cp * 2, stream));   // NaN pattern: every chunk must be written
+        fa.y_nhwc = yn;
+        fa.Cp_out = Cp;
+    }
     if (r == MB_OK) r = flrelu_launch_impl(fa, impl ? atoi(impl) : 0, stream);
-    if (r == MB_OK) r = half_to_float_launch(yh, y, B, C, Ho, Wo, Wpo, stream);
+    if (r == MB_OK) r = yn ? nhwc_to_float_launch(yn, y, B, C, Ho, Wo, Cp, stream) : half_to_float_launch(yh, y, B, C, Ho, Wo, Wpo, stream);
     cudaError_t e = cudaStreamSynchronize(stream);
+    if (yn && r == MB_OK && e == cudaSuccess && Cp > C) {
+        // the pad channels feed zero weights of the next conv: they must hold zeros, not stale bytes
+        std::vector<uint16_t> host(static_cast<size_t>(B) * Ho * Wo * Cp);
+        e = cudaMemcpy(host.data(), yn, host.size() * 2, cudaMemcpyDeviceToHost);
+        for (size_t px = 0; e == cudaSuccess && r == MB_OK && px < host.size() / Cp; ++px)
+            for (int cpad = C; cpad < Cp; ++cpad)
+                if ((host[px * Cp + cpad] & 0x7fff) != 0) {
+                    set_error("mb_filtered_lrelu: channels-last pad channel %d of pixel %zu is not zero (0x%04x)", cpad, px, host[px * Cp + cpad]);
+                    r = MB_ECUDA;
+                    break;
+                }
+    }
     cudaFree(xh); cudaFree(yh);
+    if (yn) cudaFree(yn);
     if (r == MB_OK && e != cudaSuccess) {
         set_error("mb_filtered_lrelu: %s", cudaGetErrorString(e));
         return MB_ECUDA;

@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
 }
 
 __global__ void modulate_to_half_kernel(const float* __restrict__ x, const float* __restrict__ s, float gain,
-                                        __half* __restrict__ out, int B, int C, int H, int W, int Wp) {
+                                        __half* __restrict__ out, int B, int C, int H, int W, int Wp,
+                                        const float* __restrict__ bias) {
     const long long total = static_cast<long long>(B) * C * H * Wp;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -387,6 +388,7 @@ __global__ void modulate_to_half_kernel(const float* __restrict__ x, const float
         if (w < W) {
             v = x[r * W + w] * gain;
             if (s) v *= s[bc];
+            if (bias) v += bias[bc % C];
         }
         out[idx] = __float2half_rn(v);
     }
@@ -621,9 +623,9 @@ int torgb_out_launch(const ToRgbArgs& a, cudaStream_t stream) {
 }
 
 int modulate_to_half_launch(const float* x, const float* s, float gain, __half* out, int B, int C, int H, int W, int Wp,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const float* bias) {
     const long long total = static_cast<long long>(B) * C * H * Wp;
-    modulate_to_half_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, s, gain, out, B, C, H, W, Wp);
+    modulate_to_half_kernel<<<grid_for(total, 256), 256, 0, stream>>>(x, s, gain, out, B, C, H, W, Wp, bias);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -84,3 +84,49 @@ def test_filtered_lrelu(cuda, case, impl, monkeypatch):
     # max error relative to the RMS (values reach ~4-5 RMS).  CUDA-core kernels: fp32 arithmetic, fp16 output
     # rounding only.  Tensor-core chain: fp16 taps (DC-corrected) and fp16 rounding between the four passes.
     assert _rel_err(got, ref) < (1e-2 if impl == "tensorcore" else 5e-3)
+
+
+# Streaming kernels (flrelu_stream.cuh) against the tile kernels (flrelu_mma.cu) they replace: the MMA sequence per output
+# element is the same, so the results must be bit-identical; and against the oracle, in both output layouts.
+# C covers full 16-channel groups, partial last groups (v = 1, 3, 11 channels) and fewer than 16 channels;
+# heights cover columns of one block up to columns the planner splits into several segments.
+STREAM_CASES = [
+    # B, C, H, W, up, ut, pad(lo,hi), radial
+    (2, 16, 38, 38, 2, 12, (9, 8), False),
+    (1, 17, 54, 54, 4, 24, (-6, -9), False),
+    (2, 19, 150, 130, 2, 12, (-11, -12), False),
+    (1, 35, 86, 86, 4, 24, (-6, -9), True),
+    (1, 3, 300, 90, 2, 12, (9, 8), False),
+    (1, 27, 200, 180, 4, 24, (-7, -8), False),
+    (3, 32, 90, 70, 2, 12, (-10, -13), False),
+    (1, 51, 276, 70, 2, 12, (-10, -13), False),
+    (1, 20, 120, 100, 2, 12, (-10, -13), True),
+    (1, 81, 140, 64, 4, 24, (-6, -9), False),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES)
+@pytest.mark.parametrize("layout", ["planar", "nhwc"])
+def test_filtered_lrelu_stream(cuda, case, layout, monkeypatch):
+    from maua_b200 import ops
+
+    B, C, H, W, up, ut, (lo, hi), radial = case
+    monkeypatch.setenv("MB_FLRELU_IMPL", "0")
+    monkeypatch.setenv("MB_FLRELU_TEST_NHWC", "1" if layout == "nhwc" else "0")
+    g = torch.Generator().manual_seed(7 + H + C)
+    x = (torch.randn(B, C, H, W, generator=g) * 2).half().float()
+    b = torch.randn(C, generator=g)
+    fu = O.design_lowpass_filter(ut, 8.0, 9.0, 64.0)
+    fd = O.design_lowpass_filter(12, 8.0, 9.0, 64.0, radial=radial)
+    pad = [lo, hi, lo, hi]
+    kw = dict(up=up, down=2, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=256)
+    args = (x.to(cuda), fu.to(cuda), fd.to(cuda), b.to(cuda))
+    monkeypatch.setenv("MB_FLRELU_STREAM", "1")
+    got = ops.filtered_lrelu(*args, **kw)
+    monkeypatch.setenv("MB_FLRELU_STREAM", "0")
+    tile = ops.filtered_lrelu(*args, **kw)
+    ref = O.filtered_lrelu_ref(x, fu=fu, fd=fd, b=b, **kw)
+    assert got.shape == ref.shape
+    assert torch.isfinite(got).all()
+    assert _rel_err(got, ref) < 1e-2
+    assert torch.equal(got, tile), f"stream vs tile kernels differ: max {float((got - tile).abs().max()):.3e}"

@@ -1041,7 +1041,7 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
             MB_REQUIRE(a.Wp_in % 8 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "filtered_lrelu: input rows must be 16-byte aligned");
             cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.Win), static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B) * a.C};
             cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.Wp_in) * 2, static_cast<cuuint64_t>(a.Wp_in) * 2 * a.Hin};
-            cuuint32_t box[3] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(kRowBlk), 1};
+            cuuint32_t box[3] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(S::BOXROWS), 1};
             cuuint32_t es[3] = {1, 1, 1};
             CUresult cr = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(a.x), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,

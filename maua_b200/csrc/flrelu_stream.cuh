@@ -29,19 +29,22 @@
 // order), so results are bit-identical to the tile kernels.
 #pragma once
 
-constexpr int kRowBlk = 8;                         // input rows per ring block (one n8 block of the S1 GEMM)
-constexpr int kBlkBytes = kRowBlk * kXP * 2;       // 896
+constexpr int kRowBlk = 8;                         // input rows per S1 block (one n8 block of the S1 GEMM)
 constexpr int kOB = 16;                            // output rows per finished block
 constexpr int kPlaneBytes = kOB * kSP * 2 + 16;    // staged 16x32 block of one channel (+16: ldmatrix rows of 8 planes on distinct banks)
 constexpr int kBufBytes = kCG * kPlaneBytes;       // 20736 = 162 * 128
-constexpr int kSTail = 2048;                       // zero chunk | block descriptors | mbarriers
+constexpr int kSTail = 2048;                       // zero chunk | item table | block descriptors | mbarriers
+constexpr int kItemSlots = 8;                      // items whose blocks may still be waiting for their write-out
 
 template <int UP>
 struct SC {
-    static constexpr int NRING = (UP == 2) ? 6 : 4;  // input blocks in flight per warp (up=2 consumes two per output block)
+    // One TMA box feeds one output block: 16 input rows (two S1 blocks) at up=2, 8 rows at up=4.
+    static constexpr int BOXROWS = (UP == 2) ? 16 : 8;
+    static constexpr int BOXBYTES = BOXROWS * kXP * 2;
+    static constexpr int NRING = (UP == 2) ? 3 : 4;  // boxes per warp: the fetch runs two / three output blocks ahead
     static constexpr int NSB = 6;                    // staging buffers
     static constexpr int LAG = 3;                    // the write-out runs this many blocks behind the staging
-    static constexpr int RING_BYTES = kCG * NRING * kBlkBytes;
+    static constexpr int RING_BYTES = kCG * NRING * BOXBYTES;
     static constexpr int SMEM = RING_BYTES + NSB * kBufBytes + kSTail + 128;
 };
 
@@ -163,16 +166,17 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     const uint32_t sbase = (smem_u32(smem_dyn) + 127u) & ~127u;   // TMA destinations
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, tig = lane & 3;
-    const uint32_t ring = sbase + warp * (S::NRING * kBlkBytes);
+    const uint32_t ring = sbase + warp * (S::NRING * S::BOXBYTES);
     const uint32_t stg = sbase + S::RING_BYTES;
     const uint32_t tail = stg + S::NSB * kBufBytes;
-    const uint32_t zero_a = tail;                 // 16 zero bytes: the pad channels of a partial group
-    const uint32_t desc_a = tail + 64;            // [NSB] x 32 bytes: where a staged block goes
-    const uint32_t full_a = tail + 64 + S::NSB * 32;
+    const uint32_t zero_a = tail;                               // 16 zero bytes: the pad channels of a partial group
+    const uint32_t itab_a = tail + 64;                          // [kItemSlots] x 32 bytes: where the blocks of an item go
+    const uint32_t desc_a = itab_a + kItemSlots * 32;           // [NSB] x 8 bytes: (item slot, first row) of a staged block
+    const uint32_t full_a = desc_a + S::NSB * 8;
     const uint32_t empty_a = full_a + S::NSB * 8;
     const uint32_t xbar_a = empty_a + S::NSB * 8 + warp * (S::NRING * 8);
-    const uint32_t rad_a = tail + kSTail;         // radial down filter: [nt][6][32] uint4
-    static_assert(64 + SC<UP>::NSB * 48 + kCG * SC<UP>::NRING * 8 <= kSTail, "tail too small");
+    const uint32_t rad_a = tail + kSTail;                       // radial down filter: [nt][6][32] uint4
+    static_assert(64 + kItemSlots * 32 + SC<UP>::NSB * 24 + kCG * SC<UP>::NRING * 8 <= kSTail, "tail too small");
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmap_x);
@@ -192,33 +196,32 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     __syncthreads();  // the only block-wide barrier: warps run decoupled from here on
 
     const int G = gridDim.x;
-    // layer constants of the column geometry: every column starts at the same offset inside its 16-byte aligned box
-    const int dx = first_in<UP>(0, p.px0, p.e) & 7;
-    const uint32_t xlane = static_cast<uint32_t>((g * kXP + dx + 2 * tig) * 2);
+    // layer constant of the column geometry: every column starts at the same offset inside its 16-byte aligned box
+    const uint32_t xlane = ring + static_cast<uint32_t>((g * kXP + (first_in<UP>(0, p.px0, p.e) & 7) + 2 * tig) * 2);
 
-    // ---- load cursor (meaningful in lane 0 only): next (item, block) this warp fetches ----
-    int l_item = static_cast<int>(blockIdx.x) - G, l_blk = 0, l_nblk = 0, l_plane = 0, l_ixa = 0, l_iy0 = 0;
+    // ---- load cursor (meaningful in lane 0 only): next (item, box) this warp fetches ----
+    int l_item = static_cast<int>(blockIdx.x) - G, l_left = 0, l_plane = 0, l_ixa = 0, l_row = 0;
     auto refill = [&](int slot) {
-        while (l_blk >= l_nblk) {   // next item in which this warp has a share
+        while (l_left == 0) {   // next item in which this warp has a share
             l_item += G;
-            if (l_item >= p.n_total) { l_nblk = -1; return; }
+            if (l_item >= p.n_total) { l_left = -1; return; }
             SItem it;
             decode_item(p, l_item, it);
             int c, oy0;
             if (!warp_share(p, it, warp, c, oy0)) continue;
-            l_blk = 0;
-            l_nblk = (UP == 2) ? 2 * it.R + 2 : it.R + 2;
+            l_left = it.R + ((UP == 2) ? 1 : 2);   // up=2: 2R+2 row blocks in 16-row boxes, up=4: R+2 8-row boxes
             l_plane = it.b * p.C + c;
             l_ixa = first_in<UP>(it.tx * kOT, p.px0, p.e) & ~7;
-            l_iy0 = first_in<UP>(oy0, p.px0, p.e);
+            l_row = first_in<UP>(oy0, p.px0, p.e);
         }
-        sbar_expect_tx(xbar_a + 8 * slot, kBlkBytes);
-        tma_box_3d(ring + slot * kBlkBytes, &tmap_x, xbar_a + 8 * slot, l_ixa, l_iy0 + kRowBlk * l_blk, l_plane);
-        ++l_blk;
+        sbar_expect_tx(xbar_a + 8 * slot, S::BOXBYTES);
+        tma_box_3d(ring + slot * S::BOXBYTES, &tmap_x, xbar_a + 8 * slot, l_ixa, l_row, l_plane);
+        l_row += S::BOXROWS;
+        --l_left;
     };
     if (lane == 0) {
         for (int s = 0; s < S::NRING; ++s) {
-            if (l_nblk < 0) break;
+            if (l_left < 0) break;
             refill(s);
         }
     }
@@ -230,35 +233,39 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     uint32_t s_par = 0, w_par = 0;        // parity of the use count of the buffer at the cursor
 
     // item state of the compute side
-    SItem it = {};
-    int c = 0, oy0 = 0, blk = 0;
+    int Rit = 0, blk = 0, islot = 0, oyb0 = 0;
     bool valid = false;
     float oscale = 0.0f;
+    __half* yp = nullptr;   // PLANAR: this warp's plane at (first row of the segment, first column of the item)
+    int rows_left = 0;      // PLANAR: image rows from the segment's first row down
 
     auto writeout = [&]() {
         sbar_wait(full_a + 8 * w_sb, w_par);
-        const uint4 d0 = lds128(desc_a + 32 * w_sb), d1 = lds128(desc_a + 32 * w_sb + 16);
-        const int db = d0.x, dc0 = d0.y, dv = d0.z, dnsc = d0.w, dox0 = d1.x, doyb = d1.y, dsegrows = d1.z;
+        uint32_t dslot, doyb;
+        asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(dslot), "=r"(doyb) : "r"(desc_a + 8 * w_sb));
+        const uint4 d0 = lds128(itab_a + 32 * dslot), d1 = lds128(itab_a + 32 * dslot + 16);
+        const int dv = d0.z, dnsc = d0.w, dox0 = d1.x, dsegrows = d1.y;
         // ldmatrix row of this lane: matrix (lane >> 3) = pixel group (lane >> 4), channel set (lane >> 3) & 1; its 8 rows are
         // the channels {0,1,4,5,8,9,12,13} + 2 * set, so that a thread ends up with four ADJACENT channels of one pixel.
         const int chl = 4 * ((lane & 7) >> 1) + (lane & 1) + 2 * ((lane >> 3) & 1);
+        const bool real = chl < dv;
         const uint32_t buf = stg + w_sb * kBufBytes;
+        uint8_t* base = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(d0.y) << 32) | d0.x) + 8 * (lane & 3) +
+                        static_cast<long long>(lane >> 2) * p.Cp_out * 2;
+        const int ox = dox0 + (lane >> 2);
         for (int t = 0; t < dnsc; ++t) {
             const int r = warp * dnsc + t;
             const int q = r >> 4, yr = r & 15;
-            const int oy = doyb + q * dsegrows + yr;
+            const int oy = static_cast<int>(doyb) + q * dsegrows + yr;
             if (oy < p.Hout) {   // warp-uniform
-                const uint32_t a = (chl < dv) ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a;
-                const uint32_t hstep = (chl < dv) ? 32u : 0u;
-                uint8_t* row = reinterpret_cast<uint8_t*>(p.y) +
-                               ((static_cast<long long>(db) * p.Hout + oy) * p.Wout * p.Cp_out + dc0) * 2 + 8 * (lane & 3);
+                const uint32_t a = real ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a;
+                uint8_t* row = base + static_cast<long long>(oy) * p.Wout * p.Cp_out * 2;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r4[4];
-                    ldsm_x4_trans(a + h * hstep, r4);
-                    const int ox = dox0 + h * 16 + (lane >> 2);
-                    if (ox < p.Wout) stg64(row + static_cast<long long>(ox) * p.Cp_out * 2, r4[0], r4[1]);
-                    if (ox + 8 < p.Wout) stg64(row + static_cast<long long>(ox + 8) * p.Cp_out * 2, r4[2], r4[3]);
+                    ldsm_x4_trans(real ? a + h * 32 : a, r4);
+                    if (ox + h * 16 < p.Wout) stg64(row + static_cast<long long>(h * 16) * p.Cp_out * 2, r4[0], r4[1]);
+                    if (ox + h * 16 + 8 < p.Wout) stg64(row + static_cast<long long>(h * 16 + 8) * p.Cp_out * 2, r4[2], r4[3]);
                 }
             }
         }
@@ -270,24 +277,21 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     // A finished 16x32 block of this warp's channel (fp32 accumulators O) leaves the register file.
     auto finalize = [&](float (&O)[4][4]) {
         if constexpr (PLANAR) {
-            if (valid) {
-                const uint32_t pl = stg + warp * kPlaneBytes;
+            const uint32_t pl = stg + warp * kPlaneBytes;
 #pragma unroll
-                for (int no = 0; no < 4; ++no)
+            for (int no = 0; no < 4; ++no)
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh)
-                        sts32(pl + ((hh * 8 + g) * kSP + no * 8 + 2 * tig) * 2, pack2(O[no][hh * 2 + 0] * oscale, O[no][hh * 2 + 1] * oscale));
-                __syncwarp();
-                const int row = lane >> 1, oy = oy0 + blk * kOB + row;
-                __half* yp = p.y + ((static_cast<long long>(it.b) * p.C + c) * p.Hout + oy) * p.Wp_out;
+                for (int hh = 0; hh < 2; ++hh)
+                    sts32(pl + ((hh * 8 + g) * kSP + no * 8 + 2 * tig) * 2, pack2(O[no][hh * 2 + 0] * oscale, O[no][hh * 2 + 1] * oscale));
+            __syncwarp();
+            const int row = blk * kOB + (lane >> 1);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const int ch = (lane & 1) * 2 + k, ox = it.tx * kOT + ch * 8;
-                    const uint4 v = lds128(pl + row * (kSP * 2) + ch * 16);
-                    if (oy < p.Hout && ox < p.Wout) stg128(yp + ox, v);
-                }
-                __syncwarp();
+            for (int k = 0; k < 2; ++k) {
+                const int ch = (lane & 1) * 2 + k;
+                const uint4 v = lds128(pl + (lane >> 1) * (kSP * 2) + ch * 16);
+                if (row < rows_left && ch * 8 < oyb0) stg128(yp + static_cast<long long>(row) * p.Wp_out + ch * 8, v);   // oyb0: columns left
             }
+            __syncwarp();
             ++blk;
         } else {
             if (nb >= S::NSB) sbar_wait(empty_a + 8 * s_sb, s_par ^ 1);
@@ -299,10 +303,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
                     for (int hh = 0; hh < 2; ++hh)
                         sts32(pl + ((hh * 8 + g) * kSP + no * 8 + 2 * tig) * 2, pack2(O[no][hh * 2 + 0] * oscale, O[no][hh * 2 + 1] * oscale));
             }
-            if (warp == 0 && lane == 0) {
-                sts128(desc_a + 32 * s_sb, make_uint4(it.b, it.c0, it.v, it.nsc));
-                sts128(desc_a + 32 * s_sb + 16, make_uint4(it.tx * kOT, it.seg0 * it.segrows + blk * kOB, it.segrows, 0));
-            }
+            if (threadIdx.x == 0)
+                asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(desc_a + 8 * s_sb), "r"(islot), "r"(oyb0 + blk * kOB) : "memory");
             __syncwarp();
             if (lane == 0) sbar_arrive(full_a + 8 * s_sb);
             if (++s_sb == S::NSB) { s_sb = 0; s_par ^= 1; }
@@ -313,22 +315,27 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     };
 
     // ---- the chain ----
+    constexpr int NSET = RAD ? 2 : 1;   // separable filter: one block of accumulators (k-step 2 of block i-1 is finished and
+                                        // staged before k-step 0 of block i overwrites it); radial: both accumulate over the terms
     uint32_t P1[2][kMB][2];   // packed A1^T of the two input-row blocks under the current strip
-    float OUT[2][4][4];       // two output blocks in flight (block i: strips 2i, 2i+1, 2i+2)
+    float OUT[NSET][4][4];
 
-    auto s1 = [&](uint32_t (&P)[kMB][2]) {   // consume the next ring block
-        sbar_wait(xbar_a + 8 * c_slot, c_par);
-        const uint32_t a = ring + c_slot * kBlkBytes + xlane;
+    // S1 of one 8-row input block at byte offset `off` inside the current ring box
+    auto s1 = [&](uint32_t (&P)[kMB][2], int off) {
+        const uint32_t a = xlane + c_slot * S::BOXBYTES + off;
 #pragma unroll
         for (int m = 0; m < kMB; ++m) {
             const uint32_t b0 = lds32(a + K::wblk(m) * 16), b1 = lds32(a + K::wblk(m) * 16 + 16);
             mma16816_h(P[m], LC.AU[K::var(m)], b0, b1);
         }
-        __syncwarp();   // every lane has its operands: the slot can take the next block of the sequence
-        if (lane == 0 && l_nblk >= 0) refill(c_slot);
+    };
+    auto box_wait = [&]() { sbar_wait(xbar_a + 8 * c_slot, c_par); };
+    auto box_release = [&]() {
+        __syncwarp();   // every lane has its operands: the slot can take the next box of the sequence
+        if (lane == 0 && l_left >= 0) refill(c_slot);
         if (++c_slot == S::NRING) { c_slot = 0; c_par ^= 1; }
     };
-    // S2 (+activation) and S3 of one strip: P3 = packed O3^T, the B operands of S4.  RAD: term k's fragments from shared memory.
+    // S2 (+activation) of one strip
     auto s2 = [&](const uint4& A, uint32_t (&Pa)[kMB][2], uint32_t (&Pb)[kMB][2], uint32_t (&P2)[kJB][2]) {
 #pragma unroll
         for (int n8 = 0; n8 < kJB; ++n8) {
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             P2[n8][1] = lrelu_clamp2(t2[1], LC.sl2, LC.cl2);
         }
     };
+    // S3: P3 = packed O3^T of the strip, the B operands of S4
     auto s3 = [&](const uint4& H0, const uint4& H1, const uint4& H2, uint32_t (&P2)[kJB][2], uint32_t (&P3)[4][2]) {
 #pragma unroll
         for (int mo = 0; mo < 2; ++mo) {
@@ -352,90 +360,129 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             }
         }
     };
-    // S3 + S4 of one strip.  kstep_lo >= 0: this strip is k-step `kstep_lo` (0 or 1) of block Ocur; fin: it is also k-step 2 of Oprev.
-    auto s34 = [&](uint32_t (&P2)[kJB][2], float (&Ocur)[4][4], float (&Oprev)[4][4], int kstep_lo, bool fin) {
-        if constexpr (!RAD) {
-            uint32_t P3[4][2];
-            s3(LC.AD[0], LC.AD[1], LC.AD[2], P2, P3);
-            if (fin) {
+    // radial: S3 + S4 of one strip over the separable terms (fragments from shared memory).  kstep_lo >= 0: the strip is
+    // k-step `kstep_lo` (0 or 1) of block Ocur; fin: it is also k-step 2 of Oprev.
+    auto s34_rad = [&](uint32_t (&P2)[kJB][2], float (&Ocur)[4][4], float (&Oprev)[4][4], int kstep_lo, bool fin) {
+        if (kstep_lo == 0) {
 #pragma unroll
-                for (int no = 0; no < 4; ++no) mma16816(Oprev[no], LC.AD[2], P3[no][0], P3[no][1]);
-            }
-            if (kstep_lo == 0) {
+            for (int no = 0; no < 4; ++no)
 #pragma unroll
-                for (int no = 0; no < 4; ++no) mma16816_z(Ocur[no], LC.AD[0], P3[no][0], P3[no][1]);
-            } else if (kstep_lo == 1) {
-#pragma unroll
-                for (int no = 0; no < 4; ++no) mma16816(Ocur[no], LC.AD[1], P3[no][0], P3[no][1]);
-            }
-        } else {
-            if (kstep_lo == 0) {
-#pragma unroll
-                for (int no = 0; no < 4; ++no)
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) Ocur[no][q] = 0.0f;
-            }
+                for (int q = 0; q < 4; ++q) Ocur[no][q] = 0.0f;
+        }
 #pragma unroll 1
-            for (int k = 0; k < p.nt; ++k) {
-                const uint32_t fr = rad_a + ((k * 6) * 32 + lane) * 16;
-                const uint4 H0 = lds128(fr), H1 = lds128(fr + 512), H2 = lds128(fr + 1024);
-                uint32_t P3[4][2];
-                s3(H0, H1, H2, P2, P3);
-                if (fin) {
-                    const uint4 V = lds128(fr + 5 * 512);
+        for (int k = 0; k < p.nt; ++k) {
+            const uint32_t fr = rad_a + ((k * 6) * 32 + lane) * 16;
+            const uint4 H0 = lds128(fr), H1 = lds128(fr + 512), H2 = lds128(fr + 1024);
+            uint32_t P3[4][2];
+            s3(H0, H1, H2, P2, P3);
+            if (fin) {
+                const uint4 V = lds128(fr + 5 * 512);
 #pragma unroll
-                    for (int no = 0; no < 4; ++no) mma16816(Oprev[no], V, P3[no][0], P3[no][1]);
-                }
-                if (kstep_lo >= 0) {
-                    const uint4 V = lds128(fr + (3 + kstep_lo) * 512);
+                for (int no = 0; no < 4; ++no) mma16816(Oprev[no], V, P3[no][0], P3[no][1]);
+            }
+            if (kstep_lo >= 0) {
+                const uint4 V = lds128(fr + (3 + kstep_lo) * 512);
 #pragma unroll
-                    for (int no = 0; no < 4; ++no) mma16816(Ocur[no], V, P3[no][0], P3[no][1]);
-                }
+                for (int no = 0; no < 4; ++no) mma16816(Ocur[no], V, P3[no][0], P3[no][1]);
             }
         }
     };
-    // Output block i of the running segment (PAR = i & 1: which register set is "current").  Returns true after the last strip.
+    // Output block i of the running segment: strips 2i (which also finishes block i-1) and 2i+1.  PAR = i & 1 selects the
+    // P1 slots (up=4) and the accumulator set (radial).  Returns true after the last strip of the segment.
     auto block_iter = [&](auto PARc, int i) -> bool {
         constexpr int PAR = decltype(PARc)::value;
+        constexpr int CUR = RAD ? PAR : 0, PRV = RAD ? (PAR ^ 1) : 0;
         uint32_t P2[kJB][2];
-        // even strip 2i: blocks wb, wb+1
+        // even strip 2i
         if constexpr (UP == 2) {
-            s1(P1[1]);                                   // input block 2i+1
+            s1(P1[1], kRowBlk * kXP * 2);                // input block 2i+1: second half of box i
+            box_release();
             s2(LC.AU[0], P1[0], P1[1], P2);
         } else {
-            s1(P1[PAR ^ 1]);                             // input block i+1
+            box_wait();
+            s1(P1[PAR ^ 1], 0);                          // input block i+1
+            box_release();
             s2(LC.AU[0], P1[PAR], P1[PAR ^ 1], P2);
         }
-        const bool last = i == it.R;
-        s34(P2, OUT[PAR], OUT[PAR ^ 1], last ? -1 : 0, i > 0);
-        if (i > 0) finalize(OUT[PAR ^ 1]);
-        if (last) return true;
+        const bool last = i == Rit;
+        if constexpr (!RAD) {
+            uint32_t P3[4][2];
+            s3(LC.AD[0], LC.AD[1], LC.AD[2], P2, P3);
+            if (i > 0) {
+#pragma unroll
+                for (int no = 0; no < 4; ++no) mma16816(OUT[0][no], LC.AD[2], P3[no][0], P3[no][1]);
+                finalize(OUT[0]);
+            }
+            if (last) return true;
+#pragma unroll
+            for (int no = 0; no < 4; ++no) mma16816_z(OUT[0][no], LC.AD[0], P3[no][0], P3[no][1]);
+        } else {
+            s34_rad(P2, OUT[CUR], OUT[PRV], last ? -1 : 0, i > 0);
+            if (i > 0) finalize(OUT[PRV]);
+            if (last) return true;
+        }
         // odd strip 2i+1
         if constexpr (UP == 2) {
-            s1(P1[0]);                                   // input block 2i+2
+            box_wait();
+            s1(P1[0], 0);                                // input block 2i+2: first half of box i+1
             s2(LC.AU[0], P1[1], P1[0], P2);
         } else {
             s2(LC.AU[1], P1[PAR], P1[PAR ^ 1], P2);
         }
-        s34(P2, OUT[PAR], OUT[PAR ^ 1], 1, false);
+        if constexpr (!RAD) {
+            uint32_t P3[4][2];
+            s3(LC.AD[0], LC.AD[1], LC.AD[2], P2, P3);
+#pragma unroll
+            for (int no = 0; no < 4; ++no) mma16816(OUT[0][no], LC.AD[1], P3[no][0], P3[no][1]);
+        } else {
+            s34_rad(P2, OUT[CUR], OUT[PRV], 1, false);
+        }
         return false;
     };
 
-    for (int item = blockIdx.x; item < p.n_total; item += G) {
-        decode_item(p, item, it);
-        valid = warp_share(p, it, warp, c, oy0);
-        blk = 0;
+    int nitem = 0;
+    for (int item = blockIdx.x; item < p.n_total; item += G, ++nitem) {
+        int c, oy0;
+        {
+            SItem it;
+            decode_item(p, item, it);
+            valid = warp_share(p, it, warp, c, oy0);
+            Rit = it.R;
+            blk = 0;
+            oscale = (valid && p.scale ? p.scale[it.b * p.C + c] : 1.0f) * p.out_gain;
+            if constexpr (PLANAR) {
+                yp = p.y + ((static_cast<long long>(it.b) * p.C + c) * p.Hout + oy0) * p.Wp_out + it.tx * kOT;
+                rows_left = p.Hout - oy0;
+                oyb0 = p.Wout - it.tx * kOT;   // columns left (a 16-byte chunk is stored when its first column is inside)
+            } else {
+                islot = nitem & (kItemSlots - 1);
+                oyb0 = it.seg0 * it.segrows;
+                if (threadIdx.x == 0) {
+                    // where this item's blocks go: channels-last address of (frame, row 0, first column, first channel)
+                    const unsigned long long base = reinterpret_cast<unsigned long long>(p.y) +
+                        ((static_cast<long long>(it.b) * p.Hout * p.Wout + it.tx * kOT) * p.Cp_out + it.c0) * 2;
+                    sts128(itab_a + 32 * islot, make_uint4(static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32), it.v, it.nsc));
+                    sts128(itab_a + 32 * islot + 16, make_uint4(it.tx * kOT, it.segrows, 0, 0));
+                }
+            }
+        }
         if (valid) {
-            oscale = (p.scale ? p.scale[it.b * p.C + c] : 1.0f) * p.out_gain;
-            s1(P1[0]);   // input block 0
-            for (int i = 0;; i += 2) {
-                if (block_iter(std::integral_constant<int, 0>(), i)) break;
-                if (block_iter(std::integral_constant<int, 1>(), i + 1)) break;
+            box_wait();
+            s1(P1[0], 0);   // input block 0
+            if constexpr (UP == 4) box_release();
+            if constexpr (UP == 2 && !RAD) {
+                for (int i = 0;; ++i)
+                    if (block_iter(std::integral_constant<int, 0>(), i)) break;
+            } else {
+                for (int i = 0;; i += 2) {
+                    if (block_iter(std::integral_constant<int, 0>(), i)) break;
+                    if (block_iter(std::integral_constant<int, 1>(), i + 1)) break;
+                }
             }
         } else if (!PLANAR) {
             // no share in this item: keep the staging protocol in step (and take part in the write-out)
             float dummy[4][4];
-            for (int i = 0; i < it.R; ++i) finalize(dummy);
+            for (int i = 0; i < Rit; ++i) finalize(dummy);
         }
     }
     if constexpr (!PLANAR) {

@@ -13,8 +13,9 @@ aggregated error when none succeeds (:192-207).  Differences, all forced by what
   depth) instead of being assumed (the reference's ``load_nvidia_pt`` assumes 1024^2 / 8 mapping layers, :167-169).
 * StyleGAN2 checkpoints in the NVIDIA training layout (``synthesis.b64.conv0...``, ``mapping.fc3``, ``noise_strength``)
   are mapped onto the in-tree inference layout this build implements (``synthesis.bs.4.conv0...``, ``mapping.fcs.3``,
-  the same mapping the reference's converter uses at :23,65,71); the inference network adds its noise unscaled
-  (inference/ops.py:184), so ``noise_strength`` is folded into ``noise_const``.
+  the same mapping the reference's converter uses at :23,65,71).  What the training network does differently stays with the
+  loaded generator: every layer's ``noise_strength`` (it scales the constant AND any per-frame noise map the wrapper swaps
+  in) and the standard ``x @ W.T`` mapping layers (the inference network's lrelu layers multiply by ``W`` itself).
 """
 from __future__ import annotations
 
@@ -32,91 +33,126 @@ from .networks import stylegan2, stylegan3
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# rosinality -> ADA / inference layout (maua/GAN/load.py:18-127)
+# rosinality -> in-tree layout (maua/GAN/load.py:18-127)
 # ---------------------------------------------------------------------------------------------------------------------
-def rosinality_to_inference_state(state_dict, blur_scale=4.0):
-    """Key-for-key restatement of load_rosinality2ada's mapping for ``for_inference=True`` (:18-113): returns
-    (state_nv, max_res, num_map)."""
-    state_ros = state_dict["g_ema"]
-    state_nv = {}
-    nv_key = "bs.0"
-    if tuple(state_ros["input.input"].shape) != (1,):
-        state_nv[f"synthesis.{nv_key}.const"] = state_ros["input.input"].squeeze(0)
-    else:
-        raise NotImplementedError("rosinality checkpoints with a learned-affine input (no const) are not supported")
-    state_nv[f"synthesis.{nv_key}.conv1.noise_const"] = state_ros["noises.noise_0"].squeeze(0).squeeze(0)
-    state_nv[f"synthesis.{nv_key}.conv1.weight"] = state_ros["conv1.conv.weight"].squeeze(0)
-    state_nv[f"synthesis.{nv_key}.conv1.bias"] = state_ros["conv1.activate.bias"]
-    state_nv[f"synthesis.{nv_key}.conv1.affine.weight"] = state_ros["conv1.conv.modulation.weight"]
-    state_nv[f"synthesis.{nv_key}.conv1.affine.bias"] = state_ros["conv1.conv.modulation.bias"]
-    state_nv[f"synthesis.{nv_key}.torgb.weight"] = state_ros["to_rgb1.conv.weight"].squeeze(0)
-    state_nv[f"synthesis.{nv_key}.torgb.bias"] = state_ros["to_rgb1.bias"].squeeze(-1).squeeze(-1).squeeze(0)
-    state_nv[f"synthesis.{nv_key}.torgb.affine.weight"] = state_ros["to_rgb1.conv.modulation.weight"]
-    state_nv[f"synthesis.{nv_key}.torgb.affine.bias"] = state_ros["to_rgb1.conv.modulation.bias"]
-    state_nv[f"synthesis.{nv_key}.resample_filter"] = state_ros["convs.0.conv.blur.kernel"] / blur_scale
-    state_nv[f"synthesis.{nv_key}.conv1.resample_filter"] = state_ros["convs.0.conv.blur.kernel"] / blur_scale
+# The converter is a key map, stated as a table: (pattern of the rosinality key, target key(s), value transform).  In a
+# target, {b} is the block index and {c} the conv index the pattern's layer number n stands for (``convs.n`` is conv n % 2 of
+# block n // 2 + 1, ``to_rgbs.n`` belongs to block n + 1, ``noises.noise_n`` to conv (n - 1) % 2 of block (n - 1) // 2 + 1;
+# reference :61-112), {p} is the captured ``weight`` / ``bias``.
+def _drop_lead(v):
+    return v.squeeze(0)
 
-    max_res, num_map = 4, 1
-    for key, val in state_ros.items():
-        if key.startswith("style"):
-            _, num, weight_or_bias = key.split(".")
-            state_nv[f"mapping.fcs.{int(num) - 1}.{weight_or_bias}"] = val
-            num_map = max(num_map, int(num))
-        if key.startswith("noises"):
-            n = int(key.split("_")[1])
-            if n == 0:
+
+def _drop_lead2(v):
+    return v.squeeze(0).squeeze(0)
+
+
+def _rgb_bias(v):
+    return v.squeeze(-1).squeeze(-1).squeeze(0)
+
+
+def _keep(v):
+    return v
+
+
+_CONV_OF = lambda n: dict(b=n // 2 + 1, c=n % 2)          # noqa: E731
+_RGB_OF = lambda n: dict(b=n + 1, c=0)                     # noqa: E731
+_NOISE_OF = lambda n: dict(b=(n - 1) // 2 + 1, c=(n - 1) % 2) if n else dict(b=0, c=1)   # noqa: E731
+_FIRST = lambda n: dict(b=0, c=1)                          # noqa: E731
+
+_ROSINALITY_TABLE = [
+    # first block (4x4): constant input, one conv, one ToRGB
+    (r"input\.input", _FIRST, ["synthesis.bs.0.const"], _drop_lead),
+    (r"conv1\.conv\.weight", _FIRST, ["synthesis.bs.0.conv1.weight"], _drop_lead),
+    (r"conv1\.activate\.bias", _FIRST, ["synthesis.bs.0.conv1.bias"], _keep),
+    (r"conv1\.conv\.modulation\.(?P<p>weight|bias)", _FIRST, ["synthesis.bs.0.conv1.affine.{p}"], _keep),
+    (r"conv1\.noise\.weight", _FIRST, ["synthesis.bs.0.conv1.noise_strength"], _drop_lead),
+    (r"to_rgb1\.conv\.weight", _FIRST, ["synthesis.bs.0.torgb.weight"], _drop_lead),
+    (r"to_rgb1\.bias", _FIRST, ["synthesis.bs.0.torgb.bias"], _rgb_bias),
+    (r"to_rgb1\.conv\.modulation\.(?P<p>weight|bias)", _FIRST, ["synthesis.bs.0.torgb.affine.{p}"], _keep),
+    # mapping network, noise maps
+    (r"style\.(?P<n>\d+)\.(?P<p>weight|bias)", lambda n: dict(b=n - 1, c=0), ["mapping.fcs.{b}.{p}"], _keep),
+    (r"noises\.noise_(?P<n>\d+)", _NOISE_OF, ["synthesis.bs.{b}.conv{c}.noise_const"], _drop_lead2),
+    # the two convs of every later block
+    (r"convs\.(?P<n>\d+)\.conv\.weight", _CONV_OF, ["synthesis.bs.{b}.conv{c}.weight"], _drop_lead),
+    (r"convs\.(?P<n>\d+)\.activate\.bias", _CONV_OF, ["synthesis.bs.{b}.conv{c}.bias"], _keep),
+    (r"convs\.(?P<n>\d+)\.conv\.modulation\.(?P<p>weight|bias)", _CONV_OF, ["synthesis.bs.{b}.conv{c}.affine.{p}"], _keep),
+    (r"convs\.(?P<n>\d+)\.noise\.weight", _CONV_OF, ["synthesis.bs.{b}.conv{c}.noise_strength"], _drop_lead),
+    (r"convs\.(?P<n>\d+)\.conv\.blur\.kernel", _CONV_OF,
+     ["synthesis.bs.{b}.conv0.resample_filter", "synthesis.bs.{b}.conv1.resample_filter"], "blur"),
+    # ToRGB of every later block
+    (r"to_rgbs\.(?P<n>\d+)\.conv\.weight", _RGB_OF, ["synthesis.bs.{b}.torgb.weight"], _drop_lead),
+    (r"to_rgbs\.(?P<n>\d+)\.bias", _RGB_OF, ["synthesis.bs.{b}.torgb.bias"], _rgb_bias),
+    (r"to_rgbs\.(?P<n>\d+)\.conv\.modulation\.(?P<p>weight|bias)", _RGB_OF, ["synthesis.bs.{b}.torgb.affine.{p}"], _keep),
+    (r"to_rgbs\.(?P<n>\d+)\.upsample\.kernel", _RGB_OF, ["synthesis.bs.{b}.resample_filter"], "blur"),
+]
+_ROSINALITY_RULES = [(re.compile(pat), where, targets, fn) for pat, where, targets, fn in _ROSINALITY_TABLE]
+_STRICT_PREFIXES = ("convs.", "to_rgbs.")   # an unknown key under these aborts the conversion (reference :88,109)
+
+
+def rosinality_to_inference_state(state_dict, blur_scale=4.0):
+    """rosinality ``g_ema`` state dict -> (state in the in-tree layout incl. ``*.noise_strength`` entries, max_res,
+    num_map); the key map of load_rosinality2ada (:18-113)."""
+    source = state_dict["g_ema"]
+    if tuple(source["input.input"].shape) == (1,):
+        raise NotImplementedError("rosinality checkpoints with a learned-affine input (no const) are not supported")
+    out, max_res, num_map = {}, 4, 1
+    for key, val in source.items():
+        for pat, where, targets, fn in _ROSINALITY_RULES:
+            m = pat.fullmatch(key)
+            if m is None:
                 continue
-            state_nv[f"synthesis.bs.{(n - 1) // 2 + 1}.conv{(n - 1) % 2}.noise_const"] = val.squeeze(0).squeeze(0)
-        if key.startswith("convs"):
-            n = int(key.split(".")[1])
-            r = 2 ** (3 + n // 2)
-            nv_block = f"synthesis.bs.{(n // 2) + 1}"
-            ros_name = ".".join(key.split(".")[2:])
-            if ros_name == "conv.weight":
-                state_nv[f"{nv_block}.conv{n % 2}.weight"] = val.squeeze(0)
-            elif ros_name == "activate.bias":
-                state_nv[f"{nv_block}.conv{n % 2}.bias"] = val
-            elif ros_name == "conv.modulation.weight":
-                state_nv[f"{nv_block}.conv{n % 2}.affine.weight"] = val
-            elif ros_name == "conv.modulation.bias":
-                state_nv[f"{nv_block}.conv{n % 2}.affine.bias"] = val
-            elif ros_name == "noise.weight":
-                pass  # the inference layout has no noise_strength (:39,84)
-            elif ros_name == "conv.blur.kernel":
-                state_nv[f"{nv_block}.conv0.resample_filter"] = val / blur_scale
-                state_nv[f"{nv_block}.conv1.resample_filter"] = val / blur_scale
-            else:
+            groups = m.groupdict()
+            n = int(groups.get("n") or 0)
+            fields = dict(where(n), p=groups.get("p"))
+            value = val / blur_scale if fn == "blur" else fn(val)
+            for t in targets:
+                out[t.format(**fields)] = value
+            if key.startswith("style."):
+                num_map = max(num_map, n)
+            if key.startswith("convs."):
+                max_res = max(max_res, 2 ** (3 + n // 2))
+            break
+        else:
+            if key.startswith(_STRICT_PREFIXES):
                 raise Exception(f"Key {key} not recognized!")
-            max_res = max(max_res, r)
-        if key.startswith("to_rgbs"):
-            n = int(key.split(".")[1])
-            nv_block = f"synthesis.bs.{n + 1}"
-            ros_name = ".".join(key.split(".")[2:])
-            if ros_name == "conv.weight":
-                state_nv[f"{nv_block}.torgb.weight"] = val.squeeze(0)
-            elif ros_name == "bias":
-                state_nv[f"{nv_block}.torgb.bias"] = val.squeeze(-1).squeeze(-1).squeeze(0)
-            elif ros_name == "conv.modulation.weight":
-                state_nv[f"{nv_block}.torgb.affine.weight"] = val
-            elif ros_name == "conv.modulation.bias":
-                state_nv[f"{nv_block}.torgb.affine.bias"] = val
-            elif ros_name == "upsample.kernel":
-                state_nv[f"{nv_block}.resample_filter"] = val / blur_scale
-            else:
-                raise Exception(f"Key {key} not recognized!")
-    state_nv["mapping.w_avg"] = state_dict["latent_avg"] if "latent_avg" in state_dict else torch.zeros(512)
-    return state_nv, max_res, num_map
+    # the 4x4 block borrows the first blur kernel (:46-47)
+    first_blur = source["convs.0.conv.blur.kernel"] / blur_scale
+    out["synthesis.bs.0.resample_filter"] = first_blur
+    out["synthesis.bs.0.conv1.resample_filter"] = first_blur
+    out["mapping.w_avg"] = state_dict["latent_avg"] if "latent_avg" in state_dict else torch.zeros(512)
+    return out, max_res, num_map
+
+
+def _take_noise_strengths(state):
+    """Split the ``*.noise_strength`` entries off a state dict (they are attributes of the layers here, not buffers)."""
+    return {k[: -len(".noise_strength")]: float(state.pop(k)) for k in [k for k in state if k.endswith(".noise_strength")]}
+
+
+def _finish_sg2(G, strengths, standard_fc):
+    """Training-layout semantics on the in-tree network: per-layer noise strength (the training network scales the noise map,
+    constant or supplied per frame, by it; the inference network of the reference adds it unscaled, inference/ops.py:184) and
+    the standard ``x @ W.T`` mapping layers (the inference network's lrelu branch multiplies by ``W`` itself,
+    inference/stylegan2.py:57)."""
+    for prefix, value in strengths.items():
+        G.get_submodule(prefix).noise_strength = value
+    if standard_fc:
+        for fc in G.mapping.fcs:
+            fc.standard_matmul = True
+    return G
 
 
 def load_rosinality2ada(path, blur_scale=4.0, for_inference=False):
-    """maua/GAN/load.py:18-127.  Both values of for_inference give the inference-layout network (the only StyleGAN2
-    network of this build)."""
+    """maua/GAN/load.py:18-127.  ``for_inference=True`` reproduces the reference's inference network (noise added unscaled,
+    mapping layers with its transposed-weight quirk); ``for_inference=False`` gives the semantics of the training network the
+    reference instantiates in that case (noise strength applied, standard mapping layers) on the same in-tree network."""
     state_dict = torch.load(path, map_location="cpu", weights_only=False)
     state_nv, max_res, num_map = rosinality_to_inference_state(state_dict, blur_scale)
+    strengths = _take_noise_strengths(state_nv)
     z_dim = w_dim = state_nv["mapping.fcs.0.weight"].shape[1] if "mapping.fcs.0.weight" in state_nv else 512
     G = stylegan2.Generator(z_dim, 0, w_dim, max_res, 3, mapping_kwargs=dict(num_layers=num_map), **_sg2_channels(state_nv))
     G.load_state_dict(state_nv)
-    return G
+    return G if for_inference else _finish_sg2(G, strengths, standard_fc=True)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -137,8 +173,8 @@ def _sg2_channels(state):
 
 
 def nvidia_sg2_to_inference_state(state):
-    """NVIDIA training layout -> in-tree inference layout: b{res} -> bs.{log2(res) - 2}, mapping.fc{i} -> mapping.fcs.{i},
-    noise_const * noise_strength folded (the inference net adds noise unscaled, inference/ops.py:184)."""
+    """NVIDIA training layout -> in-tree layout: b{res} -> bs.{log2(res) - 2}, mapping.fc{i} -> mapping.fcs.{i}; the
+    ``noise_strength`` entries keep their (renamed) keys and are split off by the caller."""
     out = {}
     for k, v in state.items():
         m = re.fullmatch(r"synthesis\.b(\d+)\.(.*)", k)
@@ -148,10 +184,6 @@ def nvidia_sg2_to_inference_state(state):
         if m:
             k = f"mapping.fcs.{m.group(1)}.{m.group(2)}"
         out[k] = v
-    for k in [k for k in out if k.endswith(".noise_strength")]:
-        strength = out.pop(k)
-        nc = k[: -len("noise_strength")] + "noise_const"
-        out[nc] = out[nc] * strength
     return out
 
 
@@ -186,8 +218,10 @@ def generator_from_state(state):
                                 channel_base=found, **kw)
         G.load_state_dict(state)
         return G
-    if any(re.match(r"synthesis\.b\d+\.", k) for k in state):
+    training_layout = any(re.match(r"synthesis\.b\d+\.", k) for k in state)
+    if training_layout:
         state = nvidia_sg2_to_inference_state(state)
+    strengths = _take_noise_strengths(state)
     if "synthesis.bs.0.const" not in state:
         raise ValueError("not a StyleGAN2 / StyleGAN3 generator state dict")
     n_blocks = len({k.split(".")[2] for k in state if k.startswith("synthesis.bs.")})
@@ -201,7 +235,7 @@ def generator_from_state(state):
         z_dim -= state["mapping.embed.weight"].shape[0]
     G = stylegan2.Generator(z_dim, c_dim, w_dim, res, img_channels, mapping_kwargs=dict(num_layers=n_map), **_sg2_channels(state))
     G.load_state_dict(state)
-    return G
+    return _finish_sg2(G, strengths, standard_fc=training_layout)
 
 
 def load_nvidia_pt(path, for_inference=False, **unused):
@@ -225,17 +259,31 @@ def _reconstruct_persistent_obj(meta):
 
 
 class _PersistenceUnpickler(pickle.Unpickler):
-    """legacy._LegacyUnpickler (nvGAN legacy.py) without dnnlib: persistent objects become _Bag trees; only torch /
-    numpy / collections / builtins globals needed to rebuild tensors are allowed."""
+    """legacy._LegacyUnpickler (nvGAN legacy.py) without dnnlib: persistent objects become _Bag trees.  Only the exact
+    globals a tensor / array / OrderedDict needs to rebuild itself resolve; anything else (``builtins.eval``,
+    ``torch.load``, ``numpy.load``, ``os.system`` ...) is refused, so a crafted pickle cannot run code through this loader."""
 
-    _ALLOWED_PREFIXES = ("torch", "numpy", "collections", "builtins", "_codecs")
+    _ALLOWED = {
+        ("collections", "OrderedDict"),
+        ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"),
+        ("torch._utils", "_rebuild_parameter_with_state"), ("torch._tensor", "_rebuild_from_type_v2"),
+        ("torch.storage", "_load_from_bytes"), ("torch", "Size"), ("torch", "device"), ("torch", "Tensor"),
+        ("torch.nn.parameter", "Parameter"),
+        ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+        ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+        ("numpy", "ndarray"), ("numpy", "dtype"), ("_codecs", "encode"),
+        ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"), ("builtins", "frozenset"),
+        ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"),
+        ("builtins", "complex"), ("builtins", "slice"), ("builtins", "range"), ("builtins", "bytearray"),
+    }
+    _ALLOWED_TORCH_NAMES = re.compile(r"(\w+Storage|float\d+|bfloat16|half|double|u?int\d+|long|short|bool|complex\d+)")
 
     def find_class(self, module, name):
         if module == "torch_utils.persistence" and name == "_reconstruct_persistent_obj":
             return _reconstruct_persistent_obj
         if module == "dnnlib.util" and name == "EasyDict":
             return dict
-        if module.split(".")[0] in self._ALLOWED_PREFIXES:
+        if (module, name) in self._ALLOWED or (module == "torch" and self._ALLOWED_TORCH_NAMES.fullmatch(name)):
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"global '{module}.{name}' is not allowed in a generator pickle")
 

@@ -23,6 +23,10 @@ class NativeNet(torch.nn.Module):
         """True for tensors that must be re-uploaded on every forward (their identity does not reveal a change)."""
         return False
 
+    def _prepare_param(self, name, d):
+        """Last host-side touch of a float32 device copy before it is handed to mb_net_set_param."""
+        return d
+
     # ---- library handle management ----------------------------------------------------
     def _handle(self):
         if self._net is None:
@@ -52,15 +56,16 @@ class NativeNet(torch.nn.Module):
     _POKED = ("input.affine.bias", "input.affine.weight", "input.transform")
 
     def _param_key(self, name, t):
-        """Identity of a parameter's current value: storage pointer + autograd version counter.  Inference-mode
-        tensors carry no version counter; for those the three tensors the wrapper pokes are fingerprinted."""
+        """Identity of a parameter's current value: storage pointer + autograd version counter (inference-mode tensors
+        carry none); the three tensors the wrapper pokes are compared by value."""
         try:
             version = t._version
         except RuntimeError:
             version = None
-            if name in self._POKED:
-                d = t.detach().double()
-                version = (float(d.sum()), float((d * d).sum()))
+        if name in self._POKED:
+            # edits through ``.data`` (the reference's stabilisation trick, wrappers/stylegan3.py:54-55) do not bump the
+            # version counter either: these three tiny tensors are always fingerprinted by value
+            version = (version, tuple(t.detach().double().flatten().tolist()))
         return (t.data_ptr(), version, str(t.device), tuple(t.shape))
 
     def _sync_params(self, device):
@@ -76,7 +81,7 @@ class NativeNet(torch.nn.Module):
             volatile = self._is_volatile(name, t)
             if not volatile and self._uploaded.get(name) == key:
                 continue
-            d = t.detach().to(device=device, dtype=torch.float32).contiguous()
+            d = self._prepare_param(name, t.detach().to(device=device, dtype=torch.float32)).contiguous()
             keep.append(d)
             shape = (C.c_int64 * max(d.ndim, 1))(*d.shape)
             _lib.check(lib.mb_net_set_param(net, name.encode(), _lib.ptr(d), shape, d.ndim, _lib.stream_ptr()))

@@ -36,6 +36,7 @@ class FullyConnectedLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
         self.weight_gain = lr_multiplier / sqrt(in_features)
         self.bias_gain = lr_multiplier
+        self.standard_matmul = False
 
     def forward(self, x):
         # Off the render hot path (mapping network: once per key latent); plain library GEMM.
@@ -45,7 +46,9 @@ class FullyConnectedLayer(torch.nn.Module):
             b = b * self.bias_gain
         if self.activation == "linear":
             return torch.nn.functional.linear(x, w, b)
-        y = torch.nn.functional.linear(x, w.T, None)
+        # the reference's inference network multiplies by w itself here (:57, square layers only); checkpoints in the
+        # training layout were trained with x @ w.T and set standard_matmul (GAN/load.py::_finish_sg2)
+        y = torch.nn.functional.linear(x, w if self.standard_matmul else w.T, None)
         if b is not None:
             y = y + b.to(y.dtype)
         return torch.nn.functional.leaky_relu(y, 0.2) * sqrt(2)
@@ -103,6 +106,9 @@ class SynthesisLayer(torch.nn.Module):
         self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
         self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]))
         self.register_buffer("noise_const", torch.randn([resolution, resolution]))
+        # scale of the noise map (constant or swapped in per frame): 1 = the reference's inference network, which adds it
+        # unscaled (inference/ops.py:184); the loaders set the trained strength for training-layout checkpoints
+        self.noise_strength = 1.0
         self.noise_adjusted = False
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
@@ -176,6 +182,20 @@ class SynthesisNetwork(NativeNet):
     def _is_volatile(self, name, t):
         # per-frame noise maps are swapped in on every call by the wrapper (wrappers/stylegan2.py:83-96): always upload
         return name.endswith("noise_const") and t.ndim != 2
+
+    def _noise_strength(self, name):
+        return float(getattr(self.get_submodule(name.rsplit(".", 1)[0]), "noise_strength", 1.0))
+
+    def _param_key(self, name, t):
+        key = super()._param_key(name, t)
+        return key + (self._noise_strength(name),) if name.endswith("noise_const") else key
+
+    def _prepare_param(self, name, d):
+        if name.endswith("noise_const"):
+            strength = self._noise_strength(name)
+            if strength != 1.0:
+                d = d * strength
+        return d
 
     def layer_resolution(self, layer):
         """Resolution of the wrapper's layer_names[layer] (maua/GAN/wrappers/stylegan2.py:48-51: entries 0 and 1 are

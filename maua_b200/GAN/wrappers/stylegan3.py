@@ -54,16 +54,18 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
     ) -> torch.Tensor:
         # out_fmt is an extension of the reference signature: "f32_01" fuses render()'s (x+1)/2 .clamp(0,1) into the
         # last kernel, "u8" also the uint8 conversion of tensor2bytes; the default is the reference's raw ~[-1,1] output
-        batched = (
-            torch.is_tensor(translation) and torch.is_tensor(rotation) and translation.ndim == 2 and translation.shape[0] > 1
-        )
+        # a [B,2] translation with a tensor rotation is one transform per frame, for B == 1 too (the last batch of a render
+        # whose length is not a multiple of the batch size; MemMap's batch size of one)
+        batched = torch.is_tensor(translation) and torch.is_tensor(rotation) and translation.ndim == 2
         if batched:
-            # one transform per frame (not expressible in the reference: make_transform_mat squeezes to one matrix)
+            # (not expressible in the reference for B > 1: make_transform_mat squeezes to one matrix)
             return self.G_synth.forward(latents, out_fmt=out_fmt, transforms=make_transform_mats(translation, rotation))
-        if translation == 0 and rotation == 0:
+        scalar_zero = lambda v: v is not None and (not torch.is_tensor(v) or v.numel() == 1) and float(v) == 0.0  # noqa: E731
+        if scalar_zero(translation) and scalar_zero(rotation):
             # stabilization trick by @RiversHaveWings and @nshepperd1
-            self.G_synth.input.affine.bias.data.add_(self.avg_shift)
-            self.G_synth.input.affine.weight.data.zero_()
+            with torch.no_grad():
+                self.G_synth.input.affine.bias.add_(self.avg_shift)
+                self.G_synth.input.affine.weight.zero_()
         elif not (translation is None or rotation is None):
             self.G_synth.input.transform.copy_(make_transform_mat(translation, rotation))
         return self.G_synth.forward(latents, out_fmt=out_fmt)

@@ -11,7 +11,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libmaua_b200.so")
+# MAUA_B200_LIB: load / build another copy of the library (A/B runs of kernel variants built with extra -D flags)
+LIB_PATH = os.environ.get("MAUA_B200_LIB") or os.path.join(LIB_DIR, "libmaua_b200.so")
 SOURCES = ["net.cu", "conv_tc.cu", "flrelu.cu", "flrelu_sep.cu", "flrelu_mma.cu", "sg3_misc.cu", "feature_resize.cu", "sg2.cu", "audio.cu", "chroma.cu", "signal_ops.cu", "sequencers.cu", "image_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -32,16 +33,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
     """Compile every CUDA source into maua_b200/lib/libmaua_b200.so (sm_100a, -lineinfo)."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libmaua_b200.so")
-    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
@@ -52,4 +53,6 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force=True, verbose=True))
+    import sys
+
+    print(build(force=True, verbose="-v" in sys.argv[1:], extra_flags=[a for a in sys.argv[1:] if a.startswith("-D")]))

@@ -42,8 +42,12 @@ struct SC {
     static constexpr int BOXROWS = (UP == 2) ? 16 : 8;
     static constexpr int BOXBYTES = BOXROWS * kXP * 2;
     static constexpr int NRING = (UP == 2) ? 3 : 4;  // boxes per warp: the fetch runs two / three output blocks ahead
-    static constexpr int NSB = 6;                    // staging buffers
-    static constexpr int LAG = 3;                    // the write-out runs this many blocks behind the staging
+#ifndef MB_FL_NSB
+#define MB_FL_NSB 6
+#define MB_FL_LAG 3
+#endif
+    static constexpr int NSB = MB_FL_NSB;            // staging buffers
+    static constexpr int LAG = MB_FL_LAG;            // the write-out runs this many blocks behind the staging
     static constexpr int RING_BYTES = kCG * NRING * BOXBYTES;
     static constexpr int SMEM = RING_BYTES + NSB * kBufBytes + kSTail + 128;
 };
@@ -96,20 +100,31 @@ __device__ __forceinline__ void sbar_arrive(uint32_t bar) { asm volatile("mbarri
 __device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin (a broken pipeline traps instead of hanging the GPU box).
+// Wait for a phase.  The first probe is the fast path; a waiting warp then parks inside try_wait (suspend-time hint) instead
+// of spinning through the issue port its three neighbours on the scheduler need (the r2a capture showed ~12 spins x 6
+// instructions per block on the staging-buffer barrier: 12 % of all issued instructions).  Bounded: a broken pipeline
+// traps instead of hanging the GPU box.
 __device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
     uint32_t spins = 0;
     for (;;) {
-        uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok)
-            : "r"(bar), "r"(parity)
+            : "r"(bar), "r"(parity), "r"(20000u)
             : "memory");
         if (ok) return;
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 20)) __trap();
     }
 }
 __device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
@@ -250,8 +265,10 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         const int chl = 4 * ((lane & 7) >> 1) + (lane & 1) + 2 * ((lane >> 3) & 1);
         const bool real = chl < dv;
         const uint32_t buf = stg + w_sb * kBufBytes;
-        uint8_t* base = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(d0.y) << 32) | d0.x) + 8 * (lane & 3) +
-                        static_cast<long long>(lane >> 2) * p.Cp_out * 2;
+        // byte offsets inside the frame fit 32 bits (a 1044^2 x 96-channel map is 209 MB): one 64-bit add per store
+        uint8_t* base = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(d0.y) << 32) | d0.x);
+        const uint32_t pix = static_cast<uint32_t>(p.Cp_out) * 2u;
+        const uint32_t lane_off = 8u * (lane & 3) + static_cast<uint32_t>(lane >> 2) * pix;
         const int ox = dox0 + (lane >> 2);
         for (int t = 0; t < dnsc; ++t) {
             const int r = warp * dnsc + t;
@@ -259,13 +276,13 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             const int oy = static_cast<int>(doyb) + q * dsegrows + yr;
             if (oy < p.Hout) {   // warp-uniform
                 const uint32_t a = real ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a;
-                uint8_t* row = base + static_cast<long long>(oy) * p.Wout * p.Cp_out * 2;
+                const uint32_t off = static_cast<uint32_t>(oy) * static_cast<uint32_t>(p.Wout) * pix + lane_off;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r4[4];
                     ldsm_x4_trans(real ? a + h * 32 : a, r4);
-                    if (ox + h * 16 < p.Wout) stg64(row + static_cast<long long>(h * 16) * p.Cp_out * 2, r4[0], r4[1]);
-                    if (ox + h * 16 + 8 < p.Wout) stg64(row + static_cast<long long>(h * 16 + 8) * p.Cp_out * 2, r4[2], r4[3]);
+                    if (ox + h * 16 < p.Wout) stg64(base + (off + (h * 16) * pix), r4[0], r4[1]);
+                    if (ox + h * 16 + 8 < p.Wout) stg64(base + (off + (h * 16 + 8) * pix), r4[2], r4[3]);
                 }
             }
         }

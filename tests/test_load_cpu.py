@@ -97,10 +97,49 @@ def test_nvidia_pt_stylegan2_training_layout(tmp_path):
     torch.save({"G_ema": to_nvidia_sg2(G)}, path)
     G2 = L.load_network(str(path))
     assert isinstance(G2, stylegan2.Generator)
-    sa, sb = G.state_dict(), G2.state_dict()
-    for k in sa:
-        want = sa[k] * 0.5 if k.endswith("noise_const") else sa[k]   # noise_strength folded into noise_const
-        assert torch.allclose(want, sb[k]), k
+    assert_same_state(G, G2)
+    # what the training network does differently stays with the loaded generator: the trained noise strength of every layer
+    # (it scales the constant and any per-frame map the wrapper swaps in) ...
+    layers = [m for m in G2.synthesis.modules() if isinstance(m, stylegan2.SynthesisLayer)]
+    assert layers and all(m.noise_strength == 0.5 for m in layers)
+    name = "bs.1.conv0.noise_const"
+    nc = G2.synthesis.get_buffer(name)
+    assert torch.equal(G2.synthesis._prepare_param(name, nc.clone()), nc * 0.5)
+    assert G2.synthesis._param_key(name, nc)[-1] == 0.5
+    # ... and the standard x @ W.T mapping layers: the checkpoint's mapping must give what plain F.linear + lrelu gives
+    z = torch.randn(4, 512)
+    x = z * (z.square().mean(1, keepdim=True) + 1e-8).rsqrt()
+    sd = to_nvidia_sg2(G)
+    for i in range(3):
+        w, b = sd[f"mapping.fc{i}.weight"], sd[f"mapping.fc{i}.bias"]
+        x = torch.nn.functional.leaky_relu(torch.nn.functional.linear(x, w * (0.01 / 512 ** 0.5), b * 0.01), 0.2) * 2 ** 0.5
+    got = G2.mapping(z)
+    assert torch.allclose(got[:, 0], x, atol=1e-5), float((got[:, 0] - x).abs().max())
+    assert not torch.allclose(G.mapping(z)[:, 0], x, atol=1e-3)   # the inference-layout quirk multiplies by W itself
+
+
+def test_rosinality_training_semantics(tmp_path):
+    """for_inference=False: the reference builds the training network, which applies ``noise.weight`` and standard FCs."""
+    G = small_sg2(5)
+    ck = to_rosinality(G)
+    for k in ck["g_ema"]:
+        if k.endswith("noise.weight"):
+            ck["g_ema"][k] = torch.full((1,), 0.25)
+    path = tmp_path / "ros_train.pt"
+    torch.save(ck, path)
+    G_train = L.load_rosinality2ada(str(path), for_inference=False)
+    G_inf = L.load_rosinality2ada(str(path), for_inference=True)
+    assert_same_state(G_train, G_inf)
+    assert all(fc.standard_matmul for fc in G_train.mapping.fcs) and not any(fc.standard_matmul for fc in G_inf.mapping.fcs)
+    assert G_train.synthesis.bs[0].conv1.noise_strength == 0.25 and G_train.synthesis.bs[2].conv0.noise_strength == 0.25
+    assert G_inf.synthesis.bs[0].conv1.noise_strength == 1.0
+
+
+def test_rosinality_unknown_key_aborts(tmp_path):
+    ck = to_rosinality(small_sg2(6))
+    ck["g_ema"]["convs.0.conv.surprise"] = torch.zeros(1)
+    with pytest.raises(Exception, match="not recognized"):
+        L.rosinality_to_inference_state(ck)
 
 
 @pytest.mark.parametrize("config", ["T", "R"])
@@ -169,6 +208,24 @@ def test_unpickler_refuses_foreign_globals(tmp_path):
         L.load_nvidia(str(path))
     with pytest.raises(Exception, match="None of the converters succeeded"):
         L.load_network(str(path))
+
+
+class _Evil:
+    def __reduce__(self):
+        return (eval, ("{'G_ema': 'pwned'}",))
+
+
+def test_unpickler_refuses_code_execution(tmp_path):
+    """A pickle whose reduce calls eval / torch.load / numpy.load must not get those globals (they sit under the module
+    prefixes a tensor pickle needs, so prefixes are not enough: the loader whitelists exact names)."""
+    path = tmp_path / "eval.pkl"
+    with open(path, "wb") as f:
+        pickle.dump(_Evil(), f)
+    with pytest.raises(pickle.UnpicklingError, match="builtins.eval"):
+        L.load_nvidia(str(path))
+    for module, name in [("torch", "load"), ("numpy", "load"), ("torch.hub", "load"), ("os", "system"), ("builtins", "exec")]:
+        with pytest.raises(pickle.UnpicklingError):
+            L._PersistenceUnpickler(__import__("io").BytesIO(b"")).find_class(module, name)
 
 
 def test_wrapper_loads_a_model_file(tmp_path):

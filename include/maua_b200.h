@@ -290,6 +290,15 @@ int mb_chroma_cens_post(const float* chroma_raw, int n_chroma, int T, const floa
 int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal, mb_stream stream);
 int mb_normalize(const float* x, float* y, int64_t n, float eps, float* scratch2 /* device float[2] */, mb_stream stream);
 int mb_resample_linear(const float* x, float* y, int T, int S, int C, mb_stream stream);
+/* scipy.signal.sosfilt(sos, x) as the reference's low_pass / high_pass / band_pass call it (audioreactive/audio.py:96-110):
+ * cascade of second-order sections [b0 b1 b2 a0 a1 a2] (HOST array, n_sections x 6) over a device float64 signal, zero
+ * initial state, double precision.  Chunk-parallel (zero-state pass, state chain through A^256, apply pass); y may alias x.
+ * scratch: device double[4 * ceil(n / 256)]. */
+int mb_sosfilt(const double* x, double* y, int64_t n, const double* sos_host, int n_sections, double* scratch, mb_stream stream);
+/* quantile(tensor, q) of selfsupervised/features/efficient_quantile/__init__.py:6-7 (the reference's compiled
+ * efficient_quantile.cpp:86-208, method 3 "mid point", NaNs ignored, q taken as float32): device float32 [n] -> out[0].
+ * Radix select on the device; n == 0 or all-NaN gives NaN. */
+int mb_quantile_mid(const float* x, int64_t n, float q, float* out /* device float[1] */, mb_stream stream);
 int mb_multi_weighted(const float* latents /*[K,D]*/, const float* envelopes /*[T,A]*/, float* out /*[T,D]*/, int T, int A,
                       int K, int D, mb_stream stream);
 int mb_single_weighted(const float* low /*[D]*/, const float* high /*[D]*/, const float* envelope /*[T]*/, float* out /*[T,D]*/,

@@ -87,6 +87,8 @@ _SIGNATURES = {
     "mb_gaussian_filter": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, _P]),
     "mb_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P]),
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "mb_quantile_mid": (C.c_int, [_P, C.c_int64, C.c_float, _P, _P]),
+    "mb_sosfilt": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P]),
     "mb_multi_weighted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mb_single_weighted": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),
     "mb_slerp_rows": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),

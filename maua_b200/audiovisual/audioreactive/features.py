@@ -133,7 +133,7 @@ def onsets_rms(audio, sr):
 
 
 # ---- spectral descriptors of the torch-native feature list (features/audio.py:59-133) ---------------------------------
-def _spectrogram(y, sr, want_mag, want_mel):
+def _spectrogram(y, sr, want_mag, want_mel, mel_fmax=None):
     """Device magnitude spectrogram [T,1025] and / or mel power spectrogram [T,128] (frame-major)."""
     if not y.is_cuda:
         raise RuntimeError("maua_b200 audio features need a CUDA tensor (no CPU fallback)")
@@ -147,7 +147,7 @@ def _spectrogram(y, sr, want_mag, want_mel):
     with torch.cuda.device(dev):
         mag = torch.empty(T, N_FFT // 2 + 1, device=dev) if want_mag else None
         mel = torch.empty(T, N_MELS, device=dev) if want_mel else None
-        fb = mel_filterbank(sr, fmax=None).to(dev) if want_mel else None
+        fb = mel_filterbank(sr, fmax=mel_fmax).to(dev) if want_mel else None
         nbytes = lib.mb_audio_workspace_bytes(n)
         ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
         off = (-ws.data_ptr()) % 256

@@ -36,6 +36,39 @@ def normalize(array):
     return _normalize(array, eps=1e-8)
 
 
+def quantile(tensor, q):
+    """features/efficient_quantile/__init__.py:6-7: mid-point quantile of the flattened tensor (NaNs ignored, q rounded to
+    float32 as the reference's FloatTensor([q]) does) -> 0-d tensor.  The reference copies to the host and partially sorts
+    there; here a radix select on the device (csrc/signal_ops.cu::quantile_mid_kernel)."""
+    x = _cuda32(tensor, "tensor").flatten().contiguous()
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().mb_quantile_mid(_lib.ptr(x), x.numel(), float(q), _lib.ptr(out), _lib.stream_ptr()))
+    return out[0].to(tensor.dtype)
+
+
+def standardize(array):
+    """features/processing.py:58-61: clamp to the inter-quartile range (+1e-10 on the upper bound), then normalize."""
+    array = _cuda32(array, "array")
+    return normalize(torch.clamp(array, quantile(array, 0.25), quantile(array, 0.75) + 1e-10))
+
+
+def spectral_flux(spec):
+    """features/processing.py:88-89: forward difference along time, last row against zero."""
+    spec = _cuda32(spec, "spec")
+    return torch.diff(spec, dim=0, append=torch.zeros((1, spec.shape[1]), device=spec.device))
+
+
+def onset_envelope(flux):
+    """features/processing.py:93-98: half-wave rectified flux summed over bins, clamped to its 2.5 % .. 97.5 % quantiles,
+    shifted and scaled to [0, 1]."""
+    flux = _cuda32(flux, "flux")
+    u = torch.sum(0.5 * (flux + torch.abs(flux)), dim=1)
+    u = torch.clamp(u, quantile(u, 0.025), quantile(u, 0.975))
+    u = u - u.min()
+    return u / u.max()
+
+
 def salience_weighted(envelope, short_sigma=5, long_sigma=80):
     """mir.py:13-21: (gaussian(short) / gaussian(long))^2 * envelope, reflect padding -> [T, 1]."""
     env = _cuda32(envelope, "envelope")
@@ -113,6 +146,42 @@ def tonnetz(y, sr, chroma_fn=None):
     with torch.cuda.device(chroma.device):  # out[T, 6] = frames[T, 12] @ phi[12, 6]: the mixing kernel of the noise sequencers
         _lib.check(_lib.load().mb_noise_mix(_lib.ptr(phi), _lib.ptr(frames), frames.shape[0], n, 6, 0, _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+def plp(y, sr, hop_length=1024, win_length=1024, tempo_min=60, tempo_max=180):
+    """Predominant local pulse (features/rosa/beat.py:41-75) -> [T] in [0, 1].  The mel power spectrogram comes from the fused
+    STFT kernel; the tempogram is a Fourier transform over a [T] envelope with hop 1 (T x 513 bins, once per track): torch's
+    device stft / istft, as in the reference."""
+    from .features import _spectrogram
+
+    if hop_length != 1024:
+        raise NotImplementedError("plp: the device STFT is built for hop_length = 1024 (one hop per video frame)")
+    mel = _spectrogram(y, sr, False, True, mel_fmax=11025.0)[1]                       # [T, 128] power
+    s = 10.0 * torch.log10(torch.clamp(mel.t(), min=1e-10))
+    s = torch.maximum(s, s.max() - 80.0)
+    env = torch.clamp(s[:, 1:] - s[:, :-1], min=0).median(dim=0).values              # onset_strength, median over the bands
+    env = torch.nn.functional.pad(env, (2, 0))[: s.shape[1]]
+    n = min(len(env), win_length)
+    win = torch.hann_window(n, device=env.device)
+    ft = torch.stft(env, n_fft=n, hop_length=1, center=True, window=win, pad_mode="reflect", return_complex=True)
+    freqs = torch.linspace(0, float(sr * 60 / float(hop_length)) / 2, int(1 + n // 2), device=env.device)
+    if tempo_min is not None:
+        ft[freqs < tempo_min] = 0
+    if tempo_max is not None:
+        ft[freqs > tempo_max] = 0
+    mag = torch.log1p(1e6 * torch.abs(ft))
+    ft[mag < mag.max(dim=0, keepdim=True).values] = 0
+    ft = ft / (torch.finfo(ft.dtype).tiny ** 0.5 + torch.abs(ft.abs().max(dim=0, keepdim=True).values))
+    pulse = torch.istft(ft, n_fft=n, hop_length=1, center=True, window=win, length=len(env))
+    pulse = torch.clamp(pulse, torch.zeros((), device=pulse.device), pulse.max())
+    return normalize(pulse)
+
+
+def pulse(audio, sr):
+    """features/audio.py:67-68: plp(percussive(audio), sr) -> [T, 1]."""
+    from .features import percussive
+
+    return plp(percussive(audio), sr).unsqueeze(-1)
 
 
 def spline_loop_latents(y, size, n_loops=1):

@@ -2,23 +2,7 @@
 import torch
 
 
-def load_audio(audio_file, offset=0, duration=-1):
-    """(audio float32 [N] mono, sr, duration_s) -- audioreactive/audio.py:15-48 without the joblib cache.
-    WAV files through the standard library (this image has no ffmpeg / torchaudio backend for mp3)."""
-    import wave
-
-    import numpy as np
-
-    with wave.open(audio_file, "rb") as w:
-        sr, ch, width, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        raw = w.readframes(n)
-    if width != 2:
-        raise NotImplementedError("load_audio: 16-bit PCM WAV only")
-    a = np.frombuffer(raw, dtype="<i2").astype(np.float32).reshape(-1, ch).mean(axis=1) / 32768.0
-    start = int(offset * sr)
-    end = len(a) if duration is None or duration < 0 else min(len(a), start + int(duration * sr))
-    a = a[start:end]
-    return torch.from_numpy(a.copy()), sr, len(a) / sr
+from ...audioreactive.audio import load_audio  # noqa: E402  (ar.load_audio, audioreactive/audio.py:15-48)
 
 
 class MauaPatch:

@@ -162,6 +162,137 @@ int grid1d(long long total) {
     return g < 1 ? 1 : static_cast<int>(g);
 }
 
+
+// ---- midpoint quantile (the reference's compiled efficient_quantile behind features/efficient_quantile/__init__.py:6-7) ----
+// quantile(t, q) = method 3 of efficient_quantile.cpp:86-208 called with the quantile as a FLOAT32 tensor and NaNs dropped:
+//   qs = double(float(q));  qm = qs * (size - 1);  ql = trunc(qm);  qu = ceil(qm);
+//   out = float( ql == qu ? v[ql] : v[qu] - (v[qu] - v[ql]) * 0.5 )      (torch::lerp in double, weight 0.5)
+// with v the ascending order statistics.  The reference partially sorts on the host (std::nth_element after a device ->
+// host copy); here the two order statistics come from a most-significant-byte-first radix SELECT over order-preserving
+// 32-bit keys: four 256-bin histogram passes per rank, no sort, the data never leaves the device.  One CTA: the arrays
+// of this path are envelopes of a few thousand frames.
+__device__ __forceinline__ uint32_t order_key(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+// key of the element of rank r (0-based, NaNs excluded); all threads of the CTA call it and receive the result
+__device__ uint32_t radix_select(const float* __restrict__ x, long long n, long long r, unsigned int* hist, unsigned int* sh) {
+    uint32_t prefix = 0, mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const int shift = 8 * pass;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            const float v = x[i];
+            if (v != v) continue;
+            const uint32_t k = order_key(v);
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            long long acc = 0;
+            int b = 0;
+            for (; b < 255; ++b) {
+                if (acc + hist[b] > r) break;
+                acc += hist[b];
+            }
+            sh[0] = static_cast<unsigned int>(b);
+            sh[1] = static_cast<unsigned int>(acc);          // elements below the chosen bin (fits: <= n of one CTA pass)
+            sh[2] = static_cast<unsigned int>(acc >> 32);
+        }
+        __syncthreads();
+        prefix |= sh[0] << shift;
+        mask |= 255u << shift;
+        r -= static_cast<long long>(sh[1]) | (static_cast<long long>(sh[2]) << 32);
+        __syncthreads();
+    }
+    return prefix;
+}
+__global__ void __launch_bounds__(1024) quantile_mid_kernel(const float* __restrict__ x, long long n, float q, float* __restrict__ out) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned int sh[4];
+    __shared__ unsigned long long cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) mine += (x[i] == x[i]) ? 1u : 0u;
+    for (int s = 16; s > 0; s >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&cnt, mine);
+    __syncthreads();
+    const long long size = static_cast<long long>(cnt);
+    if (size == 0) {
+        if (threadIdx.x == 0) out[0] = __int_as_float(0x7fc00000);
+        return;
+    }
+    const double qm = static_cast<double>(q) * static_cast<double>(size - 1);
+    const long long ql = static_cast<long long>(qm), qu = static_cast<long long>(ceil(qm));
+    const double lo = static_cast<double>(key_value(radix_select(x, n, ql, hist, sh)));
+    double res = lo;
+    if (qu > ql) {
+        const double hi = static_cast<double>(key_value(radix_select(x, n, qu, hist, sh)));
+        res = hi - (hi - lo) * 0.5;
+    }
+    if (threadIdx.x == 0) out[0] = static_cast<float>(res);
+}
+
+// ---- cascaded second-order sections (the reference's low_pass / high_pass / band_pass: scipy.signal.sosfilt of a
+// Butterworth design, maua/audiovisual/audioreactive/audio.py:96-110) -------------------------------------------------
+// One section in transposed direct form II (what scipy's _sosfilt runs):  y = b0 x + z0;  z0' = b1 x - a1 y + z1;
+// z1' = b2 x - a2 y.  The state is linear in (z, x):  z' = A z + B x  with  A = [[-a1, 1], [-a2, 0]],
+// B = [b1 - a1 b0, b2 - a2 b0].  A recurrence over 1.4 M samples is serial on the host; here the signal is cut into
+// chunks: (1) every chunk runs from a zero state and keeps its end state, (2) one thread chains the true start states
+// through A^L (2x2, from the host), (3) every chunk runs again from its true start state and writes y.  Double
+// precision throughout, like scipy on a float64 coefficient array.
+constexpr int kSosChunk = 256;
+struct SosCoef {
+    double b0, a1, a2, B0, B1;   // B = (b1 - a1 b0, b2 - a2 b0)
+    double AL[4];                // A^L row-major
+};
+__global__ void sos_zero_state_kernel(const double* __restrict__ x, long long n, SosCoef c, double* __restrict__ zend) {
+    const long long chunk = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long i0 = chunk * kSosChunk;
+    if (i0 >= n) return;
+    const long long i1 = i0 + kSosChunk < n ? i0 + kSosChunk : n;
+    double z0 = 0.0, z1 = 0.0;
+    for (long long i = i0; i < i1; ++i) {
+        const double xv = x[i];
+        const double nz0 = -c.a1 * z0 + z1 + c.B0 * xv;
+        z1 = -c.a2 * z0 + c.B1 * xv;
+        z0 = nz0;
+    }
+    zend[2 * chunk] = z0;
+    zend[2 * chunk + 1] = z1;
+}
+__global__ void sos_chain_kernel(const double* __restrict__ zend, double* __restrict__ zstart, long long chunks, SosCoef c) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    double z0 = 0.0, z1 = 0.0;
+    for (long long k = 0; k < chunks; ++k) {
+        zstart[2 * k] = z0;
+        zstart[2 * k + 1] = z1;
+        const double n0 = c.AL[0] * z0 + c.AL[1] * z1 + zend[2 * k];
+        const double n1 = c.AL[2] * z0 + c.AL[3] * z1 + zend[2 * k + 1];
+        z0 = n0;
+        z1 = n1;
+    }
+}
+__global__ void sos_apply_kernel(const double* __restrict__ x, double* __restrict__ y, long long n, SosCoef c,
+                                 const double* __restrict__ zstart) {
+    const long long chunk = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    const long long i0 = chunk * kSosChunk;
+    if (i0 >= n) return;
+    const long long i1 = i0 + kSosChunk < n ? i0 + kSosChunk : n;
+    double z0 = zstart[2 * chunk], z1 = zstart[2 * chunk + 1];
+    for (long long i = i0; i < i1; ++i) {
+        const double xv = x[i];
+        y[i] = c.b0 * xv + z0;
+        const double nz0 = -c.a1 * z0 + z1 + c.B0 * xv;
+        z1 = -c.a2 * z0 + c.B1 * xv;
+        z0 = nz0;
+    }
+}
 }  // namespace
 }  // namespace mb
 
@@ -233,5 +364,45 @@ extern "C" int mb_single_weighted(const float* low, const float* high, const flo
     MB_REQUIRE(low && high && envelope && out && T > 0 && D > 0, "mb_single_weighted: bad argument");
     single_weighted_kernel<<<grid1d(static_cast<long long>(T) * D), 256, 0, static_cast<cudaStream_t>(stream)>>>(low, high, envelope, out, T, D);
     MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_quantile_mid(const float* x, int64_t n, float q, float* out, mb_stream stream) {
+    MB_REQUIRE(x && out && n >= 0, "mb_quantile_mid: bad argument");
+    MB_REQUIRE(q >= 0.0f && q <= 1.0f, "mb_quantile_mid: the quantile must be in [0, 1] (got %g)", static_cast<double>(q));
+    quantile_mid_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n, q, out);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_sosfilt(const double* x, double* y, int64_t n, const double* sos_host, int n_sections, double* scratch,
+                          mb_stream stream_) {
+    MB_REQUIRE(x && y && sos_host && scratch && n > 0 && n_sections > 0, "mb_sosfilt: bad argument");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long chunks = (n + kSosChunk - 1) / kSosChunk;
+    double* zend = scratch;
+    double* zstart = scratch + 2 * chunks;
+    const double* src = x;
+    for (int s = 0; s < n_sections; ++s) {
+        const double* q = sos_host + 6 * s;
+        MB_REQUIRE(q[3] != 0.0, "mb_sosfilt: a0 of section %d is zero", s);
+        SosCoef c;
+        const double b0 = q[0] / q[3], b1 = q[1] / q[3], b2 = q[2] / q[3];
+        c.b0 = b0; c.a1 = q[4] / q[3]; c.a2 = q[5] / q[3];
+        c.B0 = b1 - c.a1 * b0; c.B1 = b2 - c.a2 * b0;
+        // A^L by repeated squaring (L = 256 = 2^8)
+        double m[4] = {-c.a1, 1.0, -c.a2, 0.0};
+        for (int k = 0; k < 8; ++k) {
+            const double r[4] = {m[0] * m[0] + m[1] * m[2], m[0] * m[1] + m[1] * m[3], m[2] * m[0] + m[3] * m[2], m[2] * m[1] + m[3] * m[3]};
+            for (int j = 0; j < 4; ++j) m[j] = r[j];
+        }
+        for (int j = 0; j < 4; ++j) c.AL[j] = m[j];
+        const int grid = static_cast<int>((chunks + 127) / 128);
+        sos_zero_state_kernel<<<grid, 128, 0, stream>>>(src, n, c, zend);
+        sos_chain_kernel<<<1, 32, 0, stream>>>(zend, zstart, chunks, c);
+        sos_apply_kernel<<<grid, 128, 0, stream>>>(src, y, n, c, zstart);
+        MB_CUDA(cudaGetLastError());
+        src = y;   // the next section filters in place (each chunk reads x[i] before it writes y[i])
+    }
     return MB_OK;
 }

@@ -124,6 +124,40 @@ def onset_strength(y, sr):
     return env[: s.shape[1]]
 
 
+def onset_strength_median(y, sr):
+    """rosa/beat.py:10-23 with aggregate = median over the mel bins (torch.median: the lower middle value), as plp passes it
+    (:41-43)."""
+    s = power_to_db(melspectrogram(y, sr, fmax=11025.0))
+    env = torch.clamp(s[:, 1:] - s[:, :-1], min=0).median(dim=0).values
+    env = torch.nn.functional.pad(env, (2, 0))[: s.shape[1]]
+    return env
+
+
+def plp(y, sr, hop_length=1024, win_length=1024, tempo_min=60, tempo_max=180):
+    """Predominant local pulse, rosa/beat.py:41-75: Fourier tempogram of the (median-aggregated) onset envelope (hann window
+    of min(T, 1024) frames, hop 1), kept to [tempo_min, tempo_max] bpm, only the per-frame peak bin survives, unit magnitude,
+    inverse transform, positive part, min-max normalised."""
+    env = onset_strength_median(y, sr)
+    n = min(len(env), win_length)
+    win = torch.hann_window(n)
+    ft = torch.stft(env, n_fft=n, hop_length=1, center=True, window=win, pad_mode="reflect", return_complex=True)
+    freqs = torch.linspace(0, float(sr * 60 / float(hop_length)) / 2, int(1 + n // 2))
+    ft[freqs < tempo_min] = 0
+    ft[freqs > tempo_max] = 0
+    mag = torch.log1p(1e6 * torch.abs(ft))
+    ft[mag < mag.max(dim=0, keepdim=True).values] = 0
+    ft = ft / (torch.finfo(ft.dtype).tiny ** 0.5 + torch.abs(ft.abs().max(dim=0, keepdim=True).values))
+    pulse = torch.istft(ft, n_fft=n, hop_length=1, center=True, window=win, length=len(env))
+    pulse = torch.clamp(pulse, torch.zeros(()), pulse.max())
+    pulse = pulse - pulse.min()
+    return pulse / (pulse.max() + 1e-8)
+
+
+def pulse(y, sr):
+    """features/audio.py:67-68 -> [T, 1]."""
+    return plp(percussive(y), sr).unsqueeze(-1)
+
+
 def normalize(x):
     """processing.py:53-56."""
     x = x - x.min()

@@ -50,7 +50,15 @@ _pkg("maua.audiovisual.audioreactive", base)
 _pkg("maua.audiovisual.audioreactive.selfsupervised", base + "/selfsupervised")
 _pkg("maua.audiovisual.audioreactive.selfsupervised.features", base + "/selfsupervised/features")
 eq = types.ModuleType("maua.audiovisual.audioreactive.selfsupervised.features.efficient_quantile")
-eq.quantile = lambda t, q: torch.quantile(t, q)
+# the reference's own compiled efficient_quantile.cpp (oracle/_ref, built by oracle/build_ref.py) behind the wrapper of
+# efficient_quantile/__init__.py:6-7 -- not a torch.quantile stand-in (that one interpolates linearly, the reference takes the
+# mid point with a float32 q)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.build_ref import load_efficient_quantile  # noqa: E402
+
+_eq = load_efficient_quantile()
+assert _eq is not None, "run `python oracle/build_ref.py` first"
+eq.quantile = lambda tensor, q: _eq(tensor.cpu().flatten(), torch.FloatTensor([q]), True, 3).squeeze().to(tensor.device)
 sys.modules[eq.__name__] = eq
 
 ref_audio = importlib.import_module("maua.audiovisual.audioreactive.selfsupervised.features.audio")
@@ -94,6 +102,8 @@ with torch.inference_mode():
     same(OA.onsets(y, sr), on_ref, "onsets")
     rms_ref = ref_audio.rms(y, sr)
     same(OA.rms(y), rms_ref, "rms")
+    pulse_ref = ref_audio.pulse(y, sr)
+    same(OA.pulse(y, sr), pulse_ref, "pulse (plp)")
 
     import warnings
     warnings.filterwarnings("ignore")  # torchaudio's deprecation notice for the "kaiser_window" method name
@@ -151,7 +161,7 @@ with torch.inference_mode():
     peaks = OA.peak_indices(on_ref)
     margins = torch.minimum(on_ref[peaks, 0] - on_ref[(peaks - 1).clamp(0), 0], on_ref[peaks, 0] - on_ref[(peaks + 1).clamp(max=len(on_ref) - 1), 0])
     out = dict(sr=sr, fps=fps, audio=y.half(), audio_exact=y, stft_abs=d.abs()[:, ::16].half(), perc_abs=pr.abs()[:, ::16].half(),
-               onsets=on_ref[:, 0], rms=rms_ref[:, 0], peaks=peaks, peak_margins=margins,
+               onsets=on_ref[:, 0], rms=rms_ref[:, 0], pulse=pulse_ref[:, 0], peaks=peaks, peak_margins=margins,
                gauss2=ref_signal.gaussian_filter(env, 2.0), pclip90=ref_signal.percentile_clip(env.clone(), 90)[:, 0],
                resample57=ref_signal.resample(env, 57), lat=lat[:, :2, :4].clone(), lat_gauss=ref_signal.gaussian_filter(lat, 3.0, causal=0.3)[:, :2, :4].clone(),
                harmonic=harm_ref.half(), cqt_abs=cq_ref.abs(), chroma_cqt=chroma_ref, chroma_cqt_harmonic=chroma_h_ref,

@@ -37,7 +37,15 @@ _pkg("maua.audiovisual.audioreactive", base)
 _pkg("maua.audiovisual.audioreactive.selfsupervised", base + "/selfsupervised")
 _pkg("maua.audiovisual.audioreactive.selfsupervised.features", base + "/selfsupervised/features")
 eq = types.ModuleType("maua.audiovisual.audioreactive.selfsupervised.features.efficient_quantile")
-eq.quantile = lambda t, q: torch.quantile(t, q)
+# the reference's own compiled efficient_quantile.cpp (oracle/_ref, built by oracle/build_ref.py) behind the wrapper of
+# efficient_quantile/__init__.py:6-7 -- not a torch.quantile stand-in (that one interpolates linearly, the reference takes the
+# mid point with a float32 q)
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.build_ref import load_efficient_quantile  # noqa: E402
+
+_eq = load_efficient_quantile()
+assert _eq is not None, "run `python oracle/build_ref.py` first"
+eq.quantile = lambda tensor, q: _eq(tensor.cpu().flatten(), torch.FloatTensor([q]), True, 3).squeeze().to(tensor.device)
 sys.modules[eq.__name__] = eq
 mir = types.ModuleType("maua.audiovisual.audioreactive.selfsupervised.mir")
 consts = {}

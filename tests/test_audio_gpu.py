@@ -47,11 +47,14 @@ def test_config_sized_sweep_matches_oracle(cuda, fps, dur):
     assert float(err.max()) < 1e-3 and float(err.mean()) < 5e-5, (float(err.max()), float(err.mean()))
     assert float((rms[:, 0].cpu() - OA.rms(y)[:, 0]).abs().max()) < 1e-6
     got_pk = ar.onset_peaks(y.to(cuda), sr).cpu()
+    # how decisive every comparison of the peak picker is (signal.py:69-76: x[i] > x[i-1] and x[i] > x[i+1]): the smallest
+    # |x[i] - x[i+1]| of the envelope against the device's deviation from the oracle
+    gaps = (ref_on[1:] - ref_on[:-1]).abs()
     margins = torch.minimum(ref_on[ref_pk] - ref_on[(ref_pk - 1).clamp(0)], ref_on[ref_pk] - ref_on[(ref_pk + 1).clamp(max=len(ref_on) - 1)])
-    solid = ref_pk[margins > 1e-4]  # peaks whose margin is far above fp32 noise must be found exactly
-    assert set(solid.tolist()) <= set(got_pk.tolist())
-    if float(margins.min()) > 1e-4:
-        assert torch.equal(got_pk, ref_pk)
+    hist = torch.histc(margins.log10().clamp(-8, 0), bins=8, min=-8, max=0).int().tolist()
+    print(f"{fps} fps: {len(ref_pk)} peaks; peak margins per decade 1e-8..1 {hist}; smallest margin {float(margins.min()):.2e}, "
+          f"smallest neighbour gap {float(gaps.min()):.2e}; envelope deviation max {float(err.max()):.2e}")
+    assert torch.equal(got_pk, ref_pk), (sorted(set(got_pk.tolist()) ^ set(ref_pk.tolist())))   # unconditional: bit-exact indices
 
 
 def test_errors(cuda):

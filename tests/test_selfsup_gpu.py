@@ -143,3 +143,32 @@ def test_extract_features_end_to_end(cuda, gold):
         want = OS.normalize(OS.salience_weighted(OS.gaussian_filter(v.cpu(), sigma=2)))
         close(post[k].reshape(want.shape), want, 2e-4)
         assert float(post[k].min()) >= 0.0 and float(post[k].max()) <= 1.0 + 1e-6
+
+
+def test_midpoint_quantile_on_the_device(cuda):
+    """quantile / standardize / onset_envelope (efficient_quantile + processing.py:58-61,93-98): the device radix select
+    against vectors from the reference's own compiled routine -- bit for bit (order statistics are exact, the mid point is
+    formed in double as the reference does)."""
+    import os
+
+    from maua_b200.audiovisual.audioreactive import selfsupervised as ss
+    from oracle import quantile as OQ
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "quantile.pt"))
+    for name, c in gold["cases"].items():
+        x = c["x"].to(cuda)
+        got = torch.stack([ss.quantile(x, q) for q in c["qs"]]).cpu()
+        assert torch.equal(got, c["want"]), (name, got, c["want"])
+    assert torch.equal(ss.standardize(gold["flow"].to(cuda)).cpu(), gold["standardize"])
+    flux = ss.spectral_flux(gold["spec"].to(cuda))
+    assert torch.equal(flux.cpu(), OQ.spectral_flux(gold["spec"]))
+    env = ss.onset_envelope(flux).cpu()
+    # the sum over bins is a device reduction (different order than the host's): values to 1e-6, the clamp bounds exact
+    assert float((env - gold["onset_envelope"]).abs().max()) < 1e-6
+    g = torch.Generator().manual_seed(8)
+    big = torch.randn(300001, generator=g)
+    big[::1000] = float("nan")
+    for q in (0.0015, 0.5, 0.9985):
+        assert torch.equal(ss.quantile(big.to(cuda), q).cpu(), OQ.quantile(big, q)), q
+    with pytest.raises(RuntimeError):
+        ss.quantile(big, 0.5)   # host tensor: no CPU fallback

@@ -89,6 +89,29 @@ def test_full_size_frame_matches_oracle(cuda):
     assert out.shape == (1, 3, 1024, 1024)
 
 
+def test_benched_batch_matches_oracle_and_is_batch_invariant(cuda):
+    """The configuration bench.py times: StyleGAN3-T 1024^2 at 16 frames per step (per-layer kernel variants, column
+    segmentation and staging are chosen from the batch size).  Frames 0 and 15 of the batch against the oracle, and every
+    frame of the batch bit-identical to the same frame rendered alone and in a batch of 8."""
+    from maua_b200.workload import c2_latents
+
+    onet, net = make_pair("T", 1024)
+    lat, _ = c2_latents(net.num_ws)
+    ws = lat[200:216]
+    torch.set_num_threads(os.cpu_count() or 1)
+    out16 = net(ws.to(cuda)).clone()
+    assert out16.shape == (16, 3, 1024, 1024)
+    for i in (0, 15):
+        ref = onet(ws[i:i + 1])
+        err = float((pix(out16[i:i + 1]) - pix(ref)).abs().max())
+        print(f"1024^2, 16 frames per step, frame {i}: max-abs pixel error vs oracle {err:.3e}")
+        assert err <= PIX_TOL, (i, err)
+    for i in (0, 7, 15):
+        assert torch.equal(net(ws[i:i + 1].to(cuda)), out16[i:i + 1]), f"frame {i} differs between B=1 and B=16"
+    out8 = net(ws[8:16].to(cuda))
+    assert torch.equal(out8, out16[8:16]), "frames differ between B=8 and B=16"
+
+
 def test_full_size_R_frame_matches_oracle(cuda):
     """BASELINE.json configs[2] network (StyleGAN3-R 1024^2: 1x1 convs, radial down filters run as separable
     eigen-terms on the tensor-core chain), one frame."""

@@ -25,6 +25,13 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec StyleGAN3 1024^2 audio-reactive render"
 WORKLOAD = "StyleGAN3-T 1024^2 random-init, 30 s @ 24 fps (720 frames) audio-reactive latents, 48 kHz sine sweep"
+# --config: BASELINE.json configs[1] (the default, the configuration the metric is quoted on) and configs[2]
+CONFIGS = {
+    "c2": dict(arch="T", seconds=30.0, fps=24, workload=WORKLOAD),
+    "c3": dict(arch="R", seconds=180.0, fps=60,
+               workload="StyleGAN3-R 1024^2 random-init, 180 s @ 60 fps (10 800 frames) audio-reactive latents, 48 kHz sine sweep, "
+                        "frames sharded over the ranks"),
+}
 
 
 _REAL_STDOUT = None
@@ -140,7 +147,8 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    net = O.make_synthesis("T", 1024, seed=0)
+    cfg = CONFIGS[args.config]
+    net = O.make_synthesis(cfg["arch"], 1024, seed=0)
     lat, _ = c2_latents(net.num_ws)
     # one step = ONE frame of the 720-frame job (a bounded sample: the CPU needs tens of seconds per frame);
     # the timed steps are additionally capped by a wall-clock budget so the arm ends within minutes.
@@ -168,7 +176,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": len(times), "steps_requested": args.steps, "warmup": done_w, "ms_per_step": 1000 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step": 1},
+        "config": {"workload": cfg["workload"], "name": args.config, "frames_per_step": 1},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{len(times)} of 720 frames, one frame per step (fp32 PyTorch restatement of the "
                                    "reference algorithm; the reference's own network source is an un-vendored submodule)"},
@@ -198,21 +206,29 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     from maua_b200.GAN.wrappers import get_generator_class
-    from maua_b200.workload import c2_latents_device
+    from maua_b200.workload import job_latents_device, resampled_sweep, audio_reactive_latents
 
     B, K, W = args.batch, args.steps, args.warmup
+    cfg = CONFIGS[args.config]
+    n_job = int(round(cfg["seconds"] * cfg["fps"]))
     torch.manual_seed(0)
-    G = get_generator_class("stylegan3")(model_file=None).to(dev)
+    G = get_generator_class("stylegan3")(model_file=None)
+    if cfg["arch"] == "R":
+        from maua_b200.GAN.networks import stylegan3 as N
+
+        torch.manual_seed(0)
+        G.synthesizer.G_synth = N.SynthesisNetwork(w_dim=512, img_resolution=1024, img_channels=3, **N.SG3_R_KWARGS)
+    G = G.to(dev)
     net = G.synthesizer.G_synth
     if world > 1:  # generator weights broadcast once over NCCL
         for t in list(net.parameters()) + list(net.buffers()):
             dist.broadcast(t.data, src=0)
-    # audio-reactive latents of the 720-frame job: built on rank 0, broadcast, sharded by contiguous frame range
+    # audio-reactive latents of the job: built on rank 0, broadcast, sharded by contiguous frame range
     audio_info = {}
     if rank == 0:
-        lat, audio_info = c2_latents_device(net.num_ws, dev)   # onset / rms features by the library's audio kernels
+        lat, audio_info = job_latents_device(net.num_ws, dev, cfg["seconds"], cfg["fps"])   # the library's audio kernels
     else:
-        lat = torch.empty(720, net.num_ws, 512, device=dev)
+        lat = torch.empty(n_job, net.num_ws, 512, device=dev)
     if world > 1:
         dist.broadcast(lat, src=0)
     T = lat.shape[0]
@@ -220,10 +236,29 @@ def run_ours(args):
     my = lat[rank * per:(rank + 1) * per].contiguous()
     nb = max(per // B, 1)
 
-    frames = torch.empty(B, 1024, 1024, 3, device=dev, dtype=torch.uint8)
+    # Finished uint8 frames are gathered to rank 0 over NCCL INSIDE the timed region (north_star: "rendered frames gathered
+    # across the GPUs with NCCL over NVLink"): one gather per step (grouped ncclSend / ncclRecv on NCCL's own stream),
+    # double-buffered so the transfer of step i overlaps the kernels of step i + 1.
+    frame_shape = (B, 1024, 1024, 3)
+    frames = [torch.empty(frame_shape, device=dev, dtype=torch.uint8) for _ in range(2)]
+    gathered = [[torch.empty(frame_shape, device=dev, dtype=torch.uint8) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else None
+    pending = [None, None]
+    gather_bytes = (world - 1) * B * 1024 * 1024 * 3 if world > 1 else 0
+
     def step(i):
         j = (i % nb) * B
-        net(my[j:j + B], out_fmt="u8", out=frames)
+        k = i % 2
+        if pending[k] is not None:
+            pending[k].wait()          # stream-level: the gather that read frames[k] two steps ago is done
+        net(my[j:j + B], out_fmt="u8", out=frames[k])
+        if world > 1:
+            pending[k] = dist.gather(frames[k], gathered[k] if rank == 0 else None, dst=0, async_op=True)
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
 
     def barrier():
         if world > 1:
@@ -232,6 +267,7 @@ def run_ours(args):
 
     for i in range(W):
         step(i)
+    drain()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -244,6 +280,7 @@ def run_ours(args):
     e0.record()
     for i in range(K):
         step(W + i)
+    drain()                      # the last gathers are inside the timed region
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -257,32 +294,60 @@ def run_ours(args):
     ms = float(tmax.item())
     launches = net.last_launch_count() * K
 
-    # ---- e2e: the public call with HOST buffers; H2D of the latents and D2H of the frames every step ----
-    from maua_b200.audiovisual.render._loop import AsyncFrameDownloader
+    # ---- e2e: the product's own entry points with HOST buffers ------------------------------------------------------------
+    # What a reference-style patch + renderer does for this rank's frames, timed wall-clock from host audio to the last byte in
+    # the sink: (1) the track (pinned host memory) -> device -> resample -> audio features -> latent sequence -> host tensors
+    # (process_audio / process_synthesizer_inputs of a patch), (2) FFMPEG.__call__(synthesizer, {"latents": host}, postprocess)
+    # = pinned staging, per-batch H2D, synthesis, (x+1)/2, postprocess, tensor2bytes, D2H into the pinned ring, writer thread
+    # -> sink (a byte counter standing in for the ffmpeg pipe: the x264 encode is not part of the path).
+    from maua_b200.audiovisual.render.ffmpeg import FFMPEG
+    from maua_b200.workload import sine_sweep
 
-    host_lat = my[: nb * B].cpu().pin_memory()
-    dl = AsyncFrameDownloader((B, 1024, 1024, 3), dev, depth=2)   # pinned host ring, D2H on a side stream
     net.set_option("profile", 0)
 
-    def e2e_step(i):
-        j = (i % nb) * B
-        ws = host_lat[j:j + B].to(dev, non_blocking=True)
-        net(ws, out_fmt="u8", out=dl.device_buffer(i))
-        dl.download(i)
+    class ByteCounter:
+        def __init__(self):
+            self.n = 0
 
-    for i in range(min(W, 2)):
-        e2e_step(i)
-    dl.synchronize()
+        def write(self, view):
+            self.n += len(view)
+
+        def close(self):
+            pass
+
+    track48, sr48 = sine_sweep(cfg["seconds"], tremolo_hz=4.0)
+    track_host = torch.from_numpy(track48).pin_memory()
+    n_e2e = min(K * B, per)
+    lo = 0
+    postprocess = lambda video: video   # noqa: E731  (a patch's process_outputs + force_output_size at native size)
+
+    def e2e_job():
+        import torchaudio
+
+        y48 = track_host.to(dev, non_blocking=True)
+        sr = 1024 * cfg["fps"]
+        y = torchaudio.functional.resample(y48, sr48, sr)
+        n = n_job * 1024
+        y = (y[:n] if y.numel() >= n else torch.nn.functional.pad(y, (0, n - y.numel()))).contiguous()
+        lat_dev = audio_reactive_latents(y, sr, net.num_ws)
+        t_audio = time.perf_counter()
+        host_lat = lat_dev[rank * per + lo: rank * per + lo + n_e2e].cpu()          # the patch hands host tensors to the renderer
+        sink = ByteCounter()
+        FFMPEG(None, fps=cfg["fps"], batch_size=B, sink=sink)(G.synthesizer, {"latents": host_lat}, postprocess)
+        return sink.n, t_audio
+
+    e2e_job()                    # warm-up of this path (pinned rings, resample kernel cache)
     barrier()
     t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(i)
-    dl.synchronize()          # the last batch's frames are in pinned host memory
+    nbytes, t_audio = e2e_job()
     torch.cuda.synchronize()
-    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    t1 = time.perf_counter()
+    assert nbytes == n_e2e * 1024 * 1024 * 3, (nbytes, n_e2e)
+    t_e2e = torch.tensor([t1 - t0], device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_fps = world * B * K / float(t_e2e.item())
+    e2e_fps = world * n_e2e / float(t_e2e.item())
+    e2e_audio_ms = 1000.0 * (t_audio - t0)
 
     if rank != 0:
         if world > 1:
@@ -322,7 +387,7 @@ def run_ours(args):
 
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        onet = O.make_synthesis("T", 1024, seed=0)
+        onet = O.make_synthesis(cfg["arch"], 1024, seed=0)
         wl = my[:1].cpu()
         t0 = time.perf_counter()
         onet(wl)
@@ -334,13 +399,20 @@ def run_ours(args):
         "metric": METRIC, "value": world * B * K / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "frames_per_gpu": per,
+        "config": {"workload": cfg["workload"], "name": args.config, "frames_per_step_per_gpu": B, "frames_per_gpu": per,
+                   "collective": (f"per step: gather of the step's uint8 frames to rank 0 over NCCL (grouped ncclSend/ncclRecv, "
+                                  f"{gather_bytes} bytes into the root per step), overlapped with the next step's kernels; weights and "
+                                  f"latents broadcast once before the timed region") if world > 1 else "none (one rank)",
                    "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush",
                    "output": "uint8 NHWC frames resident in HBM",
-                   "audio_features": {**audio_info, "note": "device STFT/HPSS/onset/rms + chromagram (harmonic, tuning estimate, constant-Q, CENS) pass run once before the timed region"}, "sharding": f"contiguous frame ranges over {world} rank(s), no data-path collective"},
+                   "audio_features": {**audio_info, "note": "device STFT/HPSS/onset/rms + chromagram (harmonic, tuning estimate, constant-Q, CENS) pass run once before the timed region"}, "sharding": f"contiguous frame ranges over {world} rank(s)"},
         "clocks": clk,
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * net.num_ws * 512 * 4,
-                "d2h_bytes_per_step": B * 1024 * 1024 * 3},
+                "d2h_bytes_per_step": B * 1024 * 1024 * 3,
+                "path": "host audio -> device features + latent sequence -> host latents -> FFMPEG.__call__ (pinned staging, H2D per "
+                        "batch, synthesis, postprocess, tensor2bytes, D2H ring, writer thread -> byte-counting sink)",
+                "frames_per_gpu": n_e2e, "audio_and_latents_ms": round(e2e_audio_ms, 2),
+                "h2d_bytes_once": int(track_host.numel() * 4)},
         "gpu_launches": launches,
         "roofline": roof_fl if dominant == 3 else roof_conv,
         "roofline_other": roof_conv if dominant == 3 else roof_fl,
@@ -361,6 +433,7 @@ def main():
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (16 = the reference FFMPEG renderer's batch size, maua/audiovisual/render/ffmpeg.py:31)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2 = BASELINE configs[1] (default, the headline), c3 = configs[2]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

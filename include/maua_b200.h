@@ -119,6 +119,8 @@ size_t mb_net_workspace_bytes(const mb_net* net, int batch);
 #define MB_OUT_F32_NCHW_01 1 /* float32 [B,3,H,W] = clamp((x+1)/2, 0, 1): what MauaGenerator.render yields (wrappers/__init__.py:93) */
 #define MB_OUT_U8_NHWC 2  /* uint8 [B,H,W,3] = round(clamp((x+1)/2,0,1)*255): the
                              tensor2bytes() wire format of maua/ops/io.py:47-70 */
+#define MB_OUT_F32_NCHW_UNIT 3 /* float32 [B,3,H,W] = (x+1)/2, NOT clamped: what the FFMPEG / MemMap renderers hand to the
+                                  patch's postprocess before tensor2bytes clamps (render/ffmpeg.py:72-73, memmap.py:30) */
 
 /* One synthesis forward for `batch` frames.
  *   ws        device float32 [batch, num_ws, w_dim]   (W+ latents, stylegan3.py:51 `latents`)
@@ -290,6 +292,10 @@ int mb_chroma_cens_post(const float* chroma_raw, int n_chroma, int T, const floa
 int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal, mb_stream stream);
 int mb_normalize(const float* x, float* y, int64_t n, float eps, float* scratch2 /* device float[2] */, mb_stream stream);
 int mb_resample_linear(const float* x, float* y, int T, int S, int C, mb_stream stream);
+/* tensor2bytes (maua/ops/io.py:47-70) without the host copy: float32 [B,C,H,W] in [lo, hi] ->
+ * uint8 [B,H,W,C] = round(clamp((x - lo) / (hi - lo), 0, 1) * 255), one pass (the reference chains
+ * permute / clamp / sub / div / mul / round / byte: seven elementwise kernels). */
+int mb_frames_to_rgb24(const float* x, uint8_t* out, int B, int C, int H, int W, float lo, float hi, mb_stream stream);
 /* scipy.signal.sosfilt(sos, x) as the reference's low_pass / high_pass / band_pass call it (audioreactive/audio.py:96-110):
  * cascade of second-order sections [b0 b1 b2 a0 a1 a2] (HOST array, n_sections x 6) over a device float64 signal, zero
  * initial state, double precision.  Chunk-parallel (zero-state pass, state chain through A^256, apply pass); y may alias x.

@@ -220,8 +220,8 @@ class SynthesisNetwork(NativeNet):
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
             res = self.img_resolution
-            if out_fmt in ("f32", "f32_01"):
-                fmt = _lib.MB_OUT_F32_NCHW if out_fmt == "f32" else _lib.MB_OUT_F32_NCHW_01
+            if out_fmt in ("f32", "f32_01", "f32_unit"):
+                fmt = {"f32": _lib.MB_OUT_F32_NCHW, "f32_01": _lib.MB_OUT_F32_NCHW_01, "f32_unit": _lib.MB_OUT_F32_NCHW_UNIT}[out_fmt]
                 if out is None:
                     out = torch.empty(B, self.img_channels, res, res, device=device, dtype=torch.float32)
             elif out_fmt == "u8":
@@ -229,7 +229,7 @@ class SynthesisNetwork(NativeNet):
                 if out is None:
                     out = torch.empty(B, res, res, self.img_channels, device=device, dtype=torch.uint8)
             else:
-                raise ValueError("out_fmt must be 'f32', 'f32_01' or 'u8'")
+                raise ValueError("out_fmt must be 'f32', 'f32_01', 'f32_unit' or 'u8'")
             warps = list(warps or [])
             if bool(warps) != getattr(self, "_warps_on", False):
                 self._workspace = {}  # the warp ping-pong buffers change the workspace size

@@ -232,14 +232,14 @@ class SynthesisNetwork(NativeNet):
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
             oh, ow = self.output_hw()
-            if out_fmt in ("f32", "f32_01"):
-                fmt = _lib.MB_OUT_F32_NCHW if out_fmt == "f32" else _lib.MB_OUT_F32_NCHW_01
+            if out_fmt in ("f32", "f32_01", "f32_unit"):
+                fmt = {"f32": _lib.MB_OUT_F32_NCHW, "f32_01": _lib.MB_OUT_F32_NCHW_01, "f32_unit": _lib.MB_OUT_F32_NCHW_UNIT}[out_fmt]
                 shape, dtype = (B, self.img_channels, oh, ow), torch.float32
             elif out_fmt == "u8":
                 fmt = _lib.MB_OUT_U8_NHWC
                 shape, dtype = (B, oh, ow, self.img_channels), torch.uint8
             else:
-                raise ValueError("out_fmt must be 'f32', 'f32_01' or 'u8'")
+                raise ValueError("out_fmt must be 'f32', 'f32_01', 'f32_unit' or 'u8'")
             if out is None:
                 out = torch.empty(shape, device=device, dtype=dtype)
             elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous() or out.device != device:

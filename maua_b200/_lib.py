@@ -13,6 +13,7 @@ from ._build import LIB_PATH
 MB_OUT_F32_NCHW = 0
 MB_OUT_F32_NCHW_01 = 1
 MB_OUT_U8_NHWC = 2
+MB_OUT_F32_NCHW_UNIT = 3
 MB_RESIZE_NONE, MB_RESIZE_STRETCH, MB_RESIZE_PAD_ZERO = 0, 1, 2
 
 
@@ -88,6 +89,7 @@ _SIGNATURES = {
     "mb_normalize": (C.c_int, [_P, _P, C.c_int64, C.c_float, _P, _P]),
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mb_quantile_mid": (C.c_int, [_P, C.c_int64, C.c_float, _P, _P]),
+    "mb_frames_to_rgb24": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "mb_sosfilt": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P]),
     "mb_multi_weighted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mb_single_weighted": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -8,5 +8,5 @@ from . import noise  # noqa: F401,E402
 from .signal import compress, expand, gaussian_filter, normalize, percentile, percentile_clip, resample  # noqa: F401,E402
 from . import selfsupervised  # noqa: F401,E402  (torch-native twins: latent_patch, noise_patch, salience_weighted, ...)
 from .audio import band_pass, high_pass, load_audio, low_pass  # noqa: F401,E402  (classic maua.audiovisual.audioreactive.audio)
-from .mir_classic import chroma, pitch_dominance, pulse, spectral_max, tempo, tonnetz, volume  # noqa: F401,E402  (classic mir.py)
+from .mir_classic import pitch_dominance, pulse, spectral_max, tempo, tonnetz, volume  # noqa: F401,E402  (classic mir.py; its chroma() lives in mir_classic: `chroma` is the constant-Q module here)
 from .util import info, plot_signals, plot_spectra  # noqa: F401,E402

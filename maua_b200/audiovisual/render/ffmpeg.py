@@ -12,19 +12,25 @@ import subprocess
 import torch
 
 from . import Renderer
-from ._loop import frame_batches, to_uint8
+from ._loop import frame_batches, frames_to_rgb24
 from ._sink import RingWriter
 
 
 class FFMPEG(Renderer):
+    """``sink`` (an extension of the reference signature): an object with write(bytes-like) that receives the rgb24 stream
+    instead of ffmpeg / the raw file (bench.py counts the bytes with it)."""
+
     def __init__(self, output_file, fps=24, audio_file=None, audio_offset=0, audio_duration=None, ffmpeg_preset="medium",
-                 batch_size=16):
+                 batch_size=16, sink=None):
         super().__init__()
         self.output_file, self.fps, self.ffmpeg_preset = output_file, fps, ffmpeg_preset
         self.audio_file, self.audio_offset, self.audio_duration = audio_file, audio_offset, audio_duration
-        self.batch_size = batch_size
+        self.batch_size, self.sink = batch_size, sink
+        self.frames_written = 0
 
     def _open_sink(self, w, h):
+        if self.sink is not None:
+            return self.sink, None
         exe = shutil.which("ffmpeg")
         if exe is None:
             return open(self.output_file + ".rgb24", "wb"), None
@@ -38,27 +44,45 @@ class FFMPEG(Renderer):
     ring_depth = 3
 
     def __call__(self, synthesizer, inputs, postprocess, fp16=True):
+        """render/ffmpeg.py:37-75: batches -> synthesizer -> (x + 1) / 2 -> postprocess -> tensor2bytes -> sink.  The
+        (x + 1) / 2 is the network's output format, tensor2bytes one kernel into a device ring slot, and the device -> host
+        copy runs on a side stream into the pinned ring a writer thread drains: the render stream never waits for a copy or
+        a pipe write unless every slot is still unwritten (back-pressure)."""
         sink, proc, writer = None, None, None
+        copy_stream = torch.cuda.Stream(device=self.device)
+        dev_ring, slot_free = None, None
+        self.frames_written = 0
         try:
-            for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device):
-                frame_batch = postprocess(frames.add(1).div(2))
-                u8 = to_uint8(frame_batch).permute(0, 2, 3, 1).contiguous()  # rgb24: H, W, 3 per frame
+            for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device, out_fmt="f32_unit"):
+                frame_batch = postprocess(frames)
+                n = frame_batch.shape[0]
                 if writer is None:
-                    sink, proc = self._open_sink(u8.shape[2], u8.shape[1])
-                    ring = [torch.empty((self.batch_size,) + tuple(u8.shape[1:]), dtype=torch.uint8).pin_memory()
-                            for _ in range(self.ring_depth)]
-                    writer = RingWriter(sink, ring)
-                k = writer.acquire()
-                writer.ring[k][: u8.shape[0]].copy_(u8, non_blocking=True)
-                event = torch.cuda.Event()
-                event.record(torch.cuda.current_stream())
-                writer.submit(k, u8.shape[0], event)
+                    _, c, h, w = frame_batch.shape
+                    sink, proc = self._open_sink(w, h)
+                    shape = (self.batch_size, h, w, c)
+                    writer = RingWriter(sink, [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(self.ring_depth)])
+                    dev_ring = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(self.ring_depth)]
+                    slot_free = [None] * self.ring_depth
+                k = writer.acquire()                      # host slot k (and with it device slot k) has been written out
+                if slot_free[k] is not None:
+                    torch.cuda.current_stream().wait_event(slot_free[k])
+                u8 = frames_to_rgb24(frame_batch, out=dev_ring[k])      # rgb24: H, W, 3 per frame
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream())
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ready)
+                    writer.ring[k][:n].copy_(u8, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(copy_stream)
+                slot_free[k] = done
+                writer.submit(k, n, done)
+                self.frames_written += n
         finally:
             try:
                 if writer is not None:
                     writer.close()
             finally:
-                if sink is not None:
+                if sink is not None and sink is not self.sink:
                     sink.close()
                 if proc is not None:
                     proc.wait()

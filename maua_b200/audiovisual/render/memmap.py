@@ -25,8 +25,8 @@ class MemMap(Renderer):
         out = None
         pinned = None
         pending = None  # (start, count, buffer index)
-        for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device):
-            u8 = frames.add(1).div(2).clamp(0, 1).mul(255).to(torch.uint8)  # the reference truncates (astype), memmap.py:31
+        for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device, out_fmt="f32_01"):
+            u8 = frames.mul(255).to(torch.uint8)  # (x+1)/2 .clamp(0,1) fused into the network; the reference truncates (astype), memmap.py:31
             if out is None:
                 out = np.lib.format.open_memmap(self.cache_file, mode="w+", dtype=np.uint8, shape=(T,) + tuple(u8.shape[1:]))
                 pinned = [torch.empty((self.batch_size,) + tuple(u8.shape[1:]), dtype=torch.uint8).pin_memory() for _ in range(2)]

@@ -71,7 +71,12 @@ class VideoWriter:
             from ... import ops
 
             tensor = ops.resample(tensor.float(), (2 * ceil(h / 2), 2 * ceil(w / 2)))
-        u8 = tensor2bytes_device(tensor, self.value_range)
+        if tensor.is_cuda:
+            from ._loop import frames_to_rgb24
+
+            u8 = frames_to_rgb24(tensor, value_range=self.value_range)      # one kernel
+        else:
+            u8 = tensor2bytes_device(tensor, self.value_range)
         if self._writer is None or tuple(self._writer.ring[0].shape[1:]) != tuple(u8.shape[1:]) or self._writer.ring[0].shape[0] < b:
             if self._writer is not None:
                 self._writer.close()

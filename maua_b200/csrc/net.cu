@@ -704,7 +704,8 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
                        void* workspace, size_t workspace_bytes, mb_stream stream_) {
     MB_REQUIRE(net && ws && out && workspace, "mb_net_forward: null argument");
     MB_REQUIRE(B > 0, "mb_net_forward: batch must be positive");
-    MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_U8_NHWC, "mb_net_forward: unknown out_fmt %d", out_fmt);
+    MB_REQUIRE(out_fmt == MB_OUT_F32_NCHW || out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_U8_NHWC || out_fmt == MB_OUT_F32_NCHW_UNIT,
+               "mb_net_forward: unknown out_fmt %d", out_fmt);
     if (net->sg2) {
         MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
         return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, static_cast<cudaStream_t>(stream_));

@@ -236,9 +236,11 @@ __global__ void upsample_rgb_kernel(const float* __restrict__ x, float* __restri
 }
 
 // (x + 1) / 2 clamped to [0, 1]: MB_OUT_F32_NCHW_01
-__global__ void img_to_unit_kernel(const float* __restrict__ img, float* __restrict__ out, long long n) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x)
-        out[i] = fminf(fmaxf((img[i] + 1.0f) * 0.5f, 0.0f), 1.0f);
+__global__ void img_to_unit_kernel(const float* __restrict__ img, float* __restrict__ out, long long n, int clamp01) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float v = (img[i] + 1.0f) * 0.5f;
+        out[i] = clamp01 ? fminf(fmaxf(v, 0.0f), 1.0f) : v;
+    }
 }
 
 __global__ void img_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int B, int C, int R) {
@@ -649,8 +651,8 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
     const long long nout = static_cast<long long>(B) * n->img_channels * n->res * n->res;
     if (out_fmt == MB_OUT_F32_NCHW) {
         MB_CUDA(cudaMemcpyAsync(out, img[cur], nout * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    } else if (out_fmt == MB_OUT_F32_NCHW_01) {
-        img_to_unit_kernel<<<grid1d(nout), 256, 0, stream>>>(img[cur], static_cast<float*>(out), nout);
+    } else if (out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_F32_NCHW_UNIT) {
+        img_to_unit_kernel<<<grid1d(nout), 256, 0, stream>>>(img[cur], static_cast<float*>(out), nout, out_fmt == MB_OUT_F32_NCHW_01);
         MB_CUDA(cudaGetLastError());
         launches += 1;
     } else {

@@ -327,15 +327,17 @@ __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
                 acc[o][i] = v * a.output_scale;
             }
         }
-        if (a.out_fmt == MB_OUT_F32_NCHW || a.out_fmt == MB_OUT_F32_NCHW_01) {
+        if (a.out_fmt == MB_OUT_F32_NCHW || a.out_fmt == MB_OUT_F32_NCHW_01 || a.out_fmt == MB_OUT_F32_NCHW_UNIT) {
             const bool unit = a.out_fmt == MB_OUT_F32_NCHW_01;   // (x + 1) / 2 clamped to [0, 1]
+            const bool unit_raw = a.out_fmt == MB_OUT_F32_NCHW_UNIT;   // (x + 1) / 2, not clamped
             float* out = static_cast<float*>(a.out);
 #pragma unroll
             for (int o = 0; o < COUT; ++o) {
                 float* op = out + ((static_cast<long long>(b) * COUT + o) * a.H + h) * a.W + w0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (w0 + i < a.W) op[i] = unit ? fminf(fmaxf((acc[o][i] + 1.0f) * 0.5f, 0.0f), 1.0f) : acc[o][i];
+                    if (w0 + i < a.W)
+                        op[i] = unit ? fminf(fmaxf((acc[o][i] + 1.0f) * 0.5f, 0.0f), 1.0f) : (unit_raw ? (acc[o][i] + 1.0f) * 0.5f : acc[o][i]);
             }
         } else {
             uint8_t* out = static_cast<uint8_t*>(a.out);

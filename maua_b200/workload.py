@@ -63,36 +63,50 @@ def c2_latents(num_ws: int = 16, duration_s: float = 30.0, fps: int = 24):
     return envelope_latents(key_latents(num_ws), chroma, onsets), (audio, sr)
 
 
-def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 24):
-    """Config 2 latents with the audio-reactive part computed ON THE DEVICE by the library's feature kernels:
-    sweep -> resample to sr = 1024*fps (one hop per frame) -> onsets / rms (mb_audio_onsets_rms) and the chromagram
-    (mb_audio_hpss_component -> mb_estimate_tuning -> mb_chroma_cqt -> mb_chroma_cens_post) -> Gaussian smoothing ->
-    chroma-weighted key-latent mix blended by the onset envelope.  Returns (latents [T,num_ws,512] on `device`,
-    info dict with the device time of the feature pass)."""
-    from .audiovisual import audioreactive as ar
+def resampled_sweep(duration_s: float, fps: int, device):
+    """The job's audio as the torch-native entry point prepares it (selfsupervised/sample.py:16-32): 48 kHz tremolo sweep,
+    resampled to sr = 1024 * fps with torchaudio.functional.resample (one hop per video frame) -> (float32 [T * 1024] on
+    `device`, sr)."""
+    import torchaudio
 
     audio, sr_file = sine_sweep(duration_s, tremolo_hz=4.0)
-    T = int(round(duration_s * fps))
     sr = 1024 * fps
-    t = np.arange(T * 1024) / sr
-    y = torch.from_numpy(np.interp(t, np.arange(len(audio)) / sr_file, audio).astype(np.float32)).to(device)
-    ar.onsets_rms(y, sr)                                   # warm-up (allocations, module load, filter design)
-    ar.chromagram(y, sr)
+    T = int(round(duration_s * fps))
+    y = torchaudio.functional.resample(torch.from_numpy(audio).to(device), sr_file, sr)
+    n = T * 1024
+    y = y[:n] if y.numel() >= n else torch.nn.functional.pad(y, (0, n - y.numel()))
+    return y.contiguous(), sr
+
+
+def audio_reactive_latents(y, sr, num_ws: int, n_loops: int = 4):
+    """SURVEY §8d's latent recipe on the device, from the resampled track `y`: onsets / rms (mb_audio_onsets_rms) and the
+    chromagram (harmonic -> tuning estimate -> constant-Q -> CENS) -> ``multi_weighted(w, chroma)`` mixed by the onset envelope
+    with ``spline_loops(w, T, n_loops)``, then ``gaussian_filter(sigma=2)`` over time -> [T, num_ws, 512]."""
+    from .audiovisual import audioreactive as ar
+
+    onsets, _ = ar.onsets_rms(y, sr)
+    chroma = ar.chromagram(y, sr).contiguous()                 # [T, 12]
+    T = onsets.shape[0]
+    keys = key_latents(num_ws).to(y.device)
+    drive = ar.normalize(ar.gaussian_filter(onsets[:, 0], 2.0), eps=1e-8).reshape(T, 1, 1)
+    tonal = ar.multi_weighted(keys, chroma + 1e-6)
+    loops = ar.spline_loops(keys, T, n_loops)
+    return ar.gaussian_filter(drive * tonal + (1 - drive) * loops, 2.0).contiguous()
+
+
+def job_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 24):
+    """Latents of a BASELINE.json job (configs[1]: 30 s @ 24 fps = 720 frames; configs[2]: 180 s @ 60 fps = 10 800 frames) with the
+    whole audio-reactive part computed ON THE DEVICE.  Returns (latents [T,num_ws,512] on `device`, info dict with the device
+    time of the feature + sequencing pass)."""
+    y, sr = resampled_sweep(duration_s, fps, device)
+    audio_reactive_latents(y, sr, num_ws)                      # warm-up (allocations, module load, filter design)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    onsets, rms = ar.onsets_rms(y, sr)
-    chroma = ar.chromagram(y, sr).contiguous()   # [T, 12]: harmonic -> tuning estimate -> constant-Q -> CENS
+    lat = audio_reactive_latents(y, sr, num_ws)
     e1.record()
     torch.cuda.synchronize()
-    keys = key_latents(num_ws).to(device)
-    drive = ar.gaussian_filter(onsets[:, 0], 2.0)
-    drive = ar.normalize(drive, eps=1e-8)
-    tonal = ar.multi_weighted(keys, chroma + 1e-6)
-    K = keys.shape[0]
-    pos = torch.linspace(0, 4 * K, T + 1, device=device)[:-1]
-    i0 = pos.floor().long() % K
-    frac = (pos - pos.floor())[:, None, None]
-    loop = keys[i0] * (1 - frac) + keys[(i0 + 1) % K] * frac
-    o = drive.reshape(T, 1, 1)
-    lat = (o * tonal + (1 - o) * loop).contiguous()
     return lat, {"audio_features_ms": e0.elapsed_time(e1), "audio_samples": int(y.numel()), "sr": sr}
+
+
+def c2_latents_device(num_ws: int, device, duration_s: float = 30.0, fps: int = 24):
+    return job_latents_device(num_ws, device, duration_s, fps)

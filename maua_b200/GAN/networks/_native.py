@@ -21,7 +21,7 @@ class NativeNet(torch.nn.Module):
 
     def _is_volatile(self, name, t):
         """True for tensors that must be re-uploaded on every forward (their identity does not reveal a change)."""
-        return False
+        return name in self._POKED
 
     def _prepare_param(self, name, d):
         """Last host-side touch of a float32 device copy before it is handed to mb_net_set_param."""
@@ -57,15 +57,13 @@ class NativeNet(torch.nn.Module):
 
     def _param_key(self, name, t):
         """Identity of a parameter's current value: storage pointer + autograd version counter (inference-mode tensors
-        carry none); the three tensors the wrapper pokes are compared by value."""
+        carry none).  Neither sees an edit through ``.data`` (the reference's stabilisation trick, wrappers/stylegan3.py:54-55):
+        the three tiny tensors the wrapper pokes are therefore volatile -- re-uploaded on every forward (three asynchronous
+        device copies, no synchronisation, no finalize)."""
         try:
             version = t._version
         except RuntimeError:
             version = None
-        if name in self._POKED:
-            # edits through ``.data`` (the reference's stabilisation trick, wrappers/stylegan3.py:54-55) do not bump the
-            # version counter either: these three tiny tensors are always fingerprinted by value
-            version = (version, tuple(t.detach().double().flatten().tolist()))
         return (t.data_ptr(), version, str(t.device), tuple(t.shape))
 
     def _sync_params(self, device):

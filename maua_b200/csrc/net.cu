@@ -415,7 +415,10 @@ extern "C" int mb_net_set_param(mb_net* net, const char* name, const float* data
     MB_CUDA(cudaMemcpyAsync(p.dev, data, sizeof(float) * p.numel, cudaMemcpyDeviceToDevice,
                             static_cast<cudaStream_t>(stream)));
     p.set = true;
-    net->finalized = false;
+    // The input layer's affine and the user transform are read by the kernels as they are (no packed copy): the wrapper
+    // edits them between forwards (stabilisation trick, per-call transform), so updating them does not ask for a finalize.
+    const bool read_directly = &p == &net->in_affine_w || &p == &net->in_affine_b || &p == &net->in_transform;
+    if (!read_directly) net->finalized = false;
     return MB_OK;
 }
 

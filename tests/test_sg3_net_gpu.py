@@ -182,3 +182,48 @@ def test_errors_are_python_exceptions(cuda):
     from maua_b200 import ops
     with pytest.raises(RuntimeError):
         ops.modulated_conv2d(torch.randn(1, 4, 8, 8, device=cuda), torch.randn(4, 4, 5, 5, device=cuda), torch.randn(1, 4, device=cuda))
+
+
+def _wrapper_around(net):
+    from maua_b200.GAN.wrappers.stylegan3 import StyleGAN3Synthesizer
+
+    S = StyleGAN3Synthesizer.__new__(StyleGAN3Synthesizer)
+    torch.nn.Module.__init__(S)
+    S.G_synth = net
+    S._hook_handles = []
+    S.avg_shift = torch.tensor([0.3, -0.2, 0.1, 0.05])
+    return S
+
+
+def test_edits_of_the_input_affine_reach_the_device(cuda):
+    """The stabilisation trick of the wrapper (wrappers/stylegan3.py:54-55) edits input.affine between forwards -- upstream
+    through ``.data``, which bumps no version counter.  After the parameters have been uploaded once, such an edit must still
+    change the next frame (the three poked tensors are re-uploaded on every forward)."""
+    _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    net = net.to(cuda)
+    S = _wrapper_around(net)
+    torch.manual_seed(2)
+    ws = torch.randn(1, net.num_ws, 512, device=cuda)
+    before = S.forward(ws).clone()
+    net.input.affine.bias.data.add_(torch.tensor([0.0, 0.0, 0.2, -0.1], device=cuda))     # a raw .data edit, as upstream does it
+    after_data_edit = S.forward(ws).clone()
+    assert not torch.equal(before, after_data_edit)
+    stabilised = S.forward(ws, translation=0, rotation=0).clone()                          # the trick itself
+    assert not torch.equal(after_data_edit, stabilised)
+    assert float(net.input.affine.weight.abs().max()) == 0.0
+
+
+def test_per_frame_transform_for_a_single_frame(cuda):
+    """[1,2] translation + [1] rotation (the last batch of a render, MemMap's batch size of one) takes the per-frame path and
+    equals the same frame inside a batch of three."""
+    _, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    S = _wrapper_around(net.to(cuda))
+    torch.manual_seed(6)
+    ws = torch.randn(3, net.num_ws, 512, device=cuda)
+    tr = torch.tensor([[0.1, -0.05], [0.0, 0.2], [-0.15, 0.1]])
+    rot = torch.tensor([10.0, -20.0, 35.0])
+    batch = S.forward(ws, translation=tr, rotation=rot).clone()
+    one = S.forward(ws[2:3], translation=tr[2:3], rotation=rot[2:3]).clone()
+    assert torch.equal(one, batch[2:3])
+    one_col = S.forward(ws[1:2], translation=tr[1:2], rotation=rot[1:2, None]).clone()    # rotation as [1,1]
+    assert torch.equal(one_col, batch[1:2])

@@ -333,7 +333,8 @@ def run_ours(args):
         y = (y[:n] if y.numel() >= n else torch.nn.functional.pad(y, (0, n - y.numel()))).contiguous()
         lat_dev = audio_reactive_latents(y, sr, net.num_ws)
         t_audio = time.perf_counter()
-        host_lat = lat_dev[e2e_index[:n_frames]].cpu()                              # the patch hands host tensors to the renderer
+        host_lat = torch.empty((n_frames,) + tuple(lat_dev.shape[1:]), dtype=lat_dev.dtype).pin_memory()
+        host_lat.copy_(lat_dev[e2e_index[:n_frames]])                               # the patch hands host tensors to the renderer
         sink = ByteCounter()
         FFMPEG(None, fps=cfg["fps"], batch_size=B, sink=sink)(G.synthesizer, {"latents": host_lat}, postprocess)
         return sink.n, t_audio

@@ -64,7 +64,8 @@ class StyleGAN3Synthesizer(StyleGANSynthesizer):
         if scalar_zero(translation) and scalar_zero(rotation):
             # stabilization trick by @RiversHaveWings and @nshepperd1
             with torch.no_grad():
-                self.G_synth.input.affine.bias.add_(self.avg_shift)
+                bias = self.G_synth.input.affine.bias
+                bias.add_(self.avg_shift.to(device=bias.device, dtype=bias.dtype))
                 self.G_synth.input.affine.weight.zero_()
         elif not (translation is None or rotation is None):
             self.G_synth.input.transform.copy_(make_transform_mat(translation, rotation))

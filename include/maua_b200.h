@@ -292,6 +292,15 @@ int mb_chroma_cens_post(const float* chroma_raw, int n_chroma, int T, const floa
 int mb_gaussian_filter(const float* x, float* y, int T, int C, float sigma, int causal_mode, float causal, mb_stream stream);
 int mb_normalize(const float* x, float* y, int64_t n, float eps, float* scratch2 /* device float[2] */, mb_stream stream);
 int mb_resample_linear(const float* x, float* y, int T, int S, int C, mb_stream stream);
+/* Op-level entry points of the in-tree inference network's resampling / activation ops (maua/GAN/wrappers/inference/ops.py):
+ * upfirdn2d :87-114 -- zero insertion x up, padding [px0, px1, py0, py1] (negative = crop), correlation with the 2-D filter
+ * f [fh, fw] scaled by gain (not flipped), decimation by down: float32 [B,C,H,W] -> [B,C,Ho,Wo],
+ * Ho = (H*up + py0 + py1 - fh) / down + 1; bias_act :65-84 -- x + b[c], act (0 linear, 1 leaky ReLU with slope alpha),
+ * * gain, clamp to [-clamp, clamp] when clamp >= 0.  (Inside mb_net_forward both are fused into one kernel between the convs.) */
+int mb_upfirdn2d(const float* x, const float* f, float* y, int B, int C, int H, int W, int fh, int fw, int up, int down, int px0,
+                 int px1, int py0, int py1, float gain, mb_stream stream);
+int mb_bias_act(const float* x, const float* b /* [C] or NULL */, float* y, int B, int C, int H, int W, int act, float alpha,
+                float gain, float clamp, mb_stream stream);
 /* tensor2bytes (maua/ops/io.py:47-70) without the host copy: float32 [B,C,H,W] in [lo, hi] ->
  * uint8 [B,H,W,C] = round(clamp((x - lo) / (hi - lo), 0, 1) * 255), one pass (the reference chains
  * permute / clamp / sub / div / mul / round / byte: seven elementwise kernels). */

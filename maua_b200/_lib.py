@@ -90,6 +90,8 @@ _SIGNATURES = {
     "mb_resample_linear": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "mb_quantile_mid": (C.c_int, [_P, C.c_int64, C.c_float, _P, _P]),
     "mb_frames_to_rgb24": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "mb_upfirdn2d": (C.c_int, [_P, _P, _P] + [C.c_int] * 12 + [C.c_float, _P]),
+    "mb_bias_act": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P]),
     "mb_sosfilt": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_double), C.c_int, _P, _P]),
     "mb_multi_weighted": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "mb_single_weighted": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, _P]),

@@ -197,6 +197,49 @@ __global__ void frames_to_rgb24_kernel(const float* __restrict__ x, uint8_t* __r
         }
     }
 }
+
+// ---- op-level upfirdn2d / bias_act of the in-tree inference network (maua/GAN/wrappers/inference/ops.py:65-114) ----------
+// These are the standalone forms of what sg2_act_kernel fuses between two convolutions; exported for callers of the ops
+// themselves and for op-level parity tests.  upfirdn2d: zero insertion x `up`, padding (negative = crop),
+// correlation with the 2-D filter f * gain (NOT flipped, ops.py:106-111), decimation by `down`.  Polyphase: a thread only
+// visits the taps that land on a real sample.
+__global__ void upfirdn2d_kernel(const float* __restrict__ x, const float* __restrict__ f, float* __restrict__ y, int planes, int H,
+                                 int W, int fh, int fw, int up, int down, int px0, int py0, int Ho, int Wo, float gain) {
+    const long long total = static_cast<long long>(planes) * Ho * Wo;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % Wo);
+        const long long r = idx / Wo;
+        const int oy = static_cast<int>(r % Ho);
+        const long long pl = r / Ho;
+        const float* xp = x + pl * H * W;
+        // out[oy][ox] = sum_{ky,kx} f[ky][kx] * xu[oy*down + ky - py0][ox*down + kx - px0],  xu[a][b] = x[a/up][b/up] on the grid
+        const int by = oy * down - py0, bx = ox * down - px0;
+        float acc = 0.0f;
+        for (int ky = ((-by) % up + up) % up; ky < fh; ky += up) {
+            const int iy = (by + ky) / up;
+            if (by + ky < 0 || iy >= H) continue;
+            for (int kx = ((-bx) % up + up) % up; kx < fw; kx += up) {
+                const int ix = (bx + kx) / up;
+                if (bx + kx < 0 || ix >= W) continue;
+                acc = fmaf(f[ky * fw + kx], xp[static_cast<long long>(iy) * W + ix], acc);
+            }
+        }
+        y[idx] = acc * gain;
+    }
+}
+// act: 0 linear, 1 lrelu(alpha)
+__global__ void bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b, float* __restrict__ y, long long n, int C,
+                                long long plane, int act, float alpha, float gain, float clamp) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        float v = x[i];
+        if (b) v += b[(i / plane) % C];
+        if (act == 1) v = v < 0.0f ? v * alpha : v;
+        v *= gain;
+        if (clamp >= 0.0f) v = fminf(fmaxf(v, -clamp), clamp);
+        y[i] = v;
+    }
+}
 }  // namespace
 }  // namespace mb
 
@@ -238,6 +281,29 @@ extern "C" int mb_frames_to_rgb24(const float* x, uint8_t* out, int B, int C, in
     const long long total = static_cast<long long>(B) * H * ((W + 3) / 4);
     const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     frames_to_rgb24_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, B, C, H, W, lo, 1.0f / (hi - lo));
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_upfirdn2d(const float* x, const float* f, float* y, int B, int C, int H, int W, int fh, int fw, int up, int down,
+                            int px0, int px1, int py0, int py1, float gain, mb_stream stream) {
+    MB_REQUIRE(x && f && y && B > 0 && C > 0 && H > 0 && W > 0 && fh > 0 && fw > 0 && up >= 1 && down >= 1, "mb_upfirdn2d: bad argument");
+    const int Ho = (H * up + py0 + py1 - fh) / down + 1, Wo = (W * up + px0 + px1 - fw) / down + 1;
+    MB_REQUIRE(H * up + py0 + py1 >= fh && W * up + px0 + px1 >= fw, "mb_upfirdn2d: the padded signal is smaller than the filter");
+    const long long total = static_cast<long long>(B) * C * Ho * Wo;
+    const int grid = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
+    // ops.py:106: f * gain^(ndim / 2) with a 2-D filter = f * gain
+    upfirdn2d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, f, y, B * C, H, W, fh, fw, up, down, px0, py0, Ho, Wo, gain);
+    MB_CUDA(cudaGetLastError());
+    return MB_OK;
+}
+
+extern "C" int mb_bias_act(const float* x, const float* b, float* y, int B, int C, int H, int W, int act, float alpha, float gain, float clamp,
+                           mb_stream stream) {
+    MB_REQUIRE(x && y && B > 0 && C > 0 && H > 0 && W > 0 && (act == 0 || act == 1), "mb_bias_act: bad argument (act: 0 linear, 1 lrelu)");
+    const long long n = static_cast<long long>(B) * C * H * W;
+    const int grid = static_cast<int>(n / 256 + 1 < 148 * 16 ? n / 256 + 1 : 148 * 16);
+    bias_act_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, b, y, n, C, static_cast<long long>(H) * W, act, alpha, gain, clamp);
     MB_CUDA(cudaGetLastError());
     return MB_OK;
 }

@@ -13,6 +13,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "sg2.h"
@@ -750,8 +752,32 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         cudaEventRecord(net->ev_pool[net->ev_used], stream);
         return net->ev_used++;
     };
+    // MB_NVTX=1: one NVTX range per stage of the forward (styles, input, conv Lk, filtered_lrelu Lk, resize, torgb) inside a
+    // range for the call, for timeline tools (tracing).  A range is opened when the previous stage's mark is passed.
+    static const bool nvtx_on = [] { const char* e = getenv("MB_NVTX"); return e && atoi(e) != 0; }();
+    if (nvtx_on) {
+        char nm[64];
+        snprintf(nm, sizeof(nm), "mb_net_forward B=%d", B);
+        nvtxRangePushA(nm);
+        nvtxRangePushA("styles");
+    }
+    auto nvtx_next = [&](int kind, int layer) {
+        if (!nvtx_on) return;
+        nvtxRangePop();
+        char nm[64];
+        if (kind == 0) snprintf(nm, sizeof(nm), "input");
+        else if (kind == 2) snprintf(nm, sizeof(nm), "filtered_lrelu L%d", layer);
+        else if (kind == 5) snprintf(nm, sizeof(nm), "done");
+        else snprintf(nm, sizeof(nm), "%s L%d", (layer + 1 < nl && net->layers[layer + 1].g.is_torgb) ? "torgb+output" : "modulated_conv2d", layer + 1);
+        nvtxRangePushA(nm);
+    };
+    struct NvtxClose {
+        bool on;
+        ~NvtxClose() { if (on) { nvtxRangePop(); nvtxRangePop(); } }
+    } nvtx_close{nvtx_on};
     int ev_prev = net->profile ? ev_next() : -1;
     auto prof_mark = [&](int kind, int layer) {
+        nvtx_next(kind, layer);
         if (!net->profile) return;
         const int e = ev_next();
         net->prof.push_back({kind, layer, ev_prev, e});

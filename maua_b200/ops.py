@@ -64,6 +64,64 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=2 
 
 
 # ---- image-space helpers (csrc/image_ops.cu) ---------------------------------------------------------------------
+def setup_filter(f=(1, 3, 3, 1)):
+    """inference/ops.py:236-256: 1-D taps -> normalised 2-D outer-product filter (host-sized constant)."""
+    f = torch.as_tensor(f, dtype=torch.float32)
+    f = torch.outer(f, f)
+    return f / f.sum()
+
+
+def upfirdn2d(x, f, up=1, down=1, padding=(0, 0, 0, 0), gain=1):
+    """inference/ops.py:87-114 on the device: x [B,C,H,W], f 2-D (or 1-D taps, applied separably = their outer product; None =
+    identity), padding [x0, x1, y0, y1]."""
+    lib = _lib.load()
+    x = _cuda_f32(x, "x")
+    gain = float(gain)
+    if f is None:
+        f = torch.ones(1, 1, device=x.device)
+    f = _cuda_f32(f, "f")
+    if f.ndim == 1:
+        f, gain = torch.outer(f, f).contiguous(), gain       # ops.py:109-111 applies the taps per axis, each scaled by gain^(1/2)
+    px0, px1, py0, py1 = [int(p) for p in padding]
+    B, Cc, H, W = x.shape
+    fh, fw = f.shape
+    up, down = int(up), int(down)
+    Ho = (H * up + py0 + py1 - fh) // down + 1
+    Wo = (W * up + px0 + px1 - fw) // down + 1
+    y = torch.empty(B, Cc, Ho, Wo, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(lib.mb_upfirdn2d(_lib.ptr(x), _lib.ptr(f), _lib.ptr(y), B, Cc, H, W, fh, fw, up, down, px0, px1, py0, py1, gain,
+                                    _lib.stream_ptr()))
+    return y
+
+
+def upsample2d(x, f, up=2, padding=0, gain=1):
+    """inference/ops.py:117-133."""
+    fw, fh = f.shape[-1], f.shape[0]
+    p = (padding + (fw + up - 1) // 2, padding + (fw - up) // 2, padding + (fh + up - 1) // 2, padding + (fh - up) // 2)
+    return upfirdn2d(x, f, up=up, padding=p, gain=gain * up * up)
+
+
+def bias_act(x, b=None, act="linear", alpha=None, gain=None, clamp=None):
+    """inference/ops.py:65-84 on the device (act: "linear" | "lrelu"; defaults alpha 0.2 and gain sqrt(2) for lrelu, :29-62)."""
+    if act not in ("linear", "lrelu"):
+        raise NotImplementedError(f"bias_act: activation '{act}' (built: linear, lrelu -- what the synthesis network uses)")
+    lib = _lib.load()
+    x4 = _cuda_f32(x, "x")
+    if x4.ndim != 4:
+        raise ValueError("bias_act: x must be [B, C, H, W]")
+    b = _cuda_f32(b, "b")
+    alpha = (0.2 if act == "lrelu" else 0.0) if alpha is None else float(alpha)
+    gain = (2 ** 0.5 if act == "lrelu" else 1.0) if gain is None else float(gain)
+    clamp = -1.0 if clamp is None else float(clamp)
+    B, Cc, H, W = x4.shape
+    y = torch.empty_like(x4)
+    with torch.cuda.device(x4.device):
+        _lib.check(lib.mb_bias_act(_lib.ptr(x4), _lib.ptr(b), _lib.ptr(y), B, Cc, H, W, int(act == "lrelu"), alpha, gain, clamp,
+                                   _lib.stream_ptr()))
+    return y
+
+
 def resize_bicubic(x, size, align_corners=False):
     """F.interpolate(x, size, mode="bicubic", align_corners=...) on the device kernels: x [N,C,h,w] -> [N,C,H,W]."""
     lib = _lib.load()

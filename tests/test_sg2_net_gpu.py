@@ -123,3 +123,40 @@ def test_render_api_sg2(cuda):
     assert [tuple(f.shape) for f in frames] == [(2, 3, 64, 64), (2, 3, 64, 64), (1, 3, 64, 64)]
     allf = torch.cat(frames)
     assert float(allf.min()) >= 0 and float(allf.max()) <= 1
+
+
+@pytest.mark.parametrize("case", [
+    # H, W, up, down, padding (x0, x1, y0, y1), gain
+    (16, 16, 1, 1, (1, 1, 1, 1), 1.0),
+    (9, 13, 2, 1, (2, 1, 2, 1), 4.0),       # upsample2d / the conv0 FIR of a synthesis block
+    (17, 17, 1, 1, (1, 1, 1, 1), 4.0),      # the FIR after the stride-2 transposed conv (ops.py:225)
+    (20, 14, 1, 2, (1, 1, 1, 1), 1.0),
+    (12, 12, 2, 2, (-1, 2, 3, -2), 1.0),    # negative padding crops
+])
+def test_upfirdn2d_op(cuda, case):
+    """mb_upfirdn2d (the op the fused kernel contains) against the oracle pinned to inference/ops.py:87-114."""
+    from maua_b200 import ops
+
+    H, W, up, down, pad, gain = case
+    g = torch.Generator().manual_seed(H * 31 + W)
+    x = torch.randn(2, 5, H, W, generator=g)
+    f = O.setup_filter()
+    ref = O.upfirdn2d(x, f, up=up, down=down, padding=pad, gain=gain)
+    got = ops.upfirdn2d(x.to(cuda), f.to(cuda), up=up, down=down, padding=pad, gain=gain).cpu()
+    assert got.shape == ref.shape
+    assert float((got - ref).abs().max()) <= 2e-6 * max(1.0, float(ref.abs().max()))
+    if up == 2 and down == 1 and pad == (2, 1, 2, 1):
+        assert torch.allclose(ops.upsample2d(x.to(cuda), f.to(cuda)).cpu(), O.upsample2d(x, f), atol=1e-5)
+
+
+@pytest.mark.parametrize("act,clamp", [("lrelu", 256.0), ("lrelu", 0.5), ("linear", None), ("linear", 1.0)])
+def test_bias_act_op(cuda, act, clamp):
+    from maua_b200 import ops
+
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7, 11, 13, generator=g) * 2
+    b = torch.randn(7, generator=g)
+    ref = O.bias_act(x, b, act=act, clamp=clamp)
+    got = ops.bias_act(x.to(cuda), b.to(cuda), act=act, clamp=clamp).cpu()
+    assert float((got - ref).abs().max()) <= 1e-6
+    assert torch.equal(ops.bias_act(x.to(cuda), None, act="linear").cpu(), x)

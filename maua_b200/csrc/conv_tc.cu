@@ -64,7 +64,19 @@ struct KArgs {
     // (L13: 0.51 ms product path; shift mode 0.46 ms without its stores, 0.70 ms with every store aimed at two planes,
     // 1.03-1.08 ms with the real 32-plane scatter, aligned or not; 0.90 ms with direct per-lane 4-byte stores).
     int shift, tile_wv;
+    unsigned int* absmax;  // device word or nullptr: atomicMax of the bits of max |y| over the stored outputs (read by the
+                           // following filtered_lrelu to prove its clamp inactive, flrelu_stream.cuh)
 };
+
+// running maximum of |y| in packed halves (one HMNMX2 per stored pair) and its hand-over at the end of an epilogue warp
+__device__ __forceinline__ void track_abs(__half2& m, const __half2& v) { m = __hmax2(m, __habs2(v)); }
+__device__ __forceinline__ void publish_abs(unsigned int* dst, const __half2& m) {
+    if (dst == nullptr) return;
+    float f = fmaxf(__low2float(m), __high2float(m));
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) f = fmaxf(f, __shfl_xor_sync(0xffffffffu, f, s));
+    if ((threadIdx.x & 31) == 0) atomicMax(dst, __float_as_uint(f));   // non-negative floats order like their bit patterns
+}
 
 template <int TW>
 __global__ void __launch_bounds__(256, 1)
@@ -233,6 +245,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         const int q = warp - 4;  // TMEM lane quadrant == warp % 4
         int acc = 0;
         uint32_t acc_ph = 0;
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             int r = t;
             const int mt = r % a.tiles_m; r /= a.tiles_m;
@@ -266,6 +279,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                     for (int k2 = 0; k2 < 16; ++k2) {
                         const __half2 hv = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k2]), scale, bias),
                                                              fmaf(__uint_as_float(v[2 * k2 + 1]), scale, bias));
+                        if (co_ok) track_abs(amax, hv);
                         pk[k2] = *reinterpret_cast<const uint32_t*>(&hv);
                     }
                     __syncwarp();  // the previous chunk's read-out is done
@@ -309,6 +323,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                                                             fmaf(__uint_as_float(v[g * 8 + 5]), scale, bias));
                             __half2 h3v = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 6]), scale, bias),
                                                             fmaf(__uint_as_float(v[g * 8 + 7]), scale, bias));
+                            track_abs(amax, h0v); track_abs(amax, h1v); track_abs(amax, h2v); track_abs(amax, h3v);
                             pk.x = *reinterpret_cast<uint32_t*>(&h0v);
                             pk.y = *reinterpret_cast<uint32_t*>(&h1v);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2v);
@@ -323,6 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             if (lane == 0) { mbar_arrive(&tempty[acc]); if (q == 0) dbg_inc(a.dbg, 2); }
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
+        publish_abs(a.absmax, amax);
     }
 
     tc_fence_before();
@@ -519,6 +535,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         float2* tab = sc_tab + q * 128;   // per-warp copy (one table shared under a named barrier measured 20 % slower)
         const int par = lane & 1;
         const uint32_t sel = par ? 0x3276u : 0x5410u;   // even lane keeps cout c of a pair, odd lane cout c+1
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         int acc = 0;
         uint32_t acc_ph = 0;
         int tab_b = -1;
@@ -557,6 +574,8 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         const float4 sb = *reinterpret_cast<const float4*>(tab + c0 + 2 * k);  // (d, bias) of couts c, c+1
                         const __half2 mine = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k]), sb.x, sb.y),
                                                                fmaf(__uint_as_float(v[2 * k + 1]), sb.z, sb.w));
+                        if (c0 + 2 * k + 1 < a.Cout) track_abs(amax, mine);
+                        else if (c0 + 2 * k < a.Cout) track_abs(amax, __halves2half2(__low2half(mine), __low2half(mine)));
                         const uint32_t m = *reinterpret_cast<const uint32_t*>(&mine);
                         const uint32_t o = __shfl_xor_sync(0xffffffffu, m, 1);
                         const uint32_t pr = __byte_perm(m, o, sel);
@@ -571,6 +590,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             if (lane == 0) mbar_arrive(&tempty[acc]);
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
+        publish_abs(a.absmax, amax);
     }
 
     tc_fence_before();
@@ -667,6 +687,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.d = p.d; a.bias = p.bias; a.y = p.y;
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
     a.dbg = debug_words_device();
+    a.absmax = p.absmax;
     a.a_tile_bytes = a_tile_bytes;
     a.resident = resident ? 1 : 0;
     a.nstages = nstages;

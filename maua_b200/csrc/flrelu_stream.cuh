@@ -65,6 +65,11 @@ struct StreamParams {
     int nsc, Rp;  // partial group: concurrent segments per item (16 / vlast), blocks per segment
     int n_full, n_total;
     float slope, clamp_pre, out_gain;
+    // Clamp guard: when the producer of the input recorded max |x| (bits of a non-negative float, written by the conv
+    // epilogue) and max |x| <= safe_abs, no intermediate can reach the clamp (|t| <= max|x| * (L1 norm of the up filter)^2),
+    // and the activation runs without its two clamp instructions.  nullptr = unknown: always clamp.
+    const unsigned int* in_absmax;
+    float safe_abs;
 };
 
 // ---- explicit shared-space accessors (32-bit shared addresses) ----
@@ -201,6 +206,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         }
         for (int i = 0; i < kCG * S::NRING; ++i) sbar_init(empty_a + S::NSB * 8 + 8 * i, 1);
         sts128(zero_a, make_uint4(0u, 0u, 0u, 0u));
+        for (int i = 0; i < S::NSB; ++i)   // no block staged yet: the write-out cursor starts LAG buffers behind and skips these
+            asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(desc_a + 8 * i), "r"(0xffffffffu), "r"(0u) : "memory");
         fence_barrier_init();
     }
     if (RAD) {
@@ -243,9 +250,14 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     int c_slot = 0;
     uint32_t c_par = 0;   // consume cursor of the ring
 
-    // ---- staging cursors ----
-    int s_sb = 0, w_sb = 0, nb = 0;       // nb: blocks staged so far by this CTA (same count in every warp)
-    uint32_t s_par = 0, w_par = 0;        // parity of the use count of the buffer at the cursor
+    // ---- staging cursors: buffer index and parity of its use count.  A fresh mbarrier passes a wait on parity 1, so neither
+    // cursor needs a "first round" case: the staging cursor waits for `empty` of use u - 1 (parity s_par ^ 1, passes at u = 0),
+    // the write-out cursor starts LAG buffers behind (use -1, parity 1: passes, finds an invalid descriptor, skips).
+    int s_sb = 0, w_sb = S::NSB - S::LAG;
+    uint32_t s_par = 0, w_par = 1;
+    // write-out constants of this lane: its ldmatrix row (channel chl of pixel group lane >> 4) and its 8 bytes of a pixel chunk
+    const int chl = 4 * ((lane & 7) >> 1) + (lane & 1) + 2 * ((lane >> 3) & 1);
+    const uint32_t pix = static_cast<uint32_t>(p.Cp_out) * 2u;
 
     // item state of the compute side
     int Rit = 0, blk = 0, islot = 0, oyb0 = 0;
@@ -254,40 +266,47 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     __half* yp = nullptr;   // PLANAR: this warp's plane at (first row of the segment, first column of the item)
     int rows_left = 0;      // PLANAR: image rows from the segment's first row down
 
+    // ldmatrix row of a lane: matrix (lane >> 3) = pixel group (lane >> 4), channel set (lane >> 3) & 1; its 8 rows are the
+    // channels {0,1,4,5,8,9,12,13} + 2 * set, so that a thread ends up with four ADJACENT channels of one pixel.
     auto writeout = [&]() {
         sbar_wait(full_a + 8 * w_sb, w_par);
         uint32_t dslot, doyb;
         asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(dslot), "=r"(doyb) : "r"(desc_a + 8 * w_sb));
-        const uint4 d0 = lds128(itab_a + 32 * dslot), d1 = lds128(itab_a + 32 * dslot + 16);
-        const int dv = d0.z, dnsc = d0.w, dox0 = d1.x, dsegrows = d1.y;
-        // ldmatrix row of this lane: matrix (lane >> 3) = pixel group (lane >> 4), channel set (lane >> 3) & 1; its 8 rows are
-        // the channels {0,1,4,5,8,9,12,13} + 2 * set, so that a thread ends up with four ADJACENT channels of one pixel.
-        const int chl = 4 * ((lane & 7) >> 1) + (lane & 1) + 2 * ((lane >> 3) & 1);
-        const bool real = chl < dv;
-        const uint32_t buf = stg + w_sb * kBufBytes;
-        // byte offsets inside the frame fit 32 bits (a 1044^2 x 96-channel map is 209 MB): one 64-bit add per store
-        uint8_t* base = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(d0.y) << 32) | d0.x);
-        const uint32_t pix = static_cast<uint32_t>(p.Cp_out) * 2u;
-        const uint32_t lane_off = 8u * (lane & 3) + static_cast<uint32_t>(lane >> 2) * pix;
-        const int ox = dox0 + (lane >> 2);
-        for (int t = 0; t < dnsc; ++t) {
-            const int r = warp * dnsc + t;
-            const int q = r >> 4, yr = r & 15;
-            const int oy = static_cast<int>(doyb) + q * dsegrows + yr;
-            if (oy < p.Hout) {   // warp-uniform
-                const uint32_t a = real ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a;
+        if (dslot != 0xffffffffu) {
+            const uint4 d0 = lds128(itab_a + 32 * dslot);
+            uint8_t* base = reinterpret_cast<uint8_t*>((static_cast<unsigned long long>(d0.y) << 32) | d0.x);
+            const int dv = d0.z & 0xffff, dnsc = d0.z >> 16, dox0 = d0.w & 0xffff, dsegrows = d0.w >> 16;
+            const uint32_t buf = stg + w_sb * kBufBytes;
+            // byte offsets inside the frame fit 32 bits (a 1044^2 x 96-channel map is 209 MB): one 64-bit add per store
+            const uint32_t lane_off = 8u * (lane & 3) + static_cast<uint32_t>(lane >> 2) * pix;
+            const int ox = dox0 + (lane >> 2);
+            auto row_out = [&](int oy, uint32_t a, uint32_t hstep) {
                 const uint32_t off = static_cast<uint32_t>(oy) * static_cast<uint32_t>(p.Wout) * pix + lane_off;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     uint32_t r4[4];
-                    ldsm_x4_trans(real ? a + h * 32 : a, r4);
+                    ldsm_x4_trans(a + h * hstep, r4);
                     if (ox + h * 16 < p.Wout) stg64(base + (off + (h * 16) * pix), r4[0], r4[1]);
                     if (ox + h * 16 + 8 < p.Wout) stg64(base + (off + (h * 16 + 8) * pix), r4[2], r4[3]);
                 }
+            };
+            if (dnsc == 1) {
+                // a full group: warp w writes image row w of the block, plane = channel
+                const int oy = static_cast<int>(doyb) + warp;
+                if (oy < p.Hout) row_out(oy, buf + chl * kPlaneBytes + warp * (kSP * 2) + (lane >> 4) * 16, 32u);
+            } else {
+                const bool real = chl < dv;
+                for (int t = 0; t < dnsc; ++t) {
+                    const int r = warp * dnsc + t;
+                    const int q = r >> 4, yr = r & 15;
+                    const int oy = static_cast<int>(doyb) + q * dsegrows + yr;
+                    if (oy < p.Hout)   // warp-uniform
+                        row_out(oy, real ? buf + (q * dv + chl) * kPlaneBytes + yr * (kSP * 2) + (lane >> 4) * 16 : zero_a, real ? 32u : 0u);
+                }
             }
+            __syncwarp();
+            if (lane == 0) sbar_arrive(empty_a + 8 * w_sb);
         }
-        __syncwarp();
-        if (lane == 0) sbar_arrive(empty_a + 8 * w_sb);
         if (++w_sb == S::NSB) { w_sb = 0; w_par ^= 1; }
     };
 
@@ -311,7 +330,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             __syncwarp();
             ++blk;
         } else {
-            if (nb >= S::NSB) sbar_wait(empty_a + 8 * s_sb, s_par ^ 1);
+            sbar_wait(empty_a + 8 * s_sb, s_par ^ 1);
             if (valid) {
                 const uint32_t pl = stg + s_sb * kBufBytes + warp * kPlaneBytes;
 #pragma unroll
@@ -325,21 +344,21 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             __syncwarp();
             if (lane == 0) sbar_arrive(full_a + 8 * s_sb);
             if (++s_sb == S::NSB) { s_sb = 0; s_par ^= 1; }
-            ++nb;
             ++blk;
-            if (nb > S::LAG) writeout();
+            writeout();
         }
     };
 
     // ---- the chain ----
     constexpr int NSET = RAD ? 2 : 1;   // separable filter: one block of accumulators (k-step 2 of block i-1 is finished and
                                         // staged before k-step 0 of block i overwrites it); radial: both accumulate over the terms
+    uint32_t x_box = xlane;   // this lane's S1 read address inside the ring box at the consume cursor
     uint32_t P1[2][kMB][2];   // packed A1^T of the two input-row blocks under the current strip
     float OUT[NSET][4][4];
 
     // S1 of one 8-row input block at byte offset `off` inside the current ring box
     auto s1 = [&](uint32_t (&P)[kMB][2], int off) {
-        const uint32_t a = xlane + c_slot * S::BOXBYTES + off;
+        const uint32_t a = x_box + off;
 #pragma unroll
         for (int m = 0; m < kMB; ++m) {
             const uint32_t b0 = lds32(a + K::wblk(m) * 16), b1 = lds32(a + K::wblk(m) * 16 + 16);
@@ -347,19 +366,28 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         }
     };
     auto box_wait = [&]() { sbar_wait(xbar_a + 8 * c_slot, c_par); };
+    auto box_next = [&]() {
+        x_box += S::BOXBYTES;
+        if (++c_slot == S::NRING) { c_slot = 0; c_par ^= 1; x_box = xlane; }
+    };
     auto box_release = [&]() {
         __syncwarp();   // every lane has its operands: the slot can take the next box of the sequence
         if (lane == 0 && l_left >= 0) refill(c_slot);
-        if (++c_slot == S::NRING) { c_slot = 0; c_par ^= 1; }
+        box_next();
     };
     // S2 (+activation) of one strip
-    auto s2 = [&](const uint4& A, uint32_t (&Pa)[kMB][2], uint32_t (&Pb)[kMB][2], uint32_t (&P2)[kJB][2]) {
+    auto s2 = [&](auto FASTc, const uint4& A, uint32_t (&Pa)[kMB][2], uint32_t (&Pb)[kMB][2], uint32_t (&P2)[kJB][2]) {
 #pragma unroll
         for (int n8 = 0; n8 < kJB; ++n8) {
             uint32_t t2[2];
             mma16816_h(t2, A, Pa[n8 >> 1][n8 & 1], Pb[n8 >> 1][n8 & 1]);
-            P2[n8][0] = lrelu_clamp2(t2[0], LC.sl2, LC.cl2);
-            P2[n8][1] = lrelu_clamp2(t2[1], LC.sl2, LC.cl2);
+            if constexpr (decltype(FASTc)::value) {
+                P2[n8][0] = lrelu2(t2[0], LC.sl2);
+                P2[n8][1] = lrelu2(t2[1], LC.sl2);
+            } else {
+                P2[n8][0] = lrelu_clamp2(t2[0], LC.sl2, LC.cl2);
+                P2[n8][1] = lrelu_clamp2(t2[1], LC.sl2, LC.cl2);
+            }
         }
     };
     // S3: P3 = packed O3^T of the strip, the B operands of S4
@@ -406,7 +434,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     };
     // Output block i of the running segment: strips 2i (which also finishes block i-1) and 2i+1.  PAR = i & 1 selects the
     // P1 slots (up=4) and the accumulator set (radial).  Returns true after the last strip of the segment.
-    auto block_iter = [&](auto PARc, int i) -> bool {
+    auto block_iter = [&](auto PARc, auto FASTc, int i) -> bool {
         constexpr int PAR = decltype(PARc)::value;
         constexpr int CUR = RAD ? PAR : 0, PRV = RAD ? (PAR ^ 1) : 0;
         uint32_t P2[kJB][2];
@@ -414,12 +442,12 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         if constexpr (UP == 2) {
             s1(P1[1], kRowBlk * kXP * 2);                // input block 2i+1: second half of box i
             box_release();
-            s2(LC.AU[0], P1[0], P1[1], P2);
+            s2(FASTc, LC.AU[0], P1[0], P1[1], P2);
         } else {
             box_wait();
             s1(P1[PAR ^ 1], 0);                          // input block i+1
             box_release();
-            s2(LC.AU[0], P1[PAR], P1[PAR ^ 1], P2);
+            s2(FASTc, LC.AU[0], P1[PAR], P1[PAR ^ 1], P2);
         }
         const bool last = i == Rit;
         if constexpr (!RAD) {
@@ -442,9 +470,9 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         if constexpr (UP == 2) {
             box_wait();
             s1(P1[0], 0);                                // input block 2i+2: first half of box i+1
-            s2(LC.AU[0], P1[1], P1[0], P2);
+            s2(FASTc, LC.AU[0], P1[1], P1[0], P2);
         } else {
-            s2(LC.AU[1], P1[PAR], P1[PAR ^ 1], P2);
+            s2(FASTc, LC.AU[1], P1[PAR], P1[PAR ^ 1], P2);
         }
         if constexpr (!RAD) {
             uint32_t P3[4][2];
@@ -457,6 +485,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         return false;
     };
 
+    const bool no_clamp = p.in_absmax != nullptr && __uint_as_float(*p.in_absmax) <= p.safe_abs;   // uniform over the grid
     int nitem = 0;
     for (int item = blockIdx.x; item < p.n_total; item += G, ++nitem) {
         int c, oy0;
@@ -478,8 +507,8 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
                     // where this item's blocks go: channels-last address of (frame, row 0, first column, first channel)
                     const unsigned long long base = reinterpret_cast<unsigned long long>(p.y) +
                         ((static_cast<long long>(it.b) * p.Hout * p.Wout + it.tx * kOT) * p.Cp_out + it.c0) * 2;
-                    sts128(itab_a + 32 * islot, make_uint4(static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32), it.v, it.nsc));
-                    sts128(itab_a + 32 * islot + 16, make_uint4(it.tx * kOT, it.segrows, 0, 0));
+                    sts128(itab_a + 32 * islot, make_uint4(static_cast<uint32_t>(base), static_cast<uint32_t>(base >> 32),
+                                                           it.v | (it.nsc << 16), (it.tx * kOT) | (it.segrows << 16)));
                 }
             }
         }
@@ -487,15 +516,19 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             box_wait();
             s1(P1[0], 0);   // input block 0
             if constexpr (UP == 4) box_release();
-            if constexpr (UP == 2 && !RAD) {
-                for (int i = 0;; ++i)
-                    if (block_iter(std::integral_constant<int, 0>(), i)) break;
-            } else {
-                for (int i = 0;; i += 2) {
-                    if (block_iter(std::integral_constant<int, 0>(), i)) break;
-                    if (block_iter(std::integral_constant<int, 1>(), i + 1)) break;
+            auto column = [&](auto FASTc) {
+                if constexpr (UP == 2 && !RAD) {
+                    for (int i = 0;; ++i)
+                        if (block_iter(std::integral_constant<int, 0>(), FASTc, i)) break;
+                } else {
+                    for (int i = 0;; i += 2) {
+                        if (block_iter(std::integral_constant<int, 0>(), FASTc, i)) break;
+                        if (block_iter(std::integral_constant<int, 1>(), FASTc, i + 1)) break;
+                    }
                 }
-            }
+            };
+            if (no_clamp) column(std::true_type());
+            else column(std::false_type());
         } else if (!PLANAR) {
             // no share in this item: keep the staging protocol in step (and take part in the write-out)
             float dummy[4][4];
@@ -503,8 +536,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         }
     }
     if constexpr (!PLANAR) {
-        const int pending = nb < S::LAG ? nb : S::LAG;
-        for (int k = 0; k < pending; ++k) writeout();
+        for (int k = 0; k < S::LAG; ++k) writeout();
     }
 }
 

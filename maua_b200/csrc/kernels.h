@@ -32,6 +32,7 @@ struct ConvTcArgs {
                            // (correct, measured slower than per-kw loads: see KArgs::shift in conv_tc.cu)
     int narrow_a = 1;      // Cout <= 128: load only ceil8(Cout) weight rows per tile and keep them resident when they fit
     int num_sms;
+    unsigned int* absmax = nullptr;  // device word (zeroed by the caller): atomicMax of the bits of max |y| over the stored outputs
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);
 int conv_tc_smem_bytes(int tw);
@@ -133,6 +134,7 @@ struct FlreluArgs {
     int px0, py0;        // leading padding of the zero-inserted signal (may be negative = crop)
     float gain, slope, clamp;
     int num_sms;
+    const unsigned int* in_absmax = nullptr;  // device word: bits of max |x| over the input (ConvTcArgs::absmax), or nullptr
 };
 int flrelu_launch(const FlreluArgs& a, cudaStream_t stream);
 // impl: 0 = best available (tensor-core chain), 1 = generic loops, 2 = CUDA-core polyphase kernel

@@ -566,7 +566,8 @@ WsLayout ws_layout(const mb_net* net, int B, const SizePlan& sp) {
     size_t off = 0;
     w.styles_off = off; off = round_up_sz(off + ns * sizeof(float), 1024);
     w.d_off = off; off = round_up_sz(off + nd * sizeof(float), 1024);
-    w.scratch_off = off; off = round_up_sz(off + static_cast<size_t>(B) * net->in_channels * 4 * sizeof(float), 1024);
+    // scratch: [B][C][4] floats of the input layer, then one word per layer for the conv's max |y| (clamp guard of the filter)
+    w.scratch_off = off; off = round_up_sz(off + static_cast<size_t>(B) * net->in_channels * 4 * sizeof(float) + kMaxLayers * sizeof(unsigned int), 1024);
     w.x_off = off; off = round_up_sz(off + max_x * sizeof(__half), 1024);
     w.x2_off = off;
     if (net->resize_mode != MB_RESIZE_NONE) off = round_up_sz(off + max_x * sizeof(__half), 1024);
@@ -732,6 +733,8 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
     float* styles = reinterpret_cast<float*>(base + wl.styles_off);
     float* dco = reinterpret_cast<float*>(base + wl.d_off);
     float* scratch = reinterpret_cast<float*>(base + wl.scratch_off);
+    unsigned int* absmax = reinterpret_cast<unsigned int*>(scratch + static_cast<size_t>(B) * net->in_channels * 4);
+    MB_CUDA(cudaMemsetAsync(absmax, 0, kMaxLayers * sizeof(unsigned int), stream));
     __half* X = reinterpret_cast<__half*>(base + wl.x_off);
     __half* X2 = reinterpret_cast<__half*>(base + wl.x2_off);
     __half* Y = reinterpret_cast<__half*>(base + wl.y_off);
@@ -923,6 +926,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         ca.pm_shift = net->conv_pm_shift;
         ca.cm_shift = net->conv_cm_shift;
         ca.num_sms = g_num_sms;
+        ca.absmax = net->conv_impl == 0 ? absmax + i : nullptr;
         r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         if (r != MB_OK) return r;
         launches += 1;
@@ -945,6 +949,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         fa.gain = sqrtf(2.0f); fa.slope = 0.2f;
         fa.clamp = static_cast<float>(net->cfg.conv_clamp);
         fa.num_sms = g_num_sms;
+        fa.in_absmax = ca.absmax;
         // Layers that feed another conv write channels-last straight from the tensor-core kernel; the
         // fallback kernels (and the last layer, whose consumer is the planar ToRGB kernel) write planar.
         const bool next_is_conv = !net->layers[i + 1].g.is_torgb;

@@ -227,3 +227,20 @@ def test_per_frame_transform_for_a_single_frame(cuda):
     assert torch.equal(one, batch[2:3])
     one_col = S.forward(ws[1:2], translation=tr[1:2], rotation=rot[1:2, None]).clone()    # rotation as [1,1]
     assert torch.equal(one_col, batch[1:2])
+
+
+def test_clamp_guard_follows_the_activations(cuda):
+    """The conv epilogue records max |y|; the following filter clamps only when that maximum can reach the clamp.  A layer
+    whose bias pushes the activations past conv_clamp = 256 must still match the oracle (the guard selects the clamping
+    variant for it), and so must the untouched network (guard selects the clamp-free variant)."""
+    onet, net = make_pair("T", 256, channel_base=8192, channel_max=128)
+    torch.manual_seed(12)
+    ws = torch.randn(1, net.num_ws, 512)
+    assert float((pix(net(ws.to(cuda))) - pix(onet(ws))).abs().max()) <= PIX_TOL
+    name = net.layer_names[3]
+    with torch.no_grad():
+        getattr(net, name).bias.add_(400.0)
+        getattr(onet, name).bias.add_(400.0)
+    ref = onet(ws)
+    out = net(ws.to(cuda))
+    assert float((pix(out) - pix(ref)).abs().max()) <= PIX_TOL

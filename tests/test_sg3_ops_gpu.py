@@ -130,3 +130,31 @@ def test_filtered_lrelu_stream(cuda, case, layout, monkeypatch):
     assert torch.isfinite(got).all()
     assert _rel_err(got, ref) < 1e-2
     assert torch.equal(got, tile), f"stream vs tile kernels differ: max {float((got - tile).abs().max()):.3e}"
+
+
+def test_filtered_lrelu_clamp_guard(cuda, monkeypatch):
+    """The streaming kernel drops the two clamp instructions of its activation when the producer's recorded max |x| proves the
+    clamp inactive.  On inputs far below the clamp the guarded and the clamping variants must agree bit for bit; on inputs
+    that do reach the clamp, the clamping variant (what an unknown or large maximum selects) must match the oracle."""
+    from maua_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    fu = O.design_lowpass_filter(12, 8.0, 9.0, 64.0)
+    fd = O.design_lowpass_filter(12, 8.0, 9.0, 64.0)
+    kw = dict(up=2, down=2, padding=[9, 8, 9, 8], gain=np.sqrt(2), slope=0.2, clamp=256)
+    monkeypatch.setenv("MB_FLRELU_IMPL", "0")
+    monkeypatch.setenv("MB_FLRELU_STREAM", "1")
+    for layout in ("0", "1"):
+        monkeypatch.setenv("MB_FLRELU_TEST_NHWC", layout)
+        x = (torch.randn(2, 32, 70, 50, generator=g) * 2).half().float()
+        b = torch.randn(32, generator=g)
+        args = (x.to(cuda), fu.to(cuda), fd.to(cuda), b.to(cuda))
+        monkeypatch.setenv("MB_FLRELU_ASSUME_SAFE", "1")
+        fast = ops.filtered_lrelu(*args, **kw)
+        monkeypatch.setenv("MB_FLRELU_ASSUME_SAFE", "0")
+        safe = ops.filtered_lrelu(*args, **kw)
+        assert torch.equal(fast, safe)
+    big = (torch.randn(1, 16, 40, 40, generator=g) * 150).half().float()      # reaches +-256 / sqrt(2) after up-sampling
+    ref = O.filtered_lrelu_ref(big, fu=fu, fd=fd, b=None, **kw)
+    got = ops.filtered_lrelu(big.to(cuda), fu.to(cuda), fd.to(cuda), None, **kw)
+    assert float(ref.abs().max()) > 100 and _rel_err(got, ref) < 1e-2

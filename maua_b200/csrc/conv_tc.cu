@@ -574,8 +574,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         const float4 sb = *reinterpret_cast<const float4*>(tab + c0 + 2 * k);  // (d, bias) of couts c, c+1
                         const __half2 mine = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k]), sb.x, sb.y),
                                                                fmaf(__uint_as_float(v[2 * k + 1]), sb.z, sb.w));
-                        if (c0 + 2 * k + 1 < a.Cout) track_abs(amax, mine);
-                        else if (c0 + 2 * k < a.Cout) track_abs(amax, __halves2half2(__low2half(mine), __low2half(mine)));
+                        track_abs(amax, mine);   // padded couts carry (d, bias) = (0, 0): they contribute |0|
                         const uint32_t m = *reinterpret_cast<const uint32_t*>(&mine);
                         const uint32_t o = __shfl_xor_sync(0xffffffffu, m, 1);
                         const uint32_t pr = __byte_perm(m, o, sel);

@@ -1045,7 +1045,9 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
                 MB_CUDA(cudaMalloc(&zero_word, 4));
                 MB_CUDA(cudaMemset(zero_word, 0, 4));
             }
-            sp.in_absmax = a.in_absmax ? a.in_absmax : (assume_safe ? zero_word : nullptr);
+            const char* gev = getenv("MB_FLRELU_GUARD");          // MB_FLRELU_GUARD=0: ignore the recorded maximum, always clamp
+            const bool use_guard = !(gev && atoi(gev) == 0);
+            sp.in_absmax = (a.in_absmax && use_guard) ? a.in_absmax : (assume_safe ? zero_word : nullptr);
             const double lim = fmin(static_cast<double>(p.clamp_pre), 60000.0);
             sp.safe_abs = static_cast<float>(lim / (L * L * 1.01));
         }

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
                     if (ox + h * 16 + 8 < p.Wout) stg64(base + (off + (h * 16 + 8) * pix), r4[2], r4[3]);
                 }
             };
-            if (dnsc == 1) {
+            if (dv == kCG) {
                 // a full group: warp w writes image row w of the block, plane = channel
                 const int oy = static_cast<int>(doyb) + warp;
                 if (oy < p.Hout) row_out(oy, buf + chl * kPlaneBytes + warp * (kSP * 2) + (lane >> 4) * 16, 32u);

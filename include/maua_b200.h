@@ -176,7 +176,8 @@ int mb_net_last_launch_count(const mb_net* net);
 /* 0 = tcgen05 tensor-core conv (product path), 1 = plain CUDA-core conv (bisecting aid for the
  * parity tests; never used by the host facade). */
 int mb_net_set_conv_impl(mb_net* net, int impl);
-/* Test / tuning knobs: "conv_impl" (0|1), "conv_tile_w" (32|16), "flrelu_impl" (0 auto | 1 generic),
+/* Test / tuning knobs: "sg2_precise" (StyleGAN2 handles; 1 default: fp16 hi + lo operands and conv outputs = fp32-class
+ * pixels, 0: plain fp16 operands, 3x fewer MACs), "conv_impl" (0|1), "conv_tile_w" (32|16), "flrelu_impl" (0 auto | 1 generic),
  * "debug_stop" (stop the forward after layer N; -1 = after the input layer; default: run all),
  * "profile" (0 off | 1 record per-launch CUDA events of the last forward | 2 accumulate over forwards),
  * "profile_reset" (drop accumulated records). */

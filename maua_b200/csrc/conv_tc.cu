@@ -64,6 +64,8 @@ struct KArgs {
     // (L13: 0.51 ms product path; shift mode 0.46 ms without its stores, 0.70 ms with every store aimed at two planes,
     // 1.03-1.08 ms with the real 32-plane scatter, aligned or not; 0.90 ms with direct per-lane 4-byte stores).
     int shift, tile_wv;
+    long long lo_off;      // > 0: split output -- y holds fp16(v), y + lo_off holds fp16(v - fp16(v)) (fp32-class precision for
+                           // consumers that add the two; cout-major tile without shift only)
     unsigned int* absmax;  // device word or nullptr: atomicMax of the bits of max |y| over the stored outputs (read by the
                            // following filtered_lrelu to prove its clamp inactive, flrelu_stream.cuh)
 };
@@ -329,6 +331,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                             pk.z = *reinterpret_cast<uint32_t*>(&h2v);
                             pk.w = *reinterpret_cast<uint32_t*>(&h3v);
                             *reinterpret_cast<uint4*>(yplane + static_cast<long long>(h) * a.Wp_out + w) = pk;
+                            if (a.lo_off > 0) {
+                                // the part of each value its fp16 rounding dropped, as a second fp16 plane
+                                const __half2 hs[4] = {h0v, h1v, h2v, h3v};
+                                uint32_t lo[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 hf = __half22float2(hs[k]);
+                                    const __half2 l2 = __floats2half2_rn(fmaf(__uint_as_float(v[g * 8 + 2 * k]), scale, bias) - hf.x,
+                                                                         fmaf(__uint_as_float(v[g * 8 + 2 * k + 1]), scale, bias) - hf.y);
+                                    lo[k] = *reinterpret_cast<const uint32_t*>(&l2);
+                                }
+                                *reinterpret_cast<uint4*>(yplane + a.lo_off + static_cast<long long>(h) * a.Wp_out + w) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                            }
                         }
                     }
                 }
@@ -616,7 +631,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     const int pad = p.pad;
     const int halo = p.ksz - 1;
     MB_REQUIRE(pad >= 0 && pad <= halo, "conv_tc: padding %d unsupported for kernel size %d", pad, p.ksz);
-    MB_REQUIRE(p.ksz == 1 || p.ksz == 3, "conv_tc: kernel size %d unsupported", p.ksz);
+    MB_REQUIRE(p.ksz >= 1 && p.ksz <= 3, "conv_tc: kernel size %d unsupported", p.ksz);
     MB_REQUIRE(p.Cp_in % 8 == 0 && p.Wp_out % 8 == 0, "conv_tc: channel / row pitch must be a multiple of 8 elements");
     MB_REQUIRE((reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(p.wpk) & 15) == 0,
@@ -633,6 +648,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     // shift mode (one patch load per chunk, see KArgs) needs resident weights and room for its epilogue staging tiles
     const bool want_shift = !pixel_major && p.cm_shift && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
                             w_all + 2 * patch_bytes + 1024 + 256 + kEpiStageBytes <= kSmemMax;
+    MB_REQUIRE(p.split_lo_off <= 0 || (!pixel_major && !want_shift), "conv_tc: the split output needs the plain cout-major tile");
     const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (want_shift ? kEpiStageBytes : 0);
     const bool resident = p.narrow_a && Mp == kTileM && w_all + 2 * patch_bytes + fixed_bytes <= kSmemMax;
     const int stage_alloc = patch_bytes + (resident ? 0 : p.ksz * a_tile_bytes);
@@ -687,6 +703,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
     a.dbg = debug_words_device();
     a.absmax = p.absmax;
+    a.lo_off = p.split_lo_off;
     a.a_tile_bytes = a_tile_bytes;
     a.resident = resident ? 1 : 0;
     a.nstages = nstages;

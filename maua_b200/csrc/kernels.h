@@ -32,6 +32,7 @@ struct ConvTcArgs {
                            // (correct, measured slower than per-kw loads: see KArgs::shift in conv_tc.cu)
     int narrow_a = 1;      // Cout <= 128: load only ceil8(Cout) weight rows per tile and keep them resident when they fit
     int num_sms;
+    long long split_lo_off = 0;      // > 0: also store fp16(v - fp16(v)) at y + split_lo_off (needs the cout-major tile: pm_max_cout = 0, cm_shift = 0)
     unsigned int* absmax = nullptr;  // device word (zeroed by the caller): atomicMax of the bits of max |y| over the stored outputs
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);

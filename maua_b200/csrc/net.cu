@@ -650,6 +650,10 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
         net->conv_impl = value;
         if (net->sg2) sg2_set_conv_impl(net->sg2, value);
     }
+    else if (k == "sg2_precise") {
+        MB_REQUIRE(net->sg2, "mb_net_set_option: sg2_precise needs a StyleGAN2 handle");
+        sg2_set_precise(net->sg2, value);
+    }
     else if (k == "conv_tile_w") net->conv_tile_w = value == 16 ? 16 : 32;
     else if (k == "conv_pm_max") net->conv_pm_max = value;
     else if (k == "conv_narrow_a") net->conv_narrow_a = value;

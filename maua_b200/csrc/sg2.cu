@@ -5,9 +5,17 @@
 //
 // Per block (resolution r):  conv0 = stride-2 transposed 3x3 modulated conv + 4x4 FIR  ->  conv1 = 3x3 'same'
 // modulated conv  ->  ToRGB 1x1 (no demodulation) added to the FIR-upsampled image of the previous block.
-//   * both 3x3 convs run on the tcgen05 implicit-GEMM kernel (conv_tc.cu): conv1 with padding 1; conv0 as a
-//     stride-1 'full' convolution with spatially flipped taps over the zero-inserted input (identical arithmetic
-//     to conv_transpose2d(stride 2), ops.py:224);
+//   * both 3x3 convs run on the tcgen05 implicit-GEMM kernel (conv_tc.cu): conv1 with padding 1; conv0 = the stride-2
+//     transposed conv (ops.py:213-230) in POLYPHASE form: the four output parities (row, column even / odd) are four
+//     2x2 kernels over the un-inserted input -- taps {0,2}x{0,2}, {0,2}x{1}, {1}x{0,2}, {1}x{1} of the flipped 3x3
+//     kernel -- run as ONE 2x2 'full' convolution with 4*Cout output channels (phase-major); no zero-inserted copy of
+//     the input exists and no MAC lands on an inserted zero (16 instead of 36 multiply-adds per input pixel, channel
+//     pair and output channel);
+//   * precision (`precise`, default on): activations and weights go to the tensor core as fp16 hi + lo pairs --
+//     x*w = xh*wh + xl*wh + xh*wl as one contraction over 3*Cp channels [xh | xl | xh] x [wh | wh | wl], products exact
+//     in the fp32 accumulator -- and the conv output leaves as an fp16 hi / lo plane pair, so the whole path carries
+//     fp32-class values.  A random-init StyleGAN2 image swings over +-30: the reference's 1e-3 pixel tolerance asks
+//     for ~3e-5 of that range, which fp16 storage (5e-4) cannot hold.  `precise` off = plain fp16 operands (3x fewer MACs);
 //   * everything between two convs is ONE fused kernel (sg2_act_kernel): [4x4 FIR, gain 4] + noise + bias +
 //     leaky-ReLU*sqrt2 + clamp (bias_act), the next conv's style and the planar -> channels-last store, plus the
 //     ToRGB reduction over channels and the skip-image accumulation.
@@ -30,26 +38,60 @@ namespace {
 
 inline int cpad16(int c) { return (c + 15) / 16 * 16; }
 
-// x channels-last [B][h][w][Cp] -> zero-inserted [B][2h-1][2w-1][Cp] (uint4 = 8 channels per thread)
-__global__ void zero_insert_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int h, int w, int cp8) {
-    const int H2 = 2 * h - 1, W2 = 2 * w - 1;
-    const long long total = static_cast<long long>(B) * H2 * W2 * cp8;
+// Effective fp32 weights of one 3x3 layer for the conv kernel: out [Cout'][ns * Cp][k'][k'].
+//   phase = 0: k' = 3, Cout' = Cout, out = w.
+//   phase = 1: k' = 2, Cout' = 4 * Cout: output channel (pa * 2 + pb) * Cout + co holds the 2x2 kernel of output parity
+//              (pa, pb) of the stride-2 transposed conv: tap (a', b') = flipped tap (row(pa, a'), col(pb, b')) with
+//              row(0, .) = {0, 2}, row(1, .) = {none, 1} (a' = 0 reads input row u - 1, a' = 1 row u).
+//   ns = 3 (precise): channel blocks [w | w | w - fp16(w)]; the fp16 packing that follows turns them into [wh | wh | wl].
+__global__ void sg2_prep_weights_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int Cp, int phase, int ns) {
+    const int kk = phase ? 2 : 3, Co = phase ? 4 * Cout : Cout, Ci = ns * Cp;
+    const long long total = static_cast<long long>(Co) * Ci * kk * kk;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int c = static_cast<int>(idx % cp8);
-        long long r = idx / cp8;
-        const int X = static_cast<int>(r % W2); r /= W2;
-        const int Y = static_cast<int>(r % H2);
-        const int b = static_cast<int>(r / H2);
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (!(X & 1) && !(Y & 1)) v = x[((static_cast<long long>(b) * h + (Y >> 1)) * w + (X >> 1)) * cp8 + c];
-        y[idx] = v;
+        const int b = static_cast<int>(idx % kk);
+        long long r = idx / kk;
+        const int a = static_cast<int>(r % kk); r /= kk;
+        const int cq = static_cast<int>(r % Ci);
+        const int cop = static_cast<int>(r / Ci);
+        const int part = cq / Cp, ci = cq - part * Cp;
+        float v = 0.0f;
+        if (ci < Cin) {
+            if (!phase) {
+                v = w[((static_cast<long long>(cop) * Cin + ci) * 3 + a) * 3 + b];
+            } else {
+                const int ph = cop / Cout, co = cop - ph * Cout, pa = ph >> 1, pb = ph & 1;
+                const int fr = pa ? (a == 1 ? 1 : -1) : (a == 0 ? 0 : 2);   // row of the flipped kernel wf[r][c] = w[2 - r][2 - c]
+                const int fc = pb ? (b == 1 ? 1 : -1) : (b == 0 ? 0 : 2);
+                if (fr >= 0 && fc >= 0) v = w[((static_cast<long long>(co) * Cin + ci) * 3 + (2 - fr)) * 3 + (2 - fc)];
+            }
+            if (part == 2) v -= __half2float(__float2half_rn(v));
+        }
+        out[idx] = v;
+    }
+}
+// wsqT [Cin][Cout] -> [Cin][4 * Cout] (the four parities of a transposed conv share the demodulation coefficient)
+__global__ void sg2_tile4_kernel(const float* __restrict__ in, float* __restrict__ out, int Cin, int Cout) {
+    const int total = Cin * 4 * Cout;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int o = idx % (4 * Cout), i = idx / (4 * Cout);
+        out[idx] = in[i * Cout + o % Cout];
     }
 }
 
-// const [C][r][r] f32 * style[b][c] -> channels-last fp16 [B][r][r][Cp]
+// one activation value -> its channels-last slots: fp16(v) at c (and at 2 Cp + c), fp16(v - fp16(v)) at Cp + c when ns == 3
+__device__ __forceinline__ void put_split(__half* px, int c, int Cp, int ns, float v) {
+    const __half h = __float2half_rn(v);
+    px[c] = h;
+    if (ns == 3) {
+        px[Cp + c] = __float2half_rn(v - __half2float(h));
+        px[2 * Cp + c] = h;
+    }
+}
+
+// const [C][r][r] f32 * style[b][c] -> channels-last fp16 [B][r][r][ns * Cp]
 __global__ void const_input_kernel(const float* __restrict__ cst, const float* __restrict__ style, __half* __restrict__ out,
-                                   int B, int C, int r, int Cp) {
+                                   int B, int C, int r, int Cp, int ns) {
     const long long total = static_cast<long long>(B) * r * r * Cp;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -57,12 +99,15 @@ __global__ void const_input_kernel(const float* __restrict__ cst, const float* _
         long long q = idx / Cp;
         const int px = static_cast<int>(q % (r * r));
         const int b = static_cast<int>(q / (r * r));
-        out[idx] = __float2half_rn(c < C ? cst[c * r * r + px] * style[b * C + c] : 0.0f);
+        put_split(out + q * (static_cast<long long>(ns) * Cp), c, Cp, ns, c < C ? cst[c * r * r + px] * style[b * C + c] : 0.0f);
     }
 }
 
 struct ActArgs {
-    const __half* y;        // planar conv output [B][C][Hy][Wpy]; Hy = R (+1 with FIR)
+    const __half* y;        // planar conv output [B][C][Hy][Wpy]; Hy = R (+1 with FIR).  phase: the four parity planes of the
+                            // polyphase transposed conv, [B][4][C][R/2 + 1][Wpy]: y(yy, xx) = plane (yy & 1) * 2 + (xx & 1) at (yy >> 1, xx >> 1)
+    long long y_lo;         // > 0: y + y_lo holds the low halves of a split output (value = hi + lo)
+    int phase, ns;          // ns: channel blocks of x_next (3 = [xh | xl | xh], 1 = plain fp16)
     const __half* pre;      // if set: the finished activation, channels-last [B][R][R][Cp] (a warped feature map); y, noise, bias unused
     const float* noise;     // [R][R] (noise_bstride 0) or per-frame [B][R][R] (noise_bstride R*R) or nullptr
     const float* bias;      // [C]
@@ -92,7 +137,16 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
         if (a.pre) {
             if (w < a.R) v = __half2float(a.pre[((static_cast<long long>(b) * a.R + h) * a.R + w) * a.Cp + c]);
         } else if (w < a.R) {
-            const __half* yp = a.y + (static_cast<long long>(b) * a.C + c) * a.Hy * a.Wpy;
+            const int hp = a.phase ? a.R / 2 + 1 : a.Hy;               // rows of a stored plane
+            const long long plane = static_cast<long long>(hp) * a.Wpy;
+            const __half* yp = a.y + (static_cast<long long>(b) * (a.phase ? 4 : 1) * a.C + c) * plane;
+            auto at = [&](int yy, int xx) -> float {
+                const __half* q = a.phase ? yp + static_cast<long long>(((yy & 1) * 2 + (xx & 1)) * a.C) * plane + static_cast<long long>(yy >> 1) * a.Wpy + (xx >> 1)
+                                          : yp + static_cast<long long>(yy) * a.Wpy + xx;
+                float v = __half2float(*q);
+                if (a.y_lo > 0) v += __half2float(q[a.y_lo]);
+                return v;
+            };
             if (a.fir) {
                 // upfirdn2d(pad 1): out[h][w] = sum_{ky,kx} f[ky] f[kx] y[h - 1 + ky][w - 1 + kx], zero outside
 #pragma unroll
@@ -103,12 +157,12 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
 #pragma unroll
                     for (int kx = 0; kx < 4; ++kx) {
                         const int xx = w - 1 + kx;
-                        if (xx >= 0 && xx < a.Hy) row = fmaf(f4[kx], __half2float(yp[static_cast<long long>(yy) * a.Wpy + xx]), row);
+                        if (xx >= 0 && xx < a.Hy) row = fmaf(f4[kx], at(yy, xx), row);
                     }
                     v = fmaf(f4[ky], row, v);
                 }
             } else {
-                v = __half2float(yp[static_cast<long long>(h) * a.Wpy + w]);
+                v = at(h, w);
             }
             if (a.noise) v += a.noise[b * a.noise_bstride + h * a.R + w];
             v += a.bias[c];
@@ -120,14 +174,22 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
     __syncthreads();
     const int npx = min(kActP, a.R - w0);
     if (a.x_next) {
-        __half* o = a.x_next + ((static_cast<long long>(b) * a.R + h) * a.R + w0) * a.Cp;
+        const int cpx = a.ns * a.Cp;   // halfs per pixel of x_next
+        __half* o = a.x_next + ((static_cast<long long>(b) * a.R + h) * a.R + w0) * cpx;
         for (int idx = threadIdx.x; idx < npx * (a.Cp / 2); idx += blockDim.x) {
             const int px = idx / (a.Cp / 2), c = (idx - px * (a.Cp / 2)) * 2;
             const float s0 = c < a.C ? (a.style_next ? a.style_next[b * a.C + c] : 1.0f) : 0.0f;
             const float s1 = c + 1 < a.C ? (a.style_next ? a.style_next[b * a.C + c + 1] : 1.0f) : 0.0f;
             const float v0 = c < a.C ? xs[c * (kActP + 1) + px] * s0 : 0.0f;
             const float v1 = c + 1 < a.C ? xs[(c + 1) * (kActP + 1) + px] * s1 : 0.0f;
-            *reinterpret_cast<__half2*>(o + static_cast<long long>(px) * a.Cp + c) = __floats2half2_rn(v0, v1);
+            __half* op = o + static_cast<long long>(px) * cpx;
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            *reinterpret_cast<__half2*>(op + c) = hi;
+            if (a.ns == 3) {
+                const float2 hf = __half22float2(hi);
+                *reinterpret_cast<__half2*>(op + a.Cp + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                *reinterpret_cast<__half2*>(op + 2 * a.Cp + c) = hi;
+            }
         }
     }
     if (a.rgb_w) {
@@ -276,8 +338,10 @@ struct Sg2Param {
 struct Sg2Layer {   // one modulated conv (conv0 / conv1) or ToRGB
     int cin = 0, cout = 0, res = 0, up = 1, ksz = 3;
     Sg2Param affine_w, affine_b, weight, bias, noise;
-    __half* wpk = nullptr;
-    float* wsqT = nullptr;
+    __half* wpk = nullptr;   // packed effective weights (sg2_prep_weights_kernel -> pack_weights_launch)
+    size_t wpk_elems = 0;
+    float* wsqT = nullptr;   // [cin][cout]: sum over the 3x3 taps of w^2 (demodulation)
+    float* wsq4 = nullptr;   // conv0: wsqT tiled to [cin][4 * cout] for the four parity planes
 };
 struct Sg2Block {
     int res = 0, cin = 0, cout = 0;
@@ -291,6 +355,8 @@ struct Sg2Net {
     std::map<std::string, Sg2Param*> by_name;
     bool finalized = false;
     int conv_impl = 0;
+    int precise = 1;         // fp16 hi + lo operands and conv outputs (see the header); 0 = plain fp16
+    int packed_precise = -1; // the mode the packed weights were built for
     int last_launches = 0;
     // feature-map warps applied by the next forwards (sg2_set_warps): layer = index into the wrapper's layer_names
     std::vector<int> warp_layer;
@@ -315,6 +381,7 @@ void sg2_destroy(Sg2Net* n) {
         for (Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
             if (L->wpk) cudaFree(L->wpk);
             if (L->wsqT) cudaFree(L->wsqT);
+            if (L->wsq4) cudaFree(L->wsq4);
         }
     delete n;
 }
@@ -352,8 +419,8 @@ int sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base
                 n->by_name[pre + name + ".noise_const"] = &L.noise;
             }
             if (ksz == 3) {
-                if (cudaMalloc(&L.wpk, packed_weight_elems(cout, cin, 3) * sizeof(__half)) != cudaSuccess ||
-                    cudaMalloc(&L.wsqT, sizeof(float) * cin * cout) != cudaSuccess) {
+                if (cudaMalloc(&L.wsqT, sizeof(float) * cin * cout) != cudaSuccess ||
+                    (up == 2 && cudaMalloc(&L.wsq4, sizeof(float) * cin * 4 * cout) != cudaSuccess)) {
                     set_error("mb_sg2_create: cudaMalloc failed");
                     return MB_ECUDA;
                 }
@@ -415,6 +482,39 @@ int sg2_set_param(Sg2Net* n, const char* name, const float* data, const int64_t*
     return MB_OK;
 }
 
+static int sg2_pack_layer(Sg2Net* n, Sg2Layer& L, int phase, cudaStream_t stream) {
+    const int ns = n->precise ? 3 : 1, Cp = cpad16(L.cin);
+    const int kk = phase ? 2 : 3, Co = phase ? 4 * L.cout : L.cout, Ci = ns * Cp;
+    // demodulation sums from the original 3x3 weights (the packed copy this call also writes is scratch)
+    __half* scratch = nullptr;
+    MB_CUDA(cudaMalloc(&scratch, packed_weight_elems(L.cout, L.cin, 3) * sizeof(__half)));
+    int rc = pack_weights_launch(L.weight.dev, scratch, L.wsqT, L.cout, L.cin, 3, 0, stream, 0);
+    if (rc == MB_OK && phase) {
+        sg2_tile4_kernel<<<grid1d(static_cast<long long>(L.cin) * 4 * L.cout), 256, 0, stream>>>(L.wsqT, L.wsq4, L.cin, L.cout);
+        if (cudaGetLastError() != cudaSuccess) rc = MB_ECUDA;
+    }
+    float* eff = nullptr;
+    const size_t eff_elems = static_cast<size_t>(Co) * Ci * kk * kk;
+    if (rc == MB_OK && cudaMalloc(&eff, eff_elems * sizeof(float)) != cudaSuccess) rc = MB_ECUDA;
+    const size_t need = packed_weight_elems(Co, Ci, kk);
+    if (rc == MB_OK && need != L.wpk_elems) {
+        if (L.wpk) cudaFree(L.wpk);
+        L.wpk = nullptr; L.wpk_elems = 0;
+        if (cudaMalloc(&L.wpk, need * sizeof(__half)) != cudaSuccess) rc = MB_ECUDA;
+        else L.wpk_elems = need;
+    }
+    if (rc == MB_OK) {
+        sg2_prep_weights_kernel<<<grid1d(static_cast<long long>(eff_elems)), 256, 0, stream>>>(L.weight.dev, eff, L.cout, L.cin, Cp, phase, ns);
+        if (cudaGetLastError() != cudaSuccess) rc = MB_ECUDA;
+    }
+    if (rc == MB_OK) rc = pack_weights_launch(eff, L.wpk, nullptr, Co, Ci, kk, 0, stream, 0);
+    cudaStreamSynchronize(stream);
+    cudaFree(scratch);
+    if (eff) cudaFree(eff);
+    if (rc == MB_ECUDA) set_error("mb_net_finalize: packing the StyleGAN2 weights failed (%s)", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}
+
 int sg2_finalize(Sg2Net* n, cudaStream_t stream) {
     for (auto& kv : n->by_name)
         if (!kv.second->set) {
@@ -423,49 +523,48 @@ int sg2_finalize(Sg2Net* n, cudaStream_t stream) {
         }
     for (auto& b : n->blocks) {
         int rc;
-        if (b.has_conv0 && (rc = pack_weights_launch(b.conv0.weight.dev, b.conv0.wpk, b.conv0.wsqT, b.conv0.cout, b.conv0.cin, 3, 0,
-                                                     stream, /*flip=*/1)) != MB_OK)
-            return rc;
-        if ((rc = pack_weights_launch(b.conv1.weight.dev, b.conv1.wpk, b.conv1.wsqT, b.conv1.cout, b.conv1.cin, 3, 0, stream, 0)) != MB_OK)
-            return rc;
+        if (b.has_conv0 && (rc = sg2_pack_layer(n, b.conv0, 1, stream)) != MB_OK) return rc;
+        if ((rc = sg2_pack_layer(n, b.conv1, 0, stream)) != MB_OK) return rc;
     }
     MB_CUDA(cudaStreamSynchronize(stream));
+    n->packed_precise = n->precise;
     n->finalized = true;
     return MB_OK;
 }
 
 namespace {
 struct Sg2Ws {
-    size_t styles, d, x, xu, y, img0, img1, t0, t1, total;
+    size_t styles, d, x, y, img0, img1, t0, t1, total;
     std::vector<size_t> style_l, d_l;  // per layer (conv0, conv1, torgb per block) float offsets
 };
 Sg2Ws sg2_ws(const Sg2Net* n, int B) {
     Sg2Ws w;
-    size_t ns = 0, nd = 0, mx = 0, mxu = 0, my = 0;
+    size_t ns = 0, nd = 0, mx = 0, my = 0, mt = 0;
+    const size_t nsx = n->precise ? 3 : 1, nsy = n->precise ? 2 : 1;   // channel blocks of X, planes (hi, lo) of Y
     for (const auto& b : n->blocks) {
         for (const Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
             w.style_l.push_back(ns);
             w.d_l.push_back(nd);
             ns += static_cast<size_t>(B) * L->cin;
-            nd += static_cast<size_t>(B) * L->cout;
+            nd += static_cast<size_t>(B) * L->cout * (L == &b.conv0 ? 4 : 1);   // conv0: one coefficient per parity plane
         }
         const size_t r = b.res;
-        mx = std::max(mx, static_cast<size_t>(B) * r * r * cpad16(b.cout));
+        mx = std::max(mx, static_cast<size_t>(B) * r * r * cpad16(b.cout) * nsx);
+        mt = std::max(mt, static_cast<size_t>(B) * r * r * cpad16(b.cout));
         if (b.has_conv0) {
-            mx = std::max(mx, static_cast<size_t>(B) * (r / 2) * (r / 2) * cpad16(b.cin));
-            mxu = std::max(mxu, static_cast<size_t>(B) * (r - 1) * (r - 1) * cpad16(b.cin));
-            my = std::max(my, static_cast<size_t>(B) * b.cout * (r + 1) * pitch8(static_cast<int>(r + 1)));
+            mx = std::max(mx, static_cast<size_t>(B) * (r / 2) * (r / 2) * cpad16(b.cin) * nsx);
+            my = std::max(my, static_cast<size_t>(B) * 4 * b.cout * (r / 2 + 1) * pitch8(static_cast<int>(r / 2 + 1)) * nsy);
         }
-        my = std::max(my, static_cast<size_t>(B) * b.cout * r * pitch8(static_cast<int>(r)));
+        my = std::max(my, static_cast<size_t>(B) * b.cout * r * pitch8(static_cast<int>(r)) * nsy);
     }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 1024); return o; };
     w.styles = take(ns * 4); w.d = take(nd * 4);
-    w.x = take(mx * 2); w.xu = take(mxu * 2); w.y = take(my * 2);
+    w.x = take(mx * 2); w.y = take(my * 2);
     const size_t img = static_cast<size_t>(B) * n->img_channels * n->res * n->res * 4;
     w.img0 = take(img); w.img1 = take(img);
     w.t0 = w.t1 = off;
-    if (!n->warp_layer.empty()) { w.t0 = take(mx * 2); w.t1 = take(mx * 2); }  // ping-pong buffers of the warped feature map
+    if (!n->warp_layer.empty()) { w.t0 = take(mt * 2); w.t1 = take(mt * 2); }  // ping-pong buffers of the warped feature map (plain fp16)
     w.total = off;
     return w;
 }
@@ -476,6 +575,7 @@ int sg2_num_ws(const Sg2Net* n) { return n->num_ws; }
 int sg2_resolution(const Sg2Net* n) { return n->res; }
 int sg2_last_launches(const Sg2Net* n) { return n->last_launches; }
 void sg2_set_conv_impl(Sg2Net* n, int impl) { n->conv_impl = impl; }
+void sg2_set_precise(Sg2Net* n, int on) { n->precise = on ? 1 : 0; }
 
 int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* inv_mats, int batch) {
     MB_REQUIRE(n_warps >= 0 && n_warps <= 16, "mb_sg2_set_warps: between 0 and 16 warps, got %d", n_warps);
@@ -499,6 +599,11 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
         set_error("mb_net_forward: call mb_net_finalize after setting parameters");
         return MB_ESTATE;
     }
+    if (n->packed_precise != n->precise) {   // the precision mode was switched after the weights were packed
+        int rr = sg2_finalize(n, stream);
+        if (rr != MB_OK) return rr;
+    }
+    const int nsx = n->precise ? 3 : 1;
     const Sg2Ws wl = sg2_ws(n, B);
     if (workspace_bytes < wl.total) {
         set_error("mb_net_forward: workspace too small (%zu < %zu bytes)", workspace_bytes, wl.total);
@@ -508,7 +613,6 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
     float* styles = reinterpret_cast<float*>(base + wl.styles);
     float* dco = reinterpret_cast<float*>(base + wl.d);
     __half* X = reinterpret_cast<__half*>(base + wl.x);
-    __half* XU = reinterpret_cast<__half*>(base + wl.xu);
     __half* Y = reinterpret_cast<__half*>(base + wl.y);
     float* img[2] = {reinterpret_cast<float*>(base + wl.img0), reinterpret_cast<float*>(base + wl.img1)};
     __half* T[2] = {reinterpret_cast<__half*>(base + wl.t0), reinterpret_cast<__half*>(base + wl.t1)};
@@ -536,10 +640,11 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
                 if (present) {
                     StyleLayerDesc& d = sa.L[sa.num_layers++];
                     d.affine_w = L->affine_w.dev; d.affine_b = L->affine_b.dev;
-                    d.wsqT = L->wsqT; d.magnitude_ema = nullptr;
+                    const bool parity4 = L == &b.conv0;   // polyphase transposed conv: 4 * cout output planes, same coefficient each
+                    d.wsqT = parity4 ? L->wsq4 : L->wsqT; d.magnitude_ema = nullptr;
                     d.s_out = styles + wl.style_l[li];
                     d.d_out = L->ksz == 3 ? dco + wl.d_l[li] : nullptr;
-                    d.Cin = L->cin; d.Cout = L->cout; d.ws_index = w_idx + j;
+                    d.Cin = L->cin; d.Cout = parity4 ? 4 * L->cout : L->cout; d.ws_index = w_idx + j;
                     d.demodulate = L->ksz == 3; d.normalize_style = 0;
                     d.style_scale = L->ksz == 1 ? 1.0f / sqrtf(static_cast<float>(L->cin)) : 1.0f;
                     ++j;
@@ -561,16 +666,23 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
         const float* s_conv0 = styles + wl.style_l[bi * 3 + 0];
         const float* s_conv1 = styles + wl.style_l[bi * 3 + 1];
         const float* s_rgb = styles + wl.style_l[bi * 3 + 2];
-        auto conv = [&](const Sg2Layer& L, const __half* xin, int hin, int pad, const float* d) -> int {
+        // phase = 1: the polyphase transposed conv (2x2 'full' kernel, 4 * cout parity planes of (hin + 1)^2); else 3x3 'same'
+        auto conv = [&](const Sg2Layer& L, const __half* xin, int hin, int phase, const float* d) -> int {
             ConvTcArgs ca;
             ca.x = xin; ca.wpk = L.wpk; ca.d = d; ca.bias = nullptr; ca.y = Y;
-            ca.B = B; ca.Cin = L.cin; ca.Cout = L.cout; ca.Hin = hin; ca.Win = hin; ca.Cp_in = cpad16(L.cin);
-            ca.Wp_out = pitch8(hin + 2 * pad - 2); ca.ksz = 3; ca.pad = pad; ca.tile_w = 32; ca.num_sms = num_sms;
+            ca.B = B; ca.Cin = nsx * cpad16(L.cin); ca.Cout = phase ? 4 * L.cout : L.cout; ca.Hin = hin; ca.Win = hin; ca.Cp_in = ca.Cin;
+            ca.ksz = phase ? 2 : 3; ca.pad = 1;
+            const int hout = hin + 2 * ca.pad - (ca.ksz - 1);
+            ca.Wp_out = pitch8(hout); ca.tile_w = 32; ca.num_sms = num_sms;
+            if (n->precise && n->conv_impl == 0) {
+                ca.pm_max_cout = 0; ca.cm_shift = 0;   // the split epilogue lives in the plain cout-major tile
+                ca.split_lo_off = static_cast<long long>(B) * ca.Cout * hout * ca.Wp_out;
+            }
             launches += 1;
             return n->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         };
         auto act_raw = [&](const Sg2Layer& L, int fir, const float* style_next, __half* x_next, bool rgb, const float* prev,
-                           const __half* pre) -> int {
+                           const __half* pre, int ns_out) -> int {
             ActArgs a;
             a.y = Y; a.pre = pre; a.noise = L.noise.dev; a.bias = L.bias.dev;
             const size_t nb = L.noise.numel / L.noise.plane;
@@ -580,7 +692,10 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             a.style_next = style_next; a.x_next = x_next;
             a.rgb_w = rgb ? b.torgb.weight.dev : nullptr; a.rgb_style = s_rgb; a.rgb_bias = b.torgb.bias.dev;
             a.img_prev = prev; a.img = img[cur ^ 1];
-            a.B = B; a.C = L.cout; a.R = r; a.Hy = fir ? r + 1 : r; a.Wpy = pitch8(a.Hy); a.Cp = cpad16(L.cout);
+            a.B = B; a.C = L.cout; a.R = r; a.Hy = fir ? r + 1 : r; a.Cp = cpad16(L.cout);
+            a.phase = fir; a.ns = ns_out;
+            a.Wpy = fir ? pitch8(r / 2 + 1) : pitch8(r);
+            a.y_lo = (n->precise && n->conv_impl == 0) ? static_cast<long long>(B) * (fir ? 4 : 1) * L.cout * (fir ? r / 2 + 1 : r) * a.Wpy : 0;
             a.fir = fir; a.nimg = n->img_channels; a.clamp = 256.0f;
             const size_t smem = sizeof(float) * L.cout * (kActP + 1);
             static size_t smem_set = 0;
@@ -601,9 +716,9 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             bool warped = false;
             for (int wl_ : n->warp_layer)
                 if (wl_ == name_idx || (bi == 0 && wl_ <= 1)) warped = true;
-            if (!warped) return act_raw(L, fir, style_next, style_next ? X : nullptr, rgb, prev, nullptr);
+            if (!warped) return act_raw(L, fir, style_next, style_next ? X : nullptr, rgb, prev, nullptr, nsx);
             int rr;
-            if ((rr = act_raw(L, fir, nullptr, T[0], false, nullptr, nullptr)) != MB_OK) return rr;
+            if ((rr = act_raw(L, fir, nullptr, T[0], false, nullptr, nullptr, 1)) != MB_OK) return rr;   // the warps run on plain fp16
             int cur_t = 0;
             const int cp = cpad16(L.cout);
             for (size_t wi = 0; wi < n->warp_layer.size(); ++wi) {
@@ -615,25 +730,20 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
                 launches += 1;
                 cur_t ^= 1;
             }
-            return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, T[cur_t]);
+            return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, T[cur_t], nsx);
         };
         if (!b.has_conv0) {
             const long long tot = static_cast<long long>(B) * r * r * cpad16(b.cout);
-            const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout));
+            const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout), nsx);
             MB_CUDA(cudaGetLastError());
             launches += 1;
         } else {
-            // conv0: X holds x * style(conv0) at r/2 -> zero insert -> 'full' conv with flipped taps -> FIR + act
-            const int h = r / 2, cp8 = cpad16(b.cin) / 8;
-            const long long tot = static_cast<long long>(B) * (2 * h - 1) * (2 * h - 1) * cp8;
-            zero_insert_kernel<<<grid1d(tot), 256, 0, stream>>>(reinterpret_cast<const uint4*>(X), reinterpret_cast<uint4*>(XU), B, h, h, cp8);
-            MB_CUDA(cudaGetLastError());
-            launches += 1;
-            if ((rc = conv(b.conv0, XU, 2 * h - 1, 2, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
+            // conv0: X holds x * style(conv0) at r/2 -> polyphase transposed conv (four parity planes) -> FIR + act
+            if ((rc = conv(b.conv0, X, r / 2, 1, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
             if ((rc = act(b.conv0, 1, s_conv1, false, nullptr, static_cast<int>(2 * bi))) != MB_OK) return rc;
         }
         (void)s_conv0;
-        if ((rc = conv(b.conv1, X, r, 1, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
+        if ((rc = conv(b.conv1, X, r, 0, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
         const float* prev = nullptr;
         if (have_img) {
             // img[cur] (r/2) -> upsampled into img[cur^1]?  keep three-step: upsample into the other buffer, accumulate in place

@@ -16,6 +16,7 @@ int sg2_resolution(const Sg2Net* n);
 int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* inv_mats, int batch);
 int sg2_last_launches(const Sg2Net* n);
 void sg2_set_conv_impl(Sg2Net* n, int impl);
+void sg2_set_precise(Sg2Net* n, int on);   // 1 (default): fp16 hi + lo operands and conv outputs; 0: plain fp16
 int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
                 int num_sms, cudaStream_t stream);
 }  // namespace mb

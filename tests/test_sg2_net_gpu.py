@@ -25,6 +25,11 @@ def make_pair(res, seed=0, **kw):
     return onet, net
 
 
+def pix_err(a, b):
+    """max-abs error on fp32 pixels = clamp((x + 1) / 2, 0, 1): BASELINE.json's tolerance, on the image as it is."""
+    return float((pix(a) - pix(b)).abs().max())
+
+
 def rel_err(a, b):
     return float((a.float().cpu() - b).abs().max() / b.abs().max())
 
@@ -38,11 +43,11 @@ def test_reference_golden_images(cuda):
     net.load_state_dict(g["state"], strict=True)
     out = net(g["ws"].to(cuda))
     print("sg2 32^2 vs reference image: rel", rel_err(out, g["img"]), "pix", float((pix(out) - pix(g["img"])).abs().max()))
-    assert rel_err(out, g["img"]) < 5e-3
+    assert pix_err(out, g["img"]) <= PIX_TOL          # the reference's own render, the north-star tolerance, no rescaling
     g = gold["sg2_64"]
     _, net = make_pair(64, seed=g["seed"], **g["kw"])
     out = net(g["ws"].to(cuda))
-    assert rel_err(out, g["img"]) < 5e-3
+    assert pix_err(out, g["img"]) <= PIX_TOL
 
 
 @pytest.mark.parametrize("res,kw", [(64, dict(channel_base=4096, channel_max=128)), (256, dict(channel_base=16384, channel_max=96))])
@@ -52,27 +57,32 @@ def test_network_matches_oracle(cuda, res, kw):
     ws = torch.randn(3, net.num_ws, 512)
     ref = onet(ws)
     out = net(ws.to(cuda))
-    print(f"sg2 {res}^2: rel err {rel_err(out, ref):.3e}, |img| max {float(ref.abs().max()):.1f}")
-    assert rel_err(out, ref) < 5e-3
+    print(f"sg2 {res}^2: pixel err {pix_err(out, ref):.3e}, rel err {rel_err(out, ref):.3e}, |img| max {float(ref.abs().max()):.1f}")
+    assert pix_err(out, ref) <= PIX_TOL
     u8 = net(ws.to(cuda), out_fmt="u8").cpu()
     want8 = (pix(ref) * 255).round().permute(0, 2, 3, 1)
-    # random-init images swing over +-30: an fp16-operand error of 5e-3 * 30 moves a pixel that is not saturated
-    assert float(((u8.float() - want8).abs() <= 1).float().mean()) > 0.97
+    assert float((u8.float() - want8).abs().max()) <= 1.0
     assert net.last_launch_count() > 0
+    # plain fp16 operands (sg2_precise = 0, 3x fewer MACs): the random-init image swings over +-30, so fp16's 5e-4 relative
+    # storage error is visible in the unsaturated pixels -- a looser, relative bound
+    net.set_option("sg2_precise", 0)
+    fast = net(ws.to(cuda))
+    assert rel_err(fast, ref) < 5e-3 and not torch.equal(fast, out)
+    net.set_option("sg2_precise", 1)
+    assert torch.equal(net(ws.to(cuda)), out)
 
 
 def test_c1_network_256_pixels(cuda):
     """BASELINE.json configs[0] network: StyleGAN2 256^2 default channels, 8 frames worth of latents (2 checked here).
-    Pixel tolerance applied on output scaled into the visible range (random-init images overshoot [-1,1] by ~30x)."""
+    The north-star tolerance (1e-3 max-abs on fp32 pixels) on the image as rendered."""
     onet, net = make_pair(256)
     torch.manual_seed(1)
     ws = torch.randn(2, net.num_ws, 512)
     torch.set_num_threads(os.cpu_count() or 1)
     ref = onet(ws)
     out = net(ws.to(cuda)).cpu()
-    scale = float(ref.abs().max())
-    err = float((pix(out / scale) - pix(ref / scale)).abs().max())
-    print(f"sg2 256^2 default: scaled-pixel max-abs err {err:.3e} (image range +-{scale:.1f})")
+    err = pix_err(out, ref)
+    print(f"sg2 256^2 default: pixel max-abs err {err:.3e} (image range +-{float(ref.abs().max()):.1f}, no rescaling)")
     assert err <= PIX_TOL
 
 
@@ -99,7 +109,7 @@ def test_per_frame_noise_and_wrapper(cuda):
             L.noise_const = n[b, 0].clone()
         refs.append(onet(ws[b:b + 1]))
     ref = torch.cat(refs)
-    assert rel_err(out, ref) < 5e-3
+    assert pix_err(out, ref) <= PIX_TOL
     # batch invariance + determinism
     again = S.forward(ws.to(cuda), **noise)
     assert torch.equal(out, again)

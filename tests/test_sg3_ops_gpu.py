@@ -26,6 +26,8 @@ CONV_CASES = [
     (1, 96, 64, 33, 41, 3, True),
     (2, 128, 81, 60, 50, 3, True),
     (1, 40, 17, 45, 37, 3, True),
+    (2, 64, 96, 20, 24, 2, True),      # 2x2 kernels: the parity kernels of the polyphase transposed conv (csrc/sg2.cu)
+    (1, 48, 256, 33, 33, 2, True),
 ]
 
 

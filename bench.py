@@ -147,7 +147,7 @@ def run_reference(args):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cfg = CONFIGS[args.config]
+    cfg = CONFIGS.get(args.config, CONFIGS["c2"])
     net = O.make_synthesis(cfg["arch"], 1024, seed=0)
     lat, _ = c2_latents(net.num_ws)
     # one step = ONE frame of the 720-frame job (a bounded sample: the CPU needs tens of seconds per frame);
@@ -428,6 +428,148 @@ def run_ours(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------
+# secondary line: the StyleGAN2 path (the generator of selfsupervised/sample.generate), --config sg2
+# ----------------------------------------------------------------------------------------------------
+def sg2_algorithmic_work(res, channel_base=32768, channel_max=512, img_channels=3):
+    """Per-frame algorithmic work of the in-tree StyleGAN2 synthesis network: modulated-conv FLOPs
+    (2 Cin Cout 9 h_out^2 for the 3x3 convs, 2 Cin Cout 9 h_in^2 for the stride-2 transposed conv, + ToRGB) and the bytes the
+    fused FIR / bias_act kernel has to move once (conv output in, next conv input out, fp16 pairs in `precise` mode)."""
+    ch = lambda r: min(channel_base // r, channel_max)   # noqa: E731
+    flops, act_vals = 0.0, 0.0
+    r = 4
+    while r <= res:
+        co = ch(r)
+        if r > 4:
+            ci = ch(r // 2)
+            flops += 2.0 * ci * co * 9 * (r // 2) ** 2            # transposed conv: one MAC set per INPUT pixel
+            act_vals += co * ((r + 1) ** 2 + r * r)                # FIR input (2h+1)^2, activation output
+        flops += 2.0 * co * co * 9 * r * r
+        act_vals += co * 2 * r * r
+        flops += 2.0 * co * img_channels * r * r
+        r *= 2
+    return flops, act_vals
+
+
+def run_sg2(args):
+    import torch
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise RuntimeError("--config sg2 is a single-GPU line")
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: maua_b200 has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    from maua_b200.GAN.networks import stylegan2 as N2
+    from maua_b200.GAN.wrappers.stylegan2 import StyleGAN2Synthesizer
+    from maua_b200.audiovisual.render.ffmpeg import FFMPEG
+    from maua_b200.workload import job_latents_device
+
+    B, K, W = min(args.batch, 8), args.steps, args.warmup
+    res = 1024
+    torch.manual_seed(0)
+    net = N2.SynthesisNetwork(w_dim=512, img_resolution=res, img_channels=3).to(dev)
+    S = StyleGAN2Synthesizer.__new__(StyleGAN2Synthesizer)
+    torch.nn.Module.__init__(S)
+    S.G_synth, S._hook_handles, S._warp_hooks = net, [], {}
+    lat, audio_info = job_latents_device(net.num_ws, dev, 30.0, 24)
+    nb = lat.shape[0] // B
+    frames = torch.empty(B, res, res, 3, device=dev, dtype=torch.uint8)
+
+    def step(i):
+        j = (i % nb) * B
+        net(lat[j:j + B], out_fmt="u8", out=frames)
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    net.set_option("profile", 2)
+    net.set_option("profile_reset", 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    per_kind = {}
+    for kind, _, t in net.profile_read():
+        per_kind[kind] = per_kind.get(kind, 0.0) + t / K
+    clk = clocks.stop()
+    net.set_option("profile", 0)
+    launches = net.last_launch_count() * K
+
+    class ByteCounter:
+        n = 0
+
+        def write(self, view):
+            self.n += len(view)
+
+        def close(self):
+            pass
+
+    def e2e_job(n_frames):
+        host = torch.empty((n_frames,) + tuple(lat.shape[1:])).pin_memory()
+        host.copy_(lat[:n_frames])
+        sink = ByteCounter()
+        FFMPEG(None, fps=24, batch_size=B, sink=sink)(S, {"latents": host}, lambda v: v)
+        return sink.n
+
+    e2e_job(3 * B)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_e2e = lat.shape[0]
+    nbytes = e2e_job(n_e2e)
+    torch.cuda.synchronize()
+    e2e_fps = n_e2e / (time.perf_counter() - t0)
+    assert nbytes == n_e2e * res * res * 3
+
+    peaks = measured_peaks()
+    flops, act_vals = sg2_algorithmic_work(res)
+    conv_ms, act_ms = per_kind.get(2, 0.0), per_kind.get(3, 0.0)
+    bytes_per_val_in, bytes_per_val_out = 4.0, 6.0     # conv output hi + lo planes in; next conv input [xh | xl | xh] out
+    act_bytes = act_vals / 2 * bytes_per_val_in + act_vals / 2 * bytes_per_val_out
+    roof_conv = {"kernel": "modulated_conv2d tcgen05 implicit GEMM (fp16 hi+lo operands: 3 MMAs per algorithmic MAC)", "bound": "tensor",
+                 "achieved": flops * B / (conv_ms * 1e-3) / 1e12 if conv_ms else None, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                 "traffic": None, "peak_source": peaks["source"] + ", sustained", "ms_per_step": conv_ms}
+    roof_conv["frac"] = roof_conv["achieved"] / roof_conv["peak"] if roof_conv["achieved"] else None
+    roof_act = {"kernel": "fused upfirdn2d + noise + bias_act + ToRGB kernel", "bound": "hbm",
+                "achieved": act_bytes * B / (act_ms * 1e-3) / 1e9 if act_ms else None, "peak": peaks["hbm"], "unit": "GB/s", "traffic": None,
+                "peak_source": peaks["source"], "ms_per_step": act_ms}
+    roof_act["frac"] = roof_act["achieved"] / roof_act["peak"] if roof_act["achieved"] else None
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import sg2 as O2
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        onet = O2.make_synthesis(res, seed=0)
+        t0 = time.perf_counter()
+        onet(lat[:1].cpu())
+        cpu = {"value": 1.0 / (time.perf_counter() - t0), "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "1 of 720 frames (oracle/sg2.py, pinned against the reference's in-tree inference network, all host threads)"}
+    names = {0: "styles", 1: "const input", 2: "modulated_conv2d (tcgen05)", 3: "upfirdn2d+bias_act+ToRGB (fused)", 4: "feature warp", 5: "skip image / output"}
+    emit({
+        "metric": "frames/sec StyleGAN2 1024^2 audio-reactive render", "value": B * K / (ms * 1e-3), "unit": "frames/s", "n_gpus": 1,
+        "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 hi+lo pairs (fp32-class), fp32 accumulate", "data": "synthetic",
+        "config": {"workload": "StyleGAN2 1024^2 random-init (the generator of selfsupervised/sample.generate), 30 s @ 24 fps audio-reactive "
+                               "latents, constant noise", "name": "sg2", "frames_per_step_per_gpu": B, "audio_features": audio_info,
+                   "l2": "per-step working set >> 126 MB L2, no explicit flush"},
+        "clocks": clk,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * net.num_ws * 512 * 4, "d2h_bytes_per_step": B * res * res * 3,
+                "path": "host latents -> FFMPEG.__call__ -> byte-counting sink", "frames_per_gpu": n_e2e},
+        "gpu_launches": launches,
+        "roofline": roof_conv if conv_ms >= act_ms else roof_act, "roofline_other": roof_act if conv_ms >= act_ms else roof_conv,
+        "kernel_ms_per_step": {names[k]: round(v, 4) for k, v in sorted(per_kind.items())},
+        "cpu_baseline": cpu,
+    })
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,7 +578,8 @@ def main():
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (16 = the reference FFMPEG renderer's batch size, maua/audiovisual/render/ffmpeg.py:31)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="c2 = BASELINE configs[1] (default, the headline), c3 = configs[2]")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["sg2"],
+                    help="c2 = BASELINE configs[1] (default, the headline), c3 = configs[2], sg2 = the StyleGAN2-1024 path (secondary line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -451,6 +594,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
     guard_stdout()
+    if args.config == "sg2":
+        return run_sg2(args)
     return run_ours(args)
 
 

@@ -718,7 +718,24 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
                "mb_net_forward: unknown out_fmt %d", out_fmt);
     if (net->sg2) {
         MB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "mb_net_forward: workspace must be 1024-byte aligned");
-        return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, static_cast<cudaStream_t>(stream_));
+        cudaStream_t st = static_cast<cudaStream_t>(stream_);
+        if (!net->profile) return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, st);
+        if (net->profile != 2) { net->prof.clear(); net->ev_used = 0; }
+        auto ev_next2 = [&]() -> int {
+            if (net->ev_used == static_cast<int>(net->ev_pool.size())) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                net->ev_pool.push_back(e);
+            }
+            cudaEventRecord(net->ev_pool[net->ev_used], st);
+            return net->ev_used++;
+        };
+        int ev_prev2 = ev_next2();
+        return sg2_forward(net->sg2, ws, B, out, out_fmt, workspace, workspace_bytes, g_num_sms, st, [&](int kind, int layer) {
+            const int e = ev_next2();
+            net->prof.push_back({kind, layer, ev_prev2, e});
+            ev_prev2 = e;
+        });
     }
     if (!net->finalized) {
         set_error("mb_net_forward: call mb_net_finalize after setting parameters");
@@ -1026,7 +1043,7 @@ extern "C" int mb_net_activation_shape(const mb_net* net, int32_t* c, int32_t* h
 extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* s, float* y, int B, int Cin, int Cout,
                                    int H, int W, int k, int demodulate, float input_gain, int impl, mb_stream stream_) {
     MB_REQUIRE(x && w && s && y, "mb_modulated_conv2d: null argument");
-    MB_REQUIRE(k == 1 || k == 3, "mb_modulated_conv2d: kernel size %d unsupported (1 or 3)", k);
+    MB_REQUIRE(k >= 1 && k <= 3, "mb_modulated_conv2d: kernel size %d unsupported (1..3)", k);
     if (g_device < 0) {
         int r = ensure_init();
         if (r != MB_OK) return r;

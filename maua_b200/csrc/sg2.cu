@@ -594,7 +594,8 @@ int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* in
 }
 
 int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
-                int num_sms, cudaStream_t stream) {
+                int num_sms, cudaStream_t stream, const std::function<void(int, int)>& mark_fn) {
+    auto mark = [&](int kind, int layer) { if (mark_fn) mark_fn(kind, layer); };
     if (!n->finalized) {
         set_error("mb_net_forward: call mb_net_finalize after setting parameters");
         return MB_ESTATE;
@@ -655,6 +656,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             w_idx += b.has_conv0 ? 2 : 1;
         }
         if ((rc = flush()) != MB_OK) return rc;
+        mark(0, -1);
     }
 
     int cur = 0;  // which img buffer holds the previous block's image
@@ -679,7 +681,9 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
                 ca.split_lo_off = static_cast<long long>(B) * ca.Cout * hout * ca.Wp_out;
             }
             launches += 1;
-            return n->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
+            const int rr = n->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
+            mark(2, static_cast<int>(2 * bi) + (phase ? 0 : 1));
+            return rr;
         };
         auto act_raw = [&](const Sg2Layer& L, int fir, const float* style_next, __half* x_next, bool rgb, const float* prev,
                            const __half* pre, int ns_out) -> int {
@@ -707,6 +711,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             sg2_act_kernel<<<grid, 256, smem, stream>>>(a);
             MB_CUDA(cudaGetLastError());
             launches += 1;
+            mark(3, static_cast<int>(2 * bi) + (fir ? 0 : 1));
             return MB_OK;
         };
         // name_idx = position of this layer in the wrapper's layer_names (stylegan2.py:48-51): block 0 owns entries 0 and 1
@@ -728,6 +733,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
                 sg2_warp_kernel<<<grid1d(tot), 256, 0, stream>>>(T[cur_t], T[cur_t ^ 1], n->warp_mats + wi * static_cast<size_t>(B) * 6, B, r, cp);
                 MB_CUDA(cudaGetLastError());
                 launches += 1;
+                mark(4, name_idx);
                 cur_t ^= 1;
             }
             return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, T[cur_t], nsx);
@@ -737,6 +743,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout), nsx);
             MB_CUDA(cudaGetLastError());
             launches += 1;
+            mark(1, -1);
         } else {
             // conv0: X holds x * style(conv0) at r/2 -> polyphase transposed conv (four parity planes) -> FIR + act
             if ((rc = conv(b.conv0, X, r / 2, 1, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
@@ -751,6 +758,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             upsample_rgb_kernel<<<grid1d(tot), 256, 0, stream>>>(img[cur], img[cur ^ 1], B * n->img_channels, r / 2);
             MB_CUDA(cudaGetLastError());
             launches += 1;
+            mark(5, static_cast<int>(bi));
             prev = img[cur ^ 1];
         }
         const float* s_next = last ? nullptr : styles + wl.style_l[(bi + 1) * 3 + 0];
@@ -770,6 +778,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
         MB_CUDA(cudaGetLastError());
         launches += 1;
     }
+    mark(5, static_cast<int>(n->blocks.size()));
     n->last_launches = launches;
     return MB_OK;
 }

@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <functional>
+
 namespace mb {
 struct Sg2Net;
 int sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base, int channel_max, Sg2Net** out);
@@ -17,6 +19,8 @@ int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* in
 int sg2_last_launches(const Sg2Net* n);
 void sg2_set_conv_impl(Sg2Net* n, int impl);
 void sg2_set_precise(Sg2Net* n, int on);   // 1 (default): fp16 hi + lo operands and conv outputs; 0: plain fp16
+// mark(kind, layer): called after every launch group (kind: 0 styles, 1 constant input, 2 modulated conv, 3 fused FIR /
+// noise / bias_act / ToRGB kernel, 4 feature warp, 5 skip-image upsample and output conversion) for the per-launch timing
 int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void* workspace, size_t workspace_bytes,
-                int num_sms, cudaStream_t stream);
+                int num_sms, cudaStream_t stream, const std::function<void(int, int)>& mark = nullptr);
 }  // namespace mb

@@ -23,6 +23,7 @@
 // StyleGAN3 (net.cu); the feature map after conv1 has two consumers (ToRGB and the next conv0) with different
 // styles, so the fused kernel applies each while the activation tile is in shared memory.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -211,6 +212,122 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
     }
 }
 
+// Tiled form of the fused kernel for activations that come straight from a conv (no warped feature map): one CTA = (frame,
+// TH image rows, 32 pixels) x all channels.  sg2_act_kernel above reads its 16 FIR taps per output value from global memory
+// (32 loads per value with the hi / lo planes: the r2 bench line showed it at 7 % of the HBM roof, 75 % of a StyleGAN2 step).
+// Here a warp stages the (TH + 3) x 35 input patch of one channel in shared memory (hi + lo summed to fp32, the four parity
+// planes read as two interleaved coalesced streams), runs the separable [1,3,3,1] FIR from there (7 shared loads per output at
+// TH = 4), and the finished TH x 32 x C block leaves pixel-major like before.  ToRGB: one thread per (pixel, colour) walks
+// the channels of the staged block against a per-frame weight * style table.
+template <int TH>
+__global__ void __launch_bounds__(256) sg2_act_tiled_kernel(const ActArgs a) {
+    extern __shared__ float sm[];
+    constexpr int PXT = TH * kActP;             // pixels of the tile
+    constexpr int XP = PXT + 1;                 // pitch of a channel row in xs
+    constexpr int PR = TH + 3, PC = 36;         // per-warp input patch (rows x padded columns)
+    float* xs = sm;                             // [C][XP]
+    float* patch = xs + a.C * XP;               // [8 warps][PR][PC]
+    float* nz = patch + 8 * PR * PC;            // [PXT] noise of the tile
+    float* wrgb = nz + PXT;                     // [nimg][C] ToRGB weight * style of this frame
+    const int w0 = blockIdx.x * kActP, h0 = blockIdx.y * TH, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
+    for (int i = threadIdx.x; i < PXT; i += blockDim.x) {
+        const int hh = h0 + i / kActP, ww = w0 + i % kActP;
+        nz[i] = (a.noise && hh < a.R && ww < a.R) ? a.noise[b * a.noise_bstride + hh * a.R + ww] : 0.0f;
+    }
+    if (a.rgb_w)
+        for (int i = threadIdx.x; i < a.nimg * a.C; i += blockDim.x) wrgb[i] = a.rgb_w[i] * a.rgb_style[b * a.C + i % a.C];
+    __syncthreads();
+    const int hp = a.phase ? a.R / 2 + 1 : a.Hy;
+    const long long plane = static_cast<long long>(hp) * a.Wpy;
+    float* pw = patch + warp * PR * PC;
+    for (int c = warp; c < a.C; c += 8) {
+        const __half* yp = a.y + (static_cast<long long>(b) * (a.phase ? 4 : 1) * a.C + c) * plane;
+        auto at = [&](int yy, int xx) -> float {
+            const __half* q = a.phase ? yp + static_cast<long long>(((yy & 1) * 2 + (xx & 1)) * a.C) * plane + static_cast<long long>(yy >> 1) * a.Wpy + (xx >> 1)
+                                      : yp + static_cast<long long>(yy) * a.Wpy + xx;
+            float v = __half2float(*q);
+            if (a.y_lo > 0) v += __half2float(q[a.y_lo]);
+            return v;
+        };
+        const float bias = a.bias[c];
+        float outv[TH];
+        if (a.fir) {
+            // patch rows h0 - 1 .. h0 + TH + 1, columns w0 - 1 .. w0 + 33 of the (R + 1)^2 conv output, zero outside
+            for (int r = 0; r < PR; ++r) {
+                const int yy = h0 - 1 + r;
+                for (int cc = lane; cc < 35; cc += 32) {
+                    const int xx = w0 - 1 + cc;
+                    pw[r * PC + cc] = (yy >= 0 && yy < a.Hy && xx >= 0 && xx < a.Hy) ? at(yy, xx) : 0.0f;
+                }
+            }
+            __syncwarp();
+            float hrow[PR];
+#pragma unroll
+            for (int r = 0; r < PR; ++r) {
+                float t = 0.0f;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) t = fmaf(f4[kx], pw[r * PC + lane + kx], t);
+                hrow[r] = t;
+            }
+#pragma unroll
+            for (int t = 0; t < TH; ++t) {
+                float v = 0.0f;
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky) v = fmaf(f4[ky], hrow[t + ky], v);
+                outv[t] = v;
+            }
+            __syncwarp();   // the patch is free for the next channel
+        } else {
+#pragma unroll
+            for (int t = 0; t < TH; ++t) outv[t] = (h0 + t < a.R && w0 + lane < a.R) ? at(h0 + t, w0 + lane) : 0.0f;
+        }
+#pragma unroll
+        for (int t = 0; t < TH; ++t) {
+            float v = outv[t] + nz[t * kActP + lane] + bias;
+            v = (v < 0.0f ? v * 0.2f : v) * 1.41421356237309515f;
+            v = fminf(fmaxf(v, -a.clamp), a.clamp);
+            xs[c * XP + t * kActP + lane] = (h0 + t < a.R && w0 + lane < a.R) ? v : 0.0f;
+        }
+    }
+    __syncthreads();
+    const int npx = min(kActP, a.R - w0);
+    if (a.x_next) {
+        const int cpx = a.ns * a.Cp, half_cp = a.Cp / 2;
+        for (int idx = threadIdx.x; idx < PXT * half_cp; idx += blockDim.x) {
+            const int pix = idx / half_cp, c = (idx - pix * half_cp) * 2;
+            const int t = pix / kActP, px = pix - t * kActP;
+            if (px >= npx || h0 + t >= a.R) continue;
+            const float s0 = c < a.C ? (a.style_next ? a.style_next[b * a.C + c] : 1.0f) : 0.0f;
+            const float s1 = c + 1 < a.C ? (a.style_next ? a.style_next[b * a.C + c + 1] : 1.0f) : 0.0f;
+            const float v0 = c < a.C ? xs[c * XP + pix] * s0 : 0.0f;
+            const float v1 = c + 1 < a.C ? xs[(c + 1) * XP + pix] * s1 : 0.0f;
+            __half* op = a.x_next + ((static_cast<long long>(b) * a.R + h0 + t) * a.R + w0 + px) * cpx;
+            const __half2 hi = __floats2half2_rn(v0, v1);
+            *reinterpret_cast<__half2*>(op + c) = hi;
+            if (a.ns == 3) {
+                const float2 hf = __half22float2(hi);
+                *reinterpret_cast<__half2*>(op + a.Cp + c) = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+                *reinterpret_cast<__half2*>(op + 2 * a.Cp + c) = hi;
+            }
+        }
+    }
+    if (a.rgb_w) {
+        for (int item = threadIdx.x; item < PXT * a.nimg; item += blockDim.x) {
+            const int o = item / PXT, pix = item - o * PXT;
+            const int t = pix / kActP, px = pix - t * kActP;
+            if (px >= npx || h0 + t >= a.R) continue;
+            float acc = 0.0f;
+            for (int c = 0; c < a.C; ++c) acc = fmaf(xs[c * XP + pix], wrgb[o * a.C + c], acc);
+            float v = fminf(fmaxf(acc + a.rgb_bias[o], -a.clamp), a.clamp);
+            const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.R + h0 + t) * a.R + w0 + px;
+            if (a.img_prev) v += a.img_prev[oi];
+            a.img[oi] = v;
+        }
+    }
+}
+
 // Feature-map warp of the network-bending hooks (maua/GAN/wrappers/stylegan2.py:153-194: kornia translate / rotate / scale
 // with padding_mode="reflection"; kornia is an un-pinned, absent dependency: its published warp_affine = affine_grid +
 // grid_sample(bilinear, align_corners=True) is restated).  out[b, y, x, :] = bilinear sample of src[b] at
@@ -356,6 +473,7 @@ struct Sg2Net {
     bool finalized = false;
     int conv_impl = 0;
     int precise = 1;         // fp16 hi + lo operands and conv outputs (see the header); 0 = plain fp16
+    int act_tiled = 1;       // 1: sg2_act_tiled_kernel between the convs; 0: the untiled sg2_act_kernel (A/B, MB_SG2_ACT_TILED=0)
     int packed_precise = -1; // the mode the packed weights were built for
     int last_launches = 0;
     // feature-map warps applied by the next forwards (sg2_set_warps): layer = index into the wrapper's layer_names
@@ -391,6 +509,7 @@ int sg2_create(int w_dim, int img_resolution, int img_channels, int channel_base
                "mb_sg2_create: img_resolution must be a power of two in [8, 2048]");
     MB_REQUIRE(img_channels >= 1 && img_channels <= 4, "mb_sg2_create: img_channels must be 1..4");
     Sg2Net* n = new Sg2Net();
+    if (const char* ev = getenv("MB_SG2_ACT_TILED")) n->act_tiled = atoi(ev);
     n->w_dim = w_dim; n->res = img_resolution; n->img_channels = img_channels;
     auto ch = [&](int r) { int c = channel_base / r; return c < channel_max ? c : channel_max; };
     int bi = 0;
@@ -701,14 +820,28 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             a.Wpy = fir ? pitch8(r / 2 + 1) : pitch8(r);
             a.y_lo = (n->precise && n->conv_impl == 0) ? static_cast<long long>(B) * (fir ? 4 : 1) * L.cout * (fir ? r / 2 + 1 : r) * a.Wpy : 0;
             a.fir = fir; a.nimg = n->img_channels; a.clamp = 256.0f;
-            const size_t smem = sizeof(float) * L.cout * (kActP + 1);
-            static size_t smem_set = 0;
-            if (smem > 48 * 1024 && smem > smem_set) {
-                MB_CUDA(cudaFuncSetAttribute(sg2_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-                smem_set = smem;
+            if (pre == nullptr && n->act_tiled) {
+                // tiled kernel: rows per CTA by what the staged block costs in shared memory
+                const int th = (L.cout <= 128 && r >= 4) ? 4 : ((L.cout <= 256 && r >= 2) ? 2 : 1);
+                const size_t smem = sizeof(float) * (static_cast<size_t>(L.cout) * (th * kActP + 1) + 8 * (th + 3) * 36 + th * kActP + n->img_channels * L.cout);
+                auto run = [&](auto kern) -> int {
+                    MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                    dim3 grid(ceil_div(r, kActP), ceil_div(r, th), B);
+                    kern<<<grid, 256, smem, stream>>>(a);
+                    return MB_OK;
+                };
+                int rr = th == 4 ? run(sg2_act_tiled_kernel<4>) : (th == 2 ? run(sg2_act_tiled_kernel<2>) : run(sg2_act_tiled_kernel<1>));
+                if (rr != MB_OK) return rr;
+            } else {
+                const size_t smem = sizeof(float) * L.cout * (kActP + 1);
+                static size_t smem_set = 0;
+                if (smem > 48 * 1024 && smem > smem_set) {
+                    MB_CUDA(cudaFuncSetAttribute(sg2_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+                    smem_set = smem;
+                }
+                dim3 grid(ceil_div(r, kActP), r, B);
+                sg2_act_kernel<<<grid, 256, smem, stream>>>(a);
             }
-            dim3 grid(ceil_div(r, kActP), r, B);
-            sg2_act_kernel<<<grid, 256, smem, stream>>>(a);
             MB_CUDA(cudaGetLastError());
             launches += 1;
             mark(3, static_cast<int>(2 * bi) + (fir ? 0 : 1));

@@ -75,10 +75,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // parks in hardware up to the hinted time
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
@@ -90,7 +90,7 @@ __device__ __forceinline__ void dbg_inc(volatile int* dbg, int idx) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dbg = nullptr, int tag = 0) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) {
+        if (++spins > (1u << 20)) {
             if (dbg) {
                 dbg[16] = tag;
                 dbg[17] = blockIdx.x;

@@ -48,6 +48,10 @@ struct KArgs {
     const float* bias;  // [Cout] or nullptr
     __half* y;
     long long plane_out;  // Hout * Wp_out
+    // output addressing: element (b, co, h, w) lives at y + b * Cout * plane_out + co * cs + h * rs + w.
+    // planar [B][C][H][Wp]: cs = plane_out, rs = Wp_out;  row-interleaved [B][H][C][Wp]: cs = Wp_out, rs = Cout * Wp_out
+    // (the couts of one image row share a 2 MB page: the narrow layers' epilogues touch 32+ planes per tile)
+    long long cs, rs;
     int* dbg;             // debug words (mapped host memory) or nullptr
     // shared-memory plan (conv_tc_launch): see the layout comment in conv_tc_kernel
     int a_tile_bytes;     // one [a_rows x 64] weight tile (a_rows = 128, or ceil8(Cout) when Cout fits one M tile)
@@ -64,6 +68,11 @@ struct KArgs {
     // (L13: 0.51 ms product path; shift mode 0.46 ms without its stores, 0.70 ms with every store aimed at two planes,
     // 1.03-1.08 ms with the real 32-plane scatter, aligned or not; 0.90 ms with direct per-lane 4-byte stores).
     int shift, tile_wv;
+    // shift = 2 (EG > 1 kernel): the patch is TW + 2 pixels wide, so every shifted window keeps all TW output columns of a row
+    // and the tile origin stays a multiple of 32 pixels (aligned vector stores).  Accumulator column n = r * (TW + 2) + c: a tile
+    // is th = 7 image rows inside one N = 240 instruction, the epilogue reads row r from TMEM columns [34 r, 34 r + 32).
+    int th, slab, colp, nchunks, mma_n, patch_tx;
+    int st256;             // 1: the output row pitch is a multiple of 16 pixels -> 32-byte stores (EG > 1 epilogue)
     long long lo_off;      // > 0: split output -- y holds fp16(v), y + lo_off holds fp16(v - fp16(v)) (fp32-class precision for
                            // consumers that add the two; cout-major tile without shift only)
     unsigned int* absmax;  // device word or nullptr: atomicMax of the bits of max |y| over the stored outputs (read by the
@@ -80,8 +89,61 @@ __device__ __forceinline__ void publish_abs(unsigned int* dst, const __half2& m)
     if ((threadIdx.x & 31) == 0) atomicMax(dst, __float_as_uint(f));   // non-negative floats order like their bit patterns
 }
 
-template <int TW>
-__global__ void __launch_bounds__(256, 1)
+// tcgen05.wait::ld with the destination registers as in/out operands: uses of `r` cannot be scheduled above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// One 32-column accumulator chunk of a cout-major tile (lane = cout): *d + bias -> fp16 -> the lane's row segments of the
+// planar output.  ST256: 32-byte stores (row pitch and tile origin are multiples of 16 pixels), else 16-byte stores.
+template <int TW, bool ST256>
+__device__ __forceinline__ void epi_chunk_planar(const uint32_t (&v)[32], int n0, float scale, float bias, __half* yplane, int h0,
+                                                 int w0, int Hout, int Wp_out, long long rs, __half2& amax) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) {
+        const __half2 hv = __floats2half2_rn(fmaf(__uint_as_float(v[2 * k2]), scale, bias), fmaf(__uint_as_float(v[2 * k2 + 1]), scale, bias));
+        track_abs(amax, hv);
+        pk[k2] = *reinterpret_cast<const uint32_t*>(&hv);
+    }
+    if constexpr (ST256) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            const int n = n0 + g * 16;
+            const int h = h0 + n / TW;
+            const int w = w0 + n % TW;
+            if (h < Hout && w < Wp_out)
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yplane + h * rs + w),
+                             "r"(pk[8 * g]), "r"(pk[8 * g + 1]), "r"(pk[8 * g + 2]), "r"(pk[8 * g + 3]), "r"(pk[8 * g + 4]), "r"(pk[8 * g + 5]),
+                             "r"(pk[8 * g + 6]), "r"(pk[8 * g + 7])
+                             : "memory");
+        }
+    } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int n = n0 + g * 8;
+            const int h = h0 + n / TW;
+            const int w = w0 + n % TW;
+            if (h < Hout && w < Wp_out)
+                *reinterpret_cast<uint4*>(yplane + h * rs + w) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+        }
+    }
+}
+
+// EG = number of epilogue warp groups (4 warps each: one per TMEM lane quadrant).  EG = 1 is the general kernel.  With few
+// couts only the first quadrant(s) hold real rows and ONE warp per quadrant cannot drain a 256-column accumulator in the time
+// the tensor core needs to fill the next (L13 of StyleGAN3-T: 2 304 MMA cycles per tile against ~5 400 epilogue cycles on the
+// single warp that owns couts 0..31).  EG > 1 adds warps 8.. whose quadrant is again warp % 4: the groups split the
+// tile's eight 32-column chunks between them, each warp double-buffers its tcgen05.ld against the convert / store of the
+// previous chunk, and the accumulator is handed back as soon as the last load has landed.
+template <int TW, int EG>
+__global__ void __launch_bounds__(128 + 128 * EG, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, KArgs a) {
     using G = Geo<TW>;
     extern __shared__ uint8_t smem_raw[];
@@ -107,9 +169,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int pad = a.pad;
-    const int patch_rows = G::TH + a.ksz - 1;
     const int a_bytes_stage = a.resident ? 0 : a.ksz * a.a_tile_bytes;
-    const uint32_t stage_tx = a_bytes_stage + patch_rows * G::SLAB;
+    const uint32_t stage_tx = a_bytes_stage + a.patch_tx;
     const int iters = a.ksz * a.nCC;
 
     if (threadIdx.x == 0) {
@@ -122,7 +183,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         mbar_init(wfull, 1);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&tempty[s], 4 * EG);
         }
         fence_barrier_init();
     }
@@ -155,7 +216,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const int wt = r % a.tiles_w; r /= a.tiles_w;
                 const int ht = r % a.tiles_h; r /= a.tiles_h;
                 const int b = r;
-                const int h0 = ht * G::TH, w0 = wt * a.tile_wv, m0 = mt * kTileM;
+                const int h0 = ht * a.th, w0 = wt * a.tile_wv, m0 = mt * kTileM;
                 const int nkw = a.shift ? 1 : a.ksz;
                 for (int kw = 0; kw < nkw; ++kw) {
                     for (int cc = 0; cc < a.nCC; ++cc) {
@@ -180,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
         // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
         {
             const bool leader = elect_one();
-            constexpr uint32_t idesc = make_idesc_f16(kTileM, kTileN, /*A K-major*/ 0, /*B K-major*/ 0);
+            const uint32_t idesc = make_idesc_f16(kTileM, a.mma_n, /*A K-major*/ 0, /*B K-major*/ 0);
             int s = 0;
             uint32_t ph = 0;
             int acc = 0;
@@ -212,7 +273,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 #pragma unroll 4
                                     for (int j = 0; j < nk16; ++j) {
                                         umma_f16(d_tmem, da + static_cast<uint64_t>((kh * a.a_tile_bytes + j * 32) >> 4),
-                                                 db + static_cast<uint64_t>((kh * G::SLAB + j * 32) >> 4), idesc, accumulate);
+                                                 db + static_cast<uint64_t>((kh * a.slab + j * 32) >> 4), idesc, accumulate);
                                         accumulate = 1;
                                     }
                                 }
@@ -242,6 +303,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 if (++acc == 2) { acc = 0; acc_ph ^= 1; }
             }
         }
+    } else if (warp >= 4 && EG > 1) {
+        // ===================== epilogue, EG groups (no shift mode, no split output) =====================
+        const int q = warp & 3;           // TMEM lane quadrant == warp % 4
+        const int grp = (warp - 4) >> 2;  // this warp handles chunks grp, grp + EG, ...
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
+        const int kChunks = a.nchunks;   // one chunk = one image row of the tile (TW = 32)
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int mt = r % a.tiles_m; r /= a.tiles_m;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            const int h0 = ht * a.th, w0 = wt * TW;
+            const int co = mt * kTileM + q * 32 + lane;
+            const bool q_ok = mt * kTileM + q * 32 < a.Cout && grp < kChunks;   // warp-uniform
+            const bool co_ok = co < a.Cout;
+            const float scale = (co_ok && a.d) ? a.d[b * a.Cout + co] : (co_ok ? 1.0f : 0.0f);
+            const float bias = (co_ok && a.bias) ? a.bias[co] : 0.0f;
+            // lanes past the last cout compute zeros and aim at the last real plane with their stores predicated off
+            __half* yplane = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + (co_ok ? co : 0) * a.cs;
+            const int hlim = co_ok ? a.Hout : 0;   // 0 switches a lane's stores off
+            mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
+            tc_fence_after();
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            };
+            if (q_ok) {
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kTileN;
+                uint32_t va[32], vb[32];
+                int ch = grp;
+                tmem_ld_32x32b_x32(tb + ch * a.colp, va);
+                for (;;) {
+                    int nx = ch + EG;
+                    tmem_ld_wait_dep(va);
+                    if (nx < kChunks) tmem_ld_32x32b_x32(tb + nx * a.colp, vb); else release();
+                    if (a.st256) epi_chunk_planar<TW, true>(va, ch * 32, scale, bias, yplane, h0, w0, hlim, a.Wp_out, a.rs, amax);
+                    else epi_chunk_planar<TW, false>(va, ch * 32, scale, bias, yplane, h0, w0, hlim, a.Wp_out, a.rs, amax);
+                    if (nx >= kChunks) break;
+                    ch = nx; nx = ch + EG;
+                    tmem_ld_wait_dep(vb);
+                    if (nx < kChunks) tmem_ld_32x32b_x32(tb + nx * a.colp, va); else release();
+                    if (a.st256) epi_chunk_planar<TW, true>(vb, ch * 32, scale, bias, yplane, h0, w0, hlim, a.Wp_out, a.rs, amax);
+                    else epi_chunk_planar<TW, false>(vb, ch * 32, scale, bias, yplane, h0, w0, hlim, a.Wp_out, a.rs, amax);
+                    if (nx >= kChunks) break;
+                    ch = nx;
+                }
+            } else {
+                release();
+            }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+        publish_abs(a.absmax, amax);
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp - 4;  // TMEM lane quadrant == warp % 4
@@ -259,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             const bool co_ok = co < a.Cout;
             const float scale = (co_ok && a.d) ? a.d[b * a.Cout + co] : 1.0f;
             const float bias = (co_ok && a.bias) ? a.bias[co] : 0.0f;
-            __half* yplane = a.y + (static_cast<long long>(b) * a.Cout + (co_ok ? co : 0)) * a.plane_out;
+            __half* yplane = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + (co_ok ? co : 0) * a.cs;
 
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
@@ -330,7 +447,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                             pk.y = *reinterpret_cast<uint32_t*>(&h1v);
                             pk.z = *reinterpret_cast<uint32_t*>(&h2v);
                             pk.w = *reinterpret_cast<uint32_t*>(&h3v);
-                            *reinterpret_cast<uint4*>(yplane + static_cast<long long>(h) * a.Wp_out + w) = pk;
+                            *reinterpret_cast<uint4*>(yplane + h * a.rs + w) = pk;
                             if (a.lo_off > 0) {
                                 // the part of each value its fp16 rounding dropped, as a second fp16 plane
                                 const __half2 hs[4] = {h0v, h1v, h2v, h3v};
@@ -577,7 +694,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                 const int h = ht * kPmTH + half * 4 + q;
                 const bool ok = w_ok && h < a.Hout;
                 // this lane's cout plane of pair k is (2k + par); it stores pixels (w & ~1, w | 1)
-                __half* yp = a.y + (static_cast<long long>(b) * a.Cout + par) * a.plane_out + static_cast<long long>(h) * a.Wp_out + (w & ~1);
+                __half* yp = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + par * a.cs + h * a.rs + (w & ~1);
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * Np + half * Np;
 #pragma unroll 1
                 for (int c0 = 0; c0 < Np; c0 += 16) {
@@ -595,9 +712,227 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
                         const uint32_t pr = __byte_perm(m, o, sel);
                         const int co = c0 + 2 * k + par;
                         if (ok && co < a.Cout)
-                            *reinterpret_cast<uint32_t*>(yp + static_cast<long long>(c0 + 2 * k) * a.plane_out) = pr;
+                            *reinterpret_cast<uint32_t*>(yp + (c0 + 2 * k) * a.cs) = pr;
                     }
                 }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+        publish_abs(a.absmax, amax);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pixel-major tile with the three kw taps STACKED ALONG N ("pms"), for 3x3 layers with few couts.
+// Both orientations above waste the tensor pipe on such layers: the cout-major tile executes M = 128 rows for 32..51
+// real couts (L12 / L13 of StyleGAN3-T run at 1.35..1.6 PFLOP/s EXECUTED, the power-capped ceiling, for 310..340 useful),
+// the pixel-major tile pays a fixed ~64 cycles of A-operand read per instruction whatever N is (t = 64 + N/2).  Here
+//     D[128 patch pixels, (kw, cout)] += A[128 patch pixels, (kh, cin)] * B[(kh, cin), (kw, cout)],   N = 3 * Np,
+// so one instruction does the work of three (the A read is amortised over three taps and K shrinks from 9 Cin to 3 Cin),
+// every executed row is a real pixel, and the kw shift never touches a descriptor: output pixel p of a row needs
+//     y[p, c] = D[p, (0, c)] + D[p + 1, (1, c)] + D[p + 2, (2, c)],
+// TMEM lane = pixel, so the epilogue adds its own column of the kw = 0 block to the lane + 1 / lane + 2 values of the
+// kw = 1 / 2 blocks (two SHFL.DOWN per value).  Lanes 30 and 31 of a row have no right-hand neighbours: a tile is 30
+// output pixels wide on a 32-pixel patch, as in the single-load pixel-major tile.  One patch load per 64-channel chunk,
+// weights resident: the stacked B tile of (chunk, kh) is three TMA boxes of the ordinary packed matrix (one per kw)
+// landing back to back.  NH = 4-row halves per tile sharing one patch (2 where the accumulators 2 x NH x 3 Np fit the 512
+// TMEM columns, i.e. Np <= 32; 1 otherwise).
+struct PmsArgs {
+    KArgs k;
+    int Np, Nst, stages;
+};
+
+template <int NH>
+__global__ void __launch_bounds__(384, 1)
+conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, PmsArgs pa) {
+    const KArgs& a = pa.k;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int TH = 4 * NH;
+    constexpr int kPatch = (TH + 2) * kPmSlab;
+    const int nst = pa.stages;
+    const int Np = pa.Np, Nst = pa.Nst;
+    const int w_tile = Np * 128;                   // bytes of one [Np x 64] weight tile
+    const int n_wtiles = 9 * a.nCC;
+    // layout: [resident weight tiles, (chunk, kh, kw) order | patch stages | (scale, bias) tables | barriers]
+    uint8_t* stages = smem + n_wtiles * w_tile;
+    float2* sc_tab = reinterpret_cast<float2*>(stages + nst * kPatch);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sc_tab + 4 * 128);
+    uint64_t* full = bars;                         // [kPmMaxStages]
+    uint64_t* empty = bars + kPmMaxStages;         // [kPmMaxStages]
+    uint64_t* tfull = bars + 2 * kPmMaxStages;     // [2]
+    uint64_t* tempty = bars + 2 * kPmMaxStages + 2;  // [2]
+    uint64_t* wfull = bars + 2 * kPmMaxStages + 4;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kPmMaxStages + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int pad = a.pad;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 8);
+        }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        if (leader && blockIdx.x < a.total_tiles) {
+            mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(n_wtiles * w_tile));
+            for (int cc = 0; cc < a.nCC; ++cc)
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw)
+                        tma_load_2d(smem + ((cc * 3 + kh) * 3 + kw) * w_tile, &tmap_w, wfull, ((kw * a.nCC + cc) * 3 + kh) * kKC, 0);
+        }
+        __syncwarp();
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            for (int cc = 0; cc < a.nCC; ++cc) {
+                mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
+                if (leader) {
+                    mbar_arrive_expect_tx(&full[s], kPatch);
+                    tma_load_4d(stages + s * kPatch, &tmap_x, &full[s], cc * kKC, wt * 30 - pad, ht * TH - pad, b);
+                }
+                __syncwarp();
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(128, Nst, 0, 0);
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        if (blockIdx.x < a.total_tiles) mbar_wait(wfull, 0, a.dbg, 5);
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * NH * Nst;
+            uint32_t accumulate = 0;
+            for (int cc = 0; cc < a.nCC; ++cc) {
+                int nk16 = (a.Cin - cc * kKC + 15) / 16;
+                if (nk16 > 4) nk16 = 4;
+                mbar_wait(&full[s], ph, a.dbg, 3);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t dx = make_smem_desc(smem_u32(stages + s * kPatch), 16, 1024, 2);
+                    const uint64_t dw = make_smem_desc(smem_u32(smem) + cc * 9 * w_tile, 16, 1024, 2);
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll 4
+                        for (int j = 0; j < nk16; ++j) {
+                            const uint64_t dwk = dw + static_cast<uint64_t>((kh * 3 * w_tile + j * 32) >> 4);
+                            const uint64_t dxk = dx + static_cast<uint64_t>((kh * kPmSlab + j * 32) >> 4);
+#pragma unroll
+                            for (int hf = 0; hf < NH; ++hf)
+                                umma_f16(d_tmem + hf * Nst, dxk + static_cast<uint64_t>((hf * 4 * kPmSlab) >> 4), dwk, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+            if (leader) umma_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else if (warp >= 4) {
+        // Two warps per TMEM lane quadrant (warps 4..7 and 8..11; quadrant = warp % 4 = image row of the half tile) share a
+        // tile's (half, 16-cout block) units alternately: one warp per quadrant is issue-latency bound at ~1 200 instructions
+        // per tile (ncu r2: tensor pipe 23 % busy, the epilogue warps stalled on the SHFL -> FADD / PRMT scoreboard).
+        const int q = warp & 3;
+        const int eg = (warp - 4) >> 2;
+        float2* tab = sc_tab + q * 128;   // shared by the two warps of a quadrant; refreshed by group 0 under a named barrier
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        int tab_b = -1;
+        const int nblk = Np >> 4;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            if (b != tab_b) {  // uniform over both warps of the quadrant
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the other warp is done with the old table
+                if (eg == 0)
+                    for (int i = lane; i < Np; i += 32) {
+                        const bool ok = i < a.Cout;
+                        tab[i] = make_float2((ok && a.d) ? a.d[b * a.Cout + i] : (ok ? 1.0f : 0.0f), (ok && a.bias) ? a.bias[i] : 0.0f);
+                    }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                tab_b = b;
+            }
+            const int w = wt * 30 + lane;
+            const bool w_ok = w < a.Wout && lane < 30;
+            __half* ybase = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + w;
+            mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NH * Nst;
+            int hf = 0, cb = eg;   // unit u = hf * nblk + cb, u = eg, eg + 2, ...
+            while (cb >= nblk) { cb -= nblk; ++hf; }
+#pragma unroll 1
+            while (hf < NH) {
+                const int c0 = cb << 4;
+                const int h = ht * TH + hf * 4 + q;
+                const bool ok = w_ok && h < a.Hout;
+                const uint32_t taddr = tacc + hf * Nst + c0;
+                uint32_t v0[16], v1[16], v2[16];
+                tmem_ld_32x32b_x16(taddr, v0);
+                tmem_ld_32x32b_x16(taddr + Np, v1);
+                tmem_ld_32x32b_x16(taddr + 2 * Np, v2);
+                tmem_ld_wait();
+                float sum[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    sum[k] = (__uint_as_float(v0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1)) +
+                             __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2);
+                // lane = pixel: a warp's 2-byte stores of one cout cover 64 contiguous bytes of its row (no pair-swap shuffles)
+                __half* yp = ybase + h * a.rs + c0 * a.cs;
+                const float4* tp = reinterpret_cast<const float4*>(tab + c0);
+                const int nco = a.Cout - c0;   // real couts in this block (>= 16 except in the last one)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float4 sb = tp[k];  // (d, bias) of couts c, c+1
+                    const __half2 mine = __floats2half2_rn(fmaf(sum[2 * k], sb.x, sb.y), fmaf(sum[2 * k + 1], sb.z, sb.w));
+                    if (lane < 30) track_abs(amax, mine);   // lanes 30 / 31 hold incomplete sums; padded couts carry (0, 0)
+                    if (ok && 2 * k < nco) *yp = __low2half(mine);
+                    if (ok && 2 * k + 1 < nco) *(yp + a.cs) = __high2half(mine);
+                    yp += 2 * a.cs;
+                }
+                cb += 2;
+                while (cb >= nblk) { cb -= nblk; ++hf; }
             }
             tc_fence_before();
             __syncwarp();
@@ -625,7 +960,14 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     const int Np = round_up(p.Cout, 16);
     // pixel-major pays off where the cout-major tile wastes >= half of its M rows and K is deep enough to amortise
     // the per-tile epilogue (B200 A/B, r1: L11 1.38 -> 1.23 ms, L12 0.77 -> 0.66 ms, but L13 with Cin = 32 0.50 -> 0.60 ms)
-    const bool pixel_major = p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && (p.Cin > 32 || p.pm_max_cout > 64);
+    // stacked pixel-major tile (conv_pms_kernel): 3x3 layers whose three kw blocks fit one instruction (3 Np <= 256) and whose
+    // weights stay resident next to two patch stages
+    const int pms_nh = (p.pm_max_cout > 0 && p.pm_stack && p.ksz == 3 && Np <= p.pm_max_cout && 3 * Np <= 256 && p.split_lo_off <= 0)
+                           ? ((12 * Np <= 512 && 9 * ceil_div(p.Cin, kKC) * Np * 128 + 2 * 10 * kPmSlab + 1024 + 4096 + 256 <= kSmemMax) ? 2
+                              : (9 * ceil_div(p.Cin, kKC) * Np * 128 + 2 * 6 * kPmSlab + 1024 + 4096 + 256 <= kSmemMax ? 1 : 0))
+                           : 0;
+    // (1x1 layers, StyleGAN3-R: the cout-major tile with three epilogue groups and 32-byte stores wins, 1.92 -> 1.37 ms on L12 / L13)
+    const bool pixel_major = pms_nh > 0 || (p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && ((p.Cin > 32 && p.ksz > 1) || p.pm_max_cout > 64));
     const int tw = pixel_major ? kPmTW : (p.tile_w == 16 ? 16 : 32);
     const int th = kTileN / tw;
     const int pad = p.pad;
@@ -643,10 +985,15 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     // shared-memory plan of the cout-major kernel (layout comment in conv_tc_kernel)
     const int a_rows = (Mp == kTileM && p.narrow_a) ? round_up(p.Cout, 8) : kTileM;
     const int a_tile_bytes = a_rows * kKC * 2;
-    const int patch_bytes = (th + halo) * tw * 128;
     const int w_all = p.ksz * p.ksz * nCC * a_tile_bytes;
+    // shift 2 (KArgs::th): 34-pixel-wide patch of 9 image rows; the windows of the two unused accumulator columns per row
+    // and of columns 238..239 read up to pixel row 309 of the stage
+    const int patch2_alloc = 40960, patch2_tx = 9 * 34 * 128;
+    const bool shift2 = !pixel_major && p.cm_shift == 2 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM && p.split_lo_off <= 0 &&
+                        (p.epi_groups == 0 || p.epi_groups == 3) && w_all + 2 * patch2_alloc + 1024 + 256 <= kSmemMax;
+    const int patch_bytes = shift2 ? patch2_alloc : (th + halo) * tw * 128;
     // shift mode (one patch load per chunk, see KArgs) needs resident weights and room for its epilogue staging tiles
-    const bool want_shift = !pixel_major && p.cm_shift && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
+    const bool want_shift = !pixel_major && p.cm_shift == 1 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
                             w_all + 2 * patch_bytes + 1024 + 256 + kEpiStageBytes <= kSmemMax;
     MB_REQUIRE(p.split_lo_off <= 0 || (!pixel_major && !want_shift), "conv_tc: the split output needs the plain cout-major tile");
     const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (want_shift ? kEpiStageBytes : 0);
@@ -679,7 +1026,8 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cp_in), static_cast<cuuint64_t>(p.Win),
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
         cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
-        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th + halo), 1};
+        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(shift2 ? 34 : tw),
+                             static_cast<cuuint32_t>(pms_nh ? 4 * pms_nh + 2 : (shift2 ? 9 : th + halo)), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -701,9 +1049,13 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
     a.d = p.d; a.bias = p.bias; a.y = p.y;
     a.plane_out = static_cast<long long>(a.Hout) * p.Wp_out;
+    a.cs = p.row_interleaved ? p.Wp_out : a.plane_out;
+    a.rs = p.row_interleaved ? static_cast<long long>(p.Cout) * p.Wp_out : p.Wp_out;
+    MB_REQUIRE(!p.row_interleaved || (p.split_lo_off <= 0 && p.cm_shift != 1), "conv_tc: the row-interleaved output needs a plain epilogue");
     a.dbg = debug_words_device();
     a.absmax = p.absmax;
     a.lo_off = p.split_lo_off;
+    a.st256 = 0;
     a.a_tile_bytes = a_tile_bytes;
     a.resident = resident ? 1 : 0;
     a.nstages = nstages;
@@ -714,7 +1066,43 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         a.tiles_w = ceil_div(a.Wout, a.tile_wv);
         a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
     }
+    a.th = th; a.slab = tw * 128; a.colp = 32; a.nchunks = kTileN / 32; a.mma_n = kTileN; a.patch_tx = (th + halo) * tw * 128;
+    if (shift2) {
+        MB_REQUIRE(resident, "conv_tc: shift 2 needs resident weights");
+        a.shift = 2;
+        a.th = 7; a.slab = 34 * 128; a.colp = 34; a.nchunks = 7; a.mma_n = 240; a.patch_tx = patch2_tx;
+        a.tiles_h = ceil_div(a.Hout, a.th);
+        a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
+    }
 
+    if (pms_nh) {
+        PmsArgs pa;
+        pa.k = a;
+        pa.Np = Np; pa.Nst = 3 * Np;
+        pa.k.tiles_m = 1;
+        pa.k.tiles_w = ceil_div(a.Wout, 30);
+        pa.k.tiles_h = ceil_div(a.Hout, 4 * pms_nh);
+        pa.k.total_tiles = p.B * pa.k.tiles_h * pa.k.tiles_w;
+        const int patch = (4 * pms_nh + 2) * kPmSlab;
+        const int fixed = 1024 + 4096 + 256;
+        const int w_all_pm = 9 * nCC * Np * 128;
+        pa.stages = (kSmemMax - fixed - w_all_pm) / patch;
+        if (pa.stages > kPmMaxStages) pa.stages = kPmMaxStages;
+        MB_REQUIRE(pa.stages >= 2, "conv_tc: stacked pixel-major shared-memory plan does not fit");
+        const int smem_bytes = fixed + w_all_pm + pa.stages * patch;
+        static bool attr_pms = false;
+        if (!attr_pms) {
+            MB_CUDA(cudaFuncSetAttribute(conv_pms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_pms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            attr_pms = true;
+        }
+        int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
+        if (grid < 1) grid = 1;
+        if (pms_nh == 2) conv_pms_kernel<2><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        else conv_pms_kernel<1><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
     if (pixel_major) {
         PmArgs pa;
         pa.k = a;
@@ -754,20 +1142,36 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     }
     int grid = a.total_tiles < p.num_sms ? a.total_tiles : p.num_sms;
     if (grid < 1) grid = 1;
-    if (tw == 32) {
+    // Epilogue groups: one warp per TMEM quadrant drains a 256-column accumulator in ~5 400 cycles (measured, L13); the tensor
+    // core fills the next one in 128 cycles per K = 16 step.  Three groups where the MMA time per tile is below that, or where
+    // few couts leave most quadrants idle.
+    int mma_steps = 0;
+    for (int cc = 0; cc < nCC; ++cc) mma_steps += p.ksz * p.ksz * ((p.Cin - cc * kKC + 15) / 16 > 4 ? 4 : (p.Cin - cc * kKC + 15) / 16);
+    int eg = p.epi_groups;
+    if (eg == 0) eg = (tw == 32 && a.shift != 1 && a.lo_off <= 0 && (a.shift == 2 || mma_steps * 128 < 6000 || p.Cout <= 64)) ? 3 : 1;
+    MB_REQUIRE((eg == 1 && a.shift != 2) || (eg == 3 && tw == 32 && a.shift != 1 && a.lo_off <= 0), "conv_tc: epilogue groups %d unsupported here", eg);
+    a.st256 = (p.Wp_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) ? 1 : 0;
+    if (tw == 32 && eg == 3) {
         static bool attr_done = false;
         if (!attr_done) {
-            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_done = true;
         }
-        conv_tc_kernel<32><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
+        conv_tc_kernel<32, 3><<<grid, 512, smem_cm, stream>>>(tm_w, tm_x, a);
+    } else if (tw == 32) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            attr_done = true;
+        }
+        conv_tc_kernel<32, 1><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
     } else {
         static bool attr_done = false;
         if (!attr_done) {
-            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_done = true;
         }
-        conv_tc_kernel<16><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
+        conv_tc_kernel<16, 1><<<grid, 256, smem_cm, stream>>>(tm_w, tm_x, a);
     }
     MB_CUDA(cudaGetLastError());
     return MB_OK;

@@ -1020,6 +1020,7 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
     // (kept for A/B runs and as the path of the op-level API with a separate bias).
     const char* sev = getenv("MB_FLRELU_STREAM");   // read per call: the A/B tests flip it inside one process
     const int use_stream = sev ? atoi(sev) : 1;
+    MB_REQUIRE(!a.in_row_interleaved || (use_stream && a.bias == nullptr), "filtered_lrelu: the row-interleaved input needs the streaming kernels");
     if (use_stream && a.bias == nullptr) {
         using S = SC<UP>;
         const int sms = a.num_sms > 0 ? a.num_sms : 148;
@@ -1068,11 +1069,12 @@ int launch(const FlreluArgs& a, cudaStream_t stream) {
                 return MB_ECUDA;
             }
             MB_REQUIRE(a.Wp_in % 8 == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15) == 0, "filtered_lrelu: input rows must be 16-byte aligned");
-            cuuint64_t dims[3] = {static_cast<cuuint64_t>(a.Win), static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.B) * a.C};
-            cuuint64_t strides[2] = {static_cast<cuuint64_t>(a.Wp_in) * 2, static_cast<cuuint64_t>(a.Wp_in) * 2 * a.Hin};
-            cuuint32_t box[3] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(S::BOXROWS), 1};
-            cuuint32_t es[3] = {1, 1, 1};
-            CUresult cr = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(a.x), dims, strides, box, es,
+            const cuuint64_t row_b = static_cast<cuuint64_t>(a.Wp_in) * 2;
+            cuuint64_t dims[4] = {static_cast<cuuint64_t>(a.Win), static_cast<cuuint64_t>(a.Hin), static_cast<cuuint64_t>(a.C), static_cast<cuuint64_t>(a.B)};
+            cuuint64_t strides[3] = {a.in_row_interleaved ? row_b * a.C : row_b, a.in_row_interleaved ? row_b : row_b * a.Hin, row_b * a.Hin * a.C};
+            cuuint32_t box[4] = {static_cast<cuuint32_t>(kXP), static_cast<cuuint32_t>(S::BOXROWS), 1, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult cr = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(a.x), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (cr != CUDA_SUCCESS) {

@@ -132,10 +132,12 @@ __device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
         if (++spins > (1u << 20)) __trap();
     }
 }
-__device__ __forceinline__ void tma_box_3d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2) {
+// the input as a 4-D tensor (x, row, channel, frame): planar [B][C][H][Wp] and row-interleaved [B][H][C][Wp] conv outputs
+// differ only in the strides of the tensor map
+__device__ __forceinline__ void tma_box_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     const uint32_t xlane = ring + static_cast<uint32_t>((g * kXP + (first_in<UP>(0, p.px0, p.e) & 7) + 2 * tig) * 2);
 
     // ---- load cursor (meaningful in lane 0 only): next (item, box) this warp fetches ----
-    int l_item = static_cast<int>(blockIdx.x) - G, l_left = 0, l_plane = 0, l_ixa = 0, l_row = 0;
+    int l_item = static_cast<int>(blockIdx.x) - G, l_left = 0, l_chan = 0, l_frame = 0, l_ixa = 0, l_row = 0;
     auto refill = [&](int slot) {
         while (l_left == 0) {   // next item in which this warp has a share
             l_item += G;
@@ -232,12 +234,12 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             int c, oy0;
             if (!warp_share(p, it, warp, c, oy0)) continue;
             l_left = it.R + ((UP == 2) ? 1 : 2);   // up=2: 2R+2 row blocks in 16-row boxes, up=4: R+2 8-row boxes
-            l_plane = it.b * p.C + c;
+            l_chan = c; l_frame = it.b;
             l_ixa = first_in<UP>(it.tx * kOT, p.px0, p.e) & ~7;
             l_row = first_in<UP>(oy0, p.px0, p.e);
         }
         sbar_expect_tx(xbar_a + 8 * slot, S::BOXBYTES);
-        tma_box_3d(ring + slot * S::BOXBYTES, &tmap_x, xbar_a + 8 * slot, l_ixa, l_row, l_plane);
+        tma_box_4d(ring + slot * S::BOXBYTES, &tmap_x, xbar_a + 8 * slot, l_ixa, l_row, l_chan, l_frame);
         l_row += S::BOXROWS;
         --l_left;
     };

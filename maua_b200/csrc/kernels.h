@@ -15,6 +15,7 @@
 namespace mb {
 
 static inline int pitch8(int w) { return (w + 7) / 8 * 8; }
+static inline int pitch16(int w) { return (w + 15) / 16 * 16; }
 
 // ---- conv_tc.cu ------------------------------------------------------------------------
 struct ConvTcArgs {
@@ -27,9 +28,12 @@ struct ConvTcArgs {
     int pad;            // zero padding per side (StyleGAN3: ksz-1 'full', StyleGAN2: ksz/2 'same'); output = in + 2*pad - (ksz-1)
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
     int pm_max_cout = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major tile (0 = never)
+    int pm_stack = 1;      // 3x3 layers with 3 * ceil16(Cout) <= 256: pixel-major tile with the kw taps stacked along N (conv_pms_kernel)
     int pm_shift = 1;      // pixel-major tile: 1 / 2 = one patch load per chunk, kw shifts through the A descriptor start
     int cm_shift = 0;      // cout-major tile with resident weights: one patch load per chunk, kw shifts through the B descriptor start
                            // (correct, measured slower than per-kw loads: see KArgs::shift in conv_tc.cu)
+    int row_interleaved = 0;  // 1: output layout [B][H][Cout][Wp_out] instead of planar [B][Cout][H][Wp_out]
+    int epi_groups = 0;    // cout-major tile: epilogue warp groups (0 = chosen per layer, 1 = one warp per TMEM quadrant, 3)
     int narrow_a = 1;      // Cout <= 128: load only ceil8(Cout) weight rows per tile and keep them resident when they fit
     int num_sms;
     long long split_lo_off = 0;      // > 0: also store fp16(v - fp16(v)) at y + split_lo_off (needs the cout-major tile: pm_max_cout = 0, cm_shift = 0)
@@ -135,6 +139,7 @@ struct FlreluArgs {
     int px0, py0;        // leading padding of the zero-inserted signal (may be negative = crop)
     float gain, slope, clamp;
     int num_sms;
+    int in_row_interleaved = 0;  // 1: x is [B][Hin][C][Wp_in] (ConvTcArgs::row_interleaved) instead of planar; streaming kernels only
     const unsigned int* in_absmax = nullptr;  // device word: bits of max |x| over the input (ConvTcArgs::absmax), or nullptr
 };
 int flrelu_launch(const FlreluArgs& a, cudaStream_t stream);

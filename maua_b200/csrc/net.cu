@@ -86,6 +86,9 @@ struct mb_net {
     bool finalized = false;
     int conv_impl = 0;
     int conv_tile_w = 32;
+    int conv_row_il = 0;      // conv outputs of layers with at most this many couts use the row-interleaved layout [B][H][C][Wp]
+    int conv_pm_stack = 1;    // stacked pixel-major conv tile for the narrow 3x3 layers (conv_pms_kernel)
+    int conv_epi_groups = 0;  // cout-major conv tile: epilogue warp groups (0 = per layer, see conv_tc_launch)
     int conv_pm_max = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major conv tile
     int conv_narrow_a = 1; // narrow/resident weight tiles for Cout <= 128 (conv_tc.cu)
     int conv_cm_shift = 0; // cout-major tile with resident weights: one patch load per chunk (conv_tc.cu)
@@ -553,7 +556,7 @@ WsLayout ws_layout(const mb_net* net, int B, const SizePlan& sp) {
             // pre-hook output of this layer in channels-last form (what the fused filtered_lrelu writes)
             const size_t xout = static_cast<size_t>(B) * ls.hout * ls.wout * cpad8(L.g.out_channels);
             if (xout > max_x) max_x = xout;
-            const size_t y = static_cast<size_t>(B) * L.g.out_channels * ls.hc * pitch8(ls.wc);
+            const size_t y = static_cast<size_t>(B) * L.g.out_channels * ls.hc * pitch16(ls.wc);
             if (y > max_y) max_y = y;
             const size_t po = static_cast<size_t>(B) * L.g.out_channels * ls.hout * pitch8(ls.wout);
             if (po > max_p) max_p = po;
@@ -656,6 +659,9 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     }
     else if (k == "conv_tile_w") net->conv_tile_w = value == 16 ? 16 : 32;
     else if (k == "conv_pm_max") net->conv_pm_max = value;
+    else if (k == "conv_epi_groups") net->conv_epi_groups = value;
+    else if (k == "conv_pm_stack") net->conv_pm_stack = value;
+    else if (k == "conv_row_il") net->conv_row_il = value;
     else if (k == "conv_narrow_a") net->conv_narrow_a = value;
     else if (k == "conv_pm_shift") net->conv_pm_shift = value;
     else if (k == "conv_cm_shift") net->conv_cm_shift = value;
@@ -936,18 +942,31 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         ca.B = B; ca.Cin = g.in_channels; ca.Cout = g.out_channels;
         ca.Hin = ls.hin; ca.Win = ls.win; ca.Cp_in = cpad8(g.in_channels);
         const int hc = ls.hc, wc = ls.wc;
-        ca.Wp_out = pitch8(wc);
+        ca.Wp_out = pitch16(wc);   // 32-byte aligned rows: the narrow layers' epilogue stores 16 pixels per instruction
         ca.ksz = g.conv_kernel;
         ca.pad = g.conv_kernel - 1;
         // 16x16 pixel tiles on the small maps (<= 64^2: a third fewer tiles per wave, measured 0.084 -> 0.061 ms on L0..L2),
         // 32x8 elsewhere (fewer halo rows per TMA box)
         ca.tile_w = (net->conv_tile_w == 32 && hc <= 64 && wc <= 64 && g.conv_kernel == 3) ? 16 : net->conv_tile_w;
         ca.pm_max_cout = net->conv_pm_max;
+        ca.epi_groups = net->conv_epi_groups;
+        ca.pm_stack = net->conv_pm_stack;
         ca.narrow_a = net->conv_narrow_a;
         ca.pm_shift = net->conv_pm_shift;
         ca.cm_shift = net->conv_cm_shift;
         ca.num_sms = g_num_sms;
         ca.absmax = net->conv_impl == 0 ? absmax + i : nullptr;
+        {
+            // row-interleaved conv output: only where the streaming filter kernels (4-D tensor map) consume it
+            FlreluArgs pr;
+            memset(&pr, 0, sizeof(pr));
+            pr.B = B; pr.C = g.out_channels; pr.up = g.up; pr.down = g.down; pr.up_taps = g.up_taps; pr.down_taps = g.down_taps;
+            pr.fd_2d = g.down_radial; pr.px0 = g.pad_lo; pr.py0 = g.pad_lo; pr.gain = sqrtf(2.0f); pr.slope = 0.2f;
+            memcpy(pr.fd, L.fd.data(), sizeof(pr.fd));
+            const char* sev = getenv("MB_FLRELU_STREAM");
+            ca.row_interleaved = (net->conv_impl == 0 && net->flrelu_impl == 0 && g.out_channels <= net->conv_row_il &&
+                                  !(sev && atoi(sev) == 0) && flrelu_mma_supported(pr)) ? 1 : 0;
+        }
         r = net->conv_impl == 0 ? conv_tc_launch(ca, stream) : conv_simt_launch(ca, stream);
         if (r != MB_OK) return r;
         launches += 1;
@@ -962,7 +981,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         memcpy(fa.fu, L.fu.data(), sizeof(fa.fu));
         memcpy(fa.fd, L.fd.data(), sizeof(fa.fd));
         fa.B = B; fa.C = g.out_channels;
-        fa.Hin = hc; fa.Win = wc; fa.Wp_in = pitch8(wc);
+        fa.Hin = hc; fa.Win = wc; fa.Wp_in = pitch16(wc);
         fa.Hout = ls.hout; fa.Wout = ls.wout; fa.Wp_out = pitch8(ls.wout);
         fa.up = g.up; fa.down = g.down; fa.up_taps = g.up_taps; fa.down_taps = g.down_taps;
         fa.fd_2d = g.down_radial;
@@ -971,6 +990,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         fa.clamp = static_cast<float>(net->cfg.conv_clamp);
         fa.num_sms = g_num_sms;
         fa.in_absmax = ca.absmax;
+        fa.in_row_interleaved = ca.row_interleaved;
         // Layers that feed another conv write channels-last straight from the tensor-core kernel; the
         // fallback kernels (and the last layer, whose consumer is the planar ToRGB kernel) write planar.
         const bool next_is_conv = !net->layers[i + 1].g.is_torgb;
@@ -1050,7 +1070,7 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
     }
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int Ho = H + k - 1, Wo = W + k - 1;
-    const int Cp = (Cin + 7) / 8 * 8, Wpo = pitch8(Wo);
+    const int Cp = (Cin + 7) / 8 * 8, Wpo = pitch16(Wo);
     __half *xh = nullptr, *wpk = nullptr, *yh = nullptr;
     float *wsqT = nullptr, *sn = nullptr, *d = nullptr;
     const size_t nx = static_cast<size_t>(B) * H * W * Cp, ny = static_cast<size_t>(B) * Cout * Ho * Wpo;
@@ -1069,12 +1089,17 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
         ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
         ca.pad = k - 1;
         ca.tile_w = (impl == 2) ? 16 : 32;
+        ca.pm_stack = (impl == 0 || impl == 11) ? 1 : 0;   // 11: stacked pixel-major tile wherever its three kw blocks fit one instruction
+        if (impl == 11) ca.pm_max_cout = 80;
+        else
         ca.pm_max_cout = (impl >= 4 && impl <= 6) ? 128 : ((impl == 0) ? 64 : 0);  // 4..6: pixel-major tile for every layer up to 128 couts
         ca.pm_shift = (impl == 0 || impl == 5) ? 1 : (impl == 6 ? 2 : 0);  // 4: one patch load per kw; 5: single load, shifted
                                                                            // A descriptors; 6: + base-offset field (WRONG results:
                                                                            // kept as the probe of scripts/conv_shift_probe.py)
-        ca.cm_shift = (impl == 7) ? 1 : 0;  // 7: cout-major tile everywhere, single patch load + shifted B descriptors
+        ca.cm_shift = (impl == 7) ? 1 : (impl == 10 ? 2 : 0);  // 7: cout-major tile everywhere, single patch load + shifted B descriptors
+                                                                 // 10: the same on a 34-pixel-wide patch (aligned 32-pixel tiles of 7 rows)
         ca.narrow_a = (impl == 3) ? 0 : 1;       // 3: always stream full 128-row weight tiles (the r1 first path)
+        ca.epi_groups = (impl == 8 || impl == 10) ? 3 : (impl == 9 ? 1 : 0);  // 8 / 9: cout-major tile everywhere with three / one epilogue warp group(s)
         ca.num_sms = g_num_sms;
         r = (impl == 1) ? conv_simt_launch(ca, stream) : conv_tc_launch(ca, stream);
     }

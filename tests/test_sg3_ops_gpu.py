@@ -33,8 +33,11 @@ CONV_CASES = [
 
 @pytest.mark.parametrize("case", CONV_CASES)
 # 1 CUDA cores, 0 tcgen05 product dispatch (narrow layers: resident weight tiles), 2 the same with 16-wide tiles,
-# 3 full weight tiles streamed per stage, 4 pixel-major tile up to 128 couts, 7 cout-major tile with one patch load per chunk
-@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4, 7])
+# 3 full weight tiles streamed per stage, 4 pixel-major tile up to 128 couts, 7 cout-major tile with one patch load per chunk,
+# 8 cout-major tile with three epilogue warp groups (column-split, double-buffered tcgen05.ld), 9 the same with one group
+# 10 cout-major tile, one 34-pixel-wide patch load per chunk (7-row tiles, N = 240), three epilogue groups
+# 11 pixel-major tile with the three kw taps stacked along N (one instruction per (kh, 16 channels), shuffle-add epilogue)
+@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4, 7, 8, 9, 10, 11])
 def test_modulated_conv2d(cuda, case, impl):
     from maua_b200 import ops
 

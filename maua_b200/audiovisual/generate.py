@@ -20,6 +20,12 @@ def generate_audiovisal_from_patch(audio_file: str, model_file: str, patch_file:
     mapped_inputs = patch.mapper(**mapper_inputs) if mapper_inputs else None
     synthesizer_inputs = patch.process_synthesizer_inputs(mapped_inputs)
     postprocess = lambda video: patch.force_output_size(patch.process_outputs(video))
+    # stock stages (an un-overridden process_outputs returns its argument, force_output_size depends on the frame size only):
+    # the renderer may then skip the float frames once the first batch came back untouched (render/ffmpeg.py)
+    from .patches.base import MauaPatch
+
+    stock_outputs = getattr(type(patch).process_outputs, "stock", False) if hasattr(type(patch), "process_outputs") else False
+    postprocess.pure = bool(stock_outputs and type(patch).force_output_size is MauaPatch.force_output_size)
     renderer_kwargs = dict(renderer_kwargs)
     if renderer == "ffmpeg":
         renderer_kwargs["fps"] = patch.fps

@@ -26,3 +26,5 @@ class StyleGAN2Patch(MauaPatch):
 
     def process_outputs(self, video):
         return video
+
+    process_outputs.stock = True   # un-overridden: generate.py may declare the postprocess chain pure (render/ffmpeg.py)

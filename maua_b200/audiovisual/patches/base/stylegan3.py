@@ -23,3 +23,5 @@ class StyleGAN3Patch(MauaPatch):
 
     def process_outputs(self, video):
         return video
+
+    process_outputs.stock = True   # un-overridden: generate.py may declare the postprocess chain pure (render/ffmpeg.py)

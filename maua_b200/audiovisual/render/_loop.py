@@ -14,7 +14,8 @@ def frame_batches(synthesizer, inputs, batch_size, device, out_fmt="f32"):
     synthesizer = synthesizer.to(device)
     for i in range(0, T, batch_size):
         batch = {k: staged[k][i:i + batch_size].to(device, non_blocking=True) for k in keys}
-        yield i, (synthesizer(**batch) if out_fmt == "f32" else synthesizer(**batch, out_fmt=out_fmt))
+        fmt = out_fmt() if callable(out_fmt) else out_fmt     # a callable is asked per batch (the renderer may switch formats)
+        yield i, (synthesizer(**batch) if fmt == "f32" else synthesizer(**batch, out_fmt=fmt))
 
 
 def to_uint8(frames01):

@@ -11,6 +11,30 @@ from __future__ import annotations
 import queue
 import threading
 
+_RING_CACHE = {}            # (shape, depth) -> [list of pinned uint8 buffers, in_use]
+_RING_LOCK = threading.Lock()
+
+
+def acquire_pinned_ring(shape, depth):
+    """A ring of `depth` pinned uint8 host buffers of `shape`, reused between renders: cudaHostAlloc of 3 x 50 MB costs tens of
+    milliseconds, more than two batches of a 1024^2 render.  Returns (ring, release); a ring that is still in use by another
+    render is never handed out twice (a fresh one is allocated instead and not cached)."""
+    import torch
+
+    key = (tuple(shape), int(depth))
+    with _RING_LOCK:
+        ent = _RING_CACHE.get(key)
+        if ent is not None and not ent[1]:
+            ent[1] = True
+            return ent[0], lambda: ent.__setitem__(1, False)
+    ring = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(depth)]
+    with _RING_LOCK:
+        if key not in _RING_CACHE:
+            ent = [ring, True]
+            _RING_CACHE[key] = ent
+            return ring, lambda: ent.__setitem__(1, False)
+    return ring, lambda: None
+
 
 class RingWriter:
     """ring: list of writable host buffers (pinned uint8 tensors or numpy arrays, indexable by [:n]);

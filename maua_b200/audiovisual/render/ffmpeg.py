@@ -13,7 +13,7 @@ import torch
 
 from . import Renderer
 from ._loop import frame_batches, frames_to_rgb24
-from ._sink import RingWriter
+from ._sink import RingWriter, acquire_pinned_ring
 
 
 class FFMPEG(Renderer):
@@ -42,6 +42,7 @@ class FFMPEG(Renderer):
         return proc.stdin, proc
 
     ring_depth = 3
+    fuse_identity = True    # False: always hand float frames to postprocess (the reference's route for every batch)
 
     def __call__(self, synthesizer, inputs, postprocess, fp16=True):
         """render/ffmpeg.py:37-75: batches -> synthesizer -> (x + 1) / 2 -> postprocess -> tensor2bytes -> sink.  The
@@ -50,23 +51,44 @@ class FFMPEG(Renderer):
         a pipe write unless every slot is still unwritten (back-pressure)."""
         sink, proc, writer = None, None, None
         copy_stream = torch.cuda.Stream(device=self.device)
-        dev_ring, slot_free = None, None
+        dev_ring, slot_free, slot_src, release_ring = None, None, None, None
         self.frames_written = 0
+        # Batch 0 takes the reference's route (float (x + 1) / 2 frames -> postprocess -> tensor2bytes).  If postprocess is
+        # declared pure (`postprocess.pure = True`: no side effects, the same function of every batch -- generate.py sets it for
+        # the stock process_outputs / force_output_size of a patch) AND handed that batch back untouched (same tensor object,
+        # contents bit-identical: the native output size), the remaining batches leave the network's last kernel as rgb24
+        # already ("u8": the same clamp -> * 255 -> round -> uint8 arithmetic) and skip the float frames altogether.
+        state = {"fmt": "f32_unit"}
         try:
-            for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device, out_fmt="f32_unit"):
-                frame_batch = postprocess(frames)
-                n = frame_batch.shape[0]
+            for start, frames in frame_batches(synthesizer, inputs, self.batch_size, self.device, out_fmt=lambda: state["fmt"]):
+                fused = state["fmt"] == "u8"
+                if fused:
+                    frame_batch = frames                                   # uint8 [n, H, W, C]
+                    n = frame_batch.shape[0]
+                else:
+                    probe = frames.clone() if (writer is None and self.fuse_identity and getattr(postprocess, "pure", False)) else None
+                    frame_batch = postprocess(frames)
+                    n = frame_batch.shape[0]
+                    if probe is not None and frame_batch is frames and torch.equal(frames, probe):
+                        state["fmt"] = "u8"
+                    del probe
                 if writer is None:
                     _, c, h, w = frame_batch.shape
                     sink, proc = self._open_sink(w, h)
                     shape = (self.batch_size, h, w, c)
-                    writer = RingWriter(sink, [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(self.ring_depth)])
+                    ring, release_ring = acquire_pinned_ring(shape, self.ring_depth)
+                    writer = RingWriter(sink, ring)
                     dev_ring = [torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in range(self.ring_depth)]
                     slot_free = [None] * self.ring_depth
+                    slot_src = [None] * self.ring_depth
                 k = writer.acquire()                      # host slot k (and with it device slot k) has been written out
-                if slot_free[k] is not None:
-                    torch.cuda.current_stream().wait_event(slot_free[k])
-                u8 = frames_to_rgb24(frame_batch, out=dev_ring[k])      # rgb24: H, W, 3 per frame
+                if fused:
+                    u8 = frame_batch
+                    slot_src[k] = u8                      # keeps the frames alive until the copy that reads them has drained
+                else:
+                    if slot_free[k] is not None:
+                        torch.cuda.current_stream().wait_event(slot_free[k])
+                    u8 = frames_to_rgb24(frame_batch, out=dev_ring[k])      # rgb24: H, W, 3 per frame
                 ready = torch.cuda.Event()
                 ready.record(torch.cuda.current_stream())
                 with torch.cuda.stream(copy_stream):
@@ -81,6 +103,8 @@ class FFMPEG(Renderer):
             try:
                 if writer is not None:
                     writer.close()
+                if release_ring is not None:
+                    release_ring()
             finally:
                 if sink is not None and sink is not self.sink:
                     sink.close()

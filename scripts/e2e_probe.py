@@ -47,11 +47,19 @@ def ffmpeg_pinned():
     FFMPEG(None, batch_size=B, sink=Sink())(G.synthesizer, {"latents": lat_pinned}, lambda v: v)
 def ffmpeg_pageable():
     FFMPEG(None, batch_size=B, sink=Sink())(G.synthesizer, {"latents": lat}, lambda v: v)
+def ffmpeg_pure():
+    pp = lambda v: v
+    pp.pure = True
+    FFMPEG(None, batch_size=B, sink=Sink())(G.synthesizer, {"latents": lat_pinned}, pp)
+def ffmpeg_pure_half():
+    pp = lambda v: v
+    pp.pure = True
+    FFMPEG(None, batch_size=B, sink=Sink())(G.synthesizer, {"latents": lat_pinned[:n // 2]}, pp)
 def wrapper_only():
     for i in range(0, n, B):
         G.synthesizer(latents=lat_dev[i:i + B], out_fmt="f32_unit")
 
 for name, fn in [("net() u8, device latents", bare), ("net() u8, pinned latents + H2D", bare_h2d), ("net() f32_unit + rgb24 kernel", bare_unit),
-                 ("wrapper forward f32_unit", wrapper_only), ("FFMPEG.__call__ pinned inputs", ffmpeg_pinned), ("FFMPEG.__call__ pageable inputs", ffmpeg_pageable)]:
+                 ("wrapper forward f32_unit", wrapper_only), ("FFMPEG.__call__ pinned inputs", ffmpeg_pinned), ("FFMPEG.__call__ pinned, pure postprocess", ffmpeg_pure), ("  same, half the frames (ms per FULL step count)", ffmpeg_pure_half), ("FFMPEG.__call__ pageable inputs", ffmpeg_pageable)]:
     t = timed(fn)
     print(f"{name:40s} {1000 * t / (n / B):7.3f} ms/step  {n / t:7.1f} frames/s")

@@ -5,6 +5,7 @@
 bench.py reports these measured DRAM bytes per step as roofline.traffic next to the algorithmic bytes."""
 import csv, json, sys
 src, dst, B = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 8
+tag = (sys.argv[4] + "_") if len(sys.argv) > 4 and sys.argv[4] != "T" else ""   # "R": keys ..._R_b16 (StyleGAN3-R)
 rows = [r for r in csv.reader(open(src)) if len(r) >= 15 and r[0].isdigit()]
 acc = {"filtered_lrelu": {"bytes": 0.0, "ns": 0.0, "launches": set()}, "modulated_conv2d": {"bytes": 0.0, "ns": 0.0, "launches": set()}}
 for r in rows:
@@ -22,8 +23,8 @@ import os
 out = json.load(open(dst)) if os.path.exists(dst) else {}
 out["source"] = "ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of ONE forward per batch size, scripts/make_traffic.py"
 for fam, d in acc.items():
-    out["%s_bytes_per_step_b%d" % (fam, B)] = d["bytes"]
+    out["%s_bytes_per_step_%sb%d" % (fam, tag, B)] = d["bytes"]
     out["%s_launches" % fam] = len(d["launches"])
-    out["%s_ncu_ms_b%d" % (fam, B)] = d["ns"] / 1e6
+    out["%s_ncu_ms_%sb%d" % (fam, tag, B)] = d["ns"] / 1e6
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out))

@@ -62,6 +62,15 @@ def test_ffmpeg_renderer_sink_bytes_match_the_frames(cuda):
     raw = np.frombuffer(sink.getvalue(), dtype=np.uint8).reshape(11, 256, 256, 3)
     want = net(lat.to(cuda), out_fmt="u8").cpu().numpy()
     assert int(np.abs(raw.astype(np.int16) - want.astype(np.int16)).max()) <= 1      # (x+1)/2 in fp32 then *255 vs fused
+    # a postprocess declared pure that hands batch 0 back untouched: the later batches leave the network as rgb24 (postprocess
+    # is not called again) and the byte stream is the same
+    sink3, seen3 = io.BytesIO(), []
+    pure = lambda v: (seen3.append(v.shape[0]), v)[1]  # noqa: E731
+    pure.pure = True
+    FFMPEG(None, fps=24, batch_size=4, sink=sink3)(S, {"latents": lat}, pure)
+    assert seen3 == [4]
+    raw3 = np.frombuffer(sink3.getvalue(), dtype=np.uint8).reshape(11, 256, 256, 3)
+    assert int(np.abs(raw3.astype(np.int16) - raw.astype(np.int16)).max()) <= 1 and np.array_equal(raw3[4:], want[4:])
     # a postprocess that changes the frame size (force_output_size) flows through the same conversion
     sink2 = io.BytesIO()
     FFMPEG(None, fps=24, batch_size=4, sink=sink2)(S, {"latents": lat[:4]}, lambda v: v[:, :, ::2, ::2].contiguous())

@@ -1,9 +1,9 @@
 """retrieve_music_information: mirror of maua/audiovisual/audioreactive/selfsupervised/mir.py:24-45.
 
 features (device kernels, selfsupervised.extract_features) -> tempo and beats from the onset envelope (beat.py, host) ->
-Laplacian segmentations per feature and k (segment.py) -> post-processed features.  The reference additionally stores
-("rosa", k) segmentations from a librosa-only pipeline (laplacian_segmentation_rosa: librosa cqt / mfcc / sklearn KMeans);
-that one is not built, so no patch may pick seq_feat "rosa" (the reference's random Patch never does: ALLFEATS has no "rosa").
+Laplacian segmentations per feature and k (segment.py) -> post-processed features, plus the ("rosa", k) segmentations of the
+whole track (segment.laplacian_segmentation_rosa: the reference's librosa / sklearn pipeline on the package's own device
+functions; parity unpinned, see its docstring).
 """
 from __future__ import annotations
 
@@ -22,5 +22,9 @@ def retrieve_music_information(audio, sr, ks=(2, 4, 6, 8, 12, 16), device="cuda"
     raw = _ss.extract_features(audio, sr, postprocess=False)
     tempo, beats = _beat.tempo_and_beats(raw["onsets"].squeeze().cpu().numpy())
     segmentations = _segment.segmentations_from_features(raw, beats, ks=ks)
+    n_frames = next(iter(raw.values())).shape[0]
+    rosa = _segment.laplacian_segmentation_rosa(audio, sr, n_frames, ks=ks)          # mir.py:40-41
+    for i, k in enumerate(ks):
+        segmentations[("rosa", k)] = rosa[:, i]
     features = {k: _ss.postprocess_feature(v) for k, v in raw.items()}
     return features, segmentations, tempo

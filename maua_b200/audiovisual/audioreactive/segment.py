@@ -143,3 +143,99 @@ def segmentations_from_features(features, beats, ks=(2, 4, 6, 8, 12, 16)):
         for k, seg in zip(ks, laplacian_segmentation(feature, beats, ks=ks)):
             out[(name, k)] = seg.argmax(1)
     return out
+
+
+# ---- the ("rosa", k) segmentations of retrieve_music_information -------------------------------------------------------
+BINS_PER_OCTAVE = 12 * 3
+N_OCTAVES = 7
+
+
+def _amplitude_to_db_max(mag, amin=1e-5, top_db=80.0):
+    """librosa.amplitude_to_db(S, ref=np.max): 20 log10(max(S, amin) / max(S.max(), amin)), floored top_db below the maximum."""
+    ref = mag.max().clamp_min(amin)
+    db = 20.0 * torch.log10(mag.clamp_min(amin)) - 20.0 * torch.log10(ref)
+    return db.clamp_min(db.max() - top_db)
+
+
+def _median_filter_rows(x, k=9):
+    """scipy.ndimage.median_filter(x, size=(k, 1)) with its default "reflect" boundary (the edge sample is repeated:
+    d c b a | a b c d), unlike F.pad's reflect which median_filter1d above uses for the reference's own torch functions."""
+    p = k // 2
+    xp = torch.cat([x[:p].flip(0), x, x[-p:].flip(0)], dim=0)
+    return xp.unfold(0, k, 1).median(dim=-1).values
+
+
+def hard_k_means(data, k, num_iter=100):
+    """Lloyd's algorithm with the seeded k-means++ start of init_plus_plus -> cluster index per row (the reference calls an
+    unseeded sklearn.cluster.KMeans(n_clusters=k).fit_predict here, segment.py:255: its labels vary from run to run)."""
+    mu = torch.tensor(init_plus_plus(data.detach().cpu().double().numpy(), k)).to(data)
+    labels = None
+    for _ in range(num_iter):
+        new = torch.cdist(data, mu).argmin(1)
+        if labels is not None and torch.equal(new, labels):
+            break
+        labels = new
+        for j in range(k):
+            sel = labels == j
+            if sel.any():
+                mu[j] = data[sel].mean(0)
+    return labels
+
+
+def laplacian_segmentation_rosa(audio, sr, out_size, ks=(2, 4, 6, 8, 16), beats=None):
+    """Pattern-recurrence segmentation of the TRACK (not of a feature envelope): mirror of laplacian_segmentation_rosa,
+    rosa/segment.py:201-258, which follows librosa's "Laplacian segmentation" example -> int64 [out_size, len(ks)].
+
+    The reference runs this one through librosa / scipy / sklearn on the host (librosa.cqt, beat_track, util.sync,
+    segment.recurrence_matrix, feature.mfcc, csgraph.laplacian, KMeans).  librosa is absent and un-pinned, so the stages are
+    the package's own device functions for the same quantities -- PARITY UNPINNED: 7-octave, 36-bins-per-octave constant-Q
+    magnitudes in dB below the maximum (csrc/chroma.cu), beats from the package's onset envelope and beat tracker with
+    librosa's default tempo prior (the reference lets librosa derive its own onset envelope), beat-synchronous medians
+    (constant-Q) and means (20 MFCCs), mutual k-NN recurrence affinity + time-lag median filter, balanced combination with
+    the MFCC path affinity, symmetric normalised Laplacian, 9-row median filter of the eigenvectors, cumulative
+    normalisation and k-means (seeded here, unseeded there).  `beats` overrides the internal beat tracker."""
+    from . import beat as _beat
+    from .chroma import cqt_magnitude
+    from .features import mfcc as _mfcc, onsets as _onsets
+
+    audio = torch.as_tensor(audio)
+    if not audio.is_cuda:
+        raise RuntimeError("laplacian_segmentation_rosa: the track must live on the GPU (no CPU path)")
+    audio = audio.float()
+    cdb = _amplitude_to_db_max(cqt_magnitude(audio, sr, hop_length=1024, n_bins=N_OCTAVES * BINS_PER_OCTAVE,
+                                             bins_per_octave=BINS_PER_OCTAVE)).T.contiguous()          # [T, 252]
+    n_frames = cdb.shape[0]
+    if beats is None:
+        env = _onsets(audio, sr).squeeze().cpu().numpy()
+        bpm = _beat.tempo(env, hop_length=1024)                      # librosa.beat.beat_track defaults: start_bpm 120, std 1
+        beats = [int(b) for b in _beat.beat_track(env, bpm, hop_length=1024, trim=False)]
+    beats = sorted({int(b) for b in beats if 0 < int(b) < n_frames})   # util.sync pads the boundaries with 0 and the end
+    edges = [0] + beats + [n_frames]
+    csync = torch.stack([cdb[a:b].median(dim=0).values for a, b in zip(edges[:-1], edges[1:])], dim=0)
+    mf = _mfcc(audio, sr, n_mfcc=20)[:n_frames]
+    msync = torch.stack([mf[a:b].mean(dim=0) for a, b in zip(edges[:-1], edges[1:])], dim=0)
+    nb = csync.shape[0]
+    if nb < 4:   # nothing to segment: one label everywhere
+        return torch.zeros(out_size, len(ks), dtype=torch.long, device=audio.device)
+
+    rf = timelag_median_filter(recurrence_matrix(csync, width=min(3, max((nb - 2) // 2, 1)), sym=True))
+    path_distance = torch.sum(torch.diff(msync, dim=0) ** 2, dim=1)
+    sigma = torch.median(path_distance)
+    if not sigma > 0:
+        sigma = path_distance.mean().clamp_min(1e-12)
+    path_sim = torch.exp(-path_distance / sigma)
+    r_path = torch.diag(path_sim, diagonal=1) + torch.diag(path_sim, diagonal=-1)
+    deg_path, deg_rec = r_path.sum(dim=1), rf.sum(dim=1)
+    mu = deg_path.dot(deg_path + deg_rec) / torch.sum((deg_path + deg_rec) ** 2).clamp_min(1e-30)
+    lap = torch.nan_to_num(normalized_laplacian(mu * rf + (1 - mu) * r_path))
+    _, evecs = torch.linalg.eigh(lap.double())
+    evecs = _median_filter_rows(evecs.float(), k=min(9, 2 * ((nb - 1) // 2) + 1))
+    cnorm = torch.cumsum(evecs ** 2, dim=1) ** 0.5
+
+    out = []
+    for k in ks:
+        kk = min(int(k), nb)
+        x = evecs[:, :kk] / cnorm[:, kk - 1:kk].clamp_min(1e-30)
+        labels = hard_k_means(x, kk).float()
+        out.append(F.interpolate(labels[None, None, :], size=out_size, mode="nearest").squeeze(0).squeeze(0))
+    return torch.stack(out, dim=1).long()

@@ -25,7 +25,7 @@ def test_music_information_drives_a_random_patch(cuda):
     for k, v in features.items():
         assert v.shape[0] == T and v.is_cuda and torch.isfinite(v).all(), k
         assert float(v.min()) >= 0 and float(v.max()) <= 1 + 1e-6
-    assert set(segmentations) == {(n, k) for n in features for k in ks}
+    assert set(segmentations) == {(n, k) for n in list(features) + ["rosa"] for k in ks}
     for (n, k), seg in segmentations.items():
         assert seg.shape == (T,) and int(seg.max()) < k
     # 2 clicks per second at 24 frames/s = a 12-frame period; in the reference's units (21.53 frames/s assumed) that reads 107.7 BPM
@@ -34,6 +34,11 @@ def test_music_information_drives_a_random_patch(cuda):
     seg = segmentations[("chromagram", 2)].cpu().numpy()
     mids = [int(np.bincount(seg[int((5 * i + 1.5) * fps): int((5 * i + 3.5) * fps)]).argmax()) for i in range(4)]
     assert mids[0] == mids[2] and mids[1] == mids[3] and mids[0] != mids[1], mids
+
+    # ... and in the whole-track ("rosa") segmentation built from constant-Q / MFCC recurrence
+    rosa = segmentations[("rosa", 2)].cpu().numpy()
+    rmids = [int(np.bincount(rosa[int((5 * i + 1.5) * fps): int((5 * i + 3.5) * fps)]).argmax()) for i in range(4)]
+    assert rmids[0] == rmids[2] and rmids[1] == rmids[3] and rmids[0] != rmids[1], rmids
 
     patch = Patch(features, segmentations, tempo, fps=fps, seed=3, device="cpu")
     palette = torch.randn(30, 18, 512, device=cuda)

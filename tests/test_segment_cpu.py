@@ -46,3 +46,32 @@ def test_normalized_laplacian_and_helpers():
     assert torch.equal(S._shear(x, 1)[:, 1], torch.roll(x[:, 1], 1))
     segs = S.segmentations_from_features({"f": torch.randn(120, 4)}, list(range(5, 120, 6)), ks=(2, 4))
     assert set(segs) == {("f", 2), ("f", 4)} and segs[("f", 4)].shape == (120,) and int(segs[("f", 4)].max()) < 4
+
+
+def test_rosa_helpers_match_scipy_and_separate_clusters():
+    """Host pieces of laplacian_segmentation_rosa: the eigenvector median filter has scipy.ndimage's boundary rule, the dB
+    conversion is librosa's amplitude_to_db(ref=max) formula, the seeded hard k-means recovers well separated clusters."""
+    import numpy as np
+    import scipy.ndimage
+
+    from maua_b200.audiovisual.audioreactive import segment as S
+
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(23, 6, generator=g)
+    want = scipy.ndimage.median_filter(x.numpy(), size=(9, 1))
+    assert np.array_equal(S._median_filter_rows(x, 9).numpy(), want)
+
+    mag = torch.rand(30, 12, generator=g) * 3
+    mag[0, 0] = 1e-9
+    db = S._amplitude_to_db_max(mag)
+    ref = 20 * np.log10(np.maximum(mag.numpy(), 1e-5)) - 20 * np.log10(mag.numpy().max())
+    ref = np.maximum(ref, ref.max() - 80.0)
+    assert np.allclose(db.numpy(), ref, atol=1e-4) and float(db.max()) == 0.0 and float(db.min()) >= -80.0
+
+    centres = torch.tensor([[0.0, 0.0], [10.0, 0.0], [0.0, 10.0]])
+    truth = torch.arange(60) % 3
+    pts = centres[truth] + 0.3 * torch.randn(60, 2, generator=g)
+    lab = S.hard_k_means(pts, 3)
+    assert len(set(lab.tolist())) == 3
+    for j in range(3):   # every true cluster maps onto exactly one label
+        assert len(set(lab[truth == j].tolist())) == 1

@@ -1,6 +1,7 @@
 # Round-2 evidence pass on one B200: per-layer tables, bench lines, ncu launch list, ncu --set full of the top kernels
 set -x
 mkdir -p gpurun_out
+python -m pytest tests/test_mir_gpu.py tests/test_video_writer_gpu.py -x -q 2>&1 | tail -3 > gpurun_out/r2_newtests.log
 python scripts/e2e_probe.py 720 > gpurun_out/e2e_probe.txt 2>&1
 python scripts/layer_times.py 16 T > gpurun_out/r2_layers_T16.txt 2>&1
 python scripts/layer_times.py 16 R > gpurun_out/r2_layers_R16.txt 2>&1
@@ -12,4 +13,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # launches 13..27 of the second forward's conv / filter kernels: L6 conv, L6 filter, L7 conv, ..., L13 conv
 ncu --set full --clock-control none --import-source on -k regex:'conv_|flrelu_' --launch-skip 41 --launch-count 15 -o gpurun_out/r2_full_b16 -f python scripts/one_forward.py 16 T > gpurun_out/ncu_r2.log 2>&1
 ls -la gpurun_out/*.ncu-rep
-cat gpurun_out/e2e_probe.txt gpurun_out/r2_bench.json
+cat gpurun_out/r2_newtests.log gpurun_out/e2e_probe.txt gpurun_out/r2_bench.json

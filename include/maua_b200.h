@@ -167,6 +167,23 @@ int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width);
  * Changes mb_net_workspace_bytes.  StyleGAN2 handles only. */
 int mb_sg2_set_warps(mb_net* net, int n_warps, const int32_t* layers, const float* inv_mats, int batch);
 
+/* Output-size hook of StyleGAN2Synthesizer.change_output_resolution (maua/GAN/wrappers/stylegan2.py:104-151, get_hook :216-340):
+ * the output of layer_names[layer] is resized to target_h x target_w and every later layer runs on the resized, possibly
+ * non-square map; the hooked block's ToRGB output is mapped back to the layer size before it joins the skip image and the
+ * block's image is resized like the features (the reference's rgb_hook / img_hook).
+ *   layer   index into the wrapper's layer_names; 0 = the reference's forward PRE-hook on bs.0.conv1: `noise` then IS the
+ *           resized constant input [C, target_h, target_w] (resize + noise done by the caller), no image hooks; -1 clears
+ *   mode    0 "stretch" (bicubic, align_corners=False), 1 constant pad with `value`, 2 reflect, 3 replicate, 4 circular
+ *           (torch.nn.functional.pad semantics; pad_top / pad_left = leading pads, the rest trails)
+ *   noise   device float32 [C, target_h, target_w] added to the resized features (the reference draws it once per channel from
+ *           N(mean_c, std_c) of the resized features, :236-249) or NULL; caller-owned, must stay valid while the hook is set
+ *   stats   device float32 [2, C] or NULL: when set, forwards write the per-channel mean / unbiased std of the resized features
+ *           there (read them after a probe forward with noise = NULL to draw the noise map)
+ * Every layer behind the hook needs a noise_const of its new size (mb_net_set_param accepts any [..., h, w] noise map; the
+ * reference swaps in fresh randn maps, :137-147).  Changes mb_net_workspace_bytes and mb_net_output_shape.  StyleGAN2 only. */
+int mb_sg2_set_resize(mb_net* net, int layer, int mode, int target_h, int target_w, int pad_top, int pad_left, float value,
+                      const float* noise, float* stats);
+
 /* Debug / parity aid: copy the activation a layer produced during the LAST forward into
  * `out` as float32 [B,C,H,W] (undoing the style pre-multiplication is the caller's business:
  * what is stored is x * style_{next}).  idx = -1 is the SynthesisInput output. */

@@ -197,6 +197,35 @@ class SynthesisNetwork(NativeNet):
                 d = d * strength
         return d
 
+    # ---- output-size hook (maua/GAN/wrappers/stylegan2.py:104-151) ---------------------------------------------------
+    RESIZE_MODES = {"stretch": 0, "constant": 1, "reflect": 2, "replicate": 3, "circular": 4}
+
+    def set_resize(self, layer, mode, target_hw, pads=(0, 0), value=0.0, noise=None, stats=None):
+        """Resize the output of layer_names[layer] to target_hw = (h, w) in every following forward (mb_sg2_set_resize).
+        mode: a RESIZE_MODES key; pads = (top, left) leading pads of the pad modes; noise: CUDA float32 [C, h, w] added to the
+        resized features (layer 0: the resized constant input itself); stats: CUDA float32 [2, C] receiving mean / std of the
+        resized features.  layer=None clears the hook."""
+        lib = _lib.load()
+        if layer is None:
+            _lib.check(lib.mb_sg2_set_resize(self._handle(), -1, 0, 1, 1, 0, 0, 0.0, None, None))
+            self._resize = None
+        else:
+            h, w = int(target_hw[0]), int(target_hw[1])
+            for t in (noise, stats):
+                if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise ValueError("set_resize: noise / stats must be contiguous float32 CUDA tensors")
+            _lib.check(lib.mb_sg2_set_resize(self._handle(), int(layer), self.RESIZE_MODES[mode], h, w, int(pads[0]), int(pads[1]),
+                                             float(value), None if noise is None else _lib.ptr(noise),
+                                             None if stats is None else _lib.ptr(stats)))
+            self._resize = (int(layer), mode, (h, w), noise, stats)    # keeps the device tensors alive while the hook is set
+        self._workspace = {}   # the workspace size follows the layer geometry
+
+    def output_hw(self):
+        """(height, width) of the image the next forward writes."""
+        h, w = C.c_int32(), C.c_int32()
+        _lib.check(_lib.load().mb_net_output_shape(self._handle(), C.byref(h), C.byref(w)))
+        return h.value, w.value
+
     def layer_resolution(self, layer):
         """Resolution of the wrapper's layer_names[layer] (maua/GAN/wrappers/stylegan2.py:48-51: entries 0 and 1 are
         bs.0.conv1, entry 2i / 2i+1 are block i's conv0 / conv1)."""
@@ -219,17 +248,19 @@ class SynthesisNetwork(NativeNet):
                 ws32 = ws32[:, :self.num_ws].contiguous()  # the reference's mapper always emits num_ws=18
             if tuple(ws32.shape[1:]) != (self.num_ws, self.w_dim):
                 raise ValueError(f"ws must be [B,{self.num_ws},{self.w_dim}], got {tuple(ws32.shape)}")
-            res = self.img_resolution
+            oh, ow = self.output_hw()
             if out_fmt in ("f32", "f32_01", "f32_unit"):
                 fmt = {"f32": _lib.MB_OUT_F32_NCHW, "f32_01": _lib.MB_OUT_F32_NCHW_01, "f32_unit": _lib.MB_OUT_F32_NCHW_UNIT}[out_fmt]
-                if out is None:
-                    out = torch.empty(B, self.img_channels, res, res, device=device, dtype=torch.float32)
+                shape, dtype = (B, self.img_channels, oh, ow), torch.float32
             elif out_fmt == "u8":
                 fmt = _lib.MB_OUT_U8_NHWC
-                if out is None:
-                    out = torch.empty(B, res, res, self.img_channels, device=device, dtype=torch.uint8)
+                shape, dtype = (B, oh, ow, self.img_channels), torch.uint8
             else:
                 raise ValueError("out_fmt must be 'f32', 'f32_01', 'f32_unit' or 'u8'")
+            if out is None:
+                out = torch.empty(shape, device=device, dtype=dtype)
+            elif tuple(out.shape) != shape or out.dtype != dtype or not out.is_contiguous():
+                raise ValueError(f"out must be a contiguous {dtype} tensor of shape {shape}")
             warps = list(warps or [])
             if bool(warps) != getattr(self, "_warps_on", False):
                 self._workspace = {}  # the warp ping-pong buffers change the workspace size

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "mb_net_set_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mb_sg3_resized_output": (C.c_int, [C.POINTER(SG3Cfg), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_sg2_set_warps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), _P, C.c_int]),
+    "mb_sg2_set_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "mb_gaussian_filter_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, _P]),
     "mb_salience": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),
     "mb_latent_merge": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -34,14 +34,12 @@ def load_audio(audio_file, offset, duration, fps, device="cuda"):
 @torch.inference_mode()
 def generate(audio_file: str, stylegan2_checkpoint: Optional[str] = None, patch_file: Optional[str] = None, seed: Optional[int] = None,
              latent_seeds: Optional[str] = None, fps: float = 30, audio_offset: float = 0, audio_duration: Optional[float] = None,
-             downscale_factor: float = 1, aspect_ratio: float = 1, batch_size: int = 32, device: str = "cuda",
+             downscale_factor: float = 4, aspect_ratio: float = 1, batch_size: int = 32, device: str = "cuda",
              out_file: Optional[str] = None, sink=None):
     """Returns (out_file, frames written, patch).  `sink`: optional object with write(bytes-like) that receives the rgb24
     stream instead of ffmpeg / the raw file (tests, custom encoders)."""
     from ...GAN.wrappers.stylegan2 import StyleGAN2
 
-    if downscale_factor != 1 or aspect_ratio != 1:
-        raise NotImplementedError("generate: downscale_factor / aspect_ratio need the StyleGAN2 output-size hooks (not built)")
     if seed is None:
         seed = torch.randint(0, 2 ** 32, size=(), device=device).item()
     audio, sr = load_audio(audio_file, audio_offset, audio_duration, fps, device)
@@ -52,10 +50,12 @@ def generate(audio_file: str, stylegan2_checkpoint: Optional[str] = None, patch_
     else:
         patch = Patch.load(patch_file, features=features, segmentations=segmentations, tempo=tempo, fps=fps, device=device)
 
-    G = StyleGAN2(model_file=stylegan2_checkpoint).to(device)
-    res = G.synthesizer.G_synth.img_resolution
+    # sample.py:53,70: the output size follows from the two factors and the wrapper's output-size hook (default: "stretch" on
+    # layer 0, i.e. a resized constant input) renders it
+    out_size = (round(aspect_ratio * 1024 / downscale_factor), round(1024 / downscale_factor))
+    G = StyleGAN2(model_file=stylegan2_checkpoint, output_size=out_size).to(device)
     if out_file is None:
-        out_file = f"output/{Path(audio_file).stem}_RandomPatches++_seed{seed}_{res}x{res}.mp4"
+        out_file = f"output/{Path(audio_file).stem}_RandomPatches++_seed{seed}_{out_size[0]}x{out_size[1]}.mp4"
     if latent_seeds is None:
         z = torch.randn((180, 512), device=device, generator=torch.Generator(device).manual_seed(seed))
         latent_palette = G.mapper(z)

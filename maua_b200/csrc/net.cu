@@ -628,10 +628,18 @@ extern "C" int mb_sg2_set_warps(mb_net* net, int n_warps, const int32_t* layers,
     return sg2_set_warps(net->sg2, n_warps, layers, inv_mats, batch);
 }
 
+extern "C" int mb_sg2_set_resize(mb_net* net, int layer, int mode, int target_h, int target_w, int pad_top, int pad_left, float value,
+                                 const float* noise, float* stats) {
+    MB_REQUIRE(net && net->sg2, "mb_sg2_set_resize: needs a StyleGAN2 handle");
+    return sg2_set_resize(net->sg2, layer, mode, target_h, target_w, pad_top, pad_left, value, noise, stats);
+}
+
 extern "C" int mb_net_output_shape(const mb_net* net, int32_t* height, int32_t* width) {
     MB_REQUIRE(net && height && width, "mb_net_output_shape: null argument");
     if (net->sg2) {
-        *height = *width = sg2_resolution(net->sg2);
+        int h = 0, w = 0;
+        sg2_output_hw(net->sg2, &h, &w);
+        *height = h; *width = w;
         return MB_OK;
     }
     const SizePlan sp = size_plan(net);

@@ -33,6 +33,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "sg2.h"
+#include "resize_taps.cuh"
 
 namespace mb {
 namespace {
@@ -90,36 +91,38 @@ __device__ __forceinline__ void put_split(__half* px, int c, int Cp, int ns, flo
     }
 }
 
-// const [C][r][r] f32 * style[b][c] -> channels-last fp16 [B][r][r][ns * Cp]
+// const [C][npix] f32 * style[b][c] -> channels-last fp16 [B][npix][ns * Cp]
 __global__ void const_input_kernel(const float* __restrict__ cst, const float* __restrict__ style, __half* __restrict__ out,
-                                   int B, int C, int r, int Cp, int ns) {
-    const long long total = static_cast<long long>(B) * r * r * Cp;
+                                   int B, int C, int npix, int Cp, int ns) {
+    const long long total = static_cast<long long>(B) * npix * Cp;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(idx % Cp);
         long long q = idx / Cp;
-        const int px = static_cast<int>(q % (r * r));
-        const int b = static_cast<int>(q / (r * r));
-        put_split(out + q * (static_cast<long long>(ns) * Cp), c, Cp, ns, c < C ? cst[c * r * r + px] * style[b * C + c] : 0.0f);
+        const int px = static_cast<int>(q % npix);
+        const int b = static_cast<int>(q / npix);
+        put_split(out + q * (static_cast<long long>(ns) * Cp), c, Cp, ns, c < C ? cst[static_cast<long long>(c) * npix + px] * style[b * C + c] : 0.0f);
     }
 }
 
 struct ActArgs {
-    const __half* y;        // planar conv output [B][C][Hy][Wpy]; Hy = R (+1 with FIR).  phase: the four parity planes of the
-                            // polyphase transposed conv, [B][4][C][R/2 + 1][Wpy]: y(yy, xx) = plane (yy & 1) * 2 + (xx & 1) at (yy >> 1, xx >> 1)
+    const __half* y;        // planar conv output [B][C][Hy][Wpy]; (Hy, Wy) = (RH, RW) (+1 with FIR).  phase: the four parity planes of the
+                            // polyphase transposed conv, [B][4][C][RH/2 + 1][Wpy]: y(yy, xx) = plane (yy & 1) * 2 + (xx & 1) at (yy >> 1, xx >> 1)
     long long y_lo;         // > 0: y + y_lo holds the low halves of a split output (value = hi + lo)
     int phase, ns;          // ns: channel blocks of x_next (3 = [xh | xl | xh], 1 = plain fp16)
-    const __half* pre;      // if set: the finished activation, channels-last [B][R][R][Cp] (a warped feature map); y, noise, bias unused
-    const float* noise;     // [R][R] (noise_bstride 0) or per-frame [B][R][R] (noise_bstride R*R) or nullptr
+    const float* pre32;     // like pre, as fp32 (behind an output-size hook: the resized map keeps fp32 precision)
+    float* x_next32;        // if set (pass 1 in front of an output-size hook): the unstyled activation as fp32 [B][RH][RW][Cp]
+    const __half* pre;      // if set: the finished activation, channels-last [B][RH][RW][Cp] (a warped / resized feature map); y, noise, bias unused
+    const float* noise;     // [RH][RW] (noise_bstride 0) or per-frame [B][RH][RW] (noise_bstride RH*RW) or nullptr
     const float* bias;      // [C]
     const float* style_next;  // [B][C] or nullptr (last block)
-    __half* x_next;         // channels-last [B][R][R][Cp] or nullptr
+    __half* x_next;         // channels-last [B][RH][RW][Cp] or nullptr
     const float* rgb_w;     // [3][C] ToRGB weight or nullptr (no ToRGB after conv0)
     const float* rgb_style; // [B][C] (already * 1/sqrt(C))
     const float* rgb_bias;  // [3]
-    const float* img_prev;  // [B][3][R][R] upsampled skip image or nullptr
-    float* img;             // [B][3][R][R]
-    int B, C, R, Hy, Wpy, Cp, fir, nimg;
+    const float* img_prev;  // [B][3][RH][RW] upsampled skip image or nullptr
+    float* img;             // [B][3][RH][RW]
+    int B, C, RH, RW, Hy, Wy, Wpy, Cp, fir, nimg;   // the map is RH x RW (non-square behind an output-size hook)
     long long noise_bstride;
     float clamp;
 };
@@ -135,10 +138,12 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
         const int c = idx / kActP, px = idx - c * kActP;
         const int w = w0 + px;
         float v = 0.0f;
-        if (a.pre) {
-            if (w < a.R) v = __half2float(a.pre[((static_cast<long long>(b) * a.R + h) * a.R + w) * a.Cp + c]);
-        } else if (w < a.R) {
-            const int hp = a.phase ? a.R / 2 + 1 : a.Hy;               // rows of a stored plane
+        if (a.pre32) {
+            if (w < a.RW) v = a.pre32[((static_cast<long long>(b) * a.RH + h) * a.RW + w) * a.Cp + c];
+        } else if (a.pre) {
+            if (w < a.RW) v = __half2float(a.pre[((static_cast<long long>(b) * a.RH + h) * a.RW + w) * a.Cp + c]);
+        } else if (w < a.RW) {
+            const int hp = a.phase ? a.RH / 2 + 1 : a.Hy;               // rows of a stored plane
             const long long plane = static_cast<long long>(hp) * a.Wpy;
             const __half* yp = a.y + (static_cast<long long>(b) * (a.phase ? 4 : 1) * a.C + c) * plane;
             auto at = [&](int yy, int xx) -> float {
@@ -158,14 +163,14 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
 #pragma unroll
                     for (int kx = 0; kx < 4; ++kx) {
                         const int xx = w - 1 + kx;
-                        if (xx >= 0 && xx < a.Hy) row = fmaf(f4[kx], at(yy, xx), row);
+                        if (xx >= 0 && xx < a.Wy) row = fmaf(f4[kx], at(yy, xx), row);
                     }
                     v = fmaf(f4[ky], row, v);
                 }
             } else {
                 v = at(h, w);
             }
-            if (a.noise) v += a.noise[b * a.noise_bstride + h * a.R + w];
+            if (a.noise) v += a.noise[b * a.noise_bstride + h * a.RW + w];
             v += a.bias[c];
             v = (v < 0.0f ? v * 0.2f : v) * 1.41421356237309515f;
             v = fminf(fmaxf(v, -a.clamp), a.clamp);
@@ -173,10 +178,17 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
         xs[c * (kActP + 1) + px] = v;
     }
     __syncthreads();
-    const int npx = min(kActP, a.R - w0);
+    const int npx = min(kActP, a.RW - w0);
+    if (a.x_next32) {
+        float* o = a.x_next32 + ((static_cast<long long>(b) * a.RH + h) * a.RW + w0) * a.Cp;
+        for (int idx = threadIdx.x; idx < npx * a.Cp; idx += blockDim.x) {
+            const int px = idx / a.Cp, c = idx - px * a.Cp;
+            o[idx] = c < a.C ? xs[c * (kActP + 1) + px] : 0.0f;
+        }
+    }
     if (a.x_next) {
         const int cpx = a.ns * a.Cp;   // halfs per pixel of x_next
-        __half* o = a.x_next + ((static_cast<long long>(b) * a.R + h) * a.R + w0) * cpx;
+        __half* o = a.x_next + ((static_cast<long long>(b) * a.RH + h) * a.RW + w0) * cpx;
         for (int idx = threadIdx.x; idx < npx * (a.Cp / 2); idx += blockDim.x) {
             const int px = idx / (a.Cp / 2), c = (idx - px * (a.Cp / 2)) * 2;
             const float s0 = c < a.C ? (a.style_next ? a.style_next[b * a.C + c] : 1.0f) : 0.0f;
@@ -204,7 +216,7 @@ __global__ void __launch_bounds__(256) sg2_act_kernel(const ActArgs a) {
             for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
             if (lane == 0) {
                 float v = fminf(fmaxf(acc + a.rgb_bias[o], -a.clamp), a.clamp);
-                const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.R + h) * a.R + w0 + px;
+                const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.RH + h) * a.RW + w0 + px;
                 if (a.img_prev) v += a.img_prev[oi];
                 a.img[oi] = v;
             }
@@ -234,12 +246,12 @@ __global__ void __launch_bounds__(256) sg2_act_tiled_kernel(const ActArgs a) {
     const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
     for (int i = threadIdx.x; i < PXT; i += blockDim.x) {
         const int hh = h0 + i / kActP, ww = w0 + i % kActP;
-        nz[i] = (a.noise && hh < a.R && ww < a.R) ? a.noise[b * a.noise_bstride + hh * a.R + ww] : 0.0f;
+        nz[i] = (a.noise && hh < a.RH && ww < a.RW) ? a.noise[b * a.noise_bstride + hh * a.RW + ww] : 0.0f;
     }
     if (a.rgb_w)
         for (int i = threadIdx.x; i < a.nimg * a.C; i += blockDim.x) wrgb[i] = a.rgb_w[i] * a.rgb_style[b * a.C + i % a.C];
     __syncthreads();
-    const int hp = a.phase ? a.R / 2 + 1 : a.Hy;
+    const int hp = a.phase ? a.RH / 2 + 1 : a.Hy;
     const long long plane = static_cast<long long>(hp) * a.Wpy;
     float* pw = patch + warp * PR * PC;
     for (int c = warp; c < a.C; c += 8) {
@@ -254,12 +266,12 @@ __global__ void __launch_bounds__(256) sg2_act_tiled_kernel(const ActArgs a) {
         const float bias = a.bias[c];
         float outv[TH];
         if (a.fir) {
-            // patch rows h0 - 1 .. h0 + TH + 1, columns w0 - 1 .. w0 + 33 of the (R + 1)^2 conv output, zero outside
+            // patch rows h0 - 1 .. h0 + TH + 1, columns w0 - 1 .. w0 + 33 of the (RH + 1) x (RW + 1) conv output, zero outside
             for (int r = 0; r < PR; ++r) {
                 const int yy = h0 - 1 + r;
                 for (int cc = lane; cc < 35; cc += 32) {
                     const int xx = w0 - 1 + cc;
-                    pw[r * PC + cc] = (yy >= 0 && yy < a.Hy && xx >= 0 && xx < a.Hy) ? at(yy, xx) : 0.0f;
+                    pw[r * PC + cc] = (yy >= 0 && yy < a.Hy && xx >= 0 && xx < a.Wy) ? at(yy, xx) : 0.0f;
                 }
             }
             __syncwarp();
@@ -281,29 +293,37 @@ __global__ void __launch_bounds__(256) sg2_act_tiled_kernel(const ActArgs a) {
             __syncwarp();   // the patch is free for the next channel
         } else {
 #pragma unroll
-            for (int t = 0; t < TH; ++t) outv[t] = (h0 + t < a.R && w0 + lane < a.R) ? at(h0 + t, w0 + lane) : 0.0f;
+            for (int t = 0; t < TH; ++t) outv[t] = (h0 + t < a.RH && w0 + lane < a.RW) ? at(h0 + t, w0 + lane) : 0.0f;
         }
 #pragma unroll
         for (int t = 0; t < TH; ++t) {
             float v = outv[t] + nz[t * kActP + lane] + bias;
             v = (v < 0.0f ? v * 0.2f : v) * 1.41421356237309515f;
             v = fminf(fmaxf(v, -a.clamp), a.clamp);
-            xs[c * XP + t * kActP + lane] = (h0 + t < a.R && w0 + lane < a.R) ? v : 0.0f;
+            xs[c * XP + t * kActP + lane] = (h0 + t < a.RH && w0 + lane < a.RW) ? v : 0.0f;
         }
     }
     __syncthreads();
-    const int npx = min(kActP, a.R - w0);
+    const int npx = min(kActP, a.RW - w0);
+    if (a.x_next32) {
+        for (int idx = threadIdx.x; idx < PXT * a.Cp; idx += blockDim.x) {
+            const int pix = idx / a.Cp, c = idx - pix * a.Cp;
+            const int t = pix / kActP, px = pix - t * kActP;
+            if (px >= npx || h0 + t >= a.RH) continue;
+            a.x_next32[((static_cast<long long>(b) * a.RH + h0 + t) * a.RW + w0 + px) * a.Cp + c] = c < a.C ? xs[c * XP + pix] : 0.0f;
+        }
+    }
     if (a.x_next) {
         const int cpx = a.ns * a.Cp, half_cp = a.Cp / 2;
         for (int idx = threadIdx.x; idx < PXT * half_cp; idx += blockDim.x) {
             const int pix = idx / half_cp, c = (idx - pix * half_cp) * 2;
             const int t = pix / kActP, px = pix - t * kActP;
-            if (px >= npx || h0 + t >= a.R) continue;
+            if (px >= npx || h0 + t >= a.RH) continue;
             const float s0 = c < a.C ? (a.style_next ? a.style_next[b * a.C + c] : 1.0f) : 0.0f;
             const float s1 = c + 1 < a.C ? (a.style_next ? a.style_next[b * a.C + c + 1] : 1.0f) : 0.0f;
             const float v0 = c < a.C ? xs[c * XP + pix] * s0 : 0.0f;
             const float v1 = c + 1 < a.C ? xs[(c + 1) * XP + pix] * s1 : 0.0f;
-            __half* op = a.x_next + ((static_cast<long long>(b) * a.R + h0 + t) * a.R + w0 + px) * cpx;
+            __half* op = a.x_next + ((static_cast<long long>(b) * a.RH + h0 + t) * a.RW + w0 + px) * cpx;
             const __half2 hi = __floats2half2_rn(v0, v1);
             *reinterpret_cast<__half2*>(op + c) = hi;
             if (a.ns == 3) {
@@ -317,11 +337,11 @@ __global__ void __launch_bounds__(256) sg2_act_tiled_kernel(const ActArgs a) {
         for (int item = threadIdx.x; item < PXT * a.nimg; item += blockDim.x) {
             const int o = item / PXT, pix = item - o * PXT;
             const int t = pix / kActP, px = pix - t * kActP;
-            if (px >= npx || h0 + t >= a.R) continue;
+            if (px >= npx || h0 + t >= a.RH) continue;
             float acc = 0.0f;
             for (int c = 0; c < a.C; ++c) acc = fmaf(xs[c * XP + pix], wrgb[o * a.C + c], acc);
             float v = fminf(fmaxf(acc + a.rgb_bias[o], -a.clamp), a.clamp);
-            const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.R + h0 + t) * a.R + w0 + px;
+            const long long oi = ((static_cast<long long>(b) * a.nimg + o) * a.RH + h0 + t) * a.RW + w0 + px;
             if (a.img_prev) v += a.img_prev[oi];
             a.img[oi] = v;
         }
@@ -345,19 +365,19 @@ __device__ __forceinline__ float reflect_coord(float x, int size) {
 }
 
 __global__ void __launch_bounds__(256) sg2_warp_kernel(const __half* __restrict__ src, __half* __restrict__ dst,
-                                                       const float* __restrict__ mats /*[B][2][3]*/, int B, int R, int Cp) {
+                                                       const float* __restrict__ mats /*[B][2][3]*/, int B, int RH, int RW, int Cp) {
     const int groups = Cp / 8;
-    const long long total = static_cast<long long>(B) * R * R * groups;
+    const long long total = static_cast<long long>(B) * RH * RW * groups;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int g = static_cast<int>(idx % groups);
         long long q = idx / groups;
-        const int x = static_cast<int>(q % R); q /= R;
-        const int y = static_cast<int>(q % R);
-        const int b = static_cast<int>(q / R);
+        const int x = static_cast<int>(q % RW); q /= RW;
+        const int y = static_cast<int>(q % RH);
+        const int b = static_cast<int>(q / RH);
         const float* m = mats + b * 6;
-        const float sx = reflect_coord(m[0] * x + m[1] * y + m[2], R);
-        const float sy = reflect_coord(m[3] * x + m[4] * y + m[5], R);
+        const float sx = reflect_coord(m[0] * x + m[1] * y + m[2], RW);
+        const float sy = reflect_coord(m[3] * x + m[4] * y + m[5], RH);
         const float fx = floorf(sx), fy = floorf(sy);
         const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
         const float tx = sx - fx, ty = sy - fy;
@@ -368,8 +388,8 @@ __global__ void __launch_bounds__(256) sg2_warp_kernel(const __half* __restrict_
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-            if (xx < 0 || xx >= R || yy < 0 || yy >= R) continue;  // grid_sample: out-of-range taps count as zero
-            const uint4 v = *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(b) * R + yy) * R + xx) * Cp + g * 8);
+            if (xx < 0 || xx >= RW || yy < 0 || yy >= RH) continue;  // grid_sample: out-of-range taps count as zero
+            const uint4 v = *reinterpret_cast<const uint4*>(src + ((static_cast<long long>(b) * RH + yy) * RW + xx) * Cp + g * 8);
             const __half2* hv = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -382,32 +402,32 @@ __global__ void __launch_bounds__(256) sg2_warp_kernel(const __half* __restrict_
         __half2* ov = reinterpret_cast<__half2*>(&o);
 #pragma unroll
         for (int c = 0; c < 4; ++c) ov[c] = __floats2half2_rn(acc[2 * c], acc[2 * c + 1]);
-        *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * R + y) * R + x) * Cp + g * 8) = o;
+        *reinterpret_cast<uint4*>(dst + ((static_cast<long long>(b) * RH + y) * RW + x) * Cp + g * 8) = o;
     }
 }
 
-// upsample2d(img, [1,3,3,1]): zero-insert x2, pad (2,1), 4x4 FIR with gain 4 (ops.py:117-133) on [N][r][r] planes
-__global__ void upsample_rgb_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int r) {
-    const int R = 2 * r;
+// upsample2d(img, [1,3,3,1]): zero-insert x2, pad (2,1), 4x4 FIR with gain 4 (ops.py:117-133) on [N][rh][rw] planes
+__global__ void upsample_rgb_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int rh, int rw) {
+    const int RH = 2 * rh, RW = 2 * rw;
     const float f4[4] = {0.25f, 0.75f, 0.75f, 0.25f};
-    const long long total = static_cast<long long>(N) * R * R;
+    const long long total = static_cast<long long>(N) * RH * RW;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int X = static_cast<int>(idx % R);
-        long long q = idx / R;
-        const int Y = static_cast<int>(q % R);
-        const int n = static_cast<int>(q / R);
-        const float* xp = x + static_cast<long long>(n) * r * r;
+        const int X = static_cast<int>(idx % RW);
+        long long q = idx / RW;
+        const int Y = static_cast<int>(q % RH);
+        const int n = static_cast<int>(q / RH);
+        const float* xp = x + static_cast<long long>(n) * rh * rw;
         float acc = 0.0f;
 #pragma unroll
         for (int ky = 0; ky < 4; ++ky) {
             const int my = Y + ky - 2;  // index into the zero-inserted signal
-            if (my < 0 || (my & 1) || (my >> 1) >= r) continue;
+            if (my < 0 || (my & 1) || (my >> 1) >= rh) continue;
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) {
                 const int mx = X + kx - 2;
-                if (mx < 0 || (mx & 1) || (mx >> 1) >= r) continue;
-                acc = fmaf(f4[ky] * f4[kx], xp[(my >> 1) * r + (mx >> 1)], acc);
+                if (mx < 0 || (mx & 1) || (mx >> 1) >= rw) continue;
+                acc = fmaf(f4[ky] * f4[kx], xp[(my >> 1) * rw + (mx >> 1)], acc);
             }
         }
         y[idx] = acc;
@@ -422,17 +442,144 @@ __global__ void img_to_unit_kernel(const float* __restrict__ img, float* __restr
     }
 }
 
-__global__ void img_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int B, int C, int R) {
-    const long long total = static_cast<long long>(B) * R * R * C;
+__global__ void img_to_u8_kernel(const float* __restrict__ img, uint8_t* __restrict__ out, int B, int C, long long npix) {
+    const long long total = static_cast<long long>(B) * npix * C;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
          idx += static_cast<long long>(gridDim.x) * blockDim.x) {
         const int c = static_cast<int>(idx % C);
         long long q = idx / C;
-        const int px = static_cast<int>(q % (static_cast<long long>(R) * R));
-        const int b = static_cast<int>(q / (static_cast<long long>(R) * R));
-        float v = (img[(static_cast<long long>(b) * C + c) * R * R + px] + 1.0f) * 0.5f;
+        const long long px = q % npix;
+        const int b = static_cast<int>(q / npix);
+        float v = (img[(static_cast<long long>(b) * C + c) * npix + px] + 1.0f) * 0.5f;
         v = fminf(fmaxf(v, 0.0f), 1.0f);
         out[idx] = static_cast<uint8_t>(rintf(v * 255.0f));
+    }
+}
+
+// ---- output-size hook (maua/GAN/wrappers/stylegan2.py:104-151, get_hook :216-340) ---------------------------------------------
+// The reference registers a forward hook on one SynthesisLayer that resizes its output ("stretch": bicubic interpolate;
+// "pad-<how>-<where>": torch.nn.functional.pad with a constant / reflect / replicate / circular border) and adds a fixed noise
+// map; the block's image is resized the same way and the hooked block's ToRGB output is mapped back first (inverse: bicubic to
+// the layer size, or the crop that undoes the padding).  Every later layer then runs on the resized, possibly non-square map.
+enum { SG2_RS_STRETCH = 0, SG2_RS_CONST = 1, SG2_RS_REFLECT = 2, SG2_RS_REPLICATE = 3, SG2_RS_CIRCULAR = 4 };
+
+// source index of padded coordinate o (already shifted by the leading pad) in a row of n samples; -1 = the constant
+__device__ __forceinline__ int pad_index(int o, int n, int mode) {
+    if (o >= 0 && o < n) return o;
+    if (mode == SG2_RS_CONST) return -1;
+    if (mode == SG2_RS_REPLICATE) return o < 0 ? 0 : n - 1;
+    if (mode == SG2_RS_CIRCULAR) { const int m = o % n; return m < 0 ? m + n : m; }
+    if (n == 1) return 0;
+    const int p = 2 * (n - 1);   // reflect without repeating the edge sample
+    int m = o % p;
+    if (m < 0) m += p;
+    return m < n ? m : p - m;
+}
+
+// channels-last fp32 [B][h][w][Cp] -> [B][oh][ow][Cp] (+ noise[c][oh][ow]) as fp32 (y32) or fp16 (y16: warps follow);
+// one thread = 4 channels of one output pixel
+__global__ void __launch_bounds__(256) sg2_resize_kernel(const float* __restrict__ x, float* __restrict__ y32, __half* __restrict__ y16,
+                                                         const float* __restrict__ noise, int B, int C, int h, int w, int Cp, int oh, int ow, int mode,
+                                                         int pad_t, int pad_l, float value) {
+    const int groups = Cp / 4;
+    const long long total = static_cast<long long>(B) * oh * ow * groups;
+    const float sh = static_cast<float>(h) / static_cast<float>(oh), sw = static_cast<float>(w) / static_cast<float>(ow);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int g = static_cast<int>(idx % groups);
+        long long r = idx / groups;
+        const int ox = static_cast<int>(r % ow); r /= ow;
+        const int oy = static_cast<int>(r % oh);
+        const int b = static_cast<int>(r / oh);
+        const float* src = x + static_cast<long long>(b) * h * w * Cp + g * 4;
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (mode == SG2_RS_STRETCH) {
+            const Taps t = make_taps(oy, ox, h, w, sh, sw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float row[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(src + (static_cast<long long>(t.iy[j]) * w + t.ix[i]) * Cp);
+                    row[0] += t.wx[i] * v.x; row[1] += t.wx[i] * v.y; row[2] += t.wx[i] * v.z; row[3] += t.wx[i] * v.w;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] += t.wy[j] * row[c];
+            }
+        } else {
+            const int sy = pad_index(oy - pad_t, h, mode), sx = pad_index(ox - pad_l, w, mode);
+            if (sy < 0 || sx < 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[c] = value;
+            } else {
+                const float4 v = *reinterpret_cast<const float4*>(src + (static_cast<long long>(sy) * w + sx) * Cp);
+                acc[0] = v.x; acc[1] = v.y; acc[2] = v.z; acc[3] = v.w;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ch = g * 4 + c;
+            if (ch >= C) acc[c] = 0.0f;   // the pad channels stay zero (conv operand)
+            else if (noise) acc[c] += noise[(static_cast<long long>(ch) * oh + oy) * ow + ox];
+        }
+        const long long o = ((static_cast<long long>(b) * oh + oy) * ow + ox) * Cp + g * 4;
+        if (y32) *reinterpret_cast<float4*>(y32 + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else {
+            *reinterpret_cast<__half2*>(y16 + o) = __floats2half2_rn(acc[0], acc[1]);
+            *reinterpret_cast<__half2*>(y16 + o + 2) = __floats2half2_rn(acc[2], acc[3]);
+        }
+    }
+}
+
+// per-channel mean and unbiased standard deviation over [B][H][W] of a channels-last map -> stats[c], stats[C + c]
+// (what the reference's hook measures on the resized features to draw its noise map, stylegan2.py:236-247); one CTA per channel
+__global__ void __launch_bounds__(256) sg2_channel_stats_kernel(const float* __restrict__ x, float* __restrict__ stats, long long npix, int C, int Cp) {
+    const int c = blockIdx.x;
+    double s = 0.0, ss = 0.0;
+    for (long long i = threadIdx.x; i < npix; i += blockDim.x) {
+        const double v = static_cast<double>(x[i * Cp + c]);
+        s += v; ss += v * v;
+    }
+    __shared__ double sh_s[256], sh_ss[256];
+    sh_s[threadIdx.x] = s; sh_ss[threadIdx.x] = ss;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (threadIdx.x < k) { sh_s[threadIdx.x] += sh_s[threadIdx.x + k]; sh_ss[threadIdx.x] += sh_ss[threadIdx.x + k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double n = static_cast<double>(npix), mean = sh_s[0] / n;
+        const double var = npix > 1 ? fmax((sh_ss[0] - n * mean * mean) / (n - 1.0), 0.0) : 0.0;
+        stats[c] = static_cast<float>(mean);
+        stats[C + c] = static_cast<float>(sqrt(var));
+    }
+}
+
+// fp32 planar images [N][h][w] -> [N][oh][ow] (+ add[N][oh][ow]): the image hooks of the hooked block.  Negative pads crop.
+__global__ void __launch_bounds__(256) sg2_img_resize_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ add,
+                                                             int N, int h, int w, int oh, int ow, int mode, int pad_t, int pad_l, float value) {
+    const long long total = static_cast<long long>(N) * oh * ow;
+    const float sh = static_cast<float>(h) / static_cast<float>(oh), sw = static_cast<float>(w) / static_cast<float>(ow);
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int ox = static_cast<int>(idx % ow);
+        const int oy = static_cast<int>((idx / ow) % oh);
+        const float* src = x + (idx / (static_cast<long long>(ow) * oh)) * h * w;
+        float acc = 0.0f;
+        if (mode == SG2_RS_STRETCH) {
+            const Taps t = make_taps(oy, ox, h, w, sh, sw);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float row = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) row += t.wx[i] * src[t.iy[j] * w + t.ix[i]];
+                acc += t.wy[j] * row;
+            }
+        } else {
+            const int sy = pad_index(oy - pad_t, h, mode), sx = pad_index(ox - pad_l, w, mode);
+            acc = (sy < 0 || sx < 0) ? value : src[sy * w + sx];
+        }
+        y[idx] = acc + (add ? add[idx] : 0.0f);
     }
 }
 
@@ -480,7 +627,37 @@ struct Sg2Net {
     std::vector<int> warp_layer;
     const float* warp_mats = nullptr;  // device [n_warps][warp_batch][2][3], caller-owned
     int warp_batch = 0;
+    // output-size hook (sg2_set_resize): layer = index into the wrapper's layer_names, -1 = none
+    int rs_layer = -1, rs_mode = 0, rs_th = 0, rs_tw = 0, rs_pad_t = 0, rs_pad_l = 0;
+    float rs_value = 0.0f;
+    const float* rs_noise = nullptr;   // device [C][th][tw] added to the resized features (layer 0: the resized constant input
+                                       // itself, noise included), caller-owned; nullptr = none
+    float* rs_stats = nullptr;         // device [2][C]: when set, the next forwards write mean / std of the resized features here
 };
+
+namespace {
+struct Sg2Dims { int h0, w0, h1, w1, ho, wo; };   // maps of conv0's output, conv1's output and what ToRGB / the next block see
+// Layer geometry behind an output-size hook on layer_names[L] (block L / 2): L = 0 resizes the constant input (a forward
+// pre-hook in the reference, no image hooks), an even L > 0 the output of conv0 (conv1 and ToRGB run resized), an odd L the
+// output of conv1 (ToRGB runs resized); every later block doubles what it receives.
+std::vector<Sg2Dims> sg2_dims(const Sg2Net* n) {
+    std::vector<Sg2Dims> d(n->blocks.size());
+    const int bk = n->rs_layer < 0 ? 1 << 30 : n->rs_layer / 2;
+    for (size_t j = 0; j < n->blocks.size(); ++j) {
+        const int s = n->blocks[j].res;
+        if (static_cast<int>(j) < bk) d[j] = {s, s, s, s, s, s};
+        else if (static_cast<int>(j) == bk) {
+            if (n->rs_layer == 0) d[j] = {n->rs_th, n->rs_tw, n->rs_th, n->rs_tw, n->rs_th, n->rs_tw};
+            else if (n->rs_layer % 2 == 0) d[j] = {s, s, n->rs_th, n->rs_tw, n->rs_th, n->rs_tw};
+            else d[j] = {s, s, s, s, n->rs_th, n->rs_tw};
+        } else {
+            const int h = 2 * d[j - 1].ho, w = 2 * d[j - 1].wo;
+            d[j] = {h, w, h, w, h, w};
+        }
+    }
+    return d;
+}
+}  // namespace
 
 static int sg2_alloc(Sg2Param& p, std::initializer_list<int64_t> shape) {
     p.shape.assign(shape.begin(), shape.end());
@@ -579,9 +756,11 @@ int sg2_set_param(Sg2Net* n, const char* name, const float* data, const int64_t*
     size_t numel = 1;
     for (int i = 0; i < ndim; ++i) numel *= static_cast<size_t>(shape[i]);
     if (p.plane) {
-        // the reference swaps noise_const for a per-frame [B,1,r,r] tensor on every call (wrappers/stylegan2.py:81-96)
-        MB_REQUIRE(numel >= p.plane && numel % p.plane == 0, "mb_net_set_param: '%s' has %zu elements, expected a multiple of %zu",
-                   name, numel, p.plane);
+        // the reference swaps noise_const for a per-frame [B,1,h,w] tensor on every call (wrappers/stylegan2.py:81-96), and
+        // behind an output-size hook for maps of the resized layer's size (:137-147): the last two dimensions are the map
+        MB_REQUIRE(ndim >= 2 && shape[ndim - 1] > 0 && shape[ndim - 2] > 0, "mb_net_set_param: '%s' needs a [..., h, w] shape", name);
+        p.plane = static_cast<size_t>(shape[ndim - 1]) * static_cast<size_t>(shape[ndim - 2]);
+        p.shape.assign(shape + ndim - 2, shape + ndim);
         if (numel > p.capacity) {
             MB_CUDA(cudaStreamSynchronize(stream));
             cudaFree(p.dev);
@@ -653,13 +832,15 @@ int sg2_finalize(Sg2Net* n, cudaStream_t stream) {
 
 namespace {
 struct Sg2Ws {
-    size_t styles, d, x, y, img0, img1, t0, t1, total;
+    size_t styles, d, x, y, img0, img1, img2, t0, t1, total;
     std::vector<size_t> style_l, d_l;  // per layer (conv0, conv1, torgb per block) float offsets
 };
 Sg2Ws sg2_ws(const Sg2Net* n, int B) {
     Sg2Ws w;
     size_t ns = 0, nd = 0, mx = 0, my = 0, mt = 0;
     const size_t nsx = n->precise ? 3 : 1, nsy = n->precise ? 2 : 1;   // channel blocks of X, planes (hi, lo) of Y
+    const std::vector<Sg2Dims> dims = sg2_dims(n);
+    size_t bi = 0, max_img = 0;
     for (const auto& b : n->blocks) {
         for (const Sg2Layer* L : {&b.conv0, &b.conv1, &b.torgb}) {
             w.style_l.push_back(ns);
@@ -667,23 +848,28 @@ Sg2Ws sg2_ws(const Sg2Net* n, int B) {
             ns += static_cast<size_t>(B) * L->cin;
             nd += static_cast<size_t>(B) * L->cout * (L == &b.conv0 ? 4 : 1);   // conv0: one coefficient per parity plane
         }
-        const size_t r = b.res;
-        mx = std::max(mx, static_cast<size_t>(B) * r * r * cpad16(b.cout) * nsx);
-        mt = std::max(mt, static_cast<size_t>(B) * r * r * cpad16(b.cout));
+        const Sg2Dims& g = dims[bi];
+        const size_t px_max = std::max({static_cast<size_t>(g.h0) * g.w0, static_cast<size_t>(g.h1) * g.w1, static_cast<size_t>(g.ho) * g.wo});
+        mx = std::max(mx, static_cast<size_t>(B) * px_max * cpad16(b.cout) * nsx);
+        mt = std::max(mt, static_cast<size_t>(B) * px_max * cpad16(b.cout));
         if (b.has_conv0) {
-            mx = std::max(mx, static_cast<size_t>(B) * (r / 2) * (r / 2) * cpad16(b.cin) * nsx);
-            my = std::max(my, static_cast<size_t>(B) * 4 * b.cout * (r / 2 + 1) * pitch8(static_cast<int>(r / 2 + 1)) * nsy);
+            const size_t hi = g.h0 / 2, wi = g.w0 / 2;
+            mx = std::max(mx, static_cast<size_t>(B) * hi * wi * cpad16(b.cin) * nsx);
+            my = std::max(my, static_cast<size_t>(B) * 4 * b.cout * (hi + 1) * pitch8(static_cast<int>(wi + 1)) * nsy);
         }
-        my = std::max(my, static_cast<size_t>(B) * b.cout * r * pitch8(static_cast<int>(r)) * nsy);
+        my = std::max(my, static_cast<size_t>(B) * b.cout * g.h1 * pitch8(g.w1) * nsy);
+        max_img = std::max({max_img, static_cast<size_t>(g.ho) * g.wo, static_cast<size_t>(b.res) * b.res});
+        ++bi;
     }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 1024); return o; };
     w.styles = take(ns * 4); w.d = take(nd * 4);
     w.x = take(mx * 2); w.y = take(my * 2);
-    const size_t img = static_cast<size_t>(B) * n->img_channels * n->res * n->res * 4;
+    const size_t img = static_cast<size_t>(B) * n->img_channels * max_img * 4;
     w.img0 = take(img); w.img1 = take(img);
+    w.img2 = n->rs_layer > 0 ? take(img) : off;   // the hooked block's ToRGB output before it is mapped back
     w.t0 = w.t1 = off;
-    if (!n->warp_layer.empty()) { w.t0 = take(mt * 2); w.t1 = take(mt * 2); }  // ping-pong buffers of the warped feature map (plain fp16)
+    if (!n->warp_layer.empty() || n->rs_layer > 0) { const size_t eb = n->rs_layer > 0 ? 4 : 2; w.t0 = take(mt * eb); w.t1 = take(mt * eb); }  // ping-pong buffers of the warped / resized feature map (plain fp16)
     w.total = off;
     return w;
 }
@@ -692,6 +878,30 @@ Sg2Ws sg2_ws(const Sg2Net* n, int B) {
 size_t sg2_workspace_bytes(const Sg2Net* n, int B) { return sg2_ws(n, B).total; }
 int sg2_num_ws(const Sg2Net* n) { return n->num_ws; }
 int sg2_resolution(const Sg2Net* n) { return n->res; }
+void sg2_output_hw(const Sg2Net* n, int* h, int* w) {
+    const Sg2Dims g = sg2_dims(n).back();
+    *h = g.ho; *w = g.wo;
+}
+
+int sg2_set_resize(Sg2Net* n, int layer, int mode, int th, int tw, int pad_t, int pad_l, float value, const float* noise, float* stats) {
+    if (layer < 0) {
+        n->rs_layer = -1; n->rs_noise = nullptr; n->rs_stats = nullptr;
+        return MB_OK;
+    }
+    MB_REQUIRE(layer < 2 * static_cast<int>(n->blocks.size()), "mb_sg2_set_resize: layer %d out of range [0, %d)", layer, 2 * static_cast<int>(n->blocks.size()));
+    MB_REQUIRE(mode >= SG2_RS_STRETCH && mode <= SG2_RS_CIRCULAR, "mb_sg2_set_resize: unknown mode %d", mode);
+    MB_REQUIRE(th >= 1 && tw >= 1 && th <= 8192 && tw <= 8192, "mb_sg2_set_resize: target size %dx%d out of range", th, tw);
+    const int s = n->blocks[layer / 2].res;
+    if (mode != SG2_RS_STRETCH) {
+        MB_REQUIRE(th >= s && tw >= s, "mb_sg2_set_resize: padding cannot shrink a %dx%d layer to %dx%d (negative padding is a TODO of the reference too)", s, s, th, tw);
+        MB_REQUIRE(pad_t >= 0 && pad_l >= 0 && pad_t <= th - s && pad_l <= tw - s, "mb_sg2_set_resize: leading pads (%d, %d) do not fit", pad_t, pad_l);
+        if (mode == SG2_RS_REFLECT) MB_REQUIRE(th - s < s && tw - s < s, "mb_sg2_set_resize: reflect padding needs pads smaller than the layer (%d)", s);
+    }
+    MB_REQUIRE(layer != 0 || noise != nullptr, "mb_sg2_set_resize: layer 0 takes the resized constant input as its map");
+    n->rs_layer = layer; n->rs_mode = mode; n->rs_th = th; n->rs_tw = tw; n->rs_pad_t = pad_t; n->rs_pad_l = pad_l; n->rs_value = value;
+    n->rs_noise = noise; n->rs_stats = stats;
+    return MB_OK;
+}
 int sg2_last_launches(const Sg2Net* n) { return n->last_launches; }
 void sg2_set_conv_impl(Sg2Net* n, int impl) { n->conv_impl = impl; }
 void sg2_set_precise(Sg2Net* n, int on) { n->precise = on ? 1 : 0; }
@@ -778,23 +988,25 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
         mark(0, -1);
     }
 
+    const std::vector<Sg2Dims> dims = sg2_dims(n);
+    float* img_y = reinterpret_cast<float*>(base + wl.img2);
     int cur = 0;  // which img buffer holds the previous block's image
     bool have_img = false;
     for (size_t bi = 0; bi < n->blocks.size(); ++bi) {
         const Sg2Block& b = n->blocks[bi];
-        const int r = b.res;
+        const Sg2Dims& g = dims[bi];
         const bool last = bi + 1 == n->blocks.size();
         const float* s_conv0 = styles + wl.style_l[bi * 3 + 0];
         const float* s_conv1 = styles + wl.style_l[bi * 3 + 1];
         const float* s_rgb = styles + wl.style_l[bi * 3 + 2];
-        // phase = 1: the polyphase transposed conv (2x2 'full' kernel, 4 * cout parity planes of (hin + 1)^2); else 3x3 'same'
-        auto conv = [&](const Sg2Layer& L, const __half* xin, int hin, int phase, const float* d) -> int {
+        // phase = 1: the polyphase transposed conv (2x2 'full' kernel, 4 * cout parity planes of (hin + 1) x (win + 1)); else 3x3 'same'
+        auto conv = [&](const Sg2Layer& L, const __half* xin, int hin, int win, int phase, const float* d) -> int {
             ConvTcArgs ca;
             ca.x = xin; ca.wpk = L.wpk; ca.d = d; ca.bias = nullptr; ca.y = Y;
-            ca.B = B; ca.Cin = nsx * cpad16(L.cin); ca.Cout = phase ? 4 * L.cout : L.cout; ca.Hin = hin; ca.Win = hin; ca.Cp_in = ca.Cin;
+            ca.B = B; ca.Cin = nsx * cpad16(L.cin); ca.Cout = phase ? 4 * L.cout : L.cout; ca.Hin = hin; ca.Win = win; ca.Cp_in = ca.Cin;
             ca.ksz = phase ? 2 : 3; ca.pad = 1;
-            const int hout = hin + 2 * ca.pad - (ca.ksz - 1);
-            ca.Wp_out = pitch8(hout); ca.tile_w = 32; ca.num_sms = num_sms;
+            const int hout = hin + 2 * ca.pad - (ca.ksz - 1), wout = win + 2 * ca.pad - (ca.ksz - 1);
+            ca.Wp_out = pitch8(wout); ca.tile_w = 32; ca.num_sms = num_sms;
             if (n->precise && n->conv_impl == 0) {
                 ca.pm_max_cout = 0; ca.cm_shift = 0;   // the split epilogue lives in the plain cout-major tile
                 ca.split_lo_off = static_cast<long long>(B) * ca.Cout * hout * ca.Wp_out;
@@ -804,29 +1016,39 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             mark(2, static_cast<int>(2 * bi) + (phase ? 0 : 1));
             return rr;
         };
+        // one pass of the fused kernel over an rh x rw map; out_img: where the ToRGB result (+ prev) goes
         auto act_raw = [&](const Sg2Layer& L, int fir, const float* style_next, __half* x_next, bool rgb, const float* prev,
-                           const __half* pre, int ns_out) -> int {
+                           const __half* pre, int ns_out, int rh, int rw, float* out_img, const float* pre32, float* x_next32) -> int {
             ActArgs a;
-            a.y = Y; a.pre = pre; a.noise = L.noise.dev; a.bias = L.bias.dev;
-            const size_t nb = L.noise.numel / L.noise.plane;
-            MB_REQUIRE(nb == 1 || nb == static_cast<size_t>(B), "mb_net_forward: noise of a %dx%d layer holds %zu maps, batch is %d",
-                       r, r, nb, B);
-            a.noise_bstride = nb == 1 ? 0 : static_cast<long long>(L.noise.plane);
+            a.y = Y; a.pre = pre; a.pre32 = pre32; a.x_next32 = x_next32; a.noise = L.noise.dev; a.bias = L.bias.dev;
+            const bool from_conv = pre == nullptr && pre32 == nullptr;
+            if (from_conv) {
+                const size_t nb = L.noise.plane ? L.noise.numel / L.noise.plane : 0;
+                MB_REQUIRE(L.noise.shape.size() == 2 && L.noise.shape[0] == rh && L.noise.shape[1] == rw,
+                           "mb_net_forward: the noise map of this %dx%d layer is %lldx%lld (behind an output-size hook every later layer needs noise of its new size)",
+                           rh, rw, L.noise.shape.size() == 2 ? static_cast<long long>(L.noise.shape[0]) : 0LL,
+                           L.noise.shape.size() == 2 ? static_cast<long long>(L.noise.shape[1]) : 0LL);
+                MB_REQUIRE(nb == 1 || nb == static_cast<size_t>(B), "mb_net_forward: noise of a %dx%d layer holds %zu maps, batch is %d",
+                           rh, rw, nb, B);
+                a.noise_bstride = nb == 1 ? 0 : static_cast<long long>(L.noise.plane);
+            } else {
+                a.noise_bstride = 0;
+            }
             a.style_next = style_next; a.x_next = x_next;
             a.rgb_w = rgb ? b.torgb.weight.dev : nullptr; a.rgb_style = s_rgb; a.rgb_bias = b.torgb.bias.dev;
-            a.img_prev = prev; a.img = img[cur ^ 1];
-            a.B = B; a.C = L.cout; a.R = r; a.Hy = fir ? r + 1 : r; a.Cp = cpad16(L.cout);
+            a.img_prev = prev; a.img = out_img;
+            a.B = B; a.C = L.cout; a.RH = rh; a.RW = rw; a.Hy = fir ? rh + 1 : rh; a.Wy = fir ? rw + 1 : rw; a.Cp = cpad16(L.cout);
             a.phase = fir; a.ns = ns_out;
-            a.Wpy = fir ? pitch8(r / 2 + 1) : pitch8(r);
-            a.y_lo = (n->precise && n->conv_impl == 0) ? static_cast<long long>(B) * (fir ? 4 : 1) * L.cout * (fir ? r / 2 + 1 : r) * a.Wpy : 0;
+            a.Wpy = fir ? pitch8(rw / 2 + 1) : pitch8(rw);
+            a.y_lo = (n->precise && n->conv_impl == 0) ? static_cast<long long>(B) * (fir ? 4 : 1) * L.cout * (fir ? rh / 2 + 1 : rh) * a.Wpy : 0;
             a.fir = fir; a.nimg = n->img_channels; a.clamp = 256.0f;
-            if (pre == nullptr && n->act_tiled) {
+            if (from_conv && n->act_tiled) {
                 // tiled kernel: rows per CTA by what the staged block costs in shared memory
-                const int th = (L.cout <= 128 && r >= 4) ? 4 : ((L.cout <= 256 && r >= 2) ? 2 : 1);
+                const int th = (L.cout <= 128 && rh >= 4) ? 4 : ((L.cout <= 256 && rh >= 2) ? 2 : 1);
                 const size_t smem = sizeof(float) * (static_cast<size_t>(L.cout) * (th * kActP + 1) + 8 * (th + 3) * 36 + th * kActP + n->img_channels * L.cout);
                 auto run = [&](auto kern) -> int {
                     MB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    dim3 grid(ceil_div(r, kActP), ceil_div(r, th), B);
+                    dim3 grid(ceil_div(rw, kActP), ceil_div(rh, th), B);
                     kern<<<grid, 256, smem, stream>>>(a);
                     return MB_OK;
                 };
@@ -839,7 +1061,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
                     MB_CUDA(cudaFuncSetAttribute(sg2_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
                     smem_set = smem;
                 }
-                dim3 grid(ceil_div(r, kActP), r, B);
+                dim3 grid(ceil_div(rw, kActP), rh, B);
                 sg2_act_kernel<<<grid, 256, smem, stream>>>(a);
             }
             MB_CUDA(cudaGetLastError());
@@ -848,58 +1070,118 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
             return MB_OK;
         };
         // name_idx = position of this layer in the wrapper's layer_names (stylegan2.py:48-51): block 0 owns entries 0 and 1
-        // (both "bs.0.conv1"), block i entries 2i (conv0) and 2i + 1 (conv1).  With warps on the layer, the activation
-        // is first written unstyled, warped in hook order (ping-pong), and only then styled / sent through ToRGB.
-        auto act = [&](const Sg2Layer& L, int fir, const float* style_next, bool rgb, const float* prev, int name_idx) -> int {
+        // (both "bs.0.conv1"), block i entries 2i (conv0) and 2i + 1 (conv1).  With an output-size hook or warps on the layer,
+        // the activation is first written unstyled (rh x rw), resized (-> oh x ow), warped in hook order (ping-pong), and only
+        // then styled / sent through ToRGB.  The reference registers the resize hook at construction, the warps later: torch runs
+        // forward hooks in registration order.
+        auto act = [&](const Sg2Layer& L, int fir, const float* style_next, bool rgb, const float* prev, int name_idx, int rh, int rw,
+                       int oh, int ow, float* out_img) -> int {
             bool warped = false;
             for (int wl_ : n->warp_layer)
                 if (wl_ == name_idx || (bi == 0 && wl_ <= 1)) warped = true;
-            if (!warped) return act_raw(L, fir, style_next, style_next ? X : nullptr, rgb, prev, nullptr, nsx);
+            const bool resized = n->rs_layer > 0 && n->rs_layer == name_idx;
+            if (!warped && !resized) return act_raw(L, fir, style_next, style_next ? X : nullptr, rgb, prev, nullptr, nsx, rh, rw, out_img, nullptr, nullptr);
             int rr;
-            if ((rr = act_raw(L, fir, nullptr, T[0], false, nullptr, nullptr, 1)) != MB_OK) return rr;   // the warps run on plain fp16
-            int cur_t = 0;
             const int cp = cpad16(L.cout);
+            int cur_t = 0;
+            const float* final32 = nullptr;
+            if (resized) {
+                // the hooked map keeps fp32 precision: unstyled activation -> fp32, resize (+ noise) in fp32, second pass reads fp32
+                float* T32[2] = {reinterpret_cast<float*>(T[0]), reinterpret_cast<float*>(T[1])};
+                if ((rr = act_raw(L, fir, nullptr, nullptr, false, nullptr, nullptr, 1, rh, rw, nullptr, nullptr, T32[0])) != MB_OK) return rr;
+                const long long tot = static_cast<long long>(B) * oh * ow * (cp / 4);
+                sg2_resize_kernel<<<grid1d(tot), 256, 0, stream>>>(T32[0], T32[1], nullptr, n->rs_noise, B, L.cout, rh, rw, cp, oh, ow, n->rs_mode,
+                                                                   n->rs_pad_t, n->rs_pad_l, n->rs_value);
+                MB_CUDA(cudaGetLastError());
+                launches += 1;
+                if (n->rs_stats) {
+                    // statistics of the resized features (the wrapper's probe forward runs while the noise map does not exist yet)
+                    sg2_channel_stats_kernel<<<L.cout, 256, 0, stream>>>(T32[1], n->rs_stats, static_cast<long long>(B) * oh * ow, L.cout, cp);
+                    MB_CUDA(cudaGetLastError());
+                    launches += 1;
+                }
+                final32 = T32[1];
+                if (warped) {
+                    // the warps run on plain fp16: identity "pad" of the resized map into the other buffer as halves
+                    sg2_resize_kernel<<<grid1d(tot), 256, 0, stream>>>(T32[1], nullptr, T[0], nullptr, B, L.cout, oh, ow, cp, oh, ow, SG2_RS_CONST, 0, 0, 0.0f);
+                    MB_CUDA(cudaGetLastError());
+                    launches += 1;
+                    final32 = nullptr;
+                    cur_t = 0;
+                }
+                mark(4, name_idx);
+            } else {
+                if ((rr = act_raw(L, fir, nullptr, T[0], false, nullptr, nullptr, 1, rh, rw, nullptr, nullptr, nullptr)) != MB_OK) return rr;   // warps run on plain fp16
+            }
             for (size_t wi = 0; wi < n->warp_layer.size(); ++wi) {
                 const int wl_ = n->warp_layer[wi];
                 if (!(wl_ == name_idx || (bi == 0 && wl_ <= 1))) continue;
-                const long long tot = static_cast<long long>(B) * r * r * (cp / 8);
-                sg2_warp_kernel<<<grid1d(tot), 256, 0, stream>>>(T[cur_t], T[cur_t ^ 1], n->warp_mats + wi * static_cast<size_t>(B) * 6, B, r, cp);
+                const long long tot = static_cast<long long>(B) * oh * ow * (cp / 8);
+                sg2_warp_kernel<<<grid1d(tot), 256, 0, stream>>>(T[cur_t], T[cur_t ^ 1], n->warp_mats + wi * static_cast<size_t>(B) * 6, B, oh, ow, cp);
                 MB_CUDA(cudaGetLastError());
                 launches += 1;
                 mark(4, name_idx);
                 cur_t ^= 1;
             }
-            return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, T[cur_t], nsx);
+            return act_raw(L, 0, style_next, style_next ? X : nullptr, rgb, prev, final32 ? nullptr : T[cur_t], nsx, oh, ow, out_img, final32, nullptr);
         };
+        const bool hooked_block = n->rs_layer > 0 && n->rs_layer / 2 == static_cast<int>(bi);   // image hooks of this block
+        const int hin = bi > 0 ? dims[bi - 1].ho : 0, win = bi > 0 ? dims[bi - 1].wo : 0;
         if (!b.has_conv0) {
-            const long long tot = static_cast<long long>(B) * r * r * cpad16(b.cout);
-            const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(b.cst.dev, s_conv1, X, B, b.cout, r, cpad16(b.cout), nsx);
+            const bool override_cst = n->rs_layer == 0;   // pre-hook on bs.0.conv1: the wrapper hands over the resized constant (+ noise)
+            const long long tot = static_cast<long long>(B) * g.h1 * g.w1 * cpad16(b.cout);
+            const_input_kernel<<<grid1d(tot), 256, 0, stream>>>(override_cst ? n->rs_noise : b.cst.dev, s_conv1, X, B, b.cout, g.h1 * g.w1,
+                                                                cpad16(b.cout), nsx);
             MB_CUDA(cudaGetLastError());
             launches += 1;
             mark(1, -1);
         } else {
-            // conv0: X holds x * style(conv0) at r/2 -> polyphase transposed conv (four parity planes) -> FIR + act
-            if ((rc = conv(b.conv0, X, r / 2, 1, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
-            if ((rc = act(b.conv0, 1, s_conv1, false, nullptr, static_cast<int>(2 * bi))) != MB_OK) return rc;
+            // conv0: X holds x * style(conv0) at (hin, win) -> polyphase transposed conv (four parity planes) -> FIR + act
+            if ((rc = conv(b.conv0, X, hin, win, 1, dco + wl.d_l[bi * 3 + 0])) != MB_OK) return rc;
+            if ((rc = act(b.conv0, 1, s_conv1, false, nullptr, static_cast<int>(2 * bi), g.h0, g.w0, g.h1, g.w1, nullptr)) != MB_OK) return rc;
         }
         (void)s_conv0;
-        if ((rc = conv(b.conv1, X, r, 0, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
+        if ((rc = conv(b.conv1, X, g.h1, g.w1, 0, dco + wl.d_l[bi * 3 + 1])) != MB_OK) return rc;
+        // skip image: the previous image upsampled to this block's ORIGINAL size (twice the previous block's output)
+        const int ih = have_img ? 2 * hin : b.res, iw = have_img ? 2 * win : b.res;
         const float* prev = nullptr;
         if (have_img) {
-            // img[cur] (r/2) -> upsampled into img[cur^1]?  keep three-step: upsample into the other buffer, accumulate in place
-            const long long tot = static_cast<long long>(B) * n->img_channels * r * r;
-            upsample_rgb_kernel<<<grid1d(tot), 256, 0, stream>>>(img[cur], img[cur ^ 1], B * n->img_channels, r / 2);
+            const long long tot = static_cast<long long>(B) * n->img_channels * ih * iw;
+            upsample_rgb_kernel<<<grid1d(tot), 256, 0, stream>>>(img[cur], img[cur ^ 1], B * n->img_channels, hin, win);
             MB_CUDA(cudaGetLastError());
             launches += 1;
             mark(5, static_cast<int>(bi));
             prev = img[cur ^ 1];
         }
         const float* s_next = last ? nullptr : styles + wl.style_l[(bi + 1) * 3 + 0];
-        if ((rc = act(b.conv1, 0, s_next, true, prev, static_cast<int>(2 * bi + 1))) != MB_OK) return rc;
+        // a hook on block 0's second name (layer 1) is the same conv1 as name 1
+        const int name1 = static_cast<int>(2 * bi + 1);
+        if (!hooked_block) {
+            if ((rc = act(b.conv1, 0, s_next, true, prev, name1, g.h1, g.w1, g.ho, g.wo, img[cur ^ 1])) != MB_OK) return rc;
+        } else {
+            // image hooks (stylegan2.py:129-135, get_hook :330-338): ToRGB sees the resized features; its output is mapped back to the
+            // layer size (rgb_hook = inverse), added to the upsampled previous image, and the block's image is resized (img_hook)
+            if ((rc = act(b.conv1, 0, s_next, true, nullptr, name1, g.h1, g.w1, g.ho, g.wo, img_y)) != MB_OK) return rc;
+            const int N3 = B * n->img_channels;
+            const bool stretch = n->rs_mode == SG2_RS_STRETCH;
+            float* img_s = img[cur];   // the previous image has been consumed by the upsample above
+            const long long tot_s = static_cast<long long>(N3) * ih * iw;
+            sg2_img_resize_kernel<<<grid1d(tot_s), 256, 0, stream>>>(img_y, img_s, prev, N3, g.ho, g.wo, ih, iw, stretch ? SG2_RS_STRETCH : SG2_RS_CONST,
+                                                                     stretch ? 0 : -n->rs_pad_t, stretch ? 0 : -n->rs_pad_l, 0.0f);
+            MB_CUDA(cudaGetLastError());
+            const long long tot_o = static_cast<long long>(N3) * g.ho * g.wo;
+            sg2_img_resize_kernel<<<grid1d(tot_o), 256, 0, stream>>>(img_s, img[cur ^ 1], nullptr, N3, ih, iw, g.ho, g.wo, n->rs_mode, n->rs_pad_t,
+                                                                     n->rs_pad_l, n->rs_value);
+            MB_CUDA(cudaGetLastError());
+            launches += 2;
+            mark(5, static_cast<int>(bi));
+        }
         cur ^= 1;
         have_img = true;
     }
-    const long long nout = static_cast<long long>(B) * n->img_channels * n->res * n->res;
+    const Sg2Dims& gl = dims.back();
+    const long long npix = static_cast<long long>(gl.ho) * gl.wo;
+    const long long nout = static_cast<long long>(B) * n->img_channels * npix;
     if (out_fmt == MB_OUT_F32_NCHW) {
         MB_CUDA(cudaMemcpyAsync(out, img[cur], nout * sizeof(float), cudaMemcpyDeviceToDevice, stream));
     } else if (out_fmt == MB_OUT_F32_NCHW_01 || out_fmt == MB_OUT_F32_NCHW_UNIT) {
@@ -907,7 +1189,7 @@ int sg2_forward(Sg2Net* n, const float* ws, int B, void* out, int out_fmt, void*
         MB_CUDA(cudaGetLastError());
         launches += 1;
     } else {
-        img_to_u8_kernel<<<grid1d(nout), 256, 0, stream>>>(img[cur], static_cast<uint8_t*>(out), B, n->img_channels, n->res);
+        img_to_u8_kernel<<<grid1d(nout), 256, 0, stream>>>(img[cur], static_cast<uint8_t*>(out), B, n->img_channels, npix);
         MB_CUDA(cudaGetLastError());
         launches += 1;
     }

@@ -16,6 +16,9 @@ size_t sg2_workspace_bytes(const Sg2Net* n, int B);
 int sg2_num_ws(const Sg2Net* n);
 int sg2_resolution(const Sg2Net* n);
 int sg2_set_warps(Sg2Net* n, int n_warps, const int32_t* layers, const float* inv_mats, int batch);
+// output-size hook (maua/GAN/wrappers/stylegan2.py:104-151): see mb_sg2_set_resize in include/maua_b200.h
+int sg2_set_resize(Sg2Net* n, int layer, int mode, int th, int tw, int pad_t, int pad_l, float value, const float* noise, float* stats);
+void sg2_output_hw(const Sg2Net* n, int* h, int* w);
 int sg2_last_launches(const Sg2Net* n);
 void sg2_set_conv_impl(Sg2Net* n, int impl);
 void sg2_set_precise(Sg2Net* n, int on);   // 1 (default): fp16 hi + lo operands and conv outputs; 0: plain fp16

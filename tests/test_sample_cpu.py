@@ -28,8 +28,22 @@ def test_load_audio_resamples_to_1024_samples_per_frame(tmp_path):
     assert 0.3 < float(audio.abs().max()) < 0.45
 
 
-def test_generate_rejects_unbuilt_sizes_before_touching_the_gpu(tmp_path):
-    from maua_b200.audiovisual.audioreactive.sample import generate
+def test_resize_strategy_parsing_matches_get_hook():
+    """Strategy strings of StyleGAN2Synthesizer.change_output_resolution (maua/GAN/wrappers/stylegan2.py:216-283): mode, leading
+    pads (top, left) and border value; the oracle restatement of get_hook agrees on the padding tuple."""
+    from maua_b200.GAN.wrappers.stylegan2 import parse_resize_strategy
+    from oracle.sg2_hooks import padding_of
 
+    assert parse_resize_strategy("stretch", 16, (20, 24)) == ("stretch", (0, 0), 0.0)
+    for how, mode, value in [("reflect", "reflect", 0.0), ("replicate", "replicate", 0.0), ("circular", "circular", 0.0), ("0.5", "constant", 0.5)]:
+        for where in ("out", "left", "right", "top", "bottom"):
+            got = parse_resize_strategy(f"pad-{how}-{where}", 16, (22, 26))
+            (left, right, top, bottom), omode, ovalue = padding_of(f"pad-{how}-{where}", 16, (22, 26))
+            assert got == (mode, (top, left), value) and (omode, ovalue) == (mode, value)
+            assert left + right == 10 and top + bottom == 6
+    assert parse_resize_strategy("pad-reflect-left", 16, (22, 26))[1] == (3, 10)
+    assert parse_resize_strategy("pad-reflect-bottom", 16, (22, 26))[1] == (0, 5)
+    with pytest.raises(Exception):
+        parse_resize_strategy("squash", 16, (20, 24))
     with pytest.raises(NotImplementedError):
-        generate(str(tmp_path / "missing.wav"), seed=1, downscale_factor=4)
+        parse_resize_strategy("pad-reflect-out", 16, (12, 24))

@@ -32,12 +32,16 @@ def test_generate_random_patch_video(cuda, tmp_path):
         w.writeframes((np.clip(y, -1, 1) * 32767).astype("<i2").tobytes())
     sink = CountingSink()
     torch.manual_seed(0)
-    out_file, written, patch = generate(wav, seed=5, fps=fps, batch_size=16, device="cuda", sink=sink)
+    out_file, written, patch = generate(wav, seed=5, fps=fps, downscale_factor=1, batch_size=16, device="cuda", sink=sink)
     T = seconds * fps
     assert written == ((T - 1) // 16) * 16 == 320          # the reference's loop drops the last partial batch (sample.py:85)
     assert sink.nbytes == written * 1024 * 1024 * 3
     assert out_file.endswith("track_RandomPatches++_seed5_1024x1024.mp4")
     assert len(set(sink.first)) > 8                          # not a constant image
     assert 2 <= len(patch.latent_patches) < 20 and patch.length == T
-    with pytest.raises(NotImplementedError):
-        generate(wav, seed=5, fps=fps, downscale_factor=4, sink=sink)
+    # a non-native size through the StyleGAN2 wrapper's output-size hook (the reference's defaults: "stretch" on layer 0):
+    # half the size, 3:2 -> the 4 x 4 constant input becomes 2 x 3 and every block runs non-square
+    sink2 = type(sink)()
+    out2, written2, _ = generate(wav, seed=5, fps=fps, downscale_factor=2, aspect_ratio=1.5, batch_size=16, device="cuda", sink=sink2)
+    assert written2 == written and sink2.nbytes == written2 * 768 * 512 * 3
+    assert out2.endswith("track_RandomPatches++_seed5_768x512.mp4") and len(set(sink2.first)) > 8

@@ -379,6 +379,25 @@ int mb_fir_reflect(const float* x, float* y, int planes, int h, int w, const flo
 int mb_std_normalize(float* x, int samples, int64_t per_sample, mb_stream stream);
 int mb_perlin_noise(const float* gradients, int s0, int s1, int s2, int r0, int r1, int r2, float* out, mb_stream stream);
 
+/* ---- RRDBNet: the RealESRGAN x4 generator (BASELINE configs[4]) ------------------------------------------------
+ * Replaces basicsr.archs.rrdbnet_arch.RRDBNet(num_in_ch=3, num_out_ch=3, num_feat=64, num_block=23 | 6, num_grow_ch=32, scale=4)
+ * as maua/super/image/models/realesrgan.py:22-41 builds it and RealESRGANer(half=True).model runs it (:44-49).  basicsr /
+ * realesrgan are absent third-party packages: the published architecture is restated (oracle/rrdb.py), parity unpinned.
+ * Parameter names = the checkpoint's state-dict keys: conv_first.{weight,bias}, body.<i>.rdb<1..3>.conv<1..5>.{weight,bias},
+ * conv_body, conv_up1, conv_up2, conv_hr, conv_last.  All data pointers are device pointers. */
+typedef struct mb_rrdb mb_rrdb;
+int mb_rrdb_create(int num_in_ch, int num_out_ch, int num_feat, int num_block, int num_grow_ch, int scale, mb_rrdb** out);
+void mb_rrdb_destroy(mb_rrdb* net);
+int mb_rrdb_set_param(mb_rrdb* net, const char* name, const float* data, const int64_t* shape, int ndim, mb_stream stream);
+int mb_rrdb_finalize(mb_rrdb* net, mb_stream stream);                    /* packs the fp16 weight tiles; synchronises */
+size_t mb_rrdb_workspace_bytes(const mb_rrdb* net, int batch, int height, int width);
+/* x: float32 NCHW in [0, 1] (in_fmt MB_OUT_F32_NCHW) or uint8 NHWC (MB_OUT_U8_NHWC), [batch, C, height, width];
+ * out: 4 * height x 4 * width as float32 NCHW (raw: MB_OUT_F32_NCHW, clamped to [0, 1]: MB_OUT_F32_NCHW_01) or uint8 NHWC
+ * (clamp, * 255, round: MB_OUT_U8_NHWC).  workspace: caller-owned, 1024-byte aligned, mb_rrdb_workspace_bytes big. */
+int mb_rrdb_forward(mb_rrdb* net, const void* x, int in_fmt, int batch, int height, int width, void* out, int out_fmt,
+                    void* workspace, size_t workspace_bytes, mb_stream stream);
+int mb_rrdb_last_launch_count(const mb_rrdb* net);
+
 #ifdef __cplusplus
 }
 #endif

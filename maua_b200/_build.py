@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 # MAUA_B200_LIB: load / build another copy of the library (A/B runs of kernel variants built with extra -D flags)
 LIB_PATH = os.environ.get("MAUA_B200_LIB") or os.path.join(LIB_DIR, "libmaua_b200.so")
-SOURCES = ["net.cu", "conv_tc.cu", "flrelu.cu", "flrelu_sep.cu", "flrelu_mma.cu", "sg3_misc.cu", "feature_resize.cu", "sg2.cu", "audio.cu", "chroma.cu", "signal_ops.cu", "sequencers.cu", "image_ops.cu"]
+SOURCES = ["net.cu", "conv_tc.cu", "flrelu.cu", "flrelu_sep.cu", "flrelu_mma.cu", "sg3_misc.cu", "feature_resize.cu", "sg2.cu", "rrdb.cu", "audio.cu", "chroma.cu", "signal_ops.cu", "sequencers.cu", "image_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

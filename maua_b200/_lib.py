@@ -61,6 +61,13 @@ _SIGNATURES = {
     "mb_net_set_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int]),
     "mb_sg3_resized_output": (C.c_int, [C.POINTER(SG3Cfg), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mb_sg2_set_warps": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), _P, C.c_int]),
+    "mb_rrdb_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "mb_rrdb_destroy": (None, [_P]),
+    "mb_rrdb_set_param": (C.c_int, [_P, C.c_char_p, _P, C.POINTER(C.c_int64), C.c_int, _P]),
+    "mb_rrdb_finalize": (C.c_int, [_P, _P]),
+    "mb_rrdb_workspace_bytes": (C.c_size_t, [_P, C.c_int, C.c_int, C.c_int]),
+    "mb_rrdb_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P, C.c_size_t, _P]),
+    "mb_rrdb_last_launch_count": (C.c_int, [_P]),
     "mb_sg2_set_resize": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "mb_gaussian_filter_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_float, C.c_int, C.c_float, C.c_int, _P]),
     "mb_salience": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P]),

@@ -747,6 +747,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
 struct PmsArgs {
     KArgs k;
     int Np, Nst, stages;
+    ConvTcArgs::NhwcOut o;   // o.y != nullptr: channels-last epilogue (bias, lrelu, residuals), see kernels.h
 };
 
 template <int NH>
@@ -918,6 +919,57 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 for (int k = 0; k < 16; ++k)
                     sum[k] = (__uint_as_float(v0[k]) + __shfl_down_sync(0xffffffffu, __uint_as_float(v1[k]), 1)) +
                              __shfl_down_sync(0xffffffffu, __uint_as_float(v2[k]), 2);
+                if (pa.o.y) {
+                    // channels-last: this lane's 16 couts of its pixel are 32 contiguous bytes
+                    if (ok) {
+                        const long long pixel = (static_cast<long long>(b) * a.Hout + h) * a.Wout + w;
+                        float v[16];
+                        const float4* tq = reinterpret_cast<const float4*>(tab + c0);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float4 sb = tq[k];
+                            v[2 * k] = fmaf(sum[2 * k], sb.x, sb.y);
+                            v[2 * k + 1] = fmaf(sum[2 * k + 1], sb.z, sb.w);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) v[k] = pa.o.alpha * (v[k] < 0.0f ? pa.o.slope * v[k] : v[k]);
+                        auto add_res = [&](const __half* r, int cp, int off, float g) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(r + pixel * cp + off + c0);
+                            const uint4 q0 = rp[0], q1 = rp[1];
+                            const __half2* h0 = reinterpret_cast<const __half2*>(&q0);
+                            const __half2* h1 = reinterpret_cast<const __half2*>(&q1);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float2 f0 = __half22float2(h0[k]), f1 = __half22float2(h1[k]);
+                                v[2 * k] = fmaf(g, f0.x, v[2 * k]); v[2 * k + 1] = fmaf(g, f0.y, v[2 * k + 1]);
+                                v[8 + 2 * k] = fmaf(g, f1.x, v[8 + 2 * k]); v[8 + 2 * k + 1] = fmaf(g, f1.y, v[8 + 2 * k + 1]);
+                            }
+                        };
+                        if (pa.o.r1) add_res(pa.o.r1, pa.o.r1_cp, pa.o.r1_off, pa.o.beta);
+                        if (pa.o.r2) add_res(pa.o.r2, pa.o.r2_cp, pa.o.r2_off, pa.o.gamma);
+                        uint4 o0, o1;
+                        __half2* p0 = reinterpret_cast<__half2*>(&o0);
+                        __half2* p1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            p0[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                            p1[k] = __floats2half2_rn(v[8 + 2 * k], v[8 + 2 * k + 1]);
+                        }
+                        __half* dst = pa.o.y + pixel * pa.o.cp + pa.o.c_off + c0;
+                        const int nco = a.Cout - c0;
+                        if (nco >= 16) {
+                            reinterpret_cast<uint4*>(dst)[0] = o0;
+                            reinterpret_cast<uint4*>(dst)[1] = o1;
+                        } else {   // a partial last block (e.g. the 3 couts of the output conv): element stores
+#pragma unroll
+                            for (int k = 0; k < 16; ++k)
+                                if (k < nco) dst[k] = __float2half_rn(v[k]);
+                        }
+                    }
+                    cb += 2;
+                    while (cb >= nblk) { cb -= nblk; ++hf; }
+                    continue;
+                }
                 // lane = pixel: a warp's 2-byte stores of one cout cover 64 contiguous bytes of its row (no pair-swap shuffles)
                 __half* yp = ybase + h * a.rs + c0 * a.cs;
                 const float4* tp = reinterpret_cast<const float4*>(tab + c0);
@@ -967,6 +1019,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
                               : (9 * ceil_div(p.Cin, kKC) * Np * 128 + 2 * 6 * kPmSlab + 1024 + 4096 + 256 <= kSmemMax ? 1 : 0))
                            : 0;
     // (1x1 layers, StyleGAN3-R: the cout-major tile with three epilogue groups and 32-byte stores wins, 1.92 -> 1.37 ms on L12 / L13)
+    MB_REQUIRE(p.nhwc.y == nullptr || pms_nh > 0, "conv_tc: the channels-last epilogue lives in the stacked pixel-major tile (3x3, <= 80 couts, resident weights)");
     const bool pixel_major = pms_nh > 0 || (p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && ((p.Cin > 32 && p.ksz > 1) || p.pm_max_cout > 64));
     const int tw = pixel_major ? kPmTW : (p.tile_w == 16 ? 16 : 32);
     const int th = kTileN / tw;
@@ -1078,7 +1131,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     if (pms_nh) {
         PmsArgs pa;
         pa.k = a;
-        pa.Np = Np; pa.Nst = 3 * Np;
+        pa.Np = Np; pa.Nst = 3 * Np; pa.o = p.nhwc;
         pa.k.tiles_m = 1;
         pa.k.tiles_w = ceil_div(a.Wout, 30);
         pa.k.tiles_h = ceil_div(a.Hout, 4 * pms_nh);

@@ -38,6 +38,19 @@ struct ConvTcArgs {
     int num_sms;
     long long split_lo_off = 0;      // > 0: also store fp16(v - fp16(v)) at y + split_lo_off (needs the cout-major tile: pm_max_cout = 0, cm_shift = 0)
     unsigned int* absmax = nullptr;  // device word (zeroed by the caller): atomicMax of the bits of max |y| over the stored outputs
+    // Channels-last output of the stacked pixel-major tile (the RRDB convs of csrc/rrdb.cu): when nhwc.y is set, the epilogue
+    // computes v = conv * d + bias, v = v < 0 ? slope * v : v, out = alpha * v + beta * r1 + gamma * r2 and stores fp16 at
+    // nhwc.y[((b * Hout + h) * Wout + w) * cp + c_off + cout]; r1 / r2 are channels-last fp16 maps of the same H x W (pixel pitch
+    // r*_cp, first channel r*_off) or nullptr.  `y` is ignored.
+    struct NhwcOut {
+        __half* y = nullptr;
+        int cp = 0, c_off = 0;
+        float slope = 1.0f, alpha = 1.0f, beta = 0.0f, gamma = 0.0f;
+        const __half* r1 = nullptr;
+        int r1_cp = 0, r1_off = 0;
+        const __half* r2 = nullptr;
+        int r2_cp = 0, r2_off = 0;
+    } nhwc;
 };
 int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream);
 int conv_tc_smem_bytes(int tw);

@@ -576,6 +576,180 @@ def run_sg2(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------
+# BASELINE configs[4]: StyleGAN2 512^2 + RealESRGAN 4x fused upscale pipeline, 60 s @ 30 fps, --config c5
+# ----------------------------------------------------------------------------------------------------
+def rrdb_algorithmic_flops(h, w, num_block=23):
+    """FLOPs per frame of RRDBNet(num_feat=64, num_grow_ch=32, scale=4) on an h x w input: 2 Cin Cout 9 per output pixel."""
+    rdb = sum(2.0 * (64 + 32 * k) * (32 if k < 4 else 64) * 9 for k in range(5))
+    per_px = 2.0 * 3 * 64 * 9 + num_block * 3 * rdb + 2.0 * 64 * 64 * 9
+    return h * w * per_px + 4 * h * w * 2.0 * 64 * 64 * 9 + 16 * h * w * (2 * 2.0 * 64 * 64 * 9 + 2.0 * 64 * 3 * 9)
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: maua_b200 has no CPU fallback")
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from maua_b200.GAN.networks import stylegan2 as N2
+    from maua_b200.audiovisual.render._loop import AsyncFrameDownloader
+    from maua_b200.super.image.models.realesrgan import RRDBNet
+    from maua_b200.workload import job_latents_device
+
+    B, K, W = min(args.batch, 4), args.steps, args.warmup
+    res, fps, seconds = 512, 30, 60.0
+    torch.manual_seed(0)
+    g = N2.SynthesisNetwork(w_dim=512, img_resolution=res, img_channels=3).to(dev)
+    up = RRDBNet(num_block=23).to(dev)
+    if world > 1:   # weights broadcast once
+        for t in list(g.parameters()) + list(g.buffers()) + list(up.parameters()):
+            dist.broadcast(t.data, src=0)
+    lat, audio_info = job_latents_device(g.num_ws, dev, seconds, fps)
+    if world > 1:
+        dist.broadcast(lat, src=0)
+    per = lat.shape[0] // world
+    my = lat[rank * per:(rank + 1) * per].contiguous()
+    nb = max(per // B, 1)
+    small = torch.empty(B, res, res, 3, device=dev, dtype=torch.uint8)
+    big = [torch.empty(B, 4 * res, 4 * res, 3, device=dev, dtype=torch.uint8) for _ in range(2)]
+    gathered = [[torch.empty_like(big[0]) for _ in range(world)] for _ in range(2)] if (world > 1 and rank == 0) else None
+    pending = [None, None]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+
+    def step(i, marks=None):
+        j, k = (i % nb) * B, i % 2
+        if pending[k] is not None:
+            pending[k].wait()
+        if marks: marks[0].record()
+        g(my[j:j + B], out_fmt="u8", out=small)                 # StyleGAN2 512^2 -> rgb24 frames in HBM
+        if marks: marks[1].record()
+        up(small, out_fmt="u8", out=big[k])                       # RealESRGAN x4 on the frames where they lie
+        if marks: marks[2].record()
+        if world > 1:
+            pending[k] = dist.gather(big[k], gathered[k] if rank == 0 else None, dst=0, async_op=True)
+
+    def drain():
+        for k in range(2):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        step(i)
+    drain()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step(W + i, ev[i])
+    drain()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    sg2_ms = sum(m[0].elapsed_time(m[1]) for m in ev) / K
+    up_ms = sum(m[1].elapsed_time(m[2]) for m in ev) / K
+    clk = clocks.stop() if rank == 0 else None
+    tmax = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    launches = (g.last_launch_count() + up.last_launch_count()) * K
+
+    # e2e: pinned host latents -> H2D per batch -> StyleGAN2 -> RealESRGAN -> rgb24 frames downloaded into a pinned ring
+    n_e2e = min(per - per % B, 40 * B)
+    host = torch.empty((n_e2e,) + tuple(my.shape[1:])).pin_memory()
+    host.copy_(my[:n_e2e])
+    dl = AsyncFrameDownloader((B, 4 * res, 4 * res, 3), dev, depth=2)
+
+    def e2e_job(n):
+        got = 0
+        for bi, j in enumerate(range(0, n, B)):
+            ws = host[j:j + B].to(dev, non_blocking=True)
+            g(ws, out_fmt="u8", out=small)
+            up(small, out_fmt="u8", out=dl.device_buffer(bi))
+            dl.download(bi)
+            if bi >= 1:
+                got += dl.host(bi - 1).numel()
+        got += dl.host((n - 1) // B).numel()
+        return got
+
+    e2e_job(2 * B)
+    barrier()
+    t0 = time.perf_counter()
+    nbytes = e2e_job(n_e2e)
+    torch.cuda.synchronize()
+    t_e2e = torch.tensor([time.perf_counter() - t0], device=dev)
+    assert nbytes == n_e2e * 16 * res * res * 3
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_fps = world * n_e2e / float(t_e2e.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = measured_peaks()
+    flops = rrdb_algorithmic_flops(res, res)
+    roof = {"kernel": "RRDBNet 3x3 convs: stacked pixel-major tcgen05 tile, channels-last lrelu / residual epilogue (353 launches / step)",
+            "bound": "tensor", "achieved": flops * B / (up_ms * 1e-3) / 1e12, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "traffic": None,
+            "peak_source": peaks["source"] + ", sustained", "ms_per_step": up_ms, "share_of_step": up_ms / (up_ms + sg2_ms)}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import rrdb as OR, sg2 as O2
+
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        onet = O2.make_synthesis(res, seed=0)
+        t0 = time.perf_counter()
+        img = onet(my[:1].cpu())
+        t_sg2 = time.perf_counter() - t0
+        ornet = OR.make(num_block=23)
+        crop = ((img[:, :, :128, :128] + 1) / 2).clamp(0, 1)
+        t0 = time.perf_counter()
+        ornet(crop)
+        t_up = (time.perf_counter() - t0) * 16.0
+        cpu = {"value": 1.0 / (t_sg2 + t_up), "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "1 frame: StyleGAN2 512^2 oracle in full, RRDBNet oracle on a 128 x 128 crop (1/16 of the frame) scaled by 16; "
+                         "fp32 PyTorch restatements, all host threads"}
+    emit({
+        "metric": "frames/sec StyleGAN2 512^2 + RealESRGAN x4 (2048^2 out) audio-reactive render", "value": world * B * K / (ms * 1e-3),
+        "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16 (StyleGAN2: hi+lo pairs), fp32 accumulate", "data": "synthetic",
+        "config": {"workload": "StyleGAN2 512^2 random-init + RealESRGAN x4plus (RRDBNet, 23 blocks, random init) fused on the device, 60 s @ 30 fps "
+                               "(1 800 frames) audio-reactive latents, frames sharded over the ranks", "name": "c5", "frames_per_step_per_gpu": B,
+                   "frames_per_gpu": per, "audio_features": audio_info,
+                   "collective": (f"per step: gather of the step's 2048^2 rgb24 frames to rank 0 over NCCL ({(world - 1) * B * 16 * res * res * 3} bytes "
+                                  f"into the root per step), overlapped with the next step") if world > 1 else "none (one rank)",
+                   "l2": "per-step working set (GBs of activations) >> 126 MB L2, no explicit flush"},
+        "clocks": clk,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * g.num_ws * 512 * 4, "d2h_bytes_per_step": B * 16 * res * res * 3,
+                "path": "pinned host latents -> H2D per batch -> StyleGAN2 (u8) -> RRDBNet (u8 in / out) -> D2H into a pinned ring", "frames_per_gpu": n_e2e},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "kernel_ms_per_step": {"stylegan2 512^2 (all kernels)": round(sg2_ms, 4), "RRDBNet x4 (all kernels)": round(up_ms, 4)},
+        "cpu_baseline": cpu,
+    })
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -584,8 +758,9 @@ def main():
     ap.add_argument("--batch", type=int, default=16,
                     help="frames per step per GPU (16 = the reference FFMPEG renderer's batch size, maua/audiovisual/render/ffmpeg.py:31)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["sg2"],
-                    help="c2 = BASELINE configs[1] (default, the headline), c3 = configs[2], sg2 = the StyleGAN2-1024 path (secondary line)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS) + ["sg2", "c5"],
+                    help="c2 = BASELINE configs[1] (default, the headline), c3 = configs[2], sg2 = the StyleGAN2-1024 path (secondary line), "
+                         "c5 = configs[4] (StyleGAN2 512^2 + RealESRGAN x4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -602,6 +777,8 @@ def main():
     guard_stdout()
     if args.config == "sg2":
         return run_sg2(args)
+    if args.config == "c5":
+        return run_c5(args)
     return run_ours(args)
 
 

@@ -999,6 +999,304 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Cout-major tile with the three kw taps STACKED ALONG M ("cms"), for 3x3 layers with at most 32 couts.
+// The stacked pixel-major tile above sits at its instruction floor, 64 cycles of A-operand (pixel rows) read per MMA.  Here the
+// pixels are the streamed B operand again (0.5 cycles per pixel and K = 16 step) and the M = 128 rows that a 32-cout layer
+// wastes in the plain cout-major tile carry the kw taps instead:
+//     D[(kw, cout), n] += A[(kw, cout), (kh, cin)] * B[(kh, cin), n],     row = 32 kw + cout  (rows 96..127 unused),
+// n = r * 34 + col over a 34-pixel-wide patch of 9 image rows (one TMA load per 64-channel chunk; tap kh = a B window that starts
+// kh * 34 pixel rows further on), N = 240 = 7 image rows per instruction, K = 3 Cin.  One MMA does the work of three of the plain
+// tile.  The kw shift is a TMEM COLUMN offset: the warp of lane quadrant kw reads row r at columns [34 r + kw, 34 r + kw + 32),
+//     y[cout, (r, col)] = D[(0, cout), 34 r + col] + D[(1, cout), 34 r + col + 1] + D[(2, cout), 34 r + col + 2],
+// and the three partials of a cout sit in three different quadrants, i.e. three different warps: quadrants 1 and 2 hand theirs to
+// quadrant 0 through a double-buffered shared-memory exchange (8 x STS.128 / LDS.128 per lane and row, one named barrier per row).
+// Three epilogue groups (warps 4..15) take the tile's seven rows in turn.  Weights resident: the A tile of (chunk, kh) is three
+// 32-row TMA boxes of the ordinary packed matrix (one per kw) landing back to back.  NHWC = channels-last epilogue (bias, lrelu,
+// residuals: csrc/rrdb.cu) through a per-warp transposition tile, else planar rows (d, bias, max |y|) like the other tiles.
+constexpr int kCmsPatchAlloc = 40960, kCmsPatchTx = 9 * 34 * 128, kCmsATile = 96 * 128, kCmsGroups = 3;
+constexpr int kCmsXchg = 2 * 4096;              // per group: two partials of 32 lanes x 32 floats; the channels-last epilogue reuses it
+                                                // as its [32 couts][33] transposition tile once the partials are in registers
+constexpr int kCmsMaxStages = 4;
+
+struct CmsArgs {
+    KArgs k;
+    int stages;
+    int xdepth;   // exchange tiles per group (2 where shared memory allows: quadrants 1 / 2 then run a row ahead of the reducer)
+    ConvTcArgs::NhwcOut o;
+};
+
+template <bool NHWC>
+__global__ void __launch_bounds__(128 + 128 * kCmsGroups, 1)
+conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, CmsArgs ca) {
+    const KArgs& a = ca.k;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int nst = ca.stages;
+    const int n_atiles = 3 * a.nCC;
+    // layout: [resident A tiles (chunk, kh): 96 rows each, + 4 KB the last M = 128 read runs into | patch stages | exchange |
+    //          transposition tiles | barriers]
+    uint8_t* stages = smem + n_atiles * kCmsATile + 4096;
+    uint8_t* xchg = stages + nst * kCmsPatchAlloc;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kCmsGroups * ca.xdepth * kCmsXchg);
+    uint64_t* full = bars;                          // [kCmsMaxStages]
+    uint64_t* empty = bars + kCmsMaxStages;         // [kCmsMaxStages]
+    uint64_t* tfull = bars + 2 * kCmsMaxStages;     // [2]
+    uint64_t* tempty = bars + 2 * kCmsMaxStages + 2;  // [2]
+    uint64_t* wfull = bars + 2 * kCmsMaxStages + 4;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCmsMaxStages + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int pad = a.pad;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_x);
+        for (int s = 0; s < nst; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull[s], 1);
+            mbar_init(&tempty[s], 4 * kCmsGroups);
+        }
+        mbar_init(wfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        const bool leader = elect_one();
+        int s = 0;
+        uint32_t ph = 0;
+        if (leader && blockIdx.x < a.total_tiles) {
+            mbar_arrive_expect_tx(wfull, static_cast<uint32_t>(n_atiles * kCmsATile));
+            for (int cc = 0; cc < a.nCC; ++cc)
+                for (int kh = 0; kh < 3; ++kh)
+                    for (int kw = 0; kw < 3; ++kw)
+                        tma_load_2d(smem + (cc * 3 + kh) * kCmsATile + kw * 4096, &tmap_w, wfull, ((kw * a.nCC + cc) * 3 + kh) * kKC, 0);
+        }
+        __syncwarp();
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            for (int cc = 0; cc < a.nCC; ++cc) {
+                mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
+                if (leader) {
+                    mbar_arrive_expect_tx(&full[s], kCmsPatchTx);
+                    tma_load_4d(stages + s * kCmsPatchAlloc, &tmap_x, &full[s], cc * kKC, wt * 32 - pad, ht * 7 - pad, b);
+                }
+                __syncwarp();
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        const bool leader = elect_one();
+        const uint32_t idesc = make_idesc_f16(128, 240, 0, 0);
+        int s = 0;
+        uint32_t ph = 0;
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        if (blockIdx.x < a.total_tiles) mbar_wait(wfull, 0, a.dbg, 5);
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * 256;
+            uint32_t accumulate = 0;
+            for (int cc = 0; cc < a.nCC; ++cc) {
+                int nk16 = (a.Cin - cc * kKC + 15) / 16;
+                if (nk16 > 4) nk16 = 4;
+                mbar_wait(&full[s], ph, a.dbg, 3);
+                tc_fence_after();
+                if (leader) {
+                    const uint64_t db = make_smem_desc(smem_u32(stages + s * kCmsPatchAlloc), 16, 1024, 2);
+                    const uint64_t da = make_smem_desc(smem_u32(smem) + cc * 3 * kCmsATile, 16, 1024, 2);
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll 4
+                        for (int j = 0; j < nk16; ++j) {
+                            umma_f16(d_tmem, da + static_cast<uint64_t>((kh * kCmsATile + j * 32) >> 4),
+                                     db + static_cast<uint64_t>((kh * 34 * 128 + j * 32) >> 4), idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == nst) { s = 0; ph ^= 1; }
+            }
+            if (leader) umma_commit(&tfull[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;            // TMEM lane quadrant = kw of this warp's partial sums
+        const int grp = (warp - 4) >> 2;   // rows grp, grp + 3, grp + 6 of every tile
+        // Exchange protocol (PTX producer / consumer barriers): per group and exchange tile one `full` barrier (quadrants 1 / 2
+        // bar.arrive after their stores, the reducer bar.sync's before its loads) and one `empty` barrier (the reducer bar.arrive's
+        // once it is done with the tile, quadrants 1 / 2 bar.sync before they overwrite it).
+        // The reducer of group g is its quadrant-g warp: warps 4, 9, 14 sit on three different schedulers (all quadrant-0 warps share
+        // one -- ncu r2: 3 600 cycles per tile with every reducer on SMSP 0, the tensor pipe 21..42 % busy).
+        const int red_q = grp;
+        const int slot = q - (q > red_q ? 1 : 0);      // exchange slot of a non-reducing quadrant (ascending kw)
+        const int xdepth = ca.xdepth;
+        uint8_t* xg = xchg + grp * xdepth * kCmsXchg;
+        const int bar_full = 1 + grp * 4, bar_empty = 3 + grp * 4;
+        int it = 0;                        // rows this warp has handled (selects the exchange tile)
+        __half2 amax = __floats2half2_rn(0.0f, 0.0f);
+        int acc = 0;
+        uint32_t acc_ph = 0;
+        const bool co_ok = lane < a.Cout;
+        const float bias = (co_ok && a.bias) ? a.bias[lane] : 0.0f;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            int r = t;
+            const int wt = r % a.tiles_w; r /= a.tiles_w;
+            const int ht = r % a.tiles_h; r /= a.tiles_h;
+            const int b = r;
+            const int h0 = ht * 7, w0 = wt * 32;
+            const float scale = (co_ok && a.d) ? a.d[b * a.Cout + lane] : (co_ok ? 1.0f : 0.0f);
+            mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
+            tc_fence_after();
+            auto release = [&]() {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+            };
+            if (q == 3) {
+                release();                     // rows 96..127 of the accumulator carry nothing
+            } else {
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + q;
+                for (int row = grp; row < 7; row += kCmsGroups) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tb + 34 * row, v);
+                    tmem_ld_wait_dep(v);
+                    if (row + kCmsGroups >= 7) release();    // this warp's last load of the tile has landed
+                    const int xbuf = it % xdepth;
+                    const bool reuse = it >= xdepth;     // the tile has been used before: wait for the reducer's hand-back
+                    ++it;
+                    const uint32_t xa = smem_u32(xg) + xbuf * kCmsXchg;
+                    float* tr = reinterpret_cast<float*>(xg + xbuf * kCmsXchg);
+                    if (q != red_q) {
+                        if (reuse) asm volatile("bar.sync %0, 96;" ::"r"(bar_empty + xbuf) : "memory");
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xa + slot * 4096 + (j * 32 + lane) * 16), "r"(v[4 * j]),
+                                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                         : "memory");
+                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_full + xbuf) : "memory");
+                        continue;
+                    }
+                    asm volatile("bar.sync %0, 96;" ::"r"(bar_full + xbuf) : "memory");
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t p1[4], p2[4];
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p1[0]), "=r"(p1[1]), "=r"(p1[2]), "=r"(p1[3]) : "r"(xa + (j * 32 + lane) * 16));
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p2[0]), "=r"(p2[1]), "=r"(p2[2]), "=r"(p2[3]) : "r"(xa + 4096 + (j * 32 + lane) * 16));
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            f[4 * j + k] = (__uint_as_float(v[4 * j + k]) + __uint_as_float(p1[k])) + __uint_as_float(p2[k]);
+                    }
+                    const int h = h0 + row;
+                    if constexpr (!NHWC) {
+                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_empty + xbuf) : "memory");   // the partials are in registers
+                        // planar rows: lane = cout writes its 32 pixels of image row h
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int k2 = 0; k2 < 16; ++k2) {
+                            const __half2 hv = __floats2half2_rn(fmaf(f[2 * k2], scale, bias), fmaf(f[2 * k2 + 1], scale, bias));
+                            track_abs(amax, hv);
+                            pk[k2] = *reinterpret_cast<const uint32_t*>(&hv);
+                        }
+                        if (co_ok && h < a.Hout) {
+                            __half* yrow = a.y + static_cast<long long>(b) * a.Cout * a.plane_out + lane * a.cs + h * a.rs + w0;
+                            if (a.st256) {
+#pragma unroll
+                                for (int g = 0; g < 2; ++g)
+                                    if (w0 + 16 * g < a.Wp_out)
+                                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(yrow + 16 * g), "r"(pk[8 * g]),
+                                                     "r"(pk[8 * g + 1]), "r"(pk[8 * g + 2]), "r"(pk[8 * g + 3]), "r"(pk[8 * g + 4]), "r"(pk[8 * g + 5]),
+                                                     "r"(pk[8 * g + 6]), "r"(pk[8 * g + 7])
+                                                     : "memory");
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    if (w0 + 8 * g < a.Wp_out)
+                                        *reinterpret_cast<uint4*>(yrow + 8 * g) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+                            }
+                        }
+                    } else {
+                        // channels-last: transpose the [32 couts][32 pixels] block through shared memory so that a lane owns a pixel
+                        __syncwarp();   // every lane holds its partials: the exchange tile becomes the transposition tile
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float y = fmaf(f[j], scale, bias);
+                            y = ca.o.alpha * (y < 0.0f ? ca.o.slope * y : y);
+                            tr[lane * 33 + j] = y;
+                        }
+                        __syncwarp();
+                        const int w = w0 + lane;
+                        float o[32];
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) o[c] = tr[c * 33 + lane];
+                        __syncwarp();
+                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_empty + xbuf) : "memory");   // exchange / transposition tile handed back
+                        if (h < a.Hout && w < a.Wout) {
+                            const long long pixel = (static_cast<long long>(b) * a.Hout + h) * a.Wout + w;
+                            auto add_res = [&](const __half* rp, int cp, int off, float gsc) {
+                                const uint4* rv = reinterpret_cast<const uint4*>(rp + pixel * cp + off);
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    const uint4 qv = rv[g];
+                                    const __half2* hh = reinterpret_cast<const __half2*>(&qv);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) {
+                                        const float2 ff = __half22float2(hh[k]);
+                                        o[8 * g + 2 * k] = fmaf(gsc, ff.x, o[8 * g + 2 * k]);
+                                        o[8 * g + 2 * k + 1] = fmaf(gsc, ff.y, o[8 * g + 2 * k + 1]);
+                                    }
+                                }
+                            };
+                            if (ca.o.r1) add_res(ca.o.r1, ca.o.r1_cp, ca.o.r1_off, ca.o.beta);
+                            if (ca.o.r2) add_res(ca.o.r2, ca.o.r2_cp, ca.o.r2_off, ca.o.gamma);
+                            __half* dst = ca.o.y + pixel * ca.o.cp + ca.o.c_off;
+                            if (a.Cout == 32) {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g) {
+                                    uint4 ov;
+                                    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k) oh[k] = __floats2half2_rn(o[8 * g + 2 * k], o[8 * g + 2 * k + 1]);
+                                    reinterpret_cast<uint4*>(dst)[g] = ov;
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 32; ++c)
+                                    if (c < a.Cout) dst[c] = __float2half_rn(o[c]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        }
+        if constexpr (!NHWC) publish_abs(a.absmax, amax);
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 int conv_tc_smem_bytes(int /*tw*/) { return kSmemMax; }
@@ -1012,15 +1310,19 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     const int Np = round_up(p.Cout, 16);
     // pixel-major pays off where the cout-major tile wastes >= half of its M rows and K is deep enough to amortise
     // the per-tile epilogue (B200 A/B, r1: L11 1.38 -> 1.23 ms, L12 0.77 -> 0.66 ms, but L13 with Cin = 32 0.50 -> 0.60 ms)
+    // cout-major stacked tile (conv_cms_kernel): 3x3 layers with at most 32 couts whose A tiles stay resident next to two patch stages
+    const int cms_fixed = 1024 + 256 + kCmsGroups * kCmsXchg + 4096;   // with one exchange tile per group
+    const bool cms = p.cm_stack && p.ksz == 3 && p.Cout <= 32 && p.split_lo_off <= 0 &&
+                     3 * ceil_div(p.Cin, kKC) * kCmsATile + 2 * kCmsPatchAlloc + cms_fixed <= kSmemMax;
     // stacked pixel-major tile (conv_pms_kernel): 3x3 layers whose three kw blocks fit one instruction (3 Np <= 256) and whose
     // weights stay resident next to two patch stages
-    const int pms_nh = (p.pm_max_cout > 0 && p.pm_stack && p.ksz == 3 && Np <= p.pm_max_cout && 3 * Np <= 256 && p.split_lo_off <= 0)
+    const int pms_nh = (!cms && p.pm_max_cout > 0 && p.pm_stack && p.ksz == 3 && Np <= p.pm_max_cout && 3 * Np <= 256 && p.split_lo_off <= 0)
                            ? ((12 * Np <= 512 && 9 * ceil_div(p.Cin, kKC) * Np * 128 + 2 * 10 * kPmSlab + 1024 + 4096 + 256 <= kSmemMax) ? 2
                               : (9 * ceil_div(p.Cin, kKC) * Np * 128 + 2 * 6 * kPmSlab + 1024 + 4096 + 256 <= kSmemMax ? 1 : 0))
                            : 0;
     // (1x1 layers, StyleGAN3-R: the cout-major tile with three epilogue groups and 32-byte stores wins, 1.92 -> 1.37 ms on L12 / L13)
-    MB_REQUIRE(p.nhwc.y == nullptr || pms_nh > 0, "conv_tc: the channels-last epilogue lives in the stacked pixel-major tile (3x3, <= 80 couts, resident weights)");
-    const bool pixel_major = pms_nh > 0 || (p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && ((p.Cin > 32 && p.ksz > 1) || p.pm_max_cout > 64));
+    MB_REQUIRE(p.nhwc.y == nullptr || pms_nh > 0 || cms, "conv_tc: the channels-last epilogue lives in the stacked tiles (3x3, <= 80 couts, resident weights)");
+    const bool pixel_major = !cms && (pms_nh > 0 || (p.pm_max_cout > 0 && Np <= p.pm_max_cout && Np <= 128 && ((p.Cin > 32 && p.ksz > 1) || p.pm_max_cout > 64)));
     const int tw = pixel_major ? kPmTW : (p.tile_w == 16 ? 16 : 32);
     const int th = kTileN / tw;
     const int pad = p.pad;
@@ -1042,11 +1344,11 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     // shift 2 (KArgs::th): 34-pixel-wide patch of 9 image rows; the windows of the two unused accumulator columns per row
     // and of columns 238..239 read up to pixel row 309 of the stage
     const int patch2_alloc = 40960, patch2_tx = 9 * 34 * 128;
-    const bool shift2 = !pixel_major && p.cm_shift == 2 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM && p.split_lo_off <= 0 &&
+    const bool shift2 = !cms && !pixel_major && p.cm_shift == 2 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM && p.split_lo_off <= 0 &&
                         (p.epi_groups == 0 || p.epi_groups == 3) && w_all + 2 * patch2_alloc + 1024 + 256 <= kSmemMax;
     const int patch_bytes = shift2 ? patch2_alloc : (th + halo) * tw * 128;
     // shift mode (one patch load per chunk, see KArgs) needs resident weights and room for its epilogue staging tiles
-    const bool want_shift = !pixel_major && p.cm_shift == 1 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
+    const bool want_shift = !cms && !pixel_major && p.cm_shift == 1 && p.ksz == 3 && tw == 32 && p.narrow_a && Mp == kTileM &&
                             w_all + 2 * patch_bytes + 1024 + 256 + kEpiStageBytes <= kSmemMax;
     MB_REQUIRE(p.split_lo_off <= 0 || (!pixel_major && !want_shift), "conv_tc: the split output needs the plain cout-major tile");
     const int fixed_bytes = 1024 /*align*/ + 256 /*barriers*/ + (want_shift ? kEpiStageBytes : 0);
@@ -1062,7 +1364,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(Ktot), static_cast<cuuint64_t>(Mp)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(Ktot) * 2};
-        cuuint32_t box[2] = {kKC, static_cast<cuuint32_t>(pixel_major ? Np : a_rows)};
+        cuuint32_t box[2] = {kKC, static_cast<cuuint32_t>(cms ? 32 : (pixel_major ? Np : a_rows))};
         cuuint32_t es[2] = {1, 1};
         CUresult r = enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(p.wpk), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1079,8 +1381,8 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cuuint64_t dims[4] = {static_cast<cuuint64_t>(p.Cp_in), static_cast<cuuint64_t>(p.Win),
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
         cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
-        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>(shift2 ? 34 : tw),
-                             static_cast<cuuint32_t>(pms_nh ? 4 * pms_nh + 2 : (shift2 ? 9 : th + halo)), 1};
+        cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>((shift2 || cms) ? 34 : tw),
+                             static_cast<cuuint32_t>(pms_nh ? 4 * pms_nh + 2 : ((shift2 || cms) ? 9 : th + halo)), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1128,6 +1430,34 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         a.total_tiles = p.B * a.tiles_h * a.tiles_w * a.tiles_m;
     }
 
+    if (cms) {
+        CmsArgs cg;
+        cg.k = a;
+        cg.o = p.nhwc;
+        cg.k.tiles_m = 1;
+        cg.k.tiles_w = ceil_div(a.Wout, 32);
+        cg.k.tiles_h = ceil_div(a.Hout, 7);
+        cg.k.total_tiles = p.B * cg.k.tiles_h * cg.k.tiles_w;
+        cg.k.st256 = (p.Wp_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) ? 1 : 0;
+        const int a_all = 3 * nCC * kCmsATile;
+        cg.xdepth = (cms_fixed + kCmsGroups * kCmsXchg + a_all + 2 * kCmsPatchAlloc <= kSmemMax) ? 2 : 1;
+        const int cms_fixed_x = cms_fixed + (cg.xdepth - 1) * kCmsGroups * kCmsXchg;
+        cg.stages = (kSmemMax - cms_fixed_x - a_all) / kCmsPatchAlloc;
+        if (cg.stages > kCmsMaxStages) cg.stages = kCmsMaxStages;
+        const int smem_bytes = cms_fixed_x + a_all + cg.stages * kCmsPatchAlloc;
+        static bool attr_cms = false;
+        if (!attr_cms) {
+            MB_CUDA(cudaFuncSetAttribute(conv_cms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute(conv_cms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            attr_cms = true;
+        }
+        int grid = cg.k.total_tiles < p.num_sms ? cg.k.total_tiles : p.num_sms;
+        if (grid < 1) grid = 1;
+        if (p.nhwc.y) conv_cms_kernel<true><<<grid, 128 + 128 * kCmsGroups, smem_bytes, stream>>>(tm_w, tm_x, cg);
+        else conv_cms_kernel<false><<<grid, 128 + 128 * kCmsGroups, smem_bytes, stream>>>(tm_w, tm_x, cg);
+        MB_CUDA(cudaGetLastError());
+        return MB_OK;
+    }
     if (pms_nh) {
         PmsArgs pa;
         pa.k = a;

@@ -28,6 +28,7 @@ struct ConvTcArgs {
     int pad;            // zero padding per side (StyleGAN3: ksz-1 'full', StyleGAN2: ksz/2 'same'); output = in + 2*pad - (ksz-1)
     int tile_w;         // pixel-tile width 32 (x8 rows) or 16 (x16 rows)
     int pm_max_cout = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major tile (0 = never)
+    int cm_stack = 0;      // 3x3 layers with <= 32 couts: cout-major tile with the kw taps stacked along M (conv_cms_kernel)
     int pm_stack = 1;      // 3x3 layers with 3 * ceil16(Cout) <= 256: pixel-major tile with the kw taps stacked along N (conv_pms_kernel)
     int pm_shift = 1;      // pixel-major tile: 1 / 2 = one patch load per chunk, kw shifts through the A descriptor start
     int cm_shift = 0;      // cout-major tile with resident weights: one patch load per chunk, kw shifts through the B descriptor start

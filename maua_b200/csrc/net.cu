@@ -87,6 +87,7 @@ struct mb_net {
     int conv_impl = 0;
     int conv_tile_w = 32;
     int conv_row_il = 0;      // conv outputs of layers with at most this many couts use the row-interleaved layout [B][H][C][Wp]
+    int conv_cm_stack = 0;    // stacked cout-major conv tile for 3x3 layers with <= 32 couts (conv_cms_kernel)
     int conv_pm_stack = 1;    // stacked pixel-major conv tile for the narrow 3x3 layers (conv_pms_kernel)
     int conv_epi_groups = 0;  // cout-major conv tile: epilogue warp groups (0 = per layer, see conv_tc_launch)
     int conv_pm_max = 64;  // layers with ceil16(Cout) <= this (and Cin > 32) run the pixel-major conv tile
@@ -669,6 +670,7 @@ extern "C" int mb_net_set_option(mb_net* net, const char* key, int value) {
     else if (k == "conv_pm_max") net->conv_pm_max = value;
     else if (k == "conv_epi_groups") net->conv_epi_groups = value;
     else if (k == "conv_pm_stack") net->conv_pm_stack = value;
+    else if (k == "conv_cm_stack") net->conv_cm_stack = value;
     else if (k == "conv_row_il") net->conv_row_il = value;
     else if (k == "conv_narrow_a") net->conv_narrow_a = value;
     else if (k == "conv_pm_shift") net->conv_pm_shift = value;
@@ -959,6 +961,7 @@ static int net_forward(mb_net* net, const float* ws, const float* transform, int
         ca.pm_max_cout = net->conv_pm_max;
         ca.epi_groups = net->conv_epi_groups;
         ca.pm_stack = net->conv_pm_stack;
+        ca.cm_stack = net->conv_cm_stack;
         ca.narrow_a = net->conv_narrow_a;
         ca.pm_shift = net->conv_pm_shift;
         ca.cm_shift = net->conv_cm_shift;
@@ -1097,6 +1100,7 @@ extern "C" int mb_modulated_conv2d(const float* x, const float* w, const float* 
         ca.B = B; ca.Cin = Cin; ca.Cout = Cout; ca.Hin = H; ca.Win = W; ca.Cp_in = Cp; ca.Wp_out = Wpo; ca.ksz = k;
         ca.pad = k - 1;
         ca.tile_w = (impl == 2) ? 16 : 32;
+        ca.cm_stack = (impl == 12) ? 1 : 0;   // 12: stacked cout-major tile where the layer has <= 32 couts (kw taps along M, TMEM column shifts)
         ca.pm_stack = (impl == 0 || impl == 11) ? 1 : 0;   // 11: stacked pixel-major tile wherever its three kw blocks fit one instruction
         if (impl == 11) ca.pm_max_cout = 80;
         else

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -117,6 +118,7 @@ struct mb_rrdb {
     bool finalized = false;
     int num_sms = 148;
     int last_launches = 0;
+    int cm_stack = 0;   // MB_RRDB_CMS=1: the <= 32-cout convs run the stacked cout-major tile (conv_cms_kernel)
 };
 
 static void rconv_free(RConv& c) {
@@ -151,6 +153,7 @@ extern "C" int mb_rrdb_create(int num_in_ch, int num_out_ch, int num_feat, int n
     sms = prop.multiProcessorCount;
     mb_rrdb* n = new mb_rrdb();
     n->in_ch = num_in_ch; n->out_ch = num_out_ch; n->blocks = num_block; n->num_sms = sms;
+    if (const char* e = getenv("MB_RRDB_CMS")) n->cm_stack = atoi(e);
     auto add = [&](RConv& c, const std::string& name, int cin, int cout) -> int {
         c.cin = cin; c.cout = cout;
         if (cudaMalloc(&c.w, sizeof(float) * cout * cin * 9) != cudaSuccess || cudaMalloc(&c.b, sizeof(float) * cout) != cudaSuccess) {
@@ -272,7 +275,7 @@ static int rrdb_conv(const mb_rrdb* n, const RConv& c, int part, const __half* x
     ca.x = x; ca.wpk = c.wpk[part]; ca.d = nullptr; ca.bias = c.b + (split ? part * 32 : 0); ca.y = o.y;
     ca.B = B; ca.Cin = c.cin < 16 ? 16 : c.cin; ca.Cout = split ? 32 : c.cout; ca.Hin = H; ca.Win = W; ca.Cp_in = cp_in;
     ca.Wp_out = pitch16(W); ca.ksz = 3; ca.pad = 1; ca.tile_w = 32;
-    ca.pm_max_cout = 64; ca.pm_stack = 1; ca.num_sms = n->num_sms;
+    ca.pm_max_cout = 64; ca.pm_stack = 1; ca.cm_stack = n->cm_stack; ca.num_sms = n->num_sms;
     ca.nhwc = o;
     return conv_tc_launch(ca, stream);
 }

@@ -1,6 +1,8 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_sg3_ops_gpu.py -x -q -k modulated_conv2d 2>&1 | tail -5 > gpurun_out/ab_tests.log
+timeout 300 python -m pytest tests/test_sg3_ops_gpu.py -x -q -k "modulated_conv2d and 12" 2>&1 | tail -5 > gpurun_out/ab_tests.log
+MB_RRDB_CMS=1 timeout 300 python -m pytest tests/test_rrdb_gpu.py -x -q -s 2>&1 | tail -8 >> gpurun_out/ab_tests.log
 python scripts/layer_times.py 16 T > gpurun_out/ab_T_default.txt 2>&1
-python scripts/layer_times.py 16 R > gpurun_out/ab_R_default.txt 2>&1
-cat gpurun_out/ab_tests.log; grep -E "L|total|conv'" gpurun_out/ab_T_default.txt; grep -E "L1[0-3]|total|conv'" gpurun_out/ab_R_default.txt
+MBOPT_CONV_CM_STACK=1 timeout 300 python scripts/layer_times.py 16 T > gpurun_out/ab_T_cms.txt 2>&1
+MB_RRDB_CMS=1 timeout 300 python bench.py --config c5 --no-cpu-baseline > gpurun_out/ab_c5_cms.json 2> gpurun_out/ab_c5_cms.err
+cat gpurun_out/ab_tests.log; grep -E "L1[0-3]|total|conv'" gpurun_out/ab_T_default.txt gpurun_out/ab_T_cms.txt; cut -c1-200 gpurun_out/ab_c5_cms.json; grep -o '"kernel_ms_per_step[^}]*}' gpurun_out/ab_c5_cms.json; tail -2 gpurun_out/ab_c5_cms.err

@@ -37,7 +37,8 @@ CONV_CASES = [
 # 8 cout-major tile with three epilogue warp groups (column-split, double-buffered tcgen05.ld), 9 the same with one group
 # 10 cout-major tile, one 34-pixel-wide patch load per chunk (7-row tiles, N = 240), three epilogue groups
 # 11 pixel-major tile with the three kw taps stacked along N (one instruction per (kh, 16 channels), shuffle-add epilogue)
-@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4, 7, 8, 9, 10, 11])
+# 12 cout-major tile with the kw taps stacked along M for layers with <= 32 couts (TMEM column shifts, cross-quadrant exchange)
+@pytest.mark.parametrize("impl", [1, 0, 2, 3, 4, 7, 8, 9, 10, 11, 12])
 def test_modulated_conv2d(cuda, case, impl):
     from maua_b200 import ops
 

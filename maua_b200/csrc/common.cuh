@@ -73,13 +73,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#ifndef MB_WAIT_HINT_NS
+#define MB_WAIT_HINT_NS 20000
+#endif
+#if MB_WAIT_HINT_NS > 0
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // parks in hardware up to the hinted time
         "selp.u32 %0, 1, 0, p;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(MB_WAIT_HINT_NS))
         : "memory");
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+#endif
     return ok != 0;
 }
 // Debug words in mapped host memory (survive a trapped kernel): see mb_debug_read().

@@ -1015,8 +1015,8 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 // 32-row TMA boxes of the ordinary packed matrix (one per kw) landing back to back.  NHWC = channels-last epilogue (bias, lrelu,
 // residuals: csrc/rrdb.cu) through a per-warp transposition tile, else planar rows (d, bias, max |y|) like the other tiles.
 constexpr int kCmsPatchAlloc = 40960, kCmsPatchTx = 9 * 34 * 128, kCmsATile = 96 * 128, kCmsGroups = 3;
-constexpr int kCmsXchg = 2 * 4096;              // per group: two partials of 32 lanes x 32 floats; the channels-last epilogue reuses it
-                                                // as its [32 couts][33] transposition tile once the partials are in registers
+constexpr int kCmsXchg = 3 * 32 * 33 * 4;       // per group: three rows x two source slots x 16 columns x 32 lanes of partial sums (12 KB);
+                                                // the channels-last epilogue reuses it as three [32 couts][33] transposition tiles
 constexpr int kCmsMaxStages = 4;
 
 struct CmsArgs {
@@ -1034,11 +1034,11 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nst = ca.stages;
     const int n_atiles = 3 * a.nCC;
-    // layout: [resident A tiles (chunk, kh): 96 rows each, + 4 KB the last M = 128 read runs into | patch stages | exchange |
-    //          transposition tiles | barriers]
-    uint8_t* stages = smem + n_atiles * kCmsATile + 4096;
+    // layout: [resident A tiles (chunk, kh): 96 rows each; the M = 128 read of the last one runs 4 KB into the first patch stage,
+    //          which feeds accumulator rows nobody reads | patch stages | exchange / transposition tiles | barriers]
+    uint8_t* stages = smem + n_atiles * kCmsATile;
     uint8_t* xchg = stages + nst * kCmsPatchAlloc;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kCmsGroups * ca.xdepth * kCmsXchg);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kCmsGroups * kCmsXchg);
     uint64_t* full = bars;                          // [kCmsMaxStages]
     uint64_t* empty = bars + kCmsMaxStages;         // [kCmsMaxStages]
     uint64_t* tfull = bars + 2 * kCmsMaxStages;     // [2]
@@ -1139,19 +1139,19 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     } else if (warp >= 4) {
+        // Epilogue.  Group g (warps 4 + 4g ..) owns image rows 3g, 3g + 1, 3g + 2 of the tile (group 2: row 6 only); inside a group
+        // the quadrant-q warp REDUCES row 3g + q: all three warps hold their kw partials of all three rows, hand the two rows they
+        // do not reduce to the shared-memory exchange and take the other two quadrants' partials of their own row back, in two
+        // halves of 16 columns (tcgen05.ld x16 x 3 rows).  So every warp converts and stores one row, three warps per scheduler share
+        // the work (the first build had ONE reducer warp per group: 3 150 cycles per tile whatever the layer's K, ncu r2).
         const int q = warp & 3;            // TMEM lane quadrant = kw of this warp's partial sums
-        const int grp = (warp - 4) >> 2;   // rows grp, grp + 3, grp + 6 of every tile
-        // Exchange protocol (PTX producer / consumer barriers): per group and exchange tile one `full` barrier (quadrants 1 / 2
-        // bar.arrive after their stores, the reducer bar.sync's before its loads) and one `empty` barrier (the reducer bar.arrive's
-        // once it is done with the tile, quadrants 1 / 2 bar.sync before they overwrite it).
-        // The reducer of group g is its quadrant-g warp: warps 4, 9, 14 sit on three different schedulers (all quadrant-0 warps share
-        // one -- ncu r2: 3 600 cycles per tile with every reducer on SMSP 0, the tensor pipe 21..42 % busy).
-        const int red_q = grp;
-        const int slot = q - (q > red_q ? 1 : 0);      // exchange slot of a non-reducing quadrant (ascending kw)
-        const int xdepth = ca.xdepth;
-        uint8_t* xg = xchg + grp * xdepth * kCmsXchg;
-        const int bar_full = 1 + grp * 4, bar_empty = 3 + grp * 4;
-        int it = 0;                        // rows this warp has handled (selects the exchange tile)
+        const int grp = (warp - 4) >> 2;
+        const int row0 = 3 * grp;
+        const int nr = grp < 2 ? 3 : 1;    // rows of this group
+        uint8_t* xg = xchg + grp * kCmsXchg;
+        const uint32_t xa = smem_u32(xg);
+        float* tr = reinterpret_cast<float*>(xg) + q * (32 * 33);   // this warp's transposition tile (channels-last epilogue)
+        const int bar_id = 1 + grp;        // named barrier of the group's quadrants 0..2 (96 threads)
         __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         int acc = 0;
         uint32_t acc_ph = 0;
@@ -1174,41 +1174,49 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (q == 3) {
                 release();                     // rows 96..127 of the accumulator carry nothing
             } else {
-                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + q;
-                for (int row = grp; row < 7; row += kCmsGroups) {
-                    uint32_t v[32];
-                    tmem_ld_32x32b_x32(tb + 34 * row, v);
-                    tmem_ld_wait_dep(v);
-                    if (row + kCmsGroups >= 7) release();    // this warp's last load of the tile has landed
-                    const int xbuf = it % xdepth;
-                    const bool reuse = it >= xdepth;     // the tile has been used before: wait for the reducer's hand-back
-                    ++it;
-                    const uint32_t xa = smem_u32(xg) + xbuf * kCmsXchg;
-                    float* tr = reinterpret_cast<float*>(xg + xbuf * kCmsXchg);
-                    if (q != red_q) {
-                        if (reuse) asm volatile("bar.sync %0, 96;" ::"r"(bar_empty + xbuf) : "memory");
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + q + 34 * row0;
+                const bool reducer = q < nr;   // this warp reduces (and stores) row row0 + q
+                float f[32];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xa + slot * 4096 + (j * 32 + lane) * 16), "r"(v[4 * j]),
-                                         "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
-                                         : "memory");
-                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_full + xbuf) : "memory");
-                        continue;
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t v[3][16];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i)
+                        if (i < nr) tmem_ld_32x32b_x16(tb + 34 * i + 16 * hf, v[i]);
+                    tmem_ld_wait();
+                    if (hf == 1) release();    // this warp's last load of the tile has landed
+                    // the exchange tile is free: every warp is done with its partial loads / transposition reads of the last use
+                    asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        if (i < nr && i != q) {
+                            const int sl = q - (q > i ? 1 : 0);   // source slot of this quadrant in row i's pair (ascending kw)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(xa + (((i * 2 + sl) * 4 + j) * 32 + lane) * 16), "r"(v[i][4 * j]),
+                                             "r"(v[i][4 * j + 1]), "r"(v[i][4 * j + 2]), "r"(v[i][4 * j + 3])
+                                             : "memory");
+                        }
                     }
-                    asm volatile("bar.sync %0, 96;" ::"r"(bar_full + xbuf) : "memory");
-                    float f[32];
+                    asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
+                    if (reducer) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t p1[4], p2[4];
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p1[0]), "=r"(p1[1]), "=r"(p1[2]), "=r"(p1[3]) : "r"(xa + (j * 32 + lane) * 16));
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p2[0]), "=r"(p2[1]), "=r"(p2[2]), "=r"(p2[3]) : "r"(xa + 4096 + (j * 32 + lane) * 16));
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t p1[4], p2[4];
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p1[0]), "=r"(p1[1]), "=r"(p1[2]), "=r"(p1[3]) : "r"(xa + (((q * 2 + 0) * 4 + j) * 32 + lane) * 16));
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(p2[0]), "=r"(p2[1]), "=r"(p2[2]), "=r"(p2[3]) : "r"(xa + (((q * 2 + 1) * 4 + j) * 32 + lane) * 16));
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            f[4 * j + k] = (__uint_as_float(v[4 * j + k]) + __uint_as_float(p1[k])) + __uint_as_float(p2[k]);
+                            for (int k = 0; k < 4; ++k) {
+                                // v[q] with a register index known at compile time: select by the warp-uniform q
+                                const uint32_t own = q == 0 ? v[0][4 * j + k] : (q == 1 ? v[1][4 * j + k] : v[2][4 * j + k]);
+                                f[16 * hf + 4 * j + k] = (__uint_as_float(own) + __uint_as_float(p1[k])) + __uint_as_float(p2[k]);
+                            }
+                        }
                     }
-                    const int h = h0 + row;
+                }
+                if (reducer) {
+                    const int h = h0 + row0 + q;
                     if constexpr (!NHWC) {
-                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_empty + xbuf) : "memory");   // the partials are in registers
                         // planar rows: lane = cout writes its 32 pixels of image row h
                         uint32_t pk[16];
 #pragma unroll
@@ -1234,9 +1242,14 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                                         *reinterpret_cast<uint4*>(yrow + 8 * g) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
                             }
                         }
-                    } else {
-                        // channels-last: transpose the [32 couts][32 pixels] block through shared memory so that a lane owns a pixel
-                        __syncwarp();   // every lane holds its partials: the exchange tile becomes the transposition tile
+                    }
+                }
+                if constexpr (NHWC) {
+                    // channels-last: transpose the [32 couts][32 pixels] block through this warp's tile so that a lane owns a pixel.
+                    // The tiles alias the exchange tile: wait until every warp of the group has read its partials.
+                    asm volatile("bar.sync %0, 96;" ::"r"(bar_id) : "memory");
+                    if (reducer) {
+                        const int h = h0 + row0 + q;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float y = fmaf(f[j], scale, bias);
@@ -1248,8 +1261,6 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                         float o[32];
 #pragma unroll
                         for (int c = 0; c < 32; ++c) o[c] = tr[c * 33 + lane];
-                        __syncwarp();
-                        asm volatile("bar.arrive %0, 96;" ::"r"(bar_empty + xbuf) : "memory");   // exchange / transposition tile handed back
                         if (h < a.Hout && w < a.Wout) {
                             const long long pixel = (static_cast<long long>(b) * a.Hout + h) * a.Wout + w;
                             auto add_res = [&](const __half* rp, int cp, int off, float gsc) {
@@ -1311,7 +1322,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
     // pixel-major pays off where the cout-major tile wastes >= half of its M rows and K is deep enough to amortise
     // the per-tile epilogue (B200 A/B, r1: L11 1.38 -> 1.23 ms, L12 0.77 -> 0.66 ms, but L13 with Cin = 32 0.50 -> 0.60 ms)
     // cout-major stacked tile (conv_cms_kernel): 3x3 layers with at most 32 couts whose A tiles stay resident next to two patch stages
-    const int cms_fixed = 1024 + 256 + kCmsGroups * kCmsXchg + 4096;   // with one exchange tile per group
+    const int cms_fixed = 1024 + 256 + kCmsGroups * kCmsXchg;
     const bool cms = p.cm_stack && p.ksz == 3 && p.Cout <= 32 && p.split_lo_off <= 0 &&
                      3 * ceil_div(p.Cin, kKC) * kCmsATile + 2 * kCmsPatchAlloc + cms_fixed <= kSmemMax;
     // stacked pixel-major tile (conv_pms_kernel): 3x3 layers whose three kw blocks fit one instruction (3 Np <= 256) and whose
@@ -1440,11 +1451,10 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cg.k.total_tiles = p.B * cg.k.tiles_h * cg.k.tiles_w;
         cg.k.st256 = (p.Wp_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) ? 1 : 0;
         const int a_all = 3 * nCC * kCmsATile;
-        cg.xdepth = (cms_fixed + kCmsGroups * kCmsXchg + a_all + 2 * kCmsPatchAlloc <= kSmemMax) ? 2 : 1;
-        const int cms_fixed_x = cms_fixed + (cg.xdepth - 1) * kCmsGroups * kCmsXchg;
-        cg.stages = (kSmemMax - cms_fixed_x - a_all) / kCmsPatchAlloc;
+        cg.xdepth = 1;
+        cg.stages = (kSmemMax - cms_fixed - a_all) / kCmsPatchAlloc;
         if (cg.stages > kCmsMaxStages) cg.stages = kCmsMaxStages;
-        const int smem_bytes = cms_fixed_x + a_all + cg.stages * kCmsPatchAlloc;
+        const int smem_bytes = cms_fixed + a_all + cg.stages * kCmsPatchAlloc;
         static bool attr_cms = false;
         if (!attr_cms) {
             MB_CUDA(cudaFuncSetAttribute(conv_cms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));

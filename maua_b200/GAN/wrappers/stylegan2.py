@@ -235,7 +235,8 @@ class _ResizeHandle:
     def _draw(mean, std, hw, gen, dev):
         """torch.normal(mean_c, std_c, size=(1, 1, h, w)) per channel (:238-247) -> [C, h, w]."""
         z = torch.randn(mean.numel(), hw[0], hw[1], generator=gen).to(dev)
-        return (mean.to(dev)[:, None, None] + std.to(dev)[:, None, None] * z).contiguous()
+        std = torch.nan_to_num(std.to(dev), nan=0.0)     # a 1 x 1 map has no spread (the reference's x.std() is NaN there)
+        return (mean.to(dev)[:, None, None] + std[:, None, None] * z).contiguous()
 
     @staticmethod
     def _resize(x, mode, hw, pads, value, layer_size):

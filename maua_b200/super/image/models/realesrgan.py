@@ -90,7 +90,11 @@ class RRDBNet(torch.nn.Module):
     def _sync_params(self, device):
         lib, net, changed, keep = _lib.load(), self._handle(), False, []
         for name, t in self.named_parameters():
-            key = (t.data_ptr(), t._version, str(t.device))
+            try:
+                version = t._version
+            except RuntimeError:     # inference-mode tensors carry no version counter
+                version = None
+            key = (t.data_ptr(), version, str(t.device))
             if self._uploaded.get(name) == key:
                 continue
             d = t.detach().to(device=device, dtype=torch.float32).contiguous()

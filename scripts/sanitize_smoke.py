@@ -29,7 +29,25 @@ for layout in ("0", "1"):
         y = ops.filtered_lrelu(x, fu.to(dev), fd.to(dev), torch.randn(C, device=dev), up=2, down=2, padding=[9, 8, 9, 8], clamp=256)
     print("filtered_lrelu layout", layout, tuple(y.shape))
 x = torch.randn(1, 40, 37, 41, device=dev)
-print("conv", tuple(ops.modulated_conv2d(x, torch.randn(17, 40, 3, 3, device=dev), torch.randn(1, 40, device=dev)).shape))
+for impl in (0, 8, 10, 11, 12):   # product dispatch, epilogue groups, 34-pixel patch, stacked pixel-major, stacked cout-major tiles
+    print("conv impl", impl, tuple(ops.modulated_conv2d(x, torch.randn(17, 40, 3, 3, device=dev), torch.randn(1, 40, device=dev), impl=impl).shape))
+# StyleGAN2 output-size hooks (mb_sg2_set_resize): bicubic stretch on conv1 of the 16^2 block, reflect padding on conv0 of the 32^2 block
+from collections import OrderedDict
+from maua_b200.GAN.wrappers.stylegan2 import StyleGAN2Synthesizer
+S = StyleGAN2Synthesizer.__new__(StyleGAN2Synthesizer)
+torch.nn.Module.__init__(S)
+S.G_synth, S._hook_handles, S._warp_hooks = net2, [], OrderedDict()
+S.layer_names = [f"bs.{c // 2}.conv{1 if r == 4 else c % 2}" for c, r in enumerate(sorted(net2.block_resolutions * 2))]
+for size, strategy, layer in (((96, 80), "stretch", 5), ((80, 72), "pad-reflect-out", 6)):
+    S.change_output_resolution(size, strategy, layer)
+    print("sg2 resize", strategy, tuple(S.forward(torch.randn(2, net2.num_ws, 512, device=dev)).shape))
+S.change_output_resolution((64, 64), "stretch", 0)
+# RRDBNet (csrc/rrdb.cu): channels-last epilogue of the stacked tiles, both conv variants
+from maua_b200.super.image.models.realesrgan import RRDBNet
+for cms in ("0", "1"):
+    os.environ["MB_RRDB_CMS"] = cms
+    up = RRDBNet(num_block=1)
+    print("rrdb cms", cms, tuple(up(torch.rand(1, 3, 23, 37, device=dev), out_fmt="u8").shape))
 f = ops.setup_filter().to(dev)
 print("upfirdn2d", tuple(ops.upfirdn2d(torch.randn(2, 3, 9, 13, device=dev), f, up=2, padding=(2, 1, 2, 1), gain=4).shape),
       tuple(ops.bias_act(torch.randn(2, 3, 9, 13, device=dev), torch.randn(3, device=dev), act="lrelu", clamp=1.0).shape))

@@ -44,6 +44,7 @@ CASES = [
     (0, (96, 80), "stretch"),            # the reference's PRE-hook: the constant input is resized
     (0, (96, 80), "pad-reflect-out"),
     (5, (48, 40), "stretch"),            # shrinking
+    (0, (32, 16), "stretch"),            # the constant input shrinks to 1 x 2: what sample.generate's default downscale does
 ]
 
 

@@ -99,8 +99,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void dbg_inc(volatile int* dbg, int idx) {
     if (dbg && blockIdx.x == 0) dbg[idx] = dbg[idx] + 1;
 }
+#ifdef MB_WAIT_PROFILE
+__shared__ int g_wait_prof[16];
+#define MB_WAIT_PROFILE_FLUSH(dbg)                                                                     \
+    do {                                                                                               \
+        __syncthreads();                                                                               \
+        if ((dbg) && blockIdx.x == 0 && threadIdx.x < 16) (dbg)[32 + (threadIdx.x & 7) + 16 * (threadIdx.x >> 3)] += g_wait_prof[threadIdx.x]; \
+    } while (0)
+#define MB_WAIT_PROFILE_INIT() do { for (int i_ = 0; i_ < 16; ++i_) g_wait_prof[i_] = 0; } while (0)
+#else
+#define MB_WAIT_PROFILE_FLUSH(dbg) do { } while (0)
+#define MB_WAIT_PROFILE_INIT() do { } while (0)
+#endif
 // Bounded spin: a broken pipeline traps instead of hanging the GPU box (a hang is a strike).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* dbg = nullptr, int tag = 0) {
+#ifdef MB_WAIT_PROFILE
+    // per-role wait accounting of CTA 0 in shared memory (flushed to the debug words by MB_WAIT_PROFILE_FLUSH at the end of a
+    // kernel: 32 + tag = cycles / 16, 48 + tag = waits); -DMB_WAIT_PROFILE builds only
+    const long long t0 = clock64();
+    {
+        uint32_t spins0 = 0;
+        while (!mbar_try_wait(bar, parity)) {
+            if (++spins0 > (1u << 20)) __trap();
+        }
+    }
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+        atomicAdd(&g_wait_prof[tag & 7], static_cast<int>((clock64() - t0) >> 4));
+        atomicAdd(&g_wait_prof[8 + (tag & 7)], 1);
+    }
+    return;
+#endif
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > (1u << 20)) {

@@ -31,7 +31,11 @@ constexpr int kMaxStages = 6;
 constexpr int kTileM = 128;         // couts per tile (UMMA M)
 constexpr int kTileN = 256;         // pixels per tile (UMMA N)
 constexpr int kKC = 64;             // channels per pipeline stage
+#ifdef MB_WAIT_PROFILE
+constexpr int kSmemMax = 232448 - 1024;   // the wait-profile build keeps 64 bytes of static shared memory
+#else
 constexpr int kSmemMax = 232448;    // 227 KB dynamic shared memory per CTA on sm_100
+#endif
 constexpr int kEpiPitch = 20;       // words per cout row of the shift-mode epilogue staging tile (16 data + 4 pad)
 constexpr int kEpiStageBytes = 4 * 32 * kEpiPitch * 4;  // one [32 couts][kEpiPitch] tile per epilogue warp
 
@@ -550,6 +554,7 @@ conv_pm_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant
             mbar_init(&tempty[s], 4);
         }
         mbar_init(wfull, 1);
+        MB_WAIT_PROFILE_INIT();
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -789,6 +794,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             mbar_init(&tempty[s], 8);
         }
         mbar_init(wfull, 1);
+        MB_WAIT_PROFILE_INIT();
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -997,6 +1003,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+    MB_WAIT_PROFILE_FLUSH(a.dbg);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1062,6 +1069,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             mbar_init(&tempty[s], 4 * kCmsGroups);
         }
         mbar_init(wfull, 1);
+        MB_WAIT_PROFILE_INIT();
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -1306,6 +1314,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+    MB_WAIT_PROFILE_FLUSH(a.dbg);
 }
 
 }  // namespace

@@ -755,8 +755,9 @@ struct PmsArgs {
     ConvTcArgs::NhwcOut o;   // o.y != nullptr: channels-last epilogue (bias, lrelu, residuals), see kernels.h
 };
 
+constexpr int kPmsGroups = 3;   // epilogue warps per TMEM lane quadrant
 template <int NH>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(128 + 128 * kPmsGroups, 1)
 conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, PmsArgs pa) {
     const KArgs& a = pa.k;
     extern __shared__ uint8_t smem_raw[];
@@ -791,7 +792,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 8);
+            mbar_init(&tempty[s], 4 * kPmsGroups);
         }
         mbar_init(wfull, 1);
         MB_WAIT_PROFILE_INIT();
@@ -875,12 +876,16 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
     } else if (warp >= 4) {
-        // Two warps per TMEM lane quadrant (warps 4..7 and 8..11; quadrant = warp % 4 = image row of the half tile) share a
-        // tile's (half, 16-cout block) units alternately: one warp per quadrant is issue-latency bound at ~1 200 instructions
-        // per tile (ncu r2: tensor pipe 23 % busy, the epilogue warps stalled on the SHFL -> FADD / PRMT scoreboard).
+        // Three warps per TMEM lane quadrant (warps 4..7, 8..11, 12..15; quadrant = warp % 4 = image row of the half tile) share a
+        // tile's (half, 16-cout block) units: one warp per quadrant is issue-latency bound at ~1 200 instructions per tile (ncu r2:
+        // tensor pipe 23 % busy, the epilogue warps stalled on the SHFL -> FADD / PRMT scoreboard); with two the epilogue warps are
+        // still 94 % busy and the MMA warp waits 630..1 400 cycles per tile for an accumulator (wait profile).  The assignment
+        // rotates from tile to tile (unit u of the CTA's i-th tile goes to warp (u + i) mod 3), so the warps with two units of one
+        // tile are not the ones with two units of the next.
         const int q = warp & 3;
         const int eg = (warp - 4) >> 2;
-        float2* tab = sc_tab + q * 128;   // shared by the two warps of a quadrant; refreshed by group 0 under a named barrier
+        float2* tab = sc_tab + q * 128;   // shared by the warps of a quadrant; refreshed by group 0 under a named barrier
+        int ti = 0;                        // tiles this CTA has handled
         __half2 amax = __floats2half2_rn(0.0f, 0.0f);
         int acc = 0;
         uint32_t acc_ph = 0;
@@ -904,13 +909,13 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (wt >= a.tiles_w) { wt -= a.tiles_w; ++ht; }
             if (ht >= a.tiles_h) { ht -= a.tiles_h; ++b; }
             if (b != tab_b) {  // uniform over both warps of the quadrant
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");   // the other warp is done with the old table
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kPmsGroups) : "memory");   // the other warps are done with the old table
                 if (eg == 0)
                     for (int i = lane; i < Np; i += 32) {
                         const bool ok = i < a.Cout;
                         tab[i] = make_float2((ok && a.d) ? a.d[b * a.Cout + i] : (ok ? 1.0f : 0.0f), (ok && a.bias) ? a.bias[i] : 0.0f);
                     }
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + q), "n"(32 * kPmsGroups) : "memory");
                 tab_b = b;
             }
             const int w = wt * 30 + lane;
@@ -919,7 +924,8 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NH * Nst;
-            int hf = 0, cb = eg;   // unit u = hf * nblk + cb, u = eg, eg + 2, ...
+            int hf = 0, cb = (eg + 2 * ti) % kPmsGroups;   // unit u = hf * nblk + cb; this warp takes u = (eg - i) mod 3, + 3, ...
+            ++ti;
             while (cb >= nblk) { cb -= nblk; ++hf; }
 #pragma unroll 1
             while (hf < NH) {
@@ -984,7 +990,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                                 if (k < nco) dst[k] = __float2half_rn(v[k]);
                         }
                     }
-                    cb += 2;
+                    cb += kPmsGroups;
                     while (cb >= nblk) { cb -= nblk; ++hf; }
                     continue;
                 }
@@ -1001,7 +1007,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     if (ok && 2 * k + 1 < nco) *(yp + a.cs) = __high2half(mine);
                     yp += 2 * a.cs;
                 }
-                cb += 2;
+                cb += kPmsGroups;
                 while (cb >= nblk) { cb -= nblk; ++hf; }
             }
             tc_fence_before();
@@ -1512,8 +1518,8 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         }
         int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
         if (grid < 1) grid = 1;
-        if (pms_nh == 2) conv_pms_kernel<2><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
-        else conv_pms_kernel<1><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        if (pms_nh == 2) conv_pms_kernel<2><<<grid, 128 + 128 * kPmsGroups, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        else conv_pms_kernel<1><<<grid, 128 + 128 * kPmsGroups, smem_bytes, stream>>>(tm_w, tm_x, pa);
         MB_CUDA(cudaGetLastError());
         return MB_OK;
     }

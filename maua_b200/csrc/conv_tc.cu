@@ -755,8 +755,9 @@ struct PmsArgs {
     ConvTcArgs::NhwcOut o;   // o.y != nullptr: channels-last epilogue (bias, lrelu, residuals), see kernels.h
 };
 
-constexpr int kPmsGroups = 3;   // epilogue warps per TMEM lane quadrant
-template <int NH>
+// kPmsGroups = epilogue warps per TMEM lane quadrant: 3 for the planar epilogue (StyleGAN3's narrow layers: L13 0.77 -> 0.69 ms),
+// 2 for the channels-last one (RRDBNet measured 54.8 ms per 4 frames with two, 56.8 with three)
+template <int NH, int kPmsGroups>
 __global__ void __launch_bounds__(128 + 128 * kPmsGroups, 1)
 conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x, PmsArgs pa) {
     const KArgs& a = pa.k;
@@ -924,7 +925,7 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * NH * Nst;
-            int hf = 0, cb = (eg + 2 * ti) % kPmsGroups;   // unit u = hf * nblk + cb; this warp takes u = (eg - i) mod 3, + 3, ...
+            int hf = 0, cb = (eg + (kPmsGroups - 1) * ti) % kPmsGroups;   // unit u = hf * nblk + cb; this warp takes u = (eg - i) mod groups, + groups, ...
             ++ti;
             while (cb >= nblk) { cb -= nblk; ++hf; }
 #pragma unroll 1
@@ -1512,14 +1513,21 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         const int smem_bytes = fixed + w_all_pm + pa.stages * patch;
         static bool attr_pms = false;
         if (!attr_pms) {
-            MB_CUDA(cudaFuncSetAttribute(conv_pms_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-            MB_CUDA(cudaFuncSetAttribute(conv_pms_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute((conv_pms_kernel<1, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute((conv_pms_kernel<2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute((conv_pms_kernel<1, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+            MB_CUDA(cudaFuncSetAttribute((conv_pms_kernel<2, 3>), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
             attr_pms = true;
         }
         int grid = pa.k.total_tiles < p.num_sms ? pa.k.total_tiles : p.num_sms;
         if (grid < 1) grid = 1;
-        if (pms_nh == 2) conv_pms_kernel<2><<<grid, 128 + 128 * kPmsGroups, smem_bytes, stream>>>(tm_w, tm_x, pa);
-        else conv_pms_kernel<1><<<grid, 128 + 128 * kPmsGroups, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        if (p.nhwc.y) {
+            if (pms_nh == 2) conv_pms_kernel<2, 2><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
+            else conv_pms_kernel<1, 2><<<grid, 384, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        } else {
+            if (pms_nh == 2) conv_pms_kernel<2, 3><<<grid, 512, smem_bytes, stream>>>(tm_w, tm_x, pa);
+            else conv_pms_kernel<1, 3><<<grid, 512, smem_bytes, stream>>>(tm_w, tm_x, pa);
+        }
         MB_CUDA(cudaGetLastError());
         return MB_OK;
     }

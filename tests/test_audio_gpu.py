@@ -26,9 +26,10 @@ def test_against_reference_golden_vectors(cuda):
     assert float((perc - ref).abs().max()) < 1e-4 * float(ref.abs().max()) + 1e-6
 
 
-@pytest.mark.parametrize("fps,dur", [(24, 30.0), (60, 12.0)])
+@pytest.mark.parametrize("fps,dur", [(24, 30.0), (60, 12.0), (60, 180.0)])
 def test_config_sized_sweep_matches_oracle(cuda, fps, dur):
-    """BASELINE.json configs[1] audio (30 s @ 24 fps -> 720 frames) and a 60 fps variant, tremolo sweep."""
+    """BASELINE.json configs[1] audio (30 s @ 24 fps -> 720 frames), a 60 fps variant, and configs[2]'s full length
+    (180 s @ 60 fps = 11 059 200 samples -> 10 800 frames), tremolo sweep."""
     from maua_b200.audiovisual import audioreactive as ar
     from maua_b200.workload import sine_sweep
 

@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) torgb_out_kernel(ToRgbArgs a) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc[o][i] = 0.0f;
         const __half* xp = a.x + static_cast<long long>(b) * a.Cin * plane + static_cast<long long>(h) * a.Wp + w0;
-#pragma unroll 4
+#pragma unroll 8
         for (int ci = 0; ci < a.Cin; ++ci) {
             const uint4 raw = *reinterpret_cast<const uint4*>(xp + ci * plane);
             const __half2* hp = reinterpret_cast<const __half2*>(&raw);

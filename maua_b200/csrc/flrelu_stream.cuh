@@ -41,7 +41,11 @@ struct SC {
     // One TMA box feeds one output block: 16 input rows (two S1 blocks) at up=2, 8 rows at up=4.
     static constexpr int BOXROWS = (UP == 2) ? 16 : 8;
     static constexpr int BOXBYTES = BOXROWS * kXP * 2;
-    static constexpr int NRING = (UP == 2) ? 3 : 4;  // boxes per warp: the fetch runs two / three output blocks ahead
+#ifndef MB_FL_NRING2
+#define MB_FL_NRING2 3
+#define MB_FL_NRING4 4
+#endif
+    static constexpr int NRING = (UP == 2) ? MB_FL_NRING2 : MB_FL_NRING4;  // boxes per warp: the fetch runs two / three output blocks ahead
 #ifndef MB_FL_NSB
 #define MB_FL_NSB 6
 #define MB_FL_LAG 3

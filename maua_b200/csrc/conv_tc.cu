@@ -1031,19 +1031,23 @@ conv_pms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
 // pixels are the streamed B operand again (0.5 cycles per pixel and K = 16 step) and the M = 128 rows that a 32-cout layer
 // wastes in the plain cout-major tile carry the kw taps instead:
 //     D[(kw, cout), n] += A[(kw, cout), (kh, cin)] * B[(kh, cin), n],     row = 32 kw + cout  (rows 96..127 unused),
-// n = r * 34 + col over a 34-pixel-wide patch of 9 image rows (one TMA load per 64-channel chunk; tap kh = a B window that starts
-// kh * 34 pixel rows further on), N = 240 = 7 image rows per instruction, K = 3 Cin.  One MMA does the work of three of the plain
+// n = r * 34 + col over a 34-pixel-wide patch of 5 image rows (one TMA load per 64-channel chunk; tap kh = a B window that starts
+// kh * 34 pixel rows further on), N = 104 = 3 image rows per instruction, K = 3 Cin.  One MMA does the work of three of the plain
 // tile.  The kw shift is a TMEM COLUMN offset: the warp of lane quadrant kw reads row r at columns [34 r + kw, 34 r + kw + 32),
 //     y[cout, (r, col)] = D[(0, cout), 34 r + col] + D[(1, cout), 34 r + col + 1] + D[(2, cout), 34 r + col + 2],
-// and the three partials of a cout sit in three different quadrants, i.e. three different warps: quadrants 1 and 2 hand theirs to
-// quadrant 0 through a double-buffered shared-memory exchange (8 x STS.128 / LDS.128 per lane and row, one named barrier per row).
-// Three epilogue groups (warps 4..15) take the tile's seven rows in turn.  Weights resident: the A tile of (chunk, kh) is three
-// 32-row TMA boxes of the ordinary packed matrix (one per kw) landing back to back.  NHWC = channels-last epilogue (bias, lrelu,
-// residuals: csrc/rrdb.cu) through a per-warp transposition tile, else planar rows (d, bias, max |y|) like the other tiles.
-constexpr int kCmsPatchAlloc = 40960, kCmsPatchTx = 9 * 34 * 128, kCmsATile = 96 * 128, kCmsGroups = 3;
+// and the three partials of a cout sit in three different quadrants, i.e. three different warps: they meet through a shared-memory
+// exchange (each warp reduces one of the tile's three rows, see the epilogue).  Four accumulators in TMEM, one epilogue group of
+// four warps per tile, three groups: three tiles drain while the tensor core fills the fourth.  Weights resident: the A tile of
+// (chunk, kh) is three 32-row TMA boxes of the ordinary packed matrix (one per kw) landing back to back.  NHWC = channels-last
+// epilogue (bias, lrelu, residuals: csrc/rrdb.cu) through a per-warp transposition tile, else planar rows (d, bias, max |y|).
+// Measured (B200, 16 frames): bit-correct, L13 0.86 ms and L12 0.99 ms against 0.70 / 0.85 ms for the stacked pixel-major tile,
+// RRDBNet 68.6 against 57.5 ms per 4 frames: a group still needs ~4 000 cycles per 3-row tile.  Off by default.
+constexpr int kCmsRows = 3;                     // image rows per tile: N = 3 * 34 + 2 = 104 accumulator columns, four accumulators in TMEM
+constexpr int kCmsN = 104, kCmsAcc = 4, kCmsAccStride = 128;
+constexpr int kCmsPatchAlloc = 22528, kCmsPatchTx = (kCmsRows + 2) * 34 * 128, kCmsATile = 96 * 128, kCmsGroups = 3;
 constexpr int kCmsXchg = 3 * 32 * 33 * 4;       // per group: three rows x two source slots x 16 columns x 32 lanes of partial sums (12 KB);
                                                 // the channels-last epilogue reuses it as three [32 couts][33] transposition tiles
-constexpr int kCmsMaxStages = 4;
+constexpr int kCmsMaxStages = 6;
 
 struct CmsArgs {
     KArgs k;
@@ -1067,10 +1071,10 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(xchg + kCmsGroups * kCmsXchg);
     uint64_t* full = bars;                          // [kCmsMaxStages]
     uint64_t* empty = bars + kCmsMaxStages;         // [kCmsMaxStages]
-    uint64_t* tfull = bars + 2 * kCmsMaxStages;     // [2]
-    uint64_t* tempty = bars + 2 * kCmsMaxStages + 2;  // [2]
-    uint64_t* wfull = bars + 2 * kCmsMaxStages + 4;   // [1]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCmsMaxStages + 5);
+    uint64_t* tfull = bars + 2 * kCmsMaxStages;                  // [kCmsAcc]
+    uint64_t* tempty = bars + 2 * kCmsMaxStages + kCmsAcc;       // [kCmsAcc]
+    uint64_t* wfull = bars + 2 * kCmsMaxStages + 2 * kCmsAcc;    // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kCmsMaxStages + 2 * kCmsAcc + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -1083,9 +1087,9 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < kCmsAcc; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4 * kCmsGroups);
+            mbar_init(&tempty[s], 4);      // the four warps of the group that owns the tile
         }
         mbar_init(wfull, 1);
         MB_WAIT_PROFILE_INIT();
@@ -1121,7 +1125,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                 mbar_wait(&empty[s], ph ^ 1, a.dbg, 1);
                 if (leader) {
                     mbar_arrive_expect_tx(&full[s], kCmsPatchTx);
-                    tma_load_4d(stages + s * kCmsPatchAlloc, &tmap_x, &full[s], cc * kKC, wt * 32 - pad, ht * 7 - pad, b);
+                    tma_load_4d(stages + s * kCmsPatchAlloc, &tmap_x, &full[s], cc * kKC, wt * 32 - pad, ht * kCmsRows - pad, b);
                 }
                 __syncwarp();
                 if (++s == nst) { s = 0; ph ^= 1; }
@@ -1129,7 +1133,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         }
     } else if (warp == 1) {
         const bool leader = elect_one();
-        const uint32_t idesc = make_idesc_f16(128, 240, 0, 0);
+        const uint32_t idesc = make_idesc_f16(128, kCmsN, 0, 0);
         int s = 0;
         uint32_t ph = 0;
         int acc = 0;
@@ -1138,7 +1142,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
             mbar_wait(&tempty[acc], acc_ph ^ 1, a.dbg, 2);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * 256;
+            const uint32_t d_tmem = tmem_base + acc * kCmsAccStride;
             uint32_t accumulate = 0;
             for (int cc = 0; cc < a.nCC; ++cc) {
                 int nk16 = (a.Cin - cc * kKC + 15) / 16;
@@ -1163,33 +1167,47 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             }
             if (leader) umma_commit(&tfull[acc]);
             __syncwarp();
-            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+            if (++acc == kCmsAcc) { acc = 0; acc_ph ^= 1; }
         }
     } else if (warp >= 4) {
-        // Epilogue.  Group g (warps 4 + 4g ..) owns image rows 3g, 3g + 1, 3g + 2 of the tile (group 2: row 6 only); inside a group
-        // the quadrant-q warp REDUCES row 3g + q: all three warps hold their kw partials of all three rows, hand the two rows they
-        // do not reduce to the shared-memory exchange and take the other two quadrants' partials of their own row back, in two
-        // halves of 16 columns (tcgen05.ld x16 x 3 rows).  So every warp converts and stores one row, three warps per scheduler share
-        // the work (the first build had ONE reducer warp per group: 3 150 cycles per tile whatever the layer's K, ncu r2).
+        // Epilogue.  A tile is three image rows and belongs to ONE group of four warps (the CTA's i-th tile to group i mod 3, in
+        // accumulator i mod 4), so three tiles drain concurrently while the tensor core fills a fourth: the first build shared every
+        // tile between the groups and had two accumulators in flight -- each epilogue warp was busy ~2 500 serial cycles per tile
+        // and the MMA warp waited 1 400..1 900 cycles per tile for an accumulator (wait profile).  Inside the group the quadrant-q
+        // warp REDUCES row q: all three warps hold their kw partials of the three rows, hand the two rows they do not reduce to
+        // the shared-memory exchange and take the other quadrants' partials of their own row back, in two halves of 16 columns
+        // (tcgen05.ld x16 x 3 rows); every warp converts and stores one row.
         const int q = warp & 3;            // TMEM lane quadrant = kw of this warp's partial sums
         const int grp = (warp - 4) >> 2;
-        const int row0 = 3 * grp;
-        const int nr = grp < 2 ? 3 : 1;    // rows of this group
+        constexpr int row0 = 0, nr = kCmsRows;
         uint8_t* xg = xchg + grp * kCmsXchg;
         const uint32_t xa = smem_u32(xg);
         float* tr = reinterpret_cast<float*>(xg) + q * (32 * 33);   // this warp's transposition tile (channels-last epilogue)
         const int bar_id = 1 + grp;        // named barrier of the group's quadrants 0..2 (96 threads)
         __half2 amax = __floats2half2_rn(0.0f, 0.0f);
-        int acc = 0;
-        uint32_t acc_ph = 0;
         const bool co_ok = lane < a.Cout;
         const float bias = (co_ok && a.bias) ? a.bias[lane] : 0.0f;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-            int r = t;
-            const int wt = r % a.tiles_w; r /= a.tiles_w;
-            const int ht = r % a.tiles_h; r /= a.tiles_h;
-            const int b = r;
-            const int h0 = ht * 7, w0 = wt * 32;
+        // division-free walk over this group's tiles: t = blockIdx.x + (grp + 3 j) * gridDim.x
+        int wt, ht, b;
+        {
+            long long r = static_cast<long long>(blockIdx.x) + static_cast<long long>(grp) * gridDim.x;
+            wt = static_cast<int>(r % a.tiles_w); r /= a.tiles_w;
+            ht = static_cast<int>(r % a.tiles_h); b = static_cast<int>(r / a.tiles_h);
+        }
+        int dwt, dht, db;
+        {
+            long long r = 3LL * gridDim.x;
+            dwt = static_cast<int>(r % a.tiles_w); r /= a.tiles_w;
+            dht = static_cast<int>(r % a.tiles_h); db = static_cast<int>(r / a.tiles_h);
+        }
+        int li = grp;                      // index of the tile among this CTA's tiles
+        for (long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(grp) * gridDim.x; t < a.total_tiles;
+             t += 3LL * gridDim.x, li += 3, wt += dwt, ht += dht, b += db) {
+            if (wt >= a.tiles_w) { wt -= a.tiles_w; ++ht; }
+            if (ht >= a.tiles_h) { ht -= a.tiles_h; ++b; }
+            const int acc = li & (kCmsAcc - 1);
+            const uint32_t acc_ph = (li >> 2) & 1;
+            const int h0 = ht * kCmsRows, w0 = wt * 32;
             const float scale = (co_ok && a.d) ? a.d[b * a.Cout + lane] : (co_ok ? 1.0f : 0.0f);
             mbar_wait(&tfull[acc], acc_ph, a.dbg, 4);
             tc_fence_after();
@@ -1201,7 +1219,7 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
             if (q == 3) {
                 release();                     // rows 96..127 of the accumulator carry nothing
             } else {
-                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256 + q + 34 * row0;
+                const uint32_t tb = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kCmsAccStride + q + 34 * row0;
                 const bool reducer = q < nr;   // this warp reduces (and stores) row row0 + q
                 float f[32];
 #pragma unroll
@@ -1325,7 +1343,6 @@ conv_cms_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constan
                     }
                 }
             }
-            if (++acc == 2) { acc = 0; acc_ph ^= 1; }
         }
         if constexpr (!NHWC) publish_abs(a.absmax, amax);
     }
@@ -1421,7 +1438,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
                               static_cast<cuuint64_t>(p.Hin), static_cast<cuuint64_t>(p.B)};
         cuuint64_t strides[3] = {cp * 2, cp * 2 * p.Win, cp * 2 * p.Win * p.Hin};
         cuuint32_t box[4] = {kKC, static_cast<cuuint32_t>((shift2 || cms) ? 34 : tw),
-                             static_cast<cuuint32_t>(pms_nh ? 4 * pms_nh + 2 : ((shift2 || cms) ? 9 : th + halo)), 1};
+                             static_cast<cuuint32_t>(pms_nh ? 4 * pms_nh + 2 : (cms ? kCmsRows + 2 : (shift2 ? 9 : th + halo))), 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         CUresult r = enc(&tm_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(p.x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1475,7 +1492,7 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cg.o = p.nhwc;
         cg.k.tiles_m = 1;
         cg.k.tiles_w = ceil_div(a.Wout, 32);
-        cg.k.tiles_h = ceil_div(a.Hout, 7);
+        cg.k.tiles_h = ceil_div(a.Hout, kCmsRows);
         cg.k.total_tiles = p.B * cg.k.tiles_h * cg.k.tiles_w;
         cg.k.st256 = (p.Wp_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) ? 1 : 0;
         const int a_all = 3 * nCC * kCmsATile;

@@ -77,6 +77,16 @@ __device__ __forceinline__ uint32_t lrelu2(uint32_t v, uint32_t s) {
     h = __hmax2(h, __hmul2(h, *reinterpret_cast<__half2*>(&s)));
     return *reinterpret_cast<uint32_t*>(&h);
 }
+// leaky relu as ONE instruction (HFMA2 with an |x| operand): lrelu(t) = a * (|t| + k t) with k = (1 + slope) / (1 - slope) and
+// a = (1 - slope) / 2; the factor a rides in the fp32 output scale behind the (linear) down filters.  For slope = 0.2, k = 1.5 is
+// exact in fp16: negative inputs become 0.5 t (exact), positive ones 2.5 t (one fp16 rounding), and the realised slope is exactly
+// 0.2 (the two-instruction form multiplies by fp16(0.2) = 0.19995).  In general a = 1 / (k + 1) of the ROUNDED k keeps the
+// positive gain at exactly one.
+__device__ __forceinline__ uint32_t lrelu2_abs(uint32_t v, uint32_t k) {
+    __half2 h = *reinterpret_cast<__half2*>(&v);
+    h = __hfma2(h, *reinterpret_cast<__half2*>(&k), __habs2(h));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 // first input sample an axis needs for output o0: ceil((2*o0 - pad) / UP) - e   (UP is 2 or 4: shifts)
 template <int UP>
 __device__ __forceinline__ int first_in(int o0, int pad, int e) {

@@ -387,8 +387,11 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
         for (int n8 = 0; n8 < kJB; ++n8) {
             uint32_t t2[2];
             mma16816_h(t2, A, Pa[n8 >> 1][n8 & 1], Pb[n8 >> 1][n8 & 1]);
-            if constexpr (decltype(FASTc)::value) {
-                P2[n8][0] = lrelu2(t2[0], LC.sl2);
+            if constexpr (decltype(FASTc)::value && !RAD) {
+                P2[n8][0] = lrelu2_abs(t2[0], LC.sl2);   // sl2 holds k = (1 + slope) / (1 - slope) on this path
+                P2[n8][1] = lrelu2_abs(t2[1], LC.sl2);
+            } else if constexpr (decltype(FASTc)::value) {
+                P2[n8][0] = lrelu2(t2[0], LC.sl2);       // radial layers (StyleGAN3-R sits closer to the pixel tolerance): exact positive branch
                 P2[n8][1] = lrelu2(t2[1], LC.sl2);
             } else {
                 P2[n8][0] = lrelu_clamp2(t2[0], LC.sl2, LC.cl2);
@@ -492,6 +495,13 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     };
 
     const bool no_clamp = p.in_absmax != nullptr && __uint_as_float(*p.in_absmax) <= p.safe_abs;   // uniform over the grid
+    float act_gain = 1.0f;
+    if (no_clamp && !RAD) {
+        // clamp-free activation as one HFMA2 (lrelu2_abs): its constant replaces the slope, its factor joins the output scale
+        const __half k16 = __float2half_rn((1.0f + p.slope) / (1.0f - p.slope));
+        LC.sl2 = pack2(__half2float(k16), __half2float(k16));
+        act_gain = 1.0f / (__half2float(k16) + 1.0f);
+    }
     int nitem = 0;
     for (int item = blockIdx.x; item < p.n_total; item += G, ++nitem) {
         int c, oy0;
@@ -501,7 +511,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
             valid = warp_share(p, it, warp, c, oy0);
             Rit = it.R;
             blk = 0;
-            oscale = (valid && p.scale ? p.scale[it.b * p.C + c] : 1.0f) * p.out_gain;
+            oscale = (valid && p.scale ? p.scale[it.b * p.C + c] : 1.0f) * p.out_gain * act_gain;
             if constexpr (PLANAR) {
                 yp = p.y + ((static_cast<long long>(it.b) * p.C + c) * p.Hout + oy0) * p.Wp_out + it.tx * kOT;
                 rows_left = p.Hout - oy0;

@@ -1052,7 +1052,6 @@ constexpr int kCmsMaxStages = 6;
 struct CmsArgs {
     KArgs k;
     int stages;
-    int xdepth;   // exchange tiles per group (2 where shared memory allows: quadrants 1 / 2 then run a row ahead of the reducer)
     ConvTcArgs::NhwcOut o;
 };
 
@@ -1496,7 +1495,6 @@ int conv_tc_launch(const ConvTcArgs& p, cudaStream_t stream) {
         cg.k.total_tiles = p.B * cg.k.tiles_h * cg.k.tiles_w;
         cg.k.st256 = (p.Wp_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0) ? 1 : 0;
         const int a_all = 3 * nCC * kCmsATile;
-        cg.xdepth = 1;
         cg.stages = (kSmemMax - cms_fixed - a_all) / kCmsPatchAlloc;
         if (cg.stages > kCmsMaxStages) cg.stages = kCmsMaxStages;
         const int smem_bytes = cms_fixed + a_all + cg.stages * kCmsPatchAlloc;

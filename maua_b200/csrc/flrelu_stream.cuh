@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(kCG * 32, 1) flrelu_stream_kernel(const __grid
     // P1 slots (up=4) and the accumulator set (radial).  Returns true after the last strip of the segment.
     auto block_iter = [&](auto PARc, auto FASTc, int i) -> bool {
         constexpr int PAR = decltype(PARc)::value;
-        constexpr int CUR = RAD ? PAR : 0, PRV = RAD ? (PAR ^ 1) : 0;
+        [[maybe_unused]] constexpr int CUR = RAD ? PAR : 0, PRV = RAD ? (PAR ^ 1) : 0;
         uint32_t P2[kJB][2];
         // even strip 2i
         if constexpr (UP == 2) {
